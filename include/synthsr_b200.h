@@ -1,0 +1,140 @@
+/* libsynthsr_b200 -- C ABI of the B200-native SynthSR training hot path.
+ *
+ * The reference (BBillot/SynthSR) has no FFI: its hot path is a Keras graph.  This header is the drop-in
+ * boundary a maintainer binds from Python (ctypes); every entry point names the reference
+ * code it replaces (file:line relative to the reference repository).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no torch types.  All data pointers are DEVICE pointers unless noted.
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates nothing and keeps no state
+ *    other than cached TMA descriptors; scratch buffers are provided by the caller.
+ *  - return value: 0 on success, <0 on error (-1 bad argument, -2 CUDA error, -3 unsupported); the message is in
+ *    ssr_last_error() (thread local).
+ *  - volumes are [B][d0][d1][d2][C] float32 (channels contiguous), labels int32 [B][d0][d1][d2]; (d0,d1,d2) are the
+ *    reference's three spatial axes in order, d2 contiguous.
+ *  - *_stride/*_off pairs address a channel slice of a wider channels-last tensor (element (v,c) at
+ *    v*stride + off + c); stride <= 0 means "dense".
+ */
+#ifndef SYNTHSR_B200_H_
+#define SYNTHSR_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- library ---------------------------------- */
+const char* ssr_last_error(void);
+unsigned long long ssr_launch_count(void);     /* kernels launched by this library since load */
+int ssr_abi_version(void);
+int ssr_device_arch(void);                     /* 100 on B200 */
+
+/* ---------------------------------------------------------------- generator -------------------------------- */
+/* nrn_layers.Resize (ext/neuron/layers.py:361-394 -> ext/neuron/utils.py:127-154), linear or nearest, C<=3. */
+int ssr_resize(const float* src, float* dst, int B, int s0, int s1, int s2, int d0, int d1, int d2, int C,
+               int nearest, int dst_stride, int dst_off, void* stream);
+
+/* nrn_layers.VecInt scaling-and-squaring (ext/neuron/layers.py:241-272 -> utils.integrate_vec :351-369).
+ * vec [B][n0][n1][n2][3] in/out, tmp same size. */
+int ssr_svf_integrate(float* vec, float* tmp, int B, int n0, int n1, int n2, int nb_steps, void* stream);
+
+/* Fused PadAroundCentre + Resize(field) + SpatialTransformer('nearest') + RandomCrop + RandomFlip(+L/R swap):
+ * ext/lab2im/layers.py:196-211, 252-270, 391-427, 1754; ext/neuron/utils.py:222-286, 112-122.  Bit exact.
+ * labels [B][n0-2p0][n1-2p1][n2-2p2]; aff [B][4][4] or NULL; field_half [B][h0][h1][h2][3] (integrated SVF) or
+ * NULL (then h*=0); crop_idx [B][3] or NULL; flip [B] bytes or NULL; swap_lut [lut_len] or NULL;
+ * out [B][c0][c1][c2]. */
+int ssr_deform_labels_nearest(const int* labels, int* out, const float* aff, const float* field_half, int B, int n0,
+                              int n1, int n2, int p0, int p1, int p2, int h0, int h1, int h2, const int* crop_idx,
+                              int c0, int c1, int c2, const unsigned char* flip, const int* swap_lut, int lut_len,
+                              void* stream);
+
+/* Same transform with SpatialTransformer('linear') on a single-channel float image (real-image target,
+ * registration-error simulation: SynthSR/labels_to_image_model.py:128-134, 202-208, 231-238). */
+int ssr_warp_linear(const float* image, float* out, const float* aff, const float* field_half, int B, int n0, int n1,
+                    int n2, int p0, int p1, int p2, int h0, int h1, int h2, const int* crop_idx, int c0, int c1, int c2,
+                    const unsigned char* flip, void* stream);
+
+/* tf.random.normal replacement: Philox4x32-10 + Box-Muller, n standard normals. */
+int ssr_philox_normal(float* out, long long n, unsigned long long seed, unsigned long long stream_id, void* stream);
+
+/* Fused SampleConditionalGMM + BiasFieldCorruption + clip + per-item min/max for ONE synthetic channel:
+ * ext/lab2im/layers.py:480-498, 1067-1097, 1214-1215, 1230-1231.
+ * lut_mean/lut_std [B][lut_len] (scatter of means/stds at generation_labels); noise [B][V] standard normals or NULL
+ * (then generated on the fly from seed/stream_id); bias_small [B][b0][b1][b2] (N(0,std) draws) or NULL;
+ * minmax [B][2] uint32 (order-preserving encoding, consumed by ssr_blur3d). */
+int ssr_gmm_bias_minmax(const int* labels, const float* lut_mean, const float* lut_std, int lut_len,
+                        const float* noise, unsigned long long seed, unsigned long long stream_id,
+                        const float* bias_small, int b0, int b1, int b2, int apply_bias, float clip_max, float* out,
+                        unsigned int* minmax, int B, int n0, int n1, int n2, void* stream);
+
+/* per-item min/max of a float volume (IntensityAugmentation(normalise=True) on a real image). */
+int ssr_minmax(const float* x, unsigned int* minmax, int B, long long nvox, void* stream);
+
+/* GaussianBlur / tf.nn.conv3d(...,'SAME') with a dense k0 x k1 x k2 kernel (ext/lab2im/layers.py:732-767), with
+ * the min-max normalisation and gamma augmentation of IntensityAugmentation (layers.py:1235-1242) optionally fused
+ * on the loads (minmax / gamma_exp[B] non-NULL).  Single channel in, single channel (slice) out. */
+int ssr_blur3d(const float* src, float* dst, const float* kern, int k0, int k1, int k2, const unsigned int* minmax,
+               const float* gamma_exp, int B, int n0, int n1, int n2, int src_stride, int src_off, int dst_stride,
+               int dst_off, void* stream);
+
+int ssr_copy_strided(const float* src, float* dst, long long n, int src_stride, int src_off, int dst_stride,
+                     int dst_off, void* stream);
+
+/* reliability map (ext/lab2im/edit_tensors.py:313-333): outer product of per-axis factors (double, device) or 1. */
+int ssr_fill_outer3(float* dst, const double* f0, const double* f1, const double* f2, int B, int n0, int n1, int n2,
+                    int dst_stride, int dst_off, void* stream);
+
+/* ---------------------------------------------------------------- U-Net: exact fp32 convolutions ------------ */
+/* KL.Conv3D(Cout, k, padding='same', activation) on the logical concat [x1, x2] (ext/neuron/models.py:316,444). */
+int ssr_conv3d_fwd_ref(const float* x1, int C1, const float* x2, int C2, const float* w, const float* bias, float* y,
+                       int B, int d0, int d1, int d2, int Cout, int k, int act, void* stream);
+int ssr_conv3d_dgrad_ref(const float* dy, const float* w, float* wd_scratch, float* dx, int B, int d0, int d1, int d2,
+                         int Cin, int Cout, int k, void* stream);
+int ssr_conv3d_wgrad_ref(const float* x1, int C1, const float* x2, int C2, const float* dy, float* dw, float* db, int B,
+                         int d0, int d1, int d2, int Cout, int k, void* stream);
+
+/* ---------------------------------------------------------------- U-Net: tcgen05 (TF32) convolutions -------- */
+/* Same contract as the *_ref functions for k == 3, computed on the 5th-generation tensor cores
+ * (tcgen05.mma.kind::tf32, TMA-staged shared-memory tiles, TMEM accumulators).  See conv_tc.cu. */
+int ssr_conv3d_pack_weights(const float* w, float* wp, int Cin1, int Cin2, int Cout, int mode, void* stream);
+long long ssr_conv3d_packed_size(int Cin1, int Cin2, int Cout, int mode);
+int ssr_conv3d_fwd_tc(const float* x1, int C1, const float* x2, int C2, const float* wp, const float* bias, float* y,
+                      int B, int d0, int d1, int d2, int Cout, int act, void* stream);
+int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const float* dy, float* dw, float* db,
+                        float* scratch, long long scratch_bytes, int B, int d0, int d1, int d2, int Cout,
+                        void* stream);
+long long ssr_conv3d_wgrad_scratch_bytes(int C1, int C2, int Cout, int B, int d0, int d1, int d2);
+int ssr_tc_selftest(void* stream);
+
+/* ---------------------------------------------------------------- U-Net: other layers ----------------------- */
+int ssr_channel_sum(const float* t, long long nvox, int C, float* out, void* stream);
+/* KL.BatchNormalization(axis=-1), training mode (ext/neuron/models.py:349-351, 475-477).
+ * stats [4*C] = mean | invstd | gamma*invstd | beta - mean*gamma*invstd ; sums_scratch 2*C doubles. */
+int ssr_bn_stats(const float* x, long long nvox, int C, const float* gamma, const float* beta, float* moving_mean,
+                 float* moving_var, float eps, float momentum, double* sums_scratch, float* stats, void* stream);
+int ssr_bn_stats_inference(int C, const float* gamma, const float* beta, const float* moving_mean,
+                           const float* moving_var, float eps, float* stats, void* stream);
+/* mode 0: BN ; 1: BN + MaxPooling3D(2,'same') (models.py:354-356) ; 2: BN + UpSampling3D(2) (models.py:425-427). */
+int ssr_bn_apply(const float* x, float* y, const float* stats, int B, int d0, int d1, int d2, int C, int mode,
+                 int dst_stride, int dst_off, void* stream);
+int ssr_bn_bwd(const float* dy, const float* x, const float* stats, long long nvox, int C, const float* add,
+               int add_stride, int add_off, int elu, float* dx, float* dgamma, float* dbeta, double* sums_scratch,
+               void* stream);
+int ssr_maxpool_bwd(const float* dp, const float* x, const float* stats, int B, int d0, int d1, int d2, int C,
+                    float* dy_full, void* stream);
+int ssr_upsample_bwd(const float* du, int du_stride, int du_off, int B, int d0, int d1, int d2, int C, float* dlow,
+                     void* stream);
+int ssr_elu_bwd(const float* dh, int dh_stride, int dh_off, const float* h, const float* add, long long nvox, int C,
+                float* da, void* stream);
+/* unet_likelihood 1x1x1 conv (models.py:480-481) + metrics_model (SynthSR/metrics_model.py:53-104), fwd + bwd. */
+int ssr_head_loss(const float* feat, const float* w, const float* bias, const float* image, int image_channels,
+                  const int* res_idx, const float* target, float* pred, float* dfeat, float* dw, float* db,
+                  double* loss, float* gout_scratch, int B, int d0, int d1, int d2, int C, int L, int metric,
+                  const int* crop_size, const int* crop_begin, int train, void* stream);
+/* keras.optimizers.Adam (SynthSR/training.py:444) on one flat parameter buffer. */
+int ssr_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
+                  float eps, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYNTHSR_B200_H_ */

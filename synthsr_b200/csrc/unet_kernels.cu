@@ -1,0 +1,775 @@
+// U-Net training-step kernels (fp32 CUDA-core reference convolutions + all non-GEMM layers), sm_100a.
+//
+// Replaces the Keras layers instantiated by ext/neuron/models.py:301-360 (conv_enc) and :420-498 (conv_dec):
+// Conv3D(+bias+ELU), BatchNormalization(axis=-1), MaxPooling3D(2), UpSampling3D(2)+concatenate, the 1x1x1
+// likelihood head, the L1/L2 loss of SynthSR/metrics_model.py:53-104 and Keras' Adam (SynthSR/training.py:444).
+// The direct convolutions here are the exact-fp32 "parity mode" and the cross-check for the tcgen05 path in
+// conv_tc.cu; everything else is shared by both modes.
+//
+// Tensors are [B][d0][d1][d2][C] float32, channels contiguous; kernels (k,k,k,Cin,Cout) exactly as Keras stores
+// them, so checkpoints interchange without reshuffling.
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace {
+
+__device__ __forceinline__ float elu_f(float a) { return a > 0.f ? a : (expf(a) - 1.f); }
+// derivative of ELU expressed through its output h = elu(a): 1 if a > 0 (h > 0) else exp(a) = h + 1
+__device__ __forceinline__ float elu_grad_from_out(float h) { return h > 0.f ? 1.f : (h + 1.f); }
+
+struct ConvGeom {
+  int B, d0, d1, d2;
+  int C1, C2;     // input channels of source 1 / source 2 (logical concat [x1, x2]; C2 = 0 if single source)
+  int Cout;
+  int k;          // cubic kernel size (odd)
+  int act;        // 1: ELU
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// direct convolution, 'same' zero padding, cross-correlation (Keras Conv3D).  One thread: 1 voxel x 8 couts.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int CO_T = 8;
+
+__global__ void __launch_bounds__(256)
+conv3d_direct_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const float* __restrict__ w,
+                     const float* __restrict__ bias, float* __restrict__ y, ConvGeom G) {
+  const long long nvox = (long long)G.B * G.d0 * G.d1 * G.d2;
+  const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int co0 = blockIdx.y * CO_T;
+  if (v >= nvox) return;
+  long long r = v;
+  const int i2 = (int)(r % G.d2); r /= G.d2;
+  const int i1 = (int)(r % G.d1); r /= G.d1;
+  const int i0 = (int)(r % G.d0);
+  const int b = (int)(r / G.d0);
+  const int Cin = G.C1 + G.C2;
+  const int rad = G.k / 2;
+  float acc[CO_T];
+#pragma unroll
+  for (int e = 0; e < CO_T; ++e) acc[e] = 0.f;
+  const bool full = (co0 + CO_T <= G.Cout) && ((G.Cout & 3) == 0);
+  for (int a = 0; a < G.k; ++a) {
+    const int j0 = i0 + a - rad;
+    if (j0 < 0 || j0 >= G.d0) continue;
+    for (int bb = 0; bb < G.k; ++bb) {
+      const int j1 = i1 + bb - rad;
+      if (j1 < 0 || j1 >= G.d1) continue;
+      for (int c = 0; c < G.k; ++c) {
+        const int j2 = i2 + c - rad;
+        if (j2 < 0 || j2 >= G.d2) continue;
+        const long long nv = (((long long)b * G.d0 + j0) * G.d1 + j1) * G.d2 + j2;
+        const int tap = (a * G.k + bb) * G.k + c;
+        const float* wt = w + (long long)tap * Cin * G.Cout + co0;
+        const float* p1 = x1 + nv * G.C1;
+        for (int ci = 0; ci < G.C1; ++ci) {
+          const float xv = p1[ci];
+          const float* wr = wt + (long long)ci * G.Cout;
+          if (full) {
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(wr));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(wr) + 1);
+            acc[0] += xv * w0.x; acc[1] += xv * w0.y; acc[2] += xv * w0.z; acc[3] += xv * w0.w;
+            acc[4] += xv * w1.x; acc[5] += xv * w1.y; acc[6] += xv * w1.z; acc[7] += xv * w1.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < CO_T; ++e)
+              if (co0 + e < G.Cout) acc[e] += xv * __ldg(wr + e);
+          }
+        }
+        if (G.C2 > 0) {
+          const float* p2 = x2 + nv * G.C2;
+          for (int ci = 0; ci < G.C2; ++ci) {
+            const float xv = p2[ci];
+            const float* wr = wt + (long long)(G.C1 + ci) * G.Cout;
+            if (full) {
+              const float4 w0 = __ldg(reinterpret_cast<const float4*>(wr));
+              const float4 w1 = __ldg(reinterpret_cast<const float4*>(wr) + 1);
+              acc[0] += xv * w0.x; acc[1] += xv * w0.y; acc[2] += xv * w0.z; acc[3] += xv * w0.w;
+              acc[4] += xv * w1.x; acc[5] += xv * w1.y; acc[6] += xv * w1.z; acc[7] += xv * w1.w;
+            } else {
+#pragma unroll
+              for (int e = 0; e < CO_T; ++e)
+                if (co0 + e < G.Cout) acc[e] += xv * __ldg(wr + e);
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < CO_T; ++e) {
+    if (co0 + e < G.Cout) {
+      float o = acc[e] + (bias ? bias[co0 + e] : 0.f);
+      if (G.act) o = elu_f(o);
+      y[v * G.Cout + co0 + e] = o;
+    }
+  }
+}
+
+// weights for the data-gradient expressed as a forward convolution of dy:
+//   wd[tap'][co][ci] = w[K-1-tap'][ci][co]   (flip all three axes, swap channel roles)
+__global__ void flip_transpose_kernel(const float* __restrict__ w, float* __restrict__ wd, int ntap, int Cin, int Cout) {
+  const long long n = (long long)ntap * Cin * Cout;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(t % Cin);
+    const int co = (int)((t / Cin) % Cout);
+    const int tp = (int)(t / ((long long)Cin * Cout));
+    wd[t] = w[((long long)(ntap - 1 - tp) * Cin + ci) * Cout + co];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// weight gradient: dW[tap][ci][co] = sum_v x[v + tap][ci] * dy[v][co].  block = (tap, ci, voxel split),
+// threads run over co (coalesced dy rows, broadcast x).  fp32 accumulate per thread, atomicAdd across splits.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+wgrad_direct_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const float* __restrict__ dy,
+                    float* __restrict__ dw, ConvGeom G, int nsplit) {
+  const int Cin = G.C1 + G.C2;
+  const int tap = blockIdx.x;
+  const int ci = blockIdx.y;
+  const int split = blockIdx.z;
+  const int rad = G.k / 2;
+  const int c = tap % G.k, bb = (tap / G.k) % G.k, a = tap / (G.k * G.k);
+  const float* xs = ci < G.C1 ? x1 : x2;
+  const int xc = ci < G.C1 ? ci : ci - G.C1;
+  const int xC = ci < G.C1 ? G.C1 : G.C2;
+  const long long nvox = (long long)G.B * G.d0 * G.d1 * G.d2;
+  const long long per = (nvox + nsplit - 1) / nsplit;
+  const long long v0 = split * per, v1 = min(nvox, v0 + per);
+  for (int co = threadIdx.x; co < G.Cout; co += blockDim.x) {
+    float acc = 0.f;
+    for (long long v = v0; v < v1; ++v) {
+      long long r = v;
+      const int i2 = (int)(r % G.d2); r /= G.d2;
+      const int i1 = (int)(r % G.d1); r /= G.d1;
+      const int i0 = (int)(r % G.d0);
+      const int b = (int)(r / G.d0);
+      const int j0 = i0 + a - rad, j1 = i1 + bb - rad, j2 = i2 + c - rad;
+      if (j0 < 0 || j0 >= G.d0 || j1 < 0 || j1 >= G.d1 || j2 < 0 || j2 >= G.d2) continue;
+      const long long nv = (((long long)b * G.d0 + j0) * G.d1 + j1) * G.d2 + j2;
+      acc += xs[nv * xC + xc] * dy[v * G.Cout + co];
+    }
+    float* o = dw + ((long long)tap * Cin + ci) * G.Cout + co;
+    if (nsplit == 1) *o += acc; else atomicAdd(o, acc);
+  }
+}
+
+// per-channel sum over voxels of t[v][C] (bias gradients): out[c] += sum_v t[v][c]
+__global__ void channel_sum_kernel(const float* __restrict__ t, long long nvox, int C, float* __restrict__ out) {
+  extern __shared__ double sh[];
+  const int cx = threadIdx.x;          // channel lane
+  const int ry = threadIdx.y;          // voxel sub-lane
+  const int ny = blockDim.y;
+  for (int c0 = 0; c0 < C; c0 += blockDim.x) {
+    const int c = c0 + cx;
+    double acc = 0.0;
+    if (c < C)
+      for (long long v = blockIdx.x * (long long)ny + ry; v < nvox; v += (long long)gridDim.x * ny) acc += t[v * C + c];
+    sh[ry * blockDim.x + cx] = acc;
+    __syncthreads();
+    if (ry == 0 && c < C) {
+      double s = 0.0;
+      for (int y = 0; y < ny; ++y) s += sh[y * blockDim.x + cx];
+      atomicAdd(out + c, (float)s);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// BatchNormalization (training mode): statistics, finalize, apply (+pool / +upsample), backward
+// ---------------------------------------------------------------------------------------------------------
+// sums[0..C) = sum x, sums[C..2C) = sum x^2   (double)
+__global__ void bn_stats_kernel(const float* __restrict__ x, long long nvox, int C, double* __restrict__ sums) {
+  extern __shared__ double sh[];
+  const int cx = threadIdx.x, ry = threadIdx.y, ny = blockDim.y, nx = blockDim.x;
+  for (int c0 = 0; c0 < C; c0 += nx) {
+    const int c = c0 + cx;
+    double s = 0.0, q = 0.0;
+    if (c < C)
+      for (long long v = blockIdx.x * (long long)ny + ry; v < nvox; v += (long long)gridDim.x * ny) {
+        const double f = x[v * C + c];
+        s += f; q += f * f;
+      }
+    sh[(ry * nx + cx) * 2] = s;
+    sh[(ry * nx + cx) * 2 + 1] = q;
+    __syncthreads();
+    if (ry == 0 && c < C) {
+      double ts = 0.0, tq = 0.0;
+      for (int y = 0; y < ny; ++y) { ts += sh[(y * nx + cx) * 2]; tq += sh[(y * nx + cx) * 2 + 1]; }
+      atomicAdd(sums + c, ts);
+      atomicAdd(sums + C + c, tq);
+    }
+    __syncthreads();
+  }
+}
+
+// stats layout (float, 4*C): mean | invstd | scale (= gamma*invstd) | shift (= beta - mean*scale)
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, long long n, int C, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ moving_mean,
+                                   float* __restrict__ moving_var, float eps, float momentum, float* __restrict__ stats) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = sums[c] / (double)n;
+  double var = sums[C + c] / (double)n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float scale = gamma[c] * invstd;
+  stats[c] = (float)mean;
+  stats[C + c] = invstd;
+  stats[2 * C + c] = scale;
+  stats[3 * C + c] = beta[c] - (float)mean * scale;
+  if (moving_mean) {   // Keras 2.3.1: moving = moving*m + batch*(1-m); variance with n/(n-(1+eps)) correction
+    moving_mean[c] = moving_mean[c] * momentum + (float)mean * (1.f - momentum);
+    const double corr = (double)n / ((double)n - (1.0 + (double)eps));
+    moving_var[c] = moving_var[c] * momentum + (float)(var * corr) * (1.f - momentum);
+  }
+}
+
+// inference-mode stats from the moving averages
+__global__ void bn_stats_from_moving_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                            const float* __restrict__ mm, const float* __restrict__ mv, float eps,
+                                            float* __restrict__ stats) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invstd = 1.f / sqrtf(mv[c] + eps);
+  const float scale = gamma[c] * invstd;
+  stats[c] = mm[c]; stats[C + c] = invstd; stats[2 * C + c] = scale; stats[3 * C + c] = beta[c] - mm[c] * scale;
+}
+
+// mode 0: y = BN(x);  mode 1: y = maxpool2('same')(BN(x));  mode 2: y = upsample2(BN(x)) into a channel slice
+__global__ void bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ stats,
+                                int B, int d0, int d1, int d2, int C, int mode, int dst_stride, int dst_off) {
+  const float* scale = stats + 2 * C;
+  const float* shift = stats + 3 * C;
+  if (mode == 0) {
+    const long long n = (long long)B * d0 * d1 * d2 * C;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+      const int c = (int)(t % C);
+      y[(t / C) * dst_stride + dst_off + c] = x[t] * scale[c] + shift[c];
+    }
+  } else if (mode == 1) {
+    const int o0 = (d0 + 1) / 2, o1 = (d1 + 1) / 2, o2 = (d2 + 1) / 2;
+    const long long n = (long long)B * o0 * o1 * o2 * C;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+      const int c = (int)(t % C);
+      long long r = t / C;
+      const int k = (int)(r % o2); r /= o2;
+      const int j = (int)(r % o1); r /= o1;
+      const int i = (int)(r % o0);
+      const int b = (int)(r / o0);
+      float m = -CUDART_INF_F;
+      for (int a = 0; a < 2; ++a)
+        for (int bb = 0; bb < 2; ++bb)
+          for (int cc = 0; cc < 2; ++cc) {
+            const int s0 = 2 * i + a, s1 = 2 * j + bb, s2 = 2 * k + cc;
+            if (s0 < d0 && s1 < d1 && s2 < d2)
+              m = fmaxf(m, x[((((long long)b * d0 + s0) * d1 + s1) * d2 + s2) * C + c] * scale[c] + shift[c]);
+          }
+      y[(t / C) * dst_stride + dst_off + c] = m;
+    }
+  } else {
+    const int o0 = d0 * 2, o1 = d1 * 2, o2 = d2 * 2;
+    const long long n = (long long)B * o0 * o1 * o2 * C;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+      const int c = (int)(t % C);
+      long long r = t / C;
+      const int k = (int)(r % o2); r /= o2;
+      const int j = (int)(r % o1); r /= o1;
+      const int i = (int)(r % o0);
+      const int b = (int)(r / o0);
+      const float v = x[((((long long)b * d0 + i / 2) * d1 + j / 2) * d2 + k / 2) * C + c];
+      y[(t / C) * dst_stride + dst_off + c] = v * scale[c] + shift[c];
+    }
+  }
+}
+
+// sums2[0..C) = sum dy, sums2[C..2C) = sum dy * xhat     (xhat = (x - mean) * invstd)
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                     const float* __restrict__ stats, long long nvox, int C, double* __restrict__ sums2) {
+  extern __shared__ double sh[];
+  const int cx = threadIdx.x, ry = threadIdx.y, ny = blockDim.y, nx = blockDim.x;
+  for (int c0 = 0; c0 < C; c0 += nx) {
+    const int c = c0 + cx;
+    double s = 0.0, q = 0.0;
+    if (c < C) {
+      const float mean = stats[c], invstd = stats[C + c];
+      for (long long v = blockIdx.x * (long long)ny + ry; v < nvox; v += (long long)gridDim.x * ny) {
+        const double g = dy[v * C + c];
+        s += g; q += g * (double)((x[v * C + c] - mean) * invstd);
+      }
+    }
+    sh[(ry * nx + cx) * 2] = s;
+    sh[(ry * nx + cx) * 2 + 1] = q;
+    __syncthreads();
+    if (ry == 0 && c < C) {
+      double ts = 0.0, tq = 0.0;
+      for (int y = 0; y < ny; ++y) { ts += sh[(y * nx + cx) * 2]; tq += sh[(y * nx + cx) * 2 + 1]; }
+      atomicAdd(sums2 + c, ts);
+      atomicAdd(sums2 + C + c, tq);
+    }
+    __syncthreads();
+  }
+}
+
+// dgamma += sum dy*xhat ; dbeta += sum dy
+__global__ void bn_param_grad_kernel(const double* __restrict__ sums2, int C, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  dgamma[c] += (float)sums2[C + c];
+  dbeta[c] += (float)sums2[c];
+}
+
+// dx = scale * (dy - mean(dy) - xhat * mean(dy*xhat))  [+ add]  [* elu'(x)]      (x = BN input = ELU output)
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                    const float* __restrict__ stats, const double* __restrict__ sums2, long long nvox,
+                                    int C, const float* __restrict__ add, int add_stride, int add_off, int elu,
+                                    float* __restrict__ dx) {
+  const long long n = nvox * C;
+  const double inv_n = 1.0 / (double)nvox;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(t % C);
+    const float xv = x[t];
+    const float xhat = (xv - stats[c]) * stats[C + c];
+    float g = stats[2 * C + c] * (dy[t] - (float)(sums2[c] * inv_n) - xhat * (float)(sums2[C + c] * inv_n));
+    if (add) g += add[(t / C) * add_stride + add_off + c];
+    if (elu) g *= elu_grad_from_out(xv);
+    dx[t] = g;
+  }
+}
+
+// gradient of maxpool2('same')(BN(x)) w.r.t. BN(x): route dp to the first maximum of each 2x2x2 window
+__global__ void maxpool_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ x,
+                                   const float* __restrict__ stats, int B, int d0, int d1, int d2, int C,
+                                   float* __restrict__ dyf) {
+  const float* scale = stats + 2 * C;
+  const float* shift = stats + 3 * C;
+  const int o0 = (d0 + 1) / 2, o1 = (d1 + 1) / 2, o2 = (d2 + 1) / 2;
+  const long long n = (long long)B * o0 * o1 * o2 * C;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(t % C);
+    long long r = t / C;
+    const int k = (int)(r % o2); r /= o2;
+    const int j = (int)(r % o1); r /= o1;
+    const int i = (int)(r % o0);
+    const int b = (int)(r / o0);
+    float m = -CUDART_INF_F;
+    long long arg = -1;
+    for (int a = 0; a < 2; ++a)
+      for (int bb = 0; bb < 2; ++bb)
+        for (int cc = 0; cc < 2; ++cc) {
+          const int s0 = 2 * i + a, s1 = 2 * j + bb, s2 = 2 * k + cc;
+          if (s0 < d0 && s1 < d1 && s2 < d2) {
+            const long long idx = ((((long long)b * d0 + s0) * d1 + s1) * d2 + s2) * C + c;
+            const float v = x[idx] * scale[c] + shift[c];
+            dyf[idx] = 0.f;
+            if (v > m) { m = v; arg = idx; }
+          }
+        }
+    if (arg >= 0) dyf[arg] = dp[t];
+  }
+}
+
+// gradient of upsample2: dlow[v][c] = sum of the 8 children of du (du may be a channel slice of a wider tensor)
+__global__ void upsample_bwd_kernel(const float* __restrict__ du, int du_stride, int du_off, int B, int d0, int d1,
+                                    int d2, int C, float* __restrict__ dlow) {
+  const long long n = (long long)B * d0 * d1 * d2 * C;   // low-res element count
+  const int f0 = 2 * d0, f1 = 2 * d1, f2 = 2 * d2;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(t % C);
+    long long r = t / C;
+    const int k = (int)(r % d2); r /= d2;
+    const int j = (int)(r % d1); r /= d1;
+    const int i = (int)(r % d0);
+    const int b = (int)(r / d0);
+    float s = 0.f;
+    for (int a = 0; a < 2; ++a)
+      for (int bb = 0; bb < 2; ++bb)
+        for (int cc = 0; cc < 2; ++cc)
+          s += du[((((long long)b * f0 + 2 * i + a) * f1 + 2 * j + bb) * f2 + 2 * k + cc) * du_stride + du_off + c];
+    dlow[t] = s;
+  }
+}
+
+// da = (dh [+ add]) * elu'(h)      (dh may be a channel slice of a wider tensor)
+__global__ void elu_bwd_kernel(const float* __restrict__ dh, int dh_stride, int dh_off, const float* __restrict__ h,
+                               const float* __restrict__ add, long long nvox, int C, float* __restrict__ da) {
+  const long long n = nvox * C;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(t % C);
+    float g = dh[(t / C) * dh_stride + dh_off + c];
+    if (add) g += add[t];
+    da[t] = g * elu_grad_from_out(h[t]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 1x1x1 likelihood head (models.py:480-481) + residual + crop + L1/L2 loss (metrics_model.py:53-104), forward and
+// backward in one pass: writes pred, dL/dfeat, accumulates dW_head, db_head and the loss.
+// ---------------------------------------------------------------------------------------------------------
+struct HeadParams {
+  int B, d0, d1, d2;
+  int C;            // input features
+  int L;            // nb_labels (outputs), <= 4
+  int metric;       // 1: l1, 2: l2
+  int res_stride;   // residual: image tensor channel stride (0: none)
+  int res_idx[4];   // image channel added to output l
+  int tgt_stride;   // target channels (== L)
+  int c0, c1, c2, cb0, cb1, cb2;   // loss crop window (size / begin); c0 == 0 -> no crop
+  int train;        // 1: also write dfeat / accumulate parameter gradients
+  double inv_count; // 1 / (number of elements entering the mean)
+};
+
+__global__ void __launch_bounds__(256)
+head_loss_kernel(const float* __restrict__ feat, const float* __restrict__ w, const float* __restrict__ bias,
+                 const float* __restrict__ image, const float* __restrict__ target, float* __restrict__ pred,
+                 float* __restrict__ dfeat, float* __restrict__ dw, float* __restrict__ db, double* __restrict__ loss,
+                 HeadParams P) {
+  __shared__ float sw[4 * 512];
+  __shared__ double sloss[8];
+  const int C = P.C, L = P.L;
+  for (int e = threadIdx.x; e < C * L; e += blockDim.x) sw[e] = w[e];   // w[c][l]
+  __syncthreads();
+  const long long nvox = (long long)P.B * P.d0 * P.d1 * P.d2;
+  double lloss = 0.0;
+  float ldb[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvox; v += (long long)gridDim.x * blockDim.x) {
+    const float* f = feat + v * C;
+    float o[4];
+    for (int l = 0; l < L; ++l) o[l] = bias[l];
+    for (int c = 0; c < C; ++c) {
+      const float fv = f[c];
+      for (int l = 0; l < L; ++l) o[l] += fv * sw[c * L + l];
+    }
+    bool inside = true;
+    if (P.c0 > 0) {
+      long long r = v;
+      const int i2 = (int)(r % P.d2); r /= P.d2;
+      const int i1 = (int)(r % P.d1); r /= P.d1;
+      const int i0 = (int)(r % P.d0);
+      inside = i0 >= P.cb0 && i0 < P.cb0 + P.c0 && i1 >= P.cb1 && i1 < P.cb1 + P.c1 && i2 >= P.cb2 && i2 < P.cb2 + P.c2;
+    }
+    float g[4];
+    for (int l = 0; l < L; ++l) {
+      if (pred) pred[v * L + l] = o[l];
+      float p = o[l];
+      if (P.res_stride > 0) p += image[v * P.res_stride + P.res_idx[l]];
+      const float err = p - target[v * P.tgt_stride + l];
+      g[l] = 0.f;
+      if (inside) {
+        if (P.metric == 1) {
+          lloss += fabsf(err);
+          g[l] = (err > 0.f ? 1.f : (err < 0.f ? -1.f : 0.f)) * (float)P.inv_count;
+        } else {
+          lloss += (double)err * err;
+          g[l] = 2.f * err * (float)P.inv_count;
+        }
+      }
+      ldb[l] += g[l];
+    }
+    if (P.train) {
+      for (int c = 0; c < C; ++c) {
+        float d = 0.f;
+        for (int l = 0; l < L; ++l) d += g[l] * sw[c * L + l];
+        dfeat[v * C + c] = d;
+      }
+    }
+  }
+  // loss + db: block reduction
+  for (int o = 16; o > 0; o >>= 1) {
+    lloss += __shfl_xor_sync(0xffffffffu, lloss, o);
+    for (int l = 0; l < L; ++l) ldb[l] += __shfl_xor_sync(0xffffffffu, ldb[l], o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sloss[threadIdx.x >> 5] = lloss;
+    if (P.train)
+      for (int l = 0; l < L; ++l) atomicAdd(db + l, ldb[l]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += sloss[i];
+    atomicAdd(loss, s * P.inv_count);
+  }
+}
+
+// dW_head[c][l] += sum_v feat[v][c] * g[v][l] where g is recomputed from dfeat is not possible -> separate pass
+// using the stored per-voxel output gradient gout[v][l].
+__global__ void head_wgrad_kernel(const float* __restrict__ feat, const float* __restrict__ gout, long long nvox, int C,
+                                  int L, float* __restrict__ dw) {
+  extern __shared__ double sh[];
+  const int cx = threadIdx.x, ry = threadIdx.y, ny = blockDim.y, nx = blockDim.x;
+  for (int l = 0; l < L; ++l)
+    for (int c0 = 0; c0 < C; c0 += nx) {
+      const int c = c0 + cx;
+      double s = 0.0;
+      if (c < C)
+        for (long long v = blockIdx.x * (long long)ny + ry; v < nvox; v += (long long)gridDim.x * ny)
+          s += (double)feat[v * C + c] * (double)gout[v * L + l];
+      sh[ry * nx + cx] = s;
+      __syncthreads();
+      if (ry == 0 && c < C) {
+        double ts = 0.0;
+        for (int y = 0; y < ny; ++y) ts += sh[y * nx + cx];
+        atomicAdd(dw + c * L + l, (float)ts);
+      }
+      __syncthreads();
+    }
+}
+
+// per-voxel output gradient g[v][l] of the loss (same formula as in head_loss_kernel), for head_wgrad_kernel
+__global__ void head_gout_kernel(const float* __restrict__ pred, const float* __restrict__ image,
+                                 const float* __restrict__ target, float* __restrict__ gout, HeadParams P) {
+  const long long nvox = (long long)P.B * P.d0 * P.d1 * P.d2;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvox; v += (long long)gridDim.x * blockDim.x) {
+    bool inside = true;
+    if (P.c0 > 0) {
+      long long r = v;
+      const int i2 = (int)(r % P.d2); r /= P.d2;
+      const int i1 = (int)(r % P.d1); r /= P.d1;
+      const int i0 = (int)(r % P.d0);
+      inside = i0 >= P.cb0 && i0 < P.cb0 + P.c0 && i1 >= P.cb1 && i1 < P.cb1 + P.c1 && i2 >= P.cb2 && i2 < P.cb2 + P.c2;
+    }
+    for (int l = 0; l < P.L; ++l) {
+      float p = pred[v * P.L + l];
+      if (P.res_stride > 0) p += image[v * P.res_stride + P.res_idx[l]];
+      const float err = p - target[v * P.tgt_stride + l];
+      float g = 0.f;
+      if (inside) g = P.metric == 1 ? (err > 0.f ? 1.f : (err < 0.f ? -1.f : 0.f)) * (float)P.inv_count
+                                    : 2.f * err * (float)P.inv_count;
+      gout[v * P.L + l] = g;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Keras-2.3.1 Adam on one flat buffer:  m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr_t m/(sqrt(v)+eps)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr_t, float b1, float b2, float eps,
+                            float gscale) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const float gg = g[t] * gscale;
+    const float mm = b1 * m[t] + (1.f - b1) * gg;
+    const float vv = b2 * v[t] + (1.f - b2) * gg * gg;
+    m[t] = mm; v[t] = vv;
+    p[t] = p[t] - lr_t * mm / (sqrtf(vv) + eps);
+  }
+}
+
+int grid_for(long long n, int block = 256) {
+  long long g = (n + block - 1) / block;
+  const long long cap = 148LL * 16;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ssr_conv3d_fwd_ref(const float* x1, int C1, const float* x2, int C2, const float* w, const float* bias, float* y,
+                       int B, int d0, int d1, int d2, int Cout, int k, int act, void* stream) {
+  SSR_CHECK_ARG(x1 && w && y && C1 > 0 && C2 >= 0 && (C2 == 0 || x2) && Cout > 0 && (k & 1), "conv args");
+  ConvGeom G{B, d0, d1, d2, C1, C2, Cout, k, act};
+  const long long nvox = (long long)B * d0 * d1 * d2;
+  dim3 grid((unsigned)((nvox + 255) / 256), (unsigned)((Cout + CO_T - 1) / CO_T));
+  conv3d_direct_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x1, x2, w, bias, y, G);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
+// dx[v][Cin] = sum_tap sum_co dy[v - tap][co] w[tap][ci][co];  wd_scratch: k^3*Cin*Cout floats
+int ssr_conv3d_dgrad_ref(const float* dy, const float* w, float* wd_scratch, float* dx, int B, int d0, int d1, int d2,
+                         int Cin, int Cout, int k, void* stream) {
+  SSR_CHECK_ARG(dy && w && wd_scratch && dx && Cin > 0 && Cout > 0 && (k & 1), "dgrad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ntap = k * k * k;
+  flip_transpose_kernel<<<grid_for((long long)ntap * Cin * Cout), 256, 0, st>>>(w, wd_scratch, ntap, Cin, Cout);
+  SSR_COUNT_LAUNCH();
+  ConvGeom G{B, d0, d1, d2, Cout, 0, Cin, k, 0};
+  const long long nvox = (long long)B * d0 * d1 * d2;
+  dim3 grid((unsigned)((nvox + 255) / 256), (unsigned)((Cin + CO_T - 1) / CO_T));
+  conv3d_direct_kernel<<<grid, 256, 0, st>>>(dy, nullptr, wd_scratch, nullptr, dx, G);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
+// dw (k,k,k,C1+C2,Cout) += x (*) dy ;  db[Cout] += sum dy   (db may be NULL)
+int ssr_conv3d_wgrad_ref(const float* x1, int C1, const float* x2, int C2, const float* dy, float* dw, float* db, int B,
+                         int d0, int d1, int d2, int Cout, int k, void* stream) {
+  SSR_CHECK_ARG(x1 && dy && dw && C1 > 0 && C2 >= 0 && (C2 == 0 || x2) && Cout > 0 && (k & 1), "wgrad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  ConvGeom G{B, d0, d1, d2, C1, C2, Cout, k, 0};
+  const long long nvox = (long long)B * d0 * d1 * d2;
+  int nsplit = (int)((nvox + 32767) / 32768);
+  if (nsplit > 64) nsplit = 64;
+  dim3 grid(k * k * k, C1 + C2, nsplit);
+  wgrad_direct_kernel<<<grid, 128, 0, st>>>(x1, x2, dy, dw, G, nsplit);
+  SSR_COUNT_LAUNCH();
+  if (db) {
+    dim3 blk(32, 8);
+    int g = (int)((nvox + 7) / 8); if (g > 148 * 8) g = 148 * 8;
+    channel_sum_kernel<<<g, blk, 32 * 8 * sizeof(double), st>>>(dy, nvox, Cout, db);
+    SSR_COUNT_LAUNCH();
+  }
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
+int ssr_channel_sum(const float* t, long long nvox, int C, float* out, void* stream) {
+  SSR_CHECK_ARG(t && out && nvox > 0 && C > 0, "args");
+  dim3 blk(32, 8);
+  int g = (int)((nvox + 7) / 8); if (g > 148 * 8) g = 148 * 8;
+  channel_sum_kernel<<<g, blk, 32 * 8 * sizeof(double), (cudaStream_t)stream>>>(t, nvox, C, out);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
+// training-mode BN statistics: sums (2*C doubles, zeroed here) -> stats (4*C floats) ; updates moving stats if given
+int ssr_bn_stats(const float* x, long long nvox, int C, const float* gamma, const float* beta, float* moving_mean,
+                 float* moving_var, float eps, float momentum, double* sums_scratch, float* stats, void* stream) {
+  SSR_CHECK_ARG(x && gamma && beta && sums_scratch && stats && nvox > 0 && C > 0, "args");
+  cudaStream_t st = (cudaStream_t)stream;
+  SSR_CHECK_CUDA(cudaMemsetAsync(sums_scratch, 0, 2 * C * sizeof(double), st));
+  dim3 blk(32, 8);
+  int g = (int)((nvox + 7) / 8); if (g > 148 * 8) g = 148 * 8;
+  bn_stats_kernel<<<g, blk, 32 * 8 * 2 * sizeof(double), st>>>(x, nvox, C, sums_scratch);
+  SSR_COUNT_LAUNCH();
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums_scratch, nvox, C, gamma, beta, moving_mean, moving_var, eps,
+                                                      momentum, stats);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
+int ssr_bn_stats_inference(int C, const float* gamma, const float* beta, const float* moving_mean,
+                           const float* moving_var, float eps, float* stats, void* stream) {
+  SSR_CHECK_ARG(gamma && beta && moving_mean && moving_var && stats && C > 0, "args");
+  bn_stats_from_moving_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(C, gamma, beta, moving_mean,
+                                                                                moving_var, eps, stats);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
+// mode 0 plain, 1 +maxpool2('same'), 2 +upsample2 ; (d0,d1,d2) is the INPUT spatial shape
+int ssr_bn_apply(const float* x, float* y, const float* stats, int B, int d0, int d1, int d2, int C, int mode,
+                 int dst_stride, int dst_off, void* stream) {
+  SSR_CHECK_ARG(x && y && stats && mode >= 0 && mode <= 2, "args");
+  if (dst_stride <= 0) { dst_stride = C; dst_off = 0; }
+  long long n = (long long)B * d0 * d1 * d2 * C;
+  if (mode == 1) n = (long long)B * ((d0 + 1) / 2) * ((d1 + 1) / 2) * ((d2 + 1) / 2) * C;
+  if (mode == 2) n *= 8;
+  bn_apply_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, y, stats, B, d0, d1, d2, C, mode, dst_stride,
+                                                                 dst_off);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
+// BN backward: dx = BN'(dy) [+ add] [* elu'(x)] ; dgamma/dbeta accumulated.  sums_scratch: 2*C doubles.
+int ssr_bn_bwd(const float* dy, const float* x, const float* stats, long long nvox, int C, const float* add,
+               int add_stride, int add_off, int elu, float* dx, float* dgamma, float* dbeta, double* sums_scratch,
+               void* stream) {
+  SSR_CHECK_ARG(dy && x && stats && dx && sums_scratch && nvox > 0 && C > 0, "args");
+  cudaStream_t st = (cudaStream_t)stream;
+  SSR_CHECK_CUDA(cudaMemsetAsync(sums_scratch, 0, 2 * C * sizeof(double), st));
+  dim3 blk(32, 8);
+  int g = (int)((nvox + 7) / 8); if (g > 148 * 8) g = 148 * 8;
+  bn_bwd_reduce_kernel<<<g, blk, 32 * 8 * 2 * sizeof(double), st>>>(dy, x, stats, nvox, C, sums_scratch);
+  SSR_COUNT_LAUNCH();
+  if (dgamma && dbeta) {
+    bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums_scratch, C, dgamma, dbeta);
+    SSR_COUNT_LAUNCH();
+  }
+  if (add && add_stride <= 0) { add_stride = C; add_off = 0; }
+  bn_bwd_apply_kernel<<<grid_for(nvox * C), 256, 0, st>>>(dy, x, stats, sums_scratch, nvox, C, add, add_stride, add_off,
+                                                          elu, dx);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
+int ssr_maxpool_bwd(const float* dp, const float* x, const float* stats, int B, int d0, int d1, int d2, int C,
+                    float* dy_full, void* stream) {
+  SSR_CHECK_ARG(dp && x && stats && dy_full, "args");
+  const long long n = (long long)B * ((d0 + 1) / 2) * ((d1 + 1) / 2) * ((d2 + 1) / 2) * C;
+  maxpool_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(dp, x, stats, B, d0, d1, d2, C, dy_full);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
+// (d0,d1,d2) is the LOW-res shape; du is the full-res gradient (channel slice du_off..du_off+C of du_stride)
+int ssr_upsample_bwd(const float* du, int du_stride, int du_off, int B, int d0, int d1, int d2, int C, float* dlow,
+                     void* stream) {
+  SSR_CHECK_ARG(du && dlow && du_stride >= C, "args");
+  upsample_bwd_kernel<<<grid_for((long long)B * d0 * d1 * d2 * C), 256, 0, (cudaStream_t)stream>>>(
+      du, du_stride, du_off, B, d0, d1, d2, C, dlow);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
+int ssr_elu_bwd(const float* dh, int dh_stride, int dh_off, const float* h, const float* add, long long nvox, int C,
+                float* da, void* stream) {
+  SSR_CHECK_ARG(dh && h && da && nvox > 0 && C > 0, "args");
+  if (dh_stride <= 0) { dh_stride = C; dh_off = 0; }
+  elu_bwd_kernel<<<grid_for(nvox * C), 256, 0, (cudaStream_t)stream>>>(dh, dh_stride, dh_off, h, add, nvox, C, da);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
+// head + loss forward/backward.  loss: 1 double (zeroed here).  gout_scratch: nvox*L floats (train only).
+int ssr_head_loss(const float* feat, const float* w, const float* bias, const float* image, int image_channels,
+                  const int* res_idx, const float* target, float* pred, float* dfeat, float* dw, float* db,
+                  double* loss, float* gout_scratch, int B, int d0, int d1, int d2, int C, int L, int metric,
+                  const int* crop_size, const int* crop_begin, int train, void* stream) {
+  SSR_CHECK_ARG(feat && w && bias && target && loss && pred, "pointers");
+  SSR_CHECK_ARG(L >= 1 && L <= 4 && C * L <= 2048 && (metric == 1 || metric == 2), "head shape/metric");
+  SSR_CHECK_ARG(!train || (dfeat && dw && db && gout_scratch), "train buffers");
+  HeadParams P;
+  P.B = B; P.d0 = d0; P.d1 = d1; P.d2 = d2; P.C = C; P.L = L; P.metric = metric;
+  P.res_stride = (image && res_idx) ? image_channels : 0;
+  for (int l = 0; l < 4; ++l) P.res_idx[l] = (res_idx && l < L) ? res_idx[l] : 0;
+  P.tgt_stride = L;
+  long long count = (long long)B * d0 * d1 * d2 * L;
+  if (crop_size) {
+    P.c0 = crop_size[0]; P.c1 = crop_size[1]; P.c2 = crop_size[2];
+    P.cb0 = crop_begin[0]; P.cb1 = crop_begin[1]; P.cb2 = crop_begin[2];
+    count = (long long)B * P.c0 * P.c1 * P.c2 * L;
+  } else { P.c0 = P.c1 = P.c2 = 0; P.cb0 = P.cb1 = P.cb2 = 0; }
+  P.train = train;
+  P.inv_count = 1.0 / (double)count;
+  cudaStream_t st = (cudaStream_t)stream;
+  SSR_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(double), st));
+  const long long nvox = (long long)B * d0 * d1 * d2;
+  head_loss_kernel<<<grid_for(nvox), 256, 0, st>>>(feat, w, bias, image, target, pred, dfeat, dw, db, loss, P);
+  SSR_COUNT_LAUNCH();
+  if (train) {
+    head_gout_kernel<<<grid_for(nvox), 256, 0, st>>>(pred, image, target, gout_scratch, P);
+    SSR_COUNT_LAUNCH();
+    dim3 blk(32, 8);
+    int g = (int)((nvox + 7) / 8); if (g > 148 * 8) g = 148 * 8;
+    head_wgrad_kernel<<<g, blk, 32 * 8 * sizeof(double), st>>>(feat, gout_scratch, nvox, C, L, dw);
+    SSR_COUNT_LAUNCH();
+  }
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
+int ssr_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
+                  float eps, float grad_scale, void* stream) {
+  SSR_CHECK_ARG(p && g && m && v && n > 0, "args");
+  adam_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr_t, beta1, beta2, eps, grad_scale);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,354 @@
+"""B200 U-Net training engine: ext/neuron/models.py `unet` (conv_enc :256-360 + conv_dec :363-498) + the loss of
+SynthSR/metrics_model.py + Keras Adam, executed as CUDA kernels through the C ABI (include/synthsr_b200.h).
+
+Parameters live in ONE flat float32 buffer (so the data-parallel step is a single all-reduce of one flat gradient
+buffer and a single fused Adam launch); views into it carry the Keras layer names and Keras layouts
+(kernels (k,k,k,Cin,Cout)), which is what checkpoints store.
+
+conv_impl = 'tc'  : tcgen05 TF32 implicit-GEMM convolutions (conv_tc.cu)            -- throughput mode
+conv_impl = 'ref' : exact fp32 CUDA-core convolutions (unet_kernels.cu)             -- parity mode / cross-check
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from ._lib import lib, stream_ptr
+
+BN_EPS = 1e-3
+BN_MOMENTUM = 0.99
+
+
+def layer_specs(cin, nb_features=24, nb_levels=5, feat_mult=2, nb_conv_per_level=2, nb_labels=1):
+    """[(keras_name, kind, cin, cout)] in graph order; names as in the reference's .h5 files."""
+    specs, c, enc = [], cin, []
+    for level in range(nb_levels):
+        f = int(np.round(nb_features * feat_mult ** level))
+        for j in range(nb_conv_per_level):
+            specs.append(('unet_conv_downarm_%d_%d' % (level, j), 'conv', c, f))
+            c = f
+        specs.append(('unet_bn_down_%d' % level, 'bn', f, f))
+        enc.append(f)
+    for level in range(nb_levels - 1):
+        f = int(np.round(nb_features * feat_mult ** (nb_levels - 2 - level)))
+        c = enc[nb_levels - 2 - level] + c
+        for j in range(nb_conv_per_level):
+            specs.append(('unet_conv_uparm_%d_%d' % (nb_levels + level, j), 'conv', c, f))
+            c = f
+        specs.append(('unet_bn_up_%d' % level, 'bn', f, f))
+    specs.append(('unet_likelihood', 'conv1', c, nb_labels))
+    return specs
+
+
+class UNet3D:
+    def __init__(self, input_shape, nb_features=24, nb_levels=5, conv_size=3, nb_labels=1, feat_mult=2,
+                 nb_conv_per_level=2, batchsize=1, device='cuda', conv_impl='tc', seed=None):
+        assert nb_conv_per_level == 2, 'the reference training path uses nb_conv_per_level=2 (SynthSR/training.py:75)'
+        assert conv_size == 3 or conv_impl == 'ref'
+        self.B = int(batchsize)
+        self.dims = [int(s) for s in input_shape[:3]]
+        self.cin = int(input_shape[3])
+        self.L = int(nb_levels)
+        self.k = int(conv_size)
+        self.nb_labels = int(nb_labels)
+        self.conv_impl = conv_impl
+        self.device = torch.device(device)
+        for d in self.dims:
+            if d % (2 ** (self.L - 1)) != 0:
+                raise ValueError('spatial dims %s must be divisible by %d (UpSampling/concatenate would not match; the '
+                                 'reference enforces output_div_by_n=2**n_levels)' % (self.dims, 2 ** (self.L - 1)))
+        self.specs = layer_specs(self.cin, nb_features, nb_levels, feat_mult, nb_conv_per_level, nb_labels)
+        self.feats = [int(np.round(nb_features * feat_mult ** l)) for l in range(self.L)]
+        # ---- flat parameter / gradient / Adam buffers with named views -------------------------------------------
+        self.layout = OrderedDict()
+        off = 0
+        for name, kind, ci, co in self.specs:
+            if kind in ('conv', 'conv1'):
+                k = self.k if kind == 'conv' else 1
+                self.layout[name + '/kernel'] = (off, (k, k, k, ci, co)); off += k ** 3 * ci * co
+                self.layout[name + '/bias'] = (off, (co,)); off += co
+            else:
+                self.layout[name + '/gamma'] = (off, (co,)); off += co
+                self.layout[name + '/beta'] = (off, (co,)); off += co
+        self.n_params = off
+        dev = self.device
+        self.params = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.adam_m = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.adam_v = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.iterations = 0
+        self.moving = OrderedDict()
+        for name, kind, ci, co in self.specs:
+            if kind == 'bn':
+                self.moving[name + '/moving_mean'] = torch.zeros(co, dtype=torch.float32, device=dev)
+                self.moving[name + '/moving_variance'] = torch.ones(co, dtype=torch.float32, device=dev)
+        self.p = {n: self.params[o:o + int(np.prod(s))].view(s) for n, (o, s) in self.layout.items()}
+        self.g = {n: self.grads[o:o + int(np.prod(s))].view(s) for n, (o, s) in self.layout.items()}
+        self.init_weights(seed)
+        self._alloc()
+
+    # -------------------------------------------------------------------------------------------------------------
+    def init_weights(self, seed=None):
+        """glorot_uniform kernels, zero biases, gamma=1, beta=0 (Keras defaults used by models.py:297-351)."""
+        rng = np.random.default_rng(seed)
+        host = np.zeros(self.n_params, dtype=np.float32)
+        for name, kind, ci, co in self.specs:
+            if kind in ('conv', 'conv1'):
+                k = self.k if kind == 'conv' else 1
+                limit = math.sqrt(6.0 / (k ** 3 * ci + k ** 3 * co))
+                o, s = self.layout[name + '/kernel']
+                host[o:o + int(np.prod(s))] = rng.uniform(-limit, limit, size=int(np.prod(s))).astype(np.float32)
+            else:
+                o, s = self.layout[name + '/gamma']
+                host[o:o + co] = 1.
+        self.params.copy_(torch.from_numpy(host))
+        for n, t in self.moving.items():
+            t.fill_(0. if n.endswith('mean') else 1.)
+        self.adam_m.zero_(); self.adam_v.zero_(); self.iterations = 0
+        self._packed_dirty = True
+
+    def state_dict(self):
+        sd = OrderedDict((n, self.p[n].detach().cpu().numpy().copy()) for n in self.layout)
+        for n, t in self.moving.items():
+            sd[n] = t.detach().cpu().numpy().copy()
+        return sd
+
+    def load_state_dict(self, sd, strict=True):
+        for n in self.layout:
+            if n in sd:
+                self.p[n].copy_(torch.as_tensor(np.asarray(sd[n], dtype=np.float32)).view(self.p[n].shape))
+            elif strict:
+                raise KeyError(n)
+        for n in self.moving:
+            if n in sd:
+                self.moving[n].copy_(torch.as_tensor(np.asarray(sd[n], dtype=np.float32)))
+            elif strict:
+                raise KeyError(n)
+        self._packed_dirty = True
+
+    # -------------------------------------------------------------------------------------------------------------
+    def _alloc(self):
+        B, L, F, dev = self.B, self.L, self.feats, self.device
+        f32 = torch.float32
+        self.ldims = [[d // (2 ** l) for d in self.dims] for l in range(L)]
+        self.nvox = [B * int(np.prod(d)) for d in self.ldims]
+
+        def buf(l, c):
+            return torch.empty((self.nvox[l], c), dtype=f32, device=dev)
+
+        self.inp = [None] + [buf(l, F[l - 1]) for l in range(1, L)]           # pooled BN output feeding level l
+        self.h0 = [buf(l, F[l]) for l in range(L)]
+        self.h1 = [buf(l, F[l]) for l in range(L)]
+        self.u = [buf(l, F[l + 1]) for l in range(L - 1)]                     # upsampled BN output (decoder input)
+        self.g0 = [buf(l, F[l]) for l in range(L - 1)]
+        self.g1 = [buf(l, F[l]) for l in range(L - 1)]
+        self.feat = buf(0, F[0])
+        self.pred = torch.empty((self.nvox[0], self.nb_labels), dtype=f32, device=dev)
+        self.stats_enc = [torch.empty(4 * F[l], dtype=f32, device=dev) for l in range(L)]
+        self.stats_dec = [torch.empty(4 * F[l], dtype=f32, device=dev) for l in range(L - 1)]
+        self.sums = torch.zeros(2 * max(F), dtype=torch.float64, device=dev)
+        self.loss_buf = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._bwd_alloc = False
+        self._packed = {}
+        self._packed_dirty = True
+
+    def _alloc_bwd(self):
+        if self._bwd_alloc:
+            return
+        L, F, dev = self.L, self.feats, self.device
+        f32 = torch.float32
+
+        def buf(l, c):
+            return torch.empty((self.nvox[l], c), dtype=f32, device=dev)
+
+        self.ga = [buf(l, F[l]) for l in range(L)]
+        self.gb = [buf(l, F[l]) for l in range(L)]
+        self.dcat = [buf(l, F[l] + F[l + 1]) for l in range(L - 1)]
+        self.dbn_dec = [buf(l, F[l]) for l in range(L - 1)]                   # grad wrt BN output of decoder level l
+        self.dbn_bott = buf(L - 1, F[L - 1])                                  # grad wrt BN output of the bottleneck
+        self.dp = [None] + [buf(l, F[l - 1]) for l in range(1, L)]            # grad wrt pooled input of level l
+        self.gout = torch.empty((self.nvox[0], self.nb_labels), dtype=f32, device=dev)
+        maxw = max(int(np.prod(s)) for n, (o, s) in self.layout.items() if n.endswith('kernel'))
+        self.wd_scratch = torch.empty(maxw, dtype=f32, device=dev)
+        self._bwd_alloc = True
+
+    # -------------------------------------------------------------------------------------------------------------
+    # convolution dispatch
+    # -------------------------------------------------------------------------------------------------------------
+    def _conv_fwd(self, name, x1, c1, x2, c2, y, l, cout, act=1):
+        st = stream_ptr()
+        d = self.ldims[l]
+        if self.conv_impl == 'tc' and (c1 + c2) % 8 == 0:
+            lib.ssr_conv3d_fwd_tc(x1, c1, x2, c2, self._packed_w(name, 0, c1, c2, cout), self.p[name + '/bias'], y,
+                                  self.B, *d, cout, act, st)
+        else:
+            lib.ssr_conv3d_fwd_ref(x1, c1, x2, c2, self.p[name + '/kernel'], self.p[name + '/bias'], y, self.B, *d,
+                                   cout, self.k, act, st)
+
+    def _conv_dgrad(self, name, dy, dx, l, cin, cout):
+        st = stream_ptr()
+        d = self.ldims[l]
+        if self.conv_impl == 'tc' and cout % 8 == 0:
+            # data gradient = forward convolution of dy with the flipped / transposed kernel
+            lib.ssr_conv3d_fwd_tc(dy, cout, None, 0, self._packed_w(name, 1, cin, 0, cout), None, dx, self.B, *d, cin,
+                                  0, st)
+        else:
+            lib.ssr_conv3d_dgrad_ref(dy, self.p[name + '/kernel'], self.wd_scratch, dx, self.B, *d, cin, cout, self.k,
+                                     st)
+
+    def _conv_wgrad(self, name, x1, c1, x2, c2, dy, l, cout):
+        st = stream_ptr()
+        d = self.ldims[l]
+        if self.conv_impl == 'tc' and self._wgrad_tc_ok(c1, c2, cout):
+            nbytes = lib.ssr_conv3d_wgrad_scratch_bytes(c1, c2, cout, self.B, *d)
+            if getattr(self, '_wg_scratch', None) is None or self._wg_scratch.numel() * 4 < nbytes:
+                self._wg_scratch = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
+            lib.ssr_conv3d_wgrad_tc(x1, c1, x2, c2, dy, self.g[name + '/kernel'], self.g[name + '/bias'],
+                                    self._wg_scratch, self._wg_scratch.numel() * 4, self.B, *d, cout, st)
+        else:
+            lib.ssr_conv3d_wgrad_ref(x1, c1, x2, c2, dy, self.g[name + '/kernel'], self.g[name + '/bias'], self.B, *d,
+                                     cout, self.k, st)
+
+    def _wgrad_tc_ok(self, c1, c2, cout):
+        return getattr(self, 'wgrad_tc', False) and (c1 % 8 == 0) and (c2 % 8 == 0) and cout % 8 == 0
+
+    def _packed_w(self, name, mode, c1, c2, cout):
+        """packed (K-major, zero padded) copy of a kernel for the tcgen05 path; refreshed after every optimiser step."""
+        if self._packed_dirty:
+            self._packed_valid = set()
+            self._packed_dirty = False
+        key = (name, mode)
+        if key not in self._packed:
+            n = lib.ssr_conv3d_packed_size(c1, c2, cout, mode)
+            self._packed[key] = torch.empty(n, dtype=torch.float32, device=self.device)
+        if key not in self._packed_valid:
+            lib.ssr_conv3d_pack_weights(self.p[name + '/kernel'], self._packed[key], c1, c2, cout, mode, stream_ptr())
+            self._packed_valid.add(key)
+        return self._packed[key]
+
+    # -------------------------------------------------------------------------------------------------------------
+    def forward(self, image, training=True):
+        """image: float32 cuda tensor [B, X, Y, Z, Cin] (contiguous) -> pred [B, X, Y, Z, nb_labels]."""
+        st = stream_ptr()
+        B, L, F = self.B, self.L, self.feats
+        assert image.is_cuda and image.dtype == torch.float32 and image.is_contiguous()
+        assert list(image.shape) == [B] + self.dims + [self.cin], image.shape
+        self._image = image
+        x, cx = image, self.cin
+        for l in range(L):
+            self._conv_fwd('unet_conv_downarm_%d_0' % l, x, cx, None, 0, self.h0[l], l, F[l])
+            self._conv_fwd('unet_conv_downarm_%d_1' % l, self.h0[l], F[l], None, 0, self.h1[l], l, F[l])
+            bn = 'unet_bn_down_%d' % l
+            self._bn_stats(bn, self.h1[l], self.nvox[l], F[l], self.stats_enc[l], training)
+            if l < L - 1:
+                lib.ssr_bn_apply(self.h1[l], self.inp[l + 1], self.stats_enc[l], B, *self.ldims[l], F[l], 1, 0, 0, st)
+                x, cx = self.inp[l + 1], F[l]
+        prev, prev_stats, prev_l = self.h1[L - 1], self.stats_enc[L - 1], L - 1
+        for d in range(L - 1):
+            l = L - 2 - d
+            lib.ssr_bn_apply(prev, self.u[l], prev_stats, B, *self.ldims[prev_l], F[prev_l], 2, 0, 0, st)
+            self._conv_fwd('unet_conv_uparm_%d_0' % (L + d), self.h1[l], F[l], self.u[l], F[l + 1], self.g0[l], l, F[l])
+            self._conv_fwd('unet_conv_uparm_%d_1' % (L + d), self.g0[l], F[l], None, 0, self.g1[l], l, F[l])
+            self._bn_stats('unet_bn_up_%d' % d, self.g1[l], self.nvox[l], F[l], self.stats_dec[l], training)
+            prev, prev_stats, prev_l = self.g1[l], self.stats_dec[l], l
+        lib.ssr_bn_apply(self.g1[0], self.feat, self.stats_dec[0], B, *self.ldims[0], F[0], 0, 0, 0, st)
+        return self.feat
+
+    def _bn_stats(self, bn, x, nvox, C, stats, training):
+        st = stream_ptr()
+        if training:
+            lib.ssr_bn_stats(x, nvox, C, self.p[bn + '/gamma'], self.p[bn + '/beta'], self.moving[bn + '/moving_mean'],
+                             self.moving[bn + '/moving_variance'], BN_EPS, BN_MOMENTUM, self.sums, stats, st)
+        else:
+            lib.ssr_bn_stats_inference(C, self.p[bn + '/gamma'], self.p[bn + '/beta'], self.moving[bn + '/moving_mean'],
+                                       self.moving[bn + '/moving_variance'], BN_EPS, stats, st)
+
+    def predict(self, image):
+        """inference-mode forward (moving BN statistics) -> [B,X,Y,Z,nb_labels] tensor."""
+        self.forward(image, training=False)
+        zeros = torch.zeros((self.nvox[0], self.nb_labels), dtype=torch.float32, device=self.device)
+        self._head(zeros, 'l1', None, None, train=False)
+        return self.pred.view(self.B, *self.dims, self.nb_labels)
+
+    def _head(self, target, metric, residual, loss_cropping, train):
+        import ctypes
+        st = stream_ptr()
+        res_idx = crop_size = crop_begin = None                      # HOST int arrays (kept alive on self)
+        if residual is not None:
+            residual = [int(c) for c in residual]
+            assert len(residual) == self.nb_labels and all(0 <= c < self.cin for c in residual)
+            self._res_keep = (ctypes.c_int * 4)(*(residual + [0] * (4 - len(residual))))
+            res_idx = ctypes.cast(self._res_keep, ctypes.c_void_p)
+        if loss_cropping is not None:
+            lc = [int(loss_cropping)] * 3 if isinstance(loss_cropping, (int, np.integer)) else [int(v) for v in loss_cropping]
+            cb = [int((self.dims[i] - lc[i]) / 2) for i in range(3)]
+            self._crop_keep = ((ctypes.c_int * 3)(*lc), (ctypes.c_int * 3)(*cb))
+            crop_size = ctypes.cast(self._crop_keep[0], ctypes.c_void_p)
+            crop_begin = ctypes.cast(self._crop_keep[1], ctypes.c_void_p)
+        name = 'unet_likelihood'
+        lib.ssr_head_loss(self.feat, self.p[name + '/kernel'], self.p[name + '/bias'],
+                          self._image if residual is not None else None, self.cin, res_idx, target, self.pred,
+                          self.dbn_dec[0] if train else None, self.g[name + '/kernel'] if train else None,
+                          self.g[name + '/bias'] if train else None, self.loss_buf, self.gout if train else None,
+                          self.B, *self.dims, self.feats[0], self.nb_labels, 1 if metric == 'l1' else 2, crop_size,
+                          crop_begin, 1 if train else 0, st)
+
+    # -------------------------------------------------------------------------------------------------------------
+    def loss_and_grad(self, image, target, metric='l1', work_with_residual_channel=None, loss_cropping=None):
+        """forward (training BN) + loss + full backward.  Gradients are left in self.grads (flat).  Returns the loss
+        as a 1-element float64 cuda tensor (no host sync)."""
+        assert metric in ('l1', 'l2'), "regression_metric %r is out of scope of this build ('l1'/'l2' only)" % metric
+        self._alloc_bwd()
+        st = stream_ptr()
+        B, L, F = self.B, self.L, self.feats
+        assert target.is_cuda and target.dtype == torch.float32 and target.is_contiguous()
+        self.forward(image, training=True)
+        self.grads.zero_()
+        self._head(target, metric, work_with_residual_channel, loss_cropping, train=True)
+        # ---- decoder, shallow to deep -----------------------------------------------------------------------
+        for l in range(L - 1):
+            d = L - 2 - l
+            c0, c1n = 'unet_conv_uparm_%d_0' % (L + d), 'unet_conv_uparm_%d_1' % (L + d)
+            bn = 'unet_bn_up_%d' % d
+            lib.ssr_bn_bwd(self.dbn_dec[l], self.g1[l], self.stats_dec[l], self.nvox[l], F[l], None, 0, 0, 1, self.ga[l],
+                           self.g[bn + '/gamma'], self.g[bn + '/beta'], self.sums, st)
+            self._conv_wgrad(c1n, self.g0[l], F[l], None, 0, self.ga[l], l, F[l])
+            self._conv_dgrad(c1n, self.ga[l], self.gb[l], l, F[l], F[l])
+            lib.ssr_elu_bwd(self.gb[l], 0, 0, self.g0[l], None, self.nvox[l], F[l], self.gb[l], st)
+            self._conv_wgrad(c0, self.h1[l], F[l], self.u[l], F[l + 1], self.gb[l], l, F[l])
+            self._conv_dgrad(c0, self.gb[l], self.dcat[l], l, F[l] + F[l + 1], F[l])
+            tgt = self.dbn_dec[l + 1] if l + 1 <= L - 2 else self.dbn_bott
+            lib.ssr_upsample_bwd(self.dcat[l], F[l] + F[l + 1], F[l], B, *self.ldims[l + 1], F[l + 1], tgt, st)
+        # ---- encoder, deep to shallow -----------------------------------------------------------------------
+        for l in range(L - 1, -1, -1):
+            c0, c1n, bn = 'unet_conv_downarm_%d_0' % l, 'unet_conv_downarm_%d_1' % l, 'unet_bn_down_%d' % l
+            if l == L - 1:
+                lib.ssr_bn_bwd(self.dbn_bott, self.h1[l], self.stats_enc[l], self.nvox[l], F[l], None, 0, 0, 1,
+                               self.ga[l], self.g[bn + '/gamma'], self.g[bn + '/beta'], self.sums, st)
+            else:
+                lib.ssr_maxpool_bwd(self.dp[l + 1], self.h1[l], self.stats_enc[l], B, *self.ldims[l], F[l], self.ga[l],
+                                    st)
+                lib.ssr_bn_bwd(self.ga[l], self.h1[l], self.stats_enc[l], self.nvox[l], F[l], self.dcat[l],
+                               F[l] + F[l + 1], 0, 1, self.ga[l], self.g[bn + '/gamma'], self.g[bn + '/beta'],
+                               self.sums, st)
+            self._conv_wgrad(c1n, self.h0[l], F[l], None, 0, self.ga[l], l, F[l])
+            self._conv_dgrad(c1n, self.ga[l], self.gb[l], l, F[l], F[l])
+            lib.ssr_elu_bwd(self.gb[l], 0, 0, self.h0[l], None, self.nvox[l], F[l], self.gb[l], st)
+            x, cx = (self._image, self.cin) if l == 0 else (self.inp[l], F[l - 1])
+            self._conv_wgrad(c0, x, cx, None, 0, self.gb[l], l, F[l])
+            if l > 0:
+                self._conv_dgrad(c0, self.gb[l], self.dp[l], l, F[l - 1], F[l])
+        return self.loss_buf
+
+    def adam_step(self, lr=1e-4, lr_decay=0., beta1=.9, beta2=.999, eps=1e-7, grad_scale=1.):
+        """keras.optimizers.Adam.get_updates (Keras 2.3.1) on the flat buffers, one launch."""
+        lr_eff = lr
+        if lr_decay > 0:
+            lr_eff = lr * (1. / (1. + lr_decay * self.iterations))
+        t = self.iterations + 1
+        lr_t = lr_eff * (math.sqrt(1. - beta2 ** t) / (1. - beta1 ** t))
+        lib.ssr_adam_flat(self.params, self.grads, self.adam_m, self.adam_v, self.n_params, lr_t, beta1, beta2, eps,
+                          grad_scale, stream_ptr())
+        self.iterations = t
+        self._packed_dirty = True

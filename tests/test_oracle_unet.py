@@ -1,0 +1,95 @@
+"""CPU tests pinning the torch U-Net oracle: topology / parameter count of the reference model, Keras layer names,
+analytic known-answer cases, and the Keras Adam / BN-moving-average formulas."""
+import math
+
+import numpy as np
+import torch
+
+from oracle import unet as OU
+
+
+def test_parameter_count_and_names():
+    """13,242,049 parameters for Cin=1 (13,237,633 conv + 4,416 BN), Keras layer names (3.4)."""
+    specs = OU.layer_specs(1)
+    n_conv = sum(27 * ci * co + co for n, k, ci, co in specs if k == 'conv') + sum(ci * co + co for n, k, ci, co in specs if k == 'conv1')
+    n_bn = sum(4 * co for n, k, ci, co in specs if k == "bn")   # gamma, beta + non-trainable moving mean/variance
+    assert n_conv == 13237633 and n_bn == 4416 and n_conv + n_bn == 13242049
+    names = [n for n, *_ in specs]
+    assert names[0] == 'unet_conv_downarm_0_0' and 'unet_bn_down_4' in names and 'unet_conv_uparm_8_1' in names
+    assert 'unet_bn_up_3' in names and names[-1] == 'unet_likelihood'
+    cins = {n: ci for n, k, ci, co in specs}
+    assert cins['unet_conv_uparm_5_0'] == 576 and cins['unet_conv_uparm_8_0'] == 72      # concat widths (8a-U2)
+    from synthsr_b200.unet import layer_specs
+    assert layer_specs(1) == specs and layer_specs(2, 8, 3) == OU.layer_specs(2, 8, 3)
+
+
+def test_zero_weights_output_is_bias():
+    p = OU.init_params(0, 1, nb_features=4, nb_levels=2)
+    for k in p:
+        if k.endswith('kernel'):
+            p[k].zero_()
+    p['unet_likelihood/bias'].fill_(0.25)
+    x = torch.rand(1, 8, 8, 8, 1)
+    y = OU.forward(p, x, training=True, nb_levels=2)
+    assert y.shape == (1, 8, 8, 8, 1) and torch.allclose(y, torch.full_like(y, 0.25))
+
+
+def test_skip_is_pre_bn_conv_output():
+    """the skip tensor is the second conv's post-ELU, pre-BN output (models.py:431-432): scaling BN gamma of level 0
+    must not change the skip half of the decoder input."""
+    torch.manual_seed(0)
+    p = OU.init_params(1, 1, nb_features=4, nb_levels=2)
+    x = torch.rand(1, 8, 8, 8, 1)
+    acts = {}
+    OU.forward(p, x, nb_levels=2, activations=acts)
+    skip = acts['unet_conv_downarm_0_1'].clone()
+    p['unet_bn_down_0/gamma'] *= 3.
+    acts2 = {}
+    OU.forward(p, x, nb_levels=2, activations=acts2)
+    assert torch.equal(acts2['unet_conv_downarm_0_1'], skip)
+
+
+def test_maxpool_same_odd():
+    x = torch.arange(27, dtype=torch.float32).reshape(1, 1, 3, 3, 3)
+    y = OU._maxpool_same(x)
+    assert y.shape == (1, 1, 2, 2, 2) and y[0, 0, 1, 1, 1] == 26 and y[0, 0, 0, 0, 0] == 13
+
+
+def test_adam_and_bn_moving_formulas():
+    p = OU.init_params(2, 1, nb_features=4, nb_levels=2)
+    p = {k: v.double() for k, v in p.items()}
+    opt = OU.adam_init(p)
+    x, t = torch.rand(1, 8, 8, 8, 1, dtype=torch.float64), torch.rand(1, 8, 8, 8, 1, dtype=torch.float64)
+    p0 = {k: v.clone() for k, v in p.items()}
+    # forward() default nb_levels=5 does not fit this tiny net: use the generic step below
+    names = OU.trainable_names(p)
+    leaves = {k: p[k].clone().requires_grad_(True) for k in names}
+    q = {k: leaves.get(k, p[k]) for k in p}
+    new = {}
+    acts = {}
+    pred = OU.forward(q, x, nb_levels=2, new_stats=new, activations=acts)
+    loss = OU.loss_fn(pred, x, t)
+    g = torch.autograd.grad(loss, [leaves[k] for k in names])
+    # first Adam step: m = .1 g, v = .001 g^2, lr_t = lr*sqrt(.001)/.1 -> update = lr * g/(|g| + eps*...) ~ lr*sign(g)
+    lr = 1e-3
+    lr_t = lr * math.sqrt(1 - .999) / (1 - .9)
+    k0 = names[0]
+    upd = lr_t * (.1 * g[0]) / ((.001 * g[0] ** 2).sqrt() + 1e-7)
+    assert torch.allclose(upd.abs().max(), torch.tensor(lr, dtype=torch.float64), rtol=1e-3)
+    # BN moving variance uses n/(n-(1+eps)) (Keras 2.3.1)
+    h = acts['unet_conv_downarm_0_1']
+    n = h.numel() / h.shape[1]
+    var = h.var(dim=(0, 2, 3, 4), unbiased=False)
+    exp = .99 * 1. + .01 * var * n / (n - (1 + 1e-3))
+    assert torch.allclose(new['unet_bn_down_0/moving_variance'], exp.detach())
+
+
+def test_train_step_reduces_loss():
+    torch.manual_seed(0)
+    p = OU.init_params(3, 1)
+    opt = OU.adam_init(p)
+    x, t = torch.rand(1, 16, 16, 16, 1), torch.rand(1, 16, 16, 16, 1)
+    l0, _, _ = OU.train_step(p, opt, x, t, lr=1e-3)
+    for _ in range(3):
+        l1, _, _ = OU.train_step(p, opt, x, t, lr=1e-3)
+    assert l1 < l0 and opt['iterations'] == 4

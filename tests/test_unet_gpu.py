@@ -1,0 +1,143 @@
+"""GPU parity of the U-Net training step (CUDA kernels through the C ABI) against the torch-CPU oracle.
+
+conv_impl='ref' (exact fp32 CUDA-core convolutions): every activation, the loss, every gradient and the Adam update
+must match the float64 oracle to ~1e-5 relative.  conv_impl='tc' (tcgen05 TF32 convolutions): bar 1e-3 relative
+(north_star) on the prediction / loss, measured against the same oracle; gradients are compared per tensor with a
+relative L2 bar.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
+
+
+def _rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
+
+
+def _setup(dims, cin, nb_features, nb_levels, batch, impl, seed=0, nb_labels=1):
+    from oracle import unet as OU
+    from synthsr_b200.unet import UNet3D
+    net = UNet3D(dims + [cin], nb_features=nb_features, nb_levels=nb_levels, nb_labels=nb_labels, batchsize=batch,
+                 conv_impl=impl, seed=seed)
+    sd = net.state_dict()
+    params = {k: torch.tensor(v, dtype=torch.float64) for k, v in sd.items()}
+    rng = np.random.default_rng(seed + 1)
+    image = rng.uniform(0, 1, size=(batch, *dims, cin)).astype(np.float32)
+    target = rng.uniform(0, 1, size=(batch, *dims, nb_labels)).astype(np.float32)
+    return net, params, image, target, OU
+
+
+def _one_step(dims, cin, nb_features, nb_levels, batch, impl, tol, gtol, **loss_kw):
+    net, params, image, target, OU = _setup(dims, cin, nb_features, nb_levels, batch, impl)
+    img_t, tgt_t = torch.from_numpy(image).cuda(), torch.from_numpy(target).cuda()
+    opt = OU.adam_init({k: v for k, v in params.items()})
+    # oracle step (float64)
+    p0 = {k: v.clone() for k, v in params.items()}
+    loss_o, grads_o, pred_o = _oracle_step(OU, params, opt, image, target, nb_levels, loss_kw)
+    # CUDA step
+    loss = net.loss_and_grad(img_t, tgt_t, **loss_kw)
+    torch.cuda.synchronize()
+    pred = net.pred.view(batch, *dims, -1).cpu().numpy()
+    assert _rel(pred, pred_o.numpy()) < tol, ('pred', _rel(pred, pred_o.numpy()))
+    assert abs(loss.item() - loss_o) / abs(loss_o) < tol, (loss.item(), loss_o)
+    worst = 0
+    for k in grads_o:
+        e = _rel_l2(net.g[k].cpu().numpy(), grads_o[k].numpy())
+        worst = max(worst, e)
+        assert e < gtol, ('grad', k, e)
+    net.adam_step(lr=1e-3)
+    torch.cuda.synchronize()
+    for k in grads_o:
+        upd, upd_o = net.p[k].cpu().numpy() - p0[k].numpy(), params[k].numpy() - p0[k].numpy()
+        assert _rel_l2(upd, upd_o) < max(gtol * 20, 2e-3), ('adam', k, _rel_l2(upd, upd_o))
+    for k in net.moving:
+        assert _rel(net.moving[k].cpu().numpy(), params[k].numpy()) < 1e-4, ('moving', k)
+    return worst
+
+
+def _oracle_step(OU, params, opt, image, target, nb_levels, loss_kw):
+    """train_step for nb_levels != 5 (forward takes nb_levels)."""
+    import math
+    names = OU.trainable_names(params)
+    leaves = {k: params[k].detach().clone().requires_grad_(True) for k in names}
+    p = {k: leaves.get(k, params[k]) for k in params}
+    new_stats = {}
+    img, tgt = torch.tensor(image, dtype=torch.float64), torch.tensor(target, dtype=torch.float64)
+    pred = OU.forward(p, img, training=True, nb_levels=nb_levels, new_stats=new_stats)
+    loss = OU.loss_fn(pred, img, tgt, **loss_kw)
+    grads = dict(zip(names, torch.autograd.grad(loss, [leaves[k] for k in names])))
+    t = opt['iterations'] + 1
+    lr_t = 1e-3 * (math.sqrt(1. - .999 ** t) / (1. - .9 ** t))
+    with torch.no_grad():
+        for k in names:
+            g = grads[k]
+            opt['m'][k] = .9 * opt['m'][k] + .1 * g
+            opt['v'][k] = .999 * opt['v'][k] + .001 * g * g
+            params[k] = params[k] - lr_t * opt['m'][k] / (opt['v'][k].sqrt() + 1e-7)
+        for k, v in new_stats.items():
+            params[k] = v
+    opt['iterations'] = t
+    return float(loss.detach()), grads, pred.detach()
+
+
+def test_ref_small_3level_batch2():
+    _one_step([16, 16, 16], 1, 8, 3, 2, 'ref', 2e-5, 2e-4)
+
+
+def test_ref_two_input_channels_residual_crop_l2():
+    """Hyperfine-like head: 2 input channels, residual on image channel 0, loss cropping, l2."""
+    _one_step([16, 24, 16], 2, 8, 3, 1, 'ref', 2e-5, 2e-4, metric='l2', work_with_residual_channel=[0], loss_cropping=12)
+
+
+def test_ref_full_topology_5level_32cube():
+    """the reference topology (24 features, 5 levels) at 32^3."""
+    _one_step([32, 32, 32], 1, 24, 5, 1, 'ref', 5e-5, 5e-4)
+
+
+def test_tc_matches_ref_kernels():
+    """tcgen05 TF32 convolution vs the exact fp32 kernel on the same inputs (layer-level cross-check)."""
+    from synthsr_b200._lib import lib, stream_ptr
+    rng = np.random.default_rng(0)
+    for (d, c1, c2, co) in [([16, 16, 16], 24, 0, 24), ([16, 32, 16], 24, 48, 24), ([8, 16, 24], 48, 0, 96),
+                            ([10, 10, 10], 192, 0, 384), ([16, 16, 8], 96, 192, 96), ([8, 8, 8], 8, 0, 8)]:
+        B = 1
+        nv = B * int(np.prod(d))
+        x1 = torch.from_numpy(rng.normal(size=(nv, c1)).astype(np.float32)).cuda()
+        x2 = torch.from_numpy(rng.normal(size=(nv, max(c2, 1))).astype(np.float32)).cuda() if c2 else None
+        w = torch.from_numpy((rng.normal(size=(3, 3, 3, c1 + c2, co)) / np.sqrt(27 * (c1 + c2))).astype(np.float32)).cuda()
+        b = torch.from_numpy(rng.normal(size=co).astype(np.float32)).cuda()
+        y_ref = torch.empty((nv, co), dtype=torch.float32, device='cuda')
+        y_tc = torch.full((nv, co), float('nan'), dtype=torch.float32, device='cuda')
+        st = stream_ptr()
+        lib.ssr_conv3d_fwd_ref(x1, c1, x2, c2, w, b, y_ref, B, *d, co, 3, 1, st)
+        wp = torch.empty(lib.ssr_conv3d_packed_size(c1, c2, co, 0), dtype=torch.float32, device='cuda')
+        lib.ssr_conv3d_pack_weights(w, wp, c1, c2, co, 0, st)
+        lib.ssr_conv3d_fwd_tc(x1, c1, x2, c2, wp, b, y_tc, B, *d, co, 1, st)
+        torch.cuda.synchronize()
+        err = (y_tc - y_ref).abs().max().item() / y_ref.abs().max().item()
+        assert err < 2e-3, (d, c1, c2, co, err)
+        # data gradient = forward conv with flipped/transposed kernel (mode 1)
+        dy = torch.from_numpy(rng.normal(size=(nv, co)).astype(np.float32)).cuda()
+        dx_ref = torch.empty((nv, c1 + c2), dtype=torch.float32, device='cuda')
+        dx_tc = torch.full((nv, c1 + c2), float('nan'), dtype=torch.float32, device='cuda')
+        scratch = torch.empty(w.numel(), dtype=torch.float32, device='cuda')
+        lib.ssr_conv3d_dgrad_ref(dy, w, scratch, dx_ref, B, *d, c1 + c2, co, 3, st)
+        wd = torch.empty(lib.ssr_conv3d_packed_size(c1 + c2, 0, co, 1), dtype=torch.float32, device='cuda')
+        lib.ssr_conv3d_pack_weights(w, wd, c1 + c2, 0, co, 1, st)
+        lib.ssr_conv3d_fwd_tc(dy, co, None, 0, wd, None, dx_tc, B, *d, c1 + c2, 0, st)
+        torch.cuda.synchronize()
+        err = (dx_tc - dx_ref).abs().max().item() / dx_ref.abs().max().item()
+        assert err < 2e-3, ('dgrad', d, c1, c2, co, err)
+
+
+def test_tc_training_step_32cube():
+    """full step with tcgen05 convolutions at the reference topology; bar 1e-3 on prediction and loss."""
+    _one_step([32, 32, 32], 1, 24, 5, 1, 'tc', 1e-3, 2e-2)
