@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""Headline benchmark (BASELINE.json): training volumes/sec on 160^3 single-channel volumes, 5-level 24-feature U-Net,
+generator + U-Net + Adam every step, at N GPUs of one node (data parallel, one process per GPU).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...        # CPU arm: the oracle restatement of the reference on the host cores
+
+Prints ONE JSON line (rank 0).  A "step" is one pass of the hot path (generate a synthetic scan pair from a label map,
+U-Net forward/backward, L1 loss, Adam) over one mini-batch of 1 volume per GPU.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SIZE = 160
+TRAINING_DEFAULTS = dict(scaling_bounds=0.15, rotation_bounds=15, shearing_bounds=0.02, translation_bounds=5,
+                         nonlin_std=4., nonlin_shape_factor=0.03125, bias_field_std=.3, bias_shape_factor=0.03125,
+                         blur_range=1.15, build_reliability_maps=False, output_div_by_n=32)   # SynthSR/training.py:57-73
+
+
+def conv_flops_per_step(size, cin=1):
+    """algorithmic conv FLOPs of one training step: fwd + dgrad + wgrad."""
+    from synthsr_b200.unet import layer_specs
+    v = float(size) ** 3
+    fwd, first = 0., None
+    lvl = {}
+    for name, kind, ci, co in layer_specs(cin):
+        if kind == 'bn':
+            continue
+        if 'downarm' in name:
+            l = int(name.split('_')[3])
+        elif 'uparm' in name:
+            l = 8 - int(name.split('_')[3])
+        else:
+            l = 0
+        k3 = 27 if kind == 'conv' else 1
+        f = 2. * k3 * ci * co * v / 8 ** l
+        fwd += f
+        if first is None:
+            first = f
+    return fwd, 3 * fwd - first
+
+
+def make_inputs(size, n_maps=2, seed=0):
+    from synthsr_b200.synthetic import GEN_CLASSES, GEN_LABELS, phantom_labels, synthetic_priors
+    maps = []
+    for i in range(n_maps):
+        lo = phantom_labels([size // 2] * 3, GEN_LABELS, seed=seed + i)
+        maps.append(np.ascontiguousarray(np.repeat(np.repeat(np.repeat(lo, 2, 0), 2, 1), 2, 2)[:size, :size, :size]))
+    pm, ps = synthetic_priors(int(GEN_CLASSES.max()) + 1, 1, seed)
+    return maps, pm, ps, GEN_LABELS, GEN_CLASSES
+
+
+def draw_gmm(rng, pm, ps, classes):
+    """SynthSR/model_inputs.py:118-123 ('normal' priors, negatives clipped)."""
+    m = np.clip(rng.normal(pm[0], pm[1]), 0, None)[classes]
+    s = np.clip(rng.normal(ps[0], ps[1]), 0, None)[classes]
+    return m[None, :, None].astype(np.float32), s[None, :, None].astype(np.float32)
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: 'sw_power_cap',
+                 nv.nvmlClocksThrottleReasonHwSlowdown: 'hw_slowdown',
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: 'sw_thermal_slowdown',
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: 'hw_thermal_slowdown',
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: 'hw_power_brake_slowdown'}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': []}
+        return {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
+
+
+def cpu_reference_steps(size, steps, warmup, threads):
+    """the reference's algorithm on the host cores (oracle restatement; TensorFlow itself is not installable here):
+    generator (NumPy) + U-Net fwd/bwd + Adam (torch CPU fp32).  Returns seconds per step for a size^3 volume."""
+    import torch
+    from oracle import generator as OG
+    from oracle import unet as OU
+    from synthsr_b200.draws import sample_draws
+    from synthsr_b200.generator import GeneratorPlan
+    torch.set_num_threads(threads)
+    maps, pm, ps, gl, gc = make_inputs(size, 1)
+    cfg = dict(TRAINING_DEFAULTS)
+    plan = GeneratorPlan([size] * 3, True, 0, gl, None, 1., None, **cfg)
+    rng = np.random.default_rng(0)
+    params = OU.init_params(0, 1)
+    opt = OU.adam_init(params)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        draws = sample_draws(rng, plan, 1, gmm_noise=True)
+        m, s = draw_gmm(rng, pm, ps, gc)
+        image, target = OG.labels_to_image(dict(cfg, generation_labels=gl), [maps[0][None, ..., None], m, s], draws)
+        OU.train_step(params, opt, torch.from_numpy(image), torch.from_numpy(target), lr=1e-4)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return float(np.mean(times))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--size', type=int, default=SIZE)
+    ap.add_argument('--conv-impl', default='tc', choices=['tc', 'ref'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    fwd_f, step_f = conv_flops_per_step(args.size)
+    metric = 'training volumes/sec (160^3, 24-ch 5-level U-Net, generator+U-Net+Adam step)'
+    config = {'workload': '%d^3 single-channel label map -> generator (training() defaults) -> 5-level 24-feature '
+                          'U-Net fwd/bwd, L1, Adam; batch 1 per GPU (BASELINE configs[1]/[2])' % args.size,
+              'global_batch': args.gpus, 'volume': [args.size] * 3, 'parallelism': 'dp%d' % args.gpus,
+              'l2_policy': 'per-step working set (>4 GB of activations) exceeds the 126 MB L2; no explicit flush'}
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        threads = os.cpu_count() or 1
+        sample = 64                      # bounded sample: a 64^3 step is 1/15.6 of the 160^3 workload (linear in voxels)
+        warm = min(args.warmup, 1)
+        sec = cpu_reference_steps(sample, args.steps, warm, threads)
+        vps = 1.0 / (sec * (args.size / sample) ** 3)
+        out = {'metric': metric, 'value': vps, 'unit': 'volumes/s', 'n_gpus': args.gpus, 'steps': args.steps,
+               'warmup': warm, 'ms_per_step': 1e3 / vps, 'higher_is_better': True, 'scaling': 'weak',
+               'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config, 'impl': 'reference',
+               'cpu_baseline': {'value': vps, 'unit': 'volumes/s', 'cores': threads, 'kind': 'port',
+                                'sample': 'oracle restatement (NumPy generator + torch-CPU fp32 U-Net step) on %d^3 '
+                                          'sub-volumes, scaled by voxel count to %d^3; reference TF-CPU: not run '
+                                          '(TensorFlow 2.0 not installable)' % (sample, args.size)},
+               'e2e': {'value': vps, 'unit': 'volumes/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(out))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from synthsr_b200._lib import lib
+    from synthsr_b200.generator import GeneratorPlan
+    from synthsr_b200.trainer import TrainingEngine
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    maps, pm, ps, gl, gc = make_inputs(args.size, 2, seed=rank)
+    plan = GeneratorPlan([args.size] * 3, True, 0, gl, None, 1., None, **TRAINING_DEFAULTS)
+    eng = TrainingEngine(plan, batchsize=1, conv_impl=args.conv_impl, seed=0, rank=rank, world_size=world)
+    dev_maps = [torch.from_numpy(m[None]).cuda() for m in maps]
+    pinned = [torch.from_numpy(m[None]).pin_memory() for m in maps]
+    rng = np.random.default_rng(1234 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_steps(n, host_inputs):
+        loss = None
+        for i in range(n):
+            m, s = draw_gmm(rng, pm, ps, gc)
+            if host_inputs:       # e2e: labels start in pinned host memory every step, loss is read back every step
+                lab = pinned[i % len(pinned)].cuda(non_blocking=True)
+                loss = eng.train_step(lab, m, s).item()
+            else:
+                loss = eng.train_step(dev_maps[i % len(dev_maps)], m, s)
+        return loss
+
+    def timed(n, host_inputs):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        l0 = lib.ssr_launch_count()
+        e0.record()
+        run_steps(n, host_inputs)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), lib.ssr_launch_count() - l0
+
+    run_steps(max(args.warmup, 3), False)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms, launches = timed(args.steps, False)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    value = world * args.steps / (ms / 1e3)
+    sg_before = eng.gen.stage.bytes_moved
+    ms_e2e, _ = timed(args.steps, True)
+    e2e = world * args.steps / (ms_e2e / 1e3)
+    h2d = maps[0].nbytes + (eng.gen.stage.bytes_moved - sg_before) // max(args.steps, 1)
+
+    # ---- roofline of the dominant kernel class: live CUDA-event timing of every convolution launch ------------
+    eng.net.prof = []
+    run_steps(2, False)
+    torch.cuda.synchronize()
+    agg = {}
+    for kind, fl, a, b in eng.net.prof:
+        t, f, n = agg.get(kind, (0., 0., 0))
+        agg[kind] = (t + a.elapsed_time(b), f + fl, n + 1)
+    eng.net.prof = None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = peaks.get('bf16_tflops_sustained', 1590.0)
+    peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained; TF32 runs at half the bf16 rate)' if peaks else \
+        'fallback 1590 TF/s bf16 (B200_PROFILING.md)'
+    tc_ms = sum(agg[k][0] for k in agg if k.endswith('_tc'))
+    tc_fl = sum(agg[k][1] for k in agg if k.endswith('_tc'))
+    achieved = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.
+    roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+                'traffic': None, 'peak_source': peak_src, 'kernel': 'conv3d_tc_kernel + wgrad_tc_kernel (tcgen05 kind::tf32)',
+                'frac_of_tf32_peak': achieved / (peak / 2),
+                'per_kind': {k: {'ms_per_step': agg[k][0] / 2, 'tflops': agg[k][1] / (agg[k][0] * 1e-3) / 1e12 if agg[k][0] else 0.,
+                                 'launches_per_step': agg[k][2] // 2} for k in sorted(agg)},
+                'conv_share_of_step': (sum(v[0] for v in agg.values()) / 2) / (ms / args.steps)}
+    out = {'metric': metric, 'value': value, 'unit': 'volumes/s', 'n_gpus': args.gpus, 'steps': args.steps,
+           'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+           'vs_baseline': None, 'dtype': 'tf32' if args.conv_impl == 'tc' else 'f32', 'data': 'synthetic',
+           'config': config, 'clocks': sampler.summary(), 'gpu_launches': int(launches),
+           'e2e': {'value': e2e, 'unit': 'volumes/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 8},
+           'roofline': roofline, 'conv_gflop_per_step': step_f / 1e9}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample = 64
+        sec = cpu_reference_steps(sample, 2, 1, threads)
+        vps = 1.0 / (sec * (args.size / sample) ** 3)
+        out['cpu_baseline'] = {'value': vps, 'unit': 'volumes/s', 'cores': threads, 'kind': 'port',
+                               'sample': '2 oracle steps (NumPy generator + torch-CPU fp32 U-Net fwd/bwd/Adam) on a 64^3 '
+                                         'volume, scaled by voxel count to %d^3' % args.size}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,10 +1,758 @@
-// placeholder -- replaced by the tcgen05 implementation
+// 3x3x3 'same' convolution on the 5th-generation tensor cores (tcgen05, TF32 operands, FP32 accumulate in TMEM).
+//
+// Replaces cuDNN-via-TF for KL.Conv3D (ext/neuron/models.py:316,444): forward and, with flipped/transposed packed
+// weights, the data gradient.  Implicit GEMM, nothing is materialised:
+//
+//   GEMM   D[M x N] += A[M x K] * B[N x K]^T      M = 128 output voxels (16 along d1 x 8 along d2 at one d0)
+//                                                 N = output channels (NT <= 192 per CTA)
+//                                                 K = (tap, input-channel chunk of 32)
+//   A      activation "slab": one TMA box (32 ch, 8 d2, 18 d1, 1 d0) of the NDHWC tensor -> 144 rows x 128 B in
+//          shared memory, SWIZZLE_128B.  The three d1 taps are three UMMA descriptors into the SAME slab
+//          (+k1 * 1024 B, swizzle phase preserved), the d2 tap is a shifted TMA box, the d0 tap selects which of
+//          the CTA's TZ accumulators the slab feeds.  Out-of-bounds parts of a box are zero filled by TMA =
+//          'same' padding, and so are channels beyond C when C is not a multiple of 32.
+//   B      packed weights [chunk][k2][k0][k1][Npad][32] (K-major, zero padded), TMA box (32, NT) per tap.
+//   D      TZ accumulators of NT fp32 columns in TMEM (TZ*NT <= 512); epilogue = tcgen05.ld -> +bias -> ELU -> store.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue.  mbarrier rings: A slabs (SA stages), B tap groups (2 stages), one "accumulators ready".
 #include "common.cuh"
-extern "C" {
-int ssr_conv3d_pack_weights(const float*, float*, int, int, int, int, void*) { ssr_set_error("tc path not built"); return SSR_ERR_UNSUPPORTED; }
-long long ssr_conv3d_packed_size(int, int, int, int) { return 0; }
-int ssr_conv3d_fwd_tc(const float*, int, const float*, int, const float*, const float*, float*, int, int, int, int, int, int, void*) { ssr_set_error("tc path not built"); return SSR_ERR_UNSUPPORTED; }
-int ssr_conv3d_wgrad_tc(const float*, int, const float*, int, const float*, float*, float*, float*, long long, int, int, int, int, int, void*) { ssr_set_error("tc path not built"); return SSR_ERR_UNSUPPORTED; }
-long long ssr_conv3d_wgrad_scratch_bytes(int, int, int, int, int, int, int) { return 0; }
-int ssr_tc_selftest(void*) { ssr_set_error("tc path not built"); return SSR_ERR_UNSUPPORTED; }
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include <string>
+#include <cstdlib>
+
+extern "C" int ssr_channel_sum(const float* t, long long nvox, int C, float* out, void* stream);
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 8000000000LL) { printf("conv_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives when all previously issued tcgen05 ops of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B: 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);        // start address
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major) = 16 B
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset = 1024 B
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=F32, A=B=TF32, both K-major, M=128, N
+__device__ __forceinline__ uint32_t make_idesc_tf32(int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TM1 = 16, TM2 = 8;                  // output tile: 16 (d1) x 8 (d2) voxels = 128 GEMM rows
+constexpr int SLAB_ROWS = (TM1 + 2) * TM2;         // 144 rows x 128 B
+constexpr int SLAB_BYTES = SLAB_ROWS * 128;        // 18432 (multiple of 1024)
+constexpr int SB = 2;                              // B-group stages
+constexpr int MAX_CHUNKS = 24;
+
+struct TcGeom {
+  int B, D0, D1, D2;
+  int Cout;          // real output channels
+  int Npad;          // Cout rounded up to 16 (rows per tap in the packed weights)
+  int NT;            // output channels per CTA (multiple of 16, <= 192)
+  int TZ;            // accumulators (d0 planes) per CTA
+  int KG;            // d0 taps per B group: 3 (all 9 taps resident) or 1
+  int SA;            // A stages
+  int nchunks;
+  int n1tiles, n2tiles, n0tiles, nNtiles;
+  int act;
+  int tmem_cols;
+  unsigned char chunk_src[MAX_CHUNKS];    // 0: x1, 1: x2
+  unsigned char chunk_ks[MAX_CHUNKS];     // K-steps of 8 channels actually present in the chunk (1..4)
+  short chunk_c0[MAX_CHUNKS];             // first channel of the chunk inside its source
+};
+
+__device__ __forceinline__ bool slab_needed(const TcGeom& G, int z0, int k0g, int zin) {
+  const int din = z0 + k0g + zin - 1;
+  if (din < 0 || din >= G.D0) return false;
+  for (int kk = 0; kk < G.KG; ++kk) {
+    const int zo = zin - kk;
+    if (zo >= 0 && zo < G.TZ && z0 + zo < G.D0) return true;
+  }
+  return false;
+}
+__device__ __forceinline__ bool group_needed(const TcGeom& G, int z0, int k0g) {
+  for (int zin = 0; zin < G.TZ + G.KG - 1; ++zin)
+    if (slab_needed(G, z0, k0g, zin)) return true;
+  return false;
+}
+
+__global__ void __launch_bounds__(192, 1)
+conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_x2,
+                 const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias, float* __restrict__ y,
+                 const TcGeom G) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [A stages][B stages][barriers]
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  const int bgroup_bytes = G.KG * 3 * G.NT * 128;
+  uint8_t* sB = sA + (size_t)G.SA * SLAB_BYTES;
+  uint64_t* bars = (uint64_t*)(sB + (size_t)SB * bgroup_bytes);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = bars + G.SA;
+  uint64_t* fullB = bars + 2 * G.SA;
+  uint64_t* emptyB = fullB + SB;
+  uint64_t* accFull = emptyB + SB;
+  uint32_t* tmem_slot = (uint32_t*)(accFull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile decode
+  int t = blockIdx.x;
+  const int nt = t % G.nNtiles; t /= G.nNtiles;
+  const int t2 = t % G.n2tiles; t /= G.n2tiles;
+  const int t1 = t % G.n1tiles; t /= G.n1tiles;
+  const int t0 = t % G.n0tiles;
+  const int b = t / G.n0tiles;
+  const int x0 = t2 * TM2, y0 = t1 * TM1, z0 = t0 * G.TZ, n0 = nt * G.NT;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < G.SA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, 1); }
+    for (int i = 0; i < SB; ++i) { mbar_init(fullB + i, 1); mbar_init(emptyB + i, 1); }
+    mbar_init(accFull, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x1);
+    tma_prefetch_desc(&map_x2);
+    tma_prefetch_desc(&map_w);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)G.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int sa = 0, pa = 0, sb = 0, pb = 0;
+      for (int ch = 0; ch < G.nchunks; ++ch) {
+        const CUtensorMap* mx = G.chunk_src[ch] ? &map_x2 : &map_x1;
+        const int c0 = G.chunk_c0[ch];
+        for (int k2 = 0; k2 < 3; ++k2) {
+          for (int k0g = 0; k0g < 3; k0g += G.KG) {
+            if (!group_needed(G, z0, k0g)) continue;
+            mbar_wait(emptyB + sb, pb ^ 1);
+            mbar_expect_tx(fullB + sb, (uint32_t)bgroup_bytes);
+            for (int kk = 0; kk < G.KG; ++kk)
+              for (int k1 = 0; k1 < 3; ++k1) {
+                const int row = (((ch * 3 + k2) * 3 + (k0g + kk)) * 3 + k1) * G.Npad + n0;
+                tma_load_2d(&map_w, fullB + sb, sB + (size_t)sb * bgroup_bytes + (size_t)(kk * 3 + k1) * G.NT * 128, 0, row);
+              }
+            if (++sb == SB) { sb = 0; pb ^= 1; }
+            for (int zin = 0; zin < G.TZ + G.KG - 1; ++zin) {
+              if (!slab_needed(G, z0, k0g, zin)) continue;
+              mbar_wait(emptyA + sa, pa ^ 1);
+              mbar_expect_tx(fullA + sa, SLAB_BYTES);
+              tma_load_5d(mx, fullA + sa, sA + (size_t)sa * SLAB_BYTES, c0, x0 + k2 - 1, y0 - 1, z0 + k0g + zin - 1, b);
+              if (++sa == G.SA) { sa = 0; pa ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(G.NT);
+      int sa = 0, pa = 0, sb = 0, pb = 0;
+      uint32_t started = 0;
+      for (int ch = 0; ch < G.nchunks; ++ch) {
+        const int nks = G.chunk_ks[ch];
+        for (int k2 = 0; k2 < 3; ++k2) {
+          for (int k0g = 0; k0g < 3; k0g += G.KG) {
+            if (!group_needed(G, z0, k0g)) continue;
+            mbar_wait(fullB + sb, pb);
+            const uint32_t bbase = smem_u32(sB + (size_t)sb * bgroup_bytes);
+            for (int zin = 0; zin < G.TZ + G.KG - 1; ++zin) {
+              if (!slab_needed(G, z0, k0g, zin)) continue;
+              mbar_wait(fullA + sa, pa);
+              tc_fence_after();
+              const uint32_t abase = smem_u32(sA + (size_t)sa * SLAB_BYTES);
+              for (int kk = 0; kk < G.KG; ++kk) {
+                const int zo = zin - kk;
+                if (zo < 0 || zo >= G.TZ || z0 + zo >= G.D0) continue;
+                const uint32_t dcol = tmem_base + (uint32_t)(zo * G.NT);
+                for (int k1 = 0; k1 < 3; ++k1) {
+                  const uint32_t a0 = abase + (uint32_t)k1 * (TM2 * 128);
+                  const uint32_t b0 = bbase + (uint32_t)((kk * 3 + k1) * G.NT * 128);
+                  for (int ks = 0; ks < nks; ++ks) {
+                    umma_tf32(dcol, make_desc_k_sw128(a0 + ks * 32), make_desc_k_sw128(b0 + ks * 32), idesc,
+                              (started >> zo) & 1u);
+                    started |= 1u << zo;
+                  }
+                }
+              }
+              umma_commit(emptyA + sa);            // slab may be overwritten once these MMAs have completed
+              if (++sa == G.SA) { sa = 0; pa ^= 1; }
+            }
+            umma_commit(emptyB + sb);
+            if (++sb == SB) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
+      umma_commit(accFull);
+    }
+  } else {
+    // ================================ epilogue (warps 2..5) ================================
+    const int q = warp & 3;                         // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                    // GEMM row = voxel inside the tile
+    const int i1 = y0 + (r >> 3), i2 = x0 + (r & 7);
+    mbar_wait(accFull, 0);
+    tc_fence_after();
+    const bool vox_ok = i1 < G.D1 && i2 < G.D2;
+    for (int zo = 0; zo < G.TZ; ++zo) {
+      const int i0 = z0 + zo;
+      if (i0 >= G.D0) break;                        // uniform across the CTA
+      float* orow = y + ((((long long)b * G.D0 + i0) * G.D1 + i1) * G.D2 + i2) * G.Cout + n0;
+      for (int cb = 0; cb < G.NT; cb += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(zo * G.NT + cb), v);
+        tmem_ld_wait();
+        if (!vox_ok) continue;
+        float o[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int c = n0 + cb + e;
+          float f = __uint_as_float(v[e]);
+          if (c < G.Cout) {
+            if (bias) f += __ldg(bias + c);
+            if (G.act) f = f > 0.f ? f : (expf(f) - 1.f);
+          }
+          o[e] = f;
+        }
+        if (n0 + cb + 16 <= G.Cout && (G.Cout & 3) == 0) {
+#pragma unroll
+          for (int e = 0; e < 16; e += 4)
+            *reinterpret_cast<float4*>(orow + cb + e) = make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (n0 + cb + e < G.Cout) orow[cb + e] = o[e];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)G.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// weight gradient on tcgen05:  dW[k0][k1][k2][ci][co] += sum_v X[v + (k0,k1,k2) - 1][ci] * dY[v][co]
+//
+//   GEMM   D[M x N] += A[M x K] * B[N x K]^T   with K = 8 voxels per instruction, both operands MN-major:
+//   A      the SAME activation slab as the forward kernel (TMA box 32ch x 8 x 18, SWIZZLE_128B) read as an
+//          MN-major operand: the 128 B row of a voxel is the M axis (32 channels), 8 consecutive rows are K.
+//          M = 128 = 4 atoms at +1024 B = the three d1 taps (k1 = 0,1,2) of the slab + one ignored atom.
+//   B      dY tile (TMA box 32ch x 8 x 16) per 32 output channels, MN-major, N = NT (<= 96) output channels.
+//   D      KG accumulators (one per d0 tap in the CTA's group) of NT columns in TMEM; at the end the CTA adds its
+//          partial sums to dW with fp32 atomics (split over spatial tiles / d0 ranges).
+//   CTA    = (input-channel chunk, d2 tap, d0-tap group, N tile, (d1,d2) tile, d0 range); it walks the d0 planes of
+//          its range keeping the last KG dY planes resident.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int WG_BTILE_BYTES = TM1 * TM2 * 128;     // 16384: dY tile of 128 voxels x 32 channels
+
+struct WgGeom {
+  int B, D0, D1, D2;
+  int Cin, C1, Cout;
+  int NT, nNtiles, KG, SA, SBT;
+  int nchunks, n1tiles, n2tiles, n0splits, zlen;
+  int tmem_cols;
+  unsigned char chunk_src[MAX_CHUNKS];
+  unsigned char chunk_valid[MAX_CHUNKS];
+  short chunk_c0[MAX_CHUNKS];
+};
+
+// MN-major SWIZZLE_128B descriptor: atoms (32 x 8) of 1024 B, `lbo` bytes between atoms along M/N
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr, uint32_t lbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;              // K-group stride (one group per instruction)
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(192, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_x2,
+                const __grid_constant__ CUtensorMap map_dy, float* __restrict__ dw, const WgGeom G) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  const int bstage = (G.NT / 32) * WG_BTILE_BYTES;
+  uint8_t* sB = sA + (size_t)G.SA * SLAB_BYTES;
+  uint64_t* bars = (uint64_t*)(sB + (size_t)G.SBT * bstage);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = bars + G.SA;
+  uint64_t* fullB = bars + 2 * G.SA;
+  uint64_t* emptyB = fullB + G.SBT;
+  uint64_t* accFull = emptyB + G.SBT;
+  uint32_t* tmem_slot = (uint32_t*)(accFull + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int t = blockIdx.x;
+  const int zs_i = t % G.n0splits; t /= G.n0splits;
+  const int t2 = t % G.n2tiles; t /= G.n2tiles;
+  const int t1 = t % G.n1tiles; t /= G.n1tiles;
+  const int b = t % G.B; t /= G.B;
+  const int nt = t % G.nNtiles; t /= G.nNtiles;
+  const int ngroups = 3 / G.KG;
+  const int k0g = (t % ngroups) * G.KG; t /= ngroups;
+  const int k2 = t % 3;
+  const int ch = t / 3;
+  const int x0 = t2 * TM2, y0 = t1 * TM1, n0 = nt * G.NT;
+  const int zs = zs_i * G.zlen, ze = min(G.D0, zs + G.zlen);
+  // X planes visited: zin = zo + k0 - 1 for zo in [zs,ze), k0 in [k0g, k0g+KG)
+  const int zin_lo = zs + k0g - 1, zin_hi = ze - 1 + k0g + G.KG - 2;   // inclusive
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < G.SA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, 1); }
+    for (int i = 0; i < G.SBT; ++i) { mbar_init(fullB + i, 1); mbar_init(emptyB + i, 1); }
+    mbar_init(accFull, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)G.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const CUtensorMap* mx = G.chunk_src[ch] ? &map_x2 : &map_x1;
+      const int c0 = G.chunk_c0[ch];
+      int sa = 0, pa = 0;
+      for (int zin = zin_lo; zin <= zin_hi; ++zin) {
+        const int zo_new = zin - k0g + 1;                      // dY plane first needed at this step
+        if (zo_new >= zs && zo_new < ze) {
+          const int p = zo_new - zs, sb = p % G.SBT, pb = (p / G.SBT) & 1;
+          mbar_wait(emptyB + sb, pb ^ 1);
+          mbar_expect_tx(fullB + sb, (uint32_t)bstage);
+          for (int a = 0; a < G.NT / 32; ++a)
+            tma_load_5d(&map_dy, fullB + sb, sB + (size_t)sb * bstage + (size_t)a * WG_BTILE_BYTES, n0 + a * 32, x0, y0,
+                        zo_new, b);
+        }
+        if (zin >= 0 && zin < G.D0) {
+          mbar_wait(emptyA + sa, pa ^ 1);
+          mbar_expect_tx(fullA + sa, SLAB_BYTES);
+          tma_load_5d(mx, fullA + sa, sA + (size_t)sa * SLAB_BYTES, c0, x0 + k2 - 1, y0 - 1, zin, b);
+          if (++sa == G.SA) { sa = 0; pa ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D=F32, A=B=TF32, both MN-major (bits 15,16), M=128, N=NT
+      const uint32_t idesc = make_idesc_tf32(G.NT) | (1u << 15) | (1u << 16);
+      int sa = 0, pa = 0;
+      uint32_t started = 0;
+      for (int zin = zin_lo; zin <= zin_hi; ++zin) {
+        const int zo_new = zin - k0g + 1;
+        if (zo_new >= zs && zo_new < ze) {
+          const int p = zo_new - zs;
+          mbar_wait(fullB + (p % G.SBT), (p / G.SBT) & 1);
+        }
+        if (zin >= 0 && zin < G.D0) {
+          mbar_wait(fullA + sa, pa);
+          tc_fence_after();
+          const uint32_t abase = smem_u32(sA + (size_t)sa * SLAB_BYTES);
+          for (int kk = 0; kk < G.KG; ++kk) {
+            const int zo = zin - (k0g + kk) + 1;
+            if (zo < zs || zo >= ze) continue;
+            const uint32_t bbase = smem_u32(sB + (size_t)((zo - zs) % G.SBT) * bstage);
+            const uint32_t dcol = tmem_base + (uint32_t)(kk * G.NT);
+            for (int s = 0; s < TM1; ++s) {          // 16 K-steps of 8 voxels (one d1 row of the tile each)
+              umma_tf32(dcol, make_desc_mn_sw128(abase + s * 1024, 1024),
+                        make_desc_mn_sw128(bbase + s * 1024, WG_BTILE_BYTES), idesc, (started >> kk) & 1u);
+              started |= 1u << kk;
+            }
+          }
+          umma_commit(emptyA + sa);
+          if (++sa == G.SA) { sa = 0; pa ^= 1; }
+        }
+        const int zo_old = zin - k0g - (G.KG - 1) + 1;         // dY plane whose last use was this step
+        if (zo_old >= zs && zo_old < ze) umma_commit(emptyB + ((zo_old - zs) % G.SBT));
+      }
+      umma_commit(accFull);
+    }
+  } else {
+    const int q = warp & 3;                       // rows 32q..32q+31 <-> d1 tap k1 = q (q == 3: unused atom)
+    mbar_wait(accFull, 0);
+    tc_fence_after();
+    // accumulator kk received MMAs iff some dY plane zo of the range pairs with an in-bounds X plane zo + k0 - 1
+    uint32_t started = 0;
+    for (int kk = 0; kk < G.KG; ++kk)
+      for (int zo = zs; zo < ze; ++zo) {
+        const int zin = zo + k0g + kk - 1;
+        if (zin >= 0 && zin < G.D0) { started |= 1u << kk; break; }
+      }
+    const int valid = G.chunk_valid[ch];
+    const int cin_idx = (G.chunk_src[ch] ? G.C1 : 0) + G.chunk_c0[ch] + lane;
+    for (int kk = 0; kk < G.KG; ++kk) {
+      if (!((started >> kk) & 1u)) continue;      // uniform
+      const int k0 = k0g + kk;
+      for (int cb = 0; cb < G.NT; cb += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kk * G.NT + cb), v);
+        tmem_ld_wait();
+        if (q < 3 && lane < valid) {
+          float* o = dw + ((long long)(((k0 * 3 + q) * 3 + k2)) * G.Cin + cin_idx) * G.Cout + n0 + cb;
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (n0 + cb + e < G.Cout) atomicAdd(o + e, __uint_as_float(v[e]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)G.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// weight packing:  wp[chunk][k2][k0][k1][n][32]   (K-major rows of 32 input channels, zero padded)
+//   mode 0 (forward):       value = w[k0][k1][k2][cin(chunk, s)][n]
+//   mode 1 (data gradient): value = w[2-k0][2-k1][2-k2][n][cout(chunk, s)]   (n runs over the layer's Cin)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ wp, int C1, int C2, int Cout,
+                                    int mode, int Npad, int nchunks, int nch1, int round_rn) {
+  const long long total = (long long)nchunks * 27 * Npad * 32;
+  const int Cin = C1 + C2;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(t & 31);
+    long long r = t >> 5;
+    const int n = (int)(r % Npad); r /= Npad;
+    const int k1 = (int)(r % 3); r /= 3;
+    const int k0 = (int)(r % 3); r /= 3;
+    const int k2 = (int)(r % 3);
+    const int ch = (int)(r / 3);
+    float val = 0.f;
+    if (mode == 0) {
+      int c;   // concat channel index
+      if (ch < nch1) c = ch * 32 + s < C1 ? ch * 32 + s : -1;
+      else c = (ch - nch1) * 32 + s < C2 ? C1 + (ch - nch1) * 32 + s : -1;
+      if (c >= 0 && n < Cout) val = w[((long long)((k0 * 3 + k1) * 3 + k2) * Cin + c) * Cout + n];
+    } else {
+      const int co = ch * 32 + s;      // K runs over the layer's output channels
+      if (co < Cout && n < Cin) val = w[((long long)(((2 - k0) * 3 + (2 - k1)) * 3 + (2 - k2)) * Cin + n) * Cout + co];
+    }
+    if (round_rn) {   // round-to-nearest TF32 (the tensor core would otherwise truncate the low 13 mantissa bits)
+      uint32_t u;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(val));
+      val = __uint_as_float(u);
+    }
+    wp[t] = val;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side: TMA descriptors
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// SSR_TMA_DTYPE=tf32 selects CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 (experiment: does TMA round fp32 -> tf32?)
+CUtensorMapDataType tma_dtype() {
+  const char* e = getenv("SSR_TMA_DTYPE");
+  if (e && strcmp(e, "tf32") == 0) return CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
+  return CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+}
+
+int make_map_act(CUtensorMap* m, const float* ptr, int C, int B, int D0, int D1, int D2, int box_d1 = TM1 + 2) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { ssr_set_error("cuTensorMapEncodeTiled not available"); return SSR_ERR_CUDA; }
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)D2, (cuuint64_t)D1, (cuuint64_t)D0, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)D2 * C * 4, (cuuint64_t)D1 * D2 * C * 4,
+                           (cuuint64_t)D0 * D1 * D2 * C * 4};
+  cuuint32_t box[5] = {32, TM2, (cuuint32_t)box_d1, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, tma_dtype(), 5, (void*)ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { ssr_set_error("cuTensorMapEncodeTiled(activation C=%d %dx%dx%d) failed: %d", C, D0, D1, D2, (int)r); return SSR_ERR_CUDA; }
+  return SSR_OK;
+}
+
+int make_map_w(CUtensorMap* m, const float* ptr, long long rows, int NT) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { ssr_set_error("cuTensorMapEncodeTiled not available"); return SSR_ERR_CUDA; }
+  cuuint64_t dims[2] = {32, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {32, (cuuint32_t)NT};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, tma_dtype(), 2, (void*)ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { ssr_set_error("cuTensorMapEncodeTiled(weights rows=%lld NT=%d) failed: %d", rows, NT, (int)r); return SSR_ERR_CUDA; }
+  return SSR_OK;
+}
+
+int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+int pick_nt(int Npad) {
+  if (Npad <= 192) return Npad;
+  for (int parts = 2; parts <= 8; ++parts)
+    if (Npad % parts == 0 && (Npad / parts) % 16 == 0 && Npad / parts <= 192) return Npad / parts;
+  return 16;
+}
+
+}  // namespace
+
+extern "C" {
+
+long long ssr_conv3d_packed_size(int Cin1, int Cin2, int Cout, int mode) {
+  if (mode == 0) {
+    const int nch = (Cin1 + 31) / 32 + (Cin2 + 31) / 32;
+    return (long long)nch * 27 * round_up(Cout, 16) * 32;
+  }
+  const int nch = (Cout + 31) / 32;
+  return (long long)nch * 27 * round_up(Cin1 + Cin2, 16) * 32;
+}
+
+int ssr_conv3d_pack_weights(const float* w, float* wp, int Cin1, int Cin2, int Cout, int mode, void* stream) {
+  SSR_CHECK_ARG(w && wp && Cin1 > 0 && Cin2 >= 0 && Cout > 0 && (mode == 0 || mode == 1), "pack args");
+  int Npad, nch, nch1;
+  if (mode == 0) { Npad = round_up(Cout, 16); nch1 = (Cin1 + 31) / 32; nch = nch1 + (Cin2 + 31) / 32; }
+  else { Npad = round_up(Cin1 + Cin2, 16); nch = (Cout + 31) / 32; nch1 = nch; }
+  const long long total = (long long)nch * 27 * Npad * 32;
+  long long g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  pack_weights_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(w, wp, Cin1, Cin2, Cout, mode, Npad, nch, nch1,
+                                                                      getenv("SSR_PACK_TRUNC") ? 0 : 1);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
+// y[B,D0,D1,D2,Cout] = act(conv3x3x3([x1,x2], wp) + bias) ; wp from ssr_conv3d_pack_weights.
+// Used for the data gradient too (x1 = dy, wp packed with mode 1, Cout = layer's Cin, bias NULL, act 0).
+int ssr_conv3d_fwd_tc(const float* x1, int C1, const float* x2, int C2, const float* wp, const float* bias, float* y,
+                      int B, int D0, int D1, int D2, int Cout, int act, void* stream) {
+  SSR_CHECK_ARG(x1 && wp && y && B > 0 && D0 > 0 && D1 > 0 && D2 > 0 && Cout > 0, "pointers/shape");
+  SSR_CHECK_ARG(C1 > 0 && C1 % 4 == 0 && C2 >= 0 && C2 % 4 == 0 && (C2 == 0 || x2), "channel counts must be multiples of 4");
+  SSR_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0, "channel counts must be multiples of 8 (TF32 K-step)");
+  SSR_CHECK_ARG(((uintptr_t)x1 & 15) == 0 && ((uintptr_t)wp & 127) == 0 && (!x2 || ((uintptr_t)x2 & 15) == 0), "alignment");
+  TcGeom G;
+  memset(&G, 0, sizeof(G));
+  G.B = B; G.D0 = D0; G.D1 = D1; G.D2 = D2; G.Cout = Cout; G.act = act;
+  G.Npad = round_up(Cout, 16);
+  G.NT = pick_nt(G.Npad);
+  G.nNtiles = G.Npad / G.NT;
+  int tz = 512 / G.NT; if (tz > 4) tz = 4; if (tz > D0) tz = D0; if (tz < 1) tz = 1;
+  G.TZ = tz;
+  G.KG = (3 * 3 * G.NT * 128 <= 74 * 1024) ? 3 : 1;
+  int cols = G.TZ * G.NT, pc = 32;
+  while (pc < cols) pc <<= 1;
+  G.tmem_cols = pc;
+  int nch = 0;
+  for (int c = 0; c < C1; c += 32) {
+    SSR_CHECK_ARG(nch < MAX_CHUNKS, "too many input channels");
+    G.chunk_src[nch] = 0; G.chunk_c0[nch] = (short)c; G.chunk_ks[nch] = (unsigned char)(((C1 - c < 32 ? C1 - c : 32) + 7) / 8); ++nch;
+  }
+  for (int c = 0; c < C2; c += 32) {
+    SSR_CHECK_ARG(nch < MAX_CHUNKS, "too many input channels");
+    G.chunk_src[nch] = 1; G.chunk_c0[nch] = (short)c; G.chunk_ks[nch] = (unsigned char)(((C2 - c < 32 ? C2 - c : 32) + 7) / 8); ++nch;
+  }
+  G.nchunks = nch;
+  G.n2tiles = (D2 + TM2 - 1) / TM2; G.n1tiles = (D1 + TM1 - 1) / TM1; G.n0tiles = (D0 + G.TZ - 1) / G.TZ;
+  const int bgroup = G.KG * 3 * G.NT * 128;
+  const int budget = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - SB * bgroup;
+  int sa = budget / SLAB_BYTES; if (sa > 8) sa = 8;
+  SSR_CHECK_ARG(sa >= 2, "shared memory budget");
+  G.SA = sa;
+  const size_t smem = 1024 + (size_t)G.SA * SLAB_BYTES + (size_t)SB * bgroup + 512;
+
+  CUtensorMap m1, m2, mw;
+  int rc = make_map_act(&m1, x1, C1, B, D0, D1, D2);
+  if (rc) return rc;
+  if (C2 > 0) { rc = make_map_act(&m2, x2, C2, B, D0, D1, D2); if (rc) return rc; } else m2 = m1;
+  rc = make_map_w(&mw, wp, (long long)nch * 27 * G.Npad, G.NT);
+  if (rc) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const long long ntiles = (long long)B * G.n0tiles * G.n1tiles * G.n2tiles * G.nNtiles;
+  SSR_CHECK_ARG(ntiles < (1LL << 31), "grid too large");
+  conv3d_tc_kernel<<<(unsigned)ntiles, 192, smem, (cudaStream_t)stream>>>(m1, m2, mw, bias, y, G);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
+long long ssr_conv3d_wgrad_scratch_bytes(int, int, int, int, int, int, int) { return 0; }
+
+// dw (3,3,3,C1+C2,Cout) += [x1,x2] (*) dy  ;  db[Cout] += sum_v dy   (tcgen05, see wgrad_tc_kernel)
+int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const float* dy, float* dw, float* db,
+                        float* scratch, long long scratch_bytes, int B, int D0, int D1, int D2, int Cout,
+                        void* stream) {
+  (void)scratch; (void)scratch_bytes;
+  SSR_CHECK_ARG(x1 && dy && dw && B > 0 && D0 > 0 && D1 > 0 && D2 > 0 && Cout > 0, "pointers/shape");
+  SSR_CHECK_ARG(C1 > 0 && C1 % 8 == 0 && C2 >= 0 && C2 % 8 == 0 && (C2 == 0 || x2) && Cout % 8 == 0,
+                "channel counts must be multiples of 8");
+  WgGeom G;
+  memset(&G, 0, sizeof(G));
+  G.B = B; G.D0 = D0; G.D1 = D1; G.D2 = D2; G.Cin = C1 + C2; G.Cout = Cout;
+  const int Npad = round_up(Cout, 32);
+  int ntile = Npad;
+  if (ntile > 96) { ntile = 96; while (Npad % ntile) ntile -= 32; }
+  G.NT = ntile; G.nNtiles = Npad / ntile;
+  G.KG = G.NT <= 64 ? 3 : 1;
+  G.SBT = G.KG + 1; if (G.KG == 1) G.SBT = 3;
+  const int bstage = (G.NT / 32) * WG_BTILE_BYTES;
+  int sa = (227 * 1024 - 1024 - 512 - G.SBT * bstage) / SLAB_BYTES; if (sa > 4) sa = 4;
+  SSR_CHECK_ARG(sa >= 2, "shared memory budget");
+  G.SA = sa;
+  int cols = G.KG * G.NT, pc = 32; while (pc < cols) pc <<= 1;
+  G.tmem_cols = pc;
+  int nch = 0;
+  for (int c = 0; c < C1; c += 32) { SSR_CHECK_ARG(nch < MAX_CHUNKS, "too many channels"); G.chunk_src[nch] = 0; G.chunk_c0[nch] = (short)c; G.chunk_valid[nch] = (unsigned char)(C1 - c < 32 ? C1 - c : 32); ++nch; }
+  for (int c = 0; c < C2; c += 32) { SSR_CHECK_ARG(nch < MAX_CHUNKS, "too many channels"); G.chunk_src[nch] = 1; G.chunk_c0[nch] = (short)c; G.chunk_valid[nch] = (unsigned char)(C2 - c < 32 ? C2 - c : 32); ++nch; }
+  G.nchunks = nch; G.C1 = C1;
+  G.n2tiles = (D2 + TM2 - 1) / TM2; G.n1tiles = (D1 + TM1 - 1) / TM1;
+  const long long base_units = (long long)nch * 3 * (3 / G.KG) * G.nNtiles * G.n1tiles * G.n2tiles * B;
+  int S = (int)((2 * 148 + base_units - 1) / base_units); if (S < 1) S = 1; if (S > (D0 + 3) / 4) S = (D0 + 3) / 4; if (S < 1) S = 1;
+  G.zlen = (D0 + S - 1) / S; G.n0splits = (D0 + G.zlen - 1) / G.zlen;
+  const size_t smem = 1024 + (size_t)G.SA * SLAB_BYTES + (size_t)G.SBT * bstage + 512;
+  CUtensorMap m1, m2, my;
+  int rc = make_map_act(&m1, x1, C1, B, D0, D1, D2); if (rc) return rc;
+  if (C2 > 0) { rc = make_map_act(&m2, x2, C2, B, D0, D1, D2); if (rc) return rc; } else m2 = m1;
+  rc = make_map_act(&my, dy, Cout, B, D0, D1, D2, TM1); if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSR_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const long long nblk = base_units * G.n0splits;
+  SSR_CHECK_ARG(nblk < (1LL << 31), "grid too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  wgrad_tc_kernel<<<(unsigned)nblk, 192, smem, st>>>(m1, m2, my, dw, G);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  if (db) {
+    const long long nvox = (long long)B * D0 * D1 * D2;
+    int rc2 = ssr_channel_sum(dy, nvox, Cout, db, stream);
+    if (rc2) return rc2;
+  }
+  return SSR_OK;
+}
+
+int ssr_tc_selftest(void* stream) {
+  (void)stream;
+  int arch = 0, dev = 0;
+  SSR_CHECK_CUDA(cudaGetDevice(&dev));
+  SSR_CHECK_CUDA(cudaDeviceGetAttribute(&arch, cudaDevAttrComputeCapabilityMajor, dev));
+  if (arch != 10) { ssr_set_error("tcgen05 path needs compute capability 10.x, found %d.x", arch); return SSR_ERR_UNSUPPORTED; }
+  if (!get_encode()) { ssr_set_error("cuTensorMapEncodeTiled unavailable"); return SSR_ERR_CUDA; }
+  return SSR_OK;
+}
+
+}  // extern "C"

@@ -154,6 +154,68 @@ wgrad_direct_kernel(const float* __restrict__ x1, const float* __restrict__ x2, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// weight gradient for very small Cin (the first layer: Cin = 1 or 2): dW[(tap,ci)][co] = sum_v X[v+tap][ci] dY[v][co]
+// as a skinny GEMM [27*Cin x V] . [V x Cout].  Persistent blocks stage 128 voxels (their k^3*Cin input neighbours and
+// their Cout output gradients) in shared memory, every thread owns up to WS_MAXOUT (row, col) outputs in registers,
+// one atomicAdd per output per block at the end.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int WS_VOX = 128, WS_MAXOUT = 8;
+
+__global__ void __launch_bounds__(256)
+wgrad_small_cin_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, ConvGeom G) {
+  extern __shared__ float wsm[];
+  const int Cin = G.C1, K = G.k * G.k * G.k * Cin, nout = K * G.Cout;
+  float* sx = wsm;                         // [WS_VOX][K + 1]
+  float* sdy = wsm + WS_VOX * (K + 1);     // [WS_VOX][Cout]
+  const int rad = G.k / 2;
+  const long long nvox = (long long)G.B * G.d0 * G.d1 * G.d2;
+  float acc[WS_MAXOUT];
+#pragma unroll
+  for (int e = 0; e < WS_MAXOUT; ++e) acc[e] = 0.f;
+  for (long long base = (long long)blockIdx.x * WS_VOX; base < nvox; base += (long long)gridDim.x * WS_VOX) {
+    for (int e = threadIdx.x; e < WS_VOX * K; e += blockDim.x) {
+      const int vi = e / K, r = e % K;
+      const int ci = r % Cin, tap = r / Cin;
+      const int c = tap % G.k, bb = (tap / G.k) % G.k, a = tap / (G.k * G.k);
+      const long long v = base + vi;
+      float val = 0.f;
+      if (v < nvox) {
+        long long q = v;
+        const int i2 = (int)(q % G.d2); q /= G.d2;
+        const int i1 = (int)(q % G.d1); q /= G.d1;
+        const int i0 = (int)(q % G.d0);
+        const int b = (int)(q / G.d0);
+        const int j0 = i0 + a - rad, j1 = i1 + bb - rad, j2 = i2 + c - rad;
+        if (j0 >= 0 && j0 < G.d0 && j1 >= 0 && j1 < G.d1 && j2 >= 0 && j2 < G.d2)
+          val = x[((((long long)b * G.d0 + j0) * G.d1 + j1) * G.d2 + j2) * Cin + ci];
+      }
+      sx[vi * (K + 1) + r] = val;
+    }
+    for (int e = threadIdx.x; e < WS_VOX * G.Cout; e += blockDim.x) {
+      const long long v = base + e / G.Cout;
+      sdy[e] = v < nvox ? dy[v * G.Cout + e % G.Cout] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < WS_MAXOUT; ++e) {
+      const int o = threadIdx.x + e * 256;
+      if (o < nout) {
+        const int r = o / G.Cout, col = o % G.Cout;
+        float a2 = 0.f;
+        for (int vi = 0; vi < WS_VOX; ++vi) a2 += sx[vi * (K + 1) + r] * sdy[vi * G.Cout + col];
+        acc[e] += a2;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int e = 0; e < WS_MAXOUT; ++e) {
+    const int o = threadIdx.x + e * 256;
+    if (o < nout) atomicAdd(dw + o, acc[e]);     // dw layout (tap, ci, co) == o
+  }
+}
+
 // per-channel sum over voxels of t[v][C] (bias gradients): out[c] += sum_v t[v][c]
 __global__ void channel_sum_kernel(const float* __restrict__ t, long long nvox, int C, float* __restrict__ out) {
   extern __shared__ double sh[];
@@ -604,10 +666,20 @@ int ssr_conv3d_wgrad_ref(const float* x1, int C1, const float* x2, int C2, const
   cudaStream_t st = (cudaStream_t)stream;
   ConvGeom G{B, d0, d1, d2, C1, C2, Cout, k, 0};
   const long long nvox = (long long)B * d0 * d1 * d2;
-  int nsplit = (int)((nvox + 32767) / 32768);
-  if (nsplit > 64) nsplit = 64;
-  dim3 grid(k * k * k, C1 + C2, nsplit);
-  wgrad_direct_kernel<<<grid, 128, 0, st>>>(x1, x2, dy, dw, G, nsplit);
+  const int Ksmall = k * k * k * C1;
+  if (C2 == 0 && C1 <= 4 && Ksmall * Cout <= 256 * WS_MAXOUT && nvox >= 4096) {
+    const size_t smem = (size_t)WS_VOX * (Ksmall + 1 + Cout) * sizeof(float);
+    if (smem > 48 * 1024)
+      SSR_CHECK_CUDA(cudaFuncSetAttribute(wgrad_small_cin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long nb = (nvox + WS_VOX - 1) / WS_VOX;
+    if (nb > 148 * 4) nb = 148 * 4;
+    wgrad_small_cin_kernel<<<(unsigned)nb, 256, smem, st>>>(x1, dy, dw, G);
+  } else {
+    int nsplit = (int)((nvox + 32767) / 32768);
+    if (nsplit > 64) nsplit = 64;
+    dim3 grid(k * k * k, C1 + C2, nsplit);
+    wgrad_direct_kernel<<<grid, 128, 0, st>>>(x1, x2, dy, dw, G, nsplit);
+  }
   SSR_COUNT_LAUNCH();
   if (db) {
     dim3 blk(32, 8);

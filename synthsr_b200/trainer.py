@@ -1,0 +1,68 @@
+"""One training step of SynthSR.training.training() (SynthSR/training.py:330-453) on the B200 engine:
+on-the-fly generator -> U-Net forward/backward -> (data-parallel gradient all-reduce) -> Adam.
+
+Data parallelism (one process per GPU, torch.distributed / NCCL): every rank generates and trains on its own
+mini-batch shard; the ONLY exchange per step is one all-reduce of the flat gradient buffer (the BN moving statistics
+ride at its tail so all replicas keep identical state).  BN batch statistics stay rank-local (equals the reference's
+batchsize-per-GPU semantics per shard; documented deviation from a single big batch).
+"""
+import numpy as np
+import torch
+
+from .draws import sample_draws
+from .generator import SynthGenerator
+from .unet import UNet3D
+
+
+class TrainingEngine:
+    def __init__(self, plan, batchsize=1, nb_features=24, nb_levels=5, conv_size=3, feat_mult=2, nb_conv_per_level=2,
+                 nb_labels=None, lr=1e-4, lr_decay=0., metric='l1', work_with_residual_channel=None,
+                 loss_cropping=None, conv_impl='tc', seed=0, device='cuda', rank=0, world_size=1):
+        self.plan, self.B = plan, int(batchsize)
+        self.device = torch.device(device)
+        self.rank, self.world = int(rank), int(world_size)
+        self.gen = SynthGenerator(plan, batchsize, device)
+        nb_labels = plan.n_target_channels if nb_labels is None else nb_labels
+        self.net = UNet3D(plan.image_shape, nb_features, nb_levels, conv_size, nb_labels, feat_mult, nb_conv_per_level,
+                          batchsize, device, conv_impl, seed=seed)        # same seed on every rank: identical replicas
+        self.lr, self.lr_decay, self.metric = lr, lr_decay, metric
+        self.residual, self.loss_cropping = work_with_residual_channel, loss_cropping
+        self.rng = np.random.default_rng(seed * 1000003 + 7919 * self.rank)   # per-rank augmentation stream
+        self.seed = seed * 65537 + self.rank
+        self.steps = 0
+        if self.world > 1:
+            n_mv = sum(t.numel() for t in self.net.moving.values())
+            self.flat = torch.zeros(self.net.n_params + n_mv + 1, dtype=torch.float32, device=self.device)
+
+    def train_step(self, labels, means, stds, real_image=None, draws=None):
+        """labels: int32 cuda [B, *labels_shape]; means/stds [B, L, C] host arrays.  Returns the loss (1-element cuda
+        tensor, float64; averaged over ranks when world_size > 1)."""
+        if draws is None:
+            draws = sample_draws(self.rng, self.plan, self.B)
+        image, target = self.gen.run(labels, means, stds, draws, real_image=real_image, seed=self.seed)
+        loss = self.net.loss_and_grad(image, target, self.metric, self.residual, self.loss_cropping)
+        scale = 1.
+        if self.world > 1:
+            loss = self._allreduce(loss)
+            scale = 1. / self.world
+        self.net.adam_step(self.lr, self.lr_decay, grad_scale=scale)
+        self.steps += 1
+        return loss
+
+    def _allreduce(self, loss):
+        """single NCCL all-reduce per step: [gradients | BN moving stats | loss]."""
+        import torch.distributed as dist
+        net, n = self.net, self.net.n_params
+        self.flat[:n].copy_(net.grads)
+        o = n
+        for t in net.moving.values():
+            self.flat[o:o + t.numel()].copy_(t)
+            o += t.numel()
+        self.flat[o] = loss[0].float()
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        net.grads.copy_(self.flat[:n])
+        o = n
+        for t in net.moving.values():
+            t.copy_(self.flat[o:o + t.numel()] / self.world)
+            o += t.numel()
+        return (self.flat[o:o + 1] / self.world).double()

@@ -53,6 +53,8 @@ class UNet3D:
         self.k = int(conv_size)
         self.nb_labels = int(nb_labels)
         self.conv_impl = conv_impl
+        self.wgrad_tc = conv_impl == 'tc'
+        self.prof = None          # list of (kind, flops, start_event, end_event) when profiling is enabled
         self.device = torch.device(device)
         for d in self.dims:
             if d % (2 ** (self.L - 1)) != 0:
@@ -151,6 +153,7 @@ class UNet3D:
         self.loss_buf = torch.zeros(1, dtype=torch.float64, device=dev)
         self._bwd_alloc = False
         self._packed = {}
+        self._packed_args = {}
         self._packed_dirty = True
 
     def _alloc_bwd(self):
@@ -176,10 +179,24 @@ class UNet3D:
     # -------------------------------------------------------------------------------------------------------------
     # convolution dispatch
     # -------------------------------------------------------------------------------------------------------------
+    def _timed(self, kind, l, cin, cout, fn):
+        if self.prof is None:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        self.prof.append((kind, 2. * self.k ** 3 * cin * cout * self.nvox[l], e0, e1))
+
     def _conv_fwd(self, name, x1, c1, x2, c2, y, l, cout, act=1):
+        tc = self.conv_impl == 'tc' and c1 % 8 == 0 and c2 % 8 == 0
+        self._timed('fwd_tc' if tc else 'fwd_ref', l, c1 + c2, cout,
+                    lambda: self._conv_fwd_impl(tc, name, x1, c1, x2, c2, y, l, cout, act))
+
+    def _conv_fwd_impl(self, tc, name, x1, c1, x2, c2, y, l, cout, act):
         st = stream_ptr()
         d = self.ldims[l]
-        if self.conv_impl == 'tc' and (c1 + c2) % 8 == 0:
+        if tc:
             lib.ssr_conv3d_fwd_tc(x1, c1, x2, c2, self._packed_w(name, 0, c1, c2, cout), self.p[name + '/bias'], y,
                                   self.B, *d, cout, act, st)
         else:
@@ -187,9 +204,14 @@ class UNet3D:
                                    cout, self.k, act, st)
 
     def _conv_dgrad(self, name, dy, dx, l, cin, cout):
+        tc = self.conv_impl == 'tc' and cout % 8 == 0
+        self._timed('dgrad_tc' if tc else 'dgrad_ref', l, cin, cout,
+                    lambda: self._conv_dgrad_impl(tc, name, dy, dx, l, cin, cout))
+
+    def _conv_dgrad_impl(self, tc, name, dy, dx, l, cin, cout):
         st = stream_ptr()
         d = self.ldims[l]
-        if self.conv_impl == 'tc' and cout % 8 == 0:
+        if tc:
             # data gradient = forward convolution of dy with the flipped / transposed kernel
             lib.ssr_conv3d_fwd_tc(dy, cout, None, 0, self._packed_w(name, 1, cin, 0, cout), None, dx, self.B, *d, cin,
                                   0, st)
@@ -198,9 +220,14 @@ class UNet3D:
                                      st)
 
     def _conv_wgrad(self, name, x1, c1, x2, c2, dy, l, cout):
+        tc = self.conv_impl == 'tc' and self._wgrad_tc_ok(c1, c2, cout)
+        self._timed('wgrad_tc' if tc else 'wgrad_ref', l, c1 + c2, cout,
+                    lambda: self._conv_wgrad_impl(tc, name, x1, c1, x2, c2, dy, l, cout))
+
+    def _conv_wgrad_impl(self, tc, name, x1, c1, x2, c2, dy, l, cout):
         st = stream_ptr()
         d = self.ldims[l]
-        if self.conv_impl == 'tc' and self._wgrad_tc_ok(c1, c2, cout):
+        if tc:
             nbytes = lib.ssr_conv3d_wgrad_scratch_bytes(c1, c2, cout, self.B, *d)
             if getattr(self, '_wg_scratch', None) is None or self._wg_scratch.numel() * 4 < nbytes:
                 self._wg_scratch = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
@@ -222,6 +249,7 @@ class UNet3D:
         if key not in self._packed:
             n = lib.ssr_conv3d_packed_size(c1, c2, cout, mode)
             self._packed[key] = torch.empty(n, dtype=torch.float32, device=self.device)
+            self._packed_args[key] = (c1, c2, cout)
         if key not in self._packed_valid:
             lib.ssr_conv3d_pack_weights(self.p[name + '/kernel'], self._packed[key], c1, c2, cout, mode, stream_ptr())
             self._packed_valid.add(key)
@@ -235,6 +263,13 @@ class UNet3D:
         assert image.is_cuda and image.dtype == torch.float32 and image.is_contiguous()
         assert list(image.shape) == [B] + self.dims + [self.cin], image.shape
         self._image = image
+        if self._packed_dirty and self._packed:          # refresh every packed kernel copy once per optimiser step
+            self._packed_dirty = False
+            self._packed_valid = set()
+            for (name, mode), buf in self._packed.items():
+                c1, c2, cout = self._packed_args[(name, mode)]
+                lib.ssr_conv3d_pack_weights(self.p[name + '/kernel'], buf, c1, c2, cout, mode, st)
+                self._packed_valid.add((name, mode))
         x, cx = image, self.cin
         for l in range(L):
             self._conv_fwd('unet_conv_downarm_%d_0' % l, x, cx, None, 0, self.h0[l], l, F[l])

@@ -141,3 +141,48 @@ def test_tc_matches_ref_kernels():
 def test_tc_training_step_32cube():
     """full step with tcgen05 convolutions at the reference topology; bar 1e-3 on prediction and loss."""
     _one_step([32, 32, 32], 1, 24, 5, 1, 'tc', 1e-3, 2e-2)
+
+
+def test_tc_wgrad_matches_ref():
+    """tcgen05 weight gradient (MN-major operands, split over tiles with fp32 atomics) vs the direct fp32 kernel."""
+    from synthsr_b200._lib import lib, stream_ptr
+    rng = np.random.default_rng(1)
+    for (d, c1, c2, co) in [([16, 16, 16], 24, 0, 24), ([12, 32, 16], 24, 48, 24), ([8, 16, 24], 48, 0, 96),
+                            ([10, 10, 10], 192, 0, 384), ([6, 16, 8], 96, 192, 96), ([20, 20, 20], 48, 0, 48)]:
+        B = 1
+        nv = B * int(np.prod(d))
+        x1 = torch.from_numpy(rng.normal(size=(nv, c1)).astype(np.float32)).cuda()
+        x2 = torch.from_numpy(rng.normal(size=(nv, max(c2, 1))).astype(np.float32)).cuda() if c2 else None
+        dy = torch.from_numpy(rng.normal(size=(nv, co)).astype(np.float32)).cuda()
+        n = 27 * (c1 + c2) * co
+        dw_ref = torch.zeros(n, dtype=torch.float32, device='cuda')
+        dw_tc = torch.zeros(n, dtype=torch.float32, device='cuda')
+        db_ref = torch.zeros(co, dtype=torch.float32, device='cuda')
+        db_tc = torch.zeros(co, dtype=torch.float32, device='cuda')
+        st = stream_ptr()
+        lib.ssr_conv3d_wgrad_ref(x1, c1, x2, c2, dy, dw_ref, db_ref, B, *d, co, 3, st)
+        lib.ssr_conv3d_wgrad_tc(x1, c1, x2, c2, dy, dw_tc, db_tc, None, 0, B, *d, co, st)
+        torch.cuda.synchronize()
+        err = (dw_tc - dw_ref).abs().max().item() / dw_ref.abs().max().item()
+        assert err < 2e-3, ('wgrad', d, c1, c2, co, err)
+        assert torch.allclose(db_tc, db_ref, rtol=1e-4, atol=1e-3)
+
+
+def test_small_cin_wgrad_kernel():
+    """first-layer weight gradient (Cin=1/2, skinny-GEMM kernel) vs the torch float64 reference."""
+    from synthsr_b200._lib import lib, stream_ptr
+    rng = np.random.default_rng(2)
+    for (d, cin, co) in [([24, 20, 16], 1, 24), ([16, 16, 20], 2, 24)]:
+        nv = int(np.prod(d))
+        x = torch.from_numpy(rng.normal(size=(nv, cin)).astype(np.float32)).cuda()
+        dy = torch.from_numpy(rng.normal(size=(nv, co)).astype(np.float32)).cuda()
+        dw = torch.zeros(27 * cin * co, dtype=torch.float32, device='cuda')
+        lib.ssr_conv3d_wgrad_ref(x, cin, None, 0, dy, dw, None, 1, *d, co, 3, stream_ptr())
+        torch.cuda.synchronize()
+        xt = x.double().view(1, *d, cin).permute(0, 4, 1, 2, 3).cpu().requires_grad_(False)
+        w = torch.zeros(co, cin, 3, 3, 3, dtype=torch.float64, requires_grad=True)
+        y = torch.nn.functional.conv3d(xt, w, padding=1)
+        y.backward(dy.double().view(1, *d, co).permute(0, 4, 1, 2, 3).cpu())
+        ref = w.grad.permute(2, 3, 4, 1, 0).reshape(-1)
+        err = (dw.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
+        assert err < 1e-5, (d, cin, co, err)
