@@ -77,6 +77,13 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
 
+// one elected lane of a fully converged warp (keeps descriptor operands in uniform registers: no per-MMA waterfall)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
                : "memory");
@@ -118,6 +125,26 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
   return d;
 }
+// Descriptors as (lo, hi) halves so the issue loop only adds byte offsets (>> 4) to `lo`:
+//   lo = start_address>>4 | LBO>>4 << 16 ;  hi = SBO>>4 | version(1) << 14 | layout_type << 29
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+constexpr uint32_t DESC_HI_K_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);        // K-major, SWIZZLE_128B, SBO 1024
+constexpr uint32_t DESC_HI_MN_SW128_32B = (512u >> 4) | (1u << 14) | (1u << 29);    // MN-major tf32: SWIZZLE_128B_BASE32B,
+                                                                                    // K groups of 4 rows (512 B)
+__device__ __forceinline__ void umma_tf32_lh(uint32_t d_tmem, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(alo), "r"(blo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // instruction descriptor: D=F32, A=B=TF32, both K-major, M=128, N
 __device__ __forceinline__ uint32_t make_idesc_tf32(int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
@@ -241,8 +268,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ================================
-    if (lane == 0) {
+    // ================================ MMA issuer (whole warp converged, one elected lane issues) ======
+    {
       const uint32_t idesc = make_idesc_tf32(G.NT);
       int sa = 0, pa = 0, sb = 0, pb = 0;
       uint32_t started = 0;
@@ -252,35 +279,51 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
           for (int k0g = 0; k0g < 3; k0g += G.KG) {
             if (!group_needed(G, z0, k0g)) continue;
             mbar_wait(fullB + sb, pb);
-            const uint32_t bbase = smem_u32(sB + (size_t)sb * bgroup_bytes);
+            const uint32_t blo0 = desc_lo(smem_u32(sB + (size_t)sb * bgroup_bytes), 16);
+            const uint32_t btile16 = (uint32_t)(G.NT * 128) >> 4;
             for (int zin = 0; zin < G.TZ + G.KG - 1; ++zin) {
               if (!slab_needed(G, z0, k0g, zin)) continue;
               mbar_wait(fullA + sa, pa);
               tc_fence_after();
-              const uint32_t abase = smem_u32(sA + (size_t)sa * SLAB_BYTES);
-              for (int kk = 0; kk < G.KG; ++kk) {
+              const uint32_t alo0 = desc_lo(smem_u32(sA + (size_t)sa * SLAB_BYTES), 16);
+              if (elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < 3; ++kk) {
+                if (kk >= G.KG) break;
                 const int zo = zin - kk;
                 if (zo < 0 || zo >= G.TZ || z0 + zo >= G.D0) continue;
                 const uint32_t dcol = tmem_base + (uint32_t)(zo * G.NT);
+                uint32_t acc = (started >> zo) & 1u;
+#pragma unroll
                 for (int k1 = 0; k1 < 3; ++k1) {
-                  const uint32_t a0 = abase + (uint32_t)k1 * (TM2 * 128);
-                  const uint32_t b0 = bbase + (uint32_t)((kk * 3 + k1) * G.NT * 128);
-                  for (int ks = 0; ks < nks; ++ks) {
-                    umma_tf32(dcol, make_desc_k_sw128(a0 + ks * 32), make_desc_k_sw128(b0 + ks * 32), idesc,
-                              (started >> zo) & 1u);
-                    started |= 1u << zo;
+                  const uint32_t alo = alo0 + (uint32_t)(k1 * (TM2 * 128 >> 4));
+                  const uint32_t blo = blo0 + (uint32_t)(kk * 3 + k1) * btile16;
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) {
+                    if (ks < nks) {
+                      umma_tf32_lh(dcol, alo + ks * 2, blo + ks * 2, DESC_HI_K_SW128, idesc, acc);
+                      acc = 1u;
+                    }
                   }
                 }
               }
-              umma_commit(emptyA + sa);            // slab may be overwritten once these MMAs have completed
+                umma_commit(emptyA + sa);          // slab may be overwritten once these MMAs have completed
+              }
+              __syncwarp();
+              for (int kk = 0; kk < G.KG; ++kk) {  // bookkeeping replicated on every lane (warp-uniform)
+                const int zo = zin - kk;
+                if (zo >= 0 && zo < G.TZ && z0 + zo < G.D0) started |= 1u << zo;
+              }
               if (++sa == G.SA) { sa = 0; pa ^= 1; }
             }
-            umma_commit(emptyB + sb);
+            if (elect_one()) umma_commit(emptyB + sb);
+            __syncwarp();
             if (++sb == SB) { sb = 0; pb ^= 1; }
           }
         }
       }
-      umma_commit(accFull);
+      if (elect_one()) umma_commit(accFull);
+      __syncwarp();
     }
   } else {
     // ================================ epilogue (warps 2..5) ================================
@@ -433,8 +476,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // D=F32, A=B=TF32, both MN-major (bits 15,16), M=128, N=NT
+    {
+      // whole warp converged, one elected lane issues.  D=F32, A=B=TF32, both MN-major (bits 15,16), M=128, N=NT
       const uint32_t idesc = make_idesc_tf32(G.NT) | (1u << 15) | (1u << 16);
       int sa = 0, pa = 0;
       uint32_t started = 0;
@@ -447,25 +490,39 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
         if (zin >= 0 && zin < G.D0) {
           mbar_wait(fullA + sa, pa);
           tc_fence_after();
-          const uint32_t abase = smem_u32(sA + (size_t)sa * SLAB_BYTES);
-          for (int kk = 0; kk < G.KG; ++kk) {
+          const uint32_t alo0 = desc_lo(smem_u32(sA + (size_t)sa * SLAB_BYTES), 1024);      // M atoms = d1 taps
+          if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 3; ++kk) {
+            if (kk >= G.KG) break;
             const int zo = zin - (k0g + kk) + 1;
             if (zo < zs || zo >= ze) continue;
-            const uint32_t bbase = smem_u32(sB + (size_t)((zo - zs) % G.SBT) * bstage);
+            const uint32_t blo0 = desc_lo(smem_u32(sB + (size_t)((zo - zs) % G.SBT) * bstage), WG_BTILE_BYTES);
             const uint32_t dcol = tmem_base + (uint32_t)(kk * G.NT);
+            uint32_t acc = (started >> kk) & 1u;
+#pragma unroll
             for (int s = 0; s < TM1; ++s) {          // 16 K-steps of 8 voxels (one d1 row of the tile each)
-              umma_tf32(dcol, make_desc_mn_sw128(abase + s * 1024, 1024),
-                        make_desc_mn_sw128(bbase + s * 1024, WG_BTILE_BYTES), idesc, (started >> kk) & 1u);
-              started |= 1u << kk;
+              umma_tf32_lh(dcol, alo0 + s * (1024 >> 4), blo0 + s * (1024 >> 4), DESC_HI_MN_SW128_32B, idesc, acc);
+              acc = 1u;
             }
           }
-          umma_commit(emptyA + sa);
+            umma_commit(emptyA + sa);
+          }
+          __syncwarp();
+          for (int kk = 0; kk < G.KG; ++kk) {
+            const int zo = zin - (k0g + kk) + 1;
+            if (zo >= zs && zo < ze) started |= 1u << kk;
+          }
           if (++sa == G.SA) { sa = 0; pa ^= 1; }
         }
         const int zo_old = zin - k0g - (G.KG - 1) + 1;         // dY plane whose last use was this step
-        if (zo_old >= zs && zo_old < ze) umma_commit(emptyB + ((zo_old - zs) % G.SBT));
+        if (zo_old >= zs && zo_old < ze) {
+          if (elect_one()) umma_commit(emptyB + ((zo_old - zs) % G.SBT));
+          __syncwarp();
+        }
       }
-      umma_commit(accFull);
+      if (elect_one()) umma_commit(accFull);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;                       // rows 32q..32q+31 <-> d1 tap k1 = q (q == 3: unused atom)
@@ -557,14 +614,17 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// SSR_TMA_DTYPE=tf32 selects CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 (experiment: does TMA round fp32 -> tf32?)
+// Activations are fp32 in HBM; CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 makes the TMA unit round them to nearest TF32 on the
+// way into shared memory (measured: conv error 4.7e-4 -> 2.9e-4 rel. L2 vs feeding raw fp32 bits, which the tensor
+// core truncates; profiles/r01_tf32_precision.txt).  SSR_TMA_DTYPE=f32 restores the raw-bits behaviour.
 CUtensorMapDataType tma_dtype() {
   const char* e = getenv("SSR_TMA_DTYPE");
-  if (e && strcmp(e, "tf32") == 0) return CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
-  return CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  if (e && strcmp(e, "f32") == 0) return CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  return CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
 }
 
-int make_map_act(CUtensorMap* m, const float* ptr, int C, int B, int D0, int D1, int D2, int box_d1 = TM1 + 2) {
+int make_map_act(CUtensorMap* m, const float* ptr, int C, int B, int D0, int D1, int D2, int box_d1 = TM1 + 2,
+                 CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { ssr_set_error("cuTensorMapEncodeTiled not available"); return SSR_ERR_CUDA; }
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)D2, (cuuint64_t)D1, (cuuint64_t)D0, (cuuint64_t)B};
@@ -573,7 +633,7 @@ int make_map_act(CUtensorMap* m, const float* ptr, int C, int B, int D0, int D1,
   cuuint32_t box[5] = {32, TM2, (cuuint32_t)box_d1, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, tma_dtype(), 5, (void*)ptr, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { ssr_set_error("cuTensorMapEncodeTiled(activation C=%d %dx%dx%d) failed: %d", C, D0, D1, D2, (int)r); return SSR_ERR_CUDA; }
   return SSR_OK;
@@ -586,7 +646,7 @@ int make_map_w(CUtensorMap* m, const float* ptr, long long rows, int NT) {
   cuuint64_t strides[1] = {128};
   cuuint32_t box[2] = {32, (cuuint32_t)NT};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, tma_dtype(), 2, (void*)ptr, dims, strides, box, estr,
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { ssr_set_error("cuTensorMapEncodeTiled(weights rows=%lld NT=%d) failed: %d", rows, NT, (int)r); return SSR_ERR_CUDA; }
@@ -723,9 +783,10 @@ int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const 
   G.zlen = (D0 + S - 1) / S; G.n0splits = (D0 + G.zlen - 1) / G.zlen;
   const size_t smem = 1024 + (size_t)G.SA * SLAB_BYTES + (size_t)G.SBT * bstage + 512;
   CUtensorMap m1, m2, my;
-  int rc = make_map_act(&m1, x1, C1, B, D0, D1, D2); if (rc) return rc;
-  if (C2 > 0) { rc = make_map_act(&m2, x2, C2, B, D0, D1, D2); if (rc) return rc; } else m2 = m1;
-  rc = make_map_act(&my, dy, Cout, B, D0, D1, D2, TM1); if (rc) return rc;
+  const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;     // MN-major tf32 operands (UMMA 128B_BASE32B)
+  int rc = make_map_act(&m1, x1, C1, B, D0, D1, D2, TM1 + 2, swz); if (rc) return rc;
+  if (C2 > 0) { rc = make_map_act(&m2, x2, C2, B, D0, D1, D2, TM1 + 2, swz); if (rc) return rc; } else m2 = m1;
+  rc = make_map_act(&my, dy, Cout, B, D0, D1, D2, TM1, swz); if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     SSR_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -160,59 +160,58 @@ wgrad_direct_kernel(const float* __restrict__ x1, const float* __restrict__ x2, 
 // their Cout output gradients) in shared memory, every thread owns up to WS_MAXOUT (row, col) outputs in registers,
 // one atomicAdd per output per block at the end.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int WS_VOX = 128, WS_MAXOUT = 8;
+constexpr int WS_VOX = 128;
 
-__global__ void __launch_bounds__(256)
+// thread (r, cg): row r of the [k^3*Cin] input-patch matrix, column group cg of 4 output channels
+__global__ void __launch_bounds__(384)
 wgrad_small_cin_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, ConvGeom G) {
-  extern __shared__ float wsm[];
-  const int Cin = G.C1, K = G.k * G.k * G.k * Cin, nout = K * G.Cout;
-  float* sx = wsm;                         // [WS_VOX][K + 1]
-  float* sdy = wsm + WS_VOX * (K + 1);     // [WS_VOX][Cout]
+  extern __shared__ __align__(16) float wsm[];
+  const int Cin = G.C1, K = G.k * G.k * G.k * Cin, ncg = G.Cout / 4;
+  float* sdy = wsm;                            // [WS_VOX][Cout]   (16-byte aligned rows: Cout % 4 == 0)
+  float* sx = wsm + WS_VOX * G.Cout;           // [WS_VOX][K + 1]
   const int rad = G.k / 2;
   const long long nvox = (long long)G.B * G.d0 * G.d1 * G.d2;
-  float acc[WS_MAXOUT];
-#pragma unroll
-  for (int e = 0; e < WS_MAXOUT; ++e) acc[e] = 0.f;
+  const int r = threadIdx.x / ncg, cg = threadIdx.x % ncg;
+  const bool active = r < K;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long base = (long long)blockIdx.x * WS_VOX; base < nvox; base += (long long)gridDim.x * WS_VOX) {
-    for (int e = threadIdx.x; e < WS_VOX * K; e += blockDim.x) {
-      const int vi = e / K, r = e % K;
-      const int ci = r % Cin, tap = r / Cin;
-      const int c = tap % G.k, bb = (tap / G.k) % G.k, a = tap / (G.k * G.k);
+    if (threadIdx.x < WS_VOX) {
+      const int vi = threadIdx.x;
       const long long v = base + vi;
-      float val = 0.f;
-      if (v < nvox) {
-        long long q = v;
-        const int i2 = (int)(q % G.d2); q /= G.d2;
-        const int i1 = (int)(q % G.d1); q /= G.d1;
-        const int i0 = (int)(q % G.d0);
-        const int b = (int)(q / G.d0);
-        const int j0 = i0 + a - rad, j1 = i1 + bb - rad, j2 = i2 + c - rad;
-        if (j0 >= 0 && j0 < G.d0 && j1 >= 0 && j1 < G.d1 && j2 >= 0 && j2 < G.d2)
-          val = x[((((long long)b * G.d0 + j0) * G.d1 + j1) * G.d2 + j2) * Cin + ci];
-      }
-      sx[vi * (K + 1) + r] = val;
+      long long q = v;
+      const int i2 = (int)(q % G.d2); q /= G.d2;
+      const int i1 = (int)(q % G.d1); q /= G.d1;
+      const int i0 = (int)(q % G.d0);
+      const int b = (int)(q / G.d0);
+      float* row = sx + vi * (K + 1);
+      for (int a = 0; a < G.k; ++a)
+        for (int bb = 0; bb < G.k; ++bb)
+          for (int c = 0; c < G.k; ++c) {
+            const int j0 = i0 + a - rad, j1 = i1 + bb - rad, j2 = i2 + c - rad;
+            const bool ok = v < nvox && j0 >= 0 && j0 < G.d0 && j1 >= 0 && j1 < G.d1 && j2 >= 0 && j2 < G.d2;
+            const long long nv = (((long long)b * G.d0 + j0) * G.d1 + j1) * G.d2 + j2;
+            for (int ci = 0; ci < Cin; ++ci) row[((a * G.k + bb) * G.k + c) * Cin + ci] = ok ? x[nv * Cin + ci] : 0.f;
+          }
     }
-    for (int e = threadIdx.x; e < WS_VOX * G.Cout; e += blockDim.x) {
-      const long long v = base + e / G.Cout;
-      sdy[e] = v < nvox ? dy[v * G.Cout + e % G.Cout] : 0.f;
+    for (int e = threadIdx.x; e < WS_VOX * ncg; e += blockDim.x) {
+      const long long v = base + e / ncg;
+      reinterpret_cast<float4*>(sdy)[e] =
+          v < nvox ? reinterpret_cast<const float4*>(dy)[v * ncg + e % ncg] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
-#pragma unroll
-    for (int e = 0; e < WS_MAXOUT; ++e) {
-      const int o = threadIdx.x + e * 256;
-      if (o < nout) {
-        const int r = o / G.Cout, col = o % G.Cout;
-        float a2 = 0.f;
-        for (int vi = 0; vi < WS_VOX; ++vi) a2 += sx[vi * (K + 1) + r] * sdy[vi * G.Cout + col];
-        acc[e] += a2;
+    if (active) {
+#pragma unroll 4
+      for (int vi = 0; vi < WS_VOX; ++vi) {
+        const float xv = sx[vi * (K + 1) + r];
+        const float4 d = reinterpret_cast<const float4*>(sdy)[vi * ncg + cg];
+        acc.x += xv * d.x; acc.y += xv * d.y; acc.z += xv * d.z; acc.w += xv * d.w;
       }
     }
     __syncthreads();
   }
-#pragma unroll
-  for (int e = 0; e < WS_MAXOUT; ++e) {
-    const int o = threadIdx.x + e * 256;
-    if (o < nout) atomicAdd(dw + o, acc[e]);     // dw layout (tap, ci, co) == o
+  if (active) {
+    float* o = dw + (long long)r * G.Cout + cg * 4;     // dw layout (tap, ci, co): row r = tap*Cin + ci
+    atomicAdd(o + 0, acc.x); atomicAdd(o + 1, acc.y); atomicAdd(o + 2, acc.z); atomicAdd(o + 3, acc.w);
   }
 }
 
@@ -300,49 +299,64 @@ __global__ void bn_stats_from_moving_kernel(int C, const float* __restrict__ gam
 }
 
 // mode 0: y = BN(x);  mode 1: y = maxpool2('same')(BN(x));  mode 2: y = upsample2(BN(x)) into a channel slice
+// VEC = 4: float4 over channels (C, dst_stride, dst_off multiples of 4), VEC = 1: scalar fallback
+template <int VEC>
+__device__ __forceinline__ void ldv(const float* p, float* v) {
+  if (VEC == 4) { const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  else v[0] = p[0];
+}
+
+template <int VEC>
 __global__ void bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ stats,
                                 int B, int d0, int d1, int d2, int C, int mode, int dst_stride, int dst_off) {
   const float* scale = stats + 2 * C;
   const float* shift = stats + 3 * C;
-  if (mode == 0) {
-    const long long n = (long long)B * d0 * d1 * d2 * C;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-      const int c = (int)(t % C);
-      y[(t / C) * dst_stride + dst_off + c] = x[t] * scale[c] + shift[c];
-    }
-  } else if (mode == 1) {
-    const int o0 = (d0 + 1) / 2, o1 = (d1 + 1) / 2, o2 = (d2 + 1) / 2;
-    const long long n = (long long)B * o0 * o1 * o2 * C;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-      const int c = (int)(t % C);
-      long long r = t / C;
+  const int CV = C / VEC;
+  int o0 = d0, o1 = d1, o2 = d2;
+  if (mode == 1) { o0 = (d0 + 1) / 2; o1 = (d1 + 1) / 2; o2 = (d2 + 1) / 2; }
+  if (mode == 2) { o0 = d0 * 2; o1 = d1 * 2; o2 = d2 * 2; }
+  const long long n = (long long)B * o0 * o1 * o2 * CV;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(t % CV);
+    const long long vo = t / CV;
+    float sc[VEC], sh[VEC], out[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) { sc[e] = scale[cv * VEC + e]; sh[e] = shift[cv * VEC + e]; }
+    if (mode == 0) {
+      float v[VEC];
+      ldv<VEC>(x + vo * C + cv * VEC, v);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) out[e] = v[e] * sc[e] + sh[e];
+    } else {
+      long long r = vo;
       const int k = (int)(r % o2); r /= o2;
       const int j = (int)(r % o1); r /= o1;
       const int i = (int)(r % o0);
       const int b = (int)(r / o0);
-      float m = -CUDART_INF_F;
-      for (int a = 0; a < 2; ++a)
-        for (int bb = 0; bb < 2; ++bb)
-          for (int cc = 0; cc < 2; ++cc) {
-            const int s0 = 2 * i + a, s1 = 2 * j + bb, s2 = 2 * k + cc;
-            if (s0 < d0 && s1 < d1 && s2 < d2)
-              m = fmaxf(m, x[((((long long)b * d0 + s0) * d1 + s1) * d2 + s2) * C + c] * scale[c] + shift[c]);
-          }
-      y[(t / C) * dst_stride + dst_off + c] = m;
+      if (mode == 2) {
+        float v[VEC];
+        ldv<VEC>(x + ((((long long)b * d0 + i / 2) * d1 + j / 2) * d2 + k / 2) * C + cv * VEC, v);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) out[e] = v[e] * sc[e] + sh[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) out[e] = -CUDART_INF_F;
+        for (int a = 0; a < 2; ++a)
+          for (int bb = 0; bb < 2; ++bb)
+            for (int cc = 0; cc < 2; ++cc) {
+              const int s0 = 2 * i + a, s1 = 2 * j + bb, s2 = 2 * k + cc;
+              if (s0 < d0 && s1 < d1 && s2 < d2) {
+                float v[VEC];
+                ldv<VEC>(x + ((((long long)b * d0 + s0) * d1 + s1) * d2 + s2) * C + cv * VEC, v);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) out[e] = fmaxf(out[e], v[e] * sc[e] + sh[e]);
+              }
+            }
+      }
     }
-  } else {
-    const int o0 = d0 * 2, o1 = d1 * 2, o2 = d2 * 2;
-    const long long n = (long long)B * o0 * o1 * o2 * C;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-      const int c = (int)(t % C);
-      long long r = t / C;
-      const int k = (int)(r % o2); r /= o2;
-      const int j = (int)(r % o1); r /= o1;
-      const int i = (int)(r % o0);
-      const int b = (int)(r / o0);
-      const float v = x[((((long long)b * d0 + i / 2) * d1 + j / 2) * d2 + k / 2) * C + c];
-      y[(t / C) * dst_stride + dst_off + c] = v * scale[c] + shift[c];
-    }
+    float* q = y + vo * dst_stride + dst_off + cv * VEC;
+    if (VEC == 4) *reinterpret_cast<float4*>(q) = make_float4(out[0], out[1], out[2], out[3]);
+    else q[0] = out[0];
   }
 }
 
@@ -667,13 +681,16 @@ int ssr_conv3d_wgrad_ref(const float* x1, int C1, const float* x2, int C2, const
   ConvGeom G{B, d0, d1, d2, C1, C2, Cout, k, 0};
   const long long nvox = (long long)B * d0 * d1 * d2;
   const int Ksmall = k * k * k * C1;
-  if (C2 == 0 && C1 <= 4 && Ksmall * Cout <= 256 * WS_MAXOUT && nvox >= 4096) {
+  if (C2 == 0 && C1 <= 4 && Cout % 4 == 0 && Ksmall * (Cout / 4) <= 384 && nvox >= 4096 &&
+      ((uintptr_t)dy & 15) == 0) {
     const size_t smem = (size_t)WS_VOX * (Ksmall + 1 + Cout) * sizeof(float);
     if (smem > 48 * 1024)
       SSR_CHECK_CUDA(cudaFuncSetAttribute(wgrad_small_cin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long nb = (nvox + WS_VOX - 1) / WS_VOX;
     if (nb > 148 * 4) nb = 148 * 4;
-    wgrad_small_cin_kernel<<<(unsigned)nb, 256, smem, st>>>(x1, dy, dw, G);
+    int nthr = (Ksmall * (Cout / 4) + 31) / 32 * 32;
+    if (nthr < WS_VOX) nthr = WS_VOX;
+    wgrad_small_cin_kernel<<<(unsigned)nb, nthr, smem, st>>>(x1, dy, dw, G);
   } else {
     int nsplit = (int)((nvox + 32767) / 32768);
     if (nsplit > 64) nsplit = 64;
@@ -736,8 +753,13 @@ int ssr_bn_apply(const float* x, float* y, const float* stats, int B, int d0, in
   long long n = (long long)B * d0 * d1 * d2 * C;
   if (mode == 1) n = (long long)B * ((d0 + 1) / 2) * ((d1 + 1) / 2) * ((d2 + 1) / 2) * C;
   if (mode == 2) n *= 8;
-  bn_apply_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, y, stats, B, d0, d1, d2, C, mode, dst_stride,
-                                                                 dst_off);
+  const bool vec = (C % 4 == 0) && (dst_stride % 4 == 0) && (dst_off % 4 == 0) && (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+  if (vec)
+    bn_apply_kernel<4><<<grid_for(n / 4), 256, 0, (cudaStream_t)stream>>>(x, y, stats, B, d0, d1, d2, C, mode,
+                                                                         dst_stride, dst_off);
+  else
+    bn_apply_kernel<1><<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, y, stats, B, d0, d1, d2, C, mode, dst_stride,
+                                                                      dst_off);
   SSR_COUNT_LAUNCH();
   SSR_CHECK_LAUNCH();
   return SSR_OK;
