@@ -1,0 +1,206 @@
+"""`SynthSR.training.training()` with the reference's signature (SynthSR/training.py:38-89) on the B200 engine.
+
+Every step: host sampler (label map + GMM parameters) -> CUDA generator -> U-Net forward/backward (tcgen05 TF32
+convolutions) -> [single NCCL all-reduce of the flat gradient buffer when launched with torchrun] -> fused Adam.
+One checkpoint per epoch named %03d (Keras layer names inside; .npz because no HDF5 writer is available)."""
+import os
+import time
+
+import numpy as np
+
+from ext.lab2im import utils
+from ext.neuron import models as nrn_models
+
+from .brain_generator import BrainGenerator
+from .metrics_model import IdentityLoss, add_seg_loss_to_model, metrics_model  # noqa: F401
+
+
+def training(labels_dir,
+             model_dir,
+             prior_means,
+             prior_stds,
+             path_generation_labels,
+             segmentation_label_list=None,
+             segmentation_label_equivalency=None,
+             segmentation_model_file=None,
+             fs_header_segnet=False,
+             relative_weight_segmentation=0.25,
+             prior_distributions='normal',
+             images_dir=None,
+             path_generation_classes=None,
+             FS_sort=True,
+             batchsize=1,
+             input_channels=True,
+             output_channel=0,
+             target_res=None,
+             output_shape=None,
+             flipping=True,
+             padding_margin=None,
+             scaling_bounds=0.15,
+             rotation_bounds=15,
+             shearing_bounds=0.02,
+             translation_bounds=5,
+             nonlin_std=4.,
+             nonlin_shape_factor=0.03125,
+             simulate_registration_error=True,
+             data_res=None,
+             thickness=None,
+             randomise_res=None,
+             downsample=True,
+             blur_range=1.15,
+             build_reliability_maps=True,
+             bias_field_std=.3,
+             bias_shape_factor=0.03125,
+             n_levels=5,
+             nb_conv_per_level=2,
+             conv_size=3,
+             unet_feat_count=24,
+             feat_multiplier=2,
+             dropout=0,
+             activation='elu',
+             lr=1e-4,
+             lr_decay=0,
+             epochs=100,
+             steps_per_epoch=1000,
+             regression_metric='l1',
+             work_with_residual_channel=None,
+             loss_cropping=None,
+             checkpoint=None,
+             model_file_has_different_lhood_layer=False):
+    n_channels = len(utils.reformat_to_list(input_channels))
+    if output_channel is not None:
+        output_channel = list(utils.reformat_to_list(output_channel))
+        n_output_channels = len(output_channel)
+    else:
+        n_output_channels = 1
+    # same checks and messages as the reference (training.py:252-268)
+    if (images_dir is None) & (output_channel is None):
+        raise Exception('please provide a value for output_channel or image_dir')
+    elif (images_dir is not None) & (output_channel is not None):
+        raise Exception('please provide a value either for output_channel or image_dir, but not both at the same time')
+    if output_channel is not None:
+        if any(x >= n_channels for x in output_channel):
+            raise Exception('indices in output_channel cannot be greater than the total number of channels')
+    if work_with_residual_channel is not None:
+        work_with_residual_channel = utils.reformat_to_list(work_with_residual_channel)
+        if output_channel is not None:
+            if len(work_with_residual_channel) != len(output_channel):
+                raise Exception('The number or residual channels and output channels must be the same')
+        if any(x >= n_channels for x in work_with_residual_channel):
+            raise Exception('indices in work_with_residual_channel cannot be greater than the total number of channels')
+        if build_reliability_maps:
+            # reference :270-271 does `2 * list` (repeats the list instead of doubling the indices); the indices
+            # address image_out channels [ch0, rel0, ch1, rel1, ...] (metrics_model.py:58-59), so double them here.
+            work_with_residual_channel = [2 * int(c) for c in work_with_residual_channel]
+    if segmentation_model_file is not None:
+        add_seg_loss_to_model()
+
+    generation_labels, n_neutral_labels = utils.get_list_labels(label_list=path_generation_labels,
+                                                                labels_dir=labels_dir, FS_sort=FS_sort)
+    utils.mkdir(model_dir)
+    if loss_cropping == 0:
+        padding_margin = None
+    elif padding_margin is None:
+        padding_margin = utils.get_padding_margin(output_shape, loss_cropping)
+
+    brain_generator = BrainGenerator(labels_dir=labels_dir, images_dir=images_dir, generation_labels=generation_labels,
+                                     n_neutral_labels=n_neutral_labels, padding_margin=padding_margin,
+                                     batchsize=batchsize, input_channels=input_channels, output_channel=output_channel,
+                                     target_res=target_res, output_shape=output_shape, output_div_by_n=2 ** n_levels,
+                                     generation_classes=path_generation_classes, prior_means=prior_means,
+                                     prior_stds=prior_stds, prior_distributions=prior_distributions, flipping=flipping,
+                                     scaling_bounds=scaling_bounds, rotation_bounds=rotation_bounds,
+                                     shearing_bounds=shearing_bounds, translation_bounds=translation_bounds,
+                                     nonlin_std=nonlin_std, nonlin_shape_factor=nonlin_shape_factor,
+                                     simulate_registration_error=simulate_registration_error,
+                                     randomise_res=randomise_res, data_res=data_res, thickness=thickness,
+                                     downsample=downsample, blur_range=blur_range,
+                                     build_reliability_maps=build_reliability_maps, bias_field_std=bias_field_std,
+                                     bias_shape_factor=bias_shape_factor)
+    if dropout:
+        raise NotImplementedError('dropout is not part of this build (the reference recommends dropout=0)')
+    nb_labels_unet = n_output_channels
+    plan = brain_generator.labels_to_image_model.plan
+
+    from synthsr_b200.trainer import TrainingEngine
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', 0)))
+        if not dist.is_initialized():
+            dist.init_process_group('nccl')
+    engine = TrainingEngine(plan, batchsize=batchsize, nb_features=unet_feat_count, nb_levels=n_levels,
+                            conv_size=conv_size, feat_mult=feat_multiplier, nb_conv_per_level=nb_conv_per_level,
+                            nb_labels=nb_labels_unet, lr=lr, lr_decay=lr_decay, metric=regression_metric,
+                            work_with_residual_channel=work_with_residual_channel, loss_cropping=loss_cropping,
+                            rank=rank, world_size=world)
+    # the Keras-style handles the reference builds (kept so client code can introspect the same objects)
+    model = metrics_model(nrn_models.UnetModel(engine.net, brain_generator.labels_to_image_model),
+                          loss_cropping=loss_cropping, metrics=regression_metric,
+                          work_with_residual_channel=work_with_residual_channel)
+    input_generator = utils.build_training_generator(brain_generator.model_inputs_generator, batchsize)
+
+    init_epoch = 0
+    if checkpoint is not None:
+        print('loading', checkpoint)
+        init_epoch = load_checkpoint(engine, checkpoint, model_file_has_different_lhood_layer)
+    train_model(engine, input_generator, lr, lr_decay, epochs, steps_per_epoch, model_dir, init_epoch)
+    return model
+
+
+def load_checkpoint(engine, path, different_lhood_layer=False):
+    """weights by Keras layer name (+ Adam state and epoch when the file holds them).  A file whose name ends with a
+    3-digit epoch resumes at that epoch like the reference (training.py:434-435)."""
+    sd = dict(np.load(path))
+    if different_lhood_layer:
+        sd = {k: v for k, v in sd.items() if not k.startswith('unet_likelihood')}
+    engine.net.load_state_dict({k: v for k, v in sd.items() if not k.startswith('optimizer/')}, strict=False)
+    if 'optimizer/m' in sd and not different_lhood_layer:
+        import torch
+        engine.net.adam_m.copy_(torch.as_tensor(sd['optimizer/m']))
+        engine.net.adam_v.copy_(torch.as_tensor(sd['optimizer/v']))
+        engine.net.iterations = int(sd['optimizer/iterations'])
+    stem = os.path.splitext(os.path.basename(path))[0]
+    return int(stem[-3:]) if stem[-3:].isdigit() else 0
+
+
+def save_checkpoint(engine, path):
+    sd = engine.net.state_dict()
+    sd['optimizer/m'] = engine.net.adam_m.cpu().numpy()
+    sd['optimizer/v'] = engine.net.adam_v.cpu().numpy()
+    sd['optimizer/iterations'] = np.int64(engine.net.iterations)
+    np.savez(path, **sd)
+
+
+def train_model(engine, generator, learning_rate, lr_decay, n_epochs, n_steps, model_dir, init_epoch=0):
+    """epochs x steps loop of the reference's fit_generator call (training.py:449-453) with one checkpoint per epoch
+    ('%03d', :429) and a plain-text loss log under model_dir/logs (:425-431 uses TensorBoard)."""
+    import torch
+    log_dir = os.path.join(model_dir, 'logs')
+    utils.mkdir(log_dir)
+    engine.lr, engine.lr_decay = learning_rate, lr_decay
+    is_main = engine.rank == 0
+    log = open(os.path.join(log_dir, 'loss.csv'), 'a') if is_main else None
+    for epoch in range(init_epoch, n_epochs):
+        t0, losses = time.time(), []
+        for step in range(n_steps):
+            inputs, _ = next(generator)
+            labels = torch.as_tensor(np.ascontiguousarray(np.asarray(inputs[0])[..., 0], dtype=np.int32))
+            labels = labels.pin_memory().cuda(non_blocking=True)
+            real = None
+            if len(inputs) > 3:
+                real = torch.as_tensor(np.ascontiguousarray(np.asarray(inputs[3])[..., 0], dtype=np.float32)).cuda()
+            losses.append(engine.train_step(labels, inputs[1], inputs[2], real_image=real))
+        loss = float(torch.stack([l.reshape(()) for l in losses]).mean().item())
+        if not np.isfinite(loss):
+            raise FloatingPointError('Loss not finite')              # tf.debugging.check_numerics (metrics_model.py:228)
+        if is_main:
+            dt = time.time() - t0
+            print('Epoch %d/%d - %ds - loss: %.4f - %.2f volumes/s' % (epoch + 1, n_epochs, dt, loss,
+                                                                       n_steps * engine.B * engine.world / dt))
+            log.write('%d,%.6f,%.3f\n' % (epoch + 1, loss, dt))
+            log.flush()
+            save_checkpoint(engine, os.path.join(model_dir, '%03d.npz' % (epoch + 1)))
+    if log:
+        log.close()

@@ -1,0 +1,54 @@
+"""Runs single tcgen05 convolution launches at the headline sizes (for ncu captures and quick timing).
+    python scripts/profile_conv.py [fwd24|fwd72|wgrad24|wgrad72|all] [reps]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from synthsr_b200._lib import lib, stream_ptr  # noqa: E402
+
+CASES = {'fwd24': ('fwd', [160, 160, 160], 24, 0, 24), 'fwd72': ('fwd', [160, 160, 160], 24, 48, 24),
+         'fwd48': ('fwd', [80, 80, 80], 48, 0, 48), 'fwd96': ('fwd', [40, 40, 40], 96, 0, 96),
+         'fwd384': ('fwd', [10, 10, 10], 384, 0, 384), 'dgrad72': ('fwd', [160, 160, 160], 24, 0, 72),
+         'wgrad24': ('wgrad', [160, 160, 160], 24, 0, 24), 'wgrad72': ('wgrad', [160, 160, 160], 24, 48, 24),
+         'wgrad96': ('wgrad', [40, 40, 40], 96, 0, 96)}
+
+
+def run(name, reps):
+    kind, d, c1, c2, co = CASES[name]
+    nv = int(np.prod(d))
+    g = torch.Generator(device='cuda').manual_seed(0)
+    x1 = torch.randn((nv, c1), device='cuda', generator=g)
+    x2 = torch.randn((nv, c2), device='cuda', generator=g) if c2 else None
+    st = stream_ptr()
+    flops = 2. * 27 * (c1 + c2) * co * nv
+    if kind == 'fwd':
+        w = torch.randn((3, 3, 3, c1 + c2, co), device='cuda', generator=g) / np.sqrt(27 * (c1 + c2))
+        b = torch.zeros(co, device='cuda')
+        y = torch.empty((nv, co), device='cuda')
+        wp = torch.empty(lib.ssr_conv3d_packed_size(c1, c2, co, 0), device='cuda')
+        lib.ssr_conv3d_pack_weights(w, wp, c1, c2, co, 0, st)
+        fn = lambda: lib.ssr_conv3d_fwd_tc(x1, c1, x2, c2, wp, b, y, 1, *d, co, 1, st)
+    else:
+        dy = torch.randn((nv, co), device='cuda', generator=g)
+        dw = torch.zeros(27 * (c1 + c2) * co, device='cuda')
+        fn = lambda: lib.ssr_conv3d_wgrad_tc(x1, c1, x2, c2, dy, dw, None, None, 0, 1, *d, co, st)
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print('%-8s %s c=%d+%d->%d  %.3f ms  %.1f TFLOP/s' % (name, d, c1, c2, co, ms, flops / ms / 1e9))
+
+
+if __name__ == '__main__':
+    which = sys.argv[1] if len(sys.argv) > 1 else 'all'
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    for n in (CASES if which == 'all' else which.split(',')):
+        run(n, reps)

@@ -281,40 +281,58 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             mbar_wait(fullB + sb, pb);
             const uint32_t blo0 = desc_lo(smem_u32(sB + (size_t)sb * bgroup_bytes), 16);
             const uint32_t btile16 = (uint32_t)(G.NT * 128) >> 4;
-            for (int zin = 0; zin < G.TZ + G.KG - 1; ++zin) {
-              if (!slab_needed(G, z0, k0g, zin)) continue;
-              mbar_wait(fullA + sa, pa);
+            // Consecutive MMAs into the SAME accumulator serialise on the accumulate dependency (~110 cycles each,
+            // profiles/r01_conv_fwd24_ncu.txt), so MMAs are issued round-robin over independent accumulators:
+            //   KG == 3: one slab at a time, its (up to) three accumulators zo = zin - kk interleaved;
+            //   KG == 1: a batch of up to 4 slabs (one accumulator each) interleaved.
+            const int nslab = G.TZ + G.KG - 1;
+            for (int zb = 0; zb < nslab;) {
+              int batch_zin[4], batch_sa[4], nb = 0;
+              const int want = G.KG == 3 ? 1 : 4;
+              while (zb < nslab && nb < want) {
+                if (slab_needed(G, z0, k0g, zb)) {
+                  mbar_wait(fullA + sa, pa);
+                  batch_zin[nb] = zb; batch_sa[nb] = sa; ++nb;
+                  if (++sa == G.SA) { sa = 0; pa ^= 1; }
+                }
+                ++zb;
+              }
+              if (nb == 0) continue;
               tc_fence_after();
-              const uint32_t alo0 = desc_lo(smem_u32(sA + (size_t)sa * SLAB_BYTES), 16);
+              // list of (accumulator column, A descriptor base, B tap base, accumulate flag) for this batch
+              uint32_t l_d[4], l_a[4], l_b[4], l_acc[4];
+              int nl = 0;
+              for (int i = 0; i < nb; ++i)
+                for (int kk = 0; kk < G.KG; ++kk) {
+                  const int zo = batch_zin[i] - kk;
+                  if (zo < 0 || zo >= G.TZ || z0 + zo >= G.D0) continue;
+                  l_d[nl] = tmem_base + (uint32_t)(zo * G.NT);
+                  l_a[nl] = desc_lo(smem_u32(sA + (size_t)batch_sa[i] * SLAB_BYTES), 16);
+                  l_b[nl] = blo0 + (uint32_t)(kk * 3) * btile16;
+                  l_acc[nl] = (started >> zo) & 1u;
+                  started |= 1u << zo;
+                  ++nl;
+                }
               if (elect_one()) {
 #pragma unroll
-              for (int kk = 0; kk < 3; ++kk) {
-                if (kk >= G.KG) break;
-                const int zo = zin - kk;
-                if (zo < 0 || zo >= G.TZ || z0 + zo >= G.D0) continue;
-                const uint32_t dcol = tmem_base + (uint32_t)(zo * G.NT);
-                uint32_t acc = (started >> zo) & 1u;
-#pragma unroll
                 for (int k1 = 0; k1 < 3; ++k1) {
-                  const uint32_t alo = alo0 + (uint32_t)(k1 * (TM2 * 128 >> 4));
-                  const uint32_t blo = blo0 + (uint32_t)(kk * 3 + k1) * btile16;
 #pragma unroll
                   for (int ks = 0; ks < 4; ++ks) {
                     if (ks < nks) {
-                      umma_tf32_lh(dcol, alo + ks * 2, blo + ks * 2, DESC_HI_K_SW128, idesc, acc);
-                      acc = 1u;
+#pragma unroll
+                      for (int j = 0; j < 4; ++j) {
+                        if (j < nl) {
+                          umma_tf32_lh(l_d[j], l_a[j] + (uint32_t)(k1 * (TM2 * 128 >> 4) + ks * 2),
+                                       l_b[j] + (uint32_t)k1 * btile16 + ks * 2, DESC_HI_K_SW128, idesc, l_acc[j]);
+                          l_acc[j] = 1u;
+                        }
+                      }
                     }
                   }
                 }
-              }
-                umma_commit(emptyA + sa);          // slab may be overwritten once these MMAs have completed
+                for (int i = 0; i < nb; ++i) umma_commit(emptyA + batch_sa[i]);   // slabs free once these MMAs completed
               }
               __syncwarp();
-              for (int kk = 0; kk < G.KG; ++kk) {  // bookkeeping replicated on every lane (warp-uniform)
-                const int zo = zin - kk;
-                if (zo >= 0 && zo < G.TZ && z0 + zo < G.D0) started |= 1u << zo;
-              }
-              if (++sa == G.SA) { sa = 0; pa ^= 1; }
             }
             if (elect_one()) umma_commit(emptyB + sb);
             __syncwarp();
@@ -491,21 +509,28 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
           mbar_wait(fullA + sa, pa);
           tc_fence_after();
           const uint32_t alo0 = desc_lo(smem_u32(sA + (size_t)sa * SLAB_BYTES), 1024);      // M atoms = d1 taps
-          if (elect_one()) {
-#pragma unroll
-          for (int kk = 0; kk < 3; ++kk) {
-            if (kk >= G.KG) break;
+          uint32_t l_d[3], l_b[3], l_acc[3];
+          int nl = 0;
+          for (int kk = 0; kk < G.KG; ++kk) {
             const int zo = zin - (k0g + kk) + 1;
             if (zo < zs || zo >= ze) continue;
-            const uint32_t blo0 = desc_lo(smem_u32(sB + (size_t)((zo - zs) % G.SBT) * bstage), WG_BTILE_BYTES);
-            const uint32_t dcol = tmem_base + (uint32_t)(kk * G.NT);
-            uint32_t acc = (started >> kk) & 1u;
+            l_b[nl] = desc_lo(smem_u32(sB + (size_t)((zo - zs) % G.SBT) * bstage), WG_BTILE_BYTES);
+            l_d[nl] = tmem_base + (uint32_t)(kk * G.NT);
+            l_acc[nl] = (started >> kk) & 1u;
+            ++nl;
+          }
+          if (elect_one()) {
+            // round-robin over the (up to 3) independent accumulators: same-accumulator MMAs serialise otherwise
 #pragma unroll
             for (int s = 0; s < TM1; ++s) {          // 16 K-steps of 8 voxels (one d1 row of the tile each)
-              umma_tf32_lh(dcol, alo0 + s * (1024 >> 4), blo0 + s * (1024 >> 4), DESC_HI_MN_SW128_32B, idesc, acc);
-              acc = 1u;
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                if (j < nl) {
+                  umma_tf32_lh(l_d[j], alo0 + s * (1024 >> 4), l_b[j] + s * (1024 >> 4), DESC_HI_MN_SW128_32B, idesc, l_acc[j]);
+                  l_acc[j] = 1u;
+                }
+              }
             }
-          }
             umma_commit(emptyA + sa);
           }
           __syncwarp();

@@ -50,19 +50,25 @@ class TrainingEngine:
         return loss
 
     def _allreduce(self, loss):
-        """single NCCL all-reduce per step: [gradients | BN moving stats | loss]."""
-        import torch.distributed as dist
-        net, n = self.net, self.net.n_params
-        self.flat[:n].copy_(net.grads)
-        o = n
-        for t in net.moving.values():
-            self.flat[o:o + t.numel()].copy_(t)
-            o += t.numel()
-        self.flat[o] = loss[0].float()
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-        net.grads.copy_(self.flat[:n])
-        o = n
-        for t in net.moving.values():
-            t.copy_(self.flat[o:o + t.numel()] / self.world)
-            o += t.numel()
-        return (self.flat[o:o + 1] / self.world).double()
+        return allreduce_step(self.net.grads, list(self.net.moving.values()), loss, self.flat, self.world)
+
+
+def allreduce_step(grads, moving, loss, flat, world):
+    """THE one collective of the data-parallel step: a single SUM all-reduce of [gradients | BN moving stats | loss].
+    Gradients are left SUMMED in `grads` (Adam applies the 1/world scale), moving statistics and the loss are
+    averaged in place.  Device agnostic (NCCL on GPUs, gloo in the CPU tests).  Returns the mean loss (float64)."""
+    import torch.distributed as dist
+    n = grads.numel()
+    flat[:n].copy_(grads)
+    o = n
+    for t in moving:
+        flat[o:o + t.numel()].copy_(t.reshape(-1))
+        o += t.numel()
+    flat[o] = loss.reshape(-1)[0].to(flat.dtype)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    grads.copy_(flat[:n])
+    o = n
+    for t in moving:
+        t.copy_((flat[o:o + t.numel()] / world).reshape(t.shape))
+        o += t.numel()
+    return (flat[o:o + 1] / world).double()
