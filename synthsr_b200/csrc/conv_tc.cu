@@ -38,21 +38,21 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU
+// bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.  The suspend-time hint lets the
+// hardware put the waiting warp to sleep, so warps parked on a barrier do not steal issue slots from the MMA warp.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
-  const long long t0 = clock64();
-  while (true) {
+  for (int spin = 0;; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(0x989680u)
         : "memory");
     if (done) break;
-    if (clock64() - t0 > 8000000000LL) { printf("conv_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    if (spin > 2000) { printf("conv_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -143,6 +143,32 @@ __device__ __forceinline__ void umma_tf32_lh(uint32_t d_tmem, uint32_t alo, uint
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
       ::"r"(d_tmem), "r"(alo), "r"(blo), "r"(hi), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+
+// NK back-to-back MMAs into one accumulator, both descriptors advancing by `STEP` (in 16-byte units) per MMA, emitted
+// as ONE asm block: the issuing warp is alone on its instruction stream, so every extra (dependent, uniform-datapath)
+// instruction between two UTCHMMAs costs ~10 cycles; a tight chain sustains the tensor-core rate
+// (profiles/r01_mma_issue_microbench.txt: 40 cycles per M128xN32xK8 MMA).
+#define SSR_MMA1 "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t"
+#define SSR_MMAN(STEP) "add.s64 da, da, " #STEP ";\n\tadd.s64 db, db, " #STEP ";\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, q;\n\t"
+#define SSR_MMA_HEAD "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t" \
+                     "setp.ne.b32 p, %5, 0;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+#define SSR_MMA_ARGS ::"r"(d_tmem), "r"(alo), "r"(blo), "r"(hi), "r"(idesc), "r"(accumulate), "r"(1u) : "memory"
+
+template <int NK>
+__device__ __forceinline__ void umma_chain_k(uint32_t d_tmem, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc,
+                                             uint32_t accumulate) {   // K-major operands: +32 B per K-step
+  if (NK == 1) asm volatile(SSR_MMA_HEAD SSR_MMA1 "}" SSR_MMA_ARGS);
+  if (NK == 2) asm volatile(SSR_MMA_HEAD SSR_MMA1 SSR_MMAN(2) "}" SSR_MMA_ARGS);
+  if (NK == 3) asm volatile(SSR_MMA_HEAD SSR_MMA1 SSR_MMAN(2) SSR_MMAN(2) "}" SSR_MMA_ARGS);
+  if (NK == 4) asm volatile(SSR_MMA_HEAD SSR_MMA1 SSR_MMAN(2) SSR_MMAN(2) SSR_MMAN(2) "}" SSR_MMA_ARGS);
+}
+// 16 K-steps of the weight-gradient tile (MN-major operands: +1024 B per K-step)
+__device__ __forceinline__ void umma_chain_mn16(uint32_t d_tmem, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(SSR_MMA_HEAD SSR_MMA1 SSR_MMAN(64) SSR_MMAN(64) SSR_MMAN(64) SSR_MMAN(64) SSR_MMAN(64) SSR_MMAN(64)
+               SSR_MMAN(64) SSR_MMAN(64) SSR_MMAN(64) SSR_MMAN(64) SSR_MMAN(64) SSR_MMAN(64) SSR_MMAN(64) SSR_MMAN(64)
+               SSR_MMAN(64) "}" SSR_MMA_ARGS);
 }
 
 // instruction descriptor: D=F32, A=B=TF32, both K-major, M=128, N
@@ -281,58 +307,38 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             mbar_wait(fullB + sb, pb);
             const uint32_t blo0 = desc_lo(smem_u32(sB + (size_t)sb * bgroup_bytes), 16);
             const uint32_t btile16 = (uint32_t)(G.NT * 128) >> 4;
-            // Consecutive MMAs into the SAME accumulator serialise on the accumulate dependency (~110 cycles each,
-            // profiles/r01_conv_fwd24_ncu.txt), so MMAs are issued round-robin over independent accumulators:
-            //   KG == 3: one slab at a time, its (up to) three accumulators zo = zin - kk interleaved;
-            //   KG == 1: a batch of up to 4 slabs (one accumulator each) interleaved.
-            const int nslab = G.TZ + G.KG - 1;
-            for (int zb = 0; zb < nslab;) {
-              int batch_zin[4], batch_sa[4], nb = 0;
-              const int want = G.KG == 3 ? 1 : 4;
-              while (zb < nslab && nb < want) {
-                if (slab_needed(G, z0, k0g, zb)) {
-                  mbar_wait(fullA + sa, pa);
-                  batch_zin[nb] = zb; batch_sa[nb] = sa; ++nb;
-                  if (++sa == G.SA) { sa = 0; pa ^= 1; }
-                }
-                ++zb;
-              }
-              if (nb == 0) continue;
+            for (int zin = 0; zin < G.TZ + G.KG - 1; ++zin) {
+              if (!slab_needed(G, z0, k0g, zin)) continue;
+              mbar_wait(fullA + sa, pa);
               tc_fence_after();
-              // list of (accumulator column, A descriptor base, B tap base, accumulate flag) for this batch
-              uint32_t l_d[4], l_a[4], l_b[4], l_acc[4];
-              int nl = 0;
-              for (int i = 0; i < nb; ++i)
-                for (int kk = 0; kk < G.KG; ++kk) {
-                  const int zo = batch_zin[i] - kk;
-                  if (zo < 0 || zo >= G.TZ || z0 + zo >= G.D0) continue;
-                  l_d[nl] = tmem_base + (uint32_t)(zo * G.NT);
-                  l_a[nl] = desc_lo(smem_u32(sA + (size_t)batch_sa[i] * SLAB_BYTES), 16);
-                  l_b[nl] = blo0 + (uint32_t)(kk * 3) * btile16;
-                  l_acc[nl] = (started >> zo) & 1u;
-                  started |= 1u << zo;
-                  ++nl;
-                }
+              const uint32_t alo0 = desc_lo(smem_u32(sA + (size_t)sa * SLAB_BYTES), 16);
               if (elect_one()) {
 #pragma unroll
+              for (int kk = 0; kk < 3; ++kk) {
+                if (kk >= G.KG) break;
+                const int zo = zin - kk;
+                if (zo < 0 || zo >= G.TZ || z0 + zo >= G.D0) continue;
+                const uint32_t dcol = tmem_base + (uint32_t)(zo * G.NT);
+                uint32_t acc = (started >> zo) & 1u;
+#pragma unroll
                 for (int k1 = 0; k1 < 3; ++k1) {
-#pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) {
-                    if (ks < nks) {
-#pragma unroll
-                      for (int j = 0; j < 4; ++j) {
-                        if (j < nl) {
-                          umma_tf32_lh(l_d[j], l_a[j] + (uint32_t)(k1 * (TM2 * 128 >> 4) + ks * 2),
-                                       l_b[j] + (uint32_t)k1 * btile16 + ks * 2, DESC_HI_K_SW128, idesc, l_acc[j]);
-                          l_acc[j] = 1u;
-                        }
-                      }
-                    }
-                  }
+                  const uint32_t alo = alo0 + (uint32_t)(k1 * (TM2 * 128 >> 4));
+                  const uint32_t blo = blo0 + (uint32_t)(kk * 3 + k1) * btile16;
+                  if (nks == 4) umma_chain_k<4>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+                  else if (nks == 3) umma_chain_k<3>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+                  else if (nks == 2) umma_chain_k<2>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+                  else umma_chain_k<1>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+                  acc = 1u;
                 }
-                for (int i = 0; i < nb; ++i) umma_commit(emptyA + batch_sa[i]);   // slabs free once these MMAs completed
+              }
+                umma_commit(emptyA + sa);          // slab may be overwritten once these MMAs have completed
               }
               __syncwarp();
+              for (int kk = 0; kk < G.KG; ++kk) {  // bookkeeping replicated on every lane (warp-uniform)
+                const int zo = zin - kk;
+                if (zo >= 0 && zo < G.TZ && z0 + zo < G.D0) started |= 1u << zo;
+              }
+              if (++sa == G.SA) { sa = 0; pa ^= 1; }
             }
             if (elect_one()) umma_commit(emptyB + sb);
             __syncwarp();
@@ -509,28 +515,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
           mbar_wait(fullA + sa, pa);
           tc_fence_after();
           const uint32_t alo0 = desc_lo(smem_u32(sA + (size_t)sa * SLAB_BYTES), 1024);      // M atoms = d1 taps
-          uint32_t l_d[3], l_b[3], l_acc[3];
-          int nl = 0;
-          for (int kk = 0; kk < G.KG; ++kk) {
+          if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 3; ++kk) {
+            if (kk >= G.KG) break;
             const int zo = zin - (k0g + kk) + 1;
             if (zo < zs || zo >= ze) continue;
-            l_b[nl] = desc_lo(smem_u32(sB + (size_t)((zo - zs) % G.SBT) * bstage), WG_BTILE_BYTES);
-            l_d[nl] = tmem_base + (uint32_t)(kk * G.NT);
-            l_acc[nl] = (started >> kk) & 1u;
-            ++nl;
+            const uint32_t blo0 = desc_lo(smem_u32(sB + (size_t)((zo - zs) % G.SBT) * bstage), WG_BTILE_BYTES);
+            const uint32_t dcol = tmem_base + (uint32_t)(kk * G.NT);
+            uint32_t acc = (started >> kk) & 1u;
+            umma_chain_mn16(dcol, alo0, blo0, DESC_HI_MN_SW128_32B, idesc, acc);   // 16 K-steps of 8 voxels
           }
-          if (elect_one()) {
-            // round-robin over the (up to 3) independent accumulators: same-accumulator MMAs serialise otherwise
-#pragma unroll
-            for (int s = 0; s < TM1; ++s) {          // 16 K-steps of 8 voxels (one d1 row of the tile each)
-#pragma unroll
-              for (int j = 0; j < 3; ++j) {
-                if (j < nl) {
-                  umma_tf32_lh(l_d[j], alo0 + s * (1024 >> 4), l_b[j] + s * (1024 >> 4), DESC_HI_MN_SW128_32B, idesc, l_acc[j]);
-                  l_acc[j] = 1u;
-                }
-              }
-            }
             umma_commit(emptyA + sa);
           }
           __syncwarp();
@@ -581,6 +576,51 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)G.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// microbenchmark: issue cost of tcgen05.mma.kind::tf32 (M=128, N, K=8, both operands from shared memory) as a
+// function of N, of the number of accumulators cycled through and of the chain length on one accumulator.
+// No TMA, shared memory contents are irrelevant.  out[blockIdx.x] = cycles per MMA.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+mma_microbench_kernel(float* __restrict__ out, int N, int nacc, int chain, int iters, int kmajor) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tslot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (64 * 1024) / 4; i += blockDim.x) ((float*)smem)[i] = 1.0f;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); fence_proxy_async(); }
+  if (warp == 1) tmem_alloc(&tslot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tslot;
+  if (warp == 0) {
+    const uint32_t idesc = make_idesc_tf32(N) | (kmajor ? 0u : ((1u << 15) | (1u << 16)));
+    const uint32_t hi = kmajor ? DESC_HI_K_SW128 : DESC_HI_MN_SW128_32B;
+    const uint32_t alo = desc_lo(smem_u32(smem), kmajor ? 16 : 1024);
+    const uint32_t blo = desc_lo(smem_u32(smem + 32 * 1024), kmajor ? 16 : 16384);
+    long long t0 = 0, t1 = 0;
+    if (elect_one()) {
+      t0 = clock64();
+      int acc = 0, c = 0;
+      for (int i = 0; i < iters; ++i) {
+        umma_tf32_lh(tb + (uint32_t)(acc * N), alo + (uint32_t)((i & 3) * 2), blo + (uint32_t)((i & 3) * 2), hi, idesc, 1u);
+        if (++c == chain) { c = 0; if (++acc == nacc) acc = 0; }
+      }
+      umma_commit(&bar);
+    }
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    t1 = clock64();
+    const long long tt = __shfl_sync(0xffffffffu, t0, 0) ;
+    if (threadIdx.x == 0) out[blockIdx.x] = (float)(t1 - (t0 ? t0 : tt)) / (float)iters;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tb, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -828,6 +868,17 @@ int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const 
     int rc2 = ssr_channel_sum(dy, nvox, Cout, db, stream);
     if (rc2) return rc2;
   }
+  return SSR_OK;
+}
+
+// out: `nblocks` floats (cycles per MMA measured by each CTA, one CTA per SM)
+int ssr_tc_microbench(float* out, int nblocks, int N, int nacc, int chain, int iters, int kmajor, void* stream) {
+  SSR_CHECK_ARG(out && nblocks > 0 && N % 16 == 0 && N >= 16 && N <= 256 && nacc >= 1 && nacc * N <= 512 && chain >= 1 &&
+                iters > 0, "microbench args");
+  SSR_CHECK_CUDA(cudaFuncSetAttribute(mma_microbench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  mma_microbench_kernel<<<nblocks, 128, 200 * 1024, (cudaStream_t)stream>>>(out, N, nacc, chain, iters, kmajor);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
   return SSR_OK;
 }
 

@@ -1,0 +1,100 @@
+"""Drop-in boundary: the repo's SynthSR / ext packages expose the reference's public signatures (names, order,
+defaults) and error behaviour.  Signatures come from tests/golden/reference_signatures.json (AST of the reference)."""
+import importlib
+import inspect
+import json
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SIGS = json.load(open(os.path.join(HERE, 'golden', 'reference_signatures.json')))
+
+
+def _norm(v):
+    return None if v is None else str(v).replace(' ', '').replace('0.', '.').replace("'", '"').rstrip('.')
+
+
+@pytest.mark.parametrize('key', sorted(SIGS))
+def test_signature_matches_reference(key):
+    path, name = key.split(':')
+    mod = importlib.import_module(path[:-3].replace('/', '.'))
+    obj = mod
+    for part in name.split('.'):
+        obj = getattr(obj, part)
+    params = [p for p in inspect.signature(obj).parameters.values() if p.name != 'self']
+    ref = SIGS[key]
+    got = [p.name for p in params][:len(ref)]
+    assert got == [n for n, _ in ref], key
+    for p, (n, d) in zip(params, ref):
+        if d is None:
+            assert p.default is inspect.Parameter.empty, (key, n)
+        else:
+            assert p.default is not inspect.Parameter.empty, (key, n)
+            try:
+                assert eval(d) == p.default or (eval(d) is p.default), (key, n, d, p.default)
+            except (NameError, SyntaxError):
+                assert _norm(d) == _norm(repr(p.default)), (key, n, d, p.default)
+
+
+def test_training_argument_errors_match_reference(tmp_path):
+    """same Exception messages as SynthSR/training.py:252-268 (raised before any GPU work)."""
+    from SynthSR.training import training
+    with pytest.raises(Exception, match='please provide a value for output_channel or image_dir'):
+        training('x', str(tmp_path), None, None, None, output_channel=None, images_dir=None)
+    with pytest.raises(Exception, match='but not both at the same time'):
+        training('x', str(tmp_path), None, None, None, output_channel=0, images_dir='y')
+    with pytest.raises(Exception, match='cannot be greater than the total number of channels'):
+        training('x', str(tmp_path), None, None, None, input_channels=[True, True], output_channel=2)
+    with pytest.raises(Exception, match='number or residual channels and output channels must be the same'):
+        training('x', str(tmp_path), None, None, None, input_channels=[True, True], output_channel=0,
+                 work_with_residual_channel=[0, 1])
+
+
+def test_unet_rejects_unsupported_options():
+    from ext.neuron.models import unet
+    with pytest.raises(NotImplementedError, match='final_pred_activation'):
+        unet(24, [32, 32, 32, 1], 5, 3, 1, feat_mult=2, nb_conv_per_level=2, batch_norm=-1)
+    with pytest.raises(NotImplementedError, match='batch_norm'):
+        unet(24, [32, 32, 32, 1], 5, 3, 1, feat_mult=2, nb_conv_per_level=2, final_pred_activation='linear')
+
+
+def test_nifti_roundtrip_and_volume_info(tmp_path):
+    from ext.lab2im import utils
+    rng = np.random.default_rng(0)
+    vol = rng.integers(0, 40, size=(9, 10, 11)).astype(np.float32)
+    aff = np.array([[0, 0, -1.5, 10], [1.2, 0, 0, 5], [0, -1.0, 0, 3], [0, 0, 0, 1.]])
+    p = str(tmp_path / 'a_labels.nii.gz')
+    utils.save_volume(vol, aff, None, p)
+    v2, a2, h2 = utils.load_volume(p, im_only=False)
+    np.testing.assert_array_equal(v2, vol)
+    np.testing.assert_allclose(a2, aff, atol=1e-6)
+    shape, _, n_dims, n_ch, _, res = utils.get_volume_info(p, aff_ref=np.eye(4))
+    assert n_dims == 3 and n_ch == 1 and sorted(shape) == [9, 10, 11]
+    np.testing.assert_allclose(sorted(res), sorted([1.2, 1.0, 1.5]), atol=1e-6)
+    v3 = utils.load_volume(p, dtype='int', aff_ref=np.eye(4))
+    assert v3.dtype.kind == 'i' and sorted(v3.shape) == [9, 10, 11]
+    utils.save_volume(vol, aff, h2, str(tmp_path / 'b.nii'), dtype='int32')
+    np.testing.assert_array_equal(utils.load_volume(str(tmp_path / 'b.nii')), vol)
+    assert utils.list_images_in_folder(str(tmp_path)) == sorted([p, str(tmp_path / 'b.nii')])
+
+
+def test_build_model_inputs_protocol(tmp_path):
+    from ext.lab2im import utils
+    from SynthSR.model_inputs import build_model_inputs
+    from synthsr_b200.synthetic import GEN_CLASSES, GEN_LABELS, phantom_labels, synthetic_priors
+    paths = []
+    for i in range(2):
+        p = str(tmp_path / ('m%d_labels.nii.gz' % i))
+        utils.save_volume(phantom_labels([16, 18, 14], seed=i).astype(np.float32), np.eye(4), None, p)
+        paths.append(p)
+    pm, ps = synthetic_priors(14, 2)
+    gen = build_model_inputs(paths, len(GEN_LABELS), pm, ps, 'normal', batchsize=1, n_channels=2, generation_classes=GEN_CLASSES)
+    lab, means, stds = next(gen)
+    assert lab.shape == (1, 16, 18, 14, 1) and lab.dtype.kind == 'i'
+    assert means.shape == (1, 19, 2) and stds.shape == (1, 19, 2) and (means >= 0).all()
+    assert means[0, 1, 0] == means[0, 2, 0]            # labels 14 and 15 share class 3
+    gen2 = build_model_inputs(paths, len(GEN_LABELS), pm, ps, 'normal', batchsize=3, n_channels=2, generation_classes=GEN_CLASSES)
+    lab, means, stds = next(gen2)
+    assert lab.shape == (3, 16, 18, 14, 1) and means.shape == (3, 19, 2)
