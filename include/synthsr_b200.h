@@ -104,8 +104,10 @@ int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const 
                         void* stream);
 long long ssr_conv3d_wgrad_scratch_bytes(int C1, int C2, int Cout, int B, int d0, int d1, int d2);
 int ssr_tc_selftest(void* stream);
+int ssr_tc_set_debug(long long* buf);   /* profiling: per-CTA clock64 phase stamps of conv3d_tc_kernel */
 /* tcgen05.mma issue-cost microbenchmark (cycles per MMA per CTA); see profiles/ */
-int ssr_tc_microbench(float* out, int nblocks, int N, int nacc, int chain, int iters, int kmajor, void* stream);
+int ssr_tc_microbench(float* out, int nblocks, int N, int nacc, int chain, int iters, int kmajor, int commit_every,
+                      int cycle_addr, void* stream);
 
 /* ---------------------------------------------------------------- U-Net: other layers ----------------------- */
 int ssr_channel_sum(const float* t, long long nvox, int C, float* out, void* stream);

@@ -27,6 +27,10 @@ extern "C" int ssr_channel_sum(const float* t, long long nvox, int C, float* out
 
 namespace {
 
+// optional phase timestamps (clock64) of sampled CTAs, for profiling only: ssr_tc_set_debug(buffer)
+__device__ long long* g_dbg = nullptr;
+#define DBG_STAMP(slot) do { if (dbg) dbg[slot] = clock64(); } while (0)
+
 // ---------------------------------------------------------------------------------------------------------
 // PTX wrappers
 // ---------------------------------------------------------------------------------------------------------
@@ -234,8 +238,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
   uint64_t* emptyB = fullB + SB;
   uint64_t* accFull = emptyB + SB;
   uint32_t* tmem_slot = (uint32_t*)(accFull + 1);
+  float* sbias = (float*)(bars + 32);              // NT floats (<= 192), 16-byte aligned, zero padded
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* dbg = (g_dbg && (blockIdx.x % 61) == 0 && blockIdx.x / 61 < 128) ? g_dbg + (blockIdx.x / 61) * 16 : nullptr;
+  if (threadIdx.x == 0) DBG_STAMP(0);
 
   // tile decode
   int t = blockIdx.x;
@@ -253,6 +260,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
     fence_barrier_init();
     fence_proxy_async();
   }
+  for (int i = threadIdx.x; i < G.NT; i += blockDim.x) sbias[i] = (bias && n0 + i < G.Cout) ? bias[n0 + i] : 0.f;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_x1);
     tma_prefetch_desc(&map_x2);
@@ -263,17 +271,26 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) DBG_STAMP(1);
 
+  // Closed-form slab ranges (identical in the producer and the MMA warp; no per-slab predicate evaluation in the issue
+  // loop).  nz = valid output planes of this tile.  For the d0-tap group starting at k0g, slab index zin (input plane
+  // z0 + k0g + zin - 1) contributes to accumulators zo = zin - kk, kk in [kk_lo, kk_hi]:
+  //   zin in [zin_lo, zin_hi),  zin_lo = 1 iff the first plane would be -1,  zin_hi clipped at the volume end.
+  const int nz = min(G.TZ, G.D0 - z0);
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
       int sa = 0, pa = 0, sb = 0, pb = 0;
+      long long wait_empty = 0;
       for (int ch = 0; ch < G.nchunks; ++ch) {
         const CUtensorMap* mx = G.chunk_src[ch] ? &map_x2 : &map_x1;
         const int c0 = G.chunk_c0[ch];
         for (int k2 = 0; k2 < 3; ++k2) {
           for (int k0g = 0; k0g < 3; k0g += G.KG) {
-            if (!group_needed(G, z0, k0g)) continue;
+            const int zin_lo = (z0 + k0g == 0) ? 1 : 0;
+            const int zin_hi = min(nz + G.KG - 1, G.D0 - (z0 + k0g - 1));
+            if (zin_lo >= zin_hi) continue;
             mbar_wait(emptyB + sb, pb ^ 1);
             mbar_expect_tx(fullB + sb, (uint32_t)bgroup_bytes);
             for (int kk = 0; kk < G.KG; ++kk)
@@ -282,9 +299,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                 tma_load_2d(&map_w, fullB + sb, sB + (size_t)sb * bgroup_bytes + (size_t)(kk * 3 + k1) * G.NT * 128, 0, row);
               }
             if (++sb == SB) { sb = 0; pb ^= 1; }
-            for (int zin = 0; zin < G.TZ + G.KG - 1; ++zin) {
-              if (!slab_needed(G, z0, k0g, zin)) continue;
-              mbar_wait(emptyA + sa, pa ^ 1);
+            for (int zin = zin_lo; zin < zin_hi; ++zin) {
+              { const long long w0 = dbg ? clock64() : 0; mbar_wait(emptyA + sa, pa ^ 1); if (dbg) wait_empty += clock64() - w0; }
               mbar_expect_tx(fullA + sa, SLAB_BYTES);
               tma_load_5d(mx, fullA + sa, sA + (size_t)sa * SLAB_BYTES, c0, x0 + k2 - 1, y0 - 1, z0 + k0g + zin - 1, b);
               if (++sa == G.SA) { sa = 0; pa ^= 1; }
@@ -292,62 +308,75 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
           }
         }
       }
+      DBG_STAMP(2);
+      if (dbg) dbg[8] = wait_empty;
     }
   } else if (warp == 1) {
     // ================================ MMA issuer (whole warp converged, one elected lane issues) ======
+    // The issuing warp is alone on its instruction stream: scalar work between MMA chains costs ~2 cycles per
+    // instruction per MMA (profiles/r01_mma_issue_microbench.txt), so everything is hoisted / strength-reduced.
     {
       const uint32_t idesc = make_idesc_tf32(G.NT);
+      const int KG = G.KG, SA = G.SA, nchunks = G.nchunks, D0 = G.D0;
+      const uint32_t NT = (uint32_t)G.NT;
+      const uint32_t btile16 = (NT * 128u) >> 4;
+      const uint32_t a_base = desc_lo(smem_u32(sA), 16), b_base = desc_lo(smem_u32(sB), 16);
       int sa = 0, pa = 0, sb = 0, pb = 0;
-      uint32_t started = 0;
-      for (int ch = 0; ch < G.nchunks; ++ch) {
+      uint32_t first = 1u;                       // 1 until every accumulator has received its first MMA group
+      long long wait_a = 0, wait_b = 0;
+      if (lane == 0) DBG_STAMP(3);
+      for (int ch = 0; ch < nchunks; ++ch) {
         const int nks = G.chunk_ks[ch];
         for (int k2 = 0; k2 < 3; ++k2) {
-          for (int k0g = 0; k0g < 3; k0g += G.KG) {
-            if (!group_needed(G, z0, k0g)) continue;
-            mbar_wait(fullB + sb, pb);
-            const uint32_t blo0 = desc_lo(smem_u32(sB + (size_t)sb * bgroup_bytes), 16);
-            const uint32_t btile16 = (uint32_t)(G.NT * 128) >> 4;
-            for (int zin = 0; zin < G.TZ + G.KG - 1; ++zin) {
-              if (!slab_needed(G, z0, k0g, zin)) continue;
-              mbar_wait(fullA + sa, pa);
+          for (int k0g = 0; k0g < 3; k0g += KG) {
+            const int zin_lo = (z0 + k0g == 0) ? 1 : 0;
+            const int zin_hi = min(nz + KG - 1, D0 - (z0 + k0g - 1));
+            if (zin_lo >= zin_hi) continue;
+            { const long long w0 = dbg ? clock64() : 0; mbar_wait(fullB + sb, pb); if (dbg) wait_b += clock64() - w0; }
+            const uint32_t blo0 = b_base + (uint32_t)sb * ((uint32_t)bgroup_bytes >> 4);
+            for (int zin = zin_lo; zin < zin_hi; ++zin) {
+              { const long long w0 = dbg ? clock64() : 0; mbar_wait(fullA + sa, pa); if (dbg) wait_a += clock64() - w0; }
               tc_fence_after();
-              const uint32_t alo0 = desc_lo(smem_u32(sA + (size_t)sa * SLAB_BYTES), 16);
+              const uint32_t alo0 = a_base + (uint32_t)sa * (SLAB_BYTES >> 4);
+              const int kk_lo = max(0, zin - nz + 1), kk_hi = min(KG - 1, zin);
               if (elect_one()) {
+                for (int kk = kk_lo; kk <= kk_hi; ++kk) {
+                  const int zo = zin - kk;
+                  const uint32_t dcol = tmem_base + (uint32_t)zo * NT;
+                  // first MMA ever into accumulator zo: chunk 0, k2 0, the group/slab/tap where zo is touched first
+                  uint32_t acc = 1u;
+                  if (first) {
+                    const int kfirst = (z0 + zo == 0) ? 1 : 0;           // global d0 tap that touches zo first
+                    acc = (k0g + kk == kfirst) ? 0u : 1u;
+                  }
+                  uint32_t alo = alo0;
+                  uint32_t blo = blo0 + (uint32_t)(kk * 3) * btile16;
 #pragma unroll
-              for (int kk = 0; kk < 3; ++kk) {
-                if (kk >= G.KG) break;
-                const int zo = zin - kk;
-                if (zo < 0 || zo >= G.TZ || z0 + zo >= G.D0) continue;
-                const uint32_t dcol = tmem_base + (uint32_t)(zo * G.NT);
-                uint32_t acc = (started >> zo) & 1u;
-#pragma unroll
-                for (int k1 = 0; k1 < 3; ++k1) {
-                  const uint32_t alo = alo0 + (uint32_t)(k1 * (TM2 * 128 >> 4));
-                  const uint32_t blo = blo0 + (uint32_t)(kk * 3 + k1) * btile16;
-                  if (nks == 4) umma_chain_k<4>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
-                  else if (nks == 3) umma_chain_k<3>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
-                  else if (nks == 2) umma_chain_k<2>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
-                  else umma_chain_k<1>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
-                  acc = 1u;
+                  for (int k1 = 0; k1 < 3; ++k1) {
+                    if (nks == 4) umma_chain_k<4>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+                    else if (nks == 3) umma_chain_k<3>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+                    else if (nks == 2) umma_chain_k<2>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+                    else umma_chain_k<1>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+                    acc = 1u;
+                    alo += (uint32_t)(TM2 * 128 >> 4);
+                    blo += btile16;
+                  }
                 }
-              }
                 umma_commit(emptyA + sa);          // slab may be overwritten once these MMAs have completed
               }
               __syncwarp();
-              for (int kk = 0; kk < G.KG; ++kk) {  // bookkeeping replicated on every lane (warp-uniform)
-                const int zo = zin - kk;
-                if (zo >= 0 && zo < G.TZ && z0 + zo < G.D0) started |= 1u << zo;
-              }
-              if (++sa == G.SA) { sa = 0; pa ^= 1; }
+              if (++sa == SA) { sa = 0; pa ^= 1; }
             }
             if (elect_one()) umma_commit(emptyB + sb);
             __syncwarp();
             if (++sb == SB) { sb = 0; pb ^= 1; }
           }
+          first = 0u;                              // after (chunk 0, k2 0) every accumulator has been initialised
         }
       }
       if (elect_one()) umma_commit(accFull);
       __syncwarp();
+      if (lane == 0) { DBG_STAMP(4); if (dbg) { dbg[9] = wait_a; dbg[10] = wait_b; } }
     }
   } else {
     // ================================ epilogue (warps 2..5) ================================
@@ -356,7 +385,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
     const int i1 = y0 + (r >> 3), i2 = x0 + (r & 7);
     mbar_wait(accFull, 0);
     tc_fence_after();
+    if (warp == 2 && lane == 0) DBG_STAMP(5);
     const bool vox_ok = i1 < G.D1 && i2 < G.D2;
+    const bool vec_ok = (G.Cout & 3) == 0;
     for (int zo = 0; zo < G.TZ; ++zo) {
       const int i0 = z0 + zo;
       if (i0 >= G.D0) break;                        // uniform across the CTA
@@ -365,33 +396,48 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(zo * G.NT + cb), v);
         tmem_ld_wait();
-        if (!vox_ok) continue;
         float o[16];
+        const float4* bs = reinterpret_cast<const float4*>(sbias + cb);      // zero padded to NT, 16-byte aligned
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int c = n0 + cb + e;
-          float f = __uint_as_float(v[e]);
-          if (c < G.Cout) {
-            if (bias) f += __ldg(bias + c);
-            if (G.act) f = f > 0.f ? f : (expf(f) - 1.f);
-          }
-          o[e] = f;
+        for (int e4 = 0; e4 < 4; ++e4) {
+          const float4 bb = bs[e4];
+          o[e4 * 4 + 0] = __uint_as_float(v[e4 * 4 + 0]) + bb.x;
+          o[e4 * 4 + 1] = __uint_as_float(v[e4 * 4 + 1]) + bb.y;
+          o[e4 * 4 + 2] = __uint_as_float(v[e4 * 4 + 2]) + bb.z;
+          o[e4 * 4 + 3] = __uint_as_float(v[e4 * 4 + 3]) + bb.w;
         }
-        if (n0 + cb + 16 <= G.Cout && (G.Cout & 3) == 0) {
+        if (G.act) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {             // ELU without a branch: exp(min(x,0)) - 1 selected where x <= 0
+            const float neg = __expf(fminf(o[e], 0.f)) - 1.f;
+            o[e] = o[e] > 0.f ? o[e] : neg;
+          }
+        }
+        if (!vox_ok) continue;
+        const int nvalid = G.Cout - (n0 + cb);       // channels of this 16-block that exist
+        if (nvalid >= 16 && vec_ok) {
 #pragma unroll
           for (int e = 0; e < 16; e += 4)
             *reinterpret_cast<float4*>(orow + cb + e) = make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]);
+        } else if (nvalid >= 8 && vec_ok) {
+          *reinterpret_cast<float4*>(orow + cb) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(orow + cb + 4) = make_float4(o[4], o[5], o[6], o[7]);
+#pragma unroll
+          for (int e = 8; e < 16; ++e)
+            if (e < nvalid) orow[cb + e] = o[e];
         } else {
 #pragma unroll
           for (int e = 0; e < 16; ++e)
-            if (n0 + cb + e < G.Cout) orow[cb + e] = o[e];
+            if (e < nvalid) orow[cb + e] = o[e];
         }
       }
     }
   }
+  if (warp == 2 && lane == 0) DBG_STAMP(6);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)G.tmem_cols);
+  if (threadIdx.x == 0) DBG_STAMP(7);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -584,14 +630,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
 // No TMA, shared memory contents are irrelevant.  out[blockIdx.x] = cycles per MMA.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 1)
-mma_microbench_kernel(float* __restrict__ out, int N, int nacc, int chain, int iters, int kmajor) {
+mma_microbench_kernel(float* __restrict__ out, int N, int nacc, int chain, int iters, int kmajor, int commit_every,
+                      int cycle_addr) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
+  __shared__ uint64_t bar2;
   __shared__ uint32_t tslot;
   const int warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < (64 * 1024) / 4; i += blockDim.x) ((float*)smem)[i] = 1.0f;
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); fence_proxy_async(); }
+  for (int i = threadIdx.x; i < (190 * 1024) / 4; i += blockDim.x) ((float*)smem)[i] = 1.0f + (float)(i & 255) * 0.001f;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1); fence_barrier_init(); fence_proxy_async(); }
   if (warp == 1) tmem_alloc(&tslot, 512);
   tc_fence_before();
   __syncthreads();
@@ -601,14 +649,20 @@ mma_microbench_kernel(float* __restrict__ out, int N, int nacc, int chain, int i
     const uint32_t idesc = make_idesc_tf32(N) | (kmajor ? 0u : ((1u << 15) | (1u << 16)));
     const uint32_t hi = kmajor ? DESC_HI_K_SW128 : DESC_HI_MN_SW128_32B;
     const uint32_t alo = desc_lo(smem_u32(smem), kmajor ? 16 : 1024);
-    const uint32_t blo = desc_lo(smem_u32(smem + 32 * 1024), kmajor ? 16 : 16384);
+    const uint32_t blo = desc_lo(smem_u32(smem + 150 * 1024), kmajor ? 16 : 16384);
     long long t0 = 0, t1 = 0;
     if (elect_one()) {
       t0 = clock64();
       int acc = 0, c = 0;
       for (int i = 0; i < iters; ++i) {
-        umma_tf32_lh(tb + (uint32_t)(acc * N), alo + (uint32_t)((i & 3) * 2), blo + (uint32_t)((i & 3) * 2), hi, idesc, 1u);
+        uint32_t ao = (uint32_t)((i & 3) * 2), bo = ao;
+        if (cycle_addr) {        // like the convolution: 8 slab stages x 3 d1 taps for A, 9 taps for B
+          ao += (uint32_t)(((i >> 2) % 3) * 64 + ((i / 27) % 8) * (SLAB_BYTES >> 4));
+          bo += (uint32_t)(((i >> 2) % 9) * ((N * 128) >> 4));
+        }
+        umma_tf32_lh(tb + (uint32_t)(acc * N), alo + ao, blo + bo, hi, idesc, 1u);
         if (++c == chain) { c = 0; if (++acc == nacc) acc = 0; }
+        if (commit_every > 0 && (i % commit_every) == commit_every - 1) umma_commit(&bar2);
       }
       umma_commit(&bar);
     }
@@ -787,11 +841,11 @@ int ssr_conv3d_fwd_tc(const float* x1, int C1, const float* x2, int C2, const fl
   G.nchunks = nch;
   G.n2tiles = (D2 + TM2 - 1) / TM2; G.n1tiles = (D1 + TM1 - 1) / TM1; G.n0tiles = (D0 + G.TZ - 1) / G.TZ;
   const int bgroup = G.KG * 3 * G.NT * 128;
-  const int budget = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - SB * bgroup;
+  const int budget = 227 * 1024 - 1024 /*align slack*/ - 1280 /*barriers + bias*/ - SB * bgroup;
   int sa = budget / SLAB_BYTES; if (sa > 8) sa = 8;
   SSR_CHECK_ARG(sa >= 2, "shared memory budget");
   G.SA = sa;
-  const size_t smem = 1024 + (size_t)G.SA * SLAB_BYTES + (size_t)SB * bgroup + 512;
+  const size_t smem = 1024 + (size_t)G.SA * SLAB_BYTES + (size_t)SB * bgroup + 1280;
 
   CUtensorMap m1, m2, mw;
   int rc = make_map_act(&m1, x1, C1, B, D0, D1, D2);
@@ -872,13 +926,22 @@ int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const 
 }
 
 // out: `nblocks` floats (cycles per MMA measured by each CTA, one CTA per SM)
-int ssr_tc_microbench(float* out, int nblocks, int N, int nacc, int chain, int iters, int kmajor, void* stream) {
+int ssr_tc_microbench(float* out, int nblocks, int N, int nacc, int chain, int iters, int kmajor, int commit_every,
+                      int cycle_addr, void* stream) {
   SSR_CHECK_ARG(out && nblocks > 0 && N % 16 == 0 && N >= 16 && N <= 256 && nacc >= 1 && nacc * N <= 512 && chain >= 1 &&
                 iters > 0, "microbench args");
   SSR_CHECK_CUDA(cudaFuncSetAttribute(mma_microbench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  mma_microbench_kernel<<<nblocks, 128, 200 * 1024, (cudaStream_t)stream>>>(out, N, nacc, chain, iters, kmajor);
+  SSR_CHECK_ARG(!cycle_addr || N <= 32, "address cycling needs 9*N*128 B of B tiles");
+  mma_microbench_kernel<<<nblocks, 128, 200 * 1024, (cudaStream_t)stream>>>(out, N, nacc, chain, iters, kmajor, commit_every,
+                                                                              cycle_addr);
   SSR_COUNT_LAUNCH();
   SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
+// profiling aid: phase timestamps of sampled CTAs of conv3d_tc_kernel are written to `buf` (>= 128*16 int64), NULL disables
+int ssr_tc_set_debug(long long* buf) {
+  SSR_CHECK_CUDA(cudaMemcpyToSymbol(g_dbg, &buf, sizeof(buf)));
   return SSR_OK;
 }
 
