@@ -898,7 +898,8 @@ int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const 
   G.nchunks = nch; G.C1 = C1;
   G.n2tiles = (D2 + TM2 - 1) / TM2; G.n1tiles = (D1 + TM1 - 1) / TM1;
   const long long base_units = (long long)nch * 3 * (3 / G.KG) * G.nNtiles * G.n1tiles * G.n2tiles * B;
-  int S = (int)((2 * 148 + base_units - 1) / base_units); if (S < 1) S = 1; if (S > (D0 + 3) / 4) S = (D0 + 3) / 4; if (S < 1) S = 1;
+  // enough CTAs for >= ~8 waves of 148 (tail-wave loss < ~6 %), but at least 8 planes per CTA (halo planes are re-read)
+  int S = (int)((8 * 148 + base_units - 1) / base_units); if (S < 1) S = 1; if (S > (D0 + 7) / 8) S = (D0 + 7) / 8; if (S < 1) S = 1;
   G.zlen = (D0 + S - 1) / S; G.n0splits = (D0 + G.zlen - 1) / G.zlen;
   const size_t smem = 1024 + (size_t)G.SA * SLAB_BYTES + (size_t)G.SBT * bstage + 512;
   CUtensorMap m1, m2, my;

@@ -1,0 +1,83 @@
+"""End-to-end through the drop-in boundary on a GPU: SynthSR.training.training() and BrainGenerator.generate_brain()
+on small NIfTI label maps written by the repo's own writer (nothing is read from /root/reference)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dataset(tmp_path_factory):
+    from ext.lab2im import utils
+    from synthsr_b200.synthetic import GEN_CLASSES, GEN_LABELS, phantom_labels, synthetic_priors
+    root = tmp_path_factory.mktemp('data')
+    labels_dir = root / 'labels'
+    os.makedirs(labels_dir)
+    aff = np.array([[1., 0, 0, 40], [0, 1., 0, 16], [0, 0, 1., 63], [0, 0, 0, 1]])     # like the reference fixtures
+    for i in range(2):
+        utils.save_volume(phantom_labels([44, 52, 40], seed=i).astype(np.float32), aff, None,
+                          str(labels_dir / ('brain%d_labels.nii.gz' % i)))
+    pm, ps = synthetic_priors(14, 1, seed=0)
+    pm2, ps2 = synthetic_priors(14, 2, seed=1)
+    paths = {k: str(root / (k + '.npy')) for k in ('labels', 'classes', 'means', 'stds', 'means2', 'stds2')}
+    np.save(paths['labels'], GEN_LABELS); np.save(paths['classes'], GEN_CLASSES)
+    np.save(paths['means'], pm); np.save(paths['stds'], ps); np.save(paths['means2'], pm2); np.save(paths['stds2'], ps2)
+    return str(labels_dir), paths, root
+
+
+def test_brain_generator_generate_brain(dataset):
+    """tutorial-2 style: BrainGenerator(...).generate_brain() -> (image, target) in native space."""
+    from SynthSR.brain_generator import BrainGenerator
+    labels_dir, p, _ = dataset
+    gen = BrainGenerator(labels_dir, p['means'], p['stds'], 'normal', p['labels'], generation_classes=p['classes'],
+                         output_shape=32, data_res=np.array([1., 1., 3.]), thickness=np.array([1., 1., 3.]),
+                         downsample=True, build_reliability_maps=True)
+    assert gen.labels_shape == [44, 52, 40] and gen.n_dims == 3 and gen.model_output_shape == [32, 32, 32, 2]
+    image, target = gen.generate_brain()
+    assert image.shape == (32, 32, 32, 2) and target.shape == (32, 32, 32)
+    assert image.dtype == np.float32 and np.isfinite(image).all() and np.isfinite(target).all()
+    assert 0. <= target.min() and target.max() <= 1. + 1e-6 and target.std() > 0.01
+    rel = image[..., 1]
+    assert rel.min() >= 0 and rel.max() <= 1 + 1e-6 and (rel < 0.99).any()      # interpolated slices are marked
+    image2, _ = gen.generate_brain()
+    assert not np.array_equal(image, image2)                                    # fresh augmentation every call
+
+
+def test_training_runs_checkpoints_and_resumes(dataset):
+    """tutorial-7 style training() call: 2 epochs x 3 steps, checkpoint per epoch, resume from 002."""
+    from SynthSR.training import training
+    labels_dir, p, root = dataset
+    model_dir = str(root / 'model')
+    kw = dict(path_generation_classes=p['classes'], batchsize=1, input_channels=True, output_channel=0, output_shape=32,
+              n_levels=3, unet_feat_count=8, steps_per_epoch=3, regression_metric='l1', build_reliability_maps=True,
+              work_with_residual_channel=[0], data_res=np.array([1., 1., 2.]), lr=1e-3)
+    training(labels_dir, model_dir, p['means'], p['stds'], p['labels'], epochs=2, **kw)
+    assert os.path.isfile(os.path.join(model_dir, '001.npz')) and os.path.isfile(os.path.join(model_dir, '002.npz'))
+    log = open(os.path.join(model_dir, 'logs', 'loss.csv')).read().strip().splitlines()
+    losses = [float(l.split(',')[1]) for l in log]
+    assert len(losses) == 2 and all(np.isfinite(losses)) and all(0 < l < 10 for l in losses)
+    ck = np.load(os.path.join(model_dir, '002.npz'))
+    assert 'unet_conv_downarm_0_0/kernel' in ck and ck['unet_conv_downarm_0_0/kernel'].shape == (3, 3, 3, 2, 8)
+    assert 'unet_likelihood/kernel' in ck and int(ck['optimizer/iterations']) == 6
+    training(labels_dir, model_dir, p['means'], p['stds'], p['labels'], epochs=3,
+             checkpoint=os.path.join(model_dir, '002.npz'), **kw)
+    assert os.path.isfile(os.path.join(model_dir, '003.npz'))
+    assert int(np.load(os.path.join(model_dir, '003.npz'))['optimizer/iterations']) == 9
+
+
+def test_two_channel_synthesis_config(dataset):
+    """multi-modal inputs (T1+T2-like) with a separate HR target channel, batch 2 (c4-like wiring)."""
+    from SynthSR.training import training
+    labels_dir, p, root = dataset
+    pm3 = np.concatenate([np.load(p['means']), np.load(p['means2'])])
+    ps3 = np.concatenate([np.load(p['stds']), np.load(p['stds2'])])
+    np.save(str(root / 'm3.npy'), pm3); np.save(str(root / 's3.npy'), ps3)
+    model_dir = str(root / 'model2')
+    training(labels_dir, model_dir, str(root / 'm3.npy'), str(root / 's3.npy'), p['labels'],
+             path_generation_classes=p['classes'], batchsize=2, input_channels=[False, True, True], output_channel=0,
+             output_shape=32, data_res=np.array([[1., 1., 3.], [1., 1., 2.]]), thickness=np.array([[1., 1., 3.], [1., 1., 2.]]),
+             downsample=True, build_reliability_maps=False, n_levels=3, unet_feat_count=8, epochs=1, steps_per_epoch=2)
+    ck = np.load(os.path.join(model_dir, '001.npz'))
+    assert ck['unet_conv_downarm_0_0/kernel'].shape == (3, 3, 3, 2, 8)
