@@ -120,15 +120,16 @@ int ssr_bn_stats_inference(int C, const float* gamma, const float* beta, const f
 /* mode 0: BN ; 1: BN + MaxPooling3D(2,'same') (models.py:354-356) ; 2: BN + UpSampling3D(2) (models.py:425-427). */
 int ssr_bn_apply(const float* x, float* y, const float* stats, int B, int d0, int d1, int d2, int C, int mode,
                  int dst_stride, int dst_off, void* stream);
+/* dbias (optional): += per-channel sum of the result (bias gradient of the convolution that produced x) */
 int ssr_bn_bwd(const float* dy, const float* x, const float* stats, long long nvox, int C, const float* add,
-               int add_stride, int add_off, int elu, float* dx, float* dgamma, float* dbeta, double* sums_scratch,
-               void* stream);
+               int add_stride, int add_off, int elu, float* dx, float* dgamma, float* dbeta, float* dbias,
+               double* sums_scratch, void* stream);
 int ssr_maxpool_bwd(const float* dp, const float* x, const float* stats, int B, int d0, int d1, int d2, int C,
                     float* dy_full, void* stream);
 int ssr_upsample_bwd(const float* du, int du_stride, int du_off, int B, int d0, int d1, int d2, int C, float* dlow,
                      void* stream);
 int ssr_elu_bwd(const float* dh, int dh_stride, int dh_off, const float* h, const float* add, long long nvox, int C,
-                float* da, void* stream);
+                float* da, float* dbias, void* stream);
 /* unet_likelihood 1x1x1 conv (models.py:480-481) + metrics_model (SynthSR/metrics_model.py:53-104), fwd + bwd. */
 int ssr_head_loss(const float* feat, const float* w, const float* bias, const float* image, int image_channels,
                   const int* res_idx, const float* target, float* pred, float* dfeat, float* dw, float* db,

@@ -105,6 +105,77 @@ conv3d_direct_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// first U-Net layer (Cin <= 2 -> Cout <= 32, 3x3x3): K = 27*Cin is far too small for the tensor cores, and the
+// generic direct kernel re-reads every input 3x.  Tile 4 x 8 x 32 outputs per block, input halo + weights in
+// shared memory, every thread produces all Cout channels of 4 voxels (96-byte contiguous rows out).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int FT0 = 4, FT1 = 8, FT2 = 32;
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256)
+conv3d_first_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                    float* __restrict__ y, int B, int d0, int d1, int d2, int act) {
+  __shared__ float sx[(FT0 + 2) * (FT1 + 2) * (FT2 + 2) * CIN];
+  __shared__ __align__(16) float sw[27 * CIN * COUT];
+  __shared__ float sb[COUT];
+  const int nb2 = (d2 + FT2 - 1) / FT2, nb1 = (d1 + FT1 - 1) / FT1, nb0 = (d0 + FT0 - 1) / FT0;
+  long long blk = blockIdx.x;
+  const int b2 = (int)(blk % nb2); blk /= nb2;
+  const int b1 = (int)(blk % nb1); blk /= nb1;
+  const int b0 = (int)(blk % nb0);
+  const int b = (int)(blk / nb0);
+  for (int e = threadIdx.x; e < 27 * CIN * COUT; e += 256) sw[e] = w[e];
+  if (threadIdx.x < COUT) sb[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+  const int o0 = b0 * FT0 - 1, o1 = b1 * FT1 - 1, o2 = b2 * FT2 - 1;
+  constexpr int T1 = FT1 + 2, T2 = FT2 + 2;
+  for (int e = threadIdx.x; e < (FT0 + 2) * T1 * T2; e += 256) {
+    const int c = e % T2, bb = (e / T2) % T1, a = e / (T2 * T1);
+    const int i = o0 + a, j = o1 + bb, k = o2 + c;
+    const bool ok = i >= 0 && i < d0 && j >= 0 && j < d1 && k >= 0 && k < d2;
+    const long long src = ((((long long)b * d0 + i) * d1 + j) * d2 + k) * CIN;
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) sx[e * CIN + ci] = ok ? x[src + ci] : 0.f;
+  }
+  __syncthreads();
+  const int t2 = threadIdx.x % FT2, t1 = threadIdx.x / FT2;
+  const int i1 = b1 * FT1 + t1, i2 = b2 * FT2 + t2;
+  if (i1 >= d1 || i2 >= d2) return;
+  for (int a0 = 0; a0 < FT0; ++a0) {
+    const int i0 = b0 * FT0 + a0;
+    if (i0 >= d0) break;
+    float acc[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = sb[co];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int bb = 0; bb < 3; ++bb)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float* px = sx + (((a0 + a) * T1 + (t1 + bb)) * T2 + (t2 + c)) * CIN;
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci) {
+            const float xv = px[ci];
+            const float4* pw = reinterpret_cast<const float4*>(sw + (((a * 3 + bb) * 3 + c) * CIN + ci) * COUT);
+#pragma unroll
+            for (int q = 0; q < COUT / 4; ++q) {
+              const float4 wv = pw[q];
+              acc[q * 4 + 0] += xv * wv.x; acc[q * 4 + 1] += xv * wv.y;
+              acc[q * 4 + 2] += xv * wv.z; acc[q * 4 + 3] += xv * wv.w;
+            }
+          }
+        }
+    float* o = y + ((((long long)b * d0 + i0) * d1 + i1) * d2 + i2) * COUT;
+#pragma unroll
+    for (int q = 0; q < COUT / 4; ++q) {
+      float4 v = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+      if (act) { v.x = elu_f(v.x); v.y = elu_f(v.y); v.z = elu_f(v.z); v.w = elu_f(v.w); }
+      reinterpret_cast<float4*>(o)[q] = v;
+    }
+  }
+}
+
 // weights for the data-gradient expressed as a forward convolution of dy:
 //   wd[tap'][co][ci] = w[K-1-tap'][ci][co]   (flip all three axes, swap channel roles)
 __global__ void flip_transpose_kernel(const float* __restrict__ w, float* __restrict__ wd, int ntap, int Cin, int Cout) {
@@ -397,11 +468,71 @@ __global__ void bn_param_grad_kernel(const double* __restrict__ sums2, int C, fl
   dbeta[c] += (float)sums2[c];
 }
 
+// Block-level reduction of per-thread float4 partial sums that belong to channel group `cv` (threads of a block with
+// the same cv), then one atomicAdd per channel per block: the conv bias gradient db[c] = sum_v da[v][c] comes for free
+// out of the kernel that writes da (saves a full extra pass over the tensor).
+constexpr int EW_THREADS = 192;      // multiple of every C/4 used by the U-Net (6, 12, 24, 48, 96) and of 2, 4, 8
+__device__ __forceinline__ void block_reduce_dbias(float4 part, int cv, int CV, float* __restrict__ dbias) {
+  __shared__ float4 sred[EW_THREADS];
+  sred[threadIdx.x] = part;
+  __syncthreads();
+  if ((int)threadIdx.x < CV) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = threadIdx.x; i < EW_THREADS; i += CV) { const float4 p = sred[i]; s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w; }
+    atomicAdd(dbias + cv * 4 + 0, s.x); atomicAdd(dbias + cv * 4 + 1, s.y);
+    atomicAdd(dbias + cv * 4 + 2, s.z); atomicAdd(dbias + cv * 4 + 3, s.w);
+  }
+}
+
 // dx = scale * (dy - mean(dy) - xhat * mean(dy*xhat))  [+ add]  [* elu'(x)]      (x = BN input = ELU output)
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                    const float* __restrict__ stats, const double* __restrict__ sums2, long long nvox,
-                                    int C, const float* __restrict__ add, int add_stride, int add_off, int elu,
-                                    float* __restrict__ dx) {
+// float4 over channels; every thread keeps the same channel group for its whole grid-stride loop (EW_THREADS % CV == 0)
+__global__ void __launch_bounds__(EW_THREADS)
+bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ stats,
+                    const double* __restrict__ sums2, long long nvox, int C, const float* __restrict__ add,
+                    int add_stride, int add_off, int elu, float* __restrict__ dx, float* __restrict__ dbias) {
+  const int CV = C >> 2;
+  const long long n = nvox * CV;
+  const long long tid = blockIdx.x * (long long)EW_THREADS + threadIdx.x;
+  const int cv = (int)(tid % CV);
+  const double inv_n = 1.0 / (double)nvox;
+  float mean[4], invstd[4], scale[4], m1[4], m2[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c = cv * 4 + e;
+    mean[e] = stats[c]; invstd[e] = stats[C + c]; scale[e] = stats[2 * C + c];
+    m1[e] = (float)(sums2[c] * inv_n); m2[e] = (float)(sums2[C + c] * inv_n);
+  }
+  float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long t = tid; t < n; t += (long long)gridDim.x * EW_THREADS) {
+    const long long v = t / CV;
+    const float4 g4 = reinterpret_cast<const float4*>(dy)[t];
+    const float4 x4 = reinterpret_cast<const float4*>(x)[t];
+    const float gi[4] = {g4.x, g4.y, g4.z, g4.w}, xi[4] = {x4.x, x4.y, x4.z, x4.w};
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float xhat = (xi[e] - mean[e]) * invstd[e];
+      o[e] = scale[e] * (gi[e] - m1[e] - xhat * m2[e]);
+    }
+    if (add) {
+      const float4 a4 = *reinterpret_cast<const float4*>(add + v * add_stride + add_off + cv * 4);
+      o[0] += a4.x; o[1] += a4.y; o[2] += a4.z; o[3] += a4.w;
+    }
+    if (elu) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] *= elu_grad_from_out(xi[e]);
+    }
+    reinterpret_cast<float4*>(dx)[t] = make_float4(o[0], o[1], o[2], o[3]);
+    part.x += o[0]; part.y += o[1]; part.z += o[2]; part.w += o[3];
+  }
+  if (dbias) block_reduce_dbias(part, cv, CV, dbias);
+}
+
+// scalar fallback (C not a multiple of 4 or EW_THREADS not a multiple of C/4)
+__global__ void bn_bwd_apply_scalar_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                           const float* __restrict__ stats, const double* __restrict__ sums2,
+                                           long long nvox, int C, const float* __restrict__ add, int add_stride,
+                                           int add_off, int elu, float* __restrict__ dx) {
   const long long n = nvox * C;
   const double inv_n = 1.0 / (double)nvox;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
@@ -468,9 +599,30 @@ __global__ void upsample_bwd_kernel(const float* __restrict__ du, int du_stride,
   }
 }
 
-// da = (dh [+ add]) * elu'(h)      (dh may be a channel slice of a wider tensor)
-__global__ void elu_bwd_kernel(const float* __restrict__ dh, int dh_stride, int dh_off, const float* __restrict__ h,
-                               const float* __restrict__ add, long long nvox, int C, float* __restrict__ da) {
+// da = (dh [+ add]) * elu'(h)      (dh may be a channel slice of a wider tensor); float4 over channels + fused db
+__global__ void __launch_bounds__(EW_THREADS)
+elu_bwd_kernel(const float* __restrict__ dh, int dh_stride, int dh_off, const float* __restrict__ h,
+               const float* __restrict__ add, long long nvox, int C, float* __restrict__ da, float* __restrict__ dbias) {
+  const int CV = C >> 2;
+  const long long n = nvox * CV;
+  const long long tid = blockIdx.x * (long long)EW_THREADS + threadIdx.x;
+  const int cv = (int)(tid % CV);
+  float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long t = tid; t < n; t += (long long)gridDim.x * EW_THREADS) {
+    const long long v = t / CV;
+    float4 g = *reinterpret_cast<const float4*>(dh + v * dh_stride + dh_off + cv * 4);
+    if (add) { const float4 a4 = reinterpret_cast<const float4*>(add)[t]; g.x += a4.x; g.y += a4.y; g.z += a4.z; g.w += a4.w; }
+    const float4 h4 = reinterpret_cast<const float4*>(h)[t];
+    g.x *= elu_grad_from_out(h4.x); g.y *= elu_grad_from_out(h4.y);
+    g.z *= elu_grad_from_out(h4.z); g.w *= elu_grad_from_out(h4.w);
+    reinterpret_cast<float4*>(da)[t] = g;
+    part.x += g.x; part.y += g.y; part.z += g.z; part.w += g.w;
+  }
+  if (dbias) block_reduce_dbias(part, cv, CV, dbias);
+}
+
+__global__ void elu_bwd_scalar_kernel(const float* __restrict__ dh, int dh_stride, int dh_off, const float* __restrict__ h,
+                                      const float* __restrict__ add, long long nvox, int C, float* __restrict__ da) {
   const long long n = nvox * C;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(t % C);
@@ -649,6 +801,17 @@ int ssr_conv3d_fwd_ref(const float* x1, int C1, const float* x2, int C2, const f
   SSR_CHECK_ARG(x1 && w && y && C1 > 0 && C2 >= 0 && (C2 == 0 || x2) && Cout > 0 && (k & 1), "conv args");
   ConvGeom G{B, d0, d1, d2, C1, C2, Cout, k, act};
   const long long nvox = (long long)B * d0 * d1 * d2;
+  if (k == 3 && C2 == 0 && C1 <= 2 && (Cout == 24 || Cout == 8) && (((uintptr_t)y) & 15) == 0) {   // first-layer kernel
+    const long long nblk = (long long)B * ((d0 + FT0 - 1) / FT0) * ((d1 + FT1 - 1) / FT1) * ((d2 + FT2 - 1) / FT2);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C1 == 1 && Cout == 24) conv3d_first_kernel<1, 24><<<(unsigned)nblk, 256, 0, st>>>(x1, w, bias, y, B, d0, d1, d2, act);
+    else if (C1 == 2 && Cout == 24) conv3d_first_kernel<2, 24><<<(unsigned)nblk, 256, 0, st>>>(x1, w, bias, y, B, d0, d1, d2, act);
+    else if (C1 == 1 && Cout == 8) conv3d_first_kernel<1, 8><<<(unsigned)nblk, 256, 0, st>>>(x1, w, bias, y, B, d0, d1, d2, act);
+    else conv3d_first_kernel<2, 8><<<(unsigned)nblk, 256, 0, st>>>(x1, w, bias, y, B, d0, d1, d2, act);
+    SSR_COUNT_LAUNCH();
+    SSR_CHECK_LAUNCH();
+    return SSR_OK;
+  }
   dim3 grid((unsigned)((nvox + 255) / 256), (unsigned)((Cout + CO_T - 1) / CO_T));
   conv3d_direct_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x1, x2, w, bias, y, G);
   SSR_COUNT_LAUNCH();
@@ -766,9 +929,21 @@ int ssr_bn_apply(const float* x, float* y, const float* stats, int B, int d0, in
 }
 
 // BN backward: dx = BN'(dy) [+ add] [* elu'(x)] ; dgamma/dbeta accumulated.  sums_scratch: 2*C doubles.
+static bool ew_vec_ok(int C, const void* a, const void* b, const void* c, int stride, int off) {
+  return C % 4 == 0 && EW_THREADS % (C / 4) == 0 && stride % 4 == 0 && off % 4 == 0 &&
+         (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0;
+}
+
+static int ew_grid(long long n) {       // grid * EW_THREADS must stay a multiple of C/4: any grid works (EW_THREADS is)
+  long long g = (n + EW_THREADS - 1) / EW_THREADS;
+  const long long cap = 148LL * 10;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+// dbias (optional): += sum_v dx[v][c]  (the bias gradient of the convolution that produced x)
 int ssr_bn_bwd(const float* dy, const float* x, const float* stats, long long nvox, int C, const float* add,
-               int add_stride, int add_off, int elu, float* dx, float* dgamma, float* dbeta, double* sums_scratch,
-               void* stream) {
+               int add_stride, int add_off, int elu, float* dx, float* dgamma, float* dbeta, float* dbias,
+               double* sums_scratch, void* stream) {
   SSR_CHECK_ARG(dy && x && stats && dx && sums_scratch && nvox > 0 && C > 0, "args");
   cudaStream_t st = (cudaStream_t)stream;
   SSR_CHECK_CUDA(cudaMemsetAsync(sums_scratch, 0, 2 * C * sizeof(double), st));
@@ -781,9 +956,16 @@ int ssr_bn_bwd(const float* dy, const float* x, const float* stats, long long nv
     SSR_COUNT_LAUNCH();
   }
   if (add && add_stride <= 0) { add_stride = C; add_off = 0; }
-  bn_bwd_apply_kernel<<<grid_for(nvox * C), 256, 0, st>>>(dy, x, stats, sums_scratch, nvox, C, add, add_stride, add_off,
-                                                          elu, dx);
-  SSR_COUNT_LAUNCH();
+  if (ew_vec_ok(C, dy, x, dx, add ? add_stride : 4, add ? add_off : 0) && (!add || ((uintptr_t)add & 15) == 0)) {
+    bn_bwd_apply_kernel<<<ew_grid(nvox * (C / 4)), EW_THREADS, 0, st>>>(dy, x, stats, sums_scratch, nvox, C, add,
+                                                                        add_stride, add_off, elu, dx, dbias);
+    SSR_COUNT_LAUNCH();
+  } else {
+    bn_bwd_apply_scalar_kernel<<<grid_for(nvox * C), 256, 0, st>>>(dy, x, stats, sums_scratch, nvox, C, add, add_stride,
+                                                                   add_off, elu, dx);
+    SSR_COUNT_LAUNCH();
+    if (dbias) { int rc = ssr_channel_sum(dx, nvox, C, dbias, stream); if (rc) return rc; }
+  }
   SSR_CHECK_LAUNCH();
   return SSR_OK;
 }
@@ -810,11 +992,18 @@ int ssr_upsample_bwd(const float* du, int du_stride, int du_off, int B, int d0, 
 }
 
 int ssr_elu_bwd(const float* dh, int dh_stride, int dh_off, const float* h, const float* add, long long nvox, int C,
-                float* da, void* stream) {
+                float* da, float* dbias, void* stream) {
   SSR_CHECK_ARG(dh && h && da && nvox > 0 && C > 0, "args");
   if (dh_stride <= 0) { dh_stride = C; dh_off = 0; }
-  elu_bwd_kernel<<<grid_for(nvox * C), 256, 0, (cudaStream_t)stream>>>(dh, dh_stride, dh_off, h, add, nvox, C, da);
-  SSR_COUNT_LAUNCH();
+  if (ew_vec_ok(C, dh, h, da, dh_stride, dh_off) && (!add || ((uintptr_t)add & 15) == 0)) {
+    elu_bwd_kernel<<<ew_grid(nvox * (C / 4)), EW_THREADS, 0, (cudaStream_t)stream>>>(dh, dh_stride, dh_off, h, add, nvox,
+                                                                                     C, da, dbias);
+    SSR_COUNT_LAUNCH();
+  } else {
+    elu_bwd_scalar_kernel<<<grid_for(nvox * C), 256, 0, (cudaStream_t)stream>>>(dh, dh_stride, dh_off, h, add, nvox, C, da);
+    SSR_COUNT_LAUNCH();
+    if (dbias) { int rc = ssr_channel_sum(da, nvox, C, dbias, stream); if (rc) return rc; }
+  }
   SSR_CHECK_LAUNCH();
   return SSR_OK;
 }

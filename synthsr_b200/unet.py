@@ -231,10 +231,10 @@ class UNet3D:
             nbytes = lib.ssr_conv3d_wgrad_scratch_bytes(c1, c2, cout, self.B, *d)
             if getattr(self, '_wg_scratch', None) is None or self._wg_scratch.numel() * 4 < nbytes:
                 self._wg_scratch = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
-            lib.ssr_conv3d_wgrad_tc(x1, c1, x2, c2, dy, self.g[name + '/kernel'], self.g[name + '/bias'],
+            lib.ssr_conv3d_wgrad_tc(x1, c1, x2, c2, dy, self.g[name + '/kernel'], None,
                                     self._wg_scratch, self._wg_scratch.numel() * 4, self.B, *d, cout, st)
         else:
-            lib.ssr_conv3d_wgrad_ref(x1, c1, x2, c2, dy, self.g[name + '/kernel'], self.g[name + '/bias'], self.B, *d,
+            lib.ssr_conv3d_wgrad_ref(x1, c1, x2, c2, dy, self.g[name + '/kernel'], None, self.B, *d,
                                      cout, self.k, st)
 
     def _wgrad_tc_ok(self, c1, c2, cout):
@@ -347,10 +347,10 @@ class UNet3D:
             c0, c1n = 'unet_conv_uparm_%d_0' % (L + d), 'unet_conv_uparm_%d_1' % (L + d)
             bn = 'unet_bn_up_%d' % d
             lib.ssr_bn_bwd(self.dbn_dec[l], self.g1[l], self.stats_dec[l], self.nvox[l], F[l], None, 0, 0, 1, self.ga[l],
-                           self.g[bn + '/gamma'], self.g[bn + '/beta'], self.sums, st)
+                           self.g[bn + '/gamma'], self.g[bn + '/beta'], self.g[c1n + '/bias'], self.sums, st)
             self._conv_wgrad(c1n, self.g0[l], F[l], None, 0, self.ga[l], l, F[l])
             self._conv_dgrad(c1n, self.ga[l], self.gb[l], l, F[l], F[l])
-            lib.ssr_elu_bwd(self.gb[l], 0, 0, self.g0[l], None, self.nvox[l], F[l], self.gb[l], st)
+            lib.ssr_elu_bwd(self.gb[l], 0, 0, self.g0[l], None, self.nvox[l], F[l], self.gb[l], self.g[c0 + '/bias'], st)
             self._conv_wgrad(c0, self.h1[l], F[l], self.u[l], F[l + 1], self.gb[l], l, F[l])
             self._conv_dgrad(c0, self.gb[l], self.dcat[l], l, F[l] + F[l + 1], F[l])
             tgt = self.dbn_dec[l + 1] if l + 1 <= L - 2 else self.dbn_bott
@@ -360,16 +360,16 @@ class UNet3D:
             c0, c1n, bn = 'unet_conv_downarm_%d_0' % l, 'unet_conv_downarm_%d_1' % l, 'unet_bn_down_%d' % l
             if l == L - 1:
                 lib.ssr_bn_bwd(self.dbn_bott, self.h1[l], self.stats_enc[l], self.nvox[l], F[l], None, 0, 0, 1,
-                               self.ga[l], self.g[bn + '/gamma'], self.g[bn + '/beta'], self.sums, st)
+                               self.ga[l], self.g[bn + '/gamma'], self.g[bn + '/beta'], self.g[c1n + '/bias'], self.sums, st)
             else:
                 lib.ssr_maxpool_bwd(self.dp[l + 1], self.h1[l], self.stats_enc[l], B, *self.ldims[l], F[l], self.ga[l],
                                     st)
                 lib.ssr_bn_bwd(self.ga[l], self.h1[l], self.stats_enc[l], self.nvox[l], F[l], self.dcat[l],
                                F[l] + F[l + 1], 0, 1, self.ga[l], self.g[bn + '/gamma'], self.g[bn + '/beta'],
-                               self.sums, st)
+                               self.g[c1n + '/bias'], self.sums, st)
             self._conv_wgrad(c1n, self.h0[l], F[l], None, 0, self.ga[l], l, F[l])
             self._conv_dgrad(c1n, self.ga[l], self.gb[l], l, F[l], F[l])
-            lib.ssr_elu_bwd(self.gb[l], 0, 0, self.h0[l], None, self.nvox[l], F[l], self.gb[l], st)
+            lib.ssr_elu_bwd(self.gb[l], 0, 0, self.h0[l], None, self.nvox[l], F[l], self.gb[l], self.g[c0 + '/bias'], st)
             x, cx = (self._image, self.cin) if l == 0 else (self.inp[l], F[l - 1])
             self._conv_wgrad(c0, x, cx, None, 0, self.gb[l], l, F[l])
             if l > 0:
