@@ -24,5 +24,5 @@ def probe(name):
     print('   producer wait(emptyA) %8.0f | mma wait(fullA) %8.0f | mma wait(fullB) %8.0f' % (
         np.median(d[:, 8]), np.median(d[:, 9]), np.median(d[:, 10])))
 
-for n in (sys.argv[1].split(',') if len(sys.argv) > 1 else ['fwd24', 'fwd72', 'dgrad72', 'fwd96']):
+for n in (sys.argv[1].split(',') if len(sys.argv) > 1 else ['fwd24', 'fwd72', 'dgrad72', 'fwd96', 'wgrad24', 'wgrad72', 'wgrad96']):
     probe(n)

@@ -493,6 +493,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
   uint64_t* accFull = emptyB + G.SBT;
   uint32_t* tmem_slot = (uint32_t*)(accFull + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* dbg = (g_dbg && (blockIdx.x % 13) == 0 && blockIdx.x / 13 < 128) ? g_dbg + (blockIdx.x / 13) * 16 : nullptr;
+  if (threadIdx.x == 0) DBG_STAMP(0);
 
   int t = blockIdx.x;
   const int zs_i = t % G.n0splits; t /= G.n0splits;
@@ -521,6 +523,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) DBG_STAMP(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -551,14 +554,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
       const uint32_t idesc = make_idesc_tf32(G.NT) | (1u << 15) | (1u << 16);
       int sa = 0, pa = 0;
       uint32_t started = 0;
+      long long wait_a = 0, wait_b = 0;
+      if (lane == 0) DBG_STAMP(3);
       for (int zin = zin_lo; zin <= zin_hi; ++zin) {
         const int zo_new = zin - k0g + 1;
         if (zo_new >= zs && zo_new < ze) {
           const int p = zo_new - zs;
+          const long long w0 = dbg ? clock64() : 0;
           mbar_wait(fullB + (p % G.SBT), (p / G.SBT) & 1);
+          if (dbg) wait_b += clock64() - w0;
         }
         if (zin >= 0 && zin < G.D0) {
-          mbar_wait(fullA + sa, pa);
+          { const long long w0 = dbg ? clock64() : 0; mbar_wait(fullA + sa, pa); if (dbg) wait_a += clock64() - w0; }
           tc_fence_after();
           const uint32_t alo0 = desc_lo(smem_u32(sA + (size_t)sa * SLAB_BYTES), 1024);      // M atoms = d1 taps
           if (elect_one()) {
@@ -589,11 +596,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
       }
       if (elect_one()) umma_commit(accFull);
       __syncwarp();
+      if (lane == 0) { DBG_STAMP(4); if (dbg) { dbg[9] = wait_a; dbg[10] = wait_b; } }
     }
   } else {
     const int q = warp & 3;                       // rows 32q..32q+31 <-> d1 tap k1 = q (q == 3: unused atom)
     mbar_wait(accFull, 0);
     tc_fence_after();
+    if (warp == 2 && lane == 0) DBG_STAMP(5);
     // accumulator kk received MMAs iff some dY plane zo of the range pairs with an in-bounds X plane zo + k0 - 1
     uint32_t started = 0;
     for (int kk = 0; kk < G.KG; ++kk)
@@ -618,10 +627,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
         }
       }
     }
+    if (warp == 2 && lane == 0) DBG_STAMP(6);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)G.tmem_cols);
+  if (threadIdx.x == 0) DBG_STAMP(7);
 }
 
 // ---------------------------------------------------------------------------------------------------------
