@@ -636,6 +636,145 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// weight gradient, Cout <= 32 (the full-resolution layers = most of the wgrad time): the three d2 taps ride in N.
+//   dW[k0][k1][k2][ci][co] = sum_v X[v0+k0-1, v1+k1-1, v2'][ci] * dY[v0, v1, v2'-k2+1][co]          (v2' = v2 + k2 - 1)
+//   A = X slab of plane (zo + k0 - 1), unshifted in d2;  M = (k1, ci) as before
+//   B = THREE dY tiles of plane zo, TMA boxes shifted by (1 - k2) along d2 (OOB zero-fill)  ->  N = (k2, co) = 96
+// One MMA (N = 96: 56 cycles) does the work of three N = 32 MMAs (3 x 40 cycles), X is read once instead of 3x.
+// The CTA walks the dY planes of its range; X slabs live in a rolling ring (planes zo-1, zo, zo+1 + one prefetched),
+// dY stages are double buffered: nothing the MMA warp needs is ever loaded late.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int WK_SA = 5, WK_SB = 2, WK_N = 96;
+constexpr int WK_BSTAGE = 3 * WG_BTILE_BYTES;            // 49152
+
+__global__ void __launch_bounds__(192, 1)
+wgrad_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_x2,
+                    const __grid_constant__ CUtensorMap map_dy, float* __restrict__ dw, const WgGeom G) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + (size_t)WK_SA * SLAB_BYTES;
+  uint64_t* bars = (uint64_t*)(sB + (size_t)WK_SB * WK_BSTAGE);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = bars + WK_SA;
+  uint64_t* fullB = bars + 2 * WK_SA;
+  uint64_t* emptyB = fullB + WK_SB;
+  uint64_t* accFull = emptyB + WK_SB;
+  uint32_t* tmem_slot = (uint32_t*)(accFull + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int t = blockIdx.x;
+  const int zs_i = t % G.n0splits; t /= G.n0splits;
+  const int t2 = t % G.n2tiles; t /= G.n2tiles;
+  const int t1 = t % G.n1tiles; t /= G.n1tiles;
+  const int b = t % G.B;
+  const int ch = t / G.B;
+  const int x0 = t2 * TM2, y0 = t1 * TM1;
+  const int zs = zs_i * G.zlen, ze = min(G.D0, zs + G.zlen);
+  const int pmin = max(zs - 1, 0), pmax = min(ze, G.D0 - 1);      // X planes used: [pmin, pmax]
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < WK_SA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, 1); }
+    for (int i = 0; i < WK_SB; ++i) { mbar_init(fullB + i, 1); mbar_init(emptyB + i, 1); }
+    mbar_init(accFull, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const CUtensorMap* mx = G.chunk_src[ch] ? &map_x2 : &map_x1;
+      const int c0 = G.chunk_c0[ch];
+      int next_a = pmin;
+      for (int zo = zs; zo < ze; ++zo) {
+        const int need = min(zo + 1, pmax);
+        for (; next_a <= need; ++next_a) {
+          const int i = next_a - pmin, sa = i % WK_SA;
+          mbar_wait(emptyA + sa, ((i / WK_SA) & 1) ^ 1);
+          mbar_expect_tx(fullA + sa, SLAB_BYTES);
+          tma_load_5d(mx, fullA + sa, sA + (size_t)sa * SLAB_BYTES, c0, x0, y0 - 1, next_a, b);
+        }
+        const int j = zo - zs, sb = j % WK_SB;
+        mbar_wait(emptyB + sb, ((j / WK_SB) & 1) ^ 1);
+        mbar_expect_tx(fullB + sb, WK_BSTAGE);
+        for (int k2 = 0; k2 < 3; ++k2)
+          tma_load_5d(&map_dy, fullB + sb, sB + (size_t)sb * WK_BSTAGE + (size_t)k2 * WG_BTILE_BYTES, 0, x0 - k2 + 1, y0, zo, b);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_tf32(WK_N) | (1u << 15) | (1u << 16);
+    const uint32_t a_base = desc_lo(smem_u32(sA), 1024), b_base = desc_lo(smem_u32(sB), WG_BTILE_BYTES);
+    uint32_t started = 0;
+    int waited_a = pmin - 1;                    // highest X plane whose slab has been waited for
+    for (int zo = zs; zo < ze; ++zo) {
+      const int j = zo - zs, sb = j % WK_SB;
+      mbar_wait(fullB + sb, (j / WK_SB) & 1);
+      const int need = min(zo + 1, pmax);
+      for (; waited_a < need; ++waited_a) {
+        const int i = waited_a + 1 - pmin;
+        mbar_wait(fullA + (i % WK_SA), (i / WK_SA) & 1);
+      }
+      tc_fence_after();
+      const uint32_t blo = b_base + (uint32_t)sb * (WK_BSTAGE >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int k0 = 0; k0 < 3; ++k0) {
+          const int p = zo + k0 - 1;
+          if (p < 0 || p >= G.D0) continue;
+          const uint32_t alo = a_base + (uint32_t)((p - pmin) % WK_SA) * (SLAB_BYTES >> 4);
+          umma_chain_mn16(tmem_base + (uint32_t)(k0 * WK_N), alo, blo, DESC_HI_MN_SW128_32B, idesc, (started >> k0) & 1u);
+        }
+        umma_commit(emptyB + sb);
+        if (zo - 1 >= pmin) umma_commit(emptyA + ((zo - 1 - pmin) % WK_SA));     // X plane zo-1: last use was this step
+      }
+      __syncwarp();
+#pragma unroll
+      for (int k0 = 0; k0 < 3; ++k0) {
+        const int p = zo + k0 - 1;
+        if (p >= 0 && p < G.D0) started |= 1u << k0;
+      }
+    }
+    if (elect_one()) umma_commit(accFull);
+    __syncwarp();
+  } else {
+    const int q = warp & 3;                       // rows 32q..32q+31 <-> d1 tap k1 = q (q == 3: unused atom)
+    mbar_wait(accFull, 0);
+    tc_fence_after();
+    uint32_t started = 0;
+    for (int k0 = 0; k0 < 3; ++k0)
+      for (int zo = zs; zo < ze; ++zo) {
+        const int p = zo + k0 - 1;
+        if (p >= 0 && p < G.D0) { started |= 1u << k0; break; }
+      }
+    const int valid = G.chunk_valid[ch];
+    const int cin_idx = (G.chunk_src[ch] ? G.C1 : 0) + G.chunk_c0[ch] + lane;
+    for (int k0 = 0; k0 < 3; ++k0) {
+      if (!((started >> k0) & 1u)) continue;      // uniform
+      for (int cb = 0; cb < WK_N; cb += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(k0 * WK_N + cb), v);
+        tmem_ld_wait();
+        const int k2 = cb >> 5, cobase = cb & 31;  // column = k2 * 32 + co
+        if (q < 3 && lane < valid) {
+          float* o = dw + ((long long)(((k0 * 3 + q) * 3 + k2)) * G.Cin + cin_idx) * G.Cout + cobase;
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (cobase + e < G.Cout) atomicAdd(o + e, __uint_as_float(v[e]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // microbenchmark: issue cost of tcgen05.mma.kind::tf32 (M=128, N, K=8, both operands from shared memory) as a
 // function of N, of the number of accumulators cycled through and of the chain length on one accumulator.
 // No TMA, shared memory contents are irrelevant.  out[blockIdx.x] = cycles per MMA.
@@ -908,11 +1047,14 @@ int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const 
   for (int c = 0; c < C2; c += 32) { SSR_CHECK_ARG(nch < MAX_CHUNKS, "too many channels"); G.chunk_src[nch] = 1; G.chunk_c0[nch] = (short)c; G.chunk_valid[nch] = (unsigned char)(C2 - c < 32 ? C2 - c : 32); ++nch; }
   G.nchunks = nch; G.C1 = C1;
   G.n2tiles = (D2 + TM2 - 1) / TM2; G.n1tiles = (D1 + TM1 - 1) / TM1;
-  const long long base_units = (long long)nch * 3 * (3 / G.KG) * G.nNtiles * G.n1tiles * G.n2tiles * B;
+  const bool k2n = Npad == 32 && !getenv("SSR_WGRAD_NO_K2N");    // Cout <= 32: d2 taps in the MMA N dimension
+  const long long base_units = k2n ? (long long)nch * G.n1tiles * G.n2tiles * B
+                                   : (long long)nch * 3 * (3 / G.KG) * G.nNtiles * G.n1tiles * G.n2tiles * B;
   // enough CTAs for >= ~8 waves of 148 (tail-wave loss < ~6 %), but at least 8 planes per CTA (halo planes are re-read)
   int S = (int)((8 * 148 + base_units - 1) / base_units); if (S < 1) S = 1; if (S > (D0 + 7) / 8) S = (D0 + 7) / 8; if (S < 1) S = 1;
   G.zlen = (D0 + S - 1) / S; G.n0splits = (D0 + G.zlen - 1) / G.zlen;
-  const size_t smem = 1024 + (size_t)G.SA * SLAB_BYTES + (size_t)G.SBT * bstage + 512;
+  const size_t smem = k2n ? 1024 + (size_t)WK_SA * SLAB_BYTES + (size_t)WK_SB * WK_BSTAGE + 512
+                          : 1024 + (size_t)G.SA * SLAB_BYTES + (size_t)G.SBT * bstage + 512;
   CUtensorMap m1, m2, my;
   const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;     // MN-major tf32 operands (UMMA 128B_BASE32B)
   int rc = make_map_act(&m1, x1, C1, B, D0, D1, D2, TM1 + 2, swz); if (rc) return rc;
@@ -921,12 +1063,14 @@ int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const 
   static bool attr_set = false;
   if (!attr_set) {
     SSR_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SSR_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_k2n_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const long long nblk = base_units * G.n0splits;
   SSR_CHECK_ARG(nblk < (1LL << 31), "grid too large");
   cudaStream_t st = (cudaStream_t)stream;
-  wgrad_tc_kernel<<<(unsigned)nblk, 192, smem, st>>>(m1, m2, my, dw, G);
+  if (k2n) wgrad_tc_k2n_kernel<<<(unsigned)nblk, 192, smem, st>>>(m1, m2, my, dw, G);
+  else wgrad_tc_kernel<<<(unsigned)nblk, 192, smem, st>>>(m1, m2, my, dw, G);
   SSR_COUNT_LAUNCH();
   SSR_CHECK_LAUNCH();
   if (db) {
