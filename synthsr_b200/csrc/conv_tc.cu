@@ -221,12 +221,19 @@ __device__ __forceinline__ bool group_needed(const TcGeom& G, int z0, int k0g) {
   return false;
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The TMEM holds TWO accumulator sets,
+// so the epilogue of tile i (TMEM -> registers -> bias/ELU -> global) overlaps the MMAs of tile i+1, and the TMA
+// producer runs ahead across tile boundaries (no pipeline refill, no per-tile setup).
 __global__ void __launch_bounds__(192, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_x2,
                  const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias, float* __restrict__ y,
                  const TcGeom G) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [A stages][B stages][barriers]
+  // carve: [A stages][B stages][barriers][bias]
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   const int bgroup_bytes = G.KG * 3 * G.NT * 128;
@@ -236,31 +243,23 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
   uint64_t* emptyA = bars + G.SA;
   uint64_t* fullB = bars + 2 * G.SA;
   uint64_t* emptyB = fullB + SB;
-  uint64_t* accFull = emptyB + SB;
-  uint32_t* tmem_slot = (uint32_t*)(accFull + 1);
-  float* sbias = (float*)(bars + 32);              // NT floats (<= 192), 16-byte aligned, zero padded
+  uint64_t* accFull = emptyB + SB;                 // [2]
+  uint64_t* accEmpty = accFull + 2;                // [2]
+  uint32_t* tmem_slot = (uint32_t*)(accEmpty + 2);
+  float* sbias = (float*)(bars + 32);              // Npad floats (<= 576), 16-byte aligned, zero padded
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long* dbg = (g_dbg && (blockIdx.x % 61) == 0 && blockIdx.x / 61 < 128) ? g_dbg + (blockIdx.x / 61) * 16 : nullptr;
+  long long* dbg = (g_dbg && (blockIdx.x % 2) == 0 && blockIdx.x / 2 < 74) ? g_dbg + (blockIdx.x / 2) * 16 : nullptr;
   if (threadIdx.x == 0) DBG_STAMP(0);
-
-  // tile decode
-  int t = blockIdx.x;
-  const int nt = t % G.nNtiles; t /= G.nNtiles;
-  const int t2 = t % G.n2tiles; t /= G.n2tiles;
-  const int t1 = t % G.n1tiles; t /= G.n1tiles;
-  const int t0 = t % G.n0tiles;
-  const int b = t / G.n0tiles;
-  const int x0 = t2 * TM2, y0 = t1 * TM1, z0 = t0 * G.TZ, n0 = nt * G.NT;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < G.SA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, 1); }
     for (int i = 0; i < SB; ++i) { mbar_init(fullB + i, 1); mbar_init(emptyB + i, 1); }
-    mbar_init(accFull, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(accFull + i, 1); mbar_init(accEmpty + i, 4); }   // 4 epilogue warps arrive
     fence_barrier_init();
     fence_proxy_async();
   }
-  for (int i = threadIdx.x; i < G.NT; i += blockDim.x) sbias[i] = (bias && n0 + i < G.Cout) ? bias[n0 + i] : 0.f;
+  for (int i = threadIdx.x; i < G.Npad; i += blockDim.x) sbias[i] = (bias && i < G.Cout) ? bias[i] : 0.f;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_x1);
     tma_prefetch_desc(&map_x2);
@@ -272,38 +271,53 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) DBG_STAMP(1);
+  const int ntiles = G.B * G.n0tiles * G.n1tiles * G.n2tiles * G.nNtiles;
+  const uint32_t set_cols = (uint32_t)(G.TZ * G.NT);
+
+#define DECODE_TILE(tile)                                                       \
+  int t_ = (tile);                                                               \
+  const int nt = t_ % G.nNtiles; t_ /= G.nNtiles;                                \
+  const int t2 = t_ % G.n2tiles; t_ /= G.n2tiles;                                \
+  const int t1 = t_ % G.n1tiles; t_ /= G.n1tiles;                                \
+  const int t0 = t_ % G.n0tiles;                                                 \
+  const int b = t_ / G.n0tiles;                                                  \
+  const int x0 = t2 * TM2, y0 = t1 * TM1, z0 = t0 * G.TZ, n0 = nt * G.NT;        \
+  const int nz = min(G.TZ, G.D0 - z0);                                           \
+  (void)x0; (void)y0; (void)n0; (void)b; (void)nz;
 
   // Closed-form slab ranges (identical in the producer and the MMA warp; no per-slab predicate evaluation in the issue
-  // loop).  nz = valid output planes of this tile.  For the d0-tap group starting at k0g, slab index zin (input plane
+  // loop).  nz = valid output planes of the tile.  For the d0-tap group starting at k0g, slab index zin (input plane
   // z0 + k0g + zin - 1) contributes to accumulators zo = zin - kk, kk in [kk_lo, kk_hi]:
   //   zin in [zin_lo, zin_hi),  zin_lo = 1 iff the first plane would be -1,  zin_hi clipped at the volume end.
-  const int nz = min(G.TZ, G.D0 - z0);
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
       int sa = 0, pa = 0, sb = 0, pb = 0;
       long long wait_empty = 0;
-      for (int ch = 0; ch < G.nchunks; ++ch) {
-        const CUtensorMap* mx = G.chunk_src[ch] ? &map_x2 : &map_x1;
-        const int c0 = G.chunk_c0[ch];
-        for (int k2 = 0; k2 < 3; ++k2) {
-          for (int k0g = 0; k0g < 3; k0g += G.KG) {
-            const int zin_lo = (z0 + k0g == 0) ? 1 : 0;
-            const int zin_hi = min(nz + G.KG - 1, G.D0 - (z0 + k0g - 1));
-            if (zin_lo >= zin_hi) continue;
-            mbar_wait(emptyB + sb, pb ^ 1);
-            mbar_expect_tx(fullB + sb, (uint32_t)bgroup_bytes);
-            for (int kk = 0; kk < G.KG; ++kk)
-              for (int k1 = 0; k1 < 3; ++k1) {
-                const int row = (((ch * 3 + k2) * 3 + (k0g + kk)) * 3 + k1) * G.Npad + n0;
-                tma_load_2d(&map_w, fullB + sb, sB + (size_t)sb * bgroup_bytes + (size_t)(kk * 3 + k1) * G.NT * 128, 0, row);
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        DECODE_TILE(tile)
+        for (int ch = 0; ch < G.nchunks; ++ch) {
+          const CUtensorMap* mx = G.chunk_src[ch] ? &map_x2 : &map_x1;
+          const int c0 = G.chunk_c0[ch];
+          for (int k2 = 0; k2 < 3; ++k2) {
+            for (int k0g = 0; k0g < 3; k0g += G.KG) {
+              const int zin_lo = (z0 + k0g == 0) ? 1 : 0;
+              const int zin_hi = min(nz + G.KG - 1, G.D0 - (z0 + k0g - 1));
+              if (zin_lo >= zin_hi) continue;
+              mbar_wait(emptyB + sb, pb ^ 1);
+              mbar_expect_tx(fullB + sb, (uint32_t)bgroup_bytes);
+              for (int kk = 0; kk < G.KG; ++kk)
+                for (int k1 = 0; k1 < 3; ++k1) {
+                  const int row = (((ch * 3 + k2) * 3 + (k0g + kk)) * 3 + k1) * G.Npad + n0;
+                  tma_load_2d(&map_w, fullB + sb, sB + (size_t)sb * bgroup_bytes + (size_t)(kk * 3 + k1) * G.NT * 128, 0, row);
+                }
+              if (++sb == SB) { sb = 0; pb ^= 1; }
+              for (int zin = zin_lo; zin < zin_hi; ++zin) {
+                { const long long w0 = dbg ? clock64() : 0; mbar_wait(emptyA + sa, pa ^ 1); if (dbg) wait_empty += clock64() - w0; }
+                mbar_expect_tx(fullA + sa, SLAB_BYTES);
+                tma_load_5d(mx, fullA + sa, sA + (size_t)sa * SLAB_BYTES, c0, x0 + k2 - 1, y0 - 1, z0 + k0g + zin - 1, b);
+                if (++sa == G.SA) { sa = 0; pa ^= 1; }
               }
-            if (++sb == SB) { sb = 0; pb ^= 1; }
-            for (int zin = zin_lo; zin < zin_hi; ++zin) {
-              { const long long w0 = dbg ? clock64() : 0; mbar_wait(emptyA + sa, pa ^ 1); if (dbg) wait_empty += clock64() - w0; }
-              mbar_expect_tx(fullA + sa, SLAB_BYTES);
-              tma_load_5d(mx, fullA + sa, sA + (size_t)sa * SLAB_BYTES, c0, x0 + k2 - 1, y0 - 1, z0 + k0g + zin - 1, b);
-              if (++sa == G.SA) { sa = 0; pa ^= 1; }
             }
           }
         }
@@ -321,119 +335,137 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
       const uint32_t NT = (uint32_t)G.NT;
       const uint32_t btile16 = (NT * 128u) >> 4;
       const uint32_t a_base = desc_lo(smem_u32(sA), 16), b_base = desc_lo(smem_u32(sB), 16);
-      int sa = 0, pa = 0, sb = 0, pb = 0;
-      uint32_t first = 1u;                       // 1 until every accumulator has received its first MMA group
+      int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
       long long wait_a = 0, wait_b = 0;
       if (lane == 0) DBG_STAMP(3);
-      for (int ch = 0; ch < nchunks; ++ch) {
-        const int nks = G.chunk_ks[ch];
-        for (int k2 = 0; k2 < 3; ++k2) {
-          for (int k0g = 0; k0g < 3; k0g += KG) {
-            const int zin_lo = (z0 + k0g == 0) ? 1 : 0;
-            const int zin_hi = min(nz + KG - 1, D0 - (z0 + k0g - 1));
-            if (zin_lo >= zin_hi) continue;
-            { const long long w0 = dbg ? clock64() : 0; mbar_wait(fullB + sb, pb); if (dbg) wait_b += clock64() - w0; }
-            const uint32_t blo0 = b_base + (uint32_t)sb * ((uint32_t)bgroup_bytes >> 4);
-            for (int zin = zin_lo; zin < zin_hi; ++zin) {
-              { const long long w0 = dbg ? clock64() : 0; mbar_wait(fullA + sa, pa); if (dbg) wait_a += clock64() - w0; }
-              tc_fence_after();
-              const uint32_t alo0 = a_base + (uint32_t)sa * (SLAB_BYTES >> 4);
-              const int kk_lo = max(0, zin - nz + 1), kk_hi = min(KG - 1, zin);
-              if (elect_one()) {
-                for (int kk = kk_lo; kk <= kk_hi; ++kk) {
-                  const int zo = zin - kk;
-                  const uint32_t dcol = tmem_base + (uint32_t)zo * NT;
-                  // first MMA ever into accumulator zo: chunk 0, k2 0, the group/slab/tap where zo is touched first
-                  uint32_t acc = 1u;
-                  if (first) {
-                    const int kfirst = (z0 + zo == 0) ? 1 : 0;           // global d0 tap that touches zo first
-                    acc = (k0g + kk == kfirst) ? 0u : 1u;
-                  }
-                  uint32_t alo = alo0;
-                  uint32_t blo = blo0 + (uint32_t)(kk * 3) * btile16;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        DECODE_TILE(tile)
+        const int set = it & 1;
+        const uint32_t acc_base = tmem_base + (uint32_t)set * set_cols;
+        mbar_wait(accEmpty + set, ((it >> 1) & 1) ^ 1);          // epilogue has drained this accumulator set
+        tc_fence_after();
+        uint32_t first = 1u;                       // 1 until every accumulator of the tile has received its first MMA
+        for (int ch = 0; ch < nchunks; ++ch) {
+          const int nks = G.chunk_ks[ch];
+          for (int k2 = 0; k2 < 3; ++k2) {
+            for (int k0g = 0; k0g < 3; k0g += KG) {
+              const int zin_lo = (z0 + k0g == 0) ? 1 : 0;
+              const int zin_hi = min(nz + KG - 1, D0 - (z0 + k0g - 1));
+              if (zin_lo >= zin_hi) continue;
+              { const long long w0 = dbg ? clock64() : 0; mbar_wait(fullB + sb, pb); if (dbg) wait_b += clock64() - w0; }
+              const uint32_t blo0 = b_base + (uint32_t)sb * ((uint32_t)bgroup_bytes >> 4);
+              for (int zin = zin_lo; zin < zin_hi; ++zin) {
+                { const long long w0 = dbg ? clock64() : 0; mbar_wait(fullA + sa, pa); if (dbg) wait_a += clock64() - w0; }
+                tc_fence_after();
+                const uint32_t alo0 = a_base + (uint32_t)sa * (SLAB_BYTES >> 4);
+                const int kk_lo = max(0, zin - nz + 1), kk_hi = min(KG - 1, zin);
+                if (elect_one()) {
+                  for (int kk = kk_lo; kk <= kk_hi; ++kk) {
+                    const int zo = zin - kk;
+                    const uint32_t dcol = acc_base + (uint32_t)zo * NT;
+                    // first MMA ever into accumulator zo: chunk 0, k2 0, the group/slab/tap where zo is touched first
+                    uint32_t acc = 1u;
+                    if (first) {
+                      const int kfirst = (z0 + zo == 0) ? 1 : 0;           // global d0 tap that touches zo first
+                      acc = (k0g + kk == kfirst) ? 0u : 1u;
+                    }
+                    uint32_t alo = alo0;
+                    uint32_t blo = blo0 + (uint32_t)(kk * 3) * btile16;
 #pragma unroll
-                  for (int k1 = 0; k1 < 3; ++k1) {
-                    if (nks == 4) umma_chain_k<4>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
-                    else if (nks == 3) umma_chain_k<3>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
-                    else if (nks == 2) umma_chain_k<2>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
-                    else umma_chain_k<1>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
-                    acc = 1u;
-                    alo += (uint32_t)(TM2 * 128 >> 4);
-                    blo += btile16;
+                    for (int k1 = 0; k1 < 3; ++k1) {
+                      if (nks == 4) umma_chain_k<4>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+                      else if (nks == 3) umma_chain_k<3>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+                      else if (nks == 2) umma_chain_k<2>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+                      else umma_chain_k<1>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+                      acc = 1u;
+                      alo += (uint32_t)(TM2 * 128 >> 4);
+                      blo += btile16;
+                    }
                   }
+                  umma_commit(emptyA + sa);          // slab may be overwritten once these MMAs have completed
                 }
-                umma_commit(emptyA + sa);          // slab may be overwritten once these MMAs have completed
+                __syncwarp();
+                if (++sa == SA) { sa = 0; pa ^= 1; }
               }
+              if (elect_one()) umma_commit(emptyB + sb);
               __syncwarp();
-              if (++sa == SA) { sa = 0; pa ^= 1; }
+              if (++sb == SB) { sb = 0; pb ^= 1; }
             }
-            if (elect_one()) umma_commit(emptyB + sb);
-            __syncwarp();
-            if (++sb == SB) { sb = 0; pb ^= 1; }
+            first = 0u;                              // after (chunk 0, k2 0) every accumulator has been initialised
           }
-          first = 0u;                              // after (chunk 0, k2 0) every accumulator has been initialised
         }
+        if (elect_one()) umma_commit(accFull + set);
+        __syncwarp();
+        if (lane == 0 && it == 0) { DBG_STAMP(4); if (dbg) { dbg[9] = wait_a; dbg[10] = wait_b; } }
       }
-      if (elect_one()) umma_commit(accFull);
-      __syncwarp();
-      if (lane == 0) { DBG_STAMP(4); if (dbg) { dbg[9] = wait_a; dbg[10] = wait_b; } }
+      if (lane == 0) DBG_STAMP(11);
     }
   } else {
     // ================================ epilogue (warps 2..5) ================================
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                    // GEMM row = voxel inside the tile
-    const int i1 = y0 + (r >> 3), i2 = x0 + (r & 7);
-    mbar_wait(accFull, 0);
-    tc_fence_after();
-    if (warp == 2 && lane == 0) DBG_STAMP(5);
-    const bool vox_ok = i1 < G.D1 && i2 < G.D2;
     const bool vec_ok = (G.Cout & 3) == 0;
-    for (int zo = 0; zo < G.TZ; ++zo) {
-      const int i0 = z0 + zo;
-      if (i0 >= G.D0) break;                        // uniform across the CTA
-      float* orow = y + ((((long long)b * G.D0 + i0) * G.D1 + i1) * G.D2 + i2) * G.Cout + n0;
-      for (int cb = 0; cb < G.NT; cb += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(zo * G.NT + cb), v);
-        tmem_ld_wait();
-        float o[16];
-        const float4* bs = reinterpret_cast<const float4*>(sbias + cb);      // zero padded to NT, 16-byte aligned
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      DECODE_TILE(tile)
+      const int set = it & 1;
+      const uint32_t acc_base = tmem_base + (uint32_t)set * set_cols;
+      const int i1 = y0 + (r >> 3), i2 = x0 + (r & 7);
+      mbar_wait(accFull + set, (it >> 1) & 1);
+      tc_fence_after();
+      if (warp == 2 && lane == 0 && it == 0) DBG_STAMP(5);
+      const bool vox_ok = i1 < G.D1 && i2 < G.D2;
+      for (int zo = 0; zo < nz; ++zo) {
+        const int i0 = z0 + zo;
+        float* orow = y + ((((long long)b * G.D0 + i0) * G.D1 + i1) * G.D2 + i2) * G.Cout + n0;
+        for (int cb = 0; cb < G.NT; cb += 16) {
+          uint32_t v[16];
+          tmem_ld16(acc_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(zo * G.NT + cb), v);
+          tmem_ld_wait();
+          float o[16];
+          const float4* bs = reinterpret_cast<const float4*>(sbias + n0 + cb);      // zero padded, 16-byte aligned
 #pragma unroll
-        for (int e4 = 0; e4 < 4; ++e4) {
-          const float4 bb = bs[e4];
-          o[e4 * 4 + 0] = __uint_as_float(v[e4 * 4 + 0]) + bb.x;
-          o[e4 * 4 + 1] = __uint_as_float(v[e4 * 4 + 1]) + bb.y;
-          o[e4 * 4 + 2] = __uint_as_float(v[e4 * 4 + 2]) + bb.z;
-          o[e4 * 4 + 3] = __uint_as_float(v[e4 * 4 + 3]) + bb.w;
-        }
-        if (G.act) {
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const float4 bb = bs[e4];
+            o[e4 * 4 + 0] = __uint_as_float(v[e4 * 4 + 0]) + bb.x;
+            o[e4 * 4 + 1] = __uint_as_float(v[e4 * 4 + 1]) + bb.y;
+            o[e4 * 4 + 2] = __uint_as_float(v[e4 * 4 + 2]) + bb.z;
+            o[e4 * 4 + 3] = __uint_as_float(v[e4 * 4 + 3]) + bb.w;
+          }
+          if (G.act) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {             // ELU without a branch: exp(min(x,0)) - 1 selected where x <= 0
-            const float neg = __expf(fminf(o[e], 0.f)) - 1.f;
-            o[e] = o[e] > 0.f ? o[e] : neg;
+            for (int e = 0; e < 16; ++e) {             // ELU without a branch: exp(min(x,0)) - 1 selected where x <= 0
+              const float neg = __expf(fminf(o[e], 0.f)) - 1.f;
+              o[e] = o[e] > 0.f ? o[e] : neg;
+            }
+          }
+          if (!vox_ok) continue;
+          const int nvalid = G.Cout - (n0 + cb);       // channels of this 16-block that exist
+          if (nvalid >= 16 && vec_ok) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 4)
+              *reinterpret_cast<float4*>(orow + cb + e) = make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]);
+          } else if (nvalid >= 8 && vec_ok) {
+            *reinterpret_cast<float4*>(orow + cb) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(orow + cb + 4) = make_float4(o[4], o[5], o[6], o[7]);
+#pragma unroll
+            for (int e = 8; e < 16; ++e)
+              if (e < nvalid) orow[cb + e] = o[e];
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (e < nvalid) orow[cb + e] = o[e];
           }
         }
-        if (!vox_ok) continue;
-        const int nvalid = G.Cout - (n0 + cb);       // channels of this 16-block that exist
-        if (nvalid >= 16 && vec_ok) {
-#pragma unroll
-          for (int e = 0; e < 16; e += 4)
-            *reinterpret_cast<float4*>(orow + cb + e) = make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]);
-        } else if (nvalid >= 8 && vec_ok) {
-          *reinterpret_cast<float4*>(orow + cb) = make_float4(o[0], o[1], o[2], o[3]);
-          *reinterpret_cast<float4*>(orow + cb + 4) = make_float4(o[4], o[5], o[6], o[7]);
-#pragma unroll
-          for (int e = 8; e < 16; ++e)
-            if (e < nvalid) orow[cb + e] = o[e];
-        } else {
-#pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if (e < nvalid) orow[cb + e] = o[e];
-        }
       }
+      // accumulator set drained: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(accEmpty + set);
+      if (warp == 2 && lane == 0 && it == 0) DBG_STAMP(6);
     }
   }
-  if (warp == 2 && lane == 0) DBG_STAMP(6);
+#undef DECODE_TILE
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)G.tmem_cols);
@@ -973,10 +1005,10 @@ int ssr_conv3d_fwd_tc(const float* x1, int C1, const float* x2, int C2, const fl
   G.Npad = round_up(Cout, 16);
   G.NT = pick_nt(G.Npad);
   G.nNtiles = G.Npad / G.NT;
-  int tz = 512 / G.NT; if (tz > 4) tz = 4; if (tz > D0) tz = D0; if (tz < 1) tz = 1;
+  int tz = 256 / G.NT; if (tz > 4) tz = 4; if (tz > D0) tz = D0; if (tz < 1) tz = 1;   // two accumulator sets in 512 columns
   G.TZ = tz;
   G.KG = (3 * 3 * G.NT * 128 <= 74 * 1024) ? 3 : 1;
-  int cols = G.TZ * G.NT, pc = 32;
+  int cols = 2 * G.TZ * G.NT, pc = 32;
   while (pc < cols) pc <<= 1;
   G.tmem_cols = pc;
   int nch = 0;
@@ -991,11 +1023,11 @@ int ssr_conv3d_fwd_tc(const float* x1, int C1, const float* x2, int C2, const fl
   G.nchunks = nch;
   G.n2tiles = (D2 + TM2 - 1) / TM2; G.n1tiles = (D1 + TM1 - 1) / TM1; G.n0tiles = (D0 + G.TZ - 1) / G.TZ;
   const int bgroup = G.KG * 3 * G.NT * 128;
-  const int budget = 227 * 1024 - 1024 /*align slack*/ - 1280 /*barriers + bias*/ - SB * bgroup;
+  const int budget = 227 * 1024 - 1024 /*align slack*/ - 2816 /*barriers + bias*/ - SB * bgroup;
   int sa = budget / SLAB_BYTES; if (sa > 8) sa = 8;
   SSR_CHECK_ARG(sa >= 2, "shared memory budget");
   G.SA = sa;
-  const size_t smem = 1024 + (size_t)G.SA * SLAB_BYTES + (size_t)SB * bgroup + 1280;
+  const size_t smem = 1024 + (size_t)G.SA * SLAB_BYTES + (size_t)SB * bgroup + 2816;
 
   CUtensorMap m1, m2, mw;
   int rc = make_map_act(&m1, x1, C1, B, D0, D1, D2);
@@ -1010,8 +1042,15 @@ int ssr_conv3d_fwd_tc(const float* x1, int C1, const float* x2, int C2, const fl
     attr_set = true;
   }
   const long long ntiles = (long long)B * G.n0tiles * G.n1tiles * G.n2tiles * G.nNtiles;
-  SSR_CHECK_ARG(ntiles < (1LL << 31), "grid too large");
-  conv3d_tc_kernel<<<(unsigned)ntiles, 192, smem, (cudaStream_t)stream>>>(m1, m2, mw, bias, y, G);
+  SSR_CHECK_ARG(ntiles < (1LL << 31) && G.Npad <= 576, "grid / channel count too large");
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    SSR_CHECK_CUDA(cudaGetDevice(&dev));
+    SSR_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const unsigned grid = (unsigned)(ntiles < num_sms ? ntiles : num_sms);       // persistent: one CTA per SM
+  conv3d_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(m1, m2, mw, bias, y, G);
   SSR_COUNT_LAUNCH();
   SSR_CHECK_LAUNCH();
   return SSR_OK;
