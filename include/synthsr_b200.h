@@ -109,6 +109,11 @@ int ssr_tc_set_debug(long long* buf);   /* profiling: per-CTA clock64 phase stam
 int ssr_tc_microbench(float* out, int nblocks, int N, int nacc, int chain, int iters, int kmajor, int commit_every,
                       int cycle_addr, void* stream);
 
+/* shared-memory descriptor probe (which unaligned / overlapping operand views the tensor core reads consistently with
+ * the TMA swizzle); a, b: [rows][32] fp32, d: [128][N]; p: HOST int[14], see conv_tc.cu */
+int ssr_tc_desc_probe(const float* a, int rows_a, const float* b, int rows_b, float* d, int swz, const int* p,
+                      void* stream);
+
 /* ---------------------------------------------------------------- U-Net: other layers ----------------------- */
 int ssr_channel_sum(const float* t, long long nvox, int C, float* out, void* stream);
 /* KL.BatchNormalization(axis=-1), training mode (ext/neuron/models.py:349-351, 475-477).

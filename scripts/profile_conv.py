@@ -22,6 +22,9 @@ def run(name, reps):
     g = torch.Generator(device='cuda').manual_seed(0)
     x1 = torch.randn((nv, c1), device='cuda', generator=g)
     x2 = torch.randn((nv, c2), device='cuda', generator=g) if c2 else None
+    if os.environ.get('SSR_CONST_DATA'):          # data-dependence experiment: constant operands
+        x1 = torch.full_like(x1, float(os.environ['SSR_CONST_DATA']))
+        x2 = torch.full_like(x2, float(os.environ['SSR_CONST_DATA'])) if c2 else None
     st = stream_ptr()
     flops = 2. * 27 * (c1 + c2) * co * nv
     if kind == 'fwd':
@@ -33,6 +36,8 @@ def run(name, reps):
         fn = lambda: lib.ssr_conv3d_fwd_tc(x1, c1, x2, c2, wp, b, y, 1, *d, co, 1, st)
     else:
         dy = torch.randn((nv, co), device='cuda', generator=g)
+        if os.environ.get('SSR_CONST_DATA'):
+            dy = torch.full_like(dy, float(os.environ['SSR_CONST_DATA']))
         dw = torch.zeros(27 * (c1 + c2) * co, device='cuda')
         fn = lambda: lib.ssr_conv3d_wgrad_tc(x1, c1, x2, c2, dy, dw, None, None, 0, 1, *d, co, st)
     fn()

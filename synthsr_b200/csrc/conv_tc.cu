@@ -183,6 +183,7 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(int N) {
 // ---------------------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------------------
+constexpr bool G_FENCE_IN_LOOP = false;
 constexpr int TM1 = 16, TM2 = 8;                  // output tile: 16 (d1) x 8 (d2) voxels = 128 GEMM rows
 constexpr int SLAB_ROWS = (TM1 + 2) * TM2;         // 144 rows x 128 B
 constexpr int SLAB_BYTES = SLAB_ROWS * 128;        // 18432 (multiple of 1024)
@@ -228,7 +229,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Persistent: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The TMEM holds TWO accumulator sets,
 // so the epilogue of tile i (TMEM -> registers -> bias/ELU -> global) overlaps the MMAs of tile i+1, and the TMA
 // producer runs ahead across tile boundaries (no pipeline refill, no per-tile setup).
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(288, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_x2,
                  const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias, float* __restrict__ y,
                  const TcGeom G) {
@@ -253,9 +254,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
   if (threadIdx.x == 0) DBG_STAMP(0);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < G.SA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, 1); }
-    for (int i = 0; i < SB; ++i) { mbar_init(fullB + i, 1); mbar_init(emptyB + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(accFull + i, 1); mbar_init(accEmpty + i, 4); }   // 4 epilogue warps arrive
+    // NW = G.TZ MMA warps: each of them releases every ring stage and signals every accumulator set
+    for (int i = 0; i < G.SA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, G.TZ); }
+    for (int i = 0; i < SB; ++i) { mbar_init(fullB + i, 1); mbar_init(emptyB + i, G.TZ); }
+    for (int i = 0; i < 2; ++i) { mbar_init(accFull + i, G.TZ); mbar_init(accEmpty + i, 4); }   // 4 epilogue warps arrive
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -325,11 +327,15 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
       DBG_STAMP(2);
       if (dbg) dbg[8] = wait_empty;
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer (whole warp converged, one elected lane issues) ======
-    // The issuing warp is alone on its instruction stream: scalar work between MMA chains costs ~2 cycles per
-    // instruction per MMA (profiles/r01_mma_issue_microbench.txt), so everything is hoisted / strength-reduced.
+  } else if (warp <= G.TZ) {
+    // ================================ MMA issuers: warp w owns accumulator (output plane) zo = w - 1 ================
+    // The thread that issues tcgen05.mma stalls while the tensor pipe is busy (shallow MMA queue), so with a single
+    // issuer every scalar instruction between two MMAs is exposed (measured 68 cycles per N=32 MMA against the 40-cycle
+    // pipe rate).  One issuing warp per accumulator: the chains are independent, so one warp's waits / descriptor
+    // arithmetic hide behind the other warps' MMAs.  Every warp walks all slabs (so that the ring barriers see NW
+    // arrivals per stage) and issues only the d0 tap kk = zin - zo that lands in its own accumulator.
     {
+      const int zo = warp - 1;
       const uint32_t idesc = make_idesc_tf32(G.NT);
       const int KG = G.KG, SA = G.SA, nchunks = G.nchunks, D0 = G.D0;
       const uint32_t NT = (uint32_t)G.NT;
@@ -337,14 +343,15 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
       const uint32_t a_base = desc_lo(smem_u32(sA), 16), b_base = desc_lo(smem_u32(sB), 16);
       int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
       long long wait_a = 0, wait_b = 0;
-      if (lane == 0) DBG_STAMP(3);
+      if (warp == 1 && lane == 0) DBG_STAMP(3);
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         DECODE_TILE(tile)
         const int set = it & 1;
-        const uint32_t acc_base = tmem_base + (uint32_t)set * set_cols;
+        const uint32_t dcol = tmem_base + (uint32_t)set * set_cols + (uint32_t)zo * NT;
+        const bool active = zo < nz;
         mbar_wait(accEmpty + set, ((it >> 1) & 1) ^ 1);          // epilogue has drained this accumulator set
         tc_fence_after();
-        uint32_t first = 1u;                       // 1 until every accumulator of the tile has received its first MMA
+        uint32_t acc = 0u;                         // first MMA of the tile into this accumulator overwrites
         for (int ch = 0; ch < nchunks; ++ch) {
           const int nks = G.chunk_ks[ch];
           for (int k2 = 0; k2 < 3; ++k2) {
@@ -356,20 +363,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
               const uint32_t blo0 = b_base + (uint32_t)sb * ((uint32_t)bgroup_bytes >> 4);
               for (int zin = zin_lo; zin < zin_hi; ++zin) {
                 { const long long w0 = dbg ? clock64() : 0; mbar_wait(fullA + sa, pa); if (dbg) wait_a += clock64() - w0; }
-                tc_fence_after();
-                const uint32_t alo0 = a_base + (uint32_t)sa * (SLAB_BYTES >> 4);
-                const int kk_lo = max(0, zin - nz + 1), kk_hi = min(KG - 1, zin);
-                if (elect_one()) {
-                  for (int kk = kk_lo; kk <= kk_hi; ++kk) {
-                    const int zo = zin - kk;
-                    const uint32_t dcol = acc_base + (uint32_t)zo * NT;
-                    // first MMA ever into accumulator zo: chunk 0, k2 0, the group/slab/tap where zo is touched first
-                    uint32_t acc = 1u;
-                    if (first) {
-                      const int kfirst = (z0 + zo == 0) ? 1 : 0;           // global d0 tap that touches zo first
-                      acc = (k0g + kk == kfirst) ? 0u : 1u;
-                    }
-                    uint32_t alo = alo0;
+                const int kk = zin - zo;
+                if (active && kk >= 0 && kk < KG) {            // warp-uniform
+                  if (elect_one()) {
+                    uint32_t alo = a_base + (uint32_t)sa * (SLAB_BYTES >> 4);
                     uint32_t blo = blo0 + (uint32_t)(kk * 3) * btile16;
 #pragma unroll
                     for (int k1 = 0; k1 < 3; ++k1) {
@@ -381,27 +378,29 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                       alo += (uint32_t)(TM2 * 128 >> 4);
                       blo += btile16;
                     }
+                    umma_commit(emptyA + sa);        // this warp's reads of the slab are done once these MMAs complete
                   }
-                  umma_commit(emptyA + sa);          // slab may be overwritten once these MMAs have completed
+                  acc = 1u;
+                } else if (lane == 0) {
+                  mbar_arrive(emptyA + sa);          // not my tap: release immediately
                 }
                 __syncwarp();
                 if (++sa == SA) { sa = 0; pa ^= 1; }
               }
-              if (elect_one()) umma_commit(emptyB + sb);
+              if (elect_one()) umma_commit(emptyB + sb);   // arrives when this warp's MMAs on the group are complete
               __syncwarp();
               if (++sb == SB) { sb = 0; pb ^= 1; }
             }
-            first = 0u;                              // after (chunk 0, k2 0) every accumulator has been initialised
           }
         }
         if (elect_one()) umma_commit(accFull + set);
         __syncwarp();
-        if (lane == 0 && it == 0) { DBG_STAMP(4); if (dbg) { dbg[9] = wait_a; dbg[10] = wait_b; } }
+        if (warp == 1 && lane == 0 && it == 0) { DBG_STAMP(4); if (dbg) { dbg[9] = wait_a; dbg[10] = wait_b; } }
       }
-      if (lane == 0) DBG_STAMP(11);
+      if (warp == 1 && lane == 0) DBG_STAMP(11);
     }
   } else {
-    // ================================ epilogue (warps 2..5) ================================
+    // ================================ epilogue (last four warps) ================================
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                    // GEMM row = voxel inside the tile
     const bool vec_ok = (G.Cout & 3) == 0;
@@ -413,7 +412,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
       const int i1 = y0 + (r >> 3), i2 = x0 + (r & 7);
       mbar_wait(accFull + set, (it >> 1) & 1);
       tc_fence_after();
-      if (warp == 2 && lane == 0 && it == 0) DBG_STAMP(5);
+      if (warp == G.TZ + 1 && lane == 0 && it == 0) DBG_STAMP(5);
       const bool vox_ok = i1 < G.D1 && i2 < G.D2;
       for (int zo = 0; zo < nz; ++zo) {
         const int i0 = z0 + zo;
@@ -462,7 +461,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(accEmpty + set);
-      if (warp == 2 && lane == 0 && it == 0) DBG_STAMP(6);
+      if (warp == G.TZ + 1 && lane == 0 && it == 0) DBG_STAMP(6);
     }
   }
 #undef DECODE_TILE
@@ -492,7 +491,7 @@ struct WgGeom {
   int Cin, C1, Cout;
   int NT, nNtiles, KG, SA, SBT;
   int nchunks, n1tiles, n2tiles, n0splits, zlen;
-  int tmem_cols;
+  int tmem_cols, exp_flags;
   unsigned char chunk_src[MAX_CHUNKS];
   unsigned char chunk_valid[MAX_CHUNKS];
   short chunk_c0[MAX_CHUNKS];
@@ -598,7 +597,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
         }
         if (zin >= 0 && zin < G.D0) {
           { const long long w0 = dbg ? clock64() : 0; mbar_wait(fullA + sa, pa); if (dbg) wait_a += clock64() - w0; }
-          tc_fence_after();
+          if (G_FENCE_IN_LOOP) tc_fence_after();   // not needed for TMA-written operands (mbarrier complete_tx orders them); costs a pipe drain
           const uint32_t alo0 = desc_lo(smem_u32(sA + (size_t)sa * SLAB_BYTES), 1024);      // M atoms = d1 taps
           if (elect_one()) {
 #pragma unroll
@@ -678,8 +677,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
 // ---------------------------------------------------------------------------------------------------------
 constexpr int WK_SA = 5, WK_SB = 2, WK_N = 96;
 constexpr int WK_BSTAGE = 3 * WG_BTILE_BYTES;            // 49152
+constexpr int WK_THREADS = 256;                          // warp 0 TMA, warps 1-3 MMA (one per d0 tap), warps 4-7 epilogue
 
-__global__ void __launch_bounds__(192, 1)
+// The thread that issues tcgen05.mma is stalled while the tensor pipe is busy (the MMA queue is shallow), so all the
+// scalar work between two MMA chains (descriptor arithmetic, barrier waits, commits) is exposed when a single warp
+// issues everything: measured 74 cycles per N=96 MMA against the 56-cycle pipe rate.  Here each d0 tap (= accumulator)
+// has its own issuing warp; their chains are independent, so one warp's scalar work hides behind the others' MMAs.
+__global__ void __launch_bounds__(WK_THREADS, 1)
 wgrad_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_x2,
                     const __grid_constant__ CUtensorMap map_dy, float* __restrict__ dw, const WgGeom G) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -694,6 +698,8 @@ wgrad_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_con
   uint64_t* accFull = emptyB + WK_SB;
   uint32_t* tmem_slot = (uint32_t*)(accFull + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* dbg = (g_dbg && (blockIdx.x % 9) == 0 && blockIdx.x / 9 < 128) ? g_dbg + (blockIdx.x / 9) * 16 : nullptr;
+  if (threadIdx.x == 0) DBG_STAMP(0);
 
   int t = blockIdx.x;
   const int zs_i = t % G.n0splits; t /= G.n0splits;
@@ -706,9 +712,10 @@ wgrad_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_con
   const int pmin = max(zs - 1, 0), pmax = min(ze, G.D0 - 1);      // X planes used: [pmin, pmax]
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < WK_SA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, 1); }
-    for (int i = 0; i < WK_SB; ++i) { mbar_init(fullB + i, 1); mbar_init(emptyB + i, 1); }
-    mbar_init(accFull, 1);
+    // every X slab / dY stage is released by all three MMA warps (a warp that never reads a slab arrives for it up front)
+    for (int i = 0; i < WK_SA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, 3); }
+    for (int i = 0; i < WK_SB; ++i) { mbar_init(fullB + i, 1); mbar_init(emptyB + i, 3); }
+    mbar_init(accFull, 3);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -717,6 +724,7 @@ wgrad_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) DBG_STAMP(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -737,46 +745,54 @@ wgrad_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_con
         for (int k2 = 0; k2 < 3; ++k2)
           tma_load_5d(&map_dy, fullB + sb, sB + (size_t)sb * WK_BSTAGE + (size_t)k2 * WG_BTILE_BYTES, 0, x0 - k2 + 1, y0, zo, b);
       }
+      DBG_STAMP(2);
     }
-  } else if (warp == 1) {
+  } else if (warp <= 3) {
+    // ================================ MMA issuer for d0 tap k0 = warp - 1 (accumulator k0) ================================
+    const int k0 = warp - 1;
     const uint32_t idesc = make_idesc_tf32(WK_N) | (1u << 15) | (1u << 16);
     const uint32_t a_base = desc_lo(smem_u32(sA), 1024), b_base = desc_lo(smem_u32(sB), WG_BTILE_BYTES);
-    uint32_t started = 0;
-    int waited_a = pmin - 1;                    // highest X plane whose slab has been waited for
+    const uint32_t dcol = tmem_base + (uint32_t)(k0 * WK_N);
+    // X plane read at output plane zo: p = zo + k0 - 1.  Loaded planes this warp never reads (p < zs + k0 - 1): arrive now.
+    if (lane == 0)
+      for (int p = pmin; p < min(zs + k0 - 1, pmax + 1); ++p) mbar_arrive(emptyA + ((p - pmin) % WK_SA));
+    __syncwarp();
+    uint32_t acc = 0;
+    long long wait_a = 0, wait_b = 0;
+    if (warp == 1 && lane == 0) DBG_STAMP(3);
+    int sb = 0, pb = 0;
+    int ia = zs + k0 - 1 - pmin;                       // slab index (relative to pmin) of plane p; may start at -1
+    int sa = ia < 0 ? 0 : ia % WK_SA, pa = ia < 0 ? 0 : (ia / WK_SA) & 1;
     for (int zo = zs; zo < ze; ++zo) {
-      const int j = zo - zs, sb = j % WK_SB;
-      mbar_wait(fullB + sb, (j / WK_SB) & 1);
-      const int need = min(zo + 1, pmax);
-      for (; waited_a < need; ++waited_a) {
-        const int i = waited_a + 1 - pmin;
-        mbar_wait(fullA + (i % WK_SA), (i / WK_SA) & 1);
-      }
-      tc_fence_after();
-      const uint32_t blo = b_base + (uint32_t)sb * (WK_BSTAGE >> 4);
-      if (elect_one()) {
-#pragma unroll
-        for (int k0 = 0; k0 < 3; ++k0) {
-          const int p = zo + k0 - 1;
-          if (p < 0 || p >= G.D0) continue;
-          const uint32_t alo = a_base + (uint32_t)((p - pmin) % WK_SA) * (SLAB_BYTES >> 4);
-          umma_chain_mn16(tmem_base + (uint32_t)(k0 * WK_N), alo, blo, DESC_HI_MN_SW128_32B, idesc, (started >> k0) & 1u);
+      const int p = zo + k0 - 1;
+      { const long long w0 = dbg ? clock64() : 0; mbar_wait(fullB + sb, pb); if (dbg) wait_b += clock64() - w0; }
+      const bool use = p >= 0 && p < G.D0;             // warp-uniform
+      if (use) {
+        { const long long w0 = dbg ? clock64() : 0; mbar_wait(fullA + sa, pa); if (dbg) wait_a += clock64() - w0; }
+        if (elect_one()) {
+          umma_chain_mn16(dcol, a_base + (uint32_t)sa * (SLAB_BYTES >> 4), b_base + (uint32_t)sb * (WK_BSTAGE >> 4),
+                          DESC_HI_MN_SW128_32B, idesc, acc);
+          umma_commit(emptyB + sb);
+          umma_commit(emptyA + sa);                    // this warp is done with plane p once the chain has completed
         }
-        umma_commit(emptyB + sb);
-        if (zo - 1 >= pmin) umma_commit(emptyA + ((zo - 1 - pmin) % WK_SA));     // X plane zo-1: last use was this step
+        __syncwarp();
+        acc = 1u;
+        if (++sa == WK_SA) { sa = 0; pa ^= 1; }
+      } else {
+        if (lane == 0) mbar_arrive(emptyB + sb);
+        __syncwarp();
+        if (p >= 0 && ++sa == WK_SA) { sa = 0; pa ^= 1; }
       }
-      __syncwarp();
-#pragma unroll
-      for (int k0 = 0; k0 < 3; ++k0) {
-        const int p = zo + k0 - 1;
-        if (p >= 0 && p < G.D0) started |= 1u << k0;
-      }
+      if (++sb == WK_SB) { sb = 0; pb ^= 1; }
     }
     if (elect_one()) umma_commit(accFull);
     __syncwarp();
+    if (lane == 0 && dbg) { if (warp == 1) { DBG_STAMP(4); dbg[9] = wait_a; dbg[10] = wait_b; } }
   } else {
     const int q = warp & 3;                       // rows 32q..32q+31 <-> d1 tap k1 = q (q == 3: unused atom)
     mbar_wait(accFull, 0);
     tc_fence_after();
+    if (warp == 4 && lane == 0) DBG_STAMP(5);
     uint32_t started = 0;
     for (int k0 = 0; k0 < 3; ++k0)
       for (int zo = zs; zo < ze; ++zo) {
@@ -800,10 +816,80 @@ wgrad_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_con
         }
       }
     }
+    if (warp == 4 && lane == 0) DBG_STAMP(6);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (threadIdx.x == 0) DBG_STAMP(7);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// descriptor probe: one CTA, operands A and B are [rows][32] fp32 matrices TMA-loaded whole (128 B rows, swizzled by
+// the TMA unit), then `nk` MMAs with fully caller-specified shared-memory descriptors.  Used to establish which
+// (unaligned start, base offset, LBO/SBO) combinations the tensor core reads consistently with the TMA swizzle, e.g.
+// row-shifted views of one tile.  d[128][N] receives the accumulator.
+// ---------------------------------------------------------------------------------------------------------
+struct ProbeArgs {
+  int rows_a, rows_b, N, mn_major, nk;
+  uint32_t a_off, a_lbo, a_sbo, a_bo, a_step, b_off, b_lbo, b_sbo, b_bo, b_step, layout;
+};
+
+__global__ void __launch_bounds__(128, 1)
+desc_probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  float* __restrict__ d, const ProbeArgs P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 256 * 128;
+  uint64_t* bars = (uint64_t*)(sB + 256 * 128);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bars, 1); mbar_init(bars + 1, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bars, (uint32_t)(P.rows_a + P.rows_b) * 128u);
+    tma_load_2d(&map_a, bars, sA, 0, 0);
+    tma_load_2d(&map_b, bars, sB, 0, 0);
+  }
+  mbar_wait(bars, 0);
+  tc_fence_after();
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t idesc = make_idesc_tf32(P.N);
+      if (P.mn_major) idesc |= (1u << 15) | (1u << 16);
+      const uint32_t hi_a = (P.a_sbo >> 4) | (1u << 14) | (P.a_bo << 17) | (P.layout << 29);
+      const uint32_t hi_b = (P.b_sbo >> 4) | (1u << 14) | (P.b_bo << 17) | (P.layout << 29);
+      for (int k = 0; k < P.nk; ++k) {
+        const uint64_t da = ((uint64_t)hi_a << 32) | desc_lo(smem_u32(sA) + P.a_off + k * P.a_step, P.a_lbo);
+        const uint64_t db = ((uint64_t)hi_b << 32) | desc_lo(smem_u32(sB) + P.b_off + k * P.b_step, P.b_lbo);
+        umma_tf32(tmem_base, da, db, idesc, k > 0 ? 1u : 0u);
+      }
+      umma_commit(bars + 1);
+    }
+    __syncwarp();
+  }
+  mbar_wait(bars + 1, 0);
+  tc_fence_after();
+  const int r = warp * 32 + lane;
+  for (int cb = 0; cb < P.N; cb += 16) {
+    uint32_t v[16];
+    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 16; ++e) d[(size_t)r * P.N + cb + e] = __uint_as_float(v[e]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -818,10 +904,11 @@ mma_microbench_kernel(float* __restrict__ out, int N, int nacc, int chain, int i
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
   __shared__ uint64_t bar2;
+  __shared__ uint64_t bar3;
   __shared__ uint32_t tslot;
   const int warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < (190 * 1024) / 4; i += blockDim.x) ((float*)smem)[i] = 1.0f + (float)(i & 255) * 0.001f;
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1); fence_barrier_init(); fence_proxy_async(); }
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1); mbar_init(&bar3, 1); fence_barrier_init(); fence_proxy_async(); }
   if (warp == 1) tmem_alloc(&tslot, 512);
   tc_fence_before();
   __syncthreads();
@@ -833,6 +920,32 @@ mma_microbench_kernel(float* __restrict__ out, int N, int nacc, int chain, int i
     const uint32_t alo = desc_lo(smem_u32(smem), kmajor ? 16 : 1024);
     const uint32_t blo = desc_lo(smem_u32(smem + 150 * 1024), kmajor ? 16 : 16384);
     long long t0 = 0, t1 = 0;
+    if (kmajor >= 2) {
+      // asm-chained issue exactly as the kernels do it: 2 = MN-major chains of 16 (+1024 B per K-step, A atoms 1024 B
+      // apart, B atoms 16 KB apart), 3 = K-major chains of 4 (+32 B per K-step)
+      const uint32_t idesc2 = make_idesc_tf32(N) | (kmajor == 2 ? ((1u << 15) | (1u << 16)) : 0u);
+      const uint32_t a2 = desc_lo(smem_u32(smem), kmajor == 2 ? 1024 : 16);
+      // mode 2 re-uses the scalar arguments: chain = B base (KB), commit_every = number of A slabs cycled through,
+      // nacc = accumulators, cycle_addr = parked warps; B alternates between two 48 KB stages like the k2n kernel
+      const uint32_t b_kb = kmajor == 2 ? (uint32_t)chain : 72u;
+      const int nslab = kmajor == 2 ? (commit_every > 0 ? commit_every : 3) : 3;
+      const uint32_t b2 = desc_lo(smem_u32(smem + b_kb * 1024), kmajor == 2 ? 16384 : 16);
+      if (elect_one()) {
+        t0 = clock64();
+        int acc = 0, slab = 0, plane = 0;
+        for (int i = 0; i < iters; i += (kmajor == 2 ? 16 : 4)) {
+          if (kmajor == 2) {
+            umma_chain_mn16(tb + (uint32_t)(acc * N), a2 + (uint32_t)slab * (SLAB_BYTES >> 4),
+                            b2 + (uint32_t)(plane & 1) * (49152u >> 4), DESC_HI_MN_SW128_32B, idesc2, 1u);
+            if (++slab == nslab) slab = 0;
+          } else {
+            umma_chain_k<4>(tb + (uint32_t)(acc * N), a2 + (uint32_t)((i >> 2) % 3) * 64, b2, DESC_HI_K_SW128, idesc2, 1u);
+          }
+          if (++acc == nacc) { acc = 0; ++plane; }
+        }
+        umma_commit(&bar);
+      }
+    } else
     if (elect_one()) {
       t0 = clock64();
       int acc = 0, c = 0;
@@ -853,6 +966,9 @@ mma_microbench_kernel(float* __restrict__ out, int N, int nacc, int chain, int i
     t1 = clock64();
     const long long tt = __shfl_sync(0xffffffffu, t0, 0) ;
     if (threadIdx.x == 0) out[blockIdx.x] = (float)(t1 - (t0 ? t0 : tt)) / (float)iters;
+  }
+  else if (kmajor >= 2 && warp <= cycle_addr) {
+    mbar_wait(&bar, 0);        // asm modes: `cycle_addr` extra warps park on the barrier like the kernels' epilogue warps do
   }
   tc_fence_before();
   __syncthreads();
@@ -1050,7 +1166,7 @@ int ssr_conv3d_fwd_tc(const float* x1, int C1, const float* x2, int C2, const fl
     SSR_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const unsigned grid = (unsigned)(ntiles < num_sms ? ntiles : num_sms);       // persistent: one CTA per SM
-  conv3d_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(m1, m2, mw, bias, y, G);
+  conv3d_tc_kernel<<<grid, 32 * (5 + G.TZ), smem, (cudaStream_t)stream>>>(m1, m2, mw, bias, y, G);   // TMA + TZ MMA + 4 epilogue warps
   SSR_COUNT_LAUNCH();
   SSR_CHECK_LAUNCH();
   return SSR_OK;
@@ -1108,7 +1224,7 @@ int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const 
   const long long nblk = base_units * G.n0splits;
   SSR_CHECK_ARG(nblk < (1LL << 31), "grid too large");
   cudaStream_t st = (cudaStream_t)stream;
-  if (k2n) wgrad_tc_k2n_kernel<<<(unsigned)nblk, 192, smem, st>>>(m1, m2, my, dw, G);
+  if (k2n) wgrad_tc_k2n_kernel<<<(unsigned)nblk, WK_THREADS, smem, st>>>(m1, m2, my, dw, G);
   else wgrad_tc_kernel<<<(unsigned)nblk, 192, smem, st>>>(m1, m2, my, dw, G);
   SSR_COUNT_LAUNCH();
   SSR_CHECK_LAUNCH();
@@ -1126,7 +1242,7 @@ int ssr_tc_microbench(float* out, int nblocks, int N, int nacc, int chain, int i
   SSR_CHECK_ARG(out && nblocks > 0 && N % 16 == 0 && N >= 16 && N <= 256 && nacc >= 1 && nacc * N <= 512 && chain >= 1 &&
                 iters > 0, "microbench args");
   SSR_CHECK_CUDA(cudaFuncSetAttribute(mma_microbench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  SSR_CHECK_ARG(!cycle_addr || N <= 32, "address cycling needs 9*N*128 B of B tiles");
+  SSR_CHECK_ARG(!cycle_addr || N <= 32 || kmajor >= 2, "address cycling needs 9*N*128 B of B tiles");
   mma_microbench_kernel<<<nblocks, 128, 200 * 1024, (cudaStream_t)stream>>>(out, N, nacc, chain, iters, kmajor, commit_every,
                                                                               cycle_addr);
   SSR_COUNT_LAUNCH();
@@ -1135,6 +1251,38 @@ int ssr_tc_microbench(float* out, int nblocks, int N, int nacc, int chain, int i
 }
 
 // profiling aid: phase timestamps of sampled CTAs of conv3d_tc_kernel are written to `buf` (>= 128*16 int64), NULL disables
+// see desc_probe_kernel.  swz: 0 = SWIZZLE_128B, 1 = SWIZZLE_128B_ATOM_32B.  p = 16 ints: N, mn_major, nk, layout,
+// a_off, a_lbo, a_sbo, a_bo, a_step, b_off, b_lbo, b_sbo, b_bo, b_step (HOST array).
+int ssr_tc_desc_probe(const float* a, int rows_a, const float* b, int rows_b, float* d, int swz, const int* p,
+                      void* stream) {
+  SSR_CHECK_ARG(a && b && d && p && rows_a > 0 && rows_a <= 256 && rows_b > 0 && rows_b <= 256, "probe arguments");
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { ssr_set_error("cuTensorMapEncodeTiled not available"); return SSR_ERR_CUDA; }
+  CUtensorMap ma, mb;
+  const CUtensorMapSwizzle sw = swz ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  for (int i = 0; i < 2; ++i) {
+    cuuint64_t dims[2] = {32, (cuuint64_t)(i ? rows_b : rows_a)};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {32, (cuuint32_t)(i ? rows_b : rows_a)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(i ? &mb : &ma, tma_dtype(), 2, (void*)(i ? b : a), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ssr_set_error("cuTensorMapEncodeTiled(probe) failed: %d", (int)r); return SSR_ERR_CUDA; }
+  }
+  ProbeArgs P;
+  P.rows_a = rows_a; P.rows_b = rows_b; P.N = p[0]; P.mn_major = p[1]; P.nk = p[2]; P.layout = (uint32_t)p[3];
+  P.a_off = p[4]; P.a_lbo = p[5]; P.a_sbo = p[6]; P.a_bo = p[7]; P.a_step = p[8];
+  P.b_off = p[9]; P.b_lbo = p[10]; P.b_sbo = p[11]; P.b_bo = p[12]; P.b_step = p[13];
+  SSR_CHECK_ARG(P.N >= 16 && P.N <= 256 && P.N % 16 == 0 && P.nk >= 1, "probe N/nk");
+  const size_t smem = 1024 + 2 * 256 * 128 + 64;
+  SSR_CHECK_CUDA(cudaFuncSetAttribute(desc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  desc_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(ma, mb, d, P);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
 int ssr_tc_set_debug(long long* buf) {
   SSR_CHECK_CUDA(cudaMemcpyToSymbol(g_dbg, &buf, sizeof(buf)));
   return SSR_OK;
