@@ -149,6 +149,11 @@ __device__ __forceinline__ void umma_tf32_lh(uint32_t d_tmem, uint32_t alo, uint
       : "memory");
 }
 
+__device__ __forceinline__ void umma_tf32_lh2(uint32_t d_tmem, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+  umma_tf32_lh(d_tmem, alo, blo, hi, idesc, accumulate);
+}
+
 // NK back-to-back MMAs into one accumulator, both descriptors advancing by `STEP` (in 16-byte units) per MMA, emitted
 // as ONE asm block: the issuing warp is alone on its instruction stream, so every extra (dependent, uniform-datapath)
 // instruction between two UTCHMMAs costs ~10 cycles; a tight chain sustains the tensor-core rate
@@ -173,6 +178,24 @@ __device__ __forceinline__ void umma_chain_mn16(uint32_t d_tmem, uint32_t alo, u
   asm volatile(SSR_MMA_HEAD SSR_MMA1 SSR_MMAN(64) SSR_MMAN(64) SSR_MMAN(64) SSR_MMAN(64) SSR_MMAN(64) SSR_MMAN(64)
                SSR_MMAN(64) SSR_MMAN(64) SSR_MMAN(64) SSR_MMAN(64) SSR_MMAN(64) SSR_MMAN(64) SSR_MMAN(64) SSR_MMAN(64)
                SSR_MMAN(64) "}" SSR_MMA_ARGS);
+}
+
+// weight-gradient chain with the dY tile stored as rows of 10 voxels (+1280 B per K-step) and X as rows of 8 (+1024 B)
+#define SSR_MMAN2(SA_, SB_) "add.s64 da, da, " #SA_ ";\n\tadd.s64 db, db, " #SB_ ";\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, q;\n\t"
+__device__ __forceinline__ void umma_chain_mn16_ab(uint32_t d_tmem, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(SSR_MMA_HEAD SSR_MMA1 SSR_MMAN2(64, 80) SSR_MMAN2(64, 80) SSR_MMAN2(64, 80) SSR_MMAN2(64, 80)
+               SSR_MMAN2(64, 80) SSR_MMAN2(64, 80) SSR_MMAN2(64, 80) SSR_MMAN2(64, 80) SSR_MMAN2(64, 80)
+               SSR_MMAN2(64, 80) SSR_MMAN2(64, 80) SSR_MMAN2(64, 80) SSR_MMAN2(64, 80) SSR_MMAN2(64, 80)
+               SSR_MMAN2(64, 80) "}" SSR_MMA_ARGS);
+}
+// same, `n` (< 16) K-steps: tiles that stick out of the volume along d1 skip their all-zero rows
+__device__ __forceinline__ void umma_chain_mn_ab(int n, uint32_t d_tmem, uint32_t alo, uint32_t blo, uint32_t hi,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  for (int i = 0; i < n; ++i) {
+    umma_tf32_lh2(d_tmem, alo, blo, hi, idesc, accumulate);
+    accumulate = 1u; alo += 64u; blo += 80u;
+  }
 }
 
 // instruction descriptor: D=F32, A=B=TF32, both K-major, M=128, N
@@ -675,8 +698,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
 // The CTA walks the dY planes of its range; X slabs live in a rolling ring (planes zo-1, zo, zo+1 + one prefetched),
 // dY stages are double buffered: nothing the MMA warp needs is ever loaded late.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int WK_SA = 5, WK_SB = 2, WK_N = 96;
-constexpr int WK_BSTAGE = 3 * WG_BTILE_BYTES;            // 49152
+constexpr int WK_SA = 5, WK_SB = 4, WK_N = 96;
+constexpr int WK_BROWS = (TM2 + 2) * TM1;                // dY tile with a one-voxel d2 halo: 16 rows of 10 voxels
+constexpr int WK_BSTAGE = WK_BROWS * 128;                // 20480 (multiple of 1024)
 constexpr int WK_THREADS = 256;                          // warp 0 TMA, warps 1-3 MMA (one per d0 tap), warps 4-7 epilogue
 
 // The thread that issues tcgen05.mma is stalled while the tensor pipe is busy (the MMA queue is shallow), so all the
@@ -705,9 +729,11 @@ wgrad_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_con
   const int zs_i = t % G.n0splits; t /= G.n0splits;
   const int t2 = t % G.n2tiles; t /= G.n2tiles;
   const int t1 = t % G.n1tiles; t /= G.n1tiles;
-  const int b = t % G.B;
-  const int ch = t / G.B;
-  const int x0 = t2 * TM2, y0 = t1 * TM1;
+  const int b = t % G.B; t /= G.B;
+  const int nt = t % G.nNtiles;
+  const int ch = t / G.nNtiles;
+  const int x0 = t2 * TM2, y0 = t1 * TM1, n0 = nt * 32;
+  const int nrows = min(TM1, G.D1 - y0);          // d1 rows of the tile inside the volume = K-steps that carry data
   const int zs = zs_i * G.zlen, ze = min(G.D0, zs + G.zlen);
   const int pmin = max(zs - 1, 0), pmax = min(ze, G.D0 - 1);      // X planes used: [pmin, pmax]
 
@@ -742,8 +768,7 @@ wgrad_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_con
         const int j = zo - zs, sb = j % WK_SB;
         mbar_wait(emptyB + sb, ((j / WK_SB) & 1) ^ 1);
         mbar_expect_tx(fullB + sb, WK_BSTAGE);
-        for (int k2 = 0; k2 < 3; ++k2)
-          tma_load_5d(&map_dy, fullB + sb, sB + (size_t)sb * WK_BSTAGE + (size_t)k2 * WG_BTILE_BYTES, 0, x0 - k2 + 1, y0, zo, b);
+        tma_load_5d(&map_dy, fullB + sb, sB + (size_t)sb * WK_BSTAGE, n0, x0 - 1, y0, zo, b);
       }
       DBG_STAMP(2);
     }
@@ -751,7 +776,10 @@ wgrad_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_con
     // ================================ MMA issuer for d0 tap k0 = warp - 1 (accumulator k0) ================================
     const int k0 = warp - 1;
     const uint32_t idesc = make_idesc_tf32(WK_N) | (1u << 15) | (1u << 16);
-    const uint32_t a_base = desc_lo(smem_u32(sA), 1024), b_base = desc_lo(smem_u32(sB), WG_BTILE_BYTES);
+    // B: ONE dY tile with a d2 halo; the three N atoms are the same rows shifted by one voxel (LBO = 128 B): atom j
+    // starts at voxel x0 - 1 + j = the d2 tap k2 = 2 - j.  Unaligned / overlapping operand views are read consistently
+    // with the TMA swizzle (profiles/r01_desc_probe_unaligned_views.txt).
+    const uint32_t a_base = desc_lo(smem_u32(sA), 1024), b_base = desc_lo(smem_u32(sB), 128);
     const uint32_t dcol = tmem_base + (uint32_t)(k0 * WK_N);
     // X plane read at output plane zo: p = zo + k0 - 1.  Loaded planes this warp never reads (p < zs + k0 - 1): arrive now.
     if (lane == 0)
@@ -770,8 +798,9 @@ wgrad_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_con
       if (use) {
         { const long long w0 = dbg ? clock64() : 0; mbar_wait(fullA + sa, pa); if (dbg) wait_a += clock64() - w0; }
         if (elect_one()) {
-          umma_chain_mn16(dcol, a_base + (uint32_t)sa * (SLAB_BYTES >> 4), b_base + (uint32_t)sb * (WK_BSTAGE >> 4),
-                          DESC_HI_MN_SW128_32B, idesc, acc);
+          const uint32_t alo = a_base + (uint32_t)sa * (SLAB_BYTES >> 4), blo = b_base + (uint32_t)sb * (WK_BSTAGE >> 4);
+          if (nrows == TM1) umma_chain_mn16_ab(dcol, alo, blo, DESC_HI_MN_SW128_32B, idesc, acc);
+          else umma_chain_mn_ab(nrows, dcol, alo, blo, DESC_HI_MN_SW128_32B, idesc, acc);
           umma_commit(emptyB + sb);
           umma_commit(emptyA + sa);                    // this warp is done with plane p once the chain has completed
         }
@@ -807,7 +836,7 @@ wgrad_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_con
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(k0 * WK_N + cb), v);
         tmem_ld_wait();
-        const int k2 = cb >> 5, cobase = cb & 31;  // column = k2 * 32 + co
+        const int k2 = 2 - (cb >> 5), cobase = n0 + (cb & 31);  // column = (2 - k2) * 32 + co
         if (q < 3 && lane < valid) {
           float* o = dw + ((long long)(((k0 * 3 + q) * 3 + k2)) * G.Cin + cin_idx) * G.Cout + cobase;
 #pragma unroll
@@ -1041,13 +1070,13 @@ CUtensorMapDataType tma_dtype() {
 }
 
 int make_map_act(CUtensorMap* m, const float* ptr, int C, int B, int D0, int D1, int D2, int box_d1 = TM1 + 2,
-                 CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                 CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, int box_d2 = TM2) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { ssr_set_error("cuTensorMapEncodeTiled not available"); return SSR_ERR_CUDA; }
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)D2, (cuuint64_t)D1, (cuuint64_t)D0, (cuuint64_t)B};
   cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)D2 * C * 4, (cuuint64_t)D1 * D2 * C * 4,
                            (cuuint64_t)D0 * D1 * D2 * C * 4};
-  cuuint32_t box[5] = {32, TM2, (cuuint32_t)box_d1, 1, 1};
+  cuuint32_t box[5] = {32, (cuuint32_t)box_d2, (cuuint32_t)box_d1, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, tma_dtype(), 5, (void*)ptr, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1202,8 +1231,9 @@ int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const 
   for (int c = 0; c < C2; c += 32) { SSR_CHECK_ARG(nch < MAX_CHUNKS, "too many channels"); G.chunk_src[nch] = 1; G.chunk_c0[nch] = (short)c; G.chunk_valid[nch] = (unsigned char)(C2 - c < 32 ? C2 - c : 32); ++nch; }
   G.nchunks = nch; G.C1 = C1;
   G.n2tiles = (D2 + TM2 - 1) / TM2; G.n1tiles = (D1 + TM1 - 1) / TM1;
-  const bool k2n = Npad == 32 && !getenv("SSR_WGRAD_NO_K2N");    // Cout <= 32: d2 taps in the MMA N dimension
-  const long long base_units = k2n ? (long long)nch * G.n1tiles * G.n2tiles * B
+  const bool k2n = !getenv("SSR_WGRAD_NO_K2N");    // d2 taps in the MMA N dimension, 32 output channels per CTA
+  if (k2n) G.nNtiles = Npad / 32;
+  const long long base_units = k2n ? (long long)nch * G.nNtiles * G.n1tiles * G.n2tiles * B
                                    : (long long)nch * 3 * (3 / G.KG) * G.nNtiles * G.n1tiles * G.n2tiles * B;
   // enough CTAs for >= ~8 waves of 148 (tail-wave loss < ~6 %), but at least 8 planes per CTA (halo planes are re-read)
   int S = (int)((8 * 148 + base_units - 1) / base_units); if (S < 1) S = 1; if (S > (D0 + 7) / 8) S = (D0 + 7) / 8; if (S < 1) S = 1;
@@ -1214,7 +1244,7 @@ int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const 
   const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;     // MN-major tf32 operands (UMMA 128B_BASE32B)
   int rc = make_map_act(&m1, x1, C1, B, D0, D1, D2, TM1 + 2, swz); if (rc) return rc;
   if (C2 > 0) { rc = make_map_act(&m2, x2, C2, B, D0, D1, D2, TM1 + 2, swz); if (rc) return rc; } else m2 = m1;
-  rc = make_map_act(&my, dy, Cout, B, D0, D1, D2, TM1, swz); if (rc) return rc;
+  rc = make_map_act(&my, dy, Cout, B, D0, D1, D2, TM1, swz, k2n ? TM2 + 2 : TM2); if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     SSR_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
