@@ -119,6 +119,7 @@ conv3d_first_kernel(const float* __restrict__ x, const float* __restrict__ w, co
   __shared__ float sx[(FT0 + 2) * (FT1 + 2) * (FT2 + 2) * CIN];
   __shared__ __align__(16) float sw[27 * CIN * COUT];
   __shared__ float sb[COUT];
+  __shared__ __align__(16) float sst[FT1 * FT2 * COUT];   // output staging for one plane
   const int nb2 = (d2 + FT2 - 1) / FT2, nb1 = (d1 + FT1 - 1) / FT1, nb0 = (d0 + FT0 - 1) / FT0;
   long long blk = blockIdx.x;
   const int b2 = (int)(blk % nb2); blk /= nb2;
@@ -140,10 +141,9 @@ conv3d_first_kernel(const float* __restrict__ x, const float* __restrict__ w, co
   __syncthreads();
   const int t2 = threadIdx.x % FT2, t1 = threadIdx.x / FT2;
   const int i1 = b1 * FT1 + t1, i2 = b2 * FT2 + t2;
-  if (i1 >= d1 || i2 >= d2) return;
   for (int a0 = 0; a0 < FT0; ++a0) {
     const int i0 = b0 * FT0 + a0;
-    if (i0 >= d0) break;
+    if (i0 >= d0) break;                                   // block-uniform
     float acc[COUT];
 #pragma unroll
     for (int co = 0; co < COUT; ++co) acc[co] = sb[co];
@@ -166,15 +166,27 @@ conv3d_first_kernel(const float* __restrict__ x, const float* __restrict__ w, co
             }
           }
         }
-    float* o = y + ((((long long)b * d0 + i0) * d1 + i1) * d2 + i2) * COUT;
+    // stage the plane's 256 x COUT outputs in shared memory and write them as fully coalesced float4 rows (a
+    // thread-per-voxel store pattern touches every 32-byte sector in six separate instructions)
+    __syncthreads();                                       // previous plane's copy-out has finished reading sst
 #pragma unroll
     for (int q = 0; q < COUT / 4; ++q) {
       float4 v = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
       if (act) { v.x = elu_f(v.x); v.y = elu_f(v.y); v.z = elu_f(v.z); v.w = elu_f(v.w); }
-      reinterpret_cast<float4*>(o)[q] = v;
+      reinterpret_cast<float4*>(sst + threadIdx.x * COUT)[q] = v;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < FT1 * FT2 * (COUT / 4); e += 256) {
+      const int vox = e / (COUT / 4), part = e % (COUT / 4);
+      const int j1 = b1 * FT1 + (vox >> 5), j2 = b2 * FT2 + (vox & 31);
+      if (j1 < d1 && j2 < d2)
+        reinterpret_cast<float4*>(y + ((((long long)b * d0 + i0) * d1 + j1) * d2 + j2) * COUT)[part] =
+            reinterpret_cast<const float4*>(sst)[e];
     }
   }
+  (void)i1; (void)i2;
 }
+
 
 // weights for the data-gradient expressed as a forward convolution of dy:
 //   wd[tap'][co][ci] = w[K-1-tap'][ci][co]   (flip all three axes, swap channel roles)
@@ -284,6 +296,92 @@ wgrad_small_cin_kernel(const float* __restrict__ x, const float* __restrict__ dy
     float* o = dw + (long long)r * G.Cout + cg * 4;     // dw layout (tap, ci, co): row r = tap*Cin + ci
     atomicAdd(o + 0, acc.x); atomicAdd(o + 1, acc.y); atomicAdd(o + 2, acc.z); atomicAdd(o + 3, acc.w);
   }
+}
+
+// First-layer weight gradient (Cin <= 2, Cout = 24): register-tiled.  A thread owns the (k0, k1) tap pair, an
+// 8-channel group of dy and all three k2 taps (24 * CIN accumulators); nine such thread sets stride over the voxels of a
+// plane held in shared memory (x halo tile + dy plane), so every dy value is loaded from shared memory once per
+// 27 threads and feeds 24 FMAs.  Persistent blocks: one atomic flush per block.
+template <int CIN>
+__global__ void __launch_bounds__(256)
+wgrad_first_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, int B, int d0,
+                   int d1, int d2) {
+  constexpr int COUT = 24, T1 = FT1 + 2, T2 = FT2 + 2;
+  __shared__ float sx[(FT0 + 2) * T1 * T2 * CIN];
+  __shared__ __align__(16) float sdy[FT1 * FT2 * COUT];
+  __shared__ float sacc[27 * CIN * COUT];
+  const int tid = threadIdx.x;
+  for (int e = tid; e < 27 * CIN * COUT; e += 256) sacc[e] = 0.f;
+  const int owner = tid % 27, stream = tid / 27;          // stream 9 (threads 243..255) only helps with the loads
+  const int k01 = owner / 3, cg = owner % 3, k0 = k01 / 3, k1 = k01 % 3;
+  float acc[CIN][3][8];
+#pragma unroll
+  for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[ci][c][j] = 0.f;
+  const int nb2 = (d2 + FT2 - 1) / FT2, nb1 = (d1 + FT1 - 1) / FT1, nb0 = (d0 + FT0 - 1) / FT0;
+  const long long ntiles = (long long)B * nb0 * nb1 * nb2;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    long long blk = tile;
+    const int b2 = (int)(blk % nb2); blk /= nb2;
+    const int b1 = (int)(blk % nb1); blk /= nb1;
+    const int b0 = (int)(blk % nb0);
+    const int b = (int)(blk / nb0);
+    const int o0 = b0 * FT0 - 1, o1 = b1 * FT1 - 1, o2 = b2 * FT2 - 1;
+    __syncthreads();                                      // previous tile's readers are done with sx / sdy
+    for (int e = tid; e < (FT0 + 2) * T1 * T2; e += 256) {
+      const int c = e % T2, bb = (e / T2) % T1, a = e / (T2 * T1);
+      const int i = o0 + a, j = o1 + bb, k = o2 + c;
+      const bool ok = i >= 0 && i < d0 && j >= 0 && j < d1 && k >= 0 && k < d2;
+      const long long src = ((((long long)b * d0 + i) * d1 + j) * d2 + k) * CIN;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) sx[e * CIN + ci] = ok ? x[src + ci] : 0.f;
+    }
+    for (int a0 = 0; a0 < FT0; ++a0) {
+      const int i0 = b0 * FT0 + a0;
+      if (i0 >= d0) break;                                // block-uniform
+      __syncthreads();                                    // sx visible / previous plane's readers done with sdy
+      for (int e = tid; e < FT1 * FT2 * (COUT / 4); e += 256) {
+        const int vox = e / (COUT / 4), part = e % (COUT / 4);
+        const int i1 = b1 * FT1 + (vox >> 5), i2 = b2 * FT2 + (vox & 31);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i1 < d1 && i2 < d2)
+          v = reinterpret_cast<const float4*>(dy + ((((long long)b * d0 + i0) * d1 + i1) * d2 + i2) * COUT)[part];
+        reinterpret_cast<float4*>(sdy)[e] = v;
+      }
+      __syncthreads();
+      if (stream < 9) {
+        for (int vi = stream; vi < FT1 * FT2; vi += 9) {
+          const int t1 = vi >> 5, t2 = vi & 31;
+          const float4 da = reinterpret_cast<const float4*>(sdy + vi * COUT + cg * 8)[0];
+          const float4 db = reinterpret_cast<const float4*>(sdy + vi * COUT + cg * 8)[1];
+          const float* px = sx + (((a0 + k0) * T1 + (t1 + k1)) * T2 + t2) * CIN;
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float xv = px[c * CIN + ci];
+              acc[ci][c][0] += xv * da.x; acc[ci][c][1] += xv * da.y; acc[ci][c][2] += xv * da.z; acc[ci][c][3] += xv * da.w;
+              acc[ci][c][4] += xv * db.x; acc[ci][c][5] += xv * db.y; acc[ci][c][6] += xv * db.z; acc[ci][c][7] += xv * db.w;
+            }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (stream < 9) {
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)     // dw layout (tap, ci, co), tap = (k0 * 3 + k1) * 3 + k2
+          atomicAdd(&sacc[(((k0 * 3 + k1) * 3 + c) * CIN + ci) * COUT + cg * 8 + j], acc[ci][c][j]);
+  }
+  __syncthreads();
+  for (int e = tid; e < 27 * CIN * COUT; e += 256) atomicAdd(dw + e, sacc[e]);
 }
 
 // per-channel sum over voxels of t[v][C] (bias gradients): out[c] += sum_v t[v][c]
@@ -722,6 +820,132 @@ head_loss_kernel(const float* __restrict__ feat, const float* __restrict__ w, co
   }
 }
 
+// Fused, coalesced version of head_loss_kernel + head_gout_kernel + head_wgrad_kernel for C % 4 == 0, C <= 128:
+// a group of GS lanes (GS = power of two >= C/4) owns one voxel, lane q holds the float4 of channels 4q..4q+3, the
+// 1x1x1 convolution is a shuffle reduction inside the group, dfeat is written as float4 and the head weight gradient
+// feat^T * g is accumulated in registers (one block-level reduction at the end).  feat is read once, dfeat written once.
+template <int GS>
+__global__ void __launch_bounds__(256)
+head_loss_vec_kernel(const float* __restrict__ feat, const float* __restrict__ w, const float* __restrict__ bias,
+                     const float* __restrict__ image, const float* __restrict__ target, float* __restrict__ pred,
+                     float* __restrict__ dfeat, float* __restrict__ dw, float* __restrict__ db,
+                     double* __restrict__ loss, HeadParams P) {
+  __shared__ float sw[4 * 128];
+  __shared__ float sdw[4 * 128];
+  __shared__ double sloss[8];
+  const int C = P.C, L = P.L, nq = C >> 2;
+  for (int e = threadIdx.x; e < C * L; e += blockDim.x) { sw[e] = w[e]; sdw[e] = 0.f; }   // w[c][l]
+  __syncthreads();
+  const int q = threadIdx.x % GS;
+  const bool active = q < nq;
+  float wq[4][4];                                // this lane's 4 channels x L outputs
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int l = 0; l < 4; ++l) wq[j][l] = (active && l < L) ? sw[(4 * q + j) * L + l] : 0.f;
+  float bl[4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) bl[l] = l < L ? bias[l] : 0.f;
+  float wacc[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int l = 0; l < 4; ++l) wacc[j][l] = 0.f;
+  const long long nvox = (long long)P.B * P.d0 * P.d1 * P.d2;
+  const int gpb = blockDim.x / GS;
+  double lloss = 0.0;
+  float ldb[4] = {0.f, 0.f, 0.f, 0.f};
+  // all lanes of a warp run the same number of iterations (shuffles below are full-warp)
+  const long long vstep = (long long)gridDim.x * gpb;
+  const long long niter = (nvox + vstep - 1) / vstep;
+  long long v = (long long)blockIdx.x * gpb + threadIdx.x / GS;
+  for (long long it = 0; it < niter; ++it, v += vstep) {
+    const bool vok = v < nvox;
+    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vok && active) f = *reinterpret_cast<const float4*>(feat + v * C + 4 * q);
+    float o[4];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) o[l] = f.x * wq[0][l] + f.y * wq[1][l] + f.z * wq[2][l] + f.w * wq[3][l];
+#pragma unroll
+    for (int off = GS / 2; off > 0; off >>= 1)
+#pragma unroll
+      for (int l = 0; l < 4; ++l)
+        if (l < L) o[l] += __shfl_xor_sync(0xffffffffu, o[l], off);
+    if (!vok) continue;
+    bool inside = true;
+    if (P.c0 > 0) {
+      long long r = v;
+      const int i2 = (int)(r % P.d2); r /= P.d2;
+      const int i1 = (int)(r % P.d1); r /= P.d1;
+      const int i0 = (int)(r % P.d0);
+      inside = i0 >= P.cb0 && i0 < P.cb0 + P.c0 && i1 >= P.cb1 && i1 < P.cb1 + P.c1 && i2 >= P.cb2 && i2 < P.cb2 + P.c2;
+    }
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      if (l >= L) break;
+      const float ol = o[l] + bl[l];
+      if (pred && q == 0) pred[v * L + l] = ol;
+      float pr = ol;
+      if (P.res_stride > 0) pr += image[v * P.res_stride + P.res_idx[l]];
+      const float err = pr - target[v * P.tgt_stride + l];
+      if (inside) {
+        if (P.metric == 1) {
+          if (q == 0) lloss += fabsf(err);
+          g[l] = (err > 0.f ? 1.f : (err < 0.f ? -1.f : 0.f)) * (float)P.inv_count;
+        } else {
+          if (q == 0) lloss += (double)err * err;
+          g[l] = 2.f * err * (float)P.inv_count;
+        }
+      }
+      if (q == 0) ldb[l] += g[l];
+    }
+    if (P.train && active) {
+      float4 d;
+      d.x = g[0] * wq[0][0] + g[1] * wq[0][1] + g[2] * wq[0][2] + g[3] * wq[0][3];
+      d.y = g[0] * wq[1][0] + g[1] * wq[1][1] + g[2] * wq[1][2] + g[3] * wq[1][3];
+      d.z = g[0] * wq[2][0] + g[1] * wq[2][1] + g[2] * wq[2][2] + g[3] * wq[2][3];
+      d.w = g[0] * wq[3][0] + g[1] * wq[3][1] + g[2] * wq[3][2] + g[3] * wq[3][3];
+      *reinterpret_cast<float4*>(dfeat + v * C + 4 * q) = d;
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        wacc[0][l] += f.x * g[l]; wacc[1][l] += f.y * g[l]; wacc[2][l] += f.z * g[l]; wacc[3][l] += f.w * g[l];
+      }
+    }
+  }
+  __syncwarp();
+  // head weight gradient: reduce over the groups of the warp, then over the warps through shared memory
+  if (P.train) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        if (l >= L) break;
+        float a = wacc[j][l];
+        for (int off = GS; off < 32; off <<= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        if ((threadIdx.x & 31) < GS && active) atomicAdd(&sdw[(4 * q + j) * L + l], a);
+      }
+  }
+  for (int o2 = 16; o2 > 0; o2 >>= 1) {
+    lloss += __shfl_xor_sync(0xffffffffu, lloss, o2);
+#pragma unroll
+    for (int l = 0; l < 4; ++l) ldb[l] += __shfl_xor_sync(0xffffffffu, ldb[l], o2);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sloss[threadIdx.x >> 5] = lloss;
+    if (P.train)
+      for (int l = 0; l < L; ++l) atomicAdd(db + l, ldb[l]);
+  }
+  __syncthreads();
+  if (P.train)
+    for (int e = threadIdx.x; e < C * L; e += blockDim.x) atomicAdd(dw + e, sdw[e]);
+  if (threadIdx.x == 0) {
+    double s2 = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s2 += sloss[i];
+    atomicAdd(loss, s2 * P.inv_count);
+  }
+}
+
 // dW_head[c][l] += sum_v feat[v][c] * g[v][l] where g is recomputed from dfeat is not possible -> separate pass
 // using the stored per-voxel output gradient gout[v][l].
 __global__ void head_wgrad_kernel(const float* __restrict__ feat, const float* __restrict__ gout, long long nvox, int C,
@@ -844,6 +1068,12 @@ int ssr_conv3d_wgrad_ref(const float* x1, int C1, const float* x2, int C2, const
   ConvGeom G{B, d0, d1, d2, C1, C2, Cout, k, 0};
   const long long nvox = (long long)B * d0 * d1 * d2;
   const int Ksmall = k * k * k * C1;
+  if (k == 3 && C2 == 0 && C1 <= 2 && Cout == 24 && ((uintptr_t)dy & 15) == 0) {       // first layer of the U-Net
+    const long long ntiles = (long long)B * ((d0 + FT0 - 1) / FT0) * ((d1 + FT1 - 1) / FT1) * ((d2 + FT2 - 1) / FT2);
+    const unsigned nb = (unsigned)(ntiles < 148 * 2 ? ntiles : 148 * 2);
+    if (C1 == 1) wgrad_first_kernel<1><<<nb, 256, 0, st>>>(x1, dy, dw, B, d0, d1, d2);
+    else wgrad_first_kernel<2><<<nb, 256, 0, st>>>(x1, dy, dw, B, d0, d1, d2);
+  } else
   if (C2 == 0 && C1 <= 4 && Cout % 4 == 0 && Ksmall * (Cout / 4) <= 384 && nvox >= 4096 &&
       ((uintptr_t)dy & 15) == 0) {
     const size_t smem = (size_t)WS_VOX * (Ksmall + 1 + Cout) * sizeof(float);
@@ -1032,6 +1262,26 @@ int ssr_head_loss(const float* feat, const float* w, const float* bias, const fl
   cudaStream_t st = (cudaStream_t)stream;
   SSR_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(double), st));
   const long long nvox = (long long)B * d0 * d1 * d2;
+  if (C % 4 == 0 && C <= 128 && ((uintptr_t)feat & 15) == 0 && (!train || ((uintptr_t)dfeat & 15) == 0)) {
+    // fused + coalesced path: loss, prediction, dfeat and the head weight gradient in one pass over feat
+    const int nq = C / 4;
+    const int gs = nq <= 1 ? 1 : nq <= 2 ? 2 : nq <= 4 ? 4 : nq <= 8 ? 8 : nq <= 16 ? 16 : 32;
+    long long nb = (nvox + (256 / gs) - 1) / (256 / gs);
+    if (nb > 148 * 8) nb = 148 * 8;
+#define SSR_HEAD_LAUNCH(GS_) head_loss_vec_kernel<GS_><<<(unsigned)nb, 256, 0, st>>>(feat, w, bias, image, target, pred, dfeat, dw, db, loss, P)
+    switch (gs) {
+      case 1: SSR_HEAD_LAUNCH(1); break;
+      case 2: SSR_HEAD_LAUNCH(2); break;
+      case 4: SSR_HEAD_LAUNCH(4); break;
+      case 8: SSR_HEAD_LAUNCH(8); break;
+      case 16: SSR_HEAD_LAUNCH(16); break;
+      default: SSR_HEAD_LAUNCH(32); break;
+    }
+#undef SSR_HEAD_LAUNCH
+    SSR_COUNT_LAUNCH();
+    SSR_CHECK_LAUNCH();
+    return SSR_OK;
+  }
   head_loss_kernel<<<grid_for(nvox), 256, 0, st>>>(feat, w, bias, image, target, pred, dfeat, dw, db, loss, P);
   SSR_COUNT_LAUNCH();
   if (train) {
