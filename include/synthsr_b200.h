@@ -97,6 +97,8 @@ int ssr_conv3d_wgrad_ref(const float* x1, int C1, const float* x2, int C2, const
  * (tcgen05.mma.kind::tf32, TMA-staged shared-memory tiles, TMEM accumulators).  See conv_tc.cu. */
 int ssr_conv3d_pack_weights(const float* w, float* wp, int Cin1, int Cin2, int Cout, int mode, void* stream);
 long long ssr_conv3d_packed_size(int Cin1, int Cin2, int Cout, int mode);
+/* jobs: DEVICE int64 array, njobs x {w pointer, wp pointer, Cin1, Cin2, Cout, mode}: packs every layer in one launch */
+int ssr_conv3d_pack_weights_batch(const long long* jobs, int njobs, void* stream);
 int ssr_conv3d_fwd_tc(const float* x1, int C1, const float* x2, int C2, const float* wp, const float* bias, float* y,
                       int B, int d0, int d1, int d2, int Cout, int act, void* stream);
 int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const float* dy, float* dw, float* db,

@@ -1009,8 +1009,8 @@ mma_microbench_kernel(float* __restrict__ out, int N, int nacc, int chain, int i
 //   mode 0 (forward):       value = w[k0][k1][k2][cin(chunk, s)][n]
 //   mode 1 (data gradient): value = w[2-k0][2-k1][2-k2][n][cout(chunk, s)]   (n runs over the layer's Cin)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ wp, int C1, int C2, int Cout,
-                                    int mode, int Npad, int nchunks, int nch1, int round_rn) {
+__device__ __forceinline__ void pack_weights_body(const float* __restrict__ w, float* __restrict__ wp, int C1, int C2,
+                                                  int Cout, int mode, int Npad, int nchunks, int nch1, int round_rn) {
   const long long total = (long long)nchunks * 27 * Npad * 32;
   const int Cin = C1 + C2;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -1038,6 +1038,20 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
     }
     wp[t] = val;
   }
+}
+__global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ wp, int C1, int C2, int Cout,
+                                    int mode, int Npad, int nchunks, int nch1, int round_rn) {
+  pack_weights_body(w, wp, C1, C2, Cout, mode, Npad, nchunks, nch1, round_rn);
+}
+// all layers of a network in one launch: blockIdx.y = job, jobs[j] = {w, wp, C1, C2, Cout, mode} (device array)
+__global__ void pack_weights_batch_kernel(const long long* __restrict__ jobs, int round_rn) {
+  const long long* j = jobs + (long long)blockIdx.y * 6;
+  const int C1 = (int)j[2], C2 = (int)j[3], Cout = (int)j[4], mode = (int)j[5];
+  int Npad, nch, nch1;
+  if (mode == 0) { Npad = (Cout + 15) / 16 * 16; nch1 = (C1 + 31) / 32; nch = nch1 + (C2 + 31) / 32; }
+  else { Npad = (C1 + C2 + 15) / 16 * 16; nch = (Cout + 31) / 32; nch1 = nch; }
+  pack_weights_body(reinterpret_cast<const float*>(j[0]), reinterpret_cast<float*>(j[1]), C1, C2, Cout, mode, Npad, nch,
+                    nch1, round_rn);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1112,6 +1126,14 @@ int pick_nt(int Npad) {
 
 extern "C" {
 
+// jobs: DEVICE array of njobs x {w pointer, wp pointer, Cin1, Cin2, Cout, mode} (int64); one launch packs them all
+int ssr_conv3d_pack_weights_batch(const long long* jobs, int njobs, void* stream) {
+  SSR_CHECK_ARG(jobs && njobs > 0 && njobs <= 65535, "pack batch args");
+  pack_weights_batch_kernel<<<dim3(148, (unsigned)njobs), 256, 0, (cudaStream_t)stream>>>(jobs, getenv("SSR_PACK_TRUNC") ? 0 : 1);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
 long long ssr_conv3d_packed_size(int Cin1, int Cin2, int Cout, int mode) {
   if (mode == 0) {
     const int nch = (Cin1 + 31) / 32 + (Cin2 + 31) / 32;

@@ -434,6 +434,78 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, long long nvox, int
   }
 }
 
+// Vectorised per-channel double sums over voxels for C % 4 == 0 (C <= 1024): thread (r, q) owns the float4 of channels
+// 4q..4q+3 of every (gridDim * R)-th voxel; loads are 16-byte and coalesced across the threads of a row, four
+// independent loads are in flight per thread, fp32 partials of four voxels are folded into double accumulators.
+//   MODE 0: sums = [sum a | sum a^2]                       (BatchNorm statistics)
+//   MODE 1: sums = [sum a | sum a * (b - mean) * invstd]    (BatchNorm backward: a = dy, b = x)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+colsum2_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ stats,
+                   long long nvox, int C, double* __restrict__ sums) {
+  __shared__ double sh[256 * 8];
+  const int nq = C >> 2, R = blockDim.x / nq;
+  const int q = threadIdx.x % nq, r = threadIdx.x / nq;
+  double s[4] = {0., 0., 0., 0.}, t[4] = {0., 0., 0., 0.};
+  if (r < R) {
+    float4 mean = make_float4(0.f, 0.f, 0.f, 0.f), inv = mean;
+    if (MODE == 1) {
+      mean = *reinterpret_cast<const float4*>(stats + 4 * q);
+      inv = *reinterpret_cast<const float4*>(stats + C + 4 * q);
+    }
+    const long long stride = (long long)gridDim.x * R;
+    for (long long v0 = (long long)blockIdx.x * R + r; v0 < nvox; v0 += 4 * stride) {
+      float4 x[4], y[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long v = v0 + u * stride;
+        x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        y[u] = mean;
+        if (v < nvox) {
+          x[u] = *reinterpret_cast<const float4*>(a + v * C + 4 * q);
+          if (MODE == 1) y[u] = *reinterpret_cast<const float4*>(b + v * C + 4 * q);
+        }
+      }
+      float4 fs = make_float4(0.f, 0.f, 0.f, 0.f), ft = fs;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        fs.x += x[u].x; fs.y += x[u].y; fs.z += x[u].z; fs.w += x[u].w;
+        if (MODE == 0) {
+          ft.x += x[u].x * x[u].x; ft.y += x[u].y * x[u].y; ft.z += x[u].z * x[u].z; ft.w += x[u].w * x[u].w;
+        } else {
+          ft.x += x[u].x * ((y[u].x - mean.x) * inv.x); ft.y += x[u].y * ((y[u].y - mean.y) * inv.y);
+          ft.z += x[u].z * ((y[u].z - mean.z) * inv.z); ft.w += x[u].w * ((y[u].w - mean.w) * inv.w);
+        }
+      }
+      s[0] += fs.x; s[1] += fs.y; s[2] += fs.z; s[3] += fs.w;
+      t[0] += ft.x; t[1] += ft.y; t[2] += ft.z; t[3] += ft.w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { sh[threadIdx.x * 8 + j] = s[j]; sh[threadIdx.x * 8 + 4 + j] = t[j]; }
+  __syncthreads();
+  if (threadIdx.x < nq) {
+    double ts[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+    for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ts[j] += sh[(rr * nq + q) * 8 + j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { atomicAdd(sums + 4 * q + j, ts[j]); atomicAdd(sums + C + 4 * q + j, ts[4 + j]); }
+  }
+}
+
+template <int MODE>
+static void launch_colsum2(const float* a, const float* b, const float* stats, long long nvox, int C, double* sums,
+                           cudaStream_t st) {
+  const int nq = C / 4, R = 256 / nq;
+  long long nb = (nvox + (long long)R * 4 - 1) / ((long long)R * 4);
+  if (nb > 148 * 8) nb = 148 * 8;
+  colsum2_vec_kernel<MODE><<<(unsigned)nb, nq * R, 0, st>>>(a, b, stats, nvox, C, sums);
+}
+static bool colsum_vec_ok(int C, const void* a, const void* b) {
+  return C % 4 == 0 && C <= 1024 && ((uintptr_t)a & 15) == 0 && (!b || ((uintptr_t)b & 15) == 0);
+}
+
 // stats layout (float, 4*C): mean | invstd | scale (= gamma*invstd) | shift (= beta - mean*scale)
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, long long n, int C, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ moving_mean,
@@ -676,6 +748,80 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ dp, const float* __
   }
 }
 
+// float4 version (C % 4 == 0): a thread owns 4 channels of one pooled voxel; eight 16-byte loads in flight, eight
+// 16-byte stores
+__global__ void __launch_bounds__(256)
+maxpool_bwd_vec_kernel(const float* __restrict__ dp, const float* __restrict__ x, const float* __restrict__ stats, int B,
+                       int d0, int d1, int d2, int C, float* __restrict__ dyf) {
+  const int CV = C >> 2;
+  const int o0 = (d0 + 1) / 2, o1 = (d1 + 1) / 2, o2 = (d2 + 1) / 2;
+  const long long n = (long long)B * o0 * o1 * o2 * CV;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(t % CV);
+    long long r = t / CV;
+    const int k = (int)(r % o2); r /= o2;
+    const int j = (int)(r % o1); r /= o1;
+    const int i = (int)(r % o0);
+    const int b = (int)(r / o0);
+    const float4 sc = *reinterpret_cast<const float4*>(stats + 2 * C + 4 * cv);
+    const float4 sf = *reinterpret_cast<const float4*>(stats + 3 * C + 4 * cv);
+    const float4 g = *reinterpret_cast<const float4*>(dp + t * 4);
+    float4 xv[8];
+    long long idx[8];
+    bool ok[8];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const int s0 = 2 * i + (w >> 2), s1 = 2 * j + ((w >> 1) & 1), s2 = 2 * k + (w & 1);
+      ok[w] = s0 < d0 && s1 < d1 && s2 < d2;
+      idx[w] = ((((long long)b * d0 + s0) * d1 + s1) * d2 + s2) * C + 4 * cv;
+      xv[w] = ok[w] ? *reinterpret_cast<const float4*>(x + idx[w]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4 m = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+    int ax = -1, ay = -1, az = -1, aw = -1;                 // first maximum in window order, like the scalar kernel
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (!ok[w]) continue;
+      const float vx = xv[w].x * sc.x + sf.x, vy = xv[w].y * sc.y + sf.y, vz = xv[w].z * sc.z + sf.z, vw = xv[w].w * sc.w + sf.w;
+      if (vx > m.x) { m.x = vx; ax = w; }
+      if (vy > m.y) { m.y = vy; ay = w; }
+      if (vz > m.z) { m.z = vz; az = w; }
+      if (vw > m.w) { m.w = vw; aw = w; }
+    }
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (!ok[w]) continue;
+      *reinterpret_cast<float4*>(dyf + idx[w]) =
+          make_float4(ax == w ? g.x : 0.f, ay == w ? g.y : 0.f, az == w ? g.z : 0.f, aw == w ? g.w : 0.f);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+upsample_bwd_vec_kernel(const float* __restrict__ du, int du_stride, int du_off, int B, int d0, int d1, int d2, int C,
+                        float* __restrict__ dlow) {
+  const int CV = C >> 2;
+  const long long n = (long long)B * d0 * d1 * d2 * CV;
+  const int f0 = 2 * d0, f1 = 2 * d1, f2 = 2 * d2;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(t % CV);
+    long long r = t / CV;
+    const int k = (int)(r % d2); r /= d2;
+    const int j = (int)(r % d1); r /= d1;
+    const int i = (int)(r % d0);
+    const int b = (int)(r / d0);
+    float4 v[8];
+#pragma unroll
+    for (int w = 0; w < 8; ++w)
+      v[w] = *reinterpret_cast<const float4*>(
+          du + ((((long long)b * f0 + 2 * i + (w >> 2)) * f1 + 2 * j + ((w >> 1) & 1)) * f2 + 2 * k + (w & 1)) * du_stride +
+          du_off + 4 * cv);
+    float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { sacc.x += v[w].x; sacc.y += v[w].y; sacc.z += v[w].z; sacc.w += v[w].w; }   // same order as scalar
+    *reinterpret_cast<float4*>(dlow + t * 4) = sacc;
+  }
+}
+
 // gradient of upsample2: dlow[v][c] = sum of the 8 children of du (du may be a channel slice of a wider tensor)
 __global__ void upsample_bwd_kernel(const float* __restrict__ du, int du_stride, int du_off, int B, int d0, int d1,
                                     int d2, int C, float* __restrict__ dlow) {
@@ -824,7 +970,7 @@ head_loss_kernel(const float* __restrict__ feat, const float* __restrict__ w, co
 // a group of GS lanes (GS = power of two >= C/4) owns one voxel, lane q holds the float4 of channels 4q..4q+3, the
 // 1x1x1 convolution is a shuffle reduction inside the group, dfeat is written as float4 and the head weight gradient
 // feat^T * g is accumulated in registers (one block-level reduction at the end).  feat is read once, dfeat written once.
-template <int GS>
+template <int GS, int LT>        // LT: compile-time bound of L (1 or 4) so the per-output arrays stay in few registers
 __global__ void __launch_bounds__(256)
 head_loss_vec_kernel(const float* __restrict__ feat, const float* __restrict__ w, const float* __restrict__ bias,
                      const float* __restrict__ image, const float* __restrict__ target, float* __restrict__ pred,
@@ -838,78 +984,100 @@ head_loss_vec_kernel(const float* __restrict__ feat, const float* __restrict__ w
   __syncthreads();
   const int q = threadIdx.x % GS;
   const bool active = q < nq;
-  float wq[4][4];                                // this lane's 4 channels x L outputs
+  float wq[4][LT];                                // this lane's 4 channels x L outputs
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int l = 0; l < 4; ++l) wq[j][l] = (active && l < L) ? sw[(4 * q + j) * L + l] : 0.f;
-  float bl[4];
+    for (int l = 0; l < LT; ++l) wq[j][l] = (active && l < L) ? sw[(4 * q + j) * L + l] : 0.f;
+  float bl[LT];
 #pragma unroll
-  for (int l = 0; l < 4; ++l) bl[l] = l < L ? bias[l] : 0.f;
-  float wacc[4][4];
+  for (int l = 0; l < LT; ++l) bl[l] = l < L ? bias[l] : 0.f;
+  float wacc[4][LT];
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int l = 0; l < 4; ++l) wacc[j][l] = 0.f;
+    for (int l = 0; l < LT; ++l) wacc[j][l] = 0.f;
   const long long nvox = (long long)P.B * P.d0 * P.d1 * P.d2;
   const int gpb = blockDim.x / GS;
   double lloss = 0.0;
-  float ldb[4] = {0.f, 0.f, 0.f, 0.f};
-  // all lanes of a warp run the same number of iterations (shuffles below are full-warp)
-  const long long vstep = (long long)gridDim.x * gpb;
-  const long long niter = (nvox + vstep - 1) / vstep;
-  long long v = (long long)blockIdx.x * gpb + threadIdx.x / GS;
-  for (long long it = 0; it < niter; ++it, v += vstep) {
-    const bool vok = v < nvox;
-    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (vok && active) f = *reinterpret_cast<const float4*>(feat + v * C + 4 * q);
-    float o[4];
+  float ldb[LT];
 #pragma unroll
-    for (int l = 0; l < 4; ++l) o[l] = f.x * wq[0][l] + f.y * wq[1][l] + f.z * wq[2][l] + f.w * wq[3][l];
+  for (int l = 0; l < LT; ++l) ldb[l] = 0.f;
+  // all lanes of a warp run the same number of iterations (shuffles below are full-warp); two voxels per iteration
+  // keep two independent 16-byte loads (plus the image / target loads) in flight per lane
+  const long long vstep = (long long)gridDim.x * gpb;
+  const long long niter = (nvox + 2 * vstep - 1) / (2 * vstep);
+  long long vbase = (long long)blockIdx.x * gpb + threadIdx.x / GS;
+  for (long long it = 0; it < niter; ++it, vbase += 2 * vstep) {
+    float4 f[2];
+    float o[2][LT], tg[2][LT], im[2][LT];
+    bool vok[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long v = vbase + u * vstep;
+      vok[u] = v < nvox;
+      f[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (vok[u] && active) f[u] = *reinterpret_cast<const float4*>(feat + v * C + 4 * q);
+#pragma unroll
+      for (int l = 0; l < LT; ++l) {
+        tg[u][l] = (vok[u] && l < L) ? target[v * P.tgt_stride + l] : 0.f;
+        im[u][l] = (vok[u] && l < L && P.res_stride > 0) ? image[v * P.res_stride + P.res_idx[l]] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int l = 0; l < LT; ++l) o[u][l] = f[u].x * wq[0][l] + f[u].y * wq[1][l] + f[u].z * wq[2][l] + f[u].w * wq[3][l];
 #pragma unroll
     for (int off = GS / 2; off > 0; off >>= 1)
 #pragma unroll
-      for (int l = 0; l < 4; ++l)
-        if (l < L) o[l] += __shfl_xor_sync(0xffffffffu, o[l], off);
-    if (!vok) continue;
-    bool inside = true;
-    if (P.c0 > 0) {
-      long long r = v;
-      const int i2 = (int)(r % P.d2); r /= P.d2;
-      const int i1 = (int)(r % P.d1); r /= P.d1;
-      const int i0 = (int)(r % P.d0);
-      inside = i0 >= P.cb0 && i0 < P.cb0 + P.c0 && i1 >= P.cb1 && i1 < P.cb1 + P.c1 && i2 >= P.cb2 && i2 < P.cb2 + P.c2;
-    }
-    float g[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int u = 0; u < 2; ++u)
 #pragma unroll
-    for (int l = 0; l < 4; ++l) {
-      if (l >= L) break;
-      const float ol = o[l] + bl[l];
-      if (pred && q == 0) pred[v * L + l] = ol;
-      float pr = ol;
-      if (P.res_stride > 0) pr += image[v * P.res_stride + P.res_idx[l]];
-      const float err = pr - target[v * P.tgt_stride + l];
-      if (inside) {
-        if (P.metric == 1) {
-          if (q == 0) lloss += fabsf(err);
-          g[l] = (err > 0.f ? 1.f : (err < 0.f ? -1.f : 0.f)) * (float)P.inv_count;
-        } else {
-          if (q == 0) lloss += (double)err * err;
-          g[l] = 2.f * err * (float)P.inv_count;
-        }
+        for (int l = 0; l < LT; ++l)
+          if (l < L) o[u][l] += __shfl_xor_sync(0xffffffffu, o[u][l], off);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!vok[u]) continue;
+      const long long v = vbase + u * vstep;
+      bool inside = true;
+      if (P.c0 > 0) {
+        long long r = v;
+        const int i2 = (int)(r % P.d2); r /= P.d2;
+        const int i1 = (int)(r % P.d1); r /= P.d1;
+        const int i0 = (int)(r % P.d0);
+        inside = i0 >= P.cb0 && i0 < P.cb0 + P.c0 && i1 >= P.cb1 && i1 < P.cb1 + P.c1 && i2 >= P.cb2 && i2 < P.cb2 + P.c2;
       }
-      if (q == 0) ldb[l] += g[l];
-    }
-    if (P.train && active) {
-      float4 d;
-      d.x = g[0] * wq[0][0] + g[1] * wq[0][1] + g[2] * wq[0][2] + g[3] * wq[0][3];
-      d.y = g[0] * wq[1][0] + g[1] * wq[1][1] + g[2] * wq[1][2] + g[3] * wq[1][3];
-      d.z = g[0] * wq[2][0] + g[1] * wq[2][1] + g[2] * wq[2][2] + g[3] * wq[2][3];
-      d.w = g[0] * wq[3][0] + g[1] * wq[3][1] + g[2] * wq[3][2] + g[3] * wq[3][3];
-      *reinterpret_cast<float4*>(dfeat + v * C + 4 * q) = d;
+      float g[LT];
 #pragma unroll
-      for (int l = 0; l < 4; ++l) {
-        wacc[0][l] += f.x * g[l]; wacc[1][l] += f.y * g[l]; wacc[2][l] += f.z * g[l]; wacc[3][l] += f.w * g[l];
+      for (int l = 0; l < LT; ++l) g[l] = 0.f;
+#pragma unroll
+      for (int l = 0; l < LT; ++l) {
+        if (l >= L) break;
+        const float ol = o[u][l] + bl[l];
+        if (pred && q == 0) pred[v * L + l] = ol;
+        const float err = ol + im[u][l] - tg[u][l];
+        if (inside) {
+          if (P.metric == 1) {
+            if (q == 0) lloss += fabsf(err);
+            g[l] = (err > 0.f ? 1.f : (err < 0.f ? -1.f : 0.f)) * (float)P.inv_count;
+          } else {
+            if (q == 0) lloss += (double)err * err;
+            g[l] = 2.f * err * (float)P.inv_count;
+          }
+        }
+        if (q == 0) ldb[l] += g[l];
+      }
+      if (P.train && active) {
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int l = 0; l < LT; ++l) {
+          d.x += g[l] * wq[0][l]; d.y += g[l] * wq[1][l]; d.z += g[l] * wq[2][l]; d.w += g[l] * wq[3][l];
+        }
+        *reinterpret_cast<float4*>(dfeat + v * C + 4 * q) = d;
+#pragma unroll
+        for (int l = 0; l < LT; ++l) {
+          wacc[0][l] += f[u].x * g[l]; wacc[1][l] += f[u].y * g[l]; wacc[2][l] += f[u].z * g[l]; wacc[3][l] += f[u].w * g[l];
+        }
       }
     }
   }
@@ -919,7 +1087,7 @@ head_loss_vec_kernel(const float* __restrict__ feat, const float* __restrict__ w
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int l = 0; l < 4; ++l) {
+      for (int l = 0; l < LT; ++l) {
         if (l >= L) break;
         float a = wacc[j][l];
         for (int off = GS; off < 32; off <<= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
@@ -929,7 +1097,7 @@ head_loss_vec_kernel(const float* __restrict__ feat, const float* __restrict__ w
   for (int o2 = 16; o2 > 0; o2 >>= 1) {
     lloss += __shfl_xor_sync(0xffffffffu, lloss, o2);
 #pragma unroll
-    for (int l = 0; l < 4; ++l) ldb[l] += __shfl_xor_sync(0xffffffffu, ldb[l], o2);
+    for (int l = 0; l < LT; ++l) ldb[l] += __shfl_xor_sync(0xffffffffu, ldb[l], o2);
   }
   if ((threadIdx.x & 31) == 0) {
     sloss[threadIdx.x >> 5] = lloss;
@@ -1119,7 +1287,8 @@ int ssr_bn_stats(const float* x, long long nvox, int C, const float* gamma, cons
   SSR_CHECK_CUDA(cudaMemsetAsync(sums_scratch, 0, 2 * C * sizeof(double), st));
   dim3 blk(32, 8);
   int g = (int)((nvox + 7) / 8); if (g > 148 * 8) g = 148 * 8;
-  bn_stats_kernel<<<g, blk, 32 * 8 * 2 * sizeof(double), st>>>(x, nvox, C, sums_scratch);
+  if (colsum_vec_ok(C, x, nullptr)) launch_colsum2<0>(x, nullptr, nullptr, nvox, C, sums_scratch, st);
+  else bn_stats_kernel<<<g, blk, 32 * 8 * 2 * sizeof(double), st>>>(x, nvox, C, sums_scratch);
   SSR_COUNT_LAUNCH();
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums_scratch, nvox, C, gamma, beta, moving_mean, moving_var, eps,
                                                       momentum, stats);
@@ -1179,7 +1348,8 @@ int ssr_bn_bwd(const float* dy, const float* x, const float* stats, long long nv
   SSR_CHECK_CUDA(cudaMemsetAsync(sums_scratch, 0, 2 * C * sizeof(double), st));
   dim3 blk(32, 8);
   int g = (int)((nvox + 7) / 8); if (g > 148 * 8) g = 148 * 8;
-  bn_bwd_reduce_kernel<<<g, blk, 32 * 8 * 2 * sizeof(double), st>>>(dy, x, stats, nvox, C, sums_scratch);
+  if (colsum_vec_ok(C, dy, x) && ((uintptr_t)stats & 15) == 0) launch_colsum2<1>(dy, x, stats, nvox, C, sums_scratch, st);
+  else bn_bwd_reduce_kernel<<<g, blk, 32 * 8 * 2 * sizeof(double), st>>>(dy, x, stats, nvox, C, sums_scratch);
   SSR_COUNT_LAUNCH();
   if (dgamma && dbeta) {
     bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums_scratch, C, dgamma, dbeta);
@@ -1204,7 +1374,10 @@ int ssr_maxpool_bwd(const float* dp, const float* x, const float* stats, int B, 
                     float* dy_full, void* stream) {
   SSR_CHECK_ARG(dp && x && stats && dy_full, "args");
   const long long n = (long long)B * ((d0 + 1) / 2) * ((d1 + 1) / 2) * ((d2 + 1) / 2) * C;
-  maxpool_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(dp, x, stats, B, d0, d1, d2, C, dy_full);
+  if (C % 4 == 0 && (((uintptr_t)dp | (uintptr_t)x | (uintptr_t)stats | (uintptr_t)dy_full) & 15) == 0)
+    maxpool_bwd_vec_kernel<<<grid_for(n / 4), 256, 0, (cudaStream_t)stream>>>(dp, x, stats, B, d0, d1, d2, C, dy_full);
+  else
+    maxpool_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(dp, x, stats, B, d0, d1, d2, C, dy_full);
   SSR_COUNT_LAUNCH();
   SSR_CHECK_LAUNCH();
   return SSR_OK;
@@ -1214,8 +1387,12 @@ int ssr_maxpool_bwd(const float* dp, const float* x, const float* stats, int B, 
 int ssr_upsample_bwd(const float* du, int du_stride, int du_off, int B, int d0, int d1, int d2, int C, float* dlow,
                      void* stream) {
   SSR_CHECK_ARG(du && dlow && du_stride >= C, "args");
-  upsample_bwd_kernel<<<grid_for((long long)B * d0 * d1 * d2 * C), 256, 0, (cudaStream_t)stream>>>(
-      du, du_stride, du_off, B, d0, d1, d2, C, dlow);
+  if (C % 4 == 0 && du_stride % 4 == 0 && du_off % 4 == 0 && (((uintptr_t)du | (uintptr_t)dlow) & 15) == 0)
+    upsample_bwd_vec_kernel<<<grid_for((long long)B * d0 * d1 * d2 * (C / 4)), 256, 0, (cudaStream_t)stream>>>(
+        du, du_stride, du_off, B, d0, d1, d2, C, dlow);
+  else
+    upsample_bwd_kernel<<<grid_for((long long)B * d0 * d1 * d2 * C), 256, 0, (cudaStream_t)stream>>>(
+        du, du_stride, du_off, B, d0, d1, d2, C, dlow);
   SSR_COUNT_LAUNCH();
   SSR_CHECK_LAUNCH();
   return SSR_OK;
@@ -1268,7 +1445,11 @@ int ssr_head_loss(const float* feat, const float* w, const float* bias, const fl
     const int gs = nq <= 1 ? 1 : nq <= 2 ? 2 : nq <= 4 ? 4 : nq <= 8 ? 8 : nq <= 16 ? 16 : 32;
     long long nb = (nvox + (256 / gs) - 1) / (256 / gs);
     if (nb > 148 * 8) nb = 148 * 8;
-#define SSR_HEAD_LAUNCH(GS_) head_loss_vec_kernel<GS_><<<(unsigned)nb, 256, 0, st>>>(feat, w, bias, image, target, pred, dfeat, dw, db, loss, P)
+#define SSR_HEAD_LAUNCH(GS_)                                                                                              \
+  do {                                                                                                                  \
+    if (L == 1) head_loss_vec_kernel<GS_, 1><<<(unsigned)nb, 256, 0, st>>>(feat, w, bias, image, target, pred, dfeat, dw, db, loss, P); \
+    else head_loss_vec_kernel<GS_, 4><<<(unsigned)nb, 256, 0, st>>>(feat, w, bias, image, target, pred, dfeat, dw, db, loss, P);        \
+  } while (0)
     switch (gs) {
       case 1: SSR_HEAD_LAUNCH(1); break;
       case 2: SSR_HEAD_LAUNCH(2); break;

@@ -266,10 +266,15 @@ class UNet3D:
         if self._packed_dirty and self._packed:          # refresh every packed kernel copy once per optimiser step
             self._packed_dirty = False
             self._packed_valid = set()
-            for (name, mode), buf in self._packed.items():
-                c1, c2, cout = self._packed_args[(name, mode)]
-                lib.ssr_conv3d_pack_weights(self.p[name + '/kernel'], buf, c1, c2, cout, mode, st)
-                self._packed_valid.add((name, mode))
+            if getattr(self, '_pack_jobs_n', 0) != len(self._packed):   # device job table, rebuilt when a copy is added
+                rows = []
+                for (name, mode), buf in self._packed.items():
+                    c1, c2, cout = self._packed_args[(name, mode)]
+                    rows.append([self.p[name + '/kernel'].data_ptr(), buf.data_ptr(), c1, c2, cout, mode])
+                self._pack_jobs = torch.tensor(rows, dtype=torch.int64).to(self.device)
+                self._pack_jobs_n = len(rows)
+            lib.ssr_conv3d_pack_weights_batch(self._pack_jobs, self._pack_jobs_n, st)     # every layer in one launch
+            self._packed_valid = set(self._packed.keys())
         x, cx = image, self.cin
         for l in range(L):
             self._conv_fwd('unet_conv_downarm_%d_0' % l, x, cx, None, 0, self.h0[l], l, F[l])
