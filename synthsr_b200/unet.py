@@ -8,7 +8,9 @@ buffer and a single fused Adam launch); views into it carry the Keras layer name
 conv_impl = 'tc'  : tcgen05 TF32 implicit-GEMM convolutions (conv_tc.cu)            -- throughput mode
 conv_impl = 'ref' : exact fp32 CUDA-core convolutions (unet_kernels.cu)             -- parity mode / cross-check
 """
+import contextlib
 import math
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -55,6 +57,8 @@ class UNet3D:
         self.conv_impl = conv_impl
         self.wgrad_tc = conv_impl == 'tc'
         self.prof = None          # list of (kind, flops, start_event, end_event) when profiling is enabled
+        self.overlap_wgrad = os.environ.get('SSR_NO_WGRAD_OVERLAP') is None
+        self._side, self._side_busy, self._hp = None, False, None
         self.device = torch.device(device)
         for d in self.dims:
             if d % (2 ** (self.L - 1)) != 0:
@@ -167,6 +171,10 @@ class UNet3D:
 
         self.ga = [buf(l, F[l]) for l in range(L)]
         self.gb = [buf(l, F[l]) for l in range(L)]
+        # the encoder phase has its own buffers: weight-gradient kernels of the decoder phase may still be reading
+        # ga/gb on the side stream when the encoder phase starts (see _wgrad_async)
+        self.ga_e = [buf(l, F[l]) for l in range(L)]
+        self.gb_e = [buf(l, F[l]) for l in range(L)]
         self.dcat = [buf(l, F[l] + F[l + 1]) for l in range(L - 1)]
         self.dbn_dec = [buf(l, F[l]) for l in range(L - 1)]                   # grad wrt BN output of decoder level l
         self.dbn_bott = buf(L - 1, F[L - 1])                                  # grad wrt BN output of the bottleneck
@@ -236,6 +244,32 @@ class UNet3D:
         else:
             lib.ssr_conv3d_wgrad_ref(x1, c1, x2, c2, dy, self.g[name + '/kernel'], None, self.B, *d,
                                      cout, self.k, st)
+
+    def _wgrad_async(self, *args):
+        """weight gradients only feed the optimiser, so they run on a side stream: the memory-bound elementwise kernels
+        of the backward chain (BN / ELU / pooling gradients) then overlap with tensor-core-bound wgrad kernels instead
+        of waiting for them.  Disabled while per-kernel profiling is on (timings would overlap)."""
+        if self.prof is not None or not self.overlap_wgrad:
+            return self._conv_wgrad(*args)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+            self._ev_pool = [torch.cuda.Event() for _ in range(64)]
+            self._ev_i = 0
+        ev = self._ev_pool[self._ev_i % len(self._ev_pool)]
+        self._ev_i += 1
+        ev.record()                                   # the gradient this wgrad reads is complete on the main stream
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ev)
+            self._conv_wgrad(*args)
+        self._side_busy = True
+
+    def _wgrad_join(self):
+        if self._side is not None and self._side_busy:
+            ev = self._ev_pool[self._ev_i % len(self._ev_pool)]
+            self._ev_i += 1
+            ev.record(self._side)
+            torch.cuda.current_stream().wait_event(ev)
+            self._side_busy = False
 
     def _wgrad_tc_ok(self, c1, c2, cout):
         return getattr(self, 'wgrad_tc', False) and (c1 % 8 == 0) and (c2 % 8 == 0) and cout % 8 == 0
@@ -346,39 +380,53 @@ class UNet3D:
         self.forward(image, training=True)
         self.grads.zero_()
         self._head(target, metric, work_with_residual_channel, loss_cropping, train=True)
-        # ---- decoder, shallow to deep -----------------------------------------------------------------------
-        for l in range(L - 1):
-            d = L - 2 - l
-            c0, c1n = 'unet_conv_uparm_%d_0' % (L + d), 'unet_conv_uparm_%d_1' % (L + d)
-            bn = 'unet_bn_up_%d' % d
-            lib.ssr_bn_bwd(self.dbn_dec[l], self.g1[l], self.stats_dec[l], self.nvox[l], F[l], None, 0, 0, 1, self.ga[l],
-                           self.g[bn + '/gamma'], self.g[bn + '/beta'], self.g[c1n + '/bias'], self.sums, st)
-            self._conv_wgrad(c1n, self.g0[l], F[l], None, 0, self.ga[l], l, F[l])
-            self._conv_dgrad(c1n, self.ga[l], self.gb[l], l, F[l], F[l])
-            lib.ssr_elu_bwd(self.gb[l], 0, 0, self.g0[l], None, self.nvox[l], F[l], self.gb[l], self.g[c0 + '/bias'], st)
-            self._conv_wgrad(c0, self.h1[l], F[l], self.u[l], F[l + 1], self.gb[l], l, F[l])
-            self._conv_dgrad(c0, self.gb[l], self.dcat[l], l, F[l] + F[l + 1], F[l])
-            tgt = self.dbn_dec[l + 1] if l + 1 <= L - 2 else self.dbn_bott
-            lib.ssr_upsample_bwd(self.dcat[l], F[l] + F[l + 1], F[l], B, *self.ldims[l + 1], F[l + 1], tgt, st)
-        # ---- encoder, deep to shallow -----------------------------------------------------------------------
-        for l in range(L - 1, -1, -1):
-            c0, c1n, bn = 'unet_conv_downarm_%d_0' % l, 'unet_conv_downarm_%d_1' % l, 'unet_bn_down_%d' % l
-            if l == L - 1:
-                lib.ssr_bn_bwd(self.dbn_bott, self.h1[l], self.stats_enc[l], self.nvox[l], F[l], None, 0, 0, 1,
-                               self.ga[l], self.g[bn + '/gamma'], self.g[bn + '/beta'], self.g[c1n + '/bias'], self.sums, st)
-            else:
-                lib.ssr_maxpool_bwd(self.dp[l + 1], self.h1[l], self.stats_enc[l], B, *self.ldims[l], F[l], self.ga[l],
-                                    st)
-                lib.ssr_bn_bwd(self.ga[l], self.h1[l], self.stats_enc[l], self.nvox[l], F[l], self.dcat[l],
-                               F[l] + F[l + 1], 0, 1, self.ga[l], self.g[bn + '/gamma'], self.g[bn + '/beta'],
-                               self.g[c1n + '/bias'], self.sums, st)
-            self._conv_wgrad(c1n, self.h0[l], F[l], None, 0, self.ga[l], l, F[l])
-            self._conv_dgrad(c1n, self.ga[l], self.gb[l], l, F[l], F[l])
-            lib.ssr_elu_bwd(self.gb[l], 0, 0, self.h0[l], None, self.nvox[l], F[l], self.gb[l], self.g[c0 + '/bias'], st)
-            x, cx = (self._image, self.cin) if l == 0 else (self.inp[l], F[l - 1])
-            self._conv_wgrad(c0, x, cx, None, 0, self.gb[l], l, F[l])
-            if l > 0:
-                self._conv_dgrad(c0, self.gb[l], self.dp[l], l, F[l - 1], F[l])
+        # The backward chain (dgrad + elementwise gradients) is the critical path: it runs on a high-priority stream, the
+        # weight gradients on a normal-priority side stream, so pending dgrad CTAs are dispatched ahead of wgrad CTAs
+        # and wgrad fills the SMs while the chain is in its memory-bound elementwise phases.
+        overlap = self.overlap_wgrad and self.prof is None
+        cur = torch.cuda.current_stream()
+        if overlap:
+            if self._hp is None:
+                self._hp = torch.cuda.Stream(device=self.device, priority=-1)
+            self._hp.wait_stream(cur)
+        with (torch.cuda.stream(self._hp) if overlap else contextlib.nullcontext()):
+            st = stream_ptr()
+            # ---- decoder, shallow to deep -----------------------------------------------------------------------
+            for l in range(L - 1):
+                d = L - 2 - l
+                c0, c1n = 'unet_conv_uparm_%d_0' % (L + d), 'unet_conv_uparm_%d_1' % (L + d)
+                bn = 'unet_bn_up_%d' % d
+                lib.ssr_bn_bwd(self.dbn_dec[l], self.g1[l], self.stats_dec[l], self.nvox[l], F[l], None, 0, 0, 1, self.ga[l],
+                               self.g[bn + '/gamma'], self.g[bn + '/beta'], self.g[c1n + '/bias'], self.sums, st)
+                self._wgrad_async(c1n, self.g0[l], F[l], None, 0, self.ga[l], l, F[l])
+                self._conv_dgrad(c1n, self.ga[l], self.gb[l], l, F[l], F[l])
+                lib.ssr_elu_bwd(self.gb[l], 0, 0, self.g0[l], None, self.nvox[l], F[l], self.gb[l], self.g[c0 + '/bias'], st)
+                self._wgrad_async(c0, self.h1[l], F[l], self.u[l], F[l + 1], self.gb[l], l, F[l])
+                self._conv_dgrad(c0, self.gb[l], self.dcat[l], l, F[l] + F[l + 1], F[l])
+                tgt = self.dbn_dec[l + 1] if l + 1 <= L - 2 else self.dbn_bott
+                lib.ssr_upsample_bwd(self.dcat[l], F[l] + F[l + 1], F[l], B, *self.ldims[l + 1], F[l + 1], tgt, st)
+            # ---- encoder, deep to shallow -----------------------------------------------------------------------
+            for l in range(L - 1, -1, -1):
+                c0, c1n, bn = 'unet_conv_downarm_%d_0' % l, 'unet_conv_downarm_%d_1' % l, 'unet_bn_down_%d' % l
+                if l == L - 1:
+                    lib.ssr_bn_bwd(self.dbn_bott, self.h1[l], self.stats_enc[l], self.nvox[l], F[l], None, 0, 0, 1,
+                                   self.ga_e[l], self.g[bn + '/gamma'], self.g[bn + '/beta'], self.g[c1n + '/bias'], self.sums, st)
+                else:
+                    lib.ssr_maxpool_bwd(self.dp[l + 1], self.h1[l], self.stats_enc[l], B, *self.ldims[l], F[l], self.ga_e[l],
+                                        st)
+                    lib.ssr_bn_bwd(self.ga_e[l], self.h1[l], self.stats_enc[l], self.nvox[l], F[l], self.dcat[l],
+                                   F[l] + F[l + 1], 0, 1, self.ga_e[l], self.g[bn + '/gamma'], self.g[bn + '/beta'],
+                                   self.g[c1n + '/bias'], self.sums, st)
+                self._wgrad_async(c1n, self.h0[l], F[l], None, 0, self.ga_e[l], l, F[l])
+                self._conv_dgrad(c1n, self.ga_e[l], self.gb_e[l], l, F[l], F[l])
+                lib.ssr_elu_bwd(self.gb_e[l], 0, 0, self.h0[l], None, self.nvox[l], F[l], self.gb_e[l], self.g[c0 + '/bias'], st)
+                x, cx = (self._image, self.cin) if l == 0 else (self.inp[l], F[l - 1])
+                self._wgrad_async(c0, x, cx, None, 0, self.gb_e[l], l, F[l])
+                if l > 0:
+                    self._conv_dgrad(c0, self.gb_e[l], self.dp[l], l, F[l - 1], F[l])
+            self._wgrad_join()
+        if overlap:
+            cur.wait_stream(self._hp)
         return self.loss_buf
 
     def adam_step(self, lr=1e-4, lr_decay=0., beta1=.9, beta2=.999, eps=1e-7, grad_scale=1.):
