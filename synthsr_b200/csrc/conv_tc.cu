@@ -1170,10 +1170,35 @@ int ssr_conv3d_fwd_tc(const float* x1, int C1, const float* x2, int C2, const fl
   memset(&G, 0, sizeof(G));
   G.B = B; G.D0 = D0; G.D1 = D1; G.D2 = D2; G.Cout = Cout; G.act = act;
   G.Npad = round_up(Cout, 16);
-  G.NT = pick_nt(G.Npad);
+  // Tile shape (NT output channels x TZ output planes per CTA tile): the kernel is persistent with a static round-robin
+  // over tiles, so the cost is rounds x per-tile time.  Small layers (40^3 and below) have few tiles: a narrower N tile or
+  // fewer planes per tile trades MMA efficiency for SM utilisation.  MMA cost per instruction from the measured
+  // max(N/2, 32 + N/4) (+ issue overhead), profiles/r01_mma_issue_microbench.txt.
+  {
+    int ks_total = 0;
+    for (int c = 0; c < C1; c += 32) ks_total += ((C1 - c < 32 ? C1 - c : 32) + 7) / 8;
+    for (int c = 0; c < C2; c += 32) ks_total += ((C2 - c < 32 ? C2 - c : 32) + 7) / 8;
+    const int n1t = (D1 + TM1 - 1) / TM1, n2t = (D2 + TM2 - 1) / TM2;
+    double best = 1e300;
+    int best_nt = 0, best_tz = 0;
+    for (int nt = 16; nt <= 192 && nt <= G.Npad; nt += 16) {
+      if (G.Npad % nt) continue;
+      for (int tz = 1; tz <= 4 && tz <= D0 && tz * nt <= 256; ++tz) {   // two accumulator sets in 512 TMEM columns
+        const long long tiles = (long long)B * ((D0 + tz - 1) / tz) * n1t * n2t * (G.Npad / nt);
+        const long long rounds = (tiles + 147) / 148;
+        // + issue overhead: exposed with a single issuing warp (tz == 1), mostly hidden with one warp per accumulator
+        const double mma = (nt / 2 > 32 + nt / 4 ? nt / 2 : 32 + nt / 4) + (tz == 1 ? 20.0 : 8.0);
+        // slabs are shared by up to 3 output planes: fewer planes per tile = more TMA traffic per MMA (mild penalty)
+        const double cost = rounds * (tz * 27.0 * ks_total * mma * (1.0 + 0.04 * (4 - tz)) + 2500.0);
+        if (cost < best * 0.999 || (cost < best * 1.001 && (tz > best_tz || (tz == best_tz && nt > best_nt)))) {
+          best = cost; best_nt = nt; best_tz = tz;
+        }
+      }
+    }
+    SSR_CHECK_ARG(best_nt > 0, "no tile shape");
+    G.NT = best_nt; G.TZ = best_tz;
+  }
   G.nNtiles = G.Npad / G.NT;
-  int tz = 256 / G.NT; if (tz > 4) tz = 4; if (tz > D0) tz = D0; if (tz < 1) tz = 1;   // two accumulator sets in 512 columns
-  G.TZ = tz;
   G.KG = (3 * 3 * G.NT * 128 <= 74 * 1024) ? 3 : 1;
   int cols = 2 * G.TZ * G.NT, pc = 32;
   while (pc < cols) pc <<= 1;
