@@ -101,6 +101,10 @@ long long ssr_conv3d_packed_size(int Cin1, int Cin2, int Cout, int mode);
 int ssr_conv3d_pack_weights_batch(const long long* jobs, int njobs, void* stream);
 int ssr_conv3d_fwd_tc(const float* x1, int C1, const float* x2, int C2, const float* wp, const float* bias, float* y,
                       int B, int d0, int d1, int d2, int Cout, int act, void* stream);
+/* Cin <= 32, Cout <= 32 (the full-resolution layers): the three d2 taps ride in the MMA N dimension; weights packed
+ * with mode 2 (forward) / 3 (data gradient: x = dy, Cout = the layer's Cin).  Same result contract as ssr_conv3d_fwd_tc. */
+int ssr_conv3d_fwd_tc_k2n(const float* x, int C, const float* wp, const float* bias, float* y, int B, int d0, int d1,
+                          int d2, int Cout, int act, void* stream);
 int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const float* dy, float* dw, float* db,
                         float* scratch, long long scratch_bytes, int B, int d0, int d1, int d2, int Cout,
                         void* stream);

@@ -1,4 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out; rm -f gpurun_out/unet_step_errors.txt
-timeout 900 python -m pytest tests/test_unet_gpu.py -m gpu -q -x 2>&1 | tail -3
-timeout 300 python scripts/layer_times.py 2>&1 | grep -v "^ *[0-9]* wgrad_tc\|wgrad_ref" | tee gpurun_out/layer_times2.txt
+timeout 300 python -m pytest tests/test_unet_gpu.py -m gpu -q -x -k "k2n_forward" 2>&1 | tail -15
+timeout 300 python scripts/profile_conv.py fwd24 5 2>&1 | tail -3
+SSR_NO_FWD_K2N=1 timeout 300 python scripts/profile_conv.py fwd24 5 2>&1 | tail -3

@@ -31,9 +31,14 @@ def run(name, reps):
         w = torch.randn((3, 3, 3, c1 + c2, co), device='cuda', generator=g) / np.sqrt(27 * (c1 + c2))
         b = torch.zeros(co, device='cuda')
         y = torch.empty((nv, co), device='cuda')
-        wp = torch.empty(lib.ssr_conv3d_packed_size(c1, c2, co, 0), device='cuda')
-        lib.ssr_conv3d_pack_weights(w, wp, c1, c2, co, 0, st)
-        fn = lambda: lib.ssr_conv3d_fwd_tc(x1, c1, x2, c2, wp, b, y, 1, *d, co, 1, st)
+        if c2 == 0 and c1 <= 32 and co <= 32 and not os.environ.get('SSR_NO_FWD_K2N'):
+            wp = torch.empty(lib.ssr_conv3d_packed_size(c1, 0, co, 2), device='cuda')
+            lib.ssr_conv3d_pack_weights(w, wp, c1, 0, co, 2, st)
+            fn = lambda: lib.ssr_conv3d_fwd_tc_k2n(x1, c1, wp, b, y, 1, *d, co, 1, st)
+        else:
+            wp = torch.empty(lib.ssr_conv3d_packed_size(c1, c2, co, 0), device='cuda')
+            lib.ssr_conv3d_pack_weights(w, wp, c1, c2, co, 0, st)
+            fn = lambda: lib.ssr_conv3d_fwd_tc(x1, c1, x2, c2, wp, b, y, 1, *d, co, 1, st)
     else:
         dy = torch.randn((nv, co), device='cuda', generator=g)
         if os.environ.get('SSR_CONST_DATA'):

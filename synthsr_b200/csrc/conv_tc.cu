@@ -495,6 +495,209 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Forward / data-gradient convolution for Cin <= 32, Cout <= 32 (the full-resolution 24-channel layers: half of the
+// forward + dgrad time).  With N = 32 the MMA is bound by reading the 128 x 8 A operand from shared memory (40 cycles
+// for 16 cycles of math), so the three d2 taps ride in N instead:
+//     P_j[v'] = sum_{k0,k1,ci} X[v' + (k0-1, k1-1, 0)][ci] * W[k0][k1][j][ci][:]        one MMA, N = 96 = (j, co)
+//     out[z, y, x] = P_0[z, y, x-1] + P_1[z, y, x] + P_2[z, y, x+1]                       (epilogue: lane shuffles)
+// One N = 96 MMA (56 cycles) replaces three N = 32 MMAs (120 cycles) and every X slab is loaded once, not three times.
+//   tile      8 (d1) x 16 (d2) input columns = 128 GEMM rows -> 8 x 14 outputs; the CTA walks a range of d0 planes
+//   A         slab = TMA box 32ch x 16 x 10 of plane p (K-major, SWIZZLE_128B); d1 tap k1 = descriptor + 2048 B
+//   B         all 27 taps of the layer (9 tiles of 96 rows x 128 B = 108 KB) stay resident in shared memory
+//   D         ring of four accumulators (96 TMEM columns each), one per output plane in flight; plane z takes the d0
+//             taps from slabs z-1, z, z+1.  MMA warp w owns ring slot w (one issuing warp per accumulator), the four
+//             epilogue warps drain finished planes while the next ones are being accumulated.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int KF_TM1 = 8, KF_TM2 = 16, KF_OUT2 = KF_TM2 - 2;
+constexpr int KF_SLAB_BYTES = (KF_TM1 + 2) * KF_TM2 * 128;       // 20480
+constexpr int KF_BTILE_BYTES = 96 * 128;                           // 12288 per (k0, k1)
+constexpr int KF_SA = 5, KF_NACC = 4, KF_N = 96;
+
+struct KfGeom {
+  int B, D0, D1, D2, Cout, act, nks;
+  int n1tiles, n2tiles, nzr, zlen;
+};
+
+__global__ void __launch_bounds__(288, 1)
+conv3d_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                     const float* __restrict__ bias, float* __restrict__ y, const KfGeom G) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = smem;
+  uint8_t* sA = sB + 9 * KF_BTILE_BYTES;
+  uint64_t* bars = (uint64_t*)(sA + (size_t)KF_SA * KF_SLAB_BYTES);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = bars + KF_SA;
+  uint64_t* accFull = bars + 2 * KF_SA;
+  uint64_t* accEmpty = accFull + KF_NACC;
+  uint64_t* fullB = accEmpty + KF_NACC;
+  uint32_t* tmem_slot = (uint32_t*)(fullB + 1);
+  float* sbias = (float*)(bars + 24);                    // 32 floats, zero padded
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < KF_SA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, 3); }   // planes p-1, p, p+1 read slab p
+    for (int i = 0; i < KF_NACC; ++i) { mbar_init(accFull + i, 1); mbar_init(accEmpty + i, 4); }
+    mbar_init(fullB, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (threadIdx.x < 32) sbias[threadIdx.x] = (bias && threadIdx.x < G.Cout) ? bias[threadIdx.x] : 0.f;
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_w); }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nitems = G.B * G.n1tiles * G.n2tiles * G.nzr;
+
+#define KF_DECODE(item)                                                          \
+  int t_ = (item);                                                                \
+  const int zr = t_ % G.nzr; t_ /= G.nzr;                                         \
+  const int t2 = t_ % G.n2tiles; t_ /= G.n2tiles;                                 \
+  const int t1 = t_ % G.n1tiles;                                                  \
+  const int b = t_ / G.n1tiles;                                                   \
+  const int x0 = t2 * KF_OUT2, y0 = t1 * KF_TM1;                                  \
+  const int zs = zr * G.zlen, ze = min(G.D0, zs + G.zlen);                        \
+  const int pmin = max(zs - 1, 0), pmax = min(ze, G.D0 - 1);                      \
+  (void)x0; (void)y0; (void)b; (void)pmax;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      mbar_expect_tx(fullB, 9 * KF_BTILE_BYTES);
+      for (int t = 0; t < 9; ++t) tma_load_2d(&map_w, fullB, sB + (size_t)t * KF_BTILE_BYTES, 0, t * KF_N);
+      int seq = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        KF_DECODE(item)
+        for (int p = pmin; p <= pmax; ++p, ++seq) {
+          const int slot = seq % KF_SA;
+          mbar_wait(emptyA + slot, ((seq / KF_SA) & 1) ^ 1);
+          mbar_expect_tx(fullA + slot, KF_SLAB_BYTES);
+          tma_load_5d(&map_x, fullA + slot, sA + (size_t)slot * KF_SLAB_BYTES, 0, x0 - 1, y0 - 1, p, b);
+        }
+      }
+    }
+  } else if (warp <= KF_NACC) {
+    // ================================ MMA issuers: warp w owns accumulator ring slot w - 1 ================================
+    const int w = warp - 1;
+    const uint32_t idesc = make_idesc_tf32(KF_N);
+    const uint32_t a_base = desc_lo(smem_u32(sA), 16), b_base = desc_lo(smem_u32(sB), 16);
+    const uint32_t dcol = tmem_base + (uint32_t)(w * KF_N);
+    const int nks = G.nks;
+    mbar_wait(fullB, 0);
+    int seq_base = 0;
+    uint32_t uses = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      KF_DECODE(item)
+      for (int z = zs + w; z < ze; z += KF_NACC) {
+        mbar_wait(accEmpty + w, (uses & 1u) ^ 1u);            // epilogue has drained this ring slot
+        tc_fence_after();
+        uint32_t acc = 0u;
+#pragma unroll
+        for (int k0 = 0; k0 < 3; ++k0) {
+          const int p = z + k0 - 1;
+          if (p < 0 || p >= G.D0) continue;                     // zero padding along d0: tap contributes nothing
+          const int seq = seq_base + (p - pmin), slot = seq % KF_SA;
+          mbar_wait(fullA + slot, (seq / KF_SA) & 1);
+          // slab p is released by three arrivals (planes p-1, p, p+1); planes outside this item's range never come
+          const int extra = k0 == 0 ? (z == zs ? 2 : 0) : k0 == 1 ? ((z == zs) + (z == ze - 1)) : (z == ze - 1 ? 2 : 0);
+          if (elect_one()) {
+            uint32_t alo = a_base + (uint32_t)slot * (KF_SLAB_BYTES >> 4);
+            uint32_t blo = b_base + (uint32_t)(k0 * 3) * (KF_BTILE_BYTES >> 4);
+#pragma unroll
+            for (int k1 = 0; k1 < 3; ++k1) {
+              if (nks == 4) umma_chain_k<4>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+              else if (nks == 3) umma_chain_k<3>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+              else if (nks == 2) umma_chain_k<2>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+              else umma_chain_k<1>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+              acc = 1u;
+              alo += (uint32_t)(KF_TM2 * 128 >> 4);
+              blo += (uint32_t)(KF_BTILE_BYTES >> 4);
+            }
+            umma_commit(emptyA + slot);
+          }
+          acc = 1u;
+          if (lane == 0)
+            for (int e = 0; e < extra; ++e) mbar_arrive(emptyA + slot);
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit(accFull + w);
+        __syncwarp();
+        ++uses;
+      }
+      seq_base += pmax - pmin + 1;
+    }
+  } else {
+    // ================================ epilogue (last four warps) ================================
+    const int q = warp & 3;                         // TMEM lane quarter of this warp
+    const int r = q * 32 + lane;                    // GEMM row = (d1 row r / 16, input column r % 16)
+    const int xin = r & 15, yl = r >> 4;
+    const bool vec_ok = (G.Cout & 3) == 0;
+    uint32_t par = 0;                               // phase bit per ring slot
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      KF_DECODE(item)
+      const int i1 = y0 + yl, i2 = x0 - 1 + xin;
+      const bool store_ok = xin >= 1 && xin <= KF_OUT2 && i1 < G.D1 && i2 < G.D2;
+      for (int z = zs; z < ze; ++z) {
+        const int slot = (z - zs) & (KF_NACC - 1);
+        mbar_wait(accFull + slot, (par >> slot) & 1u);
+        par ^= 1u << slot;
+        tc_fence_after();
+        float* orow = y + ((((long long)b * G.D0 + z) * G.D1 + i1) * G.D2 + i2) * G.Cout;
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * KF_N);
+        for (int cb = 0; cb < 32; cb += 16) {
+          if (cb >= G.Cout) break;                   // warp-uniform
+          uint32_t v0[16], v1[16], v2[16];
+          tmem_ld16(tbase + (uint32_t)cb, v0);
+          tmem_ld16(tbase + (uint32_t)(32 + cb), v1);
+          tmem_ld16(tbase + (uint32_t)(64 + cb), v2);
+          tmem_ld_wait();
+          float o[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[e]), 1);      // P_0 at input column x - 1
+            const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[e]), 1);   // P_2 at input column x + 1
+            o[e] = left + __uint_as_float(v1[e]) + right + sbias[cb + e];
+          }
+          if (G.act) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float neg = __expf(fminf(o[e], 0.f)) - 1.f;
+              o[e] = o[e] > 0.f ? o[e] : neg;
+            }
+          }
+          if (!store_ok) continue;
+          const int nvalid = G.Cout - cb;
+          if (nvalid >= 16 && vec_ok) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 4)
+              *reinterpret_cast<float4*>(orow + cb + e) = make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]);
+          } else if (nvalid >= 8 && vec_ok) {
+            *reinterpret_cast<float4*>(orow + cb) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(orow + cb + 4) = make_float4(o[4], o[5], o[6], o[7]);
+#pragma unroll
+            for (int e = 8; e < 16; ++e)
+              if (e < nvalid) orow[cb + e] = o[e];
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (e < nvalid) orow[cb + e] = o[e];
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(accEmpty + slot);
+      }
+    }
+  }
+#undef KF_DECODE
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // weight gradient on tcgen05:  dW[k0][k1][k2][ci][co] += sum_v X[v + (k0,k1,k2) - 1][ci] * dY[v][co]
 //
 //   GEMM   D[M x N] += A[M x K] * B[N x K]^T   with K = 8 voxels per instruction, both operands MN-major:
@@ -1011,7 +1214,7 @@ mma_microbench_kernel(float* __restrict__ out, int N, int nacc, int chain, int i
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pack_weights_body(const float* __restrict__ w, float* __restrict__ wp, int C1, int C2,
                                                   int Cout, int mode, int Npad, int nchunks, int nch1, int round_rn) {
-  const long long total = (long long)nchunks * 27 * Npad * 32;
+  const long long total = mode >= 2 ? 9LL * 96 * 32 : (long long)nchunks * 27 * Npad * 32;
   const int Cin = C1 + C2;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int s = (int)(t & 31);
@@ -1022,6 +1225,16 @@ __device__ __forceinline__ void pack_weights_body(const float* __restrict__ w, f
     const int k2 = (int)(r % 3);
     const int ch = (int)(r / 3);
     float val = 0.f;
+    if (mode >= 2) {
+      // d2-taps-in-N layout of conv3d_tc_k2n_kernel: t = ((k0 * 3 + k1) * 96 + (k2 * 32 + n)) * 32 + s, one 32-channel chunk
+      long long r2 = t >> 5;
+      const int nn = (int)(r2 % 96); r2 /= 96;
+      const int q1 = (int)(r2 % 3);
+      const int q0 = (int)(r2 / 3);
+      const int q2 = nn >> 5, no = nn & 31;
+      if (mode == 2) { if (s < C1 && no < Cout) val = w[((long long)((q0 * 3 + q1) * 3 + q2) * Cin + s) * Cout + no]; }
+      else { if (s < Cout && no < Cin) val = w[((long long)(((2 - q0) * 3 + (2 - q1)) * 3 + (2 - q2)) * Cin + no) * Cout + s]; }
+    } else
     if (mode == 0) {
       int c;   // concat channel index
       if (ch < nch1) c = ch * 32 + s < C1 ? ch * 32 + s : -1;
@@ -1048,7 +1261,8 @@ __global__ void pack_weights_batch_kernel(const long long* __restrict__ jobs, in
   const long long* j = jobs + (long long)blockIdx.y * 6;
   const int C1 = (int)j[2], C2 = (int)j[3], Cout = (int)j[4], mode = (int)j[5];
   int Npad, nch, nch1;
-  if (mode == 0) { Npad = (Cout + 15) / 16 * 16; nch1 = (C1 + 31) / 32; nch = nch1 + (C2 + 31) / 32; }
+  if (mode >= 2) { Npad = 96; nch = 1; nch1 = 1; }
+  else if (mode == 0) { Npad = (Cout + 15) / 16 * 16; nch1 = (C1 + 31) / 32; nch = nch1 + (C2 + 31) / 32; }
   else { Npad = (C1 + C2 + 15) / 16 * 16; nch = (Cout + 31) / 32; nch1 = nch; }
   pack_weights_body(reinterpret_cast<const float*>(j[0]), reinterpret_cast<float*>(j[1]), C1, C2, Cout, mode, Npad, nch,
                     nch1, round_rn);
@@ -1135,6 +1349,7 @@ int ssr_conv3d_pack_weights_batch(const long long* jobs, int njobs, void* stream
   return SSR_OK;
 }
 long long ssr_conv3d_packed_size(int Cin1, int Cin2, int Cout, int mode) {
+  if (mode >= 2) return 9LL * 96 * 32;
   if (mode == 0) {
     const int nch = (Cin1 + 31) / 32 + (Cin2 + 31) / 32;
     return (long long)nch * 27 * round_up(Cout, 16) * 32;
@@ -1144,11 +1359,13 @@ long long ssr_conv3d_packed_size(int Cin1, int Cin2, int Cout, int mode) {
 }
 
 int ssr_conv3d_pack_weights(const float* w, float* wp, int Cin1, int Cin2, int Cout, int mode, void* stream) {
-  SSR_CHECK_ARG(w && wp && Cin1 > 0 && Cin2 >= 0 && Cout > 0 && (mode == 0 || mode == 1), "pack args");
+  SSR_CHECK_ARG(w && wp && Cin1 > 0 && Cin2 >= 0 && Cout > 0 && mode >= 0 && mode <= 3, "pack args");
+  SSR_CHECK_ARG(mode < 2 || (Cin2 == 0 && Cin1 <= 32 && Cout <= 32), "k2n packing needs Cin <= 32, Cout <= 32");
   int Npad, nch, nch1;
-  if (mode == 0) { Npad = round_up(Cout, 16); nch1 = (Cin1 + 31) / 32; nch = nch1 + (Cin2 + 31) / 32; }
+  if (mode >= 2) { Npad = 96; nch = 1; nch1 = 1; }
+  else if (mode == 0) { Npad = round_up(Cout, 16); nch1 = (Cin1 + 31) / 32; nch = nch1 + (Cin2 + 31) / 32; }
   else { Npad = round_up(Cin1 + Cin2, 16); nch = (Cout + 31) / 32; nch1 = nch; }
-  const long long total = (long long)nch * 27 * Npad * 32;
+  const long long total = mode >= 2 ? 9LL * 96 * 32 : (long long)nch * 27 * Npad * 32;
   long long g = (total + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
   pack_weights_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(w, wp, Cin1, Cin2, Cout, mode, Npad, nch, nch1,
@@ -1243,6 +1460,55 @@ int ssr_conv3d_fwd_tc(const float* x1, int C1, const float* x2, int C2, const fl
   }
   const unsigned grid = (unsigned)(ntiles < num_sms ? ntiles : num_sms);       // persistent: one CTA per SM
   conv3d_tc_kernel<<<grid, 32 * (5 + G.TZ), smem, (cudaStream_t)stream>>>(m1, m2, mw, bias, y, G);   // TMA + TZ MMA + 4 epilogue warps
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
+// y = act(conv3d(x, w) + bias) for Cin <= 32, Cout <= 32 with the weights packed in mode 2 (forward) or 3 (data
+// gradient: x = dy, "Cout" = the layer's Cin).  See conv3d_tc_k2n_kernel.
+int ssr_conv3d_fwd_tc_k2n(const float* x, int C, const float* wp, const float* bias, float* y, int B, int D0, int D1,
+                          int D2, int Cout, int act, void* stream) {
+  SSR_CHECK_ARG(x && wp && y && B > 0 && D0 > 0 && D1 > 0 && D2 > 0, "pointers/shape");
+  SSR_CHECK_ARG(C > 0 && C <= 32 && C % 8 == 0 && Cout > 0 && Cout <= 32, "k2n forward needs Cin <= 32 (multiple of 8), Cout <= 32");
+  SSR_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 127) == 0, "alignment");
+  KfGeom G;
+  memset(&G, 0, sizeof(G));
+  G.B = B; G.D0 = D0; G.D1 = D1; G.D2 = D2; G.Cout = Cout; G.act = act; G.nks = C / 8;
+  G.n1tiles = (D1 + KF_TM1 - 1) / KF_TM1; G.n2tiles = (D2 + KF_OUT2 - 1) / KF_OUT2;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    SSR_CHECK_CUDA(cudaGetDevice(&dev));
+    SSR_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  // d0 ranges: long enough that the two halo slabs are a small overhead, short enough for an even static round-robin:
+  // pick the split count with the fewest (rounds x planes per CTA)
+  const long long cols = (long long)B * G.n1tiles * G.n2tiles;
+  long long best = -1; int best_nzr = 1;
+  for (int nzr = 1; nzr <= D0; ++nzr) {
+    const int zlen = (D0 + nzr - 1) / nzr;
+    if (zlen < 8 && nzr > 1) break;
+    const long long items = cols * ((D0 + zlen - 1) / zlen);
+    const long long cost = ((items + num_sms - 1) / num_sms) * (zlen + 2);
+    if (best < 0 || cost < best) { best = cost; best_nzr = (D0 + zlen - 1) / zlen; G.zlen = zlen; }
+  }
+  G.nzr = best_nzr;
+  CUtensorMap mx, mw;
+  int rc = make_map_act(&mx, x, C, B, D0, D1, D2, KF_TM1 + 2, CU_TENSOR_MAP_SWIZZLE_128B, KF_TM2);
+  if (rc) return rc;
+  rc = make_map_w(&mw, wp, 9 * KF_N, KF_N);
+  if (rc) return rc;
+  const size_t smem = 1024 + 9 * (size_t)KF_BTILE_BYTES + (size_t)KF_SA * KF_SLAB_BYTES + 24 * 8 + 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_k2n_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const long long nitems = cols * G.nzr;
+  SSR_CHECK_ARG(nitems < (1LL << 31), "grid too large");
+  const unsigned grid = (unsigned)(nitems < num_sms ? nitems : num_sms);
+  conv3d_tc_k2n_kernel<<<grid, 288, smem, (cudaStream_t)stream>>>(mx, mw, bias, y, G);
   SSR_COUNT_LAUNCH();
   SSR_CHECK_LAUNCH();
   return SSR_OK;

@@ -58,6 +58,7 @@ class UNet3D:
         self.wgrad_tc = conv_impl == 'tc'
         self.prof = None          # list of (kind, flops, start_event, end_event) when profiling is enabled
         self.overlap_wgrad = os.environ.get('SSR_NO_WGRAD_OVERLAP') is None
+        self.fwd_k2n = os.environ.get('SSR_NO_FWD_K2N') is None
         self._side, self._side_busy, self._hp = None, False, None
         self.device = torch.device(device)
         for d in self.dims:
@@ -204,7 +205,11 @@ class UNet3D:
     def _conv_fwd_impl(self, tc, name, x1, c1, x2, c2, y, l, cout, act):
         st = stream_ptr()
         d = self.ldims[l]
-        if tc:
+        if tc and self.fwd_k2n and c2 == 0 and c1 <= 32 and cout <= 32:
+            # full-resolution 24-channel layers: d2 taps in the MMA N dimension (conv3d_tc_k2n_kernel)
+            lib.ssr_conv3d_fwd_tc_k2n(x1, c1, self._packed_w(name, 2, c1, 0, cout), self.p[name + '/bias'], y,
+                                      self.B, *d, cout, act, st)
+        elif tc:
             lib.ssr_conv3d_fwd_tc(x1, c1, x2, c2, self._packed_w(name, 0, c1, c2, cout), self.p[name + '/bias'], y,
                                   self.B, *d, cout, act, st)
         else:
@@ -219,7 +224,9 @@ class UNet3D:
     def _conv_dgrad_impl(self, tc, name, dy, dx, l, cin, cout):
         st = stream_ptr()
         d = self.ldims[l]
-        if tc:
+        if tc and self.fwd_k2n and cin <= 32 and cout <= 32:
+            lib.ssr_conv3d_fwd_tc_k2n(dy, cout, self._packed_w(name, 3, cin, 0, cout), None, dx, self.B, *d, cin, 0, st)
+        elif tc:
             # data gradient = forward convolution of dy with the flipped / transposed kernel
             lib.ssr_conv3d_fwd_tc(dy, cout, None, 0, self._packed_w(name, 1, cin, 0, cout), None, dx, self.B, *d, cin,
                                   0, st)

@@ -272,3 +272,42 @@ def test_small_cin_wgrad_kernel():
         ref = w.grad.permute(2, 3, 4, 1, 0).reshape(-1)
         err = (dw.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
         assert err < 1e-5, (d, cin, co, err)
+
+
+def test_tc_k2n_forward_and_dgrad_match_float64():
+    """d2-taps-in-N kernel (Cin, Cout <= 32): forward (+bias, ELU) and data gradient against a float64 convolution of the
+    identically rounded operands; sizes that are not multiples of the 8 x 14 tile or of the d0 range length."""
+    from synthsr_b200._lib import lib, stream_ptr
+    rng = np.random.default_rng(5)
+    for (d, cin, co) in [([16, 16, 16], 24, 24), ([9, 11, 30], 24, 24), ([21, 8, 14], 32, 32), ([5, 19, 17], 8, 16),
+                         ([40, 24, 29], 24, 24)]:
+        nv = int(np.prod(d))
+        x = torch.from_numpy(rng.normal(size=(nv, cin)).astype(np.float32)).cuda()
+        w = torch.from_numpy((rng.normal(size=(3, 3, 3, cin, co)) / np.sqrt(27 * cin)).astype(np.float32)).cuda()
+        b = torch.from_numpy(rng.normal(size=co).astype(np.float32)).cuda()
+        st = stream_ptr()
+        # forward
+        y = torch.full((nv, co), float('nan'), dtype=torch.float32, device='cuda')
+        wp = torch.empty(lib.ssr_conv3d_packed_size(cin, 0, co, 2), dtype=torch.float32, device='cuda')
+        lib.ssr_conv3d_pack_weights(w, wp, cin, 0, co, 2, st)
+        lib.ssr_conv3d_fwd_tc_k2n(x, cin, wp, b, y, 1, *d, co, 1, st)
+        torch.cuda.synchronize()
+        xr = _rne_tf32(x).double().cpu().view(1, *d, cin).permute(0, 4, 1, 2, 3)
+        wr = _rna_tf32(w).double().cpu().permute(4, 3, 0, 1, 2)
+        y64 = torch.nn.functional.elu(torch.nn.functional.conv3d(xr, wr, b.double().cpu(), padding=1))
+        y64 = y64.permute(0, 2, 3, 4, 1).reshape(nv, co)
+        assert not torch.isnan(y).any(), ('fwd nan', d, cin, co)
+        err = (y.double().cpu() - y64).abs().max().item() / y64.abs().max().item()
+        assert err < 2e-5, ('fwd', d, cin, co, err)
+        # data gradient: dx = conv(dy, flipped / transposed kernel), no bias, no activation
+        dy = torch.from_numpy(rng.normal(size=(nv, co)).astype(np.float32)).cuda()
+        dx = torch.full((nv, cin), float('nan'), dtype=torch.float32, device='cuda')
+        wp3 = torch.empty(lib.ssr_conv3d_packed_size(cin, 0, co, 3), dtype=torch.float32, device='cuda')
+        lib.ssr_conv3d_pack_weights(w, wp3, cin, 0, co, 3, st)
+        lib.ssr_conv3d_fwd_tc_k2n(dy, co, wp3, None, dx, 1, *d, cin, 0, st)
+        torch.cuda.synchronize()
+        dyr = _rne_tf32(dy).double().cpu().view(1, *d, co).permute(0, 4, 1, 2, 3)
+        dx64 = torch.nn.functional.conv_transpose3d(dyr, wr, padding=1).permute(0, 2, 3, 4, 1).reshape(nv, cin)
+        assert not torch.isnan(dx).any(), ('dgrad nan', d, cin, co)
+        err = (dx.double().cpu() - dx64).abs().max().item() / dx64.abs().max().item()
+        assert err < 2e-5, ('dgrad', d, cin, co, err)
