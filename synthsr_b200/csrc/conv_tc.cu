@@ -117,6 +117,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor, K-major, SWIZZLE_128B: 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
@@ -518,7 +523,7 @@ struct KfGeom {
   int n1tiles, n2tiles, nzr, zlen;
 };
 
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(416, 1)
 conv3d_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                      const float* __restrict__ bias, float* __restrict__ y, const KfGeom G) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -629,59 +634,55 @@ conv3d_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       seq_base += pmax - pmin + 1;
     }
   } else {
-    // ================================ epilogue (last four warps) ================================
+    // ================================ epilogue (last eight warps: two sets of four) ================================
+    // Set h drains the planes with (z - zs) % 2 == h, so two planes are in the epilogue at any time; each warp of a set
+    // owns one TMEM lane quarter.  Channels are handled in blocks of 8 (24 = 3 blocks, no padded work).
     const int q = warp & 3;                         // TMEM lane quarter of this warp
+    const int h = (warp - (KF_NACC + 1)) >> 2;      // epilogue set 0 / 1
     const int r = q * 32 + lane;                    // GEMM row = (d1 row r / 16, input column r % 16)
     const int xin = r & 15, yl = r >> 4;
     const bool vec_ok = (G.Cout & 3) == 0;
+    const int nblk8 = (G.Cout + 7) >> 3;
     uint32_t par = 0;                               // phase bit per ring slot
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       KF_DECODE(item)
       const int i1 = y0 + yl, i2 = x0 - 1 + xin;
       const bool store_ok = xin >= 1 && xin <= KF_OUT2 && i1 < G.D1 && i2 < G.D2;
-      for (int z = zs; z < ze; ++z) {
+      for (int z = zs + h; z < ze; z += 2) {
         const int slot = (z - zs) & (KF_NACC - 1);
         mbar_wait(accFull + slot, (par >> slot) & 1u);
         par ^= 1u << slot;
         tc_fence_after();
         float* orow = y + ((((long long)b * G.D0 + z) * G.D1 + i1) * G.D2 + i2) * G.Cout;
         const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * KF_N);
-        for (int cb = 0; cb < 32; cb += 16) {
-          if (cb >= G.Cout) break;                   // warp-uniform
-          uint32_t v0[16], v1[16], v2[16];
-          tmem_ld16(tbase + (uint32_t)cb, v0);
-          tmem_ld16(tbase + (uint32_t)(32 + cb), v1);
-          tmem_ld16(tbase + (uint32_t)(64 + cb), v2);
+        for (int cb = 0; cb < nblk8 * 8; cb += 8) {
+          uint32_t v0[8], v1[8], v2[8];
+          tmem_ld8(tbase + (uint32_t)cb, v0);
+          tmem_ld8(tbase + (uint32_t)(32 + cb), v1);
+          tmem_ld8(tbase + (uint32_t)(64 + cb), v2);
           tmem_ld_wait();
-          float o[16];
+          float o[8];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
+          for (int e = 0; e < 8; ++e) {
             const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[e]), 1);      // P_0 at input column x - 1
             const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[e]), 1);   // P_2 at input column x + 1
             o[e] = left + __uint_as_float(v1[e]) + right + sbias[cb + e];
           }
           if (G.act) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
+            for (int e = 0; e < 8; ++e) {
               const float neg = __expf(fminf(o[e], 0.f)) - 1.f;
               o[e] = o[e] > 0.f ? o[e] : neg;
             }
           }
           if (!store_ok) continue;
           const int nvalid = G.Cout - cb;
-          if (nvalid >= 16 && vec_ok) {
-#pragma unroll
-            for (int e = 0; e < 16; e += 4)
-              *reinterpret_cast<float4*>(orow + cb + e) = make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]);
-          } else if (nvalid >= 8 && vec_ok) {
+          if (nvalid >= 8 && vec_ok) {
             *reinterpret_cast<float4*>(orow + cb) = make_float4(o[0], o[1], o[2], o[3]);
             *reinterpret_cast<float4*>(orow + cb + 4) = make_float4(o[4], o[5], o[6], o[7]);
-#pragma unroll
-            for (int e = 8; e < 16; ++e)
-              if (e < nvalid) orow[cb + e] = o[e];
           } else {
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
+            for (int e = 0; e < 8; ++e)
               if (e < nvalid) orow[cb + e] = o[e];
           }
         }
@@ -1508,7 +1509,7 @@ int ssr_conv3d_fwd_tc_k2n(const float* x, int C, const float* wp, const float* b
   const long long nitems = cols * G.nzr;
   SSR_CHECK_ARG(nitems < (1LL << 31), "grid too large");
   const unsigned grid = (unsigned)(nitems < num_sms ? nitems : num_sms);
-  conv3d_tc_k2n_kernel<<<grid, 288, smem, (cudaStream_t)stream>>>(mx, mw, bias, y, G);
+  conv3d_tc_k2n_kernel<<<grid, 416, smem, (cudaStream_t)stream>>>(mx, mw, bias, y, G);   // TMA + 4 MMA + 8 epilogue warps
   SSR_COUNT_LAUNCH();
   SSR_CHECK_LAUNCH();
   return SSR_OK;
