@@ -297,117 +297,6 @@ def main():
                                  'launches_per_step': agg[k][2] // 2} for k in sorted(agg)},
                 'conv_share_of_step': (sum(v[0] for v in agg.values()) / 2) / (ms / args.steps),
                 'note': 'per-kind times are measured with the weight-gradient overlap disabled (serialised launches)'}
-    out = {'metric': metric, 'value': vps, 'unit': 'volumes/s', 'n_gpus': args.gpus, 'steps': args.steps,
-               'warmup': warm, 'ms_per_step': 1e3 / vps, 'higher_is_better': True, 'scaling': 'weak',
-               'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config, 'impl': 'reference',
-               'cpu_baseline': {'value': vps, 'unit': 'volumes/s', 'cores': threads, 'kind': 'port',
-                                'sample': 'oracle restatement (NumPy generator + torch-CPU fp32 U-Net step) on %d^3 '
-                                          'sub-volumes, scaled by voxel count to %d^3; reference TF-CPU: not run '
-                                          '(TensorFlow 2.0 not installable)' % (sample, args.size)},
-               'e2e': {'value': vps, 'unit': 'volumes/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-        print(json.dumps(out))
-        return
-
-    import torch
-    import torch.distributed as dist
-    from synthsr_b200._lib import lib
-    from synthsr_b200.generator import GeneratorPlan
-    from synthsr_b200.trainer import TrainingEngine
-
-    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    maps, pm, ps, gl, gc = make_inputs(args.size, 2, seed=rank)
-    plan = GeneratorPlan([args.size] * 3, True, 0, gl, None, 1., None, **TRAINING_DEFAULTS)
-    eng = TrainingEngine(plan, batchsize=1, conv_impl=args.conv_impl, seed=0, rank=rank, world_size=world)
-    dev_maps = [torch.from_numpy(m[None]).cuda() for m in maps]
-    pinned = [torch.from_numpy(m[None]).pin_memory() for m in maps]
-    rng = np.random.default_rng(1234 + rank)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    host_loss = [torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(2)]
-    lab_dev = [torch.empty_like(dev_maps[0]) for _ in range(2)]
-    loss_ev = [torch.cuda.Event() for _ in range(2)]
-
-    def run_steps(n, host_inputs):
-        """host_inputs (e2e): every step copies its label map from pinned host memory and reads a loss back to the host;
-        the read-back of step i is consumed while step i+1 is being enqueued (one step of lag, like a logging callback)."""
-        loss = None
-        for i in range(n):
-            m, s = draw_gmm(rng, pm, ps, gc)
-            if host_inputs:
-                lab = lab_dev[i % 2]
-                lab.copy_(pinned[i % len(pinned)], non_blocking=True)          # H2D of this step's input, in-stream
-                host_loss[i % 2].copy_(eng.train_step(lab, m, s), non_blocking=True)
-                loss_ev[i % 2].record()
-                if i > 0:
-                    loss_ev[(i - 1) % 2].synchronize()
-                    loss = float(host_loss[(i - 1) % 2][0])
-            else:
-                loss = eng.train_step(dev_maps[i % len(dev_maps)], m, s)
-        if host_inputs and n > 0:
-            loss_ev[(n - 1) % 2].synchronize()
-            loss = float(host_loss[(n - 1) % 2][0])
-            assert np.isfinite(loss), 'loss is not finite'
-        return loss
-
-    def timed(n, host_inputs):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        l0 = lib.ssr_launch_count()
-        e0.record()
-        run_steps(n, host_inputs)
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item(), lib.ssr_launch_count() - l0
-
-    run_steps(max(args.warmup, 3), False)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ms, launches = timed(args.steps, False)
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
-    value = world * args.steps / (ms / 1e3)
-    run_steps(max(args.warmup, 3), True)              # the host-buffer path gets the same warm-up as the device path
-    sg_before = eng.gen.stage.bytes_moved
-    ms_e2e, _ = timed(args.steps, True)
-    e2e = world * args.steps / (ms_e2e / 1e3)
-    h2d = maps[0].nbytes + (eng.gen.stage.bytes_moved - sg_before) // max(args.steps, 1)
-
-    # ---- roofline of the dominant kernel class: live CUDA-event timing of every convolution launch ------------
-    eng.net.prof = []
-    run_steps(2, False)
-    torch.cuda.synchronize()
-    agg = {}
-    for kind, fl, a, b in eng.net.prof:
-        t, f, n = agg.get(kind, (0., 0., 0))
-        agg[kind] = (t + a.elapsed_time(b), f + fl, n + 1)
-    eng.net.prof = None
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-    except Exception:
-        pass
-    peak = peaks.get('bf16_tflops_sustained', 1590.0)
-    peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained; TF32 runs at half the bf16 rate)' if peaks else \
-        'fallback 1590 TF/s bf16 (B200_PROFILING.md)'
-    tc_ms = sum(agg[k][0] for k in agg if k.endswith('_tc'))
-    tc_fl = sum(agg[k][1] for k in agg if k.endswith('_tc'))
-    achieved = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.
-    roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-                'traffic': None, 'peak_source': peak_src, 'kernel': 'conv3d_tc_kernel + wgrad_tc_kernel (tcgen05 kind::tf32)',
-                'frac_of_tf32_peak': achieved / (peak / 2),
-                'per_kind': {k: {'ms_per_step': agg[k][0] / 2, 'tflops': agg[k][1] / (agg[k][0] * 1e-3) / 1e12 if agg[k][0] else 0.,
-                                 'launches_per_step': agg[k][2] // 2} for k in sorted(agg)},
-                'conv_share_of_step': (sum(v[0] for v in agg.values()) / 2) / (ms / args.steps)}
     out = {'metric': metric, 'value': value, 'unit': 'volumes/s', 'n_gpus': args.gpus, 'steps': args.steps,
            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
            'vs_baseline': None, 'dtype': 'tf32' if args.conv_impl == 'tc' else 'f32', 'data': 'synthetic',
