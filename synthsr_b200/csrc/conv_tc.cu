@@ -1058,6 +1058,219 @@ wgrad_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Persistent weight gradient (same MMA scheme as wgrad_tc_k2n_kernel).  A *unit* is (32-channel input chunk, 32 output
+// channels) = one 3 x 96 x 128 accumulator set; its work is the list of (spatial tile, d0 plane) pairs.  The global list
+// units x tiles x planes is cut into gridDim.x equal contiguous ranges, so every CTA does the same number of plane
+// steps (no tail wave), keeps accumulating in TMEM across tiles, and flushes to dW with atomics once per unit it touches
+// (normally once or twice per CTA instead of once per 8-80 planes: the flush was up to half of the CTA time on the
+// 40^3 and deeper layers).
+// ---------------------------------------------------------------------------------------------------------
+struct WpSeg { int u, tile, za, zb; bool unit_last; long long gnext; };
+
+__device__ __forceinline__ WpSeg wp_segment(long long g, long long g1, long long W, int D0) {
+  WpSeg s;
+  s.u = (int)(g / W);
+  const long long w = g - (long long)s.u * W;
+  s.tile = (int)(w / D0);
+  s.za = (int)(w - (long long)s.tile * D0);
+  long long e = (long long)s.u * W + (long long)(s.tile + 1) * D0;
+  if (e > g1) e = g1;
+  s.zb = s.za + (int)(e - g);
+  s.unit_last = e == g1 || e == (long long)(s.u + 1) * W;
+  s.gnext = e;
+  return s;
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(WK_THREADS, 1)
+wgrad_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_x2,
+                           const __grid_constant__ CUtensorMap map_dy, float* __restrict__ dw, const WgGeom G) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + (size_t)WK_SA * SLAB_BYTES;
+  uint64_t* bars = (uint64_t*)(sB + (size_t)WK_SB * WK_BSTAGE);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = bars + WK_SA;
+  uint64_t* fullB = bars + 2 * WK_SA;
+  uint64_t* emptyB = fullB + WK_SB;
+  uint64_t* accFull = emptyB + WK_SB;
+  uint64_t* accEmpty = accFull + 1;
+  uint32_t* tmem_slot = (uint32_t*)(accEmpty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int ntile = G.B * G.n1tiles * G.n2tiles;
+  const long long W = (long long)ntile * G.D0;                    // plane steps per unit
+  const long long T = W * G.nchunks * G.nNtiles;
+  const long long g0 = T * blockIdx.x / gridDim.x, g1 = T * (blockIdx.x + 1) / gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < WK_SA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, 3); }
+    for (int i = 0; i < WK_SB; ++i) { mbar_init(fullB + i, 1); mbar_init(emptyB + i, 3); }
+    mbar_init(accFull, 3);
+    mbar_init(accEmpty, 4);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+#define WP_TILE(tile)                                                      \
+  int tt_ = (tile);                                                         \
+  const int t2 = tt_ % G.n2tiles; tt_ /= G.n2tiles;                         \
+  const int t1 = tt_ % G.n1tiles;                                           \
+  const int b = tt_ / G.n1tiles;                                            \
+  const int x0 = t2 * TM2, y0 = t1 * TM1;                                   \
+  (void)x0; (void)y0; (void)b;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int seqA = 0, seqB = 0;
+      for (long long g = g0; g < g1;) {
+        const WpSeg sg = wp_segment(g, g1, W, G.D0);
+        g = sg.gnext;
+        const int ch = sg.u / G.nNtiles, n0 = (sg.u % G.nNtiles) * 32;
+        const CUtensorMap* mx = G.chunk_src[ch] ? &map_x2 : &map_x1;
+        const int c0 = G.chunk_c0[ch];
+        WP_TILE(sg.tile)
+        const int pmin = max(sg.za - 1, 0), pmax = min(sg.zb, G.D0 - 1);
+        int next_a = pmin;
+        for (int zo = sg.za; zo < sg.zb; ++zo) {
+          const int need = min(zo + 1, pmax);
+          for (; next_a <= need; ++next_a, ++seqA) {
+            const int sa = seqA % WK_SA;
+            mbar_wait(emptyA + sa, ((seqA / WK_SA) & 1) ^ 1);
+            mbar_expect_tx(fullA + sa, SLAB_BYTES);
+            tma_load_5d(mx, fullA + sa, sA + (size_t)sa * SLAB_BYTES, c0, x0, y0 - 1, next_a, b);
+          }
+          const int sb = seqB % WK_SB;
+          mbar_wait(emptyB + sb, ((seqB / WK_SB) & 1) ^ 1);
+          mbar_expect_tx(fullB + sb, WK_BSTAGE);
+          tma_load_5d(&map_dy, fullB + sb, sB + (size_t)sb * WK_BSTAGE, n0, x0 - 1, y0, zo, b);
+          ++seqB;
+        }
+      }
+    }
+  } else if (warp <= 3) {
+    // ================================ MMA issuer for d0 tap k0 = warp - 1 (accumulator k0) ================================
+    const int k0 = warp - 1;
+    const uint32_t idesc = make_idesc_tf32(WK_N) | (1u << 15) | (1u << 16);
+    const uint32_t a_base = desc_lo(smem_u32(sA), 1024), b_base = desc_lo(smem_u32(sB), 128);
+    const uint32_t dcol = tmem_base + (uint32_t)(k0 * WK_N);
+    int seqA_base = 0, seqB = 0;
+    uint32_t acc = 0u, flushes = 0u;
+    for (long long g = g0; g < g1;) {
+      const WpSeg sg = wp_segment(g, g1, W, G.D0);
+      g = sg.gnext;
+      WP_TILE(sg.tile)
+      const int nrows = min(TM1, G.D1 - y0);
+      const int pmin = max(sg.za - 1, 0), pmax = min(sg.zb, G.D0 - 1);
+      for (int zo = sg.za; zo < sg.zb; ++zo, ++seqB) {
+        const int sb = seqB % WK_SB;
+        mbar_wait(fullB + sb, (seqB / WK_SB) & 1);
+        const int p = zo + k0 - 1;
+        if (p >= 0 && p < G.D0) {                                  // warp-uniform
+          const int seq = seqA_base + (p - pmin), sa = seq % WK_SA;
+          mbar_wait(fullA + sa, (seq / WK_SA) & 1);
+          // slab p is released by three arrivals (taps k0 = 0, 1, 2 at planes p+1, p, p-1); readers that fall outside
+          // this segment's plane range are accounted for by the in-range reader at the range end they fall off
+          const int extra = (zo == sg.za ? 2 - k0 : 0) + (zo == sg.zb - 1 ? k0 : 0);
+          if (elect_one()) {
+            const uint32_t alo = a_base + (uint32_t)sa * (SLAB_BYTES >> 4), blo = b_base + (uint32_t)sb * (WK_BSTAGE >> 4);
+            if (nrows == TM1) umma_chain_mn16_ab(dcol, alo, blo, DESC_HI_MN_SW128_32B, idesc, acc);
+            else umma_chain_mn_ab(nrows, dcol, alo, blo, DESC_HI_MN_SW128_32B, idesc, acc);
+            umma_commit(emptyB + sb);
+            umma_commit(emptyA + sa);
+          }
+          if (lane == 0)
+            for (int e = 0; e < extra; ++e) mbar_arrive(emptyA + sa);
+          __syncwarp();
+          acc = 1u;
+        } else {
+          if (lane == 0) mbar_arrive(emptyB + sb);
+          __syncwarp();
+        }
+      }
+      seqA_base += pmax - pmin + 1;
+      if (sg.unit_last) {
+        if (elect_one()) umma_commit(accFull);
+        __syncwarp();
+        if (g < g1) {                                              // another unit follows: wait for the flush
+          mbar_wait(accEmpty, flushes & 1u);
+          tc_fence_after();
+        }
+        ++flushes;
+        acc = 0u;
+      }
+    }
+  } else {
+    // ================================ flush (warps 4-7): TMEM -> atomics on dW, once per unit ================================
+    const int q = warp & 3;                       // rows 32q..32q+31 <-> d1 tap k1 = q (q == 3: unused atom)
+    const bool vec = (((uintptr_t)dw) & 15) == 0 && (G.Cout & 3) == 0;
+    uint32_t flushes = 0u, touched = 0u;
+    for (long long g = g0; g < g1;) {
+      const WpSeg sg = wp_segment(g, g1, W, G.D0);
+      g = sg.gnext;
+      for (int k0 = 0; k0 < 3; ++k0)               // accumulator k0 received MMAs iff some plane pairs with an in-volume slab
+        if (max(sg.za, 1 - k0) <= min(sg.zb - 1, G.D0 - k0)) touched |= 1u << k0;
+      if (!sg.unit_last) continue;
+      const int ch = sg.u / G.nNtiles, n0 = (sg.u % G.nNtiles) * 32;
+      mbar_wait(accFull, flushes & 1u);
+      tc_fence_after();
+      const int valid = G.chunk_valid[ch];
+      const int cin_idx = (G.chunk_src[ch] ? G.C1 : 0) + G.chunk_c0[ch] + lane;
+      if (q < 3) {
+        for (int k0 = 0; k0 < 3; ++k0) {
+          if (!((touched >> k0) & 1u)) continue;      // uniform
+          for (int cb = 0; cb < WK_N; cb += 16) {
+            const int k2 = 2 - (cb >> 5), cobase = n0 + (cb & 31);  // column = (2 - k2) * 32 + co
+            if (cobase >= G.Cout) continue;           // padded output channels (uniform)
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(k0 * WK_N + cb), v);
+            tmem_ld_wait();
+            if (lane < valid) {
+              float* o = dw + ((long long)(((k0 * 3 + q) * 3 + k2)) * G.Cin + cin_idx) * G.Cout + cobase;
+              const int nv = G.Cout - cobase;
+              if (vec && nv >= 16) {
+#pragma unroll
+                for (int e = 0; e < 16; e += 4)
+                  red_add_v4(o + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+              } else if (vec && nv >= 8) {
+                red_add_v4(o, __uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+                red_add_v4(o + 4, __uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+#pragma unroll
+                for (int e = 8; e < 16; ++e)
+                  if (e < nv) atomicAdd(o + e, __uint_as_float(v[e]));
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                  if (e < nv) atomicAdd(o + e, __uint_as_float(v[e]));
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(accEmpty);
+      ++flushes;
+      touched = 0u;
+    }
+  }
+#undef WP_TILE
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // descriptor probe: one CTA, operands A and B are [rows][32] fp32 matrices TMA-loaded whole (128 B rows, swizzled by
 // the TMA unit), then `nk` MMAs with fully caller-specified shared-memory descriptors.  Used to establish which
 // (unaligned start, base offset, LBO/SBO) combinations the tensor core reads consistently with the TMA swizzle, e.g.
@@ -1568,7 +1781,20 @@ int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const 
   const long long nblk = base_units * G.n0splits;
   SSR_CHECK_ARG(nblk < (1LL << 31), "grid too large");
   cudaStream_t st = (cudaStream_t)stream;
-  if (k2n) wgrad_tc_k2n_kernel<<<(unsigned)nblk, WK_THREADS, smem, st>>>(m1, m2, my, dw, G);
+  if (k2n && !getenv("SSR_WGRAD_NO_PERSISTENT")) {
+    static int num_sms = 0;
+    if (!num_sms) {
+      int dev = 0;
+      SSR_CHECK_CUDA(cudaGetDevice(&dev));
+      SSR_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+      SSR_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    }
+    // plane steps: units x tiles x planes, cut into equal contiguous ranges (at least ~4 planes per CTA)
+    const long long T = (long long)nch * G.nNtiles * G.n1tiles * G.n2tiles * B * D0;
+    long long grid = num_sms;
+    if (T / 4 < grid) grid = T / 4 > 0 ? T / 4 : 1;
+    wgrad_tc_persistent_kernel<<<(unsigned)grid, WK_THREADS, smem, st>>>(m1, m2, my, dw, G);
+  } else if (k2n) wgrad_tc_k2n_kernel<<<(unsigned)nblk, WK_THREADS, smem, st>>>(m1, m2, my, dw, G);
   else wgrad_tc_kernel<<<(unsigned)nblk, 192, smem, st>>>(m1, m2, my, dw, G);
   SSR_COUNT_LAUNCH();
   SSR_CHECK_LAUNCH();
