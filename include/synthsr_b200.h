@@ -142,7 +142,10 @@ int ssr_upsample_bwd(const float* du, int du_stride, int du_off, int B, int d0, 
 int ssr_elu_bwd(const float* dh, int dh_stride, int dh_off, const float* h, const float* add, long long nvox, int C,
                 float* da, float* dbias, void* stream);
 /* unet_likelihood 1x1x1 conv (models.py:480-481) + metrics_model (SynthSR/metrics_model.py:53-104), fwd + bwd. */
-int ssr_head_loss(const float* feat, const float* w, const float* bias, const float* image, int image_channels,
+/* feat_stats (optional): the 4*C BatchNorm stats of the layer that produced `feat`; the normalisation is then applied on
+ * the fly (feat = raw * scale + shift) and the normalised tensor is never materialised. */
+int ssr_head_loss(const float* feat, const float* feat_stats, const float* w, const float* bias, const float* image,
+                  int image_channels,
                   const int* res_idx, const float* target, float* pred, float* dfeat, float* dw, float* db,
                   double* loss, float* gout_scratch, int B, int d0, int d1, int d2, int C, int L, int metric,
                   const int* crop_size, const int* crop_begin, int train, void* stream);

@@ -454,13 +454,14 @@ colsum2_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, con
       inv = *reinterpret_cast<const float4*>(stats + C + 4 * q);
     }
     const long long stride = (long long)gridDim.x * R;
-    for (long long v0 = (long long)blockIdx.x * R + r; v0 < nvox; v0 += 4 * stride) {
-      float4 x[4], y[4];
+    constexpr int U = MODE == 0 ? 8 : 4;       // independent 16-byte loads in flight per thread (x U, + U for b)
+    for (long long v0 = (long long)blockIdx.x * R + r; v0 < nvox; v0 += U * stride) {
+      float4 x[U], y[MODE == 1 ? U : 1];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const long long v = v0 + u * stride;
         x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        y[u] = mean;
+        if (MODE == 1) y[u] = mean;
         if (v < nvox) {
           x[u] = *reinterpret_cast<const float4*>(a + v * C + 4 * q);
           if (MODE == 1) y[u] = *reinterpret_cast<const float4*>(b + v * C + 4 * q);
@@ -468,13 +469,14 @@ colsum2_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, con
       }
       float4 fs = make_float4(0.f, 0.f, 0.f, 0.f), ft = fs;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         fs.x += x[u].x; fs.y += x[u].y; fs.z += x[u].z; fs.w += x[u].w;
         if (MODE == 0) {
           ft.x += x[u].x * x[u].x; ft.y += x[u].y * x[u].y; ft.z += x[u].z * x[u].z; ft.w += x[u].w * x[u].w;
         } else {
-          ft.x += x[u].x * ((y[u].x - mean.x) * inv.x); ft.y += x[u].y * ((y[u].y - mean.y) * inv.y);
-          ft.z += x[u].z * ((y[u].z - mean.z) * inv.z); ft.w += x[u].w * ((y[u].w - mean.w) * inv.w);
+          const float4 yy = y[MODE == 1 ? u : 0];
+          ft.x += x[u].x * ((yy.x - mean.x) * inv.x); ft.y += x[u].y * ((yy.y - mean.y) * inv.y);
+          ft.z += x[u].z * ((yy.z - mean.z) * inv.z); ft.w += x[u].w * ((yy.w - mean.w) * inv.w);
         }
       }
       s[0] += fs.x; s[1] += fs.y; s[2] += fs.z; s[3] += fs.w;
@@ -498,7 +500,8 @@ template <int MODE>
 static void launch_colsum2(const float* a, const float* b, const float* stats, long long nvox, int C, double* sums,
                            cudaStream_t st) {
   const int nq = C / 4, R = 256 / nq;
-  long long nb = (nvox + (long long)R * 4 - 1) / ((long long)R * 4);
+  const int U = MODE == 0 ? 8 : 4;
+  long long nb = (nvox + (long long)R * U - 1) / ((long long)R * U);
   if (nb > 148 * 8) nb = 148 * 8;
   colsum2_vec_kernel<MODE><<<(unsigned)nb, nq * R, 0, st>>>(a, b, stats, nvox, C, sums);
 }
@@ -972,9 +975,9 @@ head_loss_kernel(const float* __restrict__ feat, const float* __restrict__ w, co
 // feat^T * g is accumulated in registers (one block-level reduction at the end).  feat is read once, dfeat written once.
 template <int GS, int LT>        // LT: compile-time bound of L (1 or 4) so the per-output arrays stay in few registers
 __global__ void __launch_bounds__(256)
-head_loss_vec_kernel(const float* __restrict__ feat, const float* __restrict__ w, const float* __restrict__ bias,
-                     const float* __restrict__ image, const float* __restrict__ target, float* __restrict__ pred,
-                     float* __restrict__ dfeat, float* __restrict__ dw, float* __restrict__ db,
+head_loss_vec_kernel(const float* __restrict__ feat, const float* __restrict__ feat_stats, const float* __restrict__ w,
+                     const float* __restrict__ bias, const float* __restrict__ image, const float* __restrict__ target,
+                     float* __restrict__ pred, float* __restrict__ dfeat, float* __restrict__ dw, float* __restrict__ db,
                      double* __restrict__ loss, HeadParams P) {
   __shared__ float sw[4 * 128];
   __shared__ float sdw[4 * 128];
@@ -992,6 +995,13 @@ head_loss_vec_kernel(const float* __restrict__ feat, const float* __restrict__ w
   float bl[LT];
 #pragma unroll
   for (int l = 0; l < LT; ++l) bl[l] = l < L ? bias[l] : 0.f;
+  // optional BatchNorm of the feature map folded into the load (feat_stats = the layer's 4*C stats: scale at 2C, shift
+  // at 3C): the normalised tensor is never written to memory
+  float4 fsc = make_float4(1.f, 1.f, 1.f, 1.f), fsh = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (feat_stats && active) {
+    fsc = *reinterpret_cast<const float4*>(feat_stats + 2 * C + 4 * q);
+    fsh = *reinterpret_cast<const float4*>(feat_stats + 3 * C + 4 * q);
+  }
   float wacc[4][LT];
 #pragma unroll
   for (int j = 0; j < 4; ++j)
@@ -1017,7 +1027,11 @@ head_loss_vec_kernel(const float* __restrict__ feat, const float* __restrict__ w
       const long long v = vbase + u * vstep;
       vok[u] = v < nvox;
       f[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (vok[u] && active) f[u] = *reinterpret_cast<const float4*>(feat + v * C + 4 * q);
+      if (vok[u] && active) {
+        f[u] = *reinterpret_cast<const float4*>(feat + v * C + 4 * q);
+        f[u].x = f[u].x * fsc.x + fsh.x; f[u].y = f[u].y * fsc.y + fsh.y;
+        f[u].z = f[u].z * fsc.z + fsh.z; f[u].w = f[u].w * fsc.w + fsh.w;
+      }
 #pragma unroll
       for (int l = 0; l < LT; ++l) {
         tg[u][l] = (vok[u] && l < L) ? target[v * P.tgt_stride + l] : 0.f;
@@ -1416,7 +1430,8 @@ int ssr_elu_bwd(const float* dh, int dh_stride, int dh_off, const float* h, cons
 }
 
 // head + loss forward/backward.  loss: 1 double (zeroed here).  gout_scratch: nvox*L floats (train only).
-int ssr_head_loss(const float* feat, const float* w, const float* bias, const float* image, int image_channels,
+int ssr_head_loss(const float* feat, const float* feat_stats, const float* w, const float* bias, const float* image,
+                  int image_channels,
                   const int* res_idx, const float* target, float* pred, float* dfeat, float* dw, float* db,
                   double* loss, float* gout_scratch, int B, int d0, int d1, int d2, int C, int L, int metric,
                   const int* crop_size, const int* crop_begin, int train, void* stream) {
@@ -1439,7 +1454,10 @@ int ssr_head_loss(const float* feat, const float* w, const float* bias, const fl
   cudaStream_t st = (cudaStream_t)stream;
   SSR_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(double), st));
   const long long nvox = (long long)B * d0 * d1 * d2;
-  if (C % 4 == 0 && C <= 128 && ((uintptr_t)feat & 15) == 0 && (!train || ((uintptr_t)dfeat & 15) == 0)) {
+  const bool head_vec = C % 4 == 0 && C <= 128 && ((uintptr_t)feat & 15) == 0 && (!train || ((uintptr_t)dfeat & 15) == 0) &&
+                        (!feat_stats || ((uintptr_t)feat_stats & 15) == 0);
+  SSR_CHECK_ARG(!feat_stats || head_vec, "folded BatchNorm needs the vectorised head path (C % 4 == 0, C <= 128, aligned)");
+  if (head_vec) {
     // fused + coalesced path: loss, prediction, dfeat and the head weight gradient in one pass over feat
     const int nq = C / 4;
     const int gs = nq <= 1 ? 1 : nq <= 2 ? 2 : nq <= 4 ? 4 : nq <= 8 ? 8 : nq <= 16 ? 16 : 32;
@@ -1447,8 +1465,8 @@ int ssr_head_loss(const float* feat, const float* w, const float* bias, const fl
     if (nb > 148 * 8) nb = 148 * 8;
 #define SSR_HEAD_LAUNCH(GS_)                                                                                              \
   do {                                                                                                                  \
-    if (L == 1) head_loss_vec_kernel<GS_, 1><<<(unsigned)nb, 256, 0, st>>>(feat, w, bias, image, target, pred, dfeat, dw, db, loss, P); \
-    else head_loss_vec_kernel<GS_, 4><<<(unsigned)nb, 256, 0, st>>>(feat, w, bias, image, target, pred, dfeat, dw, db, loss, P);        \
+    if (L == 1) head_loss_vec_kernel<GS_, 1><<<(unsigned)nb, 256, 0, st>>>(feat, feat_stats, w, bias, image, target, pred, dfeat, dw, db, loss, P); \
+    else head_loss_vec_kernel<GS_, 4><<<(unsigned)nb, 256, 0, st>>>(feat, feat_stats, w, bias, image, target, pred, dfeat, dw, db, loss, P);        \
   } while (0)
     switch (gs) {
       case 1: SSR_HEAD_LAUNCH(1); break;

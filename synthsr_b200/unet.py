@@ -59,7 +59,8 @@ class UNet3D:
         self.prof = None          # list of (kind, flops, start_event, end_event) when profiling is enabled
         self.overlap_wgrad = os.environ.get('SSR_NO_WGRAD_OVERLAP') is None
         self.fwd_k2n = os.environ.get('SSR_NO_FWD_K2N') is None
-        self._side, self._side_busy, self._hp = None, False, None
+        self.materialise_feat = os.environ.get('SSR_MATERIALISE_FEAT') is not None
+        self._side, self._side_busy, self._hp, self._pack_event = None, False, None, None
         self.device = torch.device(device)
         for d in self.dims:
             if d % (2 ** (self.L - 1)) != 0:
@@ -296,6 +297,19 @@ class UNet3D:
             self._packed_valid.add(key)
         return self._packed[key]
 
+    def _repack(self, st):
+        """TF32-rounded, K-major packed copies of every kernel the tensor-core path has used so far, one launch."""
+        self._packed_dirty = False
+        if getattr(self, '_pack_jobs_n', 0) != len(self._packed):   # device job table, rebuilt when a copy is added
+            rows = []
+            for (name, mode), buf in self._packed.items():
+                c1, c2, cout = self._packed_args[(name, mode)]
+                rows.append([self.p[name + '/kernel'].data_ptr(), buf.data_ptr(), c1, c2, cout, mode])
+            self._pack_jobs = torch.tensor(rows, dtype=torch.int64).to(self.device)
+            self._pack_jobs_n = len(rows)
+        lib.ssr_conv3d_pack_weights_batch(self._pack_jobs, self._pack_jobs_n, st)
+        self._packed_valid = set(self._packed.keys())
+
     # -------------------------------------------------------------------------------------------------------------
     def forward(self, image, training=True):
         """image: float32 cuda tensor [B, X, Y, Z, Cin] (contiguous) -> pred [B, X, Y, Z, nb_labels]."""
@@ -305,17 +319,10 @@ class UNet3D:
         assert list(image.shape) == [B] + self.dims + [self.cin], image.shape
         self._image = image
         if self._packed_dirty and self._packed:          # refresh every packed kernel copy once per optimiser step
-            self._packed_dirty = False
-            self._packed_valid = set()
-            if getattr(self, '_pack_jobs_n', 0) != len(self._packed):   # device job table, rebuilt when a copy is added
-                rows = []
-                for (name, mode), buf in self._packed.items():
-                    c1, c2, cout = self._packed_args[(name, mode)]
-                    rows.append([self.p[name + '/kernel'].data_ptr(), buf.data_ptr(), c1, c2, cout, mode])
-                self._pack_jobs = torch.tensor(rows, dtype=torch.int64).to(self.device)
-                self._pack_jobs_n = len(rows)
-            lib.ssr_conv3d_pack_weights_batch(self._pack_jobs, self._pack_jobs_n, st)     # every layer in one launch
-            self._packed_valid = set(self._packed.keys())
+            self._repack(st)
+        if self._pack_event is not None:                  # packing ran on the side stream right after the optimiser step
+            torch.cuda.current_stream().wait_event(self._pack_event)
+            self._pack_event = None
         x, cx = image, self.cin
         for l in range(L):
             self._conv_fwd('unet_conv_downarm_%d_0' % l, x, cx, None, 0, self.h0[l], l, F[l])
@@ -333,7 +340,12 @@ class UNet3D:
             self._conv_fwd('unet_conv_uparm_%d_1' % (L + d), self.g0[l], F[l], None, 0, self.g1[l], l, F[l])
             self._bn_stats('unet_bn_up_%d' % d, self.g1[l], self.nvox[l], F[l], self.stats_dec[l], training)
             prev, prev_stats, prev_l = self.g1[l], self.stats_dec[l], l
+        if L > 1 and not self.materialise_feat:
+            # the last BatchNorm is folded into the head kernel (raw g1 + stats): no normalised feature tensor
+            self._feat_src, self._feat_stats = self.g1[0], self.stats_dec[0]
+            return self.g1[0]
         lib.ssr_bn_apply(self.g1[0], self.feat, self.stats_dec[0], B, *self.ldims[0], F[0], 0, 0, 0, st)
+        self._feat_src, self._feat_stats = self.feat, None
         return self.feat
 
     def _bn_stats(self, bn, x, nvox, C, stats, training):
@@ -368,7 +380,7 @@ class UNet3D:
             crop_size = ctypes.cast(self._crop_keep[0], ctypes.c_void_p)
             crop_begin = ctypes.cast(self._crop_keep[1], ctypes.c_void_p)
         name = 'unet_likelihood'
-        lib.ssr_head_loss(self.feat, self.p[name + '/kernel'], self.p[name + '/bias'],
+        lib.ssr_head_loss(self._feat_src, self._feat_stats, self.p[name + '/kernel'], self.p[name + '/bias'],
                           self._image if residual is not None else None, self.cin, res_idx, target, self.pred,
                           self.dbn_dec[0] if train else None, self.g[name + '/kernel'] if train else None,
                           self.g[name + '/bias'] if train else None, self.loss_buf, self.gout if train else None,
@@ -447,3 +459,13 @@ class UNet3D:
                           grad_scale, stream_ptr())
         self.iterations = t
         self._packed_dirty = True
+        if self.overlap_wgrad and self._packed and self._side is not None:
+            # re-pack on the side stream: overlaps with the next step's generator and first (exact fp32) convolution
+            ev = self._ev_pool[self._ev_i % len(self._ev_pool)]
+            self._ev_i += 1
+            ev.record()
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(ev)
+                self._repack(stream_ptr())
+                self._pack_event = torch.cuda.Event()
+                self._pack_event.record()
