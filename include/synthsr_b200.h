@@ -105,6 +105,11 @@ int ssr_conv3d_fwd_tc(const float* x1, int C1, const float* x2, int C2, const fl
  * with mode 2 (forward) / 3 (data gradient: x = dy, Cout = the layer's Cin).  Same result contract as ssr_conv3d_fwd_tc. */
 int ssr_conv3d_fwd_tc_k2n(const float* x, int C, const float* wp, const float* bias, float* y, int B, int d0, int d1,
                           int d2, int Cout, int act, void* stream);
+/* one <= 32-channel part [c0, c0 + C) of the input of a Cout <= 32 convolution (a concatenated input is the sum of its
+ * parts): weights packed with mode 4 (Cin1 = total input channels, Cin2 = (c0 << 8) | C); accumulate = add to the partial
+ * result in y, final = apply bias + activation. */
+int ssr_conv3d_fwd_tc_k2n_part(const float* x, int Ctot, int c0, int C, const float* wp, const float* bias, float* y, int B,
+                               int d0, int d1, int d2, int Cout, int act, int accumulate, int final, void* stream);
 int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const float* dy, float* dw, float* db,
                         float* scratch, long long scratch_bytes, int B, int d0, int d1, int d2, int Cout,
                         void* stream);

@@ -520,6 +520,9 @@ constexpr int KF_SA = 5, KF_NACC = 4, KF_N = 96;
 
 struct KfGeom {
   int B, D0, D1, D2, Cout, act, nks;
+  int c0;          // first channel of this part in the source tensor (TMA coordinate)
+  int accumulate;  // epilogue adds the partial result already in y (earlier channel parts of a concatenated input)
+  int final;       // last part: bias + activation are applied
   int n1tiles, n2tiles, nzr, zlen;
 };
 
@@ -579,7 +582,7 @@ conv3d_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
           const int slot = seq % KF_SA;
           mbar_wait(emptyA + slot, ((seq / KF_SA) & 1) ^ 1);
           mbar_expect_tx(fullA + slot, KF_SLAB_BYTES);
-          tma_load_5d(&map_x, fullA + slot, sA + (size_t)slot * KF_SLAB_BYTES, 0, x0 - 1, y0 - 1, p, b);
+          tma_load_5d(&map_x, fullA + slot, sA + (size_t)slot * KF_SLAB_BYTES, G.c0, x0 - 1, y0 - 1, p, b);
         }
       }
     }
@@ -666,9 +669,24 @@ conv3d_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
           for (int e = 0; e < 8; ++e) {
             const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[e]), 1);      // P_0 at input column x - 1
             const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[e]), 1);   // P_2 at input column x + 1
-            o[e] = left + __uint_as_float(v1[e]) + right + sbias[cb + e];
+            o[e] = left + __uint_as_float(v1[e]) + right;
           }
-          if (G.act) {
+          if (G.accumulate && store_ok) {             // partial sums of the earlier channel parts (fp32, pre-activation)
+            const int nv8 = G.Cout - cb;
+            if (nv8 >= 8 && vec_ok) {
+              const float4 p0 = *reinterpret_cast<const float4*>(orow + cb), p1 = *reinterpret_cast<const float4*>(orow + cb + 4);
+              o[0] += p0.x; o[1] += p0.y; o[2] += p0.z; o[3] += p0.w; o[4] += p1.x; o[5] += p1.y; o[6] += p1.z; o[7] += p1.w;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (e < nv8) o[e] += orow[cb + e];
+            }
+          }
+          if (G.final) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] += sbias[cb + e];
+          }
+          if (G.act && G.final) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const float neg = __expf(fminf(o[e], 0.f)) - 1.f;
@@ -1446,6 +1464,10 @@ __device__ __forceinline__ void pack_weights_body(const float* __restrict__ w, f
       const int q1 = (int)(r2 % 3);
       const int q0 = (int)(r2 / 3);
       const int q2 = nn >> 5, no = nn & 31;
+      if (mode == 4) {      // channel part of a (concatenated) input: C1 = total Cin, C2 = (first channel << 8) | channels
+        const int coff = C2 >> 8, cn = C2 & 255;
+        if (s < cn && no < Cout) val = w[((long long)((q0 * 3 + q1) * 3 + q2) * C1 + coff + s) * Cout + no];
+      } else
       if (mode == 2) { if (s < C1 && no < Cout) val = w[((long long)((q0 * 3 + q1) * 3 + q2) * Cin + s) * Cout + no]; }
       else { if (s < Cout && no < Cin) val = w[((long long)(((2 - q0) * 3 + (2 - q1)) * 3 + (2 - q2)) * Cin + no) * Cout + s]; }
     } else
@@ -1573,8 +1595,10 @@ long long ssr_conv3d_packed_size(int Cin1, int Cin2, int Cout, int mode) {
 }
 
 int ssr_conv3d_pack_weights(const float* w, float* wp, int Cin1, int Cin2, int Cout, int mode, void* stream) {
-  SSR_CHECK_ARG(w && wp && Cin1 > 0 && Cin2 >= 0 && Cout > 0 && mode >= 0 && mode <= 3, "pack args");
-  SSR_CHECK_ARG(mode < 2 || (Cin2 == 0 && Cin1 <= 32 && Cout <= 32), "k2n packing needs Cin <= 32, Cout <= 32");
+  SSR_CHECK_ARG(w && wp && Cin1 > 0 && Cin2 >= 0 && Cout > 0 && mode >= 0 && mode <= 4, "pack args");
+  SSR_CHECK_ARG(mode < 2 || mode == 4 || (Cin2 == 0 && Cin1 <= 32 && Cout <= 32), "k2n packing needs Cin <= 32, Cout <= 32");
+  SSR_CHECK_ARG(mode != 4 || ((Cin2 & 255) <= 32 && (Cin2 >> 8) + (Cin2 & 255) <= Cin1 && Cout <= 32),
+                "part packing: Cin1 = total input channels, Cin2 = (first channel << 8) | channels (<= 32)");
   int Npad, nch, nch1;
   if (mode >= 2) { Npad = 96; nch = 1; nch1 = 1; }
   else if (mode == 0) { Npad = round_up(Cout, 16); nch1 = (Cin1 + 31) / 32; nch = nch1 + (Cin2 + 31) / 32; }
@@ -1679,16 +1703,20 @@ int ssr_conv3d_fwd_tc(const float* x1, int C1, const float* x2, int C2, const fl
   return SSR_OK;
 }
 
-// y = act(conv3d(x, w) + bias) for Cin <= 32, Cout <= 32 with the weights packed in mode 2 (forward) or 3 (data
-// gradient: x = dy, "Cout" = the layer's Cin).  See conv3d_tc_k2n_kernel.
-int ssr_conv3d_fwd_tc_k2n(const float* x, int C, const float* wp, const float* bias, float* y, int B, int D0, int D1,
-                          int D2, int Cout, int act, void* stream) {
+// One channel part (<= 32 channels starting at c0) of a convolution with Cout <= 32 through conv3d_tc_k2n_kernel.
+// x: tensor with Ctot channels; wp: the part's weights (pack mode 2 / 3, or ssr_conv3d_pack_weights_part).  accumulate:
+// add to the partial result already in y; final: apply bias + activation.  A concatenated input [x1, x2] is the sum of
+// its parts: first part accumulate = 0, last part final = 1.
+static int conv3d_fwd_tc_k2n_impl(const float* x, int Ctot, int c0, int C, const float* wp, const float* bias, float* y,
+                                  int B, int D0, int D1, int D2, int Cout, int act, int accumulate, int final, void* stream) {
   SSR_CHECK_ARG(x && wp && y && B > 0 && D0 > 0 && D1 > 0 && D2 > 0, "pointers/shape");
-  SSR_CHECK_ARG(C > 0 && C <= 32 && C % 8 == 0 && Cout > 0 && Cout <= 32, "k2n forward needs Cin <= 32 (multiple of 8), Cout <= 32");
+  SSR_CHECK_ARG(C > 0 && C <= 32 && C % 8 == 0 && Cout > 0 && Cout <= 32 && c0 >= 0 && c0 + C <= Ctot && Ctot % 4 == 0,
+                "k2n forward needs <= 32 input channels per part (multiple of 8), Cout <= 32");
   SSR_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 127) == 0, "alignment");
   KfGeom G;
   memset(&G, 0, sizeof(G));
   G.B = B; G.D0 = D0; G.D1 = D1; G.D2 = D2; G.Cout = Cout; G.act = act; G.nks = C / 8;
+  G.c0 = c0; G.accumulate = accumulate; G.final = final;
   G.n1tiles = (D1 + KF_TM1 - 1) / KF_TM1; G.n2tiles = (D2 + KF_OUT2 - 1) / KF_OUT2;
   static int num_sms = 0;
   if (!num_sms) {
@@ -1709,7 +1737,7 @@ int ssr_conv3d_fwd_tc_k2n(const float* x, int C, const float* wp, const float* b
   }
   G.nzr = best_nzr;
   CUtensorMap mx, mw;
-  int rc = make_map_act(&mx, x, C, B, D0, D1, D2, KF_TM1 + 2, CU_TENSOR_MAP_SWIZZLE_128B, KF_TM2);
+  int rc = make_map_act(&mx, x, Ctot, B, D0, D1, D2, KF_TM1 + 2, CU_TENSOR_MAP_SWIZZLE_128B, KF_TM2);
   if (rc) return rc;
   rc = make_map_w(&mw, wp, 9 * KF_N, KF_N);
   if (rc) return rc;
@@ -1726,6 +1754,15 @@ int ssr_conv3d_fwd_tc_k2n(const float* x, int C, const float* wp, const float* b
   SSR_COUNT_LAUNCH();
   SSR_CHECK_LAUNCH();
   return SSR_OK;
+}
+
+int ssr_conv3d_fwd_tc_k2n(const float* x, int C, const float* wp, const float* bias, float* y, int B, int D0, int D1,
+                          int D2, int Cout, int act, void* stream) {
+  return conv3d_fwd_tc_k2n_impl(x, C, 0, C, wp, bias, y, B, D0, D1, D2, Cout, act, 0, 1, stream);
+}
+int ssr_conv3d_fwd_tc_k2n_part(const float* x, int Ctot, int c0, int C, const float* wp, const float* bias, float* y, int B,
+                               int D0, int D1, int D2, int Cout, int act, int accumulate, int final, void* stream) {
+  return conv3d_fwd_tc_k2n_impl(x, Ctot, c0, C, wp, bias, y, B, D0, D1, D2, Cout, act, accumulate, final, stream);
 }
 
 long long ssr_conv3d_wgrad_scratch_bytes(int, int, int, int, int, int, int) { return 0; }

@@ -59,6 +59,7 @@ class UNet3D:
         self.prof = None          # list of (kind, flops, start_event, end_event) when profiling is enabled
         self.overlap_wgrad = os.environ.get('SSR_NO_WGRAD_OVERLAP') is None
         self.fwd_k2n = os.environ.get('SSR_NO_FWD_K2N') is None
+        self.fwd_k2n_parts = self.fwd_k2n and os.environ.get('SSR_NO_FWD_K2N_PARTS') is None
         self.materialise_feat = os.environ.get('SSR_MATERIALISE_FEAT') is not None
         self._side, self._side_busy, self._hp, self._pack_event = None, False, None, None
         self.device = torch.device(device)
@@ -210,6 +211,13 @@ class UNet3D:
             # full-resolution 24-channel layers: d2 taps in the MMA N dimension (conv3d_tc_k2n_kernel)
             lib.ssr_conv3d_fwd_tc_k2n(x1, c1, self._packed_w(name, 2, c1, 0, cout), self.p[name + '/bias'], y,
                                       self.B, *d, cout, act, st)
+        elif tc and self.fwd_k2n_parts and c2 > 0 and c1 <= 32 and cout <= 32 and c2 % 8 == 0:
+            # concatenated input of the last decoder level: sum over <= 32-channel parts, each through the k2n kernel
+            parts = [(x1, c1, 0, c1, 0)] + [(x2, c2, o, min(32, c2 - o), c1 + o) for o in range(0, c2, 32)]
+            for i, (src, ctot, c0, cn, coff) in enumerate(parts):
+                wp = self._packed_w(name, 4, c1 + c2, (coff << 8) | cn, cout, tag=i)
+                lib.ssr_conv3d_fwd_tc_k2n_part(src, ctot, c0, cn, wp, self.p[name + '/bias'], y, self.B, *d, cout, act,
+                                               1 if i > 0 else 0, 1 if i == len(parts) - 1 else 0, st)
         elif tc:
             lib.ssr_conv3d_fwd_tc(x1, c1, x2, c2, self._packed_w(name, 0, c1, c2, cout), self.p[name + '/bias'], y,
                                   self.B, *d, cout, act, st)
@@ -282,12 +290,12 @@ class UNet3D:
     def _wgrad_tc_ok(self, c1, c2, cout):
         return getattr(self, 'wgrad_tc', False) and (c1 % 8 == 0) and (c2 % 8 == 0) and cout % 8 == 0
 
-    def _packed_w(self, name, mode, c1, c2, cout):
+    def _packed_w(self, name, mode, c1, c2, cout, tag=0):
         """packed (K-major, zero padded) copy of a kernel for the tcgen05 path; refreshed after every optimiser step."""
         if self._packed_dirty:
             self._packed_valid = set()
             self._packed_dirty = False
-        key = (name, mode)
+        key = (name, mode, tag)
         if key not in self._packed:
             n = lib.ssr_conv3d_packed_size(c1, c2, cout, mode)
             self._packed[key] = torch.empty(n, dtype=torch.float32, device=self.device)
@@ -302,8 +310,9 @@ class UNet3D:
         self._packed_dirty = False
         if getattr(self, '_pack_jobs_n', 0) != len(self._packed):   # device job table, rebuilt when a copy is added
             rows = []
-            for (name, mode), buf in self._packed.items():
-                c1, c2, cout = self._packed_args[(name, mode)]
+            for key, buf in self._packed.items():
+                name, mode = key[0], key[1]
+                c1, c2, cout = self._packed_args[key]
                 rows.append([self.p[name + '/kernel'].data_ptr(), buf.data_ptr(), c1, c2, cout, mode])
             self._pack_jobs = torch.tensor(rows, dtype=torch.int64).to(self.device)
             self._pack_jobs_n = len(rows)

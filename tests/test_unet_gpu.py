@@ -311,3 +311,33 @@ def test_tc_k2n_forward_and_dgrad_match_float64():
         assert not torch.isnan(dx).any(), ('dgrad nan', d, cin, co)
         err = (dx.double().cpu() - dx64).abs().max().item() / dx64.abs().max().item()
         assert err < 2e-5, ('dgrad', d, cin, co, err)
+
+
+def test_tc_k2n_channel_parts_match_float64():
+    """concatenated input [x1 (24), x2 (48)] -> 24 as three k2n passes (accumulate / final) vs float64 on rounded operands."""
+    from synthsr_b200._lib import lib, stream_ptr
+    rng = np.random.default_rng(6)
+    for (d, c1, c2, co) in [([12, 19, 30], 24, 48, 24), ([9, 8, 15], 16, 40, 8)]:
+        nv = int(np.prod(d))
+        x1 = torch.from_numpy(rng.normal(size=(nv, c1)).astype(np.float32)).cuda()
+        x2 = torch.from_numpy(rng.normal(size=(nv, c2)).astype(np.float32)).cuda()
+        w = torch.from_numpy((rng.normal(size=(3, 3, 3, c1 + c2, co)) / np.sqrt(27 * (c1 + c2))).astype(np.float32)).cuda()
+        b = torch.from_numpy(rng.normal(size=co).astype(np.float32)).cuda()
+        y = torch.full((nv, co), float('nan'), dtype=torch.float32, device='cuda')
+        st = stream_ptr()
+        parts = [(x1, c1, 0, c1, 0)] + [(x2, c2, o, min(32, c2 - o), c1 + o) for o in range(0, c2, 32)]
+        keep = []
+        for i, (src, ctot, c0, cn, coff) in enumerate(parts):
+            wp = torch.empty(lib.ssr_conv3d_packed_size(c1 + c2, (coff << 8) | cn, co, 4), dtype=torch.float32, device='cuda')
+            lib.ssr_conv3d_pack_weights(w, wp, c1 + c2, (coff << 8) | cn, co, 4, st)
+            keep.append(wp)
+            lib.ssr_conv3d_fwd_tc_k2n_part(src, ctot, c0, cn, wp, b, y, 1, *d, co, 1, 1 if i > 0 else 0,
+                                           1 if i == len(parts) - 1 else 0, st)
+        torch.cuda.synchronize()
+        xr = _rne_tf32(torch.cat([x1, x2], 1)).double().cpu().view(1, *d, c1 + c2).permute(0, 4, 1, 2, 3)
+        wr = _rna_tf32(w).double().cpu().permute(4, 3, 0, 1, 2)
+        y64 = torch.nn.functional.elu(torch.nn.functional.conv3d(xr, wr, b.double().cpu(), padding=1))
+        y64 = y64.permute(0, 2, 3, 4, 1).reshape(nv, co)
+        assert not torch.isnan(y).any()
+        err = (y.double().cpu() - y64).abs().max().item() / y64.abs().max().item()
+        assert err < 2e-5, (d, c1, c2, co, err)
