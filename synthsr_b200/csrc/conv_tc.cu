@@ -1123,7 +1123,10 @@ wgrad_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x1, const __g
   const int ntile = G.B * G.n1tiles * G.n2tiles;
   const long long W = (long long)ntile * G.D0;                    // plane steps per unit
   const long long T = W * G.nchunks * G.nNtiles;
-  const long long g0 = T * blockIdx.x / gridDim.x, g1 = T * (blockIdx.x + 1) / gridDim.x;
+  // this launch covers slice `zlen` of `n0splits` of the global list (several short launches instead of one long one let
+  // higher-priority kernels of the backward chain get SMs between them)
+  const long long sl0 = T * G.zlen / G.n0splits, sl1 = T * (G.zlen + 1) / G.n0splits;
+  const long long g0 = sl0 + (sl1 - sl0) * blockIdx.x / gridDim.x, g1 = sl0 + (sl1 - sl0) * (blockIdx.x + 1) / gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < WK_SA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, 3); }
@@ -1828,9 +1831,21 @@ int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const 
     }
     // plane steps: units x tiles x planes, cut into equal contiguous ranges (at least ~4 planes per CTA)
     const long long T = (long long)nch * G.nNtiles * G.n1tiles * G.n2tiles * B * D0;
-    long long grid = num_sms;
-    if (T / 4 < grid) grid = T / 4 > 0 ? T / 4 : 1;
-    wgrad_tc_persistent_kernel<<<(unsigned)grid, WK_THREADS, smem, st>>>(m1, m2, my, dw, G);
+    // one launch; SSR_WGRAD_SLICES > 1 cuts it into several shorter launches (measured slower: 14.2 / 14.5 / 15.1 ms per
+    // step for 1 / 2 / 4 slices -- the extra flushes cost more than the earlier SM hand-over to the dgrad chain gains)
+    int nslices = 1;
+    if (const char* e = getenv("SSR_WGRAD_SLICES")) nslices = atoi(e);
+    if (nslices < 1) nslices = 1;
+    if (nslices > 8) nslices = 8;
+    G.n0splits = nslices;
+    for (int sl = 0; sl < nslices; ++sl) {
+      G.zlen = sl;
+      const long long Ts = T * (sl + 1) / nslices - T * sl / nslices;
+      long long grid = num_sms;
+      if (Ts / 4 < grid) grid = Ts / 4 > 0 ? Ts / 4 : 1;
+      wgrad_tc_persistent_kernel<<<(unsigned)grid, WK_THREADS, smem, st>>>(m1, m2, my, dw, G);
+      if (sl + 1 < nslices) SSR_COUNT_LAUNCH();
+    }
   } else if (k2n) wgrad_tc_k2n_kernel<<<(unsigned)nblk, WK_THREADS, smem, st>>>(m1, m2, my, dw, G);
   else wgrad_tc_kernel<<<(unsigned)nblk, 192, smem, st>>>(m1, m2, my, dw, G);
   SSR_COUNT_LAUNCH();
