@@ -76,6 +76,12 @@ int ssr_blur3d(const float* src, float* dst, const float* kern, int k0, int k1, 
                const float* gamma_exp, int B, int n0, int n1, int n2, int src_stride, int src_off, int dst_stride,
                int dst_off, void* stream);
 
+/* MimicAcquisition (ext/lab2im/layers.py:835-999; randomise_res branch of labels_to_image_model.py:215-220): nearest
+ * resampling to a per-example acquisition grid + linear resampling to (o0,o1,o2), fused; params [B][9] = down_zoom[3] |
+ * up_zoom[3] | resolution[3]; dist (optional) = distance in mm to the nearest acquired voxel. */
+int ssr_mimic_acquisition(const float* src, float* dst, float* dist, const float* params, int B, int n0, int n1,
+                          int n2, int o0, int o1, int o2, int dst_stride, int dst_off, int dist_stride, int dist_off,
+                          void* stream);
 int ssr_copy_strided(const float* src, float* dst, long long n, int src_stride, int src_off, int dst_stride,
                      int dst_off, void* stream);
 

@@ -291,6 +291,70 @@ def gaussian_blur(img, sigma, blur_mult=None):
     return img
 
 
+def dynamic_sigma(atlas_res, resolution, thickness, mult_coef=.42):
+    """ext/lab2im/edit_tensors.py:66-81 (tensor branch): sigma = mult * min(res, thickness) / current_res, 0 where the
+    down-sampling resolution is 0.  resolution / thickness [B,3] float32."""
+    res = np.asarray(resolution, dtype=f32)
+    down = np.minimum(res, np.asarray(thickness, dtype=f32)).astype(f32)
+    sigma = ((f32(mult_coef) * down).astype(f32) / np.asarray(atlas_res, dtype=f32)).astype(f32)
+    return np.where(down == 0, f32(0), sigma).astype(f32)
+
+
+def dynamic_separable_kernels(sigma, max_sigma, blur_mult=None):
+    """ext/lab2im/edit_tensors.py:86-154 with sigma given as a [B,3] tensor (DynamicGaussianBlur, layers.py:813):
+    window from max_sigma (:124), jitter sigma*U(1/r,r) per (example, axis) (:119-121), 1-D Gaussians per example, and --
+    as the reference does (:147, `g / tf.reduce_sum(g)` on the [B, window] tensor) -- normalised by the sum over the
+    WHOLE batch.  Returns three arrays [B, window]."""
+    sig = np.asarray(sigma, dtype=f32)
+    if blur_mult is not None:
+        sig = (sig * np.asarray(blur_mult, dtype=f32)).astype(f32)
+    max_sigma = np.array(_to_list(max_sigma, 3), dtype=np.float64)
+    ws = np.int32(np.ceil(2.5 * max_sigma) / 2) * 2 + 1
+    out = []
+    for i, w in enumerate(ws):
+        if w > 1:
+            loc = (np.arange(w).astype(f32) - f32((w - 1) / 2)).astype(f32)[None, :]
+            si = sig[:, i:i + 1]
+            exp_term = (-np.square(loc) / (f32(2) * si ** 2).astype(f32)).astype(f32)
+            g = np.exp(exp_term - np.log((f32(np.sqrt(2 * np.pi)) * si).astype(f32)).astype(f32)).astype(f32)
+            g = (g / np.sum(g, dtype=f32)).astype(f32)
+            out.append(g)
+        else:
+            out.append(None)
+    return out
+
+
+def mimic_acquisition_zooms(inshape, volume_res, subsample_res, resample_shape):
+    """ext/lab2im/layers.py:935-939: acquisition grid shape and the two zoom factors for one example."""
+    full = (np.array(inshape) * np.array(volume_res, dtype=np.float64)).astype(f32)
+    down_shape = (full / np.asarray(subsample_res, dtype=f32)).astype(np.int32)                    # :935-936
+    down_zoom = (down_shape / np.array(inshape)).astype(f32)                                      # :937
+    up_zoom = (np.array(resample_shape, dtype=np.int32) / down_shape).astype(f32)                # :938
+    return down_shape, down_zoom, up_zoom
+
+
+def mimic_acquisition(vol, subsample_res, volume_res, min_subsample_res, resample_shape):
+    """ext/lab2im/layers.py:921-987 for one example, build_dist_map=True, noise_std=0.  vol [X,Y,Z,1] -> (vol', dist)."""
+    inshape = list(vol.shape[:3])
+    res = np.asarray(subsample_res, dtype=f32)
+    down_tensor_shape = np.int32(np.array(inshape) * np.array(volume_res) / np.array(min_subsample_res))   # :906
+    _, down_zoom, up_zoom = mimic_acquisition_zooms(inshape, volume_res, res, resample_shape)
+    grid = _grid(list(down_tensor_shape))
+    down_loc = [np.clip((grid[d] / down_zoom[d]).astype(f32), f32(0), f32(inshape[d])) for d in range(3)]   # :942-946
+    low = interpn_nearest(vol, down_loc)                                                                   # :947
+    ugrid = _grid(list(resample_shape))
+    up_loc = [(ugrid[d] / up_zoom[d]).astype(f32) for d in range(3)]                                       # :961-962
+    out = interpn_linear(low, up_loc)                                                                      # :963
+    dsq = None
+    for d in range(3):                                                                                     # :973-986
+        f_dist = (up_loc[d] - np.floor(up_loc[d])).astype(f32)
+        c_dist = (np.ceil(up_loc[d]) - up_loc[d]).astype(f32)
+        dd = (np.minimum(f_dist, c_dist) * res[d]).astype(f32)
+        sq = np.square(dd).astype(f32)
+        dsq = sq if dsq is None else (dsq + sq).astype(f32)
+    return out, np.sqrt(dsq).astype(f32)[..., None]
+
+
 def reliability_map(resample_shape, downsample_shape):
     """ext/lab2im/edit_tensors.py:313-329 -> float32 [X,Y,Z]."""
     up = np.array(resample_shape) / np.array(downsample_shape)
@@ -457,8 +521,8 @@ def labels_to_image(cfg, inputs, draws, return_intermediates=False):
     gen_labels = np.asarray(cfg['generation_labels']).astype(np.int64)
     n_neutral = cfg.get('n_neutral_labels', None)
     n_neutral = len(gen_labels) if n_neutral is None else n_neutral
-    if cfg.get('randomise_res', False):
-        raise NotImplementedError('randomise_res branch (SampleResolution/MimicAcquisition) not restated yet')
+    rr = cfg.get('randomise_res', False)
+    randomise_res = [bool(rr)] * r['n_channels'] if isinstance(rr, (bool, np.bool_)) or rr is None else [bool(v) for v in rr]
     inter = {}
 
     images, targets = [], []
@@ -564,15 +628,31 @@ def labels_to_image(cfg, inputs, draws, return_intermediates=False):
                     T = build_affine(rotation=draws['reg_rot_%d' % i][b], translation=draws['reg_trans_%d' % i][b])
                     Tinv = np.linalg.inv(T.astype(np.float64)).astype(f32)                       # tf.linalg.inv
                     ch = spatial_transformer(ch[..., None], T, None, 'linear')[..., 0]
-                sigma = blurring_sigma_for_downsampling(r['atlas_res'], r['data_res'][i], .42, r['thickness'][i])  # :223
                 blur_range = cfg.get('blur_range', 1.15)
-                mult = draws['blur_mult_%d' % i] if (blur_range is not None and blur_range != 1) else None
-                ch = gaussian_blur(ch, list(sigma), mult)                                        # :224
-                if r['downsample'][i]:
-                    ch, rel = resample_tensor(ch[..., None], r['output_shape'], list(r['data_res'][i]),
-                                              list(r['atlas_res']), True)                        # :226
+                if randomise_res[i]:                                                             # :215-220
+                    max_res = np.array([9.] * 3)
+                    res_all, thick_all = draws['res_%d' % i], draws['thick_%d' % i]              # SampleResolution
+                    sig_all = dynamic_sigma(r['atlas_res'], res_all, thick_all, .42)
+                    mult = draws['blur_mult_dyn_%d' % i] if (blur_range is not None and blur_range != 1) else None
+                    ks = dynamic_separable_kernels(sig_all, 0.75 * max_res / np.array(r['atlas_res']), mult)
+                    for ax, g in enumerate(ks):                                                  # layers.py:814-816
+                        if g is not None:
+                            kshape = [1, 1, 1]
+                            kshape[ax] = g.shape[1]
+                            ch = conv3d_same(ch, g[b].reshape(kshape))
+                    ch, rel = mimic_acquisition(ch[..., None], res_all[b], r['atlas_res'], r['atlas_res'],
+                                                r['output_shape'])
+                    if b == 0:
+                        inter['mimic_%d' % i] = ch.copy()
                 else:
-                    ch, rel = resample_tensor(ch[..., None], r['output_shape'], build_reliability_map=True)   # :228
+                    sigma = blurring_sigma_for_downsampling(r['atlas_res'], r['data_res'][i], .42, r['thickness'][i])  # :223
+                    mult = draws['blur_mult_%d' % i] if (blur_range is not None and blur_range != 1) else None
+                    ch = gaussian_blur(ch, list(sigma), mult)                                    # :224
+                    if r['downsample'][i]:
+                        ch, rel = resample_tensor(ch[..., None], r['output_shape'], list(r['data_res'][i]),
+                                                  list(r['atlas_res']), True)                    # :226
+                    else:
+                        ch, rel = resample_tensor(ch[..., None], r['output_shape'], build_reliability_map=True)   # :228
                 if do_reg:                                                                       # :231-238
                     Terr = build_affine(rotation=draws['reg_err_rot_%d' % i][b],
                                         translation=draws['reg_err_trans_%d' % i][b])

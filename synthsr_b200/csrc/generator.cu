@@ -103,6 +103,71 @@ __global__ void resize_kernel(const float* __restrict__ src, float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// MimicAcquisition (ext/lab2im/layers.py:921-987), both resamplings fused: the low-resolution acquisition is never
+// materialised.  The reference keeps it in a full-size tensor V[i] = vol[nearest(clip(i / down_zoom, 0, n))] and then
+// samples V linearly at j / up_zoom; here each of the 8 corners of the linear interpolation evaluates V on the fly.
+// params [B][9] = down_zoom[3] | up_zoom[3] | acquisition resolution[3] (float32, computed on the host exactly as the
+// reference does, :935-938).  dist = distance (mm) to the nearest acquired voxel (:973-986), optional.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int mimic_low_index(int i, float down_zoom, int n) {
+  float l = __fdiv_rn((float)i, down_zoom);
+  l = fminf(fmaxf(l, 0.f), (float)n);                       // K.clip(down_loc, 0, inshape)
+  int r = (int)rintf(l);                                    // tf.round: half to even
+  return min(max(r, 0), n - 1);
+}
+
+__global__ void mimic_acquisition_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                         float* __restrict__ dist, const float* __restrict__ params, int B, int n0,
+                                         int n1, int n2, int o0, int o1, int o2, int dst_stride, int dst_off,
+                                         int dist_stride, int dist_off) {
+  const long long nout = (long long)o0 * o1 * o2, total = nout * B;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(t / nout);
+    long long v = t - (long long)b * nout;
+    const int k = (int)(v % o2);
+    v /= o2;
+    const int j = (int)(v % o1);
+    const int i = (int)(v / o1);
+    const float* P = params + b * 9;
+    const float* sv = src + (long long)b * n0 * n1 * n2;
+    const float u0 = __fdiv_rn((float)i, P[3]), u1 = __fdiv_rn((float)j, P[4]), u2 = __fdiv_rn((float)k, P[5]);
+    const Axis a0 = lin_axis(u0, n0), a1 = lin_axis(u1, n1), a2 = lin_axis(u2, n2);
+    const int i0[2] = {mimic_low_index(a0.i0, P[0], n0), mimic_low_index(a0.i1, P[0], n0)};
+    const int i1[2] = {mimic_low_index(a1.i0, P[1], n1), mimic_low_index(a1.i1, P[1], n1)};
+    const int i2[2] = {mimic_low_index(a2.i0, P[2], n2), mimic_low_index(a2.i1, P[2], n2)};
+    const float w0[2] = {a0.w0, a0.w1}, w1[2] = {a1.w0, a1.w1}, w2[2] = {a2.w0, a2.w1};
+    float out = 0.f;
+    bool first = true;
+#pragma unroll
+    for (int c0 = 0; c0 < 2; ++c0)
+#pragma unroll
+      for (int c1 = 0; c1 < 2; ++c1)
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          const float wt = __fmul_rn(__fmul_rn(w0[c0], w1[c1]), w2[c2]);
+          const float tv = __fmul_rn(wt, __ldg(sv + ((long long)i0[c0] * n1 + i1[c1]) * n2 + i2[c2]));
+          out = first ? tv : __fadd_rn(out, tv);
+          first = false;
+        }
+    const long long ov = (long long)b * nout + (t - (long long)b * nout);
+    dst[ov * dst_stride + dst_off] = out;
+    if (dist) {
+      const float uu[3] = {u0, u1, u2};
+      float acc = 0.f;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float f = __fsub_rn(uu[d], floorf(uu[d])), c = __fsub_rn(ceilf(uu[d]), uu[d]);
+        const float m = __fmul_rn(fminf(f, c), P[6 + d]);
+        const float sq = __fmul_rn(m, m);
+        acc = d == 0 ? sq : __fadd_rn(acc, sq);
+      }
+      dist[ov * dist_stride + dist_off] = __fsqrt_rn(acc);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // K2: one scaling-and-squaring step  v_out = v + interp_linear(v, idx + v)   (ext/neuron/utils.py:366-369)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void svf_step_kernel(const float* __restrict__ vin, float* __restrict__ vout, int B, int n0, int n1, int n2,
@@ -649,6 +714,18 @@ int ssr_blur3d(const float* src, float* dst, const float* kern, int k0, int k1, 
     SSR_CHECK_CUDA(cudaFuncSetAttribute(blur3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long nblk = (long long)B * ssr_div_up(n0, BT0) * ssr_div_up(n1, BT1) * ssr_div_up(n2, BT2);
   blur3d_kernel<<<(unsigned)nblk, 256, smem, (cudaStream_t)stream>>>(src, dst, kern, minmax, gamma_exp, P);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
+int ssr_mimic_acquisition(const float* src, float* dst, float* dist, const float* params, int B, int n0, int n1,
+                          int n2, int o0, int o1, int o2, int dst_stride, int dst_off, int dist_stride, int dist_off,
+                          void* stream) {
+  SSR_CHECK_ARG(src && dst && params && B > 0 && n0 > 0 && n1 > 0 && n2 > 0 && o0 > 0 && o1 > 0 && o2 > 0, "args");
+  mimic_acquisition_kernel<<<grid_for((long long)B * o0 * o1 * o2), 256, 0, (cudaStream_t)stream>>>(
+      src, dst, dist, params, B, n0, n1, n2, o0, o1, o2, dst_stride > 0 ? dst_stride : 1, dst_off,
+      dist_stride > 0 ? dist_stride : 1, dist_off);
   SSR_COUNT_LAUNCH();
   SSR_CHECK_LAUNCH();
   return SSR_OK;

@@ -68,6 +68,18 @@ def sample_draws(rng, plan, batch, gmm_noise=False):
             r = plan.blur_range
             if r is not None and r != 1:
                 d['blur_mult_%d' % i] = rng.uniform(1. / r, r, size=3).astype(f32)
+            if plan.randomise_res[i]:
+                # SampleResolution(atlas_res, max_res_iso=[9,9,9]) (ext/lab2im/layers.py:619-625, 646-647): resolution
+                # U(atlas_res, 9) independently per (example, axis); with probability prob_min = 0.05 (one draw for the
+                # whole batch) the atlas resolution; thickness U(atlas_res, resolution)
+                lo = np.asarray(plan.atlas_res, dtype=f32)
+                res = (lo + rng.uniform(0., 1., size=(batch, 3)).astype(f32) * (f32(9.) - lo)).astype(f32)
+                if rng.uniform() < 0.05:
+                    res = np.tile(lo[None], (batch, 1)).astype(f32)
+                d['res_%d' % i] = res
+                d['thick_%d' % i] = (lo + rng.uniform(0., 1., size=(batch, 3)).astype(f32) * (res - lo)).astype(f32)
+                if r is not None and r != 1:   # gaussian_kernel jitter on the [B,3] sigma tensor (edit_tensors.py:119-121)
+                    d['blur_mult_dyn_%d' % i] = rng.uniform(1. / r, r, size=(batch, 3)).astype(f32)
             if plan.sim_reg[i] and i != plan.idx_first_input_channel:
                 d['reg_rot_%d' % i] = rng.uniform(-5., 5., size=(batch, 3)).astype(f32)
                 d['reg_trans_%d' % i] = rng.uniform(-5., 5., size=(batch, 3)).astype(f32)

@@ -145,6 +145,45 @@ def reliability_factors(resample_shape, downsample_shape):
     return out
 
 
+def dynamic_sigma(atlas_res, resolution, thickness, mult_coef=.42):
+    """blurring_sigma_for_downsampling, tensor branch (ext/lab2im/edit_tensors.py:66-81): [B,3] float32."""
+    res = np.asarray(resolution, dtype=f32)
+    down = np.minimum(res, np.asarray(thickness, dtype=f32)).astype(f32)
+    sigma = ((f32(mult_coef) * down).astype(f32) / np.asarray(atlas_res, dtype=f32)).astype(f32)
+    return np.where(down == 0, f32(0), sigma).astype(f32)
+
+
+def dynamic_kernels(sigma, window, blur_mult=None):
+    """per-example 1-D Gaussian kernels of DynamicGaussianBlur (ext/lab2im/edit_tensors.py:126-154 with a [B,3] sigma
+    tensor): jitter per (example, axis), and -- like the reference's `g / tf.reduce_sum(g)` on the [B, window] tensor --
+    normalisation by the sum over the whole batch.  Returns three float32 arrays [B, window[i]] (None for window 1)."""
+    sig = np.asarray(sigma, dtype=f32)
+    if blur_mult is not None:
+        sig = (sig * np.asarray(blur_mult, dtype=f32)).astype(f32)
+    out = []
+    for i, w in enumerate(window):
+        if w > 1:
+            loc = (np.arange(w).astype(f32) - f32((w - 1) / 2)).astype(f32)[None, :]
+            si = sig[:, i:i + 1]
+            exp_term = (-np.square(loc) / (f32(2) * si ** 2).astype(f32)).astype(f32)
+            g = np.exp(exp_term - np.log((f32(np.sqrt(2 * np.pi)) * si).astype(f32)).astype(f32)).astype(f32)
+            out.append((g / np.sum(g, dtype=f32)).astype(f32))
+        else:
+            out.append(None)
+    return out
+
+
+def mimic_zooms(inshape, volume_res, subsample_res, resample_shape):
+    """MimicAcquisition zoom factors for one example (ext/lab2im/layers.py:935-938) -> float32 [9] =
+    down_zoom | up_zoom | resolution, the parameter block of ssr_mimic_acquisition."""
+    full = (np.array(inshape) * np.array(volume_res, dtype=np.float64)).astype(f32)
+    res = np.asarray(subsample_res, dtype=f32)
+    down_shape = (full / res).astype(np.int32)
+    down_zoom = (down_shape / np.array(inshape)).astype(f32)
+    up_zoom = (np.array(resample_shape, dtype=np.int32) / down_shape).astype(f32)
+    return np.concatenate([down_zoom, up_zoom, res]).astype(f32)
+
+
 class GeneratorPlan:
     """Static configuration of one labels_to_image_model instance (same keyword names as the reference)."""
 
@@ -166,9 +205,8 @@ class GeneratorPlan:
         self.sim_reg = [bool(sr)] * self.n_channels if isinstance(sr, (bool, int, np.bool_)) else [bool(v) for v in sr]
         if isinstance(randomise_res, (bool, np.bool_)) or randomise_res is None:
             randomise_res = [bool(randomise_res)] * self.n_channels
-        if any(randomise_res):
-            raise NotImplementedError('randomise_res (SampleResolution / DynamicGaussianBlur / MimicAcquisition, '
-                                      'ext/lab2im/layers.py:504-999) is not part of this build yet')
+        self.randomise_res = [bool(v) for v in randomise_res]
+        assert len(self.randomise_res) == self.n_channels, 'randomise_res must have one entry per channel'
         self.labels_shape = [int(s) for s in labels_shape]
         atlas = _res_array(atlas_res, self.n_channels)
         data_res = None if data_res is None else (np.load(data_res) if isinstance(data_res, str) else data_res)
@@ -229,6 +267,10 @@ class GeneratorPlan:
             self.target_sigma = blurring_sigma(self.atlas_res, self.target_res)
         self.acq_sigma = [blurring_sigma(self.atlas_res, self.data_res[i], .42, self.thickness[i])
                           for i in range(self.n_channels)]
+        # randomise_res branch (labels_to_image_model.py:215-220): DynamicGaussianBlur(0.75 * max_res / atlas_res) with
+        # max_res = 9 mm -> separable 1-D kernels of a fixed window (ext/lab2im/layers.py:808, edit_tensors.py:124)
+        self.dyn_max_sigma = 0.75 * 9. / np.asarray(self.atlas_res, dtype=np.float64)
+        self.dyn_window = [int(w) for w in (np.int32(np.ceil(2.5 * self.dyn_max_sigma) / 2) * 2 + 1)]
         self.down_shape = []
         for i in range(self.n_channels):
             ds = list(self.crop_shape)
@@ -298,6 +340,8 @@ class SynthGenerator:
         if p.use_real_image:
             self.real = torch.empty((B, nc), dtype=torch.float32, device=dev)
         nd = max(int(np.prod(s)) for s in p.down_shape)
+        if any(p.randomise_res):
+            nd = max(nd, nt)                 # also holds the acquisition distance map when it has to be warped
         self.down = torch.empty((B, nd), dtype=torch.float32, device=dev)
         small = 4 * B * (16 + 3 * int(np.prod(p.svf_small_shape or [1])) + 3 + 1 + 2 * p.lut_len * p.n_channels
                          + p.n_channels * (int(np.prod(p.bias_small_shape)) + 2048 + 64)) + 8 * sum(p.output_shape) * 2
@@ -355,10 +399,19 @@ class SynthGenerator:
             gam = (np.asarray(draws['gamma_normal_%d' % i], dtype=f32) * f32(.5)).astype(f32)
             c['gamma'] = sg.put(np.exp(gam).astype(f32))
             c['k05'] = sg.put(gaussian_kernel([.5, .5, .5])[0])
-            if p.input_channels[i]:
+            if p.input_channels[i] and p.randomise_res[i]:                    # labels_to_image_model.py:215-220
+                jit = p.blur_range is not None and p.blur_range != 1
+                sig = dynamic_sigma(p.atlas_res, draws['res_%d' % i], draws['thick_%d' % i], .42)
+                ks = dynamic_kernels(sig, p.dyn_window, draws['blur_mult_dyn_%d' % i] if jit else None)
+                c['kdyn'] = [None if k is None else sg.put(k) for k in ks]   # [B, window] per axis
+                c['mimic'] = sg.put(np.stack([mimic_zooms(p.crop_shape, p.atlas_res, draws['res_%d' % i][b],
+                                                          p.output_shape) for b in range(B)]))
+                c['kacq'] = []
+            elif p.input_channels[i]:
                 mult = draws.get('blur_mult_%d' % i) if (p.blur_range is not None and p.blur_range != 1) else None
                 ks = gaussian_kernel(list(p.acq_sigma[i]), mult)
                 c['kacq'] = [(sg.put(k), k.shape) for k in ks]
+            if p.input_channels[i]:
                 do_reg = p.sim_reg[i] and i != p.idx_first_input_channel
                 c['reg'] = do_reg
                 if do_reg:
@@ -369,7 +422,7 @@ class SynthGenerator:
                                            translation=draws['reg_err_trans_%d' % i][b]) for b in range(B)]
                     c['T'] = sg.put(np.stack(T))
                     c['Tie'] = sg.put(np.stack([D.matmul4(Terr[b], Tinv[b]) for b in range(B)]))
-                if p.build_reliability_maps and p.down_shape[i] != p.crop_shape:
+                if p.build_reliability_maps and p.down_shape[i] != p.crop_shape and not p.randomise_res[i]:
                     c['rel'] = [sg.put(f) for f in reliability_factors(p.output_shape, p.down_shape[i])]
             if (not p.use_real_image) and i in p.output_channel and p.target_sigma is not None:
                 c['ktgt'] = [(sg.put(k), k.shape) for k in gaussian_kernel(list(p.target_sigma))]
@@ -436,6 +489,35 @@ class SynthGenerator:
                 dst = free(cur)
                 lib.ssr_warp_linear(cur, dst, c['T'], None, B, *cs, 0, 0, 0, 0, 0, 0, None, *cs, None, st)
                 cur = dst
+            if p.randomise_res[i]:                                             # :215-220
+                nv_in = int(np.prod(cs))
+                for ax, kp in enumerate(c['kdyn']):                            # DynamicGaussianBlur: per-example kernels
+                    if kp is None:
+                        continue
+                    ksh = [1, 1, 1]
+                    ksh[ax] = p.dyn_window[ax]
+                    dst = free(cur)
+                    for b in range(B):
+                        lib.ssr_blur3d(cur.data_ptr() + 4 * b * nv_in, dst.data_ptr() + 4 * b * nv_in,
+                                       kp + 4 * b * p.dyn_window[ax], *ksh, None, None, 1, *cs, 1, 0, 1, 0, st)
+                    cur = dst
+                want_rel = p.build_reliability_maps
+                if c['reg']:
+                    dst, dd = free(cur), self.down
+                    lib.ssr_mimic_acquisition(cur, dst, dd if want_rel else None, c['mimic'], B, *cs, *os_, 1, 0, 1, 0, st)
+                    d2 = free(dst)
+                    lib.ssr_warp_linear(dst, d2, c['Tie'], None, B, *os_, 0, 0, 0, 0, 0, 0, None, *os_, None, st)
+                    lib.ssr_copy_strided(d2, self.image, B * int(np.prod(os_)), 1, 0, p.n_image_channels, out_c, st)
+                    out_c += 1
+                    if want_rel:
+                        lib.ssr_warp_linear(dd, d2, c['Tie'], None, B, *os_, 0, 0, 0, 0, 0, 0, None, *os_, None, st)
+                        lib.ssr_copy_strided(d2, self.image, B * int(np.prod(os_)), 1, 0, p.n_image_channels, out_c, st)
+                        out_c += 1
+                else:
+                    lib.ssr_mimic_acquisition(cur, self.image, self.image if want_rel else None, c['mimic'], B, *cs, *os_,
+                                              p.n_image_channels, out_c, p.n_image_channels, out_c + 1, st)
+                    out_c += 2 if want_rel else 1
+                continue
             ksteps = c['kacq']                                                 # :223-224
             direct = (not c['reg']) and p.down_shape[i] == cs and os_ == cs
             for n, (kp, ksh) in enumerate(ksteps):

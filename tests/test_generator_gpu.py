@@ -81,6 +81,23 @@ def test_multichannel_lowres_regerror_relmaps():
     _check(*_run_case(cfg, [40, 40, 40], GEN_LABELS, seed=7))
 
 
+def test_randomise_res_single_channel():
+    """randomise_res branch (labels_to_image_model.py:215-220): SampleResolution draws -> per-example separable
+    DynamicGaussianBlur -> fused MimicAcquisition, with the acquisition distance map as reliability channel."""
+    cfg = dict(randomise_res=True, build_reliability_maps=True, output_shape=32)
+    plan, image, target, keep, o_image, o_target, inter = _run_case(cfg, [40, 44, 36], GEN_LABELS, seed=11, batch=2)
+    assert plan.n_image_channels == 2
+    _check(plan, image, target, keep, o_image, o_target, inter)
+    assert np.abs(image[..., 1] - o_image[..., 1]).max() <= 1e-5          # distance map: same float32 operations
+
+
+def test_randomise_res_two_channels_regerror():
+    """randomised acquisition on two synthetic inputs with registration error on the second (+ warped distance maps)."""
+    cfg = dict(input_channels=[True, True], output_channel=0, randomise_res=True, build_reliability_maps=True,
+               simulate_registration_error=True, output_shape=32)
+    _check(*_run_case(cfg, [40, 40, 40], GEN_LABELS, seed=12))
+
+
 def test_target_resampling_and_padding():
     """target_res != atlas_res (blur + linear resample of the target, :189-196) and padding_margin (:116-120)."""
     cfg = dict(target_res=2., padding_margin=4, nonlin_std=2.)

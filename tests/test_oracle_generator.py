@@ -201,3 +201,40 @@ def test_sample_draws_shapes_and_ranges():
     assert np.all(np.abs(d['aff_shearing']) <= .02) and 0 <= d['svf_std'] <= 4
     assert 'gmm_normal' not in d and d['bias_normal_0'].shape == (2, 5, 5, 5)
     assert np.all((d['blur_mult_0'] >= 1 / 1.15) & (d['blur_mult_0'] <= 1.15))
+
+
+def test_mimic_acquisition_identity_and_distance_pattern():
+    """ext/lab2im/layers.py:921-987: acquisition at the volume resolution is the identity with zero distance; at
+    [1,1,3] mm every third plane along the last axis is 'acquired' (distance 0) and the distance peaks in between."""
+    rng = np.random.default_rng(0)
+    vol = rng.uniform(size=(12, 10, 18, 1)).astype(np.float32)
+    out, dist = OG.mimic_acquisition(vol, [1., 1., 1.], [1., 1., 1.], [1., 1., 1.], [12, 10, 18])
+    np.testing.assert_array_equal(out, vol)
+    assert dist.max() == 0
+    out, dist = OG.mimic_acquisition(vol, [1., 1., 3.], [1., 1., 1.], [1., 1., 1.], [12, 10, 18])
+    assert out.shape == vol.shape and dist.shape == vol.shape
+    np.testing.assert_array_equal(out[:, :, 0], vol[:, :, 0])                # first plane is sampled exactly
+    np.testing.assert_allclose(dist[0, 0, :7, 0], [0., 1., 1., 0., 1., 1., 0.], atol=1e-5)   # |j/3 - round(j/3)| * 3 mm
+    ds, dz, uz = OG.mimic_acquisition_zooms([12, 10, 18], [1., 1., 1.], [1., 1., 3.], [12, 10, 18])
+    assert list(ds) == [12, 10, 6] and np.allclose(dz, [1, 1, 1 / 3]) and np.allclose(uz, [1, 1, 3])
+
+
+def test_dynamic_kernels_host_logic_matches_oracle():
+    """product-side host helpers of the randomise_res branch against the oracle restatement (same float32 formulas),
+    including the reference's normalisation of the per-example kernels by the sum over the whole batch."""
+    from synthsr_b200.generator import dynamic_kernels, dynamic_sigma, mimic_zooms
+    rng = np.random.default_rng(3)
+    res = rng.uniform(1., 9., size=(3, 3)).astype(np.float32)
+    thick = (1. + rng.uniform(size=(3, 3)) * (res - 1.)).astype(np.float32)
+    mult = rng.uniform(1 / 1.15, 1.15, size=(3, 3)).astype(np.float32)
+    sig = dynamic_sigma([1., 1., 1.], res, thick)
+    np.testing.assert_array_equal(sig, OG.dynamic_sigma([1., 1., 1.], res, thick))
+    np.testing.assert_allclose(sig, 0.42 * np.minimum(res, thick), rtol=1e-6)
+    ks = dynamic_kernels(sig, [17, 17, 17], mult)
+    oks = OG.dynamic_separable_kernels(sig, 0.75 * 9. / np.ones(3), mult)
+    for a, b in zip(ks, oks):
+        np.testing.assert_array_equal(a, b)
+        assert a.shape == (3, 17) and abs(float(a.sum()) - 1.) < 1e-5            # batch-wide normalisation (reference quirk)
+    z = mimic_zooms([40, 44, 36], [1., 1., 1.], res[0], [32, 32, 32])
+    ds, dz, uz = OG.mimic_acquisition_zooms([40, 44, 36], [1., 1., 1.], res[0], [32, 32, 32])
+    np.testing.assert_array_equal(z, np.concatenate([dz, uz, res[0]]).astype(np.float32))

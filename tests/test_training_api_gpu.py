@@ -45,6 +45,24 @@ def test_brain_generator_generate_brain(dataset):
     assert not np.array_equal(image, image2)                                    # fresh augmentation every call
 
 
+def test_brain_generator_randomise_res(dataset):
+    """tutorial-4 style (fine_tuning_with_adversary.py:64 uses it too): randomise_res=True -> random acquisition
+    resolution per call, distance-to-acquired-voxel map as the reliability channel."""
+    from SynthSR.brain_generator import BrainGenerator
+    labels_dir, p, _ = dataset
+    gen = BrainGenerator(labels_dir, p['means'], p['stds'], 'normal', p['labels'], generation_classes=p['classes'],
+                         output_shape=32, randomise_res=True, build_reliability_maps=True)
+    assert gen.model_output_shape == [32, 32, 32, 2]
+    dmax = []
+    for _ in range(4):
+        image, target = gen.generate_brain()
+        assert image.shape == (32, 32, 32, 2) and np.isfinite(image).all() and np.isfinite(target).all()
+        dist = image[..., 1]
+        assert dist.min() >= 0 and dist.max() <= np.sqrt(3 * 4.5 ** 2) + 1e-3     # at most half a 9 mm voxel per axis
+        dmax.append(float(dist.max()))
+    assert len(set(np.round(dmax, 4))) > 1                                       # the acquisition resolution is re-drawn
+
+
 def test_training_runs_checkpoints_and_resumes(dataset):
     """tutorial-7 style training() call: 2 epochs x 3 steps, checkpoint per epoch, resume from 002."""
     from SynthSR.training import training
