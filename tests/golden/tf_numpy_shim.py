@@ -29,7 +29,11 @@ class T(np.ndarray):
         return np.asarray(a, dtype=dtype).view(cls)
 
     def get_shape(self):
-        return TensorShape(np.ndarray.shape.__get__(self))
+        # `static_batch_unknown` mimics a Keras tensor whose batch dimension is None at graph-construction time
+        shp = np.ndarray.shape.__get__(self)
+        if getattr(self, 'static_batch_unknown', False):
+            return TensorShape((None,) + tuple(shp[1:]))
+        return TensorShape(shp)
 
     @property
     def shape(self):
@@ -115,6 +119,7 @@ def install(random_queue=None):
     tf = types.ModuleType('tensorflow')
     tf.__path__ = []
     tf.TensorShape = TensorShape
+    tf.float32, tf.int32, tf.float64, tf.bool = 'float32', 'int32', 'float64', 'bool'
     tf.is_tensor = lambda x: isinstance(x, T)
     tf.cast = lambda x, dtype: _t(np.trunc(_np(x)) if np.issubdtype(_dtype(dtype), np.integer) and
                                   np.issubdtype(_np(x).dtype, np.floating) else _np(x)).astype(_dtype(dtype)).view(T)
@@ -146,7 +151,10 @@ def install(random_queue=None):
     tf.reduce_sum = lambda x, axis=None, keepdims=False: _t(np.sum(_np(x), axis=axis, keepdims=keepdims, dtype=_np(x).dtype))
     tf.map_fn = lambda fn, elems, dtype=None: _t(np.stack([_np(fn(e)) for e in (zip(*elems) if isinstance(elems, (list, tuple)) else elems)]))
     tf.math = types.SimpleNamespace(log=lambda x: _t(np.log(_np(x))), exp=tf.exp, minimum=lambda a, b: _t(np.minimum(_np(a), _np(b))),
-                                    equal=tf.equal, pow=lambda a, b: _t(np.power(_np(a), _np(b))))
+                                    equal=tf.equal, pow=lambda a, b: _t(np.power(_np(a), _np(b))),
+                                    floor=lambda x: _t(np.floor(_np(x))), ceil=lambda x: _t(np.ceil(_np(x))),
+                                    sqrt=lambda x: _t(np.sqrt(_np(x))), square=lambda x: _t(np.square(_np(x))),
+                                    reduce_sum=tf.reduce_sum)
     q = random_queue if random_queue is not None else []
     tf.random = types.SimpleNamespace(
         uniform=lambda shape, minval=0, maxval=1, dtype='float32': _t(q.pop(0)),
@@ -158,6 +166,7 @@ def install(random_queue=None):
     K.reshape = lambda x, s: tf.reshape(x, s)
     K.permute_dimensions = lambda x, p: _t(np.transpose(_np(x), p))
     K.epsilon = lambda: 1e-7
+    K.clip = lambda x, lo, hi: _t(np.minimum(np.maximum(_np(x), np.asarray(_np(lo), _np(x).dtype)), np.asarray(_np(hi), _np(x).dtype)))
 
     class _Any(types.ModuleType):
         __path__ = []
@@ -177,6 +186,25 @@ def install(random_queue=None):
                  'keras.utils', 'keras.constraints', 'keras.regularizers']:
         sys.modules[name] = _Any(name)
     keras.layers = sys.modules['keras.layers']
+
+    class Lambda:                                      # KL.Lambda(fn)(x) -> fn(x)
+        def __init__(self, fn, **kwargs):
+            self.fn = fn
+
+        def __call__(self, x):
+            return self.fn(x)
+
+    class Layer:                                       # base class of the reference's custom layers
+        def __init__(self, **kwargs):
+            pass
+
+        def build(self, input_shape):
+            self.built = True
+
+    keras.layers.Lambda = Lambda
+    keras.layers.Layer = Layer
+    sys.modules['keras.engine'].Layer = Layer
+    sys.modules['keras.engine.topology'].Layer = Layer
     np.int, np.float = int, float
     import scipy.stats
     if not hasattr(scipy.stats, 'median_absolute_deviation'):

@@ -84,3 +84,22 @@ def test_host_logic_matches_reference():
     for c in H['fs_sort']:
         ll, nn = U.get_list_labels(label_list=c['labels'], FS_sort=True)
         assert [int(v) for v in ll] == c['sorted'] and nn == c['n_neutral']
+
+
+def test_randomise_res_branch_bit_exact():
+    """oracle restatement of the randomise_res branch vs the reference's own edit_tensors.blurring_sigma_for_downsampling
+    (tensor branch), gaussian_kernel (sigma as a [B,3] tensor, separable -- including its normalisation by the sum over
+    the whole batch) and layers.MimicAcquisition.call, executed on the NumPy tf shim
+    (tests/golden/make_reference_randomise_res_goldens.py)."""
+    R = np.load(os.path.join(HERE, 'golden', 'reference_randomise_res.npz'))
+    sig = OG.dynamic_sigma([1., 1., 1.], R['res'], R['thick'], .42)
+    np.testing.assert_array_equal(sig, R['sigma'].astype(np.float32))
+    ks = OG.dynamic_separable_kernels(sig, 0.75 * 9. / np.ones(3), R['mult'])
+    for i in range(3):
+        np.testing.assert_array_equal(ks[i], R['kernel_%d' % i])
+    np.testing.assert_array_equal(OG.dynamic_separable_kernels(sig, 0.75 * 9. / np.ones(3), None)[2], R['kernel_nojitter_2'])
+    assert abs(float(R['kernel_0'].sum()) - 1.) < 1e-5 and R['kernel_0'].shape == (3, 17)       # one sum for the whole batch
+    for b in range(3):
+        o, d = OG.mimic_acquisition(R['vol'][b], R['res_mimic'][b], [1., 1., 1.], [1., 1., 1.], [8, 10, 16])
+        np.testing.assert_array_equal(o, R['mimic_vol'][b])
+        np.testing.assert_array_equal(d, R['mimic_dist'][b])
