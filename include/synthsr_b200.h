@@ -116,6 +116,15 @@ int ssr_conv3d_fwd_tc_k2n(const float* x, int C, const float* wp, const float* b
  * result in y, final = apply bias + activation. */
 int ssr_conv3d_fwd_tc_k2n_part(const float* x, int Ctot, int c0, int C, const float* wp, const float* bias, float* y, int B,
                                int d0, int d1, int d2, int Cout, int act, int accumulate, int final, void* stream);
+/* k2n forward that also accumulates the BatchNorm statistics of its output in the epilogue (sums: 2*Cout doubles,
+ * zeroed here: sum | sum of squares; finish with ssr_bn_finalize).  Cout = 24 or 32.  Replaces the reduction pass of
+ * KL.BatchNormalization over the full-resolution tensor (ext/neuron/models.py:349-351, 475-477). */
+int ssr_conv3d_fwd_tc_k2n_stats(const float* x, int C, const float* wp, const float* bias, float* y, double* sums, int B,
+                                int d0, int d1, int d2, int Cout, int act, void* stream);
+/* k2n data gradient fused with the ELU backward of the convolution below (activation='elu', models.py:316,444):
+ * dx = conv(dy, wp) * elu'(h), dbias[c] += sum_v dx[v][c]; h = that convolution's forward output.  Cout = 24 or 32. */
+int ssr_conv3d_dgrad_tc_k2n_elu(const float* dy, int C, const float* wp, const float* h, float* dx, float* dbias, int B,
+                                int d0, int d1, int d2, int Cout, void* stream);
 int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const float* dy, float* dw, float* db,
                         float* scratch, long long scratch_bytes, int B, int d0, int d1, int d2, int Cout,
                         void* stream);
@@ -137,6 +146,8 @@ int ssr_channel_sum(const float* t, long long nvox, int C, float* out, void* str
  * stats [4*C] = mean | invstd | gamma*invstd | beta - mean*gamma*invstd ; sums_scratch 2*C doubles. */
 int ssr_bn_stats(const float* x, long long nvox, int C, const float* gamma, const float* beta, float* moving_mean,
                  float* moving_var, float eps, float momentum, double* sums_scratch, float* stats, void* stream);
+int ssr_bn_finalize(const double* sums, long long nvox, int C, const float* gamma, const float* beta, float* moving_mean,
+                    float* moving_var, float eps, float momentum, float* stats, void* stream);
 int ssr_bn_stats_inference(int C, const float* gamma, const float* beta, const float* moving_mean,
                            const float* moving_var, float eps, float* stats, void* stream);
 /* mode 0: BN ; 1: BN + MaxPooling3D(2,'same') (models.py:354-356) ; 2: BN + UpSampling3D(2) (models.py:425-427). */
@@ -146,6 +157,12 @@ int ssr_bn_apply(const float* x, float* y, const float* stats, int B, int d0, in
 int ssr_bn_bwd(const float* dy, const float* x, const float* stats, long long nvox, int C, const float* add,
                int add_stride, int add_off, int elu, float* dx, float* dgamma, float* dbeta, float* dbias,
                double* sums_scratch, void* stream);
+/* encoder level: MaxPooling3D backward + BatchNormalization backward (+ skip gradient `add`, + ELU') in two passes, the
+ * full-resolution unpooled gradient is never materialised (= ssr_maxpool_bwd followed by ssr_bn_bwd).  (d0,d1,d2) = shape
+ * of x; dp = gradient w.r.t. the pooled output. */
+int ssr_pool_bn_bwd(const float* dp, const float* x, const float* stats, int B, int d0, int d1, int d2, int C,
+                    const float* add, int add_stride, int add_off, int elu, float* dx, float* dgamma, float* dbeta,
+                    float* dbias, double* sums_scratch, void* stream);
 int ssr_maxpool_bwd(const float* dp, const float* x, const float* stats, int B, int d0, int d1, int d2, int C,
                     float* dy_full, void* stream);
 int ssr_upsample_bwd(const float* du, int du_stride, int du_off, int B, int d0, int d1, int d2, int C, float* dlow,

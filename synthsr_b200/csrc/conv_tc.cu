@@ -526,9 +526,18 @@ struct KfGeom {
   int n1tiles, n2tiles, nzr, zlen;
 };
 
+// Epilogue fusions (EPI): the full-resolution tensors these layers write are the largest of the net, so the two
+// memory-bound passes that used to follow them ride in the epilogue instead (per-thread fp32 partial sums over the CTA's
+// whole item list, one warp-shuffle + shared-memory reduction per CTA at the end, one atomic per channel per CTA):
+//   EPI 1 (data gradient):  out *= elu'(h)  (h = forward output of the previous convolution, prefetched before the
+//                           accumulator wait) and  dbias[c] += sum_v out[v][c]        -- replaces elu_bwd_kernel
+//   EPI 2 (forward):        sums[c] += sum_v out[v][c], sums[C + c] += sum_v out^2    -- replaces colsum2_vec_kernel<0>
+// NB = channel blocks of 8 (compile time so the accumulators stay in registers).
+template <int EPI, int NB>
 __global__ void __launch_bounds__(416, 1)
 conv3d_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                     const float* __restrict__ bias, float* __restrict__ y, const KfGeom G) {
+                     const float* __restrict__ bias, float* __restrict__ y, const KfGeom G,
+                     const float* __restrict__ elu_h, float* __restrict__ dbias, double* __restrict__ sums) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sB = smem;
@@ -541,7 +550,9 @@ conv3d_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   uint64_t* fullB = accEmpty + KF_NACC;
   uint32_t* tmem_slot = (uint32_t*)(fullB + 1);
   float* sbias = (float*)(bars + 24);                    // 32 floats, zero padded
+  double* sred = (double*)(bars + 40);                   // 64 doubles: per-CTA channel sums of the fused epilogues
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (EPI != 0 && threadIdx.x < 64) sred[threadIdx.x] = 0.0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < KF_SA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, 3); }   // planes p-1, p, p+1 read slab p
@@ -647,18 +658,31 @@ conv3d_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const bool vec_ok = (G.Cout & 3) == 0;
     const int nblk8 = (G.Cout + 7) >> 3;
     uint32_t par = 0;                               // phase bit per ring slot
+    float s1[EPI != 0 ? NB * 8 : 1], s2[EPI == 2 ? NB * 8 : 1];
+#pragma unroll
+    for (int i = 0; i < (EPI != 0 ? NB * 8 : 1); ++i) s1[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < (EPI == 2 ? NB * 8 : 1); ++i) s2[i] = 0.f;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       KF_DECODE(item)
       const int i1 = y0 + yl, i2 = x0 - 1 + xin;
       const bool store_ok = xin >= 1 && xin <= KF_OUT2 && i1 < G.D1 && i2 < G.D2;
       for (int z = zs + h; z < ze; z += 2) {
         const int slot = (z - zs) & (KF_NACC - 1);
+        const long long voff = ((((long long)b * G.D0 + z) * G.D1 + i1) * G.D2 + i2) * G.Cout;
+        float4 hp[EPI == 1 ? NB * 2 : 1];
+        if constexpr (EPI == 1) {                     // h of this thread's voxel: in flight while the MMAs finish
+#pragma unroll
+          for (int i = 0; i < NB * 2; ++i)
+            hp[i] = store_ok ? __ldg(reinterpret_cast<const float4*>(elu_h + voff) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
         mbar_wait(accFull + slot, (par >> slot) & 1u);
         par ^= 1u << slot;
         tc_fence_after();
-        float* orow = y + ((((long long)b * G.D0 + z) * G.D1 + i1) * G.D2 + i2) * G.Cout;
+        float* orow = y + voff;
         const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * KF_N);
-        for (int cb = 0; cb < nblk8 * 8; cb += 8) {
+        auto block = [&](const int cb, const int blk) {
+          (void)blk;
           uint32_t v0[8], v1[8], v2[8];
           tmem_ld8(tbase + (uint32_t)cb, v0);
           tmem_ld8(tbase + (uint32_t)(32 + cb), v1);
@@ -693,7 +717,21 @@ conv3d_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
               o[e] = o[e] > 0.f ? o[e] : neg;
             }
           }
-          if (!store_ok) continue;
+          if constexpr (EPI == 1) {                   // elu'(pre) from the ELU output: 1 where h > 0, h + 1 elsewhere
+            const float4 ha = hp[2 * blk], hb = hp[2 * blk + 1];
+            const float hv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] *= hv[e] > 0.f ? 1.f : hv[e] + 1.f;
+          }
+          if (!store_ok) return;
+          if constexpr (EPI != 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s1[blk * 8 + e] += o[e];
+          }
+          if constexpr (EPI == 2) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s2[blk * 8 + e] += o[e] * o[e];
+          }
           const int nvalid = G.Cout - cb;
           if (nvalid >= 8 && vec_ok) {
             *reinterpret_cast<float4*>(orow + cb) = make_float4(o[0], o[1], o[2], o[3]);
@@ -703,10 +741,31 @@ conv3d_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             for (int e = 0; e < 8; ++e)
               if (e < nvalid) orow[cb + e] = o[e];
           }
+        };
+        if constexpr (EPI == 0) {
+          for (int cb = 0; cb < nblk8 * 8; cb += 8) block(cb, 0);
+        } else {                                      // Cout == NB * 8 (host-checked): constant indices into s1 / s2 / hp
+#pragma unroll
+          for (int blk = 0; blk < NB; ++blk) block(blk * 8, blk);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(accEmpty + slot);
+      }
+    }
+    if constexpr (EPI != 0) {                         // per-CTA reduction: warp butterfly, then shared-memory doubles
+#pragma unroll
+      for (int i = 0; i < NB * 8; ++i) {
+        float a = s1[i];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        if (lane == 0) atomicAdd(sred + i, (double)a);
+        if constexpr (EPI == 2) {
+          float c = s2[i];
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+          if (lane == 0) atomicAdd(sred + 32 + i, (double)c);
+        }
       }
     }
   }
@@ -714,6 +773,15 @@ conv3d_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if constexpr (EPI == 1) {
+    if (threadIdx.x < NB * 8) atomicAdd(dbias + threadIdx.x, (float)sred[threadIdx.x]);
+  }
+  if constexpr (EPI == 2) {
+    if (threadIdx.x < NB * 8) {
+      atomicAdd(sums + threadIdx.x, sred[threadIdx.x]);
+      atomicAdd(sums + NB * 8 + threadIdx.x, sred[32 + threadIdx.x]);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1575,6 +1643,18 @@ int pick_nt(int Npad) {
   return 16;
 }
 
+template <int EPI, int NB>
+static int launch_k2n(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& mx, const CUtensorMap& mw,
+                      const float* bias, float* y, const KfGeom& G, const float* elu_h, float* dbias, double* sums) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_k2n_kernel<EPI, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  conv3d_tc_k2n_kernel<EPI, NB><<<grid, 416, smem, st>>>(mx, mw, bias, y, G, elu_h, dbias, sums);   // TMA + 4 MMA + 8 epilogue warps
+  return SSR_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1710,8 +1790,10 @@ int ssr_conv3d_fwd_tc(const float* x1, int C1, const float* x2, int C2, const fl
 // x: tensor with Ctot channels; wp: the part's weights (pack mode 2 / 3, or ssr_conv3d_pack_weights_part).  accumulate:
 // add to the partial result already in y; final: apply bias + activation.  A concatenated input [x1, x2] is the sum of
 // its parts: first part accumulate = 0, last part final = 1.
+// epi: 0 plain, 1 multiply by elu'(elu_h) and accumulate dbias, 2 accumulate BatchNorm sums (sum | sum of squares)
 static int conv3d_fwd_tc_k2n_impl(const float* x, int Ctot, int c0, int C, const float* wp, const float* bias, float* y,
-                                  int B, int D0, int D1, int D2, int Cout, int act, int accumulate, int final, void* stream) {
+                                  int B, int D0, int D1, int D2, int Cout, int act, int accumulate, int final, void* stream,
+                                  int epi = 0, const float* elu_h = nullptr, float* dbias = nullptr, double* sums = nullptr) {
   SSR_CHECK_ARG(x && wp && y && B > 0 && D0 > 0 && D1 > 0 && D2 > 0, "pointers/shape");
   SSR_CHECK_ARG(C > 0 && C <= 32 && C % 8 == 0 && Cout > 0 && Cout <= 32 && c0 >= 0 && c0 + C <= Ctot && Ctot % 4 == 0,
                 "k2n forward needs <= 32 input channels per part (multiple of 8), Cout <= 32");
@@ -1744,16 +1826,21 @@ static int conv3d_fwd_tc_k2n_impl(const float* x, int Ctot, int c0, int C, const
   if (rc) return rc;
   rc = make_map_w(&mw, wp, 9 * KF_N, KF_N);
   if (rc) return rc;
-  const size_t smem = 1024 + 9 * (size_t)KF_BTILE_BYTES + (size_t)KF_SA * KF_SLAB_BYTES + 24 * 8 + 128;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SSR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_k2n_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  const size_t smem = 1024 + 9 * (size_t)KF_BTILE_BYTES + (size_t)KF_SA * KF_SLAB_BYTES + 24 * 8 + 128 + 64 * 8;
   const long long nitems = cols * G.nzr;
   SSR_CHECK_ARG(nitems < (1LL << 31), "grid too large");
   const unsigned grid = (unsigned)(nitems < num_sms ? nitems : num_sms);
-  conv3d_tc_k2n_kernel<<<grid, 416, smem, (cudaStream_t)stream>>>(mx, mw, bias, y, G);   // TMA + 4 MMA + 8 epilogue warps
+  cudaStream_t st = (cudaStream_t)stream;
+  if (epi != 0) {
+    SSR_CHECK_ARG(final == 1 && (Cout == 24 || Cout == 32), "fused k2n epilogues need the final part and Cout = 24 or 32");
+    SSR_CHECK_ARG(epi == 1 ? (elu_h && dbias && ((uintptr_t)elu_h & 15) == 0) : (epi == 2 && sums), "fused epilogue buffers");
+  }
+  if (epi == 1 && Cout == 24) rc = launch_k2n<1, 3>(grid, smem, st, mx, mw, bias, y, G, elu_h, dbias, sums);
+  else if (epi == 1) rc = launch_k2n<1, 4>(grid, smem, st, mx, mw, bias, y, G, elu_h, dbias, sums);
+  else if (epi == 2 && Cout == 24) rc = launch_k2n<2, 3>(grid, smem, st, mx, mw, bias, y, G, elu_h, dbias, sums);
+  else if (epi == 2) rc = launch_k2n<2, 4>(grid, smem, st, mx, mw, bias, y, G, elu_h, dbias, sums);
+  else rc = launch_k2n<0, 4>(grid, smem, st, mx, mw, bias, y, G, nullptr, nullptr, nullptr);
+  if (rc) return rc;
   SSR_COUNT_LAUNCH();
   SSR_CHECK_LAUNCH();
   return SSR_OK;
@@ -1766,6 +1853,23 @@ int ssr_conv3d_fwd_tc_k2n(const float* x, int C, const float* wp, const float* b
 int ssr_conv3d_fwd_tc_k2n_part(const float* x, int Ctot, int c0, int C, const float* wp, const float* bias, float* y, int B,
                                int D0, int D1, int D2, int Cout, int act, int accumulate, int final, void* stream) {
   return conv3d_fwd_tc_k2n_impl(x, Ctot, c0, C, wp, bias, y, B, D0, D1, D2, Cout, act, accumulate, final, stream);
+}
+
+// Data gradient of a Cin, Cout <= 32 layer fused with the ELU backward of the convolution below it (replaces
+// ssr_conv3d_fwd_tc_k2n + ssr_elu_bwd):  dx = conv(dy, wp) * elu'(h),  dbias[c] += sum_v dx[v][c].
+// h: forward OUTPUT (post-ELU) of the layer whose pre-activation gradient dx is; Cout = channels of dx (24 or 32).
+int ssr_conv3d_dgrad_tc_k2n_elu(const float* dy, int C, const float* wp, const float* h, float* dx, float* dbias, int B,
+                                int D0, int D1, int D2, int Cout, void* stream) {
+  return conv3d_fwd_tc_k2n_impl(dy, C, 0, C, wp, nullptr, dx, B, D0, D1, D2, Cout, 0, 0, 1, stream, 1, h, dbias, nullptr);
+}
+// Forward of a Cin, Cout <= 32 layer that also accumulates the BatchNorm statistics of its output (replaces the
+// reduction pass of ssr_bn_stats): sums[0..Cout) += sum_v y, sums[Cout..2 Cout) += sum_v y^2 (zeroed here; finish with
+// ssr_bn_finalize).
+int ssr_conv3d_fwd_tc_k2n_stats(const float* x, int C, const float* wp, const float* bias, float* y, double* sums, int B,
+                                int D0, int D1, int D2, int Cout, int act, void* stream) {
+  SSR_CHECK_ARG(sums, "sums");
+  SSR_CHECK_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)Cout * sizeof(double), (cudaStream_t)stream));
+  return conv3d_fwd_tc_k2n_impl(x, C, 0, C, wp, bias, y, B, D0, D1, D2, Cout, act, 0, 1, stream, 2, nullptr, nullptr, sums);
 }
 
 long long ssr_conv3d_wgrad_scratch_bytes(int, int, int, int, int, int, int) { return 0; }

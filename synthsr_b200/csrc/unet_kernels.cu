@@ -799,6 +799,150 @@ maxpool_bwd_vec_kernel(const float* __restrict__ dp, const float* __restrict__ x
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Encoder levels: backward of  maxpool2('same')(BN(x))  +  skip gradient, in two passes over x instead of four over x
+// and a full-resolution dy (maxpool_bwd_vec_kernel + colsum2_vec_kernel<1> + bn_bwd_apply_kernel): the pooled
+// gradient dp is routed to the first maximum of each 2x2x2 window on the fly, dy is never materialised.
+// A thread owns 4 channels of one pooled voxel (EW_THREADS % (C/4) == 0 keeps the channel group fixed per thread).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pool_window_load(const float* __restrict__ x, int b, int i, int j, int k, int d0, int d1,
+                                                 int d2, int C, int cv, float4* xv, long long* idx, bool* ok) {
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    const int s0 = 2 * i + (w >> 2), s1 = 2 * j + ((w >> 1) & 1), s2 = 2 * k + (w & 1);
+    ok[w] = s0 < d0 && s1 < d1 && s2 < d2;
+    idx[w] = ((((long long)b * d0 + s0) * d1 + s1) * d2 + s2) * C + 4 * cv;
+    xv[w] = ok[w] ? *reinterpret_cast<const float4*>(x + idx[w]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+// first maximum of BN(x) in window order (same rule as maxpool_bwd_vec_kernel)
+__device__ __forceinline__ void pool_window_argmax(const float4* xv, const bool* ok, const float4 sc, const float4 sf,
+                                                   int* arg) {
+  float4 m = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+  arg[0] = arg[1] = arg[2] = arg[3] = -1;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    if (!ok[w]) continue;
+    const float vx = xv[w].x * sc.x + sf.x, vy = xv[w].y * sc.y + sf.y, vz = xv[w].z * sc.z + sf.z, vw = xv[w].w * sc.w + sf.w;
+    if (vx > m.x) { m.x = vx; arg[0] = w; }
+    if (vy > m.y) { m.y = vy; arg[1] = w; }
+    if (vz > m.z) { m.z = vz; arg[2] = w; }
+    if (vw > m.w) { m.w = vw; arg[3] = w; }
+  }
+}
+
+// sums2[0..C) = sum_v dy, sums2[C..2C) = sum_v dy * xhat  with dy = unpool(dp)
+__global__ void __launch_bounds__(EW_THREADS)
+pool_bn_bwd_reduce_kernel(const float* __restrict__ dp, const float* __restrict__ x, const float* __restrict__ stats, int B,
+                          int d0, int d1, int d2, int C, double* __restrict__ sums2) {
+  __shared__ double sh[EW_THREADS * 8];
+  const int CV = C >> 2;
+  const int o0 = (d0 + 1) / 2, o1 = (d1 + 1) / 2, o2 = (d2 + 1) / 2;
+  const long long n = (long long)B * o0 * o1 * o2 * CV;
+  const long long tid = blockIdx.x * (long long)EW_THREADS + threadIdx.x;
+  const int cv = (int)(tid % CV);
+  const float4 mean = *reinterpret_cast<const float4*>(stats + 4 * cv);
+  const float4 inv = *reinterpret_cast<const float4*>(stats + C + 4 * cv);
+  const float4 sc = *reinterpret_cast<const float4*>(stats + 2 * C + 4 * cv);
+  const float4 sf = *reinterpret_cast<const float4*>(stats + 3 * C + 4 * cv);
+  double s[4] = {0., 0., 0., 0.}, q[4] = {0., 0., 0., 0.};
+  for (long long t = tid; t < n; t += (long long)gridDim.x * EW_THREADS) {
+    long long r = t / CV;
+    const int k = (int)(r % o2); r /= o2;
+    const int j = (int)(r % o1); r /= o1;
+    const int i = (int)(r % o0);
+    const int b = (int)(r / o0);
+    const float4 g = *reinterpret_cast<const float4*>(dp + t * 4);
+    float4 xv[8]; long long idx[8]; bool ok[8]; int arg[4];
+    pool_window_load(x, b, i, j, k, d0, d1, d2, C, cv, xv, idx, ok);
+    pool_window_argmax(xv, ok, sc, sf, arg);
+    float xa[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (arg[0] == w) xa[0] = xv[w].x;
+      if (arg[1] == w) xa[1] = xv[w].y;
+      if (arg[2] == w) xa[2] = xv[w].z;
+      if (arg[3] == w) xa[3] = xv[w].w;
+    }
+    s[0] += g.x; s[1] += g.y; s[2] += g.z; s[3] += g.w;
+    q[0] += g.x * ((xa[0] - mean.x) * inv.x); q[1] += g.y * ((xa[1] - mean.y) * inv.y);
+    q[2] += g.z * ((xa[2] - mean.z) * inv.z); q[3] += g.w * ((xa[3] - mean.w) * inv.w);
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { sh[threadIdx.x * 8 + e] = s[e]; sh[threadIdx.x * 8 + 4 + e] = q[e]; }
+  __syncthreads();
+  if ((int)threadIdx.x < CV) {
+    double ts[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+    for (int i = threadIdx.x; i < EW_THREADS; i += CV)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ts[e] += sh[i * 8 + e];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { atomicAdd(sums2 + 4 * cv + e, ts[e]); atomicAdd(sums2 + C + 4 * cv + e, ts[4 + e]); }
+  }
+}
+
+// dx = scale * (unpool(dp) - mean(dy) - xhat * mean(dy*xhat)) [+ add] [* elu'(x)] ; dbias += column sums of dx
+__global__ void __launch_bounds__(EW_THREADS)
+pool_bn_bwd_apply_kernel(const float* __restrict__ dp, const float* __restrict__ x, const float* __restrict__ stats,
+                         const double* __restrict__ sums2, int B, int d0, int d1, int d2, int C,
+                         const float* __restrict__ add, int add_stride, int add_off, int elu, float* __restrict__ dx,
+                         float* __restrict__ dbias) {
+  const int CV = C >> 2;
+  const int o0 = (d0 + 1) / 2, o1 = (d1 + 1) / 2, o2 = (d2 + 1) / 2;
+  const long long n = (long long)B * o0 * o1 * o2 * CV;
+  const long long tid = blockIdx.x * (long long)EW_THREADS + threadIdx.x;
+  const int cv = (int)(tid % CV);
+  const double inv_n = 1.0 / ((double)B * d0 * d1 * d2);
+  const float4 sc = *reinterpret_cast<const float4*>(stats + 2 * C + 4 * cv);
+  const float4 sf = *reinterpret_cast<const float4*>(stats + 3 * C + 4 * cv);
+  float mean[4], invstd[4], scale[4], m1[4], m2[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c = cv * 4 + e;
+    mean[e] = stats[c]; invstd[e] = stats[C + c]; scale[e] = stats[2 * C + c];
+    m1[e] = (float)(sums2[c] * inv_n); m2[e] = (float)(sums2[C + c] * inv_n);
+  }
+  float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long t = tid; t < n; t += (long long)gridDim.x * EW_THREADS) {
+    long long r = t / CV;
+    const int k = (int)(r % o2); r /= o2;
+    const int j = (int)(r % o1); r /= o1;
+    const int i = (int)(r % o0);
+    const int b = (int)(r / o0);
+    const float4 g = *reinterpret_cast<const float4*>(dp + t * 4);
+    const float gi[4] = {g.x, g.y, g.z, g.w};
+    float4 xv[8]; long long idx[8]; bool ok[8]; int arg[4];
+    pool_window_load(x, b, i, j, k, d0, d1, d2, C, cv, xv, idx, ok);
+    float4 av[8];
+    if (add) {
+#pragma unroll
+      for (int w = 0; w < 8; ++w)
+        av[w] = ok[w] ? *reinterpret_cast<const float4*>(add + (idx[w] / C) * add_stride + add_off + 4 * cv)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    pool_window_argmax(xv, ok, sc, sf, arg);
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (!ok[w]) continue;
+      const float xi[4] = {xv[w].x, xv[w].y, xv[w].z, xv[w].w};
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float xhat = (xi[e] - mean[e]) * invstd[e];
+        o[e] = scale[e] * ((arg[e] == w ? gi[e] : 0.f) - m1[e] - xhat * m2[e]);
+      }
+      if (add) { o[0] += av[w].x; o[1] += av[w].y; o[2] += av[w].z; o[3] += av[w].w; }
+      if (elu) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] *= elu_grad_from_out(xi[e]);
+      }
+      *reinterpret_cast<float4*>(dx + idx[w]) = make_float4(o[0], o[1], o[2], o[3]);
+      part.x += o[0]; part.y += o[1]; part.z += o[2]; part.w += o[3];
+    }
+  }
+  if (dbias) block_reduce_dbias(part, cv, CV, dbias);
+}
+
 __global__ void __launch_bounds__(256)
 upsample_bwd_vec_kernel(const float* __restrict__ du, int du_stride, int du_off, int B, int d0, int d1, int d2, int C,
                         float* __restrict__ dlow) {
@@ -1311,6 +1455,17 @@ int ssr_bn_stats(const float* x, long long nvox, int C, const float* gamma, cons
   return SSR_OK;
 }
 
+// second half of ssr_bn_stats for sums produced elsewhere (the fused epilogue of ssr_conv3d_fwd_tc_k2n_stats)
+int ssr_bn_finalize(const double* sums, long long nvox, int C, const float* gamma, const float* beta, float* moving_mean,
+                    float* moving_var, float eps, float momentum, float* stats, void* stream) {
+  SSR_CHECK_ARG(sums && gamma && beta && stats && nvox > 0 && C > 0, "args");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, nvox, C, gamma, beta, moving_mean, moving_var,
+                                                                         eps, momentum, stats);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
 int ssr_bn_stats_inference(int C, const float* gamma, const float* beta, const float* moving_mean,
                            const float* moving_var, float eps, float* stats, void* stream) {
   SSR_CHECK_ARG(gamma && beta && moving_mean && moving_var && stats && C > 0, "args");
@@ -1380,6 +1535,32 @@ int ssr_bn_bwd(const float* dy, const float* x, const float* stats, long long nv
     SSR_COUNT_LAUNCH();
     if (dbias) { int rc = ssr_channel_sum(dx, nvox, C, dbias, stream); if (rc) return rc; }
   }
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
+// Encoder level backward: gradient dp w.r.t. the POOLED BatchNorm output -> dx w.r.t. the BatchNorm input x
+// (= ssr_maxpool_bwd + ssr_bn_bwd without the full-resolution intermediate).  (d0,d1,d2): shape of x.
+int ssr_pool_bn_bwd(const float* dp, const float* x, const float* stats, int B, int d0, int d1, int d2, int C,
+                    const float* add, int add_stride, int add_off, int elu, float* dx, float* dgamma, float* dbeta,
+                    float* dbias, double* sums_scratch, void* stream) {
+  SSR_CHECK_ARG(dp && x && stats && dx && sums_scratch && B > 0 && d0 > 0 && d1 > 0 && d2 > 0 && C > 0, "args");
+  if (add && add_stride <= 0) { add_stride = C; add_off = 0; }
+  SSR_CHECK_ARG(C % 4 == 0 && EW_THREADS % (C / 4) == 0 && (!add || (add_stride % 4 == 0 && add_off % 4 == 0)) &&
+                (((uintptr_t)dp | (uintptr_t)x | (uintptr_t)stats | (uintptr_t)dx | (uintptr_t)add) & 15) == 0,
+                "ssr_pool_bn_bwd needs C % 4 == 0, 192 % (C/4) == 0 and 16-byte aligned tensors");
+  cudaStream_t st = (cudaStream_t)stream;
+  SSR_CHECK_CUDA(cudaMemsetAsync(sums_scratch, 0, 2 * C * sizeof(double), st));
+  const long long n = (long long)B * ((d0 + 1) / 2) * ((d1 + 1) / 2) * ((d2 + 1) / 2) * (C / 4);
+  pool_bn_bwd_reduce_kernel<<<ew_grid(n), EW_THREADS, 0, st>>>(dp, x, stats, B, d0, d1, d2, C, sums_scratch);
+  SSR_COUNT_LAUNCH();
+  if (dgamma && dbeta) {
+    bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums_scratch, C, dgamma, dbeta);
+    SSR_COUNT_LAUNCH();
+  }
+  pool_bn_bwd_apply_kernel<<<ew_grid(n), EW_THREADS, 0, st>>>(dp, x, stats, sums_scratch, B, d0, d1, d2, C, add, add_stride,
+                                                              add_off, elu, dx, dbias);
+  SSR_COUNT_LAUNCH();
   SSR_CHECK_LAUNCH();
   return SSR_OK;
 }

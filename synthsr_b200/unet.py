@@ -61,6 +61,9 @@ class UNet3D:
         self.fwd_k2n = os.environ.get('SSR_NO_FWD_K2N') is None
         self.fwd_k2n_parts = self.fwd_k2n and os.environ.get('SSR_NO_FWD_K2N_PARTS') is None
         self.materialise_feat = os.environ.get('SSR_MATERIALISE_FEAT') is not None
+        # BN statistics / ELU backward of the full-resolution 24-channel layers inside the k2n convolution epilogues
+        self.pool_bn_fusion = os.environ.get('SSR_NO_POOL_BN_FUSION') is None    # MaxPool + BN backward in two passes
+        self.epi_fusion = self.fwd_k2n and os.environ.get('SSR_NO_EPI_FUSION') is None
         self._side, self._side_busy, self._hp, self._pack_event = None, False, None, None
         self.device = torch.device(device)
         for d in self.dims:
@@ -199,15 +202,24 @@ class UNet3D:
         e1.record()
         self.prof.append((kind, 2. * self.k ** 3 * cin * cout * self.nvox[l], e0, e1))
 
-    def _conv_fwd(self, name, x1, c1, x2, c2, y, l, cout, act=1):
+    def _k2n_epi_ok(self, cin, cout):
+        return (self.conv_impl == 'tc' and self.epi_fusion and cin % 8 == 0 and cin <= 32 and cout in (24, 32))
+
+    def _conv_fwd(self, name, x1, c1, x2, c2, y, l, cout, act=1, stats_sums=None):
+        """stats_sums (2*cout doubles): the convolution also accumulates the BatchNorm sums of its output in its epilogue
+        (only offered by the caller when _k2n_epi_ok)."""
         tc = self.conv_impl == 'tc' and c1 % 8 == 0 and c2 % 8 == 0
         self._timed('fwd_tc' if tc else 'fwd_ref', l, c1 + c2, cout,
-                    lambda: self._conv_fwd_impl(tc, name, x1, c1, x2, c2, y, l, cout, act))
+                    lambda: self._conv_fwd_impl(tc, name, x1, c1, x2, c2, y, l, cout, act, stats_sums))
 
-    def _conv_fwd_impl(self, tc, name, x1, c1, x2, c2, y, l, cout, act):
+    def _conv_fwd_impl(self, tc, name, x1, c1, x2, c2, y, l, cout, act, stats_sums=None):
         st = stream_ptr()
         d = self.ldims[l]
-        if tc and self.fwd_k2n and c2 == 0 and c1 <= 32 and cout <= 32:
+        if stats_sums is not None:
+            assert tc and c2 == 0
+            lib.ssr_conv3d_fwd_tc_k2n_stats(x1, c1, self._packed_w(name, 2, c1, 0, cout), self.p[name + '/bias'], y,
+                                            stats_sums, self.B, *d, cout, act, st)
+        elif tc and self.fwd_k2n and c2 == 0 and c1 <= 32 and cout <= 32:
             # full-resolution 24-channel layers: d2 taps in the MMA N dimension (conv3d_tc_k2n_kernel)
             lib.ssr_conv3d_fwd_tc_k2n(x1, c1, self._packed_w(name, 2, c1, 0, cout), self.p[name + '/bias'], y,
                                       self.B, *d, cout, act, st)
@@ -225,15 +237,20 @@ class UNet3D:
             lib.ssr_conv3d_fwd_ref(x1, c1, x2, c2, self.p[name + '/kernel'], self.p[name + '/bias'], y, self.B, *d,
                                    cout, self.k, act, st)
 
-    def _conv_dgrad(self, name, dy, dx, l, cin, cout):
+    def _conv_dgrad(self, name, dy, dx, l, cin, cout, elu_h=None, dbias=None):
+        """elu_h / dbias: fuse the ELU backward of the layer below (dx *= elu'(elu_h), dbias += column sums of dx)."""
         tc = self.conv_impl == 'tc' and cout % 8 == 0
         self._timed('dgrad_tc' if tc else 'dgrad_ref', l, cin, cout,
-                    lambda: self._conv_dgrad_impl(tc, name, dy, dx, l, cin, cout))
+                    lambda: self._conv_dgrad_impl(tc, name, dy, dx, l, cin, cout, elu_h, dbias))
 
-    def _conv_dgrad_impl(self, tc, name, dy, dx, l, cin, cout):
+    def _conv_dgrad_impl(self, tc, name, dy, dx, l, cin, cout, elu_h=None, dbias=None):
         st = stream_ptr()
         d = self.ldims[l]
-        if tc and self.fwd_k2n and cin <= 32 and cout <= 32:
+        if elu_h is not None:
+            assert tc
+            lib.ssr_conv3d_dgrad_tc_k2n_elu(dy, cout, self._packed_w(name, 3, cin, 0, cout), elu_h, dx, dbias, self.B,
+                                            *d, cin, st)
+        elif tc and self.fwd_k2n and cin <= 32 and cout <= 32:
             lib.ssr_conv3d_fwd_tc_k2n(dy, cout, self._packed_w(name, 3, cin, 0, cout), None, dx, self.B, *d, cin, 0, st)
         elif tc:
             # data gradient = forward convolution of dy with the flipped / transposed kernel
@@ -335,9 +352,11 @@ class UNet3D:
         x, cx = image, self.cin
         for l in range(L):
             self._conv_fwd('unet_conv_downarm_%d_0' % l, x, cx, None, 0, self.h0[l], l, F[l])
-            self._conv_fwd('unet_conv_downarm_%d_1' % l, self.h0[l], F[l], None, 0, self.h1[l], l, F[l])
             bn = 'unet_bn_down_%d' % l
-            self._bn_stats(bn, self.h1[l], self.nvox[l], F[l], self.stats_enc[l], training)
+            fused = training and self._k2n_epi_ok(F[l], F[l])
+            self._conv_fwd('unet_conv_downarm_%d_1' % l, self.h0[l], F[l], None, 0, self.h1[l], l, F[l],
+                           stats_sums=self.sums if fused else None)
+            self._bn_stats(bn, self.h1[l], self.nvox[l], F[l], self.stats_enc[l], training, have_sums=fused)
             if l < L - 1:
                 lib.ssr_bn_apply(self.h1[l], self.inp[l + 1], self.stats_enc[l], B, *self.ldims[l], F[l], 1, 0, 0, st)
                 x, cx = self.inp[l + 1], F[l]
@@ -346,8 +365,11 @@ class UNet3D:
             l = L - 2 - d
             lib.ssr_bn_apply(prev, self.u[l], prev_stats, B, *self.ldims[prev_l], F[prev_l], 2, 0, 0, st)
             self._conv_fwd('unet_conv_uparm_%d_0' % (L + d), self.h1[l], F[l], self.u[l], F[l + 1], self.g0[l], l, F[l])
-            self._conv_fwd('unet_conv_uparm_%d_1' % (L + d), self.g0[l], F[l], None, 0, self.g1[l], l, F[l])
-            self._bn_stats('unet_bn_up_%d' % d, self.g1[l], self.nvox[l], F[l], self.stats_dec[l], training)
+            fused = training and self._k2n_epi_ok(F[l], F[l])
+            self._conv_fwd('unet_conv_uparm_%d_1' % (L + d), self.g0[l], F[l], None, 0, self.g1[l], l, F[l],
+                           stats_sums=self.sums if fused else None)
+            self._bn_stats('unet_bn_up_%d' % d, self.g1[l], self.nvox[l], F[l], self.stats_dec[l], training,
+                           have_sums=fused)
             prev, prev_stats, prev_l = self.g1[l], self.stats_dec[l], l
         if L > 1 and not self.materialise_feat:
             # the last BatchNorm is folded into the head kernel (raw g1 + stats): no normalised feature tensor
@@ -357,9 +379,13 @@ class UNet3D:
         self._feat_src, self._feat_stats = self.feat, None
         return self.feat
 
-    def _bn_stats(self, bn, x, nvox, C, stats, training):
+    def _bn_stats(self, bn, x, nvox, C, stats, training, have_sums=False):
         st = stream_ptr()
-        if training:
+        if training and have_sums:       # self.sums was filled by the epilogue of the convolution that wrote x
+            lib.ssr_bn_finalize(self.sums, nvox, C, self.p[bn + '/gamma'], self.p[bn + '/beta'],
+                                self.moving[bn + '/moving_mean'], self.moving[bn + '/moving_variance'], BN_EPS,
+                                BN_MOMENTUM, stats, st)
+        elif training:
             lib.ssr_bn_stats(x, nvox, C, self.p[bn + '/gamma'], self.p[bn + '/beta'], self.moving[bn + '/moving_mean'],
                              self.moving[bn + '/moving_variance'], BN_EPS, BN_MOMENTUM, self.sums, stats, st)
         else:
@@ -427,8 +453,11 @@ class UNet3D:
                 lib.ssr_bn_bwd(self.dbn_dec[l], self.g1[l], self.stats_dec[l], self.nvox[l], F[l], None, 0, 0, 1, self.ga[l],
                                self.g[bn + '/gamma'], self.g[bn + '/beta'], self.g[c1n + '/bias'], self.sums, st)
                 self._wgrad_async(c1n, self.g0[l], F[l], None, 0, self.ga[l], l, F[l])
-                self._conv_dgrad(c1n, self.ga[l], self.gb[l], l, F[l], F[l])
-                lib.ssr_elu_bwd(self.gb[l], 0, 0, self.g0[l], None, self.nvox[l], F[l], self.gb[l], self.g[c0 + '/bias'], st)
+                if self._k2n_epi_ok(F[l], F[l]):
+                    self._conv_dgrad(c1n, self.ga[l], self.gb[l], l, F[l], F[l], elu_h=self.g0[l], dbias=self.g[c0 + '/bias'])
+                else:
+                    self._conv_dgrad(c1n, self.ga[l], self.gb[l], l, F[l], F[l])
+                    lib.ssr_elu_bwd(self.gb[l], 0, 0, self.g0[l], None, self.nvox[l], F[l], self.gb[l], self.g[c0 + '/bias'], st)
                 self._wgrad_async(c0, self.h1[l], F[l], self.u[l], F[l + 1], self.gb[l], l, F[l])
                 self._conv_dgrad(c0, self.gb[l], self.dcat[l], l, F[l] + F[l + 1], F[l])
                 tgt = self.dbn_dec[l + 1] if l + 1 <= L - 2 else self.dbn_bott
@@ -439,6 +468,10 @@ class UNet3D:
                 if l == L - 1:
                     lib.ssr_bn_bwd(self.dbn_bott, self.h1[l], self.stats_enc[l], self.nvox[l], F[l], None, 0, 0, 1,
                                    self.ga_e[l], self.g[bn + '/gamma'], self.g[bn + '/beta'], self.g[c1n + '/bias'], self.sums, st)
+                elif self.pool_bn_fusion and F[l] % 4 == 0 and 192 % (F[l] // 4) == 0:
+                    lib.ssr_pool_bn_bwd(self.dp[l + 1], self.h1[l], self.stats_enc[l], B, *self.ldims[l], F[l], self.dcat[l],
+                                        F[l] + F[l + 1], 0, 1, self.ga_e[l], self.g[bn + '/gamma'], self.g[bn + '/beta'],
+                                        self.g[c1n + '/bias'], self.sums, st)
                 else:
                     lib.ssr_maxpool_bwd(self.dp[l + 1], self.h1[l], self.stats_enc[l], B, *self.ldims[l], F[l], self.ga_e[l],
                                         st)
@@ -446,8 +479,13 @@ class UNet3D:
                                    F[l] + F[l + 1], 0, 1, self.ga_e[l], self.g[bn + '/gamma'], self.g[bn + '/beta'],
                                    self.g[c1n + '/bias'], self.sums, st)
                 self._wgrad_async(c1n, self.h0[l], F[l], None, 0, self.ga_e[l], l, F[l])
-                self._conv_dgrad(c1n, self.ga_e[l], self.gb_e[l], l, F[l], F[l])
-                lib.ssr_elu_bwd(self.gb_e[l], 0, 0, self.h0[l], None, self.nvox[l], F[l], self.gb_e[l], self.g[c0 + '/bias'], st)
+                if self._k2n_epi_ok(F[l], F[l]):
+                    self._conv_dgrad(c1n, self.ga_e[l], self.gb_e[l], l, F[l], F[l], elu_h=self.h0[l],
+                                     dbias=self.g[c0 + '/bias'])
+                else:
+                    self._conv_dgrad(c1n, self.ga_e[l], self.gb_e[l], l, F[l], F[l])
+                    lib.ssr_elu_bwd(self.gb_e[l], 0, 0, self.h0[l], None, self.nvox[l], F[l], self.gb_e[l],
+                                    self.g[c0 + '/bias'], st)
                 x, cx = (self._image, self.cin) if l == 0 else (self.inp[l], F[l - 1])
                 self._wgrad_async(c0, x, cx, None, 0, self.gb_e[l], l, F[l])
                 if l > 0:

@@ -341,3 +341,132 @@ def test_tc_k2n_channel_parts_match_float64():
         assert not torch.isnan(y).any()
         err = (y.double().cpu() - y64).abs().max().item() / y64.abs().max().item()
         assert err < 2e-5, (d, c1, c2, co, err)
+
+
+def test_tc_k2n_fused_epilogues_match_float64():
+    """k2n epilogue fusions: forward + BatchNorm sums (sum | sum of squares of the ELU output) and data gradient x elu'(h)
+    + bias-gradient column sums, against float64 on identically rounded operands; ragged sizes (partial tiles must not
+    enter the sums) and several d0 ranges per CTA."""
+    from synthsr_b200._lib import lib, stream_ptr
+    rng = np.random.default_rng(7)
+    for (d, c) in [([16, 16, 16], 24), ([9, 11, 30], 24), ([21, 8, 14], 32), ([40, 24, 29], 24), ([64, 64, 64], 24)]:
+        nv = int(np.prod(d))
+        x = torch.from_numpy(rng.normal(size=(nv, c)).astype(np.float32)).cuda()
+        w = torch.from_numpy((rng.normal(size=(3, 3, 3, c, c)) / np.sqrt(27 * c)).astype(np.float32)).cuda()
+        b = torch.from_numpy(rng.normal(size=c).astype(np.float32)).cuda()
+        st = stream_ptr()
+        wr = _rna_tf32(w).double().cpu().permute(4, 3, 0, 1, 2)
+        # ---- forward + statistics
+        y = torch.full((nv, c), float('nan'), dtype=torch.float32, device='cuda')
+        sums = torch.full((2 * c,), 123., dtype=torch.float64, device='cuda')        # must be zeroed by the call
+        wp = torch.empty(lib.ssr_conv3d_packed_size(c, 0, c, 2), dtype=torch.float32, device='cuda')
+        lib.ssr_conv3d_pack_weights(w, wp, c, 0, c, 2, st)
+        lib.ssr_conv3d_fwd_tc_k2n_stats(x, c, wp, b, y, sums, 1, *d, c, 1, st)
+        torch.cuda.synchronize()
+        xr = _rne_tf32(x).double().cpu().view(1, *d, c).permute(0, 4, 1, 2, 3)
+        y64 = torch.nn.functional.elu(torch.nn.functional.conv3d(xr, wr, b.double().cpu(), padding=1))
+        y64 = y64.permute(0, 2, 3, 4, 1).reshape(nv, c)
+        assert not torch.isnan(y).any(), ('fwd nan', d, c)
+        err = (y.double().cpu() - y64).abs().max().item() / y64.abs().max().item()
+        assert err < 2e-5, ('fwd', d, c, err)
+        yd = y.double().cpu()                       # the sums are of the values actually written
+        s_ref = torch.cat([yd.sum(0), (yd * yd).sum(0)])
+        # fp32 per-thread partials: error relative to the sum of magnitudes
+        mag = torch.cat([yd.abs().sum(0), (yd * yd).sum(0)])
+        err = ((sums.cpu() - s_ref).abs() / mag).max().item()
+        assert err < 2e-6, ('stats', d, c, err)
+        # finalize -> same stats as the separate reduction kernel
+        gamma = torch.from_numpy(rng.uniform(.5, 1.5, size=c).astype(np.float32)).cuda()
+        beta = torch.from_numpy(rng.normal(size=c).astype(np.float32)).cuda()
+        mm1, mv1 = torch.zeros(c, device='cuda'), torch.ones(c, device='cuda')
+        mm2, mv2 = torch.zeros(c, device='cuda'), torch.ones(c, device='cuda')
+        st1, st2 = torch.empty(4 * c, device='cuda'), torch.empty(4 * c, device='cuda')
+        lib.ssr_bn_finalize(sums, nv, c, gamma, beta, mm1, mv1, 1e-3, .99, st1, st)
+        scratch = torch.zeros(2 * c, dtype=torch.float64, device='cuda')
+        lib.ssr_bn_stats(y, nv, c, gamma, beta, mm2, mv2, 1e-3, .99, scratch, st2, st)
+        torch.cuda.synchronize()
+        assert torch.allclose(st1, st2, rtol=2e-5, atol=2e-6), ('finalize', d, c, (st1 - st2).abs().max().item())
+        assert torch.allclose(mm1, mm2, rtol=2e-5, atol=1e-7) and torch.allclose(mv1, mv2, rtol=2e-5, atol=1e-7)
+        # ---- data gradient x elu'(h) + bias gradient
+        dy = torch.from_numpy(rng.normal(size=(nv, c)).astype(np.float32)).cuda()
+        h = torch.nn.functional.elu(torch.from_numpy(rng.normal(size=(nv, c)).astype(np.float32))).cuda()
+        dx = torch.full((nv, c), float('nan'), dtype=torch.float32, device='cuda')
+        db = torch.from_numpy(rng.normal(size=c).astype(np.float32)).cuda()          # accumulated into (+=)
+        db0 = db.clone()
+        wp3 = torch.empty(lib.ssr_conv3d_packed_size(c, 0, c, 3), dtype=torch.float32, device='cuda')
+        lib.ssr_conv3d_pack_weights(w, wp3, c, 0, c, 3, st)
+        lib.ssr_conv3d_dgrad_tc_k2n_elu(dy, c, wp3, h, dx, db, 1, *d, c, st)
+        torch.cuda.synchronize()
+        dyr = _rne_tf32(dy).double().cpu().view(1, *d, c).permute(0, 4, 1, 2, 3)
+        dx64 = torch.nn.functional.conv_transpose3d(dyr, wr, padding=1).permute(0, 2, 3, 4, 1).reshape(nv, c)
+        hd = h.double().cpu()
+        dx64 = dx64 * torch.where(hd > 0, torch.ones_like(hd), hd + 1.)
+        assert not torch.isnan(dx).any(), ('dgrad nan', d, c)
+        err = (dx.double().cpu() - dx64).abs().max().item() / dx64.abs().max().item()
+        assert err < 2e-5, ('dgrad*elu', d, c, err)
+        dxd = dx.double().cpu()
+        err = ((db.double().cpu() - db0.double().cpu() - dxd.sum(0)).abs() / dxd.abs().sum(0)).max().item()
+        assert err < 2e-6, ('dbias', d, c, err)
+
+
+def test_tc_step_fused_epilogues_equal_separate_kernels():
+    """one training step with the fused k2n epilogues and the fused MaxPool+BN backward against the same step with the
+    separate BN-statistics / ELU-backward / unpooling kernels (identical convolution arithmetic; only the reduction order of
+    the sums differs)."""
+    from synthsr_b200.unet import UNet3D
+    dims, rng = [32, 48, 32], np.random.default_rng(11)
+    image = torch.from_numpy(rng.uniform(0, 1, size=(1, *dims, 1)).astype(np.float32)).cuda()
+    target = torch.from_numpy(rng.uniform(0, 1, size=(1, *dims, 1)).astype(np.float32)).cuda()
+    out = []
+    for fused in (True, False):
+        net = UNet3D(dims + [1], nb_levels=3, batchsize=1, conv_impl='tc', seed=3)
+        assert net.epi_fusion, 'fused epilogues are expected to be the default'
+        net.epi_fusion = net.pool_bn_fusion = fused
+        loss = net.loss_and_grad(image, target)
+        torch.cuda.synchronize()
+        out.append((loss.item(), net.grads.clone(), net.pred.clone(), {k: v.clone() for k, v in net.moving.items()}))
+    (l1, g1, p1, m1), (l2, g2, p2, m2) = out
+    assert abs(l1 - l2) <= 1e-6 * abs(l2)
+    assert (p1 - p2).abs().max().item() <= 1e-5 * p2.abs().max().item()
+    assert (g1 - g2).norm().item() <= 1e-4 * g2.norm().item()
+    for k in m1:
+        assert torch.allclose(m1[k], m2[k], rtol=1e-5, atol=1e-7), k
+
+
+def test_pool_bn_bwd_equals_maxpool_bwd_then_bn_bwd():
+    """ssr_pool_bn_bwd (two passes, no full-resolution dy) == ssr_maxpool_bwd + ssr_bn_bwd; odd sizes ('same' pooling
+    windows clipped at the end), skip gradient taken from a channel slice of a wider tensor, ties inside windows."""
+    from synthsr_b200._lib import lib, stream_ptr
+    rng = np.random.default_rng(13)
+    for (B, d, C, ctot, elu) in [(1, [16, 16, 16], 24, 72, 1), (2, [9, 11, 7], 48, 144, 1), (1, [6, 5, 8], 96, 96, 0),
+                                 (1, [32, 32, 32], 24, 72, 1)]:
+        nv = B * int(np.prod(d))
+        od = [(v + 1) // 2 for v in d]
+        npool = B * int(np.prod(od))
+        xh = rng.normal(size=(nv, C)).astype(np.float32)
+        xh[rng.uniform(size=xh.shape) < .2] = 0.5                        # ties: first maximum in window order wins
+        x = torch.from_numpy(xh).cuda()
+        dp = torch.from_numpy(rng.normal(size=(npool, C)).astype(np.float32)).cuda()
+        add = torch.from_numpy(rng.normal(size=(nv, ctot)).astype(np.float32)).cuda()
+        gamma = torch.from_numpy(rng.uniform(-1.5, 1.5, size=C).astype(np.float32)).cuda()   # negative scale: argmin of x
+        beta = torch.from_numpy(rng.normal(size=C).astype(np.float32)).cuda()
+        st = stream_ptr()
+        stats = torch.empty(4 * C, device='cuda')
+        sums = torch.zeros(2 * C, dtype=torch.float64, device='cuda')
+        lib.ssr_bn_stats(x, nv, C, gamma, beta, None, None, 1e-3, .99, sums, stats, st)
+        res = []
+        for fused in (False, True):
+            dx = torch.full((nv, C), float('nan'), device='cuda')
+            dg, db, dbias = torch.zeros(C, device='cuda'), torch.zeros(C, device='cuda'), torch.zeros(C, device='cuda')
+            if fused:
+                lib.ssr_pool_bn_bwd(dp, x, stats, B, *d, C, add, ctot, 0, elu, dx, dg, db, dbias, sums, st)
+            else:
+                dyf = torch.full((nv, C), float('nan'), device='cuda')
+                lib.ssr_maxpool_bwd(dp, x, stats, B, *d, C, dyf, st)
+                lib.ssr_bn_bwd(dyf, x, stats, nv, C, add, ctot, 0, elu, dx, dg, db, dbias, sums, st)
+            torch.cuda.synchronize()
+            assert not torch.isnan(dx).any()
+            res.append((dx, dg, db, dbias))
+        for a, b_, name in zip(res[0], res[1], ('dx', 'dgamma', 'dbeta', 'dbias')):
+            err = (a - b_).abs().max().item() / (a.abs().max().item() + 1e-30)
+            assert err < 2e-6, (name, B, d, C, err)
