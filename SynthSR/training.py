@@ -2,7 +2,7 @@
 
 Every step: host sampler (label map + GMM parameters) -> CUDA generator -> U-Net forward/backward (tcgen05 TF32
 convolutions) -> [single NCCL all-reduce of the flat gradient buffer when launched with torchrun] -> fused Adam.
-One checkpoint per epoch named %03d (Keras layer names inside; .npz because no HDF5 writer is available)."""
+One checkpoint per epoch named %03d.h5 (Keras ModelCheckpoint layout, written by synthsr_b200/h5lite.py)."""
 import os
 import time
 
@@ -150,27 +150,45 @@ def training(labels_dir,
 
 
 def load_checkpoint(engine, path, different_lhood_layer=False):
-    """weights by Keras layer name (+ Adam state and epoch when the file holds them).  A file whose name ends with a
-    3-digit epoch resumes at that epoch like the reference (training.py:434-435)."""
-    sd = dict(np.load(path))
+    """weights by Keras layer name (+ this engine's Adam state when the file holds it).  Accepts the reference's own
+    checkpoints (Keras .h5: ModelCheckpoint full-model files or `save_weights` files, training.py:353-369, 429) and the
+    earlier .npz format.  A file whose name ends with a 3-digit epoch resumes at that epoch like the reference
+    (training.py:435: int(path_checkpoint[-6:-3]))."""
+    if str(path).endswith('.h5'):
+        from synthsr_b200 import h5lite
+        sd, _ = h5lite.load_keras_weights(path)
+        opt = h5lite.load_extra(path)
+    else:
+        raw = dict(np.load(path))
+        sd = {k: v for k, v in raw.items() if not k.startswith('optimizer/')}
+        opt = {k.split('/', 1)[1]: v for k, v in raw.items() if k.startswith('optimizer/')}
     if different_lhood_layer:
         sd = {k: v for k, v in sd.items() if not k.startswith('unet_likelihood')}
-    engine.net.load_state_dict({k: v for k, v in sd.items() if not k.startswith('optimizer/')}, strict=False)
-    if 'optimizer/m' in sd and not different_lhood_layer:
+    engine.net.load_state_dict(sd, strict=False)
+    if 'm' in opt and not different_lhood_layer and np.size(opt['m']) == engine.net.n_params:
         import torch
-        engine.net.adam_m.copy_(torch.as_tensor(sd['optimizer/m']))
-        engine.net.adam_v.copy_(torch.as_tensor(sd['optimizer/v']))
-        engine.net.iterations = int(sd['optimizer/iterations'])
+        engine.net.adam_m.copy_(torch.as_tensor(np.asarray(opt['m'], dtype=np.float32)))
+        engine.net.adam_v.copy_(torch.as_tensor(np.asarray(opt['v'], dtype=np.float32)))
+        engine.net.iterations = int(np.asarray(opt['iterations']).reshape(-1)[0])
     stem = os.path.splitext(os.path.basename(path))[0]
     return int(stem[-3:]) if stem[-3:].isdigit() else 0
 
 
 def save_checkpoint(engine, path):
-    sd = engine.net.state_dict()
-    sd['optimizer/m'] = engine.net.adam_m.cpu().numpy()
-    sd['optimizer/v'] = engine.net.adam_v.cpu().numpy()
-    sd['optimizer/iterations'] = np.int64(engine.net.iterations)
-    np.savez(path, **sd)
+    """'%03d.h5' in the layout Keras' ModelCheckpoint writes (weights under /model_weights with the Keras layer names, so
+    the reference's `load_weights(by_name=True)` / predict scripts read it); the flat Adam moments ride in
+    /optimizer_weights for an exact resume on this engine."""
+    from synthsr_b200 import h5lite
+    from synthsr_b200.unet import keras_layer_order
+    extra = {'m': engine.net.adam_m.cpu().numpy(), 'v': engine.net.adam_v.cpu().numpy(),
+             'iterations': np.array([engine.net.iterations], dtype=np.int64)}
+    if str(path).endswith('.h5'):
+        h5lite.save_keras_weights(path, engine.net.state_dict(), keras_layer_order(engine.net.L), extra=extra,
+                                  full_model=True)
+    else:
+        sd = engine.net.state_dict()
+        sd.update({'optimizer/' + k: v for k, v in extra.items()})
+        np.savez(path, **sd)
 
 
 def train_model(engine, generator, learning_rate, lr_decay, n_epochs, n_steps, model_dir, init_epoch=0):
@@ -201,6 +219,6 @@ def train_model(engine, generator, learning_rate, lr_decay, n_epochs, n_steps, m
                                                                        n_steps * engine.B * engine.world / dt))
             log.write('%d,%.6f,%.3f\n' % (epoch + 1, loss, dt))
             log.flush()
-            save_checkpoint(engine, os.path.join(model_dir, '%03d.npz' % (epoch + 1)))
+            save_checkpoint(engine, os.path.join(model_dir, '%03d.h5' % (epoch + 1)))
     if log:
         log.close()

@@ -1,8 +1,8 @@
 """`ext.neuron.models.unet` of the reference (ext/neuron/models.py:26-145) on the B200 engine.
 
 Returns a `UnetModel` that plays the role of the Keras `Model` for the training path: `.predict(image)`,
-`.get_weights()/.set_weights()` by Keras layer name, `.save_weights()/.load_weights()` (.npz; an .h5 writer needs
-h5py, which this image lacks -- SURVEY.md 8f).  Auto-encoder variants (`ae`, `single_ae`, `add_prior`) are not part
+`.get_weights()/.set_weights()` by Keras layer name, `.save_weights()/.load_weights()` (Keras .h5 through the pure-Python
+HDF5 reader/writer synthsr_b200/h5lite.py -- h5py is not installed -- or .npz).  Auto-encoder variants (`ae`, `single_ae`, `add_prior`) are not part
 of SynthSR's path and are not provided."""
 import numpy as np
 
@@ -30,14 +30,29 @@ class UnetModel:
         self.net.load_state_dict(sd, strict=False)
 
     def save_weights(self, path):
-        np.savez(path, **self.net.state_dict())
+        """'.h5': Keras `save_weights` layout (readable by keras `load_weights(by_name=True)` and the reference's
+        predict scripts); anything else: .npz with the same '<layer>/<weight>' keys."""
+        if str(path).endswith('.h5'):
+            from synthsr_b200 import h5lite
+            from synthsr_b200.unet import keras_layer_order
+            h5lite.save_keras_weights(path, self.net.state_dict(), keras_layer_order(self.net.L))
+        else:
+            np.savez(path, **self.net.state_dict())
 
     def load_weights(self, path, by_name=True):
-        if path.endswith('.h5'):
-            raise NotImplementedError('reading Keras .h5 needs an HDF5 reader (h5py is not installed); convert the '
-                                      'file to .npz with the Keras layer names (kernel/bias/gamma/beta/moving_*)')
-        sd = dict(np.load(path))
-        self.net.load_state_dict({k: v for k, v in sd.items() if not k.startswith('optimizer/')}, strict=not by_name)
+        """Keras .h5 (`save_weights` or full `model.save` / ModelCheckpoint files, e.g. models/SynthSR_v10_210712.h5) or
+        .npz.  by_name=True (the only mode the reference uses, training.py:362): layers are matched by name, layers
+        absent from the file keep their values; a shape mismatch raises like Keras does."""
+        if str(path).endswith('.h5'):
+            from synthsr_b200 import h5lite
+            sd, _ = h5lite.load_keras_weights(path)
+        else:
+            sd = {k: v for k, v in dict(np.load(path)).items() if not k.startswith('optimizer/')}
+        for k, v in sd.items():
+            if k in self.net.p and tuple(self.net.p[k].shape) != tuple(np.shape(v)):
+                raise ValueError('Layer weight shape %s of %s not compatible with provided weight shape %s'
+                                 % (tuple(self.net.p[k].shape), k, tuple(np.shape(v))))
+        self.net.load_state_dict(sd, strict=not by_name)
 
 
 def unet(nb_features, input_shape, nb_levels, conv_size, nb_labels, name='unet', prefix=None, feat_mult=1, pool_size=2,

@@ -43,6 +43,22 @@ def layer_specs(cin, nb_features=24, nb_levels=5, feat_mult=2, nb_conv_per_level
     return specs
 
 
+def keras_layer_order(nb_levels=5, nb_conv_per_level=2, prefix='unet'):
+    """every Keras layer name of ext/neuron/models.py `unet` in model.layers order (weightless ones included), the way
+    `layer_names` lists them in the reference's .h5 files (models.py:281, 314, 350, 355, 425, 433, 442, 476, 480, 493)."""
+    names = ['%s_input' % prefix]
+    for level in range(nb_levels):
+        names += ['%s_conv_downarm_%d_%d' % (prefix, level, j) for j in range(nb_conv_per_level)]
+        names.append('%s_bn_down_%d' % (prefix, level))
+        if level < nb_levels - 1:
+            names.append('%s_maxpool_%d' % (prefix, level))
+    for level in range(nb_levels - 1):
+        names += ['%s_up_%d' % (prefix, nb_levels + level), '%s_merge_%d' % (prefix, nb_levels + level)]
+        names += ['%s_conv_uparm_%d_%d' % (prefix, nb_levels + level, j) for j in range(nb_conv_per_level)]
+        names.append('%s_bn_up_%d' % (prefix, level))
+    return names + ['%s_likelihood' % prefix, '%s_prediction' % prefix]
+
+
 class UNet3D:
     def __init__(self, input_shape, nb_features=24, nb_levels=5, conv_size=3, nb_labels=1, feat_mult=2,
                  nb_conv_per_level=2, batchsize=1, device='cuda', conv_impl='tc', seed=None):

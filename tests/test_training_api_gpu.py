@@ -72,17 +72,20 @@ def test_training_runs_checkpoints_and_resumes(dataset):
               n_levels=3, unet_feat_count=8, steps_per_epoch=3, regression_metric='l1', build_reliability_maps=True,
               work_with_residual_channel=[0], data_res=np.array([1., 1., 2.]), lr=1e-3)
     training(labels_dir, model_dir, p['means'], p['stds'], p['labels'], epochs=2, **kw)
-    assert os.path.isfile(os.path.join(model_dir, '001.npz')) and os.path.isfile(os.path.join(model_dir, '002.npz'))
+    assert os.path.isfile(os.path.join(model_dir, '001.h5')) and os.path.isfile(os.path.join(model_dir, '002.h5'))
     log = open(os.path.join(model_dir, 'logs', 'loss.csv')).read().strip().splitlines()
     losses = [float(l.split(',')[1]) for l in log]
     assert len(losses) == 2 and all(np.isfinite(losses)) and all(0 < l < 10 for l in losses)
-    ck = np.load(os.path.join(model_dir, '002.npz'))
-    assert 'unet_conv_downarm_0_0/kernel' in ck and ck['unet_conv_downarm_0_0/kernel'].shape == (3, 3, 3, 2, 8)
-    assert 'unet_likelihood/kernel' in ck and int(ck['optimizer/iterations']) == 6
+    # the checkpoint is a Keras ModelCheckpoint-style HDF5 file: weights under /model_weights by Keras layer name
+    from synthsr_b200 import h5lite
+    ck, attrs = h5lite.load_keras_weights(os.path.join(model_dir, '002.h5'))
+    assert ck['unet_conv_downarm_0_0/kernel'].shape == (3, 3, 3, 2, 8) and 'unet_likelihood/kernel' in ck
+    assert 'unet_maxpool_0' in [n.decode() for n in attrs['layer_names']]
+    assert int(h5lite.load_extra(os.path.join(model_dir, '002.h5'))['iterations'][0]) == 6
     training(labels_dir, model_dir, p['means'], p['stds'], p['labels'], epochs=3,
-             checkpoint=os.path.join(model_dir, '002.npz'), **kw)
-    assert os.path.isfile(os.path.join(model_dir, '003.npz'))
-    assert int(np.load(os.path.join(model_dir, '003.npz'))['optimizer/iterations']) == 9
+             checkpoint=os.path.join(model_dir, '002.h5'), **kw)
+    assert os.path.isfile(os.path.join(model_dir, '003.h5'))
+    assert int(h5lite.load_extra(os.path.join(model_dir, '003.h5'))['iterations'][0]) == 9
 
 
 def test_two_channel_synthesis_config(dataset):
@@ -97,5 +100,6 @@ def test_two_channel_synthesis_config(dataset):
              path_generation_classes=p['classes'], batchsize=2, input_channels=[False, True, True], output_channel=0,
              output_shape=32, data_res=np.array([[1., 1., 3.], [1., 1., 2.]]), thickness=np.array([[1., 1., 3.], [1., 1., 2.]]),
              downsample=True, build_reliability_maps=False, n_levels=3, unet_feat_count=8, epochs=1, steps_per_epoch=2)
-    ck = np.load(os.path.join(model_dir, '001.npz'))
+    from synthsr_b200 import h5lite
+    ck, _ = h5lite.load_keras_weights(os.path.join(model_dir, '001.h5'))
     assert ck['unet_conv_downarm_0_0/kernel'].shape == (3, 3, 3, 2, 8)
