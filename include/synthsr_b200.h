@@ -107,6 +107,22 @@ long long ssr_conv3d_packed_size(int Cin1, int Cin2, int Cout, int mode);
 int ssr_conv3d_pack_weights_batch(const long long* jobs, int njobs, void* stream);
 int ssr_conv3d_fwd_tc(const float* x1, int C1, const float* x2, int C2, const float* wp, const float* bias, float* y,
                       int B, int d0, int d1, int d2, int Cout, int act, void* stream);
+/* same, added to the partial result already in y before bias + activation */
+int ssr_conv3d_fwd_tc_acc(const float* x1, int C1, const float* x2, int C2, const float* wp, const float* bias, float* y,
+                          int B, int d0, int d1, int d2, int Cout, int act, void* stream);
+/* Decoder levels (UpSampling3D -> concatenate -> Conv3D, ext/neuron/models.py:425-446) without the upsampled tensor: per
+ * output parity class the 3x3x3 kernel over a nearest-upsampled input is an effective 2x2x2 kernel over the LOW-resolution
+ * input (8 taps instead of 27).  ssr_conv3d_up_weights forms the effective kernels weff[8][27][Cup][Cout] (unused taps
+ * zero) and a contiguous copy of the skip part; they are packed per parity class with ssr_conv3d_pack_weights (mode 0 for
+ * the forward, mode 1 for the gradient), 8 packs back to back.
+ *   fwd_tc_up:   y[B,2d0,2d1,2d2,Cout] = partial sums of the upsampled part (no bias / activation; add the skip part with
+ *                ssr_conv3d_fwd_tc_acc / ssr_conv3d_fwd_tc_k2n_part(accumulate))
+ *   dgrad_tc_up: dlow[B,d0,d1,d2,Cup] = gradient w.r.t. the low-resolution tensor (UpSampling3D backward included) */
+int ssr_conv3d_up_weights(const float* w, int Cskip, int Cup, int Cout, float* wskip, float* weff, void* stream);
+int ssr_conv3d_fwd_tc_up(const float* low, int Cup, const float* wp8, float* y, int B, int d0, int d1, int d2, int Cout,
+                         void* stream);
+int ssr_conv3d_dgrad_tc_up(const float* dy, int Cout_layer, const float* wp8, float* dlow, int B, int d0, int d1, int d2,
+                           int Cup, void* stream);
 /* Cin <= 32, Cout <= 32 (the full-resolution layers): the three d2 taps ride in the MMA N dimension; weights packed
  * with mode 2 (forward) / 3 (data gradient: x = dy, Cout = the layer's Cin).  Same result contract as ssr_conv3d_fwd_tc. */
 int ssr_conv3d_fwd_tc_k2n(const float* x, int C, const float* wp, const float* bias, float* y, int B, int d0, int d1,

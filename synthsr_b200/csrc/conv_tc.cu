@@ -229,6 +229,7 @@ struct TcGeom {
   int nchunks;
   int n1tiles, n2tiles, n0tiles, nNtiles;
   int act;
+  int accumulate;    // epilogue adds the partial result already in y (before bias / activation)
   int tmem_cols;
   unsigned char chunk_src[MAX_CHUNKS];    // 0: x1, 1: x2
   unsigned char chunk_ks[MAX_CHUNKS];     // K-steps of 8 channels actually present in the chunk (1..4)
@@ -459,6 +460,20 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             o[e4 * 4 + 2] = __uint_as_float(v[e4 * 4 + 2]) + bb.z;
             o[e4 * 4 + 3] = __uint_as_float(v[e4 * 4 + 3]) + bb.w;
           }
+          if (G.accumulate && vox_ok) {        // partial sums written earlier (the upsampled part of a decoder convolution)
+            const int nv = G.Cout - (n0 + cb);
+            if (nv >= 16 && vec_ok) {
+#pragma unroll
+              for (int e = 0; e < 16; e += 4) {
+                const float4 pv = *reinterpret_cast<const float4*>(orow + cb + e);
+                o[e] += pv.x; o[e + 1] += pv.y; o[e + 2] += pv.z; o[e + 3] += pv.w;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if (e < nv) o[e] += orow[cb + e];
+            }
+          }
           if (G.act) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) {             // ELU without a branch: exp(min(x,0)) - 1 selected where x <= 0
@@ -497,6 +512,306 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)G.tmem_cols);
   if (threadIdx.x == 0) DBG_STAMP(7);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Convolution over a nearest-neighbour 2x upsampled tensor WITHOUT the upsampled tensor (decoder levels:
+// UpSampling3D -> concatenate -> Conv3D, ext/neuron/models.py:425-446).  For an output voxel o = 2 i + p (parity p per
+// axis) the three taps of an axis read up[o - 1], up[o], up[o + 1] = low[i - 1 + p], low[i], low[i + p]: two low-res
+// voxels, so per parity class the 3x3x3 kernel collapses to an effective 2x2x2 one (sums of the original taps, formed in
+// fp32 by up_weights_kernel): 8 taps instead of 27 on the upsampled part of K, i.e. 3.4x fewer MMAs, and the 8x larger
+// upsampled tensor is neither written nor read.
+//   MODE 1 (forward):   y[2 i + p][co] = sum_{k in taps(p), ci} low[i + k - 1][ci] * Weff_p[k][ci][co]
+//                       tile index carries the parity; taps(p) per axis = {p, p + 1}; raw partial sums (no bias /
+//                       activation) go to the parity sub-lattice of the full-resolution output; the skip part of the
+//                       concatenation is added by a normal convolution with `accumulate`.
+//   MODE 2 (gradient):  dlow[j][ci] = sum_p sum_{k'} dy_p[j + k' - 1][co] * Weff_p[2 - k'][ci][co],  dy_p[i] = dy[2 i + p]
+//                       the 8 parity classes are extra K chunks: each has its own strided TMA view of dy (doubled global
+//                       strides, base offset p), its own taps {1 - p, 2 - p} per axis and its own packed weights.  This
+//                       is the gradient w.r.t. the LOW-resolution tensor: the 2x2x2 sum of UpSampling3D's backward is
+//                       part of the GEMM.
+// Same tiling / pipeline / warp roles as conv3d_tc_kernel (its protocol is kept line by line).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int UP_MAX_CHUNKS = 8;
+
+struct UpGeom {
+  int B, D0, D1, D2;     // LOW-resolution grid = GEMM rows
+  int Cout, Npad, NT, TZ, KG, SA;
+  int nchunks;           // 32-channel chunks of the input (per parity class in MODE 2)
+  int n1tiles, n2tiles, n0tiles, nNtiles;
+  int tmem_cols;
+  int par_rows;          // rows of the packed weights per parity class (= nchunks * 27 * Npad)
+  unsigned char chunk_ks[UP_MAX_CHUNKS];
+  short chunk_c0[UP_MAX_CHUNKS];
+};
+struct UpMaps { CUtensorMap x[8]; };
+
+template <int MODE>
+__global__ void __launch_bounds__(288, 1)
+conv3d_tc_up_kernel(const __grid_constant__ UpMaps maps, const __grid_constant__ CUtensorMap map_w,
+                    float* __restrict__ y, const UpGeom G) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  const int bgroup_bytes = G.KG * 3 * G.NT * 128;
+  uint8_t* sB = sA + (size_t)G.SA * SLAB_BYTES;
+  uint64_t* bars = (uint64_t*)(sB + (size_t)SB * bgroup_bytes);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = bars + G.SA;
+  uint64_t* fullB = bars + 2 * G.SA;
+  uint64_t* emptyB = fullB + SB;
+  uint64_t* accFull = emptyB + SB;                 // [2]
+  uint64_t* accEmpty = accFull + 2;                // [2]
+  uint32_t* tmem_slot = (uint32_t*)(accEmpty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < G.SA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, G.TZ); }
+    for (int i = 0; i < SB; ++i) { mbar_init(fullB + i, 1); mbar_init(emptyB + i, G.TZ); }
+    for (int i = 0; i < 2; ++i) { mbar_init(accFull + i, G.TZ); mbar_init(accEmpty + i, 4); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < (MODE == 2 ? 8 : 1); ++i) tma_prefetch_desc(&maps.x[i]);
+    tma_prefetch_desc(&map_w);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)G.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr int NPT = MODE == 1 ? 8 : 1;           // parity classes folded into the tile index
+  constexpr int NPK = MODE == 2 ? 8 : 1;           // parity classes folded into K
+  const int ntiles = G.B * G.n0tiles * G.n1tiles * G.n2tiles * G.nNtiles * NPT;
+  const uint32_t set_cols = (uint32_t)(G.TZ * G.NT);
+
+#define UP_DECODE_TILE(tile)                                                    \
+  int t_ = (tile);                                                               \
+  const int tpar = MODE == 1 ? (t_ & 7) : 0; if (MODE == 1) t_ >>= 3;            \
+  const int nt = t_ % G.nNtiles; t_ /= G.nNtiles;                                \
+  const int t2 = t_ % G.n2tiles; t_ /= G.n2tiles;                                \
+  const int t1 = t_ % G.n1tiles; t_ /= G.n1tiles;                                \
+  const int t0 = t_ % G.n0tiles;                                                 \
+  const int b = t_ / G.n0tiles;                                                  \
+  const int x0 = t2 * TM2, y0 = t1 * TM1, z0 = t0 * G.TZ, n0 = nt * G.NT;        \
+  const int nz = min(G.TZ, G.D0 - z0);                                           \
+  (void)x0; (void)y0; (void)n0; (void)b; (void)nz; (void)tpar;
+  // taps of parity class `par` per axis (bit 2: d0, bit 1: d1, bit 0: d2): MODE 1 {p, p + 1}, MODE 2 {1 - p, 2 - p}
+#define UP_TAPS(par)                                                             \
+  const int p0_ = ((par) >> 2) & 1, p1_ = ((par) >> 1) & 1, p2_ = (par) & 1;     \
+  const int k0lo = MODE == 1 ? p0_ : 1 - p0_, k1lo = MODE == 1 ? p1_ : 1 - p1_, k2lo = MODE == 1 ? p2_ : 1 - p2_;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int sa = 0, pa = 0, sb = 0, pb = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        UP_DECODE_TILE(tile)
+        for (int pk = 0; pk < NPK; ++pk) {
+          const int par = MODE == 1 ? tpar : pk;
+          UP_TAPS(par)
+          const CUtensorMap* mx = &maps.x[MODE == 2 ? pk : 0];
+          for (int ch = 0; ch < G.nchunks; ++ch) {
+            const int c0 = G.chunk_c0[ch];
+            const int brow = par * G.par_rows + ch * 27 * G.Npad + n0;
+            for (int k2 = k2lo; k2 <= k2lo + 1; ++k2) {
+              for (int k0g = 0; k0g < 3; k0g += G.KG) {
+                const int kk_lo = max(k0lo - k0g, 0), kk_hi = min(k0lo + 1 - k0g, G.KG - 1);
+                if (kk_lo > kk_hi) continue;
+                const int zin_lo = max(kk_lo, (z0 + k0g == 0) ? 1 : 0);
+                const int zin_hi = min(nz + kk_hi, G.D0 - (z0 + k0g - 1));
+                if (zin_lo >= zin_hi) continue;
+                mbar_wait(emptyB + sb, pb ^ 1);
+                mbar_expect_tx(fullB + sb, (uint32_t)((kk_hi - kk_lo + 1) * 2 * G.NT * 128));
+                for (int kk = kk_lo; kk <= kk_hi; ++kk)
+                  for (int k1 = k1lo; k1 <= k1lo + 1; ++k1)
+                    tma_load_2d(&map_w, fullB + sb, sB + (size_t)sb * bgroup_bytes + (size_t)(kk * 3 + k1) * G.NT * 128, 0,
+                                brow + ((k2 * 3 + (k0g + kk)) * 3 + k1) * G.Npad);
+                if (++sb == SB) { sb = 0; pb ^= 1; }
+                for (int zin = zin_lo; zin < zin_hi; ++zin) {
+                  mbar_wait(emptyA + sa, pa ^ 1);
+                  mbar_expect_tx(fullA + sa, SLAB_BYTES);
+                  tma_load_5d(mx, fullA + sa, sA + (size_t)sa * SLAB_BYTES, c0, x0 + k2 - 1, y0 - 1, z0 + k0g + zin - 1, b);
+                  if (++sa == G.SA) { sa = 0; pa ^= 1; }
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp <= G.TZ) {
+    // ================================ MMA issuers: warp w owns accumulator (output plane) zo = w - 1 ================
+    const int zo = warp - 1;
+    const uint32_t idesc = make_idesc_tf32(G.NT);
+    const int KG = G.KG, SA = G.SA, nchunks = G.nchunks, D0 = G.D0;
+    const uint32_t NT = (uint32_t)G.NT;
+    const uint32_t btile16 = (NT * 128u) >> 4;
+    const uint32_t a_base = desc_lo(smem_u32(sA), 16), b_base = desc_lo(smem_u32(sB), 16);
+    int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      UP_DECODE_TILE(tile)
+      const int set = it & 1;
+      const uint32_t dcol = tmem_base + (uint32_t)set * set_cols + (uint32_t)zo * NT;
+      const bool active = zo < nz;
+      mbar_wait(accEmpty + set, ((it >> 1) & 1) ^ 1);          // epilogue has drained this accumulator set
+      tc_fence_after();
+      uint32_t acc = 0u;                         // first MMA of the tile into this accumulator overwrites
+      for (int pk = 0; pk < NPK; ++pk) {
+        const int par = MODE == 1 ? tpar : pk;
+        UP_TAPS(par)
+        (void)k2lo;
+        for (int ch = 0; ch < nchunks; ++ch) {
+          const int nks = G.chunk_ks[ch];
+          for (int k2i = 0; k2i < 2; ++k2i) {
+            for (int k0g = 0; k0g < 3; k0g += KG) {
+              const int kk_lo = max(k0lo - k0g, 0), kk_hi = min(k0lo + 1 - k0g, KG - 1);
+              if (kk_lo > kk_hi) continue;
+              const int zin_lo = max(kk_lo, (z0 + k0g == 0) ? 1 : 0);
+              const int zin_hi = min(nz + kk_hi, D0 - (z0 + k0g - 1));
+              if (zin_lo >= zin_hi) continue;
+              mbar_wait(fullB + sb, pb);
+              const uint32_t blo0 = b_base + (uint32_t)sb * ((uint32_t)bgroup_bytes >> 4);
+              for (int zin = zin_lo; zin < zin_hi; ++zin) {
+                mbar_wait(fullA + sa, pa);
+                const int kk = zin - zo;
+                if (active && kk >= kk_lo && kk <= kk_hi) {            // warp-uniform
+                  if (elect_one()) {
+                    uint32_t alo = a_base + (uint32_t)sa * (SLAB_BYTES >> 4) + (uint32_t)k1lo * (uint32_t)(TM2 * 128 >> 4);
+                    uint32_t blo = blo0 + (uint32_t)(kk * 3 + k1lo) * btile16;
+#pragma unroll
+                    for (int k1i = 0; k1i < 2; ++k1i) {
+                      if (nks == 4) umma_chain_k<4>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+                      else if (nks == 3) umma_chain_k<3>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+                      else if (nks == 2) umma_chain_k<2>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+                      else umma_chain_k<1>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+                      acc = 1u;
+                      alo += (uint32_t)(TM2 * 128 >> 4);
+                      blo += btile16;
+                    }
+                    umma_commit(emptyA + sa);        // this warp's reads of the slab are done once these MMAs complete
+                  }
+                  acc = 1u;
+                } else if (lane == 0) {
+                  mbar_arrive(emptyA + sa);          // not my tap: release immediately
+                }
+                __syncwarp();
+                if (++sa == SA) { sa = 0; pa ^= 1; }
+              }
+              if (elect_one()) umma_commit(emptyB + sb);   // arrives when this warp's MMAs on the group are complete
+              __syncwarp();
+              if (++sb == SB) { sb = 0; pb ^= 1; }
+            }
+          }
+        }
+      }
+      if (elect_one()) umma_commit(accFull + set);
+      __syncwarp();
+    }
+  } else {
+    // ================================ epilogue (last four warps) ================================
+    const int q = warp & 3;                         // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                    // GEMM row = voxel inside the tile
+    const bool vec_ok = (G.Cout & 3) == 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      UP_DECODE_TILE(tile)
+      const int set = it & 1;
+      const uint32_t acc_base = tmem_base + (uint32_t)set * set_cols;
+      const int i1 = y0 + (r >> 3), i2 = x0 + (r & 7);
+      mbar_wait(accFull + set, (it >> 1) & 1);
+      tc_fence_after();
+      const bool vox_ok = i1 < G.D1 && i2 < G.D2;
+      for (int zo = 0; zo < nz; ++zo) {
+        const int i0 = z0 + zo;
+        float* orow;
+        if (MODE == 1) {      // parity sub-lattice of the 2x finer output grid
+          const long long o0 = 2 * i0 + ((tpar >> 2) & 1), o1 = 2 * i1 + ((tpar >> 1) & 1), o2 = 2 * i2 + (tpar & 1);
+          orow = y + ((((long long)b * (2 * G.D0) + o0) * (2 * G.D1) + o1) * (2 * G.D2) + o2) * G.Cout + n0;
+        } else {
+          orow = y + ((((long long)b * G.D0 + i0) * G.D1 + i1) * G.D2 + i2) * G.Cout + n0;
+        }
+        for (int cb = 0; cb < G.NT; cb += 16) {
+          uint32_t v[16];
+          tmem_ld16(acc_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(zo * G.NT + cb), v);
+          tmem_ld_wait();
+          if (!vox_ok) continue;
+          const int nvalid = G.Cout - (n0 + cb);       // channels of this 16-block that exist
+          if (nvalid >= 16 && vec_ok) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 4)
+              *reinterpret_cast<float4*>(orow + cb + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                      __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+          } else if (nvalid >= 8 && vec_ok) {
+            *reinterpret_cast<float4*>(orow + cb) = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]),
+                                                                __uint_as_float(v[2]), __uint_as_float(v[3]));
+            *reinterpret_cast<float4*>(orow + cb + 4) = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]),
+                                                                    __uint_as_float(v[6]), __uint_as_float(v[7]));
+#pragma unroll
+            for (int e = 8; e < 16; ++e)
+              if (e < nvalid) orow[cb + e] = __uint_as_float(v[e]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (e < nvalid) orow[cb + e] = __uint_as_float(v[e]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(accEmpty + set);
+    }
+  }
+#undef UP_DECODE_TILE
+#undef UP_TAPS
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)G.tmem_cols);
+}
+
+// effective weights of the upsampled part of a decoder convolution: for parity class p (bit 2: d0, bit 1: d1, bit 0: d2)
+//   weff[p][k0][k1][k2][ci][co] = sum over the original taps t_a that land on effective tap k_a under parity p_a
+//       p_a = 0:  k = 0 <- {0},  k = 1 <- {1, 2},  k = 2 <- {}        p_a = 1:  k = 0 <- {},  k = 1 <- {0, 1},  k = 2 <- {2}
+//   of w[t0][t1][t2][Cskip + ci][co];  wskip[t][ci][co] = w[t][ci][co] for ci < Cskip (contiguous copy of the skip part).
+__global__ void up_weights_kernel(const float* __restrict__ w, int Cskip, int Cup, int Cout, float* __restrict__ wskip,
+                                  float* __restrict__ weff) {
+  const int Cin = Cskip + Cup;
+  const long long n_eff = 8LL * 27 * Cup * Cout, n_skip = 27LL * Cskip * Cout;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n_eff + n_skip;
+       t += (long long)gridDim.x * blockDim.x) {
+    if (t >= n_eff) {
+      const long long u = t - n_eff;
+      const int co = (int)(u % Cout);
+      const int ci = (int)((u / Cout) % Cskip);
+      const int tap = (int)(u / ((long long)Cout * Cskip));
+      wskip[u] = w[((long long)tap * Cin + ci) * Cout + co];
+      continue;
+    }
+    long long r = t;
+    const int co = (int)(r % Cout); r /= Cout;
+    const int ci = (int)(r % Cup); r /= Cup;
+    const int k2 = (int)(r % 3); r /= 3;
+    const int k1 = (int)(r % 3); r /= 3;
+    const int k0 = (int)(r % 3);
+    const int par = (int)(r / 3);
+    const int pp[3] = {(par >> 2) & 1, (par >> 1) & 1, par & 1}, kk[3] = {k0, k1, k2};
+    int lo[3], hi[3];
+    bool any = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (pp[a] == 0) { lo[a] = kk[a] == 0 ? 0 : 1; hi[a] = kk[a] == 0 ? 0 : (kk[a] == 1 ? 2 : -1); }
+      else { lo[a] = kk[a] == 2 ? 2 : 0; hi[a] = kk[a] == 2 ? 2 : (kk[a] == 1 ? 1 : -1); }
+      if (hi[a] < lo[a]) any = false;
+    }
+    float acc = 0.f;
+    if (any)
+      for (int t0 = lo[0]; t0 <= hi[0]; ++t0)
+        for (int t1 = lo[1]; t1 <= hi[1]; ++t1)
+          for (int t2 = lo[2]; t2 <= hi[2]; ++t2)
+            acc += w[((long long)((t0 * 3 + t1) * 3 + t2) * Cin + Cskip + ci) * Cout + co];
+    weff[t] = acc;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1698,15 +2013,15 @@ int ssr_conv3d_pack_weights(const float* w, float* wp, int Cin1, int Cin2, int C
 
 // y[B,D0,D1,D2,Cout] = act(conv3x3x3([x1,x2], wp) + bias) ; wp from ssr_conv3d_pack_weights.
 // Used for the data gradient too (x1 = dy, wp packed with mode 1, Cout = layer's Cin, bias NULL, act 0).
-int ssr_conv3d_fwd_tc(const float* x1, int C1, const float* x2, int C2, const float* wp, const float* bias, float* y,
-                      int B, int D0, int D1, int D2, int Cout, int act, void* stream) {
+static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, const float* wp, const float* bias, float* y,
+                              int B, int D0, int D1, int D2, int Cout, int act, int accumulate, void* stream) {
   SSR_CHECK_ARG(x1 && wp && y && B > 0 && D0 > 0 && D1 > 0 && D2 > 0 && Cout > 0, "pointers/shape");
   SSR_CHECK_ARG(C1 > 0 && C1 % 4 == 0 && C2 >= 0 && C2 % 4 == 0 && (C2 == 0 || x2), "channel counts must be multiples of 4");
   SSR_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0, "channel counts must be multiples of 8 (TF32 K-step)");
   SSR_CHECK_ARG(((uintptr_t)x1 & 15) == 0 && ((uintptr_t)wp & 127) == 0 && (!x2 || ((uintptr_t)x2 & 15) == 0), "alignment");
   TcGeom G;
   memset(&G, 0, sizeof(G));
-  G.B = B; G.D0 = D0; G.D1 = D1; G.D2 = D2; G.Cout = Cout; G.act = act;
+  G.B = B; G.D0 = D0; G.D1 = D1; G.D2 = D2; G.Cout = Cout; G.act = act; G.accumulate = accumulate;
   G.Npad = round_up(Cout, 16);
   // Tile shape (NT output channels x TZ output planes per CTA tile): the kernel is persistent with a static round-robin
   // over tiles, so the cost is rounds x per-tile time.  Small layers (40^3 and below) have few tiles: a narrower N tile or
@@ -1781,6 +2096,147 @@ int ssr_conv3d_fwd_tc(const float* x1, int C1, const float* x2, int C2, const fl
   }
   const unsigned grid = (unsigned)(ntiles < num_sms ? ntiles : num_sms);       // persistent: one CTA per SM
   conv3d_tc_kernel<<<grid, 32 * (5 + G.TZ), smem, (cudaStream_t)stream>>>(m1, m2, mw, bias, y, G);   // TMA + TZ MMA + 4 epilogue warps
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
+int ssr_conv3d_fwd_tc(const float* x1, int C1, const float* x2, int C2, const float* wp, const float* bias, float* y,
+                      int B, int D0, int D1, int D2, int Cout, int act, void* stream) {
+  return conv3d_fwd_tc_impl(x1, C1, x2, C2, wp, bias, y, B, D0, D1, D2, Cout, act, 0, stream);
+}
+// same, added to the partial result already in y (then bias + activation): the skip part of a decoder convolution whose
+// upsampled part was written by ssr_conv3d_fwd_tc_up
+int ssr_conv3d_fwd_tc_acc(const float* x1, int C1, const float* x2, int C2, const float* wp, const float* bias, float* y,
+                          int B, int D0, int D1, int D2, int Cout, int act, void* stream) {
+  return conv3d_fwd_tc_impl(x1, C1, x2, C2, wp, bias, y, B, D0, D1, D2, Cout, act, 1, stream);
+}
+
+// ---- convolution over a 2x nearest-upsampled tensor from its LOW-resolution source (conv3d_tc_up_kernel) ------------
+static int up_tile_shape(int Npad, int B, int D0, int D1, int D2, int ks_total, int kparts, int tile_mult, int* NT, int* TZ) {
+  const int n1t = (D1 + TM1 - 1) / TM1, n2t = (D2 + TM2 - 1) / TM2;
+  double best = 1e300;
+  int best_nt = 0, best_tz = 0;
+  for (int nt = 16; nt <= 192 && nt <= Npad; nt += 16) {
+    if (Npad % nt) continue;
+    for (int tz = 1; tz <= 4 && tz <= D0 && tz * nt <= 256; ++tz) {
+      const long long tiles = (long long)B * ((D0 + tz - 1) / tz) * n1t * n2t * (Npad / nt) * tile_mult;
+      const long long rounds = (tiles + 147) / 148;
+      const double mma = (nt / 2 > 32 + nt / 4 ? nt / 2 : 32 + nt / 4) + (tz == 1 ? 20.0 : 8.0);
+      const double cost = rounds * (tz * 8.0 * kparts * ks_total * mma * (1.0 + 0.04 * (4 - tz)) + 2500.0);
+      if (cost < best * 0.999 || (cost < best * 1.001 && (tz > best_tz || (tz == best_tz && nt > best_nt)))) {
+        best = cost; best_nt = nt; best_tz = tz;
+      }
+    }
+  }
+  *NT = best_nt; *TZ = best_tz;
+  return best_nt > 0 ? SSR_OK : SSR_ERR_ARG;
+}
+
+static int make_map_view(CUtensorMap* m, const float* ptr, int C, int B, int D0, int D1, int D2, long long s2, long long s1,
+                         long long s0, long long sb) {      // strides in floats; dims (C, D2, D1, D0, B)
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { ssr_set_error("cuTensorMapEncodeTiled not available"); return SSR_ERR_CUDA; }
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)D2, (cuuint64_t)D1, (cuuint64_t)D0, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)s2 * 4, (cuuint64_t)s1 * 4, (cuuint64_t)s0 * 4, (cuuint64_t)sb * 4};
+  cuuint32_t box[5] = {32, (cuuint32_t)TM2, (cuuint32_t)(TM1 + 2), 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, tma_dtype(), 5, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { ssr_set_error("cuTensorMapEncodeTiled(strided view C=%d %dx%dx%d) failed: %d", C, D0, D1, D2, (int)r); return SSR_ERR_CUDA; }
+  return SSR_OK;
+}
+
+// mode 1: x = low-resolution input [B,d0,d1,d2,C], y = [B,2d0,2d1,2d2,Cout] partial sums (no bias / activation);
+// mode 2: x = full-resolution dy [B,2d0,2d1,2d2,C], y = gradient w.r.t. the low-resolution tensor [B,d0,d1,d2,Cout].
+// wp8: 8 parity classes x standard packed weights (mode 0 / mode 1 packing of the effective kernels).
+static int conv3d_tc_up_impl(int mode, const float* x, int C, const float* wp8, float* y, int B, int D0, int D1, int D2,
+                             int Cout, void* stream) {
+  SSR_CHECK_ARG(x && wp8 && y && B > 0 && D0 > 0 && D1 > 0 && D2 > 0 && Cout > 0, "pointers/shape");
+  SSR_CHECK_ARG(C > 0 && C % 8 == 0 && C <= 32 * UP_MAX_CHUNKS, "channel count must be a multiple of 8 (<= 256)");
+  SSR_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp8 & 127) == 0, "alignment");
+  UpGeom G;
+  memset(&G, 0, sizeof(G));
+  G.B = B; G.D0 = D0; G.D1 = D1; G.D2 = D2; G.Cout = Cout;
+  G.Npad = round_up(Cout, 16);
+  int ks_total = 0, nch = 0;
+  for (int c = 0; c < C; c += 32) {
+    G.chunk_c0[nch] = (short)c; G.chunk_ks[nch] = (unsigned char)(((C - c < 32 ? C - c : 32) + 7) / 8);
+    ks_total += G.chunk_ks[nch]; ++nch;
+  }
+  G.nchunks = nch;
+  int rc = up_tile_shape(G.Npad, B, D0, D1, D2, ks_total, mode == 2 ? 8 : 1, mode == 1 ? 8 : 1, &G.NT, &G.TZ);
+  if (rc) { ssr_set_error("no tile shape"); return rc; }
+  G.nNtiles = G.Npad / G.NT;
+  G.KG = (3 * 3 * G.NT * 128 <= 74 * 1024) ? 3 : 1;
+  int cols = 2 * G.TZ * G.NT, pc = 32;
+  while (pc < cols) pc <<= 1;
+  G.tmem_cols = pc;
+  G.par_rows = nch * 27 * G.Npad;
+  G.n2tiles = (D2 + TM2 - 1) / TM2; G.n1tiles = (D1 + TM1 - 1) / TM1; G.n0tiles = (D0 + G.TZ - 1) / G.TZ;
+  const int bgroup = G.KG * 3 * G.NT * 128;
+  const int budget = 227 * 1024 - 1024 - 2816 - SB * bgroup;
+  int sa = budget / SLAB_BYTES; if (sa > 8) sa = 8;
+  SSR_CHECK_ARG(sa >= 2, "shared memory budget");
+  G.SA = sa;
+  const size_t smem = 1024 + (size_t)G.SA * SLAB_BYTES + (size_t)SB * bgroup + 2816;
+  UpMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (mode == 1) {
+    rc = make_map_act(&maps.x[0], x, C, B, D0, D1, D2);
+    if (rc) return rc;
+    for (int i = 1; i < 8; ++i) maps.x[i] = maps.x[0];
+  } else {
+    const long long F0 = 2LL * D0, F1 = 2LL * D1, F2 = 2LL * D2;
+    for (int par = 0; par < 8; ++par) {
+      const long long off = ((((par >> 2) & 1) * F1 + ((par >> 1) & 1)) * F2 + (par & 1)) * C;
+      rc = make_map_view(&maps.x[par], x + off, C, B, D0, D1, D2, 2LL * C, 2 * F2 * C, 2 * F1 * F2 * C, F0 * F1 * F2 * C);
+      if (rc) return rc;
+    }
+  }
+  CUtensorMap mw;
+  rc = make_map_w(&mw, wp8, 8LL * G.par_rows, G.NT);
+  if (rc) return rc;
+  const long long ntiles = (long long)B * G.n0tiles * G.n1tiles * G.n2tiles * G.nNtiles * (mode == 1 ? 8 : 1);
+  SSR_CHECK_ARG(ntiles < (1LL << 31) && G.Npad <= 576, "grid / channel count too large");
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    SSR_CHECK_CUDA(cudaGetDevice(&dev));
+    SSR_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const unsigned grid = (unsigned)(ntiles < num_sms ? ntiles : num_sms);
+  if (mode == 1) {
+    static bool attr1 = false;
+    if (!attr1) { SSR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_up_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr1 = true; }
+    conv3d_tc_up_kernel<1><<<grid, 32 * (5 + G.TZ), smem, (cudaStream_t)stream>>>(maps, mw, y, G);
+  } else {
+    static bool attr2 = false;
+    if (!attr2) { SSR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_up_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr2 = true; }
+    conv3d_tc_up_kernel<2><<<grid, 32 * (5 + G.TZ), smem, (cudaStream_t)stream>>>(maps, mw, y, G);
+  }
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
+int ssr_conv3d_fwd_tc_up(const float* low, int Cup, const float* wp8, float* y, int B, int d0, int d1, int d2, int Cout,
+                         void* stream) {
+  return conv3d_tc_up_impl(1, low, Cup, wp8, y, B, d0, d1, d2, Cout, stream);
+}
+int ssr_conv3d_dgrad_tc_up(const float* dy, int Cout_layer, const float* wp8, float* dlow, int B, int d0, int d1, int d2,
+                           int Cup, void* stream) {
+  return conv3d_tc_up_impl(2, dy, Cout_layer, wp8, dlow, B, d0, d1, d2, Cup, stream);
+}
+
+// wskip (27, Cskip, Cout) = skip part of w (27, Cskip + Cup, Cout); weff (8, 27, Cup, Cout) = effective kernels of the
+// upsampled part per parity class (see up_weights_kernel)
+int ssr_conv3d_up_weights(const float* w, int Cskip, int Cup, int Cout, float* wskip, float* weff, void* stream) {
+  SSR_CHECK_ARG(w && wskip && weff && Cskip > 0 && Cup > 0 && Cout > 0, "args");
+  const long long n = 8LL * 27 * Cup * Cout + 27LL * Cskip * Cout;
+  long long g = (n + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  up_weights_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(w, Cskip, Cup, Cout, wskip, weff);
   SSR_COUNT_LAUNCH();
   SSR_CHECK_LAUNCH();
   return SSR_OK;

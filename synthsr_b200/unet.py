@@ -79,6 +79,11 @@ class UNet3D:
         self.materialise_feat = os.environ.get('SSR_MATERIALISE_FEAT') is not None
         # BN statistics / ELU backward of the full-resolution 24-channel layers inside the k2n convolution epilogues
         self.pool_bn_fusion = os.environ.get('SSR_NO_POOL_BN_FUSION') is None    # MaxPool + BN backward in two passes
+        # decoder convolutions over the upsampled tensor as 8 parity classes of effective 2x2x2 kernels on the
+        # low-resolution tensor (conv3d_tc_up_kernel): levels whose low-resolution grid is at least up_min_dim wide
+        self.up_parity = conv_impl == 'tc' and os.environ.get('SSR_NO_UP_PARITY') is None
+        self.up_min_dim = int(os.environ.get('SSR_UP_MIN_DIM', '16'))
+        self.up_wgrad = False         # weight gradient of those layers from the low-resolution tensor too
         self.epi_fusion = self.fwd_k2n and os.environ.get('SSR_NO_EPI_FUSION') is None
         self._side, self._side_busy, self._hp, self._pack_event = None, False, None, None
         self.device = torch.device(device)
@@ -171,6 +176,11 @@ class UNet3D:
         self.u = [buf(l, F[l + 1]) for l in range(L - 1)]                     # upsampled BN output (decoder input)
         self.g0 = [buf(l, F[l]) for l in range(L - 1)]
         self.g1 = [buf(l, F[l]) for l in range(L - 1)]
+        self.up_levels = [l for l in range(L - 1) if self.up_parity and F[l] % 8 == 0 and F[l + 1] % 8 == 0 and
+                          F[l + 1] <= 256 and min(self.ldims[l + 1]) >= self.up_min_dim]
+        self.vlow = {l: buf(l + 1, F[l + 1]) for l in self.up_levels}            # BN output feeding decoder level l
+        self._up = {}
+        self._up_valid = False
         self.feat = buf(0, F[0])
         self.pred = torch.empty((self.nvox[0], self.nb_labels), dtype=f32, device=dev)
         self.stats_enc = [torch.empty(4 * F[l], dtype=f32, device=dev) for l in range(L)]
@@ -180,6 +190,7 @@ class UNet3D:
         self._bwd_alloc = False
         self._packed = {}
         self._packed_args = {}
+        self._packed_src = {}
         self._packed_dirty = True
 
     def _alloc_bwd(self):
@@ -197,7 +208,8 @@ class UNet3D:
         # ga/gb on the side stream when the encoder phase starts (see _wgrad_async)
         self.ga_e = [buf(l, F[l]) for l in range(L)]
         self.gb_e = [buf(l, F[l]) for l in range(L)]
-        self.dcat = [buf(l, F[l] + F[l + 1]) for l in range(L - 1)]
+        self.dcat = [None if l in self.up_levels else buf(l, F[l] + F[l + 1]) for l in range(L - 1)]
+        self.dskip = {l: buf(l, F[l]) for l in self.up_levels}                # gradient w.r.t. the skip input of level l
         self.dbn_dec = [buf(l, F[l]) for l in range(L - 1)]                   # grad wrt BN output of decoder level l
         self.dbn_bott = buf(L - 1, F[L - 1])                                  # grad wrt BN output of the bottleneck
         self.dp = [None] + [buf(l, F[l - 1]) for l in range(1, L)]            # grad wrt pooled input of level l
@@ -252,6 +264,42 @@ class UNet3D:
         else:
             lib.ssr_conv3d_fwd_ref(x1, c1, x2, c2, self.p[name + '/kernel'], self.p[name + '/bias'], y, self.B, *d,
                                    cout, self.k, act, st)
+
+    def _conv_fwd_up(self, name, l, act=1):
+        """decoder convolution 0 of level l on [skip h1[l], upsample(vlow[l])] without the upsampled tensor: the parity
+        kernel writes the partial sums of the upsampled part, the skip convolution accumulates + bias + ELU."""
+        F = self.feats
+        self._timed('fwd_tc', l, F[l] + F[l + 1], F[l], lambda: self._conv_fwd_up_impl(name, l, act))
+
+    def _conv_fwd_up_impl(self, name, l, act):
+        st, F, B = stream_ptr(), self.feats, self.B
+        u = self._up_state(l)
+        lib.ssr_conv3d_fwd_tc_up(self.vlow[l], F[l + 1], self._up_packs(l, 'fwd8'), self.g0[l], B, *self.ldims[l + 1], F[l], st)
+        if self.fwd_k2n and F[l] <= 32:
+            wp = self._packed_w(name, 2, F[l], 0, F[l], tag='skip', src=u['wskip'])
+            lib.ssr_conv3d_fwd_tc_k2n_part(self.h1[l], F[l], 0, F[l], wp, self.p[name + '/bias'], self.g0[l], B,
+                                           *self.ldims[l], F[l], act, 1, 1, st)
+        else:
+            wp = self._packed_w(name, 0, F[l], 0, F[l], tag='skip', src=u['wskip'])
+            lib.ssr_conv3d_fwd_tc_acc(self.h1[l], F[l], None, 0, wp, self.p[name + '/bias'], self.g0[l], B, *self.ldims[l],
+                                      F[l], act, st)
+
+    def _conv_dgrad_up(self, name, l, dy, dlow):
+        """data gradient of decoder convolution 0 of level l: dskip[l] (w.r.t. the skip input, full resolution) and dlow
+        (w.r.t. the low-resolution BN output; UpSampling3D backward included)."""
+        F = self.feats
+        self._timed('dgrad_tc', l, F[l] + F[l + 1], F[l], lambda: self._conv_dgrad_up_impl(name, l, dy, dlow))
+
+    def _conv_dgrad_up_impl(self, name, l, dy, dlow):
+        st, F, B = stream_ptr(), self.feats, self.B
+        u = self._up_state(l)
+        if self.fwd_k2n and F[l] <= 32:
+            wp = self._packed_w(name, 3, F[l], 0, F[l], tag='skip', src=u['wskip'])
+            lib.ssr_conv3d_fwd_tc_k2n(dy, F[l], wp, None, self.dskip[l], B, *self.ldims[l], F[l], 0, st)
+        else:
+            wp = self._packed_w(name, 1, F[l], 0, F[l], tag='skip', src=u['wskip'])
+            lib.ssr_conv3d_fwd_tc(dy, F[l], None, 0, wp, None, self.dskip[l], B, *self.ldims[l], F[l], 0, st)
+        lib.ssr_conv3d_dgrad_tc_up(dy, F[l], self._up_packs(l, 'dgr8'), dlow, B, *self.ldims[l + 1], F[l + 1], st)
 
     def _conv_dgrad(self, name, dy, dx, l, cin, cout, elu_h=None, dbias=None):
         """elu_h / dbias: fuse the ELU backward of the layer below (dx *= elu'(elu_h), dbias += column sums of dx)."""
@@ -323,30 +371,75 @@ class UNet3D:
     def _wgrad_tc_ok(self, c1, c2, cout):
         return getattr(self, 'wgrad_tc', False) and (c1 % 8 == 0) and (c2 % 8 == 0) and cout % 8 == 0
 
-    def _packed_w(self, name, mode, c1, c2, cout, tag=0):
-        """packed (K-major, zero padded) copy of a kernel for the tcgen05 path; refreshed after every optimiser step."""
+    def _packed_w(self, name, mode, c1, c2, cout, tag=0, src=None, buf=None):
+        """packed (K-major, zero padded) copy of a kernel for the tcgen05 path; refreshed after every optimiser step.
+        src: tensor to pack instead of the layer's kernel (derived kernels of the parity path); buf: destination view."""
         if self._packed_dirty:
             self._packed_valid = set()
             self._packed_dirty = False
+            self._up_valid = False
         key = (name, mode, tag)
         if key not in self._packed:
             n = lib.ssr_conv3d_packed_size(c1, c2, cout, mode)
-            self._packed[key] = torch.empty(n, dtype=torch.float32, device=self.device)
+            self._packed[key] = buf if buf is not None else torch.empty(n, dtype=torch.float32, device=self.device)
+            assert self._packed[key].numel() == n
             self._packed_args[key] = (c1, c2, cout)
+            self._packed_src[key] = src if src is not None else self.p[name + '/kernel']
         if key not in self._packed_valid:
-            lib.ssr_conv3d_pack_weights(self.p[name + '/kernel'], self._packed[key], c1, c2, cout, mode, stream_ptr())
+            if src is not None:
+                self._up_weights_all(stream_ptr())
+            lib.ssr_conv3d_pack_weights(self._packed_src[key], self._packed[key], c1, c2, cout, mode, stream_ptr())
             self._packed_valid.add(key)
         return self._packed[key]
+
+    # ---- parity path of the decoder convolutions (conv3d_tc_up_kernel) -------------------------------------------------
+    def _up_state(self, l):
+        """scratch of decoder level l: skip part of the kernel, the 8 effective kernels of the upsampled part, and the
+        buffers of their packed copies (8 parity classes back to back)."""
+        if l not in self._up:
+            F, dev = self.feats, self.device
+            cs, cu, co = F[l], F[l + 1], F[l]
+            nf = lib.ssr_conv3d_packed_size(cu, 0, co, 0)
+            nd = lib.ssr_conv3d_packed_size(cu, 0, co, 1)
+            self._up[l] = dict(wskip=torch.empty(27 * cs * co, dtype=torch.float32, device=dev),
+                               weff=torch.empty(8 * 27 * cu * co, dtype=torch.float32, device=dev),
+                               fwd8=torch.empty(8 * nf, dtype=torch.float32, device=dev), nf=nf,
+                               dgr8=torch.empty(8 * nd, dtype=torch.float32, device=dev), nd=nd)
+        return self._up[l]
+
+    def _up_weights_all(self, st):
+        if self._up_valid:
+            return
+        F, L = self.feats, self.L
+        for l in self.up_levels:
+            u = self._up_state(l)
+            lib.ssr_conv3d_up_weights(self.p['unet_conv_uparm_%d_0/kernel' % (L + (L - 2 - l))], F[l], F[l + 1], F[l], u['wskip'],
+                                      u['weff'], st)
+        self._up_valid = True
+
+    def _up_packs(self, l, which):
+        """packed weights of the parity kernels of level l: 'fwd8' (mode 0 per class) or 'dgr8' (mode 1 per class)."""
+        F, L = self.feats, self.L
+        u = self._up_state(l)
+        name = 'unet_conv_uparm_%d_0' % (L + (L - 2 - l))
+        cu, co = F[l + 1], F[l]
+        n, mode = (u['nf'], 0) if which == 'fwd8' else (u['nd'], 1)
+        for par in range(8):
+            self._packed_w(name, mode, cu, 0, co, tag=('up', par), src=u['weff'][par * 27 * cu * co:(par + 1) * 27 * cu * co],
+                           buf=u[which][par * n:(par + 1) * n])
+        return u[which]
 
     def _repack(self, st):
         """TF32-rounded, K-major packed copies of every kernel the tensor-core path has used so far, one launch."""
         self._packed_dirty = False
+        self._up_valid = False
+        self._up_weights_all(st)
         if getattr(self, '_pack_jobs_n', 0) != len(self._packed):   # device job table, rebuilt when a copy is added
             rows = []
             for key, buf in self._packed.items():
                 name, mode = key[0], key[1]
                 c1, c2, cout = self._packed_args[key]
-                rows.append([self.p[name + '/kernel'].data_ptr(), buf.data_ptr(), c1, c2, cout, mode])
+                rows.append([self._packed_src[key].data_ptr(), buf.data_ptr(), c1, c2, cout, mode])
             self._pack_jobs = torch.tensor(rows, dtype=torch.int64).to(self.device)
             self._pack_jobs_n = len(rows)
         lib.ssr_conv3d_pack_weights_batch(self._pack_jobs, self._pack_jobs_n, st)
@@ -379,8 +472,14 @@ class UNet3D:
         prev, prev_stats, prev_l = self.h1[L - 1], self.stats_enc[L - 1], L - 1
         for d in range(L - 1):
             l = L - 2 - d
-            lib.ssr_bn_apply(prev, self.u[l], prev_stats, B, *self.ldims[prev_l], F[prev_l], 2, 0, 0, st)
-            self._conv_fwd('unet_conv_uparm_%d_0' % (L + d), self.h1[l], F[l], self.u[l], F[l + 1], self.g0[l], l, F[l])
+            if l in self.up_levels:
+                lib.ssr_bn_apply(prev, self.vlow[l], prev_stats, B, *self.ldims[prev_l], F[prev_l], 0, 0, 0, st)
+                if training and not self.up_wgrad:      # the weight gradient still reads the upsampled tensor
+                    lib.ssr_bn_apply(prev, self.u[l], prev_stats, B, *self.ldims[prev_l], F[prev_l], 2, 0, 0, st)
+                self._conv_fwd_up('unet_conv_uparm_%d_0' % (L + d), l)
+            else:
+                lib.ssr_bn_apply(prev, self.u[l], prev_stats, B, *self.ldims[prev_l], F[prev_l], 2, 0, 0, st)
+                self._conv_fwd('unet_conv_uparm_%d_0' % (L + d), self.h1[l], F[l], self.u[l], F[l + 1], self.g0[l], l, F[l])
             fused = training and self._k2n_epi_ok(F[l], F[l])
             self._conv_fwd('unet_conv_uparm_%d_1' % (L + d), self.g0[l], F[l], None, 0, self.g1[l], l, F[l],
                            stats_sums=self.sums if fused else None)
@@ -475,9 +574,12 @@ class UNet3D:
                     self._conv_dgrad(c1n, self.ga[l], self.gb[l], l, F[l], F[l])
                     lib.ssr_elu_bwd(self.gb[l], 0, 0, self.g0[l], None, self.nvox[l], F[l], self.gb[l], self.g[c0 + '/bias'], st)
                 self._wgrad_async(c0, self.h1[l], F[l], self.u[l], F[l + 1], self.gb[l], l, F[l])
-                self._conv_dgrad(c0, self.gb[l], self.dcat[l], l, F[l] + F[l + 1], F[l])
                 tgt = self.dbn_dec[l + 1] if l + 1 <= L - 2 else self.dbn_bott
-                lib.ssr_upsample_bwd(self.dcat[l], F[l] + F[l + 1], F[l], B, *self.ldims[l + 1], F[l + 1], tgt, st)
+                if l in self.up_levels:
+                    self._conv_dgrad_up(c0, l, self.gb[l], tgt)
+                else:
+                    self._conv_dgrad(c0, self.gb[l], self.dcat[l], l, F[l] + F[l + 1], F[l])
+                    lib.ssr_upsample_bwd(self.dcat[l], F[l] + F[l + 1], F[l], B, *self.ldims[l + 1], F[l + 1], tgt, st)
             # ---- encoder, deep to shallow -----------------------------------------------------------------------
             for l in range(L - 1, -1, -1):
                 c0, c1n, bn = 'unet_conv_downarm_%d_0' % l, 'unet_conv_downarm_%d_1' % l, 'unet_bn_down_%d' % l
@@ -485,14 +587,16 @@ class UNet3D:
                     lib.ssr_bn_bwd(self.dbn_bott, self.h1[l], self.stats_enc[l], self.nvox[l], F[l], None, 0, 0, 1,
                                    self.ga_e[l], self.g[bn + '/gamma'], self.g[bn + '/beta'], self.g[c1n + '/bias'], self.sums, st)
                 elif self.pool_bn_fusion and F[l] % 4 == 0 and 192 % (F[l] // 4) == 0:
-                    lib.ssr_pool_bn_bwd(self.dp[l + 1], self.h1[l], self.stats_enc[l], B, *self.ldims[l], F[l], self.dcat[l],
-                                        F[l] + F[l + 1], 0, 1, self.ga_e[l], self.g[bn + '/gamma'], self.g[bn + '/beta'],
+                    add, add_stride = (self.dskip[l], F[l]) if l in self.up_levels else (self.dcat[l], F[l] + F[l + 1])
+                    lib.ssr_pool_bn_bwd(self.dp[l + 1], self.h1[l], self.stats_enc[l], B, *self.ldims[l], F[l], add,
+                                        add_stride, 0, 1, self.ga_e[l], self.g[bn + '/gamma'], self.g[bn + '/beta'],
                                         self.g[c1n + '/bias'], self.sums, st)
                 else:
+                    add, add_stride = (self.dskip[l], F[l]) if l in self.up_levels else (self.dcat[l], F[l] + F[l + 1])
                     lib.ssr_maxpool_bwd(self.dp[l + 1], self.h1[l], self.stats_enc[l], B, *self.ldims[l], F[l], self.ga_e[l],
                                         st)
-                    lib.ssr_bn_bwd(self.ga_e[l], self.h1[l], self.stats_enc[l], self.nvox[l], F[l], self.dcat[l],
-                                   F[l] + F[l + 1], 0, 1, self.ga_e[l], self.g[bn + '/gamma'], self.g[bn + '/beta'],
+                    lib.ssr_bn_bwd(self.ga_e[l], self.h1[l], self.stats_enc[l], self.nvox[l], F[l], add,
+                                   add_stride, 0, 1, self.ga_e[l], self.g[bn + '/gamma'], self.g[bn + '/beta'],
                                    self.g[c1n + '/bias'], self.sums, st)
                 self._wgrad_async(c1n, self.h0[l], F[l], None, 0, self.ga_e[l], l, F[l])
                 if self._k2n_epi_ok(F[l], F[l]):

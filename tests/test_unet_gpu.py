@@ -470,3 +470,139 @@ def test_pool_bn_bwd_equals_maxpool_bwd_then_bn_bwd():
         for a, b_, name in zip(res[0], res[1], ('dx', 'dgamma', 'dbeta', 'dbias')):
             err = (a - b_).abs().max().item() / (a.abs().max().item() + 1e-30)
             assert err < 2e-6, (name, B, d, C, err)
+
+
+def _parity_taps(p, k):
+    """original taps of one axis that land on effective tap k for output parity p (conv over a 2x nearest-upsampled axis)."""
+    return ({0: [0], 1: [1, 2], 2: []} if p == 0 else {0: [], 1: [0, 1], 2: [2]})[k]
+
+
+def _effective_kernels(w_up):
+    """w_up (3,3,3,Cup,Cout) float64 -> weff (8,3,3,3,Cup,Cout): independent restatement of up_weights_kernel."""
+    weff = torch.zeros((8,) + tuple(w_up.shape), dtype=torch.float64)
+    for par in range(8):
+        p = [(par >> 2) & 1, (par >> 1) & 1, par & 1]
+        for k0 in range(3):
+            for k1 in range(3):
+                for k2 in range(3):
+                    for t0 in _parity_taps(p[0], k0):
+                        for t1 in _parity_taps(p[1], k1):
+                            for t2 in _parity_taps(p[2], k2):
+                                weff[par, k0, k1, k2] += w_up[t0, t1, t2]
+    return weff
+
+
+def test_tc_up_parity_kernels_match_float64():
+    """conv3d_tc_up_kernel: convolution over a nearest-upsampled tensor computed from the LOW-resolution tensor (8 parity
+    classes of effective 2x2x2 kernels) -- forward partial sums + skip accumulation, and the gradient w.r.t. the
+    low-resolution tensor -- against float64: (a) on identically rounded operands, tight; (b) against the textbook
+    upsample -> conv3d with unrounded weights, TF32 bar."""
+    from synthsr_b200._lib import lib, stream_ptr
+    F = torch.nn.functional
+    rng = np.random.default_rng(21)
+    for (dl, cs, cu, co) in [([8, 8, 8], 24, 48, 24), ([5, 9, 11], 24, 48, 24), ([6, 16, 9], 48, 96, 48),
+                             ([4, 5, 7], 96, 192, 96), ([3, 4, 2], 8, 16, 8), ([20, 20, 20], 24, 48, 24)]:
+        df = [2 * v for v in dl]
+        nl, nf = int(np.prod(dl)), int(np.prod(df))
+        st = stream_ptr()
+        w = (rng.normal(size=(3, 3, 3, cs + cu, co)) / np.sqrt(27 * (cs + cu))).astype(np.float32)
+        wt = torch.from_numpy(w).cuda()
+        low = torch.from_numpy(rng.normal(size=(nl, cu)).astype(np.float32)).cuda()
+        skip = torch.from_numpy(rng.normal(size=(nf, cs)).astype(np.float32)).cuda()
+        bias = torch.from_numpy(rng.normal(size=co).astype(np.float32)).cuda()
+        wskip = torch.empty(27 * cs * co, device='cuda')
+        weff = torch.empty(8 * 27 * cu * co, device='cuda')
+        lib.ssr_conv3d_up_weights(wt, cs, cu, co, wskip, weff, st)
+        torch.cuda.synchronize()
+        weff_ref = _effective_kernels(torch.from_numpy(w[:, :, :, cs:, :]).double())
+        assert torch.equal(wskip.cpu().view(3, 3, 3, cs, co), torch.from_numpy(w[:, :, :, :cs, :]))
+        assert (weff.cpu().double().view(8, 3, 3, 3, cu, co) - weff_ref).abs().max().item() < 1e-6
+        # ---- forward: parity kernel (partial sums), then the skip convolution accumulates + bias + ELU
+        nfw = lib.ssr_conv3d_packed_size(cu, 0, co, 0)
+        fwd8 = torch.empty(8 * nfw, device='cuda')
+        for par in range(8):
+            lib.ssr_conv3d_pack_weights(weff[par * 27 * cu * co:(par + 1) * 27 * cu * co], fwd8[par * nfw:(par + 1) * nfw],
+                                        cu, 0, co, 0, st)
+        y = torch.full((nf, co), float('nan'), device='cuda')
+        lib.ssr_conv3d_fwd_tc_up(low, cu, fwd8, y, 1, *dl, co, st)
+        torch.cuda.synchronize()
+        assert not torch.isnan(y).any(), ('fwd-up left holes', dl, cu, co)
+        # (a) float64 on rounded operands: per parity class a low-resolution convolution, scattered to the sub-lattice
+        lowr = _rne_tf32(low).double().cpu().view(1, *dl, cu).permute(0, 4, 1, 2, 3)
+        weffr = _rna_tf32(weff).double().cpu().view(8, 3, 3, 3, cu, co)
+        ya = torch.zeros(1, co, *df, dtype=torch.float64)
+        for par in range(8):
+            p = [(par >> 2) & 1, (par >> 1) & 1, par & 1]
+            ya[:, :, p[0]::2, p[1]::2, p[2]::2] = F.conv3d(lowr, weffr[par].permute(4, 3, 0, 1, 2), padding=1)
+        ya = ya.permute(0, 2, 3, 4, 1).reshape(nf, co)
+        err = (y.double().cpu() - ya).abs().max().item() / ya.abs().max().item()
+        assert err < 2e-5, ('fwd-up rounded', dl, cu, co, err)
+        # (b) textbook: upsample -> conv3d with the original (unrounded) kernel
+        up = F.interpolate(low.double().cpu().view(1, *dl, cu).permute(0, 4, 1, 2, 3), scale_factor=2, mode='nearest')
+        w64 = torch.from_numpy(w).double()
+        yb = F.conv3d(up, w64[:, :, :, cs:, :].permute(4, 3, 0, 1, 2), padding=1).permute(0, 2, 3, 4, 1).reshape(nf, co)
+        err = (y.double().cpu() - yb).norm().item() / yb.norm().item()
+        assert err < 1e-3, ('fwd-up textbook', dl, cu, co, err)
+        # skip part accumulates (generic kernel), bias + ELU
+        wps = torch.empty(lib.ssr_conv3d_packed_size(cs, 0, co, 0), device='cuda')
+        lib.ssr_conv3d_pack_weights(wskip, wps, cs, 0, co, 0, st)
+        lib.ssr_conv3d_fwd_tc_acc(skip, cs, None, 0, wps, bias, y, 1, *df, co, 1, st)
+        torch.cuda.synchronize()
+        sk = skip.double().cpu().view(1, *df, cs).permute(0, 4, 1, 2, 3)
+        full = F.elu(F.conv3d(torch.cat([sk, up], 1), w64.permute(4, 3, 0, 1, 2), bias.double().cpu(), padding=1))
+        full = full.permute(0, 2, 3, 4, 1).reshape(nf, co)
+        err = (y.double().cpu() - full).norm().item() / full.norm().item()
+        assert err < 1e-3, ('decoder conv textbook', dl, cs, cu, co, err)
+        # ---- gradient w.r.t. the low-resolution tensor (UpSampling3D backward included)
+        dy = torch.from_numpy(rng.normal(size=(nf, co)).astype(np.float32)).cuda()
+        ndg = lib.ssr_conv3d_packed_size(cu, 0, co, 1)
+        dgr8 = torch.empty(8 * ndg, device='cuda')
+        for par in range(8):
+            lib.ssr_conv3d_pack_weights(weff[par * 27 * cu * co:(par + 1) * 27 * cu * co], dgr8[par * ndg:(par + 1) * ndg],
+                                        cu, 0, co, 1, st)
+        dlow = torch.full((nl, cu), float('nan'), device='cuda')
+        lib.ssr_conv3d_dgrad_tc_up(dy, co, dgr8, dlow, 1, *dl, cu, st)
+        torch.cuda.synchronize()
+        assert not torch.isnan(dlow).any()
+        dyr = _rne_tf32(dy).double().cpu().view(1, *df, co).permute(0, 4, 1, 2, 3)
+        da = torch.zeros(1, cu, *dl, dtype=torch.float64)
+        for par in range(8):
+            p = [(par >> 2) & 1, (par >> 1) & 1, par & 1]
+            da += F.conv_transpose3d(dyr[:, :, p[0]::2, p[1]::2, p[2]::2].contiguous(), weffr[par].permute(4, 3, 0, 1, 2), padding=1)
+        da = da.permute(0, 2, 3, 4, 1).reshape(nl, cu)
+        err = (dlow.double().cpu() - da).abs().max().item() / da.abs().max().item()
+        assert err < 2e-5, ('dgrad-up rounded', dl, cu, co, err)
+        upg = up.clone().requires_grad_(True)
+        lowg = low.double().cpu().view(1, *dl, cu).permute(0, 4, 1, 2, 3).clone().requires_grad_(True)
+        yy = F.conv3d(F.interpolate(lowg, scale_factor=2, mode='nearest'), w64[:, :, :, cs:, :].permute(4, 3, 0, 1, 2), padding=1)
+        yy.backward(dy.double().cpu().view(1, *df, co).permute(0, 4, 1, 2, 3))
+        db = lowg.grad.permute(0, 2, 3, 4, 1).reshape(nl, cu)
+        err = (dlow.double().cpu() - db).norm().item() / db.norm().item()
+        assert err < 1e-3, ('dgrad-up textbook', dl, cu, co, err)
+
+
+def test_tc_step_parity_path_equals_materialised_upsampling():
+    """one training step with the parity decoder path against the same step through the materialised upsampled tensor:
+    same mathematics, TF32 rounding applied to (sums of) kernels instead of kernels -> agreement at TF32 level."""
+    from synthsr_b200.unet import UNet3D
+    dims, rng = [32, 48, 32], np.random.default_rng(12)
+    image = torch.from_numpy(rng.uniform(0, 1, size=(1, *dims, 1)).astype(np.float32)).cuda()
+    target = torch.from_numpy(rng.uniform(0, 1, size=(1, *dims, 1)).astype(np.float32)).cuda()
+    out = []
+    for parity in (True, False):
+        import os
+        if not parity:
+            os.environ['SSR_NO_UP_PARITY'] = '1'
+        try:
+            net = UNet3D(dims + [1], nb_levels=3, batchsize=1, conv_impl='tc', seed=3)
+            net.up_min_dim = 1
+        finally:
+            os.environ.pop('SSR_NO_UP_PARITY', None)
+        assert bool(net.up_levels) == parity
+        loss = net.loss_and_grad(image, target)
+        torch.cuda.synchronize()
+        out.append((loss.item(), net.grads.clone(), net.pred.clone()))
+    (l1, g1, p1), (l2, g2, p2) = out
+    assert abs(l1 - l2) <= 2e-4 * abs(l2), (l1, l2)
+    assert (p1 - p2).norm().item() <= 2e-3 * p2.norm().item()
+    assert (g1 - g2).norm().item() <= 5e-3 * g2.norm().item()
