@@ -144,6 +144,14 @@ int ssr_conv3d_dgrad_tc_k2n_elu(const float* dy, int C, const float* wp, const f
 int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const float* dy, float* dw, float* db,
                         float* scratch, long long scratch_bytes, int B, int d0, int d1, int d2, int Cout,
                         void* stream);
+/* weight gradient w.r.t. the input channels [cin_off, cin_off + C) of a kernel dw (27, cin_total, Cout) */
+int ssr_conv3d_wgrad_tc_part(const float* x, int C, const float* dy, float* dw, int cin_total, int cin_off, int B, int d0,
+                             int d1, int d2, int Cout, void* stream);
+/* upsampled part of a decoder convolution from the LOW-resolution tensor low [B,d0,d1,d2,Cup] and the full-resolution
+ * dy [B,2d0,2d1,2d2,Cout]: gradients of the 8 effective kernels (scratch: 8*27*Cup*Cout floats, zeroed here) combined into
+ * dw (27, cin_total, Cout) at input channels [cin_off, cin_off + Cup) */
+int ssr_conv3d_wgrad_tc_up(const float* low, int Cup, const float* dy, float* dw, int cin_total, int cin_off, float* scratch,
+                           int B, int d0, int d1, int d2, int Cout, void* stream);
 long long ssr_conv3d_wgrad_scratch_bytes(int C1, int C2, int Cout, int B, int d0, int d1, int d2);
 int ssr_tc_selftest(void* stream);
 int ssr_tc_set_debug(long long* buf);   /* profiling: per-CTA clock64 phase stamps of conv3d_tc_kernel */

@@ -814,6 +814,30 @@ __global__ void up_weights_kernel(const float* __restrict__ w, int Cskip, int Cu
   }
 }
 
+// dw[t][cin_off + ci][co] += sum_p geff[p][k(p, t)][ci][co]: the original tap t_a is part of the effective tap
+// k_a = (p_a == 0 ? (t_a == 0 ? 0 : 1) : (t_a == 2 ? 2 : 1)) of parity class p_a (transpose of up_weights_kernel)
+__global__ void up_wgrad_combine_kernel(const float* __restrict__ geff, float* __restrict__ dw, int cin_total, int cin_off,
+                                        int Cup, int Cout) {
+  const long long n = 27LL * Cup * Cout;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    long long r = t;
+    const int co = (int)(r % Cout); r /= Cout;
+    const int ci = (int)(r % Cup); r /= Cup;
+    const int t2 = (int)(r % 3); r /= 3;
+    const int t1 = (int)(r % 3);
+    const int t0 = (int)(r / 3);
+    float acc = 0.f;
+    for (int par = 0; par < 8; ++par) {
+      const int p0 = (par >> 2) & 1, p1 = (par >> 1) & 1, p2 = par & 1;
+      const int k0 = p0 == 0 ? (t0 == 0 ? 0 : 1) : (t0 == 2 ? 2 : 1);
+      const int k1 = p1 == 0 ? (t1 == 0 ? 0 : 1) : (t1 == 2 ? 2 : 1);
+      const int k2 = p2 == 0 ? (t2 == 0 ? 0 : 1) : (t2 == 2 ? 2 : 1);
+      acc += geff[(((long long)par * 27 + (k0 * 3 + k1) * 3 + k2) * Cup + ci) * Cout + co];
+    }
+    dw[((long long)((t0 * 3 + t1) * 3 + t2) * cin_total + cin_off + ci) * Cout + co] += acc;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Forward / data-gradient convolution for Cin <= 32, Cout <= 32 (the full-resolution 24-channel layers: half of the
 // forward + dgrad time).  With N = 32 the MMA is bound by reading the 128 x 8 A operand from shared memory (40 cycles
@@ -1120,6 +1144,7 @@ struct WgGeom {
   int NT, nNtiles, KG, SA, SBT;
   int nchunks, n1tiles, n2tiles, n0splits, zlen;
   int tmem_cols, exp_flags;
+  int cin_off;       // first input channel of this launch inside dw's Cin axis (G.Cin = dw's total Cin)
   unsigned char chunk_src[MAX_CHUNKS];
   unsigned char chunk_valid[MAX_CHUNKS];
   short chunk_c0[MAX_CHUNKS];
@@ -1486,9 +1511,15 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// PAR: weight gradient of the upsampled part of a decoder convolution from the LOW-resolution tensor (see
+// conv3d_tc_up_kernel): the 8 output parity classes are 8x more units; class p reads its own strided view of dy
+// (maps_dy.x[p]), accumulates the gradient of its effective kernel into dw + p * 27 * Cin * Cout (combined into the
+// 3x3x3 gradient by up_wgrad_combine_kernel) and skips the d0 tap its effective kernel does not have.
+template <bool PAR>
 __global__ void __launch_bounds__(WK_THREADS, 1)
 wgrad_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_x2,
-                           const __grid_constant__ CUtensorMap map_dy, float* __restrict__ dw, const WgGeom G) {
+                           const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ UpMaps maps_dy,
+                           float* __restrict__ dw, const WgGeom G) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -1505,7 +1536,8 @@ wgrad_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x1, const __g
 
   const int ntile = G.B * G.n1tiles * G.n2tiles;
   const long long W = (long long)ntile * G.D0;                    // plane steps per unit
-  const long long T = W * G.nchunks * G.nNtiles;
+  const int upp = G.nchunks * G.nNtiles;                          // units per parity class
+  const long long T = W * upp * (PAR ? 8 : 1);
   // this launch covers slice `zlen` of `n0splits` of the global list (several short launches instead of one long one let
   // higher-priority kernels of the backward chain get SMs between them)
   const long long sl0 = T * G.zlen / G.n0splits, sl1 = T * (G.zlen + 1) / G.n0splits;
@@ -1540,8 +1572,10 @@ wgrad_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x1, const __g
       for (long long g = g0; g < g1;) {
         const WpSeg sg = wp_segment(g, g1, W, G.D0);
         g = sg.gnext;
-        const int ch = sg.u / G.nNtiles, n0 = (sg.u % G.nNtiles) * 32;
+        const int par = PAR ? sg.u / upp : 0, uu = PAR ? sg.u % upp : sg.u;
+        const int ch = uu / G.nNtiles, n0 = (uu % G.nNtiles) * 32;
         const CUtensorMap* mx = G.chunk_src[ch] ? &map_x2 : &map_x1;
+        const CUtensorMap* my = PAR ? &maps_dy.x[par] : &map_dy;
         const int c0 = G.chunk_c0[ch];
         WP_TILE(sg.tile)
         const int pmin = max(sg.za - 1, 0), pmax = min(sg.zb, G.D0 - 1);
@@ -1557,7 +1591,7 @@ wgrad_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x1, const __g
           const int sb = seqB % WK_SB;
           mbar_wait(emptyB + sb, ((seqB / WK_SB) & 1) ^ 1);
           mbar_expect_tx(fullB + sb, WK_BSTAGE);
-          tma_load_5d(&map_dy, fullB + sb, sB + (size_t)sb * WK_BSTAGE, n0, x0 - 1, y0, zo, b);
+          tma_load_5d(my, fullB + sb, sB + (size_t)sb * WK_BSTAGE, n0, x0 - 1, y0, zo, b);
           ++seqB;
         }
       }
@@ -1576,6 +1610,9 @@ wgrad_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x1, const __g
       WP_TILE(sg.tile)
       const int nrows = min(TM1, G.D1 - y0);
       const int pmin = max(sg.za - 1, 0), pmax = min(sg.zb, G.D0 - 1);
+      // parity class p0 of the output planes: the effective kernel has the d0 taps {p0, p0 + 1} only
+      const int p0par = PAR ? ((sg.u / upp) >> 2) & 1 : 0;
+      const bool my_tap = !PAR || k0 == p0par || k0 == p0par + 1;
       for (int zo = sg.za; zo < sg.zb; ++zo, ++seqB) {
         const int sb = seqB % WK_SB;
         mbar_wait(fullB + sb, (seqB / WK_SB) & 1);
@@ -1586,6 +1623,14 @@ wgrad_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x1, const __g
           // slab p is released by three arrivals (taps k0 = 0, 1, 2 at planes p+1, p, p-1); readers that fall outside
           // this segment's plane range are accounted for by the in-range reader at the range end they fall off
           const int extra = (zo == sg.za ? 2 - k0 : 0) + (zo == sg.zb - 1 ? k0 : 0);
+          if (!my_tap) {                                           // tap absent from this parity class: release only
+            if (lane == 0) {
+              mbar_arrive(emptyB + sb);
+              for (int e = 0; e <= extra; ++e) mbar_arrive(emptyA + sa);
+            }
+            __syncwarp();
+            continue;
+          }
           if (elect_one()) {
             const uint32_t alo = a_base + (uint32_t)sa * (SLAB_BYTES >> 4), blo = b_base + (uint32_t)sb * (WK_BSTAGE >> 4);
             if (nrows == TM1) umma_chain_mn16_ab(dcol, alo, blo, DESC_HI_MN_SW128_32B, idesc, acc);
@@ -1625,14 +1670,17 @@ wgrad_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x1, const __g
       for (int k0 = 0; k0 < 3; ++k0)               // accumulator k0 received MMAs iff some plane pairs with an in-volume slab
         if (max(sg.za, 1 - k0) <= min(sg.zb - 1, G.D0 - k0)) touched |= 1u << k0;
       if (!sg.unit_last) continue;
-      const int ch = sg.u / G.nNtiles, n0 = (sg.u % G.nNtiles) * 32;
+      const int par = PAR ? sg.u / upp : 0, uu = PAR ? sg.u % upp : sg.u;
+      const int ch = uu / G.nNtiles, n0 = (uu % G.nNtiles) * 32;
+      float* dwp = dw + (PAR ? (long long)par * 27 * G.Cin * G.Cout : 0);
       mbar_wait(accFull, flushes & 1u);
       tc_fence_after();
       const int valid = G.chunk_valid[ch];
-      const int cin_idx = (G.chunk_src[ch] ? G.C1 : 0) + G.chunk_c0[ch] + lane;
+      const int cin_idx = G.cin_off + (G.chunk_src[ch] ? G.C1 : 0) + G.chunk_c0[ch] + lane;
       if (q < 3) {
         for (int k0 = 0; k0 < 3; ++k0) {
           if (!((touched >> k0) & 1u)) continue;      // uniform
+          if (PAR && k0 != ((par >> 2) & 1) && k0 != ((par >> 2) & 1) + 1) continue;   // tap absent from the class
           for (int cb = 0; cb < WK_N; cb += 16) {
             const int k2 = 2 - (cb >> 5), cobase = n0 + (cb & 31);  // column = (2 - k2) * 32 + co
             if (cobase >= G.Cout) continue;           // padded output channels (uniform)
@@ -1640,7 +1688,7 @@ wgrad_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x1, const __g
             tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(k0 * WK_N + cb), v);
             tmem_ld_wait();
             if (lane < valid) {
-              float* o = dw + ((long long)(((k0 * 3 + q) * 3 + k2)) * G.Cin + cin_idx) * G.Cout + cobase;
+              float* o = dwp + ((long long)(((k0 * 3 + q) * 3 + k2)) * G.Cin + cin_idx) * G.Cout + cobase;
               const int nv = G.Cout - cobase;
               if (vec && nv >= 16) {
 #pragma unroll
@@ -2134,15 +2182,16 @@ static int up_tile_shape(int Npad, int B, int D0, int D1, int D2, int ks_total, 
 }
 
 static int make_map_view(CUtensorMap* m, const float* ptr, int C, int B, int D0, int D1, int D2, long long s2, long long s1,
-                         long long s0, long long sb) {      // strides in floats; dims (C, D2, D1, D0, B)
+                         long long s0, long long sb, int box_d1 = TM1 + 2, int box_d2 = TM2,
+                         CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {      // strides in floats; dims (C, D2, D1, D0, B)
   EncodeTiledFn enc = get_encode();
   if (!enc) { ssr_set_error("cuTensorMapEncodeTiled not available"); return SSR_ERR_CUDA; }
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)D2, (cuuint64_t)D1, (cuuint64_t)D0, (cuuint64_t)B};
   cuuint64_t strides[4] = {(cuuint64_t)s2 * 4, (cuuint64_t)s1 * 4, (cuuint64_t)s0 * 4, (cuuint64_t)sb * 4};
-  cuuint32_t box[5] = {32, (cuuint32_t)TM2, (cuuint32_t)(TM1 + 2), 1, 1};
+  cuuint32_t box[5] = {32, (cuuint32_t)box_d2, (cuuint32_t)box_d1, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, tma_dtype(), 5, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { ssr_set_error("cuTensorMapEncodeTiled(strided view C=%d %dx%dx%d) failed: %d", C, D0, D1, D2, (int)r); return SSR_ERR_CUDA; }
   return SSR_OK;
 }
@@ -2331,16 +2380,19 @@ int ssr_conv3d_fwd_tc_k2n_stats(const float* x, int C, const float* wp, const fl
 long long ssr_conv3d_wgrad_scratch_bytes(int, int, int, int, int, int, int) { return 0; }
 
 // dw (3,3,3,C1+C2,Cout) += [x1,x2] (*) dy  ;  db[Cout] += sum_v dy   (tcgen05, see wgrad_tc_kernel)
-int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const float* dy, float* dw, float* db,
-                        float* scratch, long long scratch_bytes, int B, int D0, int D1, int D2, int Cout,
-                        void* stream) {
-  (void)scratch; (void)scratch_bytes;
+// cin_total / cin_off: dw is (27, cin_total, Cout) and this launch covers its input channels [cin_off, cin_off + C1 + C2)
+// (cin_total <= 0: dw is exactly (27, C1 + C2, Cout)).  parity: dy is the FULL-resolution gradient [B,2D0,2D1,2D2,Cout],
+// x1 the low-resolution tensor, dw receives the 8 effective-kernel gradients (8, 27, C1, Cout) (see conv3d_tc_up_kernel).
+static int wgrad_tc_impl(const float* x1, int C1, const float* x2, int C2, const float* dy, float* dw, float* db,
+                         int B, int D0, int D1, int D2, int Cout, void* stream, int cin_total, int cin_off, int parity) {
   SSR_CHECK_ARG(x1 && dy && dw && B > 0 && D0 > 0 && D1 > 0 && D2 > 0 && Cout > 0, "pointers/shape");
   SSR_CHECK_ARG(C1 > 0 && C1 % 8 == 0 && C2 >= 0 && C2 % 8 == 0 && (C2 == 0 || x2) && Cout % 8 == 0,
                 "channel counts must be multiples of 8");
   WgGeom G;
   memset(&G, 0, sizeof(G));
-  G.B = B; G.D0 = D0; G.D1 = D1; G.D2 = D2; G.Cin = C1 + C2; G.Cout = Cout;
+  G.B = B; G.D0 = D0; G.D1 = D1; G.D2 = D2; G.Cin = cin_total > 0 ? cin_total : C1 + C2; G.Cout = Cout;
+  G.cin_off = cin_total > 0 ? cin_off : 0;
+  SSR_CHECK_ARG(G.cin_off >= 0 && G.cin_off + C1 + C2 <= G.Cin, "channel range");
   const int Npad = round_up(Cout, 32);
   int ntile = Npad;
   if (ntile > 96) { ntile = 96; while (Npad % ntile) ntile -= 32; }
@@ -2371,7 +2423,21 @@ int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const 
   const CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;     // MN-major tf32 operands (UMMA 128B_BASE32B)
   int rc = make_map_act(&m1, x1, C1, B, D0, D1, D2, TM1 + 2, swz); if (rc) return rc;
   if (C2 > 0) { rc = make_map_act(&m2, x2, C2, B, D0, D1, D2, TM1 + 2, swz); if (rc) return rc; } else m2 = m1;
-  rc = make_map_act(&my, dy, Cout, B, D0, D1, D2, TM1, swz, k2n ? TM2 + 2 : TM2); if (rc) return rc;
+  UpMaps mys;
+  memset(&mys, 0, sizeof(mys));
+  if (parity) {
+    SSR_CHECK_ARG(k2n && !getenv("SSR_WGRAD_NO_PERSISTENT") && C2 == 0, "the parity weight gradient needs the persistent kernel");
+    const long long F0 = 2LL * D0, F1 = 2LL * D1, F2 = 2LL * D2;
+    for (int par = 0; par < 8; ++par) {
+      const long long off = ((((par >> 2) & 1) * F1 + ((par >> 1) & 1)) * F2 + (par & 1)) * Cout;
+      rc = make_map_view(&mys.x[par], dy + off, Cout, B, D0, D1, D2, 2LL * Cout, 2 * F2 * Cout, 2 * F1 * F2 * Cout,
+                         F0 * F1 * F2 * Cout, TM1, TM2 + 2, swz);
+      if (rc) return rc;
+    }
+    my = mys.x[0];
+  } else {
+    rc = make_map_act(&my, dy, Cout, B, D0, D1, D2, TM1, swz, k2n ? TM2 + 2 : TM2); if (rc) return rc;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     SSR_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -2387,10 +2453,11 @@ int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const 
       int dev = 0;
       SSR_CHECK_CUDA(cudaGetDevice(&dev));
       SSR_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-      SSR_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      SSR_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      SSR_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
     // plane steps: units x tiles x planes, cut into equal contiguous ranges (at least ~4 planes per CTA)
-    const long long T = (long long)nch * G.nNtiles * G.n1tiles * G.n2tiles * B * D0;
+    const long long T = (long long)nch * G.nNtiles * G.n1tiles * G.n2tiles * B * D0 * (parity ? 8 : 1);
     // one launch; SSR_WGRAD_SLICES > 1 cuts it into several shorter launches (measured slower: 14.2 / 14.5 / 15.1 ms per
     // step for 1 / 2 / 4 slices -- the extra flushes cost more than the earlier SM hand-over to the dgrad chain gains)
     int nslices = 1;
@@ -2403,7 +2470,8 @@ int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const 
       const long long Ts = T * (sl + 1) / nslices - T * sl / nslices;
       long long grid = num_sms;
       if (Ts / 4 < grid) grid = Ts / 4 > 0 ? Ts / 4 : 1;
-      wgrad_tc_persistent_kernel<<<(unsigned)grid, WK_THREADS, smem, st>>>(m1, m2, my, dw, G);
+      if (parity) wgrad_tc_persistent_kernel<true><<<(unsigned)grid, WK_THREADS, smem, st>>>(m1, m2, my, mys, dw, G);
+      else wgrad_tc_persistent_kernel<false><<<(unsigned)grid, WK_THREADS, smem, st>>>(m1, m2, my, mys, dw, G);
       if (sl + 1 < nslices) SSR_COUNT_LAUNCH();
     }
   } else if (k2n) wgrad_tc_k2n_kernel<<<(unsigned)nblk, WK_THREADS, smem, st>>>(m1, m2, my, dw, G);
@@ -2411,10 +2479,40 @@ int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const 
   SSR_COUNT_LAUNCH();
   SSR_CHECK_LAUNCH();
   if (db) {
-    const long long nvox = (long long)B * D0 * D1 * D2;
+    const long long nvox = (long long)B * D0 * D1 * D2 * (parity ? 8 : 1);
     int rc2 = ssr_channel_sum(dy, nvox, Cout, db, stream);
     if (rc2) return rc2;
   }
+  return SSR_OK;
+}
+
+int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const float* dy, float* dw, float* db,
+                        float* scratch, long long scratch_bytes, int B, int D0, int D1, int D2, int Cout,
+                        void* stream) {
+  (void)scratch; (void)scratch_bytes;
+  return wgrad_tc_impl(x1, C1, x2, C2, dy, dw, db, B, D0, D1, D2, Cout, stream, 0, 0, 0);
+}
+// weight gradient w.r.t. the input channels [cin_off, cin_off + C) of a kernel dw (27, cin_total, Cout)
+int ssr_conv3d_wgrad_tc_part(const float* x, int C, const float* dy, float* dw, int cin_total, int cin_off, int B, int D0,
+                             int D1, int D2, int Cout, void* stream) {
+  return wgrad_tc_impl(x, C, nullptr, 0, dy, dw, nullptr, B, D0, D1, D2, Cout, stream, cin_total, cin_off, 0);
+}
+// Upsampled part of a decoder convolution: low [B,d0,d1,d2,Cup] (the tensor that is upsampled), dy [B,2d0,2d1,2d2,Cout];
+// dw (27, cin_total, Cout) += gradient w.r.t. the input channels [cin_off, cin_off + Cup).  scratch: 8*27*Cup*Cout floats
+// (zeroed here) for the gradients of the 8 effective kernels.
+int ssr_conv3d_wgrad_tc_up(const float* low, int Cup, const float* dy, float* dw, int cin_total, int cin_off, float* scratch,
+                           int B, int d0, int d1, int d2, int Cout, void* stream) {
+  SSR_CHECK_ARG(scratch && dw && cin_off >= 0 && cin_off + Cup <= cin_total, "args");
+  cudaStream_t st = (cudaStream_t)stream;
+  SSR_CHECK_CUDA(cudaMemsetAsync(scratch, 0, 8ULL * 27 * Cup * Cout * sizeof(float), st));
+  int rc = wgrad_tc_impl(low, Cup, nullptr, 0, dy, scratch, nullptr, B, d0, d1, d2, Cout, stream, 0, 0, 1);
+  if (rc) return rc;
+  const long long n = 27LL * Cup * Cout;
+  long long g = (n + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  up_wgrad_combine_kernel<<<(unsigned)g, 256, 0, st>>>(scratch, dw, cin_total, cin_off, Cup, Cout);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
   return SSR_OK;
 }
 

@@ -83,7 +83,8 @@ class UNet3D:
         # low-resolution tensor (conv3d_tc_up_kernel): levels whose low-resolution grid is at least up_min_dim wide
         self.up_parity = conv_impl == 'tc' and os.environ.get('SSR_NO_UP_PARITY') is None
         self.up_min_dim = int(os.environ.get('SSR_UP_MIN_DIM', '16'))
-        self.up_wgrad = False         # weight gradient of those layers from the low-resolution tensor too
+        # weight gradient of those layers from the low-resolution tensor too (the upsampled tensor is never materialised)
+        self.up_wgrad = self.up_parity and os.environ.get('SSR_NO_UP_WGRAD') is None
         self.epi_fusion = self.fwd_k2n and os.environ.get('SSR_NO_EPI_FUSION') is None
         self._side, self._side_busy, self._hp, self._pack_event = None, False, None, None
         self.device = torch.device(device)
@@ -173,7 +174,7 @@ class UNet3D:
         self.inp = [None] + [buf(l, F[l - 1]) for l in range(1, L)]           # pooled BN output feeding level l
         self.h0 = [buf(l, F[l]) for l in range(L)]
         self.h1 = [buf(l, F[l]) for l in range(L)]
-        self.u = [buf(l, F[l + 1]) for l in range(L - 1)]                     # upsampled BN output (decoder input)
+        self.u = [None] * (L - 1)                                             # upsampled BN output (decoder input), lazily
         self.g0 = [buf(l, F[l]) for l in range(L - 1)]
         self.g1 = [buf(l, F[l]) for l in range(L - 1)]
         self.up_levels = [l for l in range(L - 1) if self.up_parity and F[l] % 8 == 0 and F[l + 1] % 8 == 0 and
@@ -342,12 +343,29 @@ class UNet3D:
             lib.ssr_conv3d_wgrad_ref(x1, c1, x2, c2, dy, self.g[name + '/kernel'], None, self.B, *d,
                                      cout, self.k, st)
 
-    def _wgrad_async(self, *args):
+    def _conv_wgrad_up(self, name, l, dy):
+        """weight gradient of decoder convolution 0 of level l: skip channels from h1[l], upsampled channels from the
+        low-resolution tensor vlow[l] (gradients of the 8 effective kernels, combined into the 3x3x3 gradient)."""
+        F = self.feats
+        self._timed('wgrad_tc', l, F[l] + F[l + 1], F[l], lambda: self._conv_wgrad_up_impl(name, l, dy))
+
+    def _conv_wgrad_up_impl(self, name, l, dy):
+        st, F, B = stream_ptr(), self.feats, self.B
+        u = self._up_state(l)
+        if 'gscratch' not in u:
+            u['gscratch'] = torch.empty(8 * 27 * F[l + 1] * F[l], dtype=torch.float32, device=self.device)
+        dw = self.g[name + '/kernel']
+        lib.ssr_conv3d_wgrad_tc_part(self.h1[l], F[l], dy, dw, F[l] + F[l + 1], 0, B, *self.ldims[l], F[l], st)
+        lib.ssr_conv3d_wgrad_tc_up(self.vlow[l], F[l + 1], dy, dw, F[l] + F[l + 1], F[l], u['gscratch'], B,
+                                   *self.ldims[l + 1], F[l], st)
+
+    def _wgrad_async(self, *args, fn=None):
         """weight gradients only feed the optimiser, so they run on a side stream: the memory-bound elementwise kernels
         of the backward chain (BN / ELU / pooling gradients) then overlap with tensor-core-bound wgrad kernels instead
         of waiting for them.  Disabled while per-kernel profiling is on (timings would overlap)."""
+        fn = fn or self._conv_wgrad
         if self.prof is not None or not self.overlap_wgrad:
-            return self._conv_wgrad(*args)
+            return fn(*args)
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device)
             self._ev_pool = [torch.cuda.Event() for _ in range(64)]
@@ -357,7 +375,7 @@ class UNet3D:
         ev.record()                                   # the gradient this wgrad reads is complete on the main stream
         with torch.cuda.stream(self._side):
             self._side.wait_event(ev)
-            self._conv_wgrad(*args)
+            fn(*args)
         self._side_busy = True
 
     def _wgrad_join(self):
@@ -475,10 +493,10 @@ class UNet3D:
             if l in self.up_levels:
                 lib.ssr_bn_apply(prev, self.vlow[l], prev_stats, B, *self.ldims[prev_l], F[prev_l], 0, 0, 0, st)
                 if training and not self.up_wgrad:      # the weight gradient still reads the upsampled tensor
-                    lib.ssr_bn_apply(prev, self.u[l], prev_stats, B, *self.ldims[prev_l], F[prev_l], 2, 0, 0, st)
+                    lib.ssr_bn_apply(prev, self._u(l), prev_stats, B, *self.ldims[prev_l], F[prev_l], 2, 0, 0, st)
                 self._conv_fwd_up('unet_conv_uparm_%d_0' % (L + d), l)
             else:
-                lib.ssr_bn_apply(prev, self.u[l], prev_stats, B, *self.ldims[prev_l], F[prev_l], 2, 0, 0, st)
+                lib.ssr_bn_apply(prev, self._u(l), prev_stats, B, *self.ldims[prev_l], F[prev_l], 2, 0, 0, st)
                 self._conv_fwd('unet_conv_uparm_%d_0' % (L + d), self.h1[l], F[l], self.u[l], F[l + 1], self.g0[l], l, F[l])
             fused = training and self._k2n_epi_ok(F[l], F[l])
             self._conv_fwd('unet_conv_uparm_%d_1' % (L + d), self.g0[l], F[l], None, 0, self.g1[l], l, F[l],
@@ -493,6 +511,11 @@ class UNet3D:
         lib.ssr_bn_apply(self.g1[0], self.feat, self.stats_dec[0], B, *self.ldims[0], F[0], 0, 0, 0, st)
         self._feat_src, self._feat_stats = self.feat, None
         return self.feat
+
+    def _u(self, l):
+        if self.u[l] is None:
+            self.u[l] = torch.empty((self.nvox[l], self.feats[l + 1]), dtype=torch.float32, device=self.device)
+        return self.u[l]
 
     def _bn_stats(self, bn, x, nvox, C, stats, training, have_sums=False):
         st = stream_ptr()
@@ -573,7 +596,10 @@ class UNet3D:
                 else:
                     self._conv_dgrad(c1n, self.ga[l], self.gb[l], l, F[l], F[l])
                     lib.ssr_elu_bwd(self.gb[l], 0, 0, self.g0[l], None, self.nvox[l], F[l], self.gb[l], self.g[c0 + '/bias'], st)
-                self._wgrad_async(c0, self.h1[l], F[l], self.u[l], F[l + 1], self.gb[l], l, F[l])
+                if l in self.up_levels and self.up_wgrad:
+                    self._wgrad_async(c0, l, self.gb[l], fn=self._conv_wgrad_up)
+                else:
+                    self._wgrad_async(c0, self.h1[l], F[l], self.u[l], F[l + 1], self.gb[l], l, F[l])
                 tgt = self.dbn_dec[l + 1] if l + 1 <= L - 2 else self.dbn_bott
                 if l in self.up_levels:
                     self._conv_dgrad_up(c0, l, self.gb[l], tgt)

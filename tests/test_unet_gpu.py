@@ -606,3 +606,37 @@ def test_tc_step_parity_path_equals_materialised_upsampling():
     assert abs(l1 - l2) <= 2e-4 * abs(l2), (l1, l2)
     assert (p1 - p2).norm().item() <= 2e-3 * p2.norm().item()
     assert (g1 - g2).norm().item() <= 5e-3 * g2.norm().item()
+
+
+def test_tc_up_parity_weight_gradient_matches_float64():
+    """ssr_conv3d_wgrad_tc_part (skip channels) + ssr_conv3d_wgrad_tc_up (upsampled channels from the LOW-resolution
+    tensor: 8 effective-kernel gradients combined) against the float64 weight gradient of upsample -> concat -> conv3d."""
+    from synthsr_b200._lib import lib, stream_ptr
+    F = torch.nn.functional
+    rng = np.random.default_rng(22)
+    for (dl, cs, cu, co) in [([8, 8, 8], 24, 48, 24), ([5, 9, 11], 24, 48, 24), ([6, 16, 9], 48, 96, 48), ([3, 4, 2], 8, 16, 8),
+                             ([20, 20, 20], 24, 48, 24)]:
+        df = [2 * v for v in dl]
+        nl, nf = int(np.prod(dl)), int(np.prod(df))
+        st = stream_ptr()
+        low = torch.from_numpy(rng.normal(size=(nl, cu)).astype(np.float32)).cuda()
+        skip = torch.from_numpy(rng.normal(size=(nf, cs)).astype(np.float32)).cuda()
+        dy = torch.from_numpy(rng.normal(size=(nf, co)).astype(np.float32)).cuda()
+        dw0 = torch.from_numpy(rng.normal(size=(27, cs + cu, co)).astype(np.float32)).cuda()      # accumulated into
+        dw = dw0.clone()
+        scratch = torch.full((8 * 27 * cu * co,), float('nan'), device='cuda')
+        lib.ssr_conv3d_wgrad_tc_part(skip, cs, dy, dw, cs + cu, 0, 1, *df, co, st)
+        lib.ssr_conv3d_wgrad_tc_up(low, cu, dy, dw, cs + cu, cs, scratch, 1, *dl, co, st)
+        torch.cuda.synchronize()
+        # float64 on the TF32-rounded operands (the weight gradient is bilinear in (x, dy); both are rounded by the TMA unit)
+        lowr = _rne_tf32(low).double().cpu().view(1, *dl, cu).permute(0, 4, 1, 2, 3)
+        skr = _rne_tf32(skip).double().cpu().view(1, *df, cs).permute(0, 4, 1, 2, 3)
+        dyr = _rne_tf32(dy).double().cpu().view(1, *df, co).permute(0, 4, 1, 2, 3)
+        w = torch.zeros(co, cs + cu, 3, 3, 3, dtype=torch.float64, requires_grad=True)
+        x = torch.cat([skr, F.interpolate(lowr, scale_factor=2, mode='nearest')], 1)
+        F.conv3d(x, w, padding=1).backward(dyr)
+        ref = w.grad.permute(2, 3, 4, 1, 0).reshape(27, cs + cu, co)
+        got = (dw - dw0).double().cpu()
+        for nm, sl in (('skip', slice(0, cs)), ('up', slice(cs, cs + cu))):
+            err = (got[:, sl] - ref[:, sl]).abs().max().item() / ref[:, sl].abs().max().item()
+            assert err < 3e-5, (nm, dl, cs, cu, co, err)
