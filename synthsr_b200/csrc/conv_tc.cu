@@ -872,7 +872,9 @@ struct KfGeom {
 //                           accumulator wait) and  dbias[c] += sum_v out[v][c]        -- replaces elu_bwd_kernel
 //   EPI 2 (forward):        sums[c] += sum_v out[v][c], sums[C + c] += sum_v out^2    -- replaces colsum2_vec_kernel<0>
 // NB = channel blocks of 8 (compile time so the accumulators stay in registers).
-template <int EPI, int NB>
+// ACC (with EPI 0, Cout == NB * 8): the partial sums already in y (G.accumulate) are prefetched before the accumulator wait
+// like h in EPI 1, instead of being loaded after it.
+template <int EPI, int NB, bool ACC = false>
 __global__ void __launch_bounds__(416, 1)
 conv3d_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                      const float* __restrict__ bias, float* __restrict__ y, const KfGeom G,
@@ -1009,11 +1011,16 @@ conv3d_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       for (int z = zs + h; z < ze; z += 2) {
         const int slot = (z - zs) & (KF_NACC - 1);
         const long long voff = ((((long long)b * G.D0 + z) * G.D1 + i1) * G.D2 + i2) * G.Cout;
-        float4 hp[EPI == 1 ? NB * 2 : 1];
+        float4 hp[(EPI == 1 || ACC) ? NB * 2 : 1];
         if constexpr (EPI == 1) {                     // h of this thread's voxel: in flight while the MMAs finish
 #pragma unroll
           for (int i = 0; i < NB * 2; ++i)
             hp[i] = store_ok ? __ldg(reinterpret_cast<const float4*>(elu_h + voff) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+        if constexpr (ACC) {                          // partial sums of the earlier parts (plain loads: y is written below)
+#pragma unroll
+          for (int i = 0; i < NB * 2; ++i)
+            hp[i] = store_ok ? *(reinterpret_cast<const float4*>(y + voff) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         mbar_wait(accFull + slot, (par >> slot) & 1u);
         par ^= 1u << slot;
@@ -1034,6 +1041,10 @@ conv3d_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[e]), 1);   // P_2 at input column x + 1
             o[e] = left + __uint_as_float(v1[e]) + right;
           }
+          if constexpr (ACC) {
+            const float4 pa = hp[2 * blk], pb = hp[2 * blk + 1];
+            o[0] += pa.x; o[1] += pa.y; o[2] += pa.z; o[3] += pa.w; o[4] += pb.x; o[5] += pb.y; o[6] += pb.z; o[7] += pb.w;
+          } else
           if (G.accumulate && store_ok) {             // partial sums of the earlier channel parts (fp32, pre-activation)
             const int nv8 = G.Cout - cb;
             if (nv8 >= 8 && vec_ok) {
@@ -1081,7 +1092,7 @@ conv3d_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
               if (e < nvalid) orow[cb + e] = o[e];
           }
         };
-        if constexpr (EPI == 0) {
+        if constexpr (EPI == 0 && !ACC) {
           for (int cb = 0; cb < nblk8 * 8; cb += 8) block(cb, 0);
         } else {                                      // Cout == NB * 8 (host-checked): constant indices into s1 / s2 / hp
 #pragma unroll
@@ -2006,15 +2017,15 @@ int pick_nt(int Npad) {
   return 16;
 }
 
-template <int EPI, int NB>
+template <int EPI, int NB, bool ACC = false>
 static int launch_k2n(unsigned grid, size_t smem, cudaStream_t st, const CUtensorMap& mx, const CUtensorMap& mw,
                       const float* bias, float* y, const KfGeom& G, const float* elu_h, float* dbias, double* sums) {
   static bool attr_set = false;
   if (!attr_set) {
-    SSR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_k2n_kernel<EPI, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SSR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_k2n_kernel<EPI, NB, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  conv3d_tc_k2n_kernel<EPI, NB><<<grid, 416, smem, st>>>(mx, mw, bias, y, G, elu_h, dbias, sums);   // TMA + 4 MMA + 8 epilogue warps
+  conv3d_tc_k2n_kernel<EPI, NB, ACC><<<grid, 416, smem, st>>>(mx, mw, bias, y, G, elu_h, dbias, sums);   // TMA + 4 MMA + 8 epilogue warps
   return SSR_OK;
 }
 
@@ -2344,6 +2355,8 @@ static int conv3d_fwd_tc_k2n_impl(const float* x, int Ctot, int c0, int C, const
   else if (epi == 1) rc = launch_k2n<1, 4>(grid, smem, st, mx, mw, bias, y, G, elu_h, dbias, sums);
   else if (epi == 2 && Cout == 24) rc = launch_k2n<2, 3>(grid, smem, st, mx, mw, bias, y, G, elu_h, dbias, sums);
   else if (epi == 2) rc = launch_k2n<2, 4>(grid, smem, st, mx, mw, bias, y, G, elu_h, dbias, sums);
+  else if (accumulate && Cout == 24 && !getenv("SSR_K2N_NO_ACC_PREFETCH")) rc = launch_k2n<0, 3, true>(grid, smem, st, mx, mw, bias, y, G, nullptr, nullptr, nullptr);
+  else if (accumulate && Cout == 32 && !getenv("SSR_K2N_NO_ACC_PREFETCH")) rc = launch_k2n<0, 4, true>(grid, smem, st, mx, mw, bias, y, G, nullptr, nullptr, nullptr);
   else rc = launch_k2n<0, 4>(grid, smem, st, mx, mw, bias, y, G, nullptr, nullptr, nullptr);
   if (rc) return rc;
   SSR_COUNT_LAUNCH();
