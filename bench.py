@@ -271,11 +271,14 @@ def main():
     peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained; TF32 runs at half the bf16 rate)' if peaks else \
         'fallback 1590 TF/s bf16 (B200_PROFILING.md)'
     # dominant kernel = the tensor-core convolution kind with the largest share of the step (each kind is one kernel
-    # family: wgrad_tc -> wgrad_tc_k2n_kernel, fwd_tc / dgrad_tc -> conv3d_tc_kernel + conv3d_tc_k2n_kernel)
+    # family: wgrad_tc -> wgrad_tc_persistent_kernel, fwd_tc / dgrad_tc -> conv3d_tc_kernel + conv3d_tc_k2n_kernel +
+    # conv3d_tc_up_kernel).  FLOPs are ALGORITHMIC (2*27*Cin*Cout*voxels of the reference's layer): the
+    # parity path of the decoder convolutions executes 8 instead of 27 taps on the upsampled channels.
     tc = {k: v for k, v in agg.items() if k.endswith('_tc')}
     dom = max(tc, key=lambda k: tc[k][0]) if tc else None
-    names = {'wgrad_tc': 'wgrad_tc_k2n_kernel', 'fwd_tc': 'conv3d_tc_kernel / conv3d_tc_k2n_kernel (forward)',
-             'dgrad_tc': 'conv3d_tc_kernel / conv3d_tc_k2n_kernel (data gradient)'}
+    names = {'wgrad_tc': 'wgrad_tc_persistent_kernel (<0> plain, <1> parity classes of the decoder convolutions)',
+             'fwd_tc': 'conv3d_tc_kernel / conv3d_tc_k2n_kernel / conv3d_tc_up_kernel<1> (forward)',
+             'dgrad_tc': 'conv3d_tc_kernel / conv3d_tc_k2n_kernel / conv3d_tc_up_kernel<2> (data gradient)'}
     achieved = tc[dom][1] / (tc[dom][0] * 1e-3) / 1e12 if dom else 0.       # algorithmic 2*27*Cin*Cout*voxels per launch
     tc_ms = sum(v[0] for v in tc.values())
     tc_fl = sum(v[1] for v in tc.values())
