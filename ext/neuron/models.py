@@ -7,6 +7,78 @@ of SynthSR's path and are not provided."""
 import numpy as np
 
 
+class DynamicUnetModel:
+    """`unet(input_shape=[None, None, None, C], ...)` of the inference scripts (scripts/predict_command_line.py:66-77):
+    the spatial shape is only known per scan, so the engine (activation buffers, TMA descriptors) is built -- and cached --
+    per input shape at predict() time; the weights live here by Keras layer name."""
+
+    def __init__(self, cin, kwargs, name='unet'):
+        self.cin, self.kwargs, self.name = int(cin), kwargs, name
+        self.inputs = ['%s_input' % name]
+        self.output_shape = [None, None, None, None, kwargs['nb_labels']]
+        self._sd = None
+        self._nets = {}
+
+    @property
+    def layer_names(self):
+        from synthsr_b200.unet import layer_specs
+        k = self.kwargs
+        return [n for n, *_ in layer_specs(self.cin, k['nb_features'], k['nb_levels'], k['feat_mult'],
+                                           k['nb_conv_per_level'], k['nb_labels'])]
+
+    def _net(self, dims, batch):
+        from synthsr_b200.unet import UNet3D
+        key = (tuple(dims), batch)
+        if key not in self._nets:
+            self._nets.clear()                                # one shape resident at a time (full-size scans are large)
+            net = UNet3D(list(dims) + [self.cin], batchsize=batch, seed=0, **self.kwargs)
+            if self._sd is not None:
+                net.load_state_dict(self._sd, strict=False)
+            self._nets[key] = net
+        return self._nets[key]
+
+    def predict(self, image):
+        """image [B,X,Y,Z,C] numpy (X, Y, Z multiples of 2**(nb_levels-1)) -> prediction, inference-mode BatchNorm."""
+        import torch
+        image = np.ascontiguousarray(image, dtype=np.float32)
+        assert image.ndim == 5 and image.shape[-1] == self.cin, image.shape
+        net = self._net(image.shape[1:4], image.shape[0])
+        return net.predict(torch.as_tensor(image).cuda()).cpu().numpy()
+
+    def get_weights(self):
+        return dict(self._sd or {})
+
+    def set_weights(self, sd):
+        self._sd = dict(self._sd or {}, **{k: np.asarray(v, dtype=np.float32) for k, v in sd.items()})
+        for net in self._nets.values():
+            net.load_state_dict(self._sd, strict=False)
+
+    def load_weights(self, path, by_name=True):
+        if str(path).endswith('.h5'):
+            from synthsr_b200 import h5lite
+            sd, _ = h5lite.load_keras_weights(path)
+        else:
+            sd = {k: v for k, v in dict(np.load(path)).items() if not k.startswith('optimizer/')}
+        from synthsr_b200.unet import layer_specs
+        k = self.kwargs
+        for name, kind, ci, co in layer_specs(self.cin, k['nb_features'], k['nb_levels'], k['feat_mult'],
+                                              k['nb_conv_per_level'], k['nb_labels']):
+            if kind != 'bn' and name + '/kernel' in sd:
+                ks = k['conv_size'] if kind == 'conv' else 1
+                if tuple(sd[name + '/kernel'].shape) != (ks, ks, ks, ci, co):
+                    raise ValueError('Layer weight shape %s of %s not compatible with provided weight shape %s'
+                                     % ((ks, ks, ks, ci, co), name, tuple(sd[name + '/kernel'].shape)))
+        self.set_weights(sd)
+
+    def save_weights(self, path):
+        from synthsr_b200 import h5lite
+        from synthsr_b200.unet import keras_layer_order
+        if str(path).endswith('.h5'):
+            h5lite.save_keras_weights(path, self._sd or {}, keras_layer_order(self.kwargs['nb_levels']))
+        else:
+            np.savez(path, **(self._sd or {}))
+
+
 class UnetModel:
     def __init__(self, net, input_model=None, name='unet'):
         self.net, self.input_model, self.name = net, input_model, name
@@ -80,6 +152,10 @@ def unet(nb_features, input_shape, nb_levels, conv_size, nb_labels, name='unet',
         raise NotImplementedError('unet(): options outside the SynthSR training configuration: %s' % ', '.join(unsupported))
     if input_model is not None:
         batchsize = getattr(input_model, 'batchsize', batchsize)
+    if any(d is None for d in list(input_shape)[:3]):         # inference scripts: spatial shape known per scan only
+        return DynamicUnetModel(input_shape[3], dict(nb_features=nb_features, nb_levels=nb_levels, conv_size=conv_size,
+                                                     nb_labels=nb_labels, feat_mult=feat_mult,
+                                                     nb_conv_per_level=nb_conv_per_level, conv_impl=conv_impl), name)
     net = UNet3D(list(input_shape), nb_features=nb_features, nb_levels=nb_levels, conv_size=conv_size,
                  nb_labels=nb_labels, feat_mult=feat_mult, nb_conv_per_level=nb_conv_per_level, batchsize=batchsize,
                  conv_impl=conv_impl, seed=seed)
