@@ -107,6 +107,14 @@ long long ssr_conv3d_packed_size(int Cin1, int Cin2, int Cout, int mode);
 int ssr_conv3d_pack_weights_batch(const long long* jobs, int njobs, void* stream);
 int ssr_conv3d_fwd_tc(const float* x1, int C1, const float* x2, int C2, const float* wp, const float* bias, float* y,
                       int B, int d0, int d1, int d2, int Cout, int act, void* stream);
+/* forward that also accumulates the BatchNorm sums of its output in the epilogue (sums: 2*Cout doubles, zeroed here: sum |
+ * sum of squares; finish with ssr_bn_finalize) -- KL.BatchNormalization statistics (models.py:349-351, 475-477) */
+int ssr_conv3d_fwd_tc_stats(const float* x1, int C1, const float* x2, int C2, const float* wp, const float* bias, float* y,
+                            double* sums, int B, int d0, int d1, int d2, int Cout, int act, void* stream);
+/* data gradient (wp: pack mode 1) fused with the ELU backward of the layer below: dx = conv(dy, wp) * elu'(h),
+ * dbias[c] += sum_v dx[v][c]; h = that layer's forward output, Cout = channels of dx */
+int ssr_conv3d_dgrad_tc_elu(const float* dy, int C, const float* wp, const float* h, float* dx, float* dbias, int B, int d0,
+                            int d1, int d2, int Cout, void* stream);
 /* same, added to the partial result already in y before bias + activation */
 int ssr_conv3d_fwd_tc_acc(const float* x1, int C1, const float* x2, int C2, const float* wp, const float* bias, float* y,
                           int B, int d0, int d1, int d2, int Cout, int act, void* stream);

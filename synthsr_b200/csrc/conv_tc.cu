@@ -255,13 +255,48 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Column sums over the 32 lanes of a warp of 16 values per lane in 16 shuffles ("transposed" butterfly: every exchange
+// halves the number of values a lane keeps): returns the sum of v[ch] over all lanes with
+// ch = 8 * bit4(lane) + 4 * bit3 + 2 * bit2 + bit1 (both lanes of a pair hold it).
+__device__ __forceinline__ float colsum16_transpose(const float (&v)[16], int lane) {
+  float a[8], b[4], c[2];
+  bool hi = (lane & 16) != 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float recv = __shfl_xor_sync(0xffffffffu, hi ? v[i] : v[i + 8], 16);
+    a[i] = (hi ? v[i + 8] : v[i]) + recv;
+  }
+  hi = (lane & 8) != 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float recv = __shfl_xor_sync(0xffffffffu, hi ? a[i] : a[i + 4], 8);
+    b[i] = (hi ? a[i + 4] : a[i]) + recv;
+  }
+  hi = (lane & 4) != 0;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float recv = __shfl_xor_sync(0xffffffffu, hi ? b[i] : b[i + 2], 4);
+    c[i] = (hi ? b[i + 2] : b[i]) + recv;
+  }
+  hi = (lane & 2) != 0;
+  const float recv = __shfl_xor_sync(0xffffffffu, hi ? c[0] : c[1], 2);
+  float d = (hi ? c[1] : c[0]) + recv;
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  return d;
+}
+
 // Persistent: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The TMEM holds TWO accumulator sets,
 // so the epilogue of tile i (TMEM -> registers -> bias/ELU -> global) overlaps the MMAs of tile i+1, and the TMA
 // producer runs ahead across tile boundaries (no pipeline refill, no per-tile setup).
+// EPI (epilogue fusions for the levels below full resolution, the counterpart of the k2n kernel's):
+//   1 (data gradient): out *= elu'(elu_h) and dbias[c] += sum_v out[v][c]      -- replaces elu_bwd_kernel
+//   2 (forward):       sums[c] += sum_v out, sums[Cout + c] += sum_v out^2    -- replaces colsum2_vec_kernel<0>
+// Column sums: transposed warp butterfly per 16-channel block -> shared-memory floats per CTA -> one atomic per channel.
+template <int EPI>
 __global__ void __launch_bounds__(288, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_x2,
                  const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias, float* __restrict__ y,
-                 const TcGeom G) {
+                 const TcGeom G, const float* __restrict__ elu_h, float* __restrict__ dbias, double* __restrict__ sums) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [A stages][B stages][barriers][bias]
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -277,6 +312,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
   uint64_t* accEmpty = accFull + 2;                // [2]
   uint32_t* tmem_slot = (uint32_t*)(accEmpty + 2);
   float* sbias = (float*)(bars + 32);              // Npad floats (<= 576), 16-byte aligned, zero padded
+  float* sred = sbias + 640;                       // EPI: 2 x Npad per-CTA channel sums (host reserves the space)
+  if (EPI != 0)
+    for (int i = threadIdx.x; i < 2 * G.Npad; i += blockDim.x) sred[i] = 0.f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* dbg = (g_dbg && (blockIdx.x % 2) == 0 && blockIdx.x / 2 < 74) ? g_dbg + (blockIdx.x / 2) * 16 : nullptr;
@@ -481,6 +519,38 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
               o[e] = o[e] > 0.f ? o[e] : neg;
             }
           }
+          if constexpr (EPI != 0) {
+            const int nv = G.Cout - (n0 + cb);
+            if constexpr (EPI == 1) {                  // elu'(pre) from the ELU output h: 1 where h > 0, h + 1 elsewhere
+              const float* hrow = elu_h + (orow - y);
+              if (vox_ok) {
+                if (nv >= 16 && vec_ok) {
+#pragma unroll
+                  for (int e = 0; e < 16; e += 4) {
+                    const float4 hv = __ldg(reinterpret_cast<const float4*>(hrow + cb + e));
+                    o[e] *= hv.x > 0.f ? 1.f : hv.x + 1.f; o[e + 1] *= hv.y > 0.f ? 1.f : hv.y + 1.f;
+                    o[e + 2] *= hv.z > 0.f ? 1.f : hv.z + 1.f; o[e + 3] *= hv.w > 0.f ? 1.f : hv.w + 1.f;
+                  }
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 16; ++e)
+                    if (e < nv) { const float hv = __ldg(hrow + cb + e); o[e] *= hv > 0.f ? 1.f : hv + 1.f; }
+                }
+              }
+            }
+            float sv[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) sv[e] = (vox_ok && e < nv) ? o[e] : 0.f;
+            const int chn = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            const float cs = colsum16_transpose(sv, lane);
+            if (!(lane & 1)) atomicAdd(sred + n0 + cb + chn, cs);
+            if constexpr (EPI == 2) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) sv[e] *= sv[e];
+              const float cq = colsum16_transpose(sv, lane);
+              if (!(lane & 1)) atomicAdd(sred + G.Npad + n0 + cb + chn, cq);
+            }
+          }
           if (!vox_ok) continue;
           const int nvalid = G.Cout - (n0 + cb);       // channels of this 16-block that exist
           if (nvalid >= 16 && vec_ok) {
@@ -512,6 +582,15 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)G.tmem_cols);
   if (threadIdx.x == 0) DBG_STAMP(7);
+  if constexpr (EPI == 1) {
+    for (int c = threadIdx.x; c < G.Cout; c += blockDim.x) atomicAdd(dbias + c, sred[c]);
+  }
+  if constexpr (EPI == 2) {
+    for (int c = threadIdx.x; c < G.Cout; c += blockDim.x) {
+      atomicAdd(sums + c, (double)sred[c]);
+      atomicAdd(sums + G.Cout + c, (double)sred[G.Npad + c]);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -2073,7 +2152,8 @@ int ssr_conv3d_pack_weights(const float* w, float* wp, int Cin1, int Cin2, int C
 // y[B,D0,D1,D2,Cout] = act(conv3x3x3([x1,x2], wp) + bias) ; wp from ssr_conv3d_pack_weights.
 // Used for the data gradient too (x1 = dy, wp packed with mode 1, Cout = layer's Cin, bias NULL, act 0).
 static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, const float* wp, const float* bias, float* y,
-                              int B, int D0, int D1, int D2, int Cout, int act, int accumulate, void* stream) {
+                              int B, int D0, int D1, int D2, int Cout, int act, int accumulate, void* stream, int epi = 0,
+                              const float* elu_h = nullptr, float* dbias = nullptr, double* sums = nullptr) {
   SSR_CHECK_ARG(x1 && wp && y && B > 0 && D0 > 0 && D1 > 0 && D2 > 0 && Cout > 0, "pointers/shape");
   SSR_CHECK_ARG(C1 > 0 && C1 % 4 == 0 && C2 >= 0 && C2 % 4 == 0 && (C2 == 0 || x2), "channel counts must be multiples of 4");
   SSR_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0, "channel counts must be multiples of 8 (TF32 K-step)");
@@ -2127,11 +2207,14 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
   G.nchunks = nch;
   G.n2tiles = (D2 + TM2 - 1) / TM2; G.n1tiles = (D1 + TM1 - 1) / TM1; G.n0tiles = (D0 + G.TZ - 1) / G.TZ;
   const int bgroup = G.KG * 3 * G.NT * 128;
-  const int budget = 227 * 1024 - 1024 /*align slack*/ - 2816 /*barriers + bias*/ - SB * bgroup;
+  const int tail = 2816 /*barriers + bias*/ + (epi ? 2 * 4 * 576 : 0) /*per-CTA channel sums of the fused epilogues*/;
+  const int budget = 227 * 1024 - 1024 /*align slack*/ - tail - SB * bgroup;
   int sa = budget / SLAB_BYTES; if (sa > 8) sa = 8;
   SSR_CHECK_ARG(sa >= 2, "shared memory budget");
   G.SA = sa;
-  const size_t smem = 1024 + (size_t)G.SA * SLAB_BYTES + (size_t)SB * bgroup + 2816;
+  const size_t smem = 1024 + (size_t)G.SA * SLAB_BYTES + (size_t)SB * bgroup + tail;
+  SSR_CHECK_ARG(epi == 0 || (epi == 1 ? (elu_h && dbias) : (epi == 2 && sums)), "fused epilogue buffers");
+  SSR_CHECK_ARG(epi == 0 || !accumulate, "fused epilogues do not combine with accumulate");
 
   CUtensorMap m1, m2, mw;
   int rc = make_map_act(&m1, x1, C1, B, D0, D1, D2);
@@ -2142,7 +2225,9 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
 
   static bool attr_set = false;
   if (!attr_set) {
-    SSR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SSR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SSR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SSR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const long long ntiles = (long long)B * G.n0tiles * G.n1tiles * G.n2tiles * G.nNtiles;
@@ -2154,7 +2239,10 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
     SSR_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const unsigned grid = (unsigned)(ntiles < num_sms ? ntiles : num_sms);       // persistent: one CTA per SM
-  conv3d_tc_kernel<<<grid, 32 * (5 + G.TZ), smem, (cudaStream_t)stream>>>(m1, m2, mw, bias, y, G);   // TMA + TZ MMA + 4 epilogue warps
+  // TMA + TZ MMA + 4 epilogue warps
+  if (epi == 1) conv3d_tc_kernel<1><<<grid, 32 * (5 + G.TZ), smem, (cudaStream_t)stream>>>(m1, m2, mw, bias, y, G, elu_h, dbias, sums);
+  else if (epi == 2) conv3d_tc_kernel<2><<<grid, 32 * (5 + G.TZ), smem, (cudaStream_t)stream>>>(m1, m2, mw, bias, y, G, elu_h, dbias, sums);
+  else conv3d_tc_kernel<0><<<grid, 32 * (5 + G.TZ), smem, (cudaStream_t)stream>>>(m1, m2, mw, bias, y, G, nullptr, nullptr, nullptr);
   SSR_COUNT_LAUNCH();
   SSR_CHECK_LAUNCH();
   return SSR_OK;
@@ -2169,6 +2257,20 @@ int ssr_conv3d_fwd_tc(const float* x1, int C1, const float* x2, int C2, const fl
 int ssr_conv3d_fwd_tc_acc(const float* x1, int C1, const float* x2, int C2, const float* wp, const float* bias, float* y,
                           int B, int D0, int D1, int D2, int Cout, int act, void* stream) {
   return conv3d_fwd_tc_impl(x1, C1, x2, C2, wp, bias, y, B, D0, D1, D2, Cout, act, 1, stream);
+}
+
+// forward + BatchNorm sums of the output in the epilogue (sums: 2*Cout doubles, zeroed here; finish with ssr_bn_finalize)
+int ssr_conv3d_fwd_tc_stats(const float* x1, int C1, const float* x2, int C2, const float* wp, const float* bias, float* y,
+                            double* sums, int B, int D0, int D1, int D2, int Cout, int act, void* stream) {
+  SSR_CHECK_ARG(sums, "sums");
+  SSR_CHECK_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)Cout * sizeof(double), (cudaStream_t)stream));
+  return conv3d_fwd_tc_impl(x1, C1, x2, C2, wp, bias, y, B, D0, D1, D2, Cout, act, 0, stream, 2, nullptr, nullptr, sums);
+}
+// data gradient (wp packed with mode 1) fused with the ELU backward of the layer below: dx = conv(dy, wp) * elu'(h),
+// dbias[c] += sum_v dx[v][c]; Cout = channels of dx / h
+int ssr_conv3d_dgrad_tc_elu(const float* dy, int C, const float* wp, const float* h, float* dx, float* dbias, int B, int D0,
+                            int D1, int D2, int Cout, void* stream) {
+  return conv3d_fwd_tc_impl(dy, C, nullptr, 0, wp, nullptr, dx, B, D0, D1, D2, Cout, 0, 0, stream, 1, h, dbias, nullptr);
 }
 
 // ---- convolution over a 2x nearest-upsampled tensor from its LOW-resolution source (conv3d_tc_up_kernel) ------------

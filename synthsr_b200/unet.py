@@ -86,6 +86,7 @@ class UNet3D:
         # weight gradient of those layers from the low-resolution tensor too (the upsampled tensor is never materialised)
         self.up_wgrad = self.up_parity and os.environ.get('SSR_NO_UP_WGRAD') is None
         self.epi_fusion = self.fwd_k2n and os.environ.get('SSR_NO_EPI_FUSION') is None
+        self.epi_fusion_generic = os.environ.get('SSR_NO_EPI_FUSION_GENERIC') is None   # same for the levels below
         self._side, self._side_busy, self._hp, self._pack_event = None, False, None, None
         self.device = torch.device(device)
         for d in self.dims:
@@ -231,8 +232,15 @@ class UNet3D:
         e1.record()
         self.prof.append((kind, 2. * self.k ** 3 * cin * cout * self.nvox[l], e0, e1))
 
+    def _k2n_ok(self, cin, cout):
+        return self.fwd_k2n and cin % 8 == 0 and cin <= 32 and cout in (24, 32)
+
     def _k2n_epi_ok(self, cin, cout):
-        return (self.conv_impl == 'tc' and self.epi_fusion and cin % 8 == 0 and cin <= 32 and cout in (24, 32))
+        """BN sums / ELU backward + bias gradient inside the convolution epilogue: k2n kernel for the 24 / 32-channel
+        layers, generic kernel (conv3d_tc_kernel<EPI>) for the others."""
+        if not (self.conv_impl == 'tc' and self.epi_fusion and cin % 8 == 0 and cout % 8 == 0):
+            return False
+        return self._k2n_ok(cin, cout) or (self.epi_fusion_generic and not (cin <= 32 and cout <= 32))
 
     def _conv_fwd(self, name, x1, c1, x2, c2, y, l, cout, act=1, stats_sums=None):
         """stats_sums (2*cout doubles): the convolution also accumulates the BatchNorm sums of its output in its epilogue
@@ -244,10 +252,14 @@ class UNet3D:
     def _conv_fwd_impl(self, tc, name, x1, c1, x2, c2, y, l, cout, act, stats_sums=None):
         st = stream_ptr()
         d = self.ldims[l]
-        if stats_sums is not None:
+        if stats_sums is not None and self._k2n_ok(c1, cout):
             assert tc and c2 == 0
             lib.ssr_conv3d_fwd_tc_k2n_stats(x1, c1, self._packed_w(name, 2, c1, 0, cout), self.p[name + '/bias'], y,
                                             stats_sums, self.B, *d, cout, act, st)
+        elif stats_sums is not None:
+            assert tc
+            lib.ssr_conv3d_fwd_tc_stats(x1, c1, x2, c2, self._packed_w(name, 0, c1, c2, cout), self.p[name + '/bias'], y,
+                                        stats_sums, self.B, *d, cout, act, st)
         elif tc and self.fwd_k2n and c2 == 0 and c1 <= 32 and cout <= 32:
             # full-resolution 24-channel layers: d2 taps in the MMA N dimension (conv3d_tc_k2n_kernel)
             lib.ssr_conv3d_fwd_tc_k2n(x1, c1, self._packed_w(name, 2, c1, 0, cout), self.p[name + '/bias'], y,
@@ -311,10 +323,14 @@ class UNet3D:
     def _conv_dgrad_impl(self, tc, name, dy, dx, l, cin, cout, elu_h=None, dbias=None):
         st = stream_ptr()
         d = self.ldims[l]
-        if elu_h is not None:
+        if elu_h is not None and self._k2n_ok(cout, cin):
             assert tc
             lib.ssr_conv3d_dgrad_tc_k2n_elu(dy, cout, self._packed_w(name, 3, cin, 0, cout), elu_h, dx, dbias, self.B,
                                             *d, cin, st)
+        elif elu_h is not None:
+            assert tc
+            lib.ssr_conv3d_dgrad_tc_elu(dy, cout, self._packed_w(name, 1, cin, 0, cout), elu_h, dx, dbias, self.B, *d, cin,
+                                        st)
         elif tc and self.fwd_k2n and cin <= 32 and cout <= 32:
             lib.ssr_conv3d_fwd_tc_k2n(dy, cout, self._packed_w(name, 3, cin, 0, cout), None, dx, self.B, *d, cin, 0, st)
         elif tc:

@@ -410,9 +410,13 @@ def test_tc_k2n_fused_epilogues_match_float64():
 
 
 def test_tc_step_fused_epilogues_equal_separate_kernels():
-    """one training step with the fused k2n epilogues and the fused MaxPool+BN backward against the same step with the
-    separate BN-statistics / ELU-backward / unpooling kernels (identical convolution arithmetic; only the reduction order of
-    the sums differs)."""
+    """one training step with the fused convolution epilogues (k2n and generic kernels) and the fused MaxPool+BN backward
+    against the same step with the separate BN-statistics / ELU-backward / unpooling kernels.  The convolution arithmetic is
+    identical; only the reduction order of the sums differs (last-bit differences of the BN statistics), but the TF32
+    rounding of the activations on their way into the next convolution turns last-bit differences into occasional 2^-11
+    flips, so the two steps agree at TF32 noise level, not to fp32 round-off (the kernels themselves are checked tightly
+    in test_tc_k2n_fused_epilogues_match_float64 / test_tc_generic_fused_epilogues_match_float64).  L2 loss: its gradient
+    is continuous in the prediction (the L1 sign is not)."""
     from synthsr_b200.unet import UNet3D
     dims, rng = [32, 48, 32], np.random.default_rng(11)
     image = torch.from_numpy(rng.uniform(0, 1, size=(1, *dims, 1)).astype(np.float32)).cuda()
@@ -420,17 +424,17 @@ def test_tc_step_fused_epilogues_equal_separate_kernels():
     out = []
     for fused in (True, False):
         net = UNet3D(dims + [1], nb_levels=3, batchsize=1, conv_impl='tc', seed=3)
-        assert net.epi_fusion, 'fused epilogues are expected to be the default'
+        assert net.epi_fusion and net.epi_fusion_generic, 'fused epilogues are expected to be the default'
         net.epi_fusion = net.pool_bn_fusion = fused
-        loss = net.loss_and_grad(image, target)
+        loss = net.loss_and_grad(image, target, metric='l2')
         torch.cuda.synchronize()
         out.append((loss.item(), net.grads.clone(), net.pred.clone(), {k: v.clone() for k, v in net.moving.items()}))
     (l1, g1, p1, m1), (l2, g2, p2, m2) = out
-    assert abs(l1 - l2) <= 1e-6 * abs(l2)
-    assert (p1 - p2).abs().max().item() <= 1e-5 * p2.abs().max().item()
-    assert (g1 - g2).norm().item() <= 1e-4 * g2.norm().item()
+    assert abs(l1 - l2) <= 1e-4 * abs(l2)
+    assert (p1 - p2).norm().item() <= 1e-3 * p2.norm().item()
+    assert (g1 - g2).norm().item() <= 5e-3 * g2.norm().item()
     for k in m1:
-        assert torch.allclose(m1[k], m2[k], rtol=1e-5, atol=1e-7), k
+        assert torch.allclose(m1[k], m2[k], rtol=1e-4, atol=1e-6), k
 
 
 def test_pool_bn_bwd_equals_maxpool_bwd_then_bn_bwd():
@@ -640,3 +644,56 @@ def test_tc_up_parity_weight_gradient_matches_float64():
         for nm, sl in (('skip', slice(0, cs)), ('up', slice(cs, cs + cu))):
             err = (got[:, sl] - ref[:, sl]).abs().max().item() / ref[:, sl].abs().max().item()
             assert err < 3e-5, (nm, dl, cs, cu, co, err)
+
+
+def test_tc_generic_fused_epilogues_match_float64():
+    """conv3d_tc_kernel<EPI>: forward + BatchNorm sums and data gradient x elu'(h) + bias-gradient column sums (transposed
+    warp butterfly -> shared-memory partials -> atomics) against float64 on identically rounded operands; ragged sizes,
+    channel counts that are not multiples of 16, several N tiles."""
+    from synthsr_b200._lib import lib, stream_ptr
+    rng = np.random.default_rng(8)
+    for (d, cin, co) in [([16, 16, 16], 48, 48), ([9, 11, 30], 96, 96), ([21, 8, 14], 40, 72), ([5, 19, 17], 192, 384),
+                         ([40, 24, 29], 48, 48)]:
+        nv = int(np.prod(d))
+        x = torch.from_numpy(rng.normal(size=(nv, cin)).astype(np.float32)).cuda()
+        w = torch.from_numpy((rng.normal(size=(3, 3, 3, cin, co)) / np.sqrt(27 * cin)).astype(np.float32)).cuda()
+        b = torch.from_numpy(rng.normal(size=co).astype(np.float32)).cuda()
+        st = stream_ptr()
+        wr = _rna_tf32(w).double().cpu().permute(4, 3, 0, 1, 2)
+        y = torch.full((nv, co), float('nan'), dtype=torch.float32, device='cuda')
+        sums = torch.full((2 * co,), 123., dtype=torch.float64, device='cuda')
+        wp = torch.empty(lib.ssr_conv3d_packed_size(cin, 0, co, 0), dtype=torch.float32, device='cuda')
+        lib.ssr_conv3d_pack_weights(w, wp, cin, 0, co, 0, st)
+        lib.ssr_conv3d_fwd_tc_stats(x, cin, None, 0, wp, b, y, sums, 1, *d, co, 1, st)
+        torch.cuda.synchronize()
+        xr = _rne_tf32(x).double().cpu().view(1, *d, cin).permute(0, 4, 1, 2, 3)
+        y64 = torch.nn.functional.elu(torch.nn.functional.conv3d(xr, wr, b.double().cpu(), padding=1))
+        y64 = y64.permute(0, 2, 3, 4, 1).reshape(nv, co)
+        assert not torch.isnan(y).any(), ('fwd nan', d, cin, co)
+        err = (y.double().cpu() - y64).abs().max().item() / y64.abs().max().item()
+        assert err < 2e-5, ('fwd', d, cin, co, err)
+        yd = y.double().cpu()
+        s_ref = torch.cat([yd.sum(0), (yd * yd).sum(0)])
+        mag = torch.cat([yd.abs().sum(0), (yd * yd).sum(0)])
+        err = ((sums.cpu() - s_ref).abs() / mag).max().item()
+        assert err < 3e-6, ('stats', d, cin, co, err)
+        # data gradient x elu'(h) + bias gradient
+        dy = torch.from_numpy(rng.normal(size=(nv, co)).astype(np.float32)).cuda()
+        h = torch.nn.functional.elu(torch.from_numpy(rng.normal(size=(nv, cin)).astype(np.float32))).cuda()
+        dx = torch.full((nv, cin), float('nan'), dtype=torch.float32, device='cuda')
+        db = torch.from_numpy(rng.normal(size=cin).astype(np.float32)).cuda()
+        db0 = db.clone()
+        wp1 = torch.empty(lib.ssr_conv3d_packed_size(cin, 0, co, 1), dtype=torch.float32, device='cuda')
+        lib.ssr_conv3d_pack_weights(w, wp1, cin, 0, co, 1, st)
+        lib.ssr_conv3d_dgrad_tc_elu(dy, co, wp1, h, dx, db, 1, *d, cin, st)
+        torch.cuda.synchronize()
+        dyr = _rne_tf32(dy).double().cpu().view(1, *d, co).permute(0, 4, 1, 2, 3)
+        dx64 = torch.nn.functional.conv_transpose3d(dyr, wr, padding=1).permute(0, 2, 3, 4, 1).reshape(nv, cin)
+        hd = h.double().cpu()
+        dx64 = dx64 * torch.where(hd > 0, torch.ones_like(hd), hd + 1.)
+        assert not torch.isnan(dx).any(), ('dgrad nan', d, cin, co)
+        err = (dx.double().cpu() - dx64).abs().max().item() / dx64.abs().max().item()
+        assert err < 5e-5, ('dgrad*elu', d, cin, co, err)      # fp32 accumulation over K = 27 * co up to 10368
+        dxd = dx.double().cpu()
+        err = ((db.double().cpu() - db0.double().cpu() - dxd.sum(0)).abs() / dxd.abs().sum(0)).max().item()
+        assert err < 3e-6, ('dbias', d, cin, co, err)
