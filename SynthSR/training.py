@@ -209,7 +209,12 @@ def train_model(engine, generator, learning_rate, lr_decay, n_epochs, n_steps, m
             real = None
             if len(inputs) > 3:
                 real = torch.as_tensor(np.ascontiguousarray(np.asarray(inputs[3])[..., 0], dtype=np.float32)).cuda()
-            losses.append(engine.train_step(labels, inputs[1], inputs[2], real_image=real))
+            # pipelined like fit_generator's queue: this batch is generated while the previous one is trained on; the
+            # last batch of the epoch is flushed before the loss is reported and the checkpoint written
+            l = engine.train_step_pipelined(labels, inputs[1], inputs[2], real_image=real)
+            if l is not None:
+                losses.append(l.clone())
+        losses.append(engine.flush().clone())
         loss = float(torch.stack([l.reshape(()) for l in losses]).mean().item())
         if not np.isfinite(loss):
             raise FloatingPointError('Loss not finite')              # tf.debugging.check_numerics (metrics_model.py:228)

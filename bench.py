@@ -149,6 +149,8 @@ def main():
     ap.add_argument('--size', type=int, default=SIZE)
     ap.add_argument('--conv-impl', default='tc', choices=['tc', 'ref'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-pipeline', action='store_true',
+                    help='generate and train on the same batch inside one call (no generator / training overlap)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
@@ -158,7 +160,10 @@ def main():
     config = {'workload': '%d^3 single-channel label map -> generator (training() defaults) -> 5-level 24-feature '
                           'U-Net fwd/bwd, L1, Adam; batch 1 per GPU (BASELINE configs[1]/[2])' % args.size,
               'global_batch': args.gpus, 'volume': [args.size] * 3, 'parallelism': 'dp%d' % args.gpus,
-              'l2_policy': 'per-step working set (>4 GB of activations) exceeds the 126 MB L2; no explicit flush'}
+              'l2_policy': 'per-step working set (>4 GB of activations) exceeds the 126 MB L2; no explicit flush',
+              'pipeline': 'generator of batch i+1 overlaps the U-Net step of batch i (one generator pass + one training '
+                          'pass per step, as the reference\'s fit_generator queue)' if '--no-pipeline' not in sys.argv
+                          else 'none (generate, then train, inside each step)'}
 
     if args.impl == 'reference':
         if rank != 0:
@@ -205,6 +210,14 @@ def main():
     lab_dev = [torch.empty_like(dev_maps[0]) for _ in range(2)]
     loss_ev = [torch.cuda.Event() for _ in range(2)]
 
+    pipelined = not args.no_pipeline
+
+    def step(lab, m, s):
+        """one step = one generator pass + one U-Net training pass.  Pipelined (default): the batch of this call is
+        generated on the generator stream while the network trains on the batch of the previous call, like the
+        reference's fit_generator queue; the returned loss is the previous batch's (None on the very first call)."""
+        return eng.train_step_pipelined(lab, m, s) if pipelined else eng.train_step(lab, m, s)
+
     def run_steps(n, host_inputs):
         """host_inputs (e2e): every step copies its label map from pinned host memory and reads a loss back to the host;
         the read-back of step i is consumed while step i+1 is being enqueued (one step of lag, like a logging callback)."""
@@ -212,15 +225,20 @@ def main():
         for i in range(n):
             m, s = draw_gmm(rng, pm, ps, gc)
             if host_inputs:
-                lab = lab_dev[i % 2]
-                lab.copy_(pinned[i % len(pinned)], non_blocking=True)          # H2D of this step's input, in-stream
-                host_loss[i % 2].copy_(eng.train_step(lab, m, s), non_blocking=True)
+                if pipelined:
+                    l = step(pinned[i % len(pinned)], m, s)                        # H2D of this step's input on the generator stream
+                else:
+                    lab = lab_dev[i % 2]
+                    lab.copy_(pinned[i % len(pinned)], non_blocking=True)          # H2D of this step's input, in-stream
+                    l = step(lab, m, s)
+                if l is not None:
+                    host_loss[i % 2].copy_(l, non_blocking=True)
                 loss_ev[i % 2].record()
                 if i > 0:
                     loss_ev[(i - 1) % 2].synchronize()
                     loss = float(host_loss[(i - 1) % 2][0])
             else:
-                loss = eng.train_step(dev_maps[i % len(dev_maps)], m, s)
+                loss = step(dev_maps[i % len(dev_maps)], m, s)
         if host_inputs and n > 0:
             loss_ev[(n - 1) % 2].synchronize()
             loss = float(host_loss[(n - 1) % 2][0])
@@ -248,14 +266,19 @@ def main():
     sampler.join(timeout=2)
     value = world * args.steps / (ms / 1e3)
     run_steps(max(args.warmup, 3), True)              # the host-buffer path gets the same warm-up as the device path
-    sg_before = eng.gen.stage.bytes_moved
+    def staged():
+        return sum(g.stage.bytes_moved for g in (eng._gens or [eng.gen]))
+    sg_before = staged()
     ms_e2e, _ = timed(args.steps, True)
     e2e = world * args.steps / (ms_e2e / 1e3)
-    h2d = maps[0].nbytes + (eng.gen.stage.bytes_moved - sg_before) // max(args.steps, 1)
+    h2d = maps[0].nbytes + (staged() - sg_before) // max(args.steps, 1)
 
     # ---- roofline of the dominant kernel class: live CUDA-event timing of every convolution launch ------------
+    eng.flush()                                  # train the pending batch of the pipelined loop, then profile unpipelined
+    torch.cuda.synchronize()
     eng.net.prof = []
-    run_steps(2, False)
+    for i in range(2):
+        eng.train_step(dev_maps[i % len(dev_maps)], *draw_gmm(rng, pm, ps, gc))
     torch.cuda.synchronize()
     agg = {}
     for kind, fl, a, b in eng.net.prof:

@@ -288,16 +288,27 @@ class GeneratorPlan:
 
 
 class _Staging:
-    """One pinned host buffer + one device buffer: all small per-step inputs go to the GPU in a single async copy."""
+    """Pinned host buffers + one device buffer: all small per-step inputs go to the GPU in a single async copy.
+    The host side is a ring of NBUF pinned buffers, each guarded by the event of its last copy: the host may enqueue
+    steps ahead of the GPU, and must not overwrite a buffer whose copy has not executed yet."""
+    NBUF = 4
 
     def __init__(self, nbytes, device):
-        self.host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        cuda = torch.cuda.is_available()
+        self.hosts = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=cuda) for _ in range(self.NBUF)]
+        self.nps = [h.numpy() for h in self.hosts]
+        self.events = [None] * self.NBUF
+        self.cur = -1
         self.dev = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        self.np = self.host.numpy()
+        self.host, self.np = self.hosts[0], self.nps[0]
         self.off = 0
         self.bytes_moved = 0
 
     def reset(self):
+        self.cur = (self.cur + 1) % self.NBUF
+        if self.events[self.cur] is not None:
+            self.events[self.cur].synchronize()          # the copy that last read this host buffer has completed
+        self.host, self.np = self.hosts[self.cur], self.nps[self.cur]
         self.off = 0
 
     def put(self, arr):
@@ -314,6 +325,10 @@ class _Staging:
         if self.off:
             self.dev[:self.off].copy_(self.host[:self.off], non_blocking=True)
             self.bytes_moved += self.off
+            if self.dev.is_cuda:
+                if self.events[self.cur] is None:
+                    self.events[self.cur] = torch.cuda.Event()
+                self.events[self.cur].record()
 
 
 class SynthGenerator:

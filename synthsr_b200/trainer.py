@@ -33,6 +33,8 @@ class TrainingEngine:
         if self.world > 1:
             n_mv = sum(t.numel() for t in self.net.moving.values())
             self.flat = torch.zeros(self.net.n_params + n_mv + 1, dtype=torch.float32, device=self.device)
+        # pipelined mode (train_step_pipelined): a second generator instance and a generator stream
+        self._gens, self._gen_stream, self._pending, self._pipe_i = None, None, None, 0
 
     def train_step(self, labels, means, stds, real_image=None, draws=None):
         """labels: int32 cuda [B, *labels_shape]; means/stds [B, L, C] host arrays.  Returns the loss (1-element cuda
@@ -48,6 +50,60 @@ class TrainingEngine:
         self.net.adam_step(self.lr, self.lr_decay, grad_scale=scale)
         self.steps += 1
         return loss
+
+    # -----------------------------------------------------------------------------------------------------------------
+    def train_step_pipelined(self, labels, means, stds, real_image=None, draws=None):
+        """Same work per call as train_step -- one generator pass, one U-Net training pass -- but software-pipelined like
+        the reference's `fit_generator` queue (SynthSR/training.py:449-453: the Keras generator runs ahead of the
+        optimiser): the batch passed in is generated on a second stream while the network trains on the batch of the
+        PREVIOUS call, so the latency-bound generator kernels fill the SMs the backward chain leaves idle.  Batches are
+        trained exactly once, in order.  Returns the loss of the previous call's batch (None on the first call);
+        `flush()` trains the last pending batch.  labels may be a pinned host tensor (copied on the generator stream)."""
+        if self._gens is None:
+            self._gens = [self.gen, SynthGenerator(self.plan, self.B, self.device)]
+            self._gen_stream = torch.cuda.Stream(device=self.device)
+            self._gen_done = [torch.cuda.Event(), torch.cuda.Event()]
+            self._lab_dev = [None, None]
+        i = self._pipe_i
+        k = i % 2
+        cur = torch.cuda.current_stream()
+        if draws is None:
+            draws = sample_draws(self.rng, self.plan, self.B)
+        # the generator of this call re-uses the buffers the training pass of call i-1 (batch i-2) read, and may read
+        # tensors the caller just produced on the current stream
+        self._gen_stream.wait_stream(cur)
+        with torch.cuda.stream(self._gen_stream):
+            if not labels.is_cuda:
+                if self._lab_dev[k] is None:
+                    self._lab_dev[k] = torch.empty(labels.shape, dtype=torch.int32, device=self.device)
+                self._lab_dev[k].copy_(labels, non_blocking=True)
+                labels = self._lab_dev[k]
+            self._gens[k].philox_step = max(g.philox_step for g in self._gens)    # one noise-counter sequence for both
+            image, target = self._gens[k].run(labels, means, stds, draws, real_image=real_image, seed=self.seed)
+            self._gen_done[k].record()
+        loss = self._train_pending()
+        self._pending = (image, target, k)
+        self._pipe_i += 1
+        return loss
+
+    def _train_pending(self):
+        if self._pending is None:
+            return None
+        image, target, k = self._pending
+        self._pending = None
+        torch.cuda.current_stream().wait_event(self._gen_done[k])
+        loss = self.net.loss_and_grad(image, target, self.metric, self.residual, self.loss_cropping)
+        scale = 1.
+        if self.world > 1:
+            loss = self._allreduce(loss)
+            scale = 1. / self.world
+        self.net.adam_step(self.lr, self.lr_decay, grad_scale=scale)
+        self.steps += 1
+        return loss
+
+    def flush(self):
+        """train on the batch generated by the last train_step_pipelined call (end of an epoch / of training)."""
+        return self._train_pending()
 
     def _allreduce(self, loss):
         return allreduce_step(self.net.grads, list(self.net.moving.values()), loss, self.flat, self.world)

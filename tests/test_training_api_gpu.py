@@ -103,3 +103,44 @@ def test_two_channel_synthesis_config(dataset):
     from synthsr_b200 import h5lite
     ck, _ = h5lite.load_keras_weights(os.path.join(model_dir, '001.h5'))
     assert ck['unet_conv_downarm_0_0/kernel'].shape == (3, 3, 3, 2, 8)
+
+
+def test_pipelined_steps_train_the_same_batches_in_order():
+    """TrainingEngine.train_step_pipelined (generator of batch i overlaps the U-Net step of batch i-1, second generator
+    instance + generator stream) == train_step called on the same batches: same losses (shifted by one call), same
+    parameters after flush()."""
+    import torch
+    from synthsr_b200.generator import GeneratorPlan
+    from synthsr_b200.synthetic import GEN_CLASSES, GEN_LABELS, phantom_labels, synthetic_priors
+    from synthsr_b200.trainer import TrainingEngine
+    shape = [32, 32, 32]
+    plan = GeneratorPlan(shape, True, 0, GEN_LABELS, None, 1., None, output_div_by_n=8, translation_bounds=3)
+    pm, ps = synthetic_priors(int(GEN_CLASSES.max()) + 1, 1, 0)
+    rng = np.random.default_rng(3)
+    batches = []
+    for i in range(5):
+        lab = torch.from_numpy(phantom_labels(shape, GEN_LABELS, seed=i)[None].astype(np.int32))
+        m = np.clip(rng.normal(pm[0], pm[1]), 0, None)[GEN_CLASSES][None, :, None].astype(np.float32)
+        s = np.clip(rng.normal(ps[0], ps[1]), 0, None)[GEN_CLASSES][None, :, None].astype(np.float32)
+        batches.append((lab, m, s))
+    res = []
+    for pipelined in (False, True):
+        eng = TrainingEngine(plan, batchsize=1, nb_levels=3, nb_features=8, conv_impl='ref', seed=5, lr=1e-3)
+        losses = []
+        for i, (lab, m, s) in enumerate(batches):
+            if pipelined:                      # odd batches arrive as pinned host tensors (copied on the generator stream)
+                l = eng.train_step_pipelined(lab.pin_memory() if i % 2 else lab.cuda(), m, s)
+            else:
+                l = eng.train_step(lab.cuda(), m, s)
+            if l is not None:
+                losses.append(l.item())
+        if pipelined:
+            losses.append(eng.flush().item())
+            assert eng.flush() is None
+        torch.cuda.synchronize()
+        assert eng.steps == len(batches)
+        res.append((losses, eng.net.params.clone()))
+    (l_seq, p_seq), (l_pipe, p_pipe) = res
+    assert len(l_seq) == len(l_pipe) == 5
+    np.testing.assert_allclose(l_pipe, l_seq, rtol=1e-5)
+    assert (p_seq - p_pipe).abs().max().item() <= 1e-5 * p_seq.abs().max().item()
