@@ -14,6 +14,9 @@
 namespace {
 
 __device__ __forceinline__ float elu_f(float a) { return a > 0.f ? a : (expf(a) - 1.f); }
+// branch-free ELU on the SFU exponential (same form as the tensor-core epilogues): the divergent expf of elu_f costs as
+// many instructions as the 27-tap first-layer convolution itself
+__device__ __forceinline__ float elu_fast(float a) { const float neg = __expf(fminf(a, 0.f)) - 1.f; return a > 0.f ? a : neg; }
 // derivative of ELU expressed through its output h = elu(a): 1 if a > 0 (h > 0) else exp(a) = h + 1
 __device__ __forceinline__ float elu_grad_from_out(float h) { return h > 0.f ? 1.f : (h + 1.f); }
 
@@ -140,51 +143,58 @@ conv3d_first_kernel(const float* __restrict__ x, const float* __restrict__ w, co
   }
   __syncthreads();
   const int t2 = threadIdx.x % FT2, t1 = threadIdx.x / FT2;
-  const int i1 = b1 * FT1 + t1, i2 = b2 * FT2 + t2;
-  for (int a0 = 0; a0 < FT0; ++a0) {
+  // two output planes per pass: every weight vector read from shared memory feeds both (the kernel is bound by its
+  // shared-memory loads: 6 x LDS.128 of weights + the input value per 24 FMAs when done plane by plane)
+  for (int a0 = 0; a0 < FT0; a0 += 2) {
     const int i0 = b0 * FT0 + a0;
     if (i0 >= d0) break;                                   // block-uniform
-    float acc[COUT];
+    float acc[2][COUT];
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) acc[co] = sb[co];
+    for (int co = 0; co < COUT; ++co) { acc[0][co] = sb[co]; acc[1][co] = sb[co]; }
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
       for (int bb = 0; bb < 3; ++bb)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float* px = sx + (((a0 + a) * T1 + (t1 + bb)) * T2 + (t2 + c)) * CIN;
+          const float* px0 = sx + (((a0 + a) * T1 + (t1 + bb)) * T2 + (t2 + c)) * CIN;
+          const float* px1 = px0 + T1 * T2 * CIN;          // plane a0 + 1 (inside the halo tile: FT0 is even)
 #pragma unroll
           for (int ci = 0; ci < CIN; ++ci) {
-            const float xv = px[ci];
+            const float xv0 = px0[ci], xv1 = px1[ci];
             const float4* pw = reinterpret_cast<const float4*>(sw + (((a * 3 + bb) * 3 + c) * CIN + ci) * COUT);
 #pragma unroll
             for (int q = 0; q < COUT / 4; ++q) {
               const float4 wv = pw[q];
-              acc[q * 4 + 0] += xv * wv.x; acc[q * 4 + 1] += xv * wv.y;
-              acc[q * 4 + 2] += xv * wv.z; acc[q * 4 + 3] += xv * wv.w;
+              acc[0][q * 4 + 0] += xv0 * wv.x; acc[0][q * 4 + 1] += xv0 * wv.y;
+              acc[0][q * 4 + 2] += xv0 * wv.z; acc[0][q * 4 + 3] += xv0 * wv.w;
+              acc[1][q * 4 + 0] += xv1 * wv.x; acc[1][q * 4 + 1] += xv1 * wv.y;
+              acc[1][q * 4 + 2] += xv1 * wv.z; acc[1][q * 4 + 3] += xv1 * wv.w;
             }
           }
         }
-    // stage the plane's 256 x COUT outputs in shared memory and write them as fully coalesced float4 rows (a
+    // stage each plane's 256 x COUT outputs in shared memory and write them as fully coalesced float4 rows (a
     // thread-per-voxel store pattern touches every 32-byte sector in six separate instructions)
-    __syncthreads();                                       // previous plane's copy-out has finished reading sst
 #pragma unroll
-    for (int q = 0; q < COUT / 4; ++q) {
-      float4 v = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
-      if (act) { v.x = elu_f(v.x); v.y = elu_f(v.y); v.z = elu_f(v.z); v.w = elu_f(v.w); }
-      reinterpret_cast<float4*>(sst + threadIdx.x * COUT)[q] = v;
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < FT1 * FT2 * (COUT / 4); e += 256) {
-      const int vox = e / (COUT / 4), part = e % (COUT / 4);
-      const int j1 = b1 * FT1 + (vox >> 5), j2 = b2 * FT2 + (vox & 31);
-      if (j1 < d1 && j2 < d2)
-        reinterpret_cast<float4*>(y + ((((long long)b * d0 + i0) * d1 + j1) * d2 + j2) * COUT)[part] =
-            reinterpret_cast<const float4*>(sst)[e];
+    for (int pl = 0; pl < 2; ++pl) {
+      if (i0 + pl >= d0) break;                            // block-uniform
+      __syncthreads();                                     // previous plane's copy-out has finished reading sst
+#pragma unroll
+      for (int q = 0; q < COUT / 4; ++q) {
+        float4 v = make_float4(acc[pl][q * 4], acc[pl][q * 4 + 1], acc[pl][q * 4 + 2], acc[pl][q * 4 + 3]);
+        if (act) { v.x = elu_fast(v.x); v.y = elu_fast(v.y); v.z = elu_fast(v.z); v.w = elu_fast(v.w); }
+        reinterpret_cast<float4*>(sst + threadIdx.x * COUT)[q] = v;
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < FT1 * FT2 * (COUT / 4); e += 256) {
+        const int vox = e / (COUT / 4), part = e % (COUT / 4);
+        const int j1 = b1 * FT1 + (vox >> 5), j2 = b2 * FT2 + (vox & 31);
+        if (j1 < d1 && j2 < d2)
+          reinterpret_cast<float4*>(y + ((((long long)b * d0 + i0 + pl) * d1 + j1) * d2 + j2) * COUT)[part] =
+              reinterpret_cast<const float4*>(sst)[e];
+      }
     }
   }
-  (void)i1; (void)i2;
 }
 
 
@@ -302,14 +312,29 @@ wgrad_small_cin_kernel(const float* __restrict__ x, const float* __restrict__ dy
 // 8-channel group of dy and all three k2 taps (24 * CIN accumulators); nine such thread sets stride over the voxels of a
 // plane held in shared memory (x halo tile + dy plane), so every dy value is loaded from shared memory once per
 // 27 threads and feeds 24 FMAs.  Persistent blocks: one atomic flush per block.
+// The dy planes (the only large operand: 96 B per voxel) are double-buffered with cp.async (zero-fill outside the
+// volume): plane p + 1 streams in while plane p is being accumulated, tiles are WT0 = 8 planes deep so the x halo tile is
+// re-loaded once per 8 planes (the first version loaded every plane synchronously and spent ~2/3 of its time waiting).
+constexpr int WT0 = 8;
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, bool valid) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int src_size = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "r"(src_size) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int CIN>
 __global__ void __launch_bounds__(256)
 wgrad_first_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, int B, int d0,
                    int d1, int d2) {
   constexpr int COUT = 24, T1 = FT1 + 2, T2 = FT2 + 2;
-  __shared__ float sx[(FT0 + 2) * T1 * T2 * CIN];
-  __shared__ __align__(16) float sdy[FT1 * FT2 * COUT];
-  __shared__ float sacc[27 * CIN * COUT];
+  extern __shared__ __align__(16) float wf_smem[];
+  float* sdy = wf_smem;                                        // [2][FT1 * FT2 * COUT]
+  float* sx = sdy + 2 * FT1 * FT2 * COUT;                      // [(WT0 + 2) * T1 * T2 * CIN]
+  float* sacc = sx + (WT0 + 2) * T1 * T2 * CIN;                // [27 * CIN * COUT]
   const int tid = threadIdx.x;
   for (int e = tid; e < 27 * CIN * COUT; e += 256) sacc[e] = 0.f;
   const int owner = tid % 27, stream = tid / 27;          // stream 9 (threads 243..255) only helps with the loads
@@ -321,7 +346,7 @@ wgrad_first_kernel(const float* __restrict__ x, const float* __restrict__ dy, fl
     for (int c = 0; c < 3; ++c)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[ci][c][j] = 0.f;
-  const int nb2 = (d2 + FT2 - 1) / FT2, nb1 = (d1 + FT1 - 1) / FT1, nb0 = (d0 + FT0 - 1) / FT0;
+  const int nb2 = (d2 + FT2 - 1) / FT2, nb1 = (d1 + FT1 - 1) / FT1, nb0 = (d0 + WT0 - 1) / WT0;
   const long long ntiles = (long long)B * nb0 * nb1 * nb2;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     long long blk = tile;
@@ -329,9 +354,23 @@ wgrad_first_kernel(const float* __restrict__ x, const float* __restrict__ dy, fl
     const int b1 = (int)(blk % nb1); blk /= nb1;
     const int b0 = (int)(blk % nb0);
     const int b = (int)(blk / nb0);
-    const int o0 = b0 * FT0 - 1, o1 = b1 * FT1 - 1, o2 = b2 * FT2 - 1;
+    const int o0 = b0 * WT0 - 1, o1 = b1 * FT1 - 1, o2 = b2 * FT2 - 1;
+    const int np = min(WT0, d0 - b0 * WT0);                 // planes of this tile
+    auto prefetch_plane = [&](int a0) {                     // dy plane b0 * WT0 + a0 -> buffer a0 & 1
+      float* dst = sdy + (a0 & 1) * (FT1 * FT2 * COUT);
+      const int i0 = b0 * WT0 + a0;
+      for (int e = tid; e < FT1 * FT2 * (COUT / 4); e += 256) {
+        const int vox = e / (COUT / 4), part = e % (COUT / 4);
+        const int i1 = b1 * FT1 + (vox >> 5), i2 = b2 * FT2 + (vox & 31);
+        const bool ok = i1 < d1 && i2 < d2;
+        const float* src = ok ? dy + ((((long long)b * d0 + i0) * d1 + i1) * d2 + i2) * COUT + part * 4 : dy;
+        cp_async16_zfill(dst + e * 4, src, ok);
+      }
+      cp_async_commit();
+    };
     __syncthreads();                                      // previous tile's readers are done with sx / sdy
-    for (int e = tid; e < (FT0 + 2) * T1 * T2; e += 256) {
+    prefetch_plane(0);
+    for (int e = tid; e < (np + 2) * T1 * T2; e += 256) {
       const int c = e % T2, bb = (e / T2) % T1, a = e / (T2 * T1);
       const int i = o0 + a, j = o1 + bb, k = o2 + c;
       const bool ok = i >= 0 && i < d0 && j >= 0 && j < d1 && k >= 0 && k < d2;
@@ -339,24 +378,16 @@ wgrad_first_kernel(const float* __restrict__ x, const float* __restrict__ dy, fl
 #pragma unroll
       for (int ci = 0; ci < CIN; ++ci) sx[e * CIN + ci] = ok ? x[src + ci] : 0.f;
     }
-    for (int a0 = 0; a0 < FT0; ++a0) {
-      const int i0 = b0 * FT0 + a0;
-      if (i0 >= d0) break;                                // block-uniform
-      __syncthreads();                                    // sx visible / previous plane's readers done with sdy
-      for (int e = tid; e < FT1 * FT2 * (COUT / 4); e += 256) {
-        const int vox = e / (COUT / 4), part = e % (COUT / 4);
-        const int i1 = b1 * FT1 + (vox >> 5), i2 = b2 * FT2 + (vox & 31);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i1 < d1 && i2 < d2)
-          v = reinterpret_cast<const float4*>(dy + ((((long long)b * d0 + i0) * d1 + i1) * d2 + i2) * COUT)[part];
-        reinterpret_cast<float4*>(sdy)[e] = v;
-      }
-      __syncthreads();
+    for (int a0 = 0; a0 < np; ++a0) {
+      cp_async_wait<0>();                                 // this thread's part of plane a0 has landed ...
+      __syncthreads();                                    // ... everyone's has; sx visible; plane a0 - 1 fully consumed
+      if (a0 + 1 < np) prefetch_plane(a0 + 1);            // streams in behind the accumulation of plane a0
       if (stream < 9) {
+        const float* pdy = sdy + (a0 & 1) * (FT1 * FT2 * COUT);
         for (int vi = stream; vi < FT1 * FT2; vi += 9) {
           const int t1 = vi >> 5, t2 = vi & 31;
-          const float4 da = reinterpret_cast<const float4*>(sdy + vi * COUT + cg * 8)[0];
-          const float4 db = reinterpret_cast<const float4*>(sdy + vi * COUT + cg * 8)[1];
+          const float4 da = reinterpret_cast<const float4*>(pdy + vi * COUT + cg * 8)[0];
+          const float4 db = reinterpret_cast<const float4*>(pdy + vi * COUT + cg * 8)[1];
           const float* px = sx + (((a0 + k0) * T1 + (t1 + k1)) * T2 + t2) * CIN;
 #pragma unroll
           for (int ci = 0; ci < CIN; ++ci)
@@ -1395,10 +1426,17 @@ int ssr_conv3d_wgrad_ref(const float* x1, int C1, const float* x2, int C2, const
   const long long nvox = (long long)B * d0 * d1 * d2;
   const int Ksmall = k * k * k * C1;
   if (k == 3 && C2 == 0 && C1 <= 2 && Cout == 24 && ((uintptr_t)dy & 15) == 0) {       // first layer of the U-Net
-    const long long ntiles = (long long)B * ((d0 + FT0 - 1) / FT0) * ((d1 + FT1 - 1) / FT1) * ((d2 + FT2 - 1) / FT2);
-    const unsigned nb = (unsigned)(ntiles < 148 * 2 ? ntiles : 148 * 2);
-    if (C1 == 1) wgrad_first_kernel<1><<<nb, 256, 0, st>>>(x1, dy, dw, B, d0, d1, d2);
-    else wgrad_first_kernel<2><<<nb, 256, 0, st>>>(x1, dy, dw, B, d0, d1, d2);
+    const long long ntiles = (long long)B * ((d0 + WT0 - 1) / WT0) * ((d1 + FT1 - 1) / FT1) * ((d2 + FT2 - 1) / FT2);
+    const unsigned nb = (unsigned)(ntiles < 148 * 3 ? ntiles : 148 * 3);
+    const size_t smem = sizeof(float) * (2 * FT1 * FT2 * 24 + (size_t)(WT0 + 2) * (FT1 + 2) * (FT2 + 2) * C1 + 27 * C1 * 24);
+    static bool attr_set = false;
+    if (!attr_set) {
+      SSR_CHECK_CUDA(cudaFuncSetAttribute(wgrad_first_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      SSR_CHECK_CUDA(cudaFuncSetAttribute(wgrad_first_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr_set = true;
+    }
+    if (C1 == 1) wgrad_first_kernel<1><<<nb, 256, smem, st>>>(x1, dy, dw, B, d0, d1, d2);
+    else wgrad_first_kernel<2><<<nb, 256, smem, st>>>(x1, dy, dw, B, d0, d1, d2);
   } else
   if (C2 == 0 && C1 <= 4 && Cout % 4 == 0 && Ksmall * (Cout / 4) <= 384 && nvox >= 4096 &&
       ((uintptr_t)dy & 15) == 0) {
