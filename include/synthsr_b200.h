@@ -195,6 +195,11 @@ int ssr_bn_bwd(const float* dy, const float* x, const float* stats, long long nv
 int ssr_pool_bn_bwd(const float* dp, const float* x, const float* stats, int B, int d0, int d1, int d2, int C,
                     const float* add, int add_stride, int add_off, int elu, float* dx, float* dgamma, float* dbeta,
                     float* dbias, double* sums_scratch, void* stream);
+/* ssr_bn_bwd with the two reductions already in sums2 = [sum dy | sum dy * xhat] (2*C doubles), e.g. from
+ * ssr_head_loss_bnsums: no reduction pass over dy / x */
+int ssr_bn_bwd_sums(const float* dy, const float* x, const float* stats, long long nvox, int C, const float* add,
+                    int add_stride, int add_off, int elu, float* dx, float* dgamma, float* dbeta, float* dbias,
+                    double* sums2, void* stream);
 int ssr_maxpool_bwd(const float* dp, const float* x, const float* stats, int B, int d0, int d1, int d2, int C,
                     float* dy_full, void* stream);
 int ssr_upsample_bwd(const float* du, int du_stride, int du_off, int B, int d0, int d1, int d2, int C, float* dlow,
@@ -209,6 +214,14 @@ int ssr_head_loss(const float* feat, const float* feat_stats, const float* w, co
                   const int* res_idx, const float* target, float* pred, float* dfeat, float* dw, float* db,
                   double* loss, float* gout_scratch, int B, int d0, int d1, int d2, int C, int L, int metric,
                   const int* crop_size, const int* crop_begin, int train, void* stream);
+/* training-mode ssr_head_loss with the BatchNorm folded in (feat_stats required) that also returns the two reductions of
+ * that BatchNorm's backward, sums2 = [sum_v dfeat | sum_v dfeat * xhat] (2*C doubles), obtained algebraically from the head
+ * gradients (dfeat = g w^T): db must be ZERO on entry; xdot_scratch: C*L floats. */
+int ssr_head_loss_bnsums(const float* feat, const float* feat_stats, const float* w, const float* bias, const float* image,
+                         int image_channels, const int* res_idx, const float* target, float* pred, float* dfeat,
+                         float* dw, float* db, double* loss, float* gout_scratch, int B, int d0, int d1, int d2, int C,
+                         int L, int metric, const int* crop_size, const int* crop_begin, float* xdot_scratch,
+                         double* sums2, void* stream);
 /* keras.optimizers.Adam (SynthSR/training.py:444) on one flat parameter buffer. */
 int ssr_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
                   float eps, float grad_scale, void* stream);

@@ -1153,12 +1153,15 @@ __global__ void __launch_bounds__(256)
 head_loss_vec_kernel(const float* __restrict__ feat, const float* __restrict__ feat_stats, const float* __restrict__ w,
                      const float* __restrict__ bias, const float* __restrict__ image, const float* __restrict__ target,
                      float* __restrict__ pred, float* __restrict__ dfeat, float* __restrict__ dw, float* __restrict__ db,
-                     double* __restrict__ loss, HeadParams P) {
+                     double* __restrict__ loss, float* __restrict__ xdot, HeadParams P) {
+  // xdot (optional, with feat_stats): xdot[c][l] += sum_v g[v][l] * xhat[v][c] -- with db it gives the two reductions of
+  // the BatchNorm backward of the folded layer (sum dy, sum dy * xhat for dy = g w^T) without another pass over feat
   __shared__ float sw[4 * 128];
   __shared__ float sdw[4 * 128];
+  __shared__ float sdx[4 * 128];
   __shared__ double sloss[8];
   const int C = P.C, L = P.L, nq = C >> 2;
-  for (int e = threadIdx.x; e < C * L; e += blockDim.x) { sw[e] = w[e]; sdw[e] = 0.f; }   // w[c][l]
+  for (int e = threadIdx.x; e < C * L; e += blockDim.x) { sw[e] = w[e]; sdw[e] = 0.f; sdx[e] = 0.f; }   // w[c][l]
   __syncthreads();
   const int q = threadIdx.x % GS;
   const bool active = q < nq;
@@ -1177,11 +1180,17 @@ head_loss_vec_kernel(const float* __restrict__ feat, const float* __restrict__ f
     fsc = *reinterpret_cast<const float4*>(feat_stats + 2 * C + 4 * q);
     fsh = *reinterpret_cast<const float4*>(feat_stats + 3 * C + 4 * q);
   }
-  float wacc[4][LT];
+  const bool want_x = xdot != nullptr && feat_stats != nullptr;
+  float4 fmean = make_float4(0.f, 0.f, 0.f, 0.f), finv = fmean;
+  if (want_x && active) {
+    fmean = *reinterpret_cast<const float4*>(feat_stats + 4 * q);
+    finv = *reinterpret_cast<const float4*>(feat_stats + C + 4 * q);
+  }
+  float wacc[4][LT], xacc[4][LT];
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int l = 0; l < LT; ++l) wacc[j][l] = 0.f;
+    for (int l = 0; l < LT; ++l) { wacc[j][l] = 0.f; xacc[j][l] = 0.f; }
   const long long nvox = (long long)P.B * P.d0 * P.d1 * P.d2;
   const int gpb = blockDim.x / GS;
   double lloss = 0.0;
@@ -1194,7 +1203,7 @@ head_loss_vec_kernel(const float* __restrict__ feat, const float* __restrict__ f
   const long long niter = (nvox + 2 * vstep - 1) / (2 * vstep);
   long long vbase = (long long)blockIdx.x * gpb + threadIdx.x / GS;
   for (long long it = 0; it < niter; ++it, vbase += 2 * vstep) {
-    float4 f[2];
+    float4 f[2], xh[2];
     float o[2][LT], tg[2][LT], im[2][LT];
     bool vok[2];
 #pragma unroll
@@ -1202,8 +1211,11 @@ head_loss_vec_kernel(const float* __restrict__ feat, const float* __restrict__ f
       const long long v = vbase + u * vstep;
       vok[u] = v < nvox;
       f[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      xh[u] = f[u];
       if (vok[u] && active) {
         f[u] = *reinterpret_cast<const float4*>(feat + v * C + 4 * q);
+        xh[u] = make_float4((f[u].x - fmean.x) * finv.x, (f[u].y - fmean.y) * finv.y, (f[u].z - fmean.z) * finv.z,
+                            (f[u].w - fmean.w) * finv.w);
         f[u].x = f[u].x * fsc.x + fsh.x; f[u].y = f[u].y * fsc.y + fsh.y;
         f[u].z = f[u].z * fsc.z + fsh.z; f[u].w = f[u].w * fsc.w + fsh.w;
       }
@@ -1266,6 +1278,7 @@ head_loss_vec_kernel(const float* __restrict__ feat, const float* __restrict__ f
 #pragma unroll
         for (int l = 0; l < LT; ++l) {
           wacc[0][l] += f[u].x * g[l]; wacc[1][l] += f[u].y * g[l]; wacc[2][l] += f[u].z * g[l]; wacc[3][l] += f[u].w * g[l];
+          xacc[0][l] += xh[u].x * g[l]; xacc[1][l] += xh[u].y * g[l]; xacc[2][l] += xh[u].z * g[l]; xacc[3][l] += xh[u].w * g[l];
         }
       }
     }
@@ -1281,6 +1294,11 @@ head_loss_vec_kernel(const float* __restrict__ feat, const float* __restrict__ f
         float a = wacc[j][l];
         for (int off = GS; off < 32; off <<= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
         if ((threadIdx.x & 31) < GS && active) atomicAdd(&sdw[(4 * q + j) * L + l], a);
+        if (want_x) {                                  // block-uniform
+          float x2 = xacc[j][l];
+          for (int off = GS; off < 32; off <<= 1) x2 += __shfl_xor_sync(0xffffffffu, x2, off);
+          if ((threadIdx.x & 31) < GS && active) atomicAdd(&sdx[(4 * q + j) * L + l], x2);
+        }
       }
   }
   for (int o2 = 16; o2 > 0; o2 >>= 1) {
@@ -1295,7 +1313,10 @@ head_loss_vec_kernel(const float* __restrict__ feat, const float* __restrict__ f
   }
   __syncthreads();
   if (P.train)
-    for (int e = threadIdx.x; e < C * L; e += blockDim.x) atomicAdd(dw + e, sdw[e]);
+    for (int e = threadIdx.x; e < C * L; e += blockDim.x) {
+      atomicAdd(dw + e, sdw[e]);
+      if (want_x) atomicAdd(xdot + e, sdx[e]);
+    }
   if (threadIdx.x == 0) {
     double s2 = 0.0;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s2 += sloss[i];
@@ -1547,17 +1568,19 @@ static int ew_grid(long long n) {       // grid * EW_THREADS must stay a multipl
 }
 
 // dbias (optional): += sum_v dx[v][c]  (the bias gradient of the convolution that produced x)
-int ssr_bn_bwd(const float* dy, const float* x, const float* stats, long long nvox, int C, const float* add,
+static int bn_bwd_impl(const float* dy, const float* x, const float* stats, long long nvox, int C, const float* add,
                int add_stride, int add_off, int elu, float* dx, float* dgamma, float* dbeta, float* dbias,
-               double* sums_scratch, void* stream) {
+               double* sums_scratch, void* stream, int have_sums) {
   SSR_CHECK_ARG(dy && x && stats && dx && sums_scratch && nvox > 0 && C > 0, "args");
   cudaStream_t st = (cudaStream_t)stream;
-  SSR_CHECK_CUDA(cudaMemsetAsync(sums_scratch, 0, 2 * C * sizeof(double), st));
-  dim3 blk(32, 8);
-  int g = (int)((nvox + 7) / 8); if (g > 148 * 8) g = 148 * 8;
-  if (colsum_vec_ok(C, dy, x) && ((uintptr_t)stats & 15) == 0) launch_colsum2<1>(dy, x, stats, nvox, C, sums_scratch, st);
-  else bn_bwd_reduce_kernel<<<g, blk, 32 * 8 * 2 * sizeof(double), st>>>(dy, x, stats, nvox, C, sums_scratch);
-  SSR_COUNT_LAUNCH();
+  if (!have_sums) {
+    SSR_CHECK_CUDA(cudaMemsetAsync(sums_scratch, 0, 2 * C * sizeof(double), st));
+    dim3 blk(32, 8);
+    int g = (int)((nvox + 7) / 8); if (g > 148 * 8) g = 148 * 8;
+    if (colsum_vec_ok(C, dy, x) && ((uintptr_t)stats & 15) == 0) launch_colsum2<1>(dy, x, stats, nvox, C, sums_scratch, st);
+    else bn_bwd_reduce_kernel<<<g, blk, 32 * 8 * 2 * sizeof(double), st>>>(dy, x, stats, nvox, C, sums_scratch);
+    SSR_COUNT_LAUNCH();
+  }
   if (dgamma && dbeta) {
     bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums_scratch, C, dgamma, dbeta);
     SSR_COUNT_LAUNCH();
@@ -1601,6 +1624,18 @@ int ssr_pool_bn_bwd(const float* dp, const float* x, const float* stats, int B, 
   SSR_COUNT_LAUNCH();
   SSR_CHECK_LAUNCH();
   return SSR_OK;
+}
+
+int ssr_bn_bwd(const float* dy, const float* x, const float* stats, long long nvox, int C, const float* add,
+               int add_stride, int add_off, int elu, float* dx, float* dgamma, float* dbeta, float* dbias,
+               double* sums_scratch, void* stream) {
+  return bn_bwd_impl(dy, x, stats, nvox, C, add, add_stride, add_off, elu, dx, dgamma, dbeta, dbias, sums_scratch, stream, 0);
+}
+// same with the two reductions already in sums2 (= [sum dy | sum dy * xhat], e.g. from ssr_head_loss_bnsums)
+int ssr_bn_bwd_sums(const float* dy, const float* x, const float* stats, long long nvox, int C, const float* add,
+                    int add_stride, int add_off, int elu, float* dx, float* dgamma, float* dbeta, float* dbias,
+                    double* sums2, void* stream) {
+  return bn_bwd_impl(dy, x, stats, nvox, C, add, add_stride, add_off, elu, dx, dgamma, dbeta, dbias, sums2, stream, 1);
 }
 
 int ssr_maxpool_bwd(const float* dp, const float* x, const float* stats, int B, int d0, int d1, int d2, int C,
@@ -1649,11 +1684,23 @@ int ssr_elu_bwd(const float* dh, int dh_stride, int dh_off, const float* h, cons
 }
 
 // head + loss forward/backward.  loss: 1 double (zeroed here).  gout_scratch: nvox*L floats (train only).
-int ssr_head_loss(const float* feat, const float* feat_stats, const float* w, const float* bias, const float* image,
+// sums2[c] = sum_l w[c][l] db[l] (= sum_v dy[v][c]), sums2[C + c] = sum_l w[c][l] xdot[c][l] (= sum_v dy * xhat) for
+// dy = g w^T: the reductions of the BatchNorm backward of the layer folded into the head
+__global__ void head_bn_sums_kernel(const float* __restrict__ w, const float* __restrict__ db, const float* __restrict__ xdot,
+                                    int C, int L, double* __restrict__ sums2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0, b = 0.0;
+  for (int l = 0; l < L; ++l) { a += (double)w[c * L + l] * (double)db[l]; b += (double)w[c * L + l] * (double)xdot[c * L + l]; }
+  sums2[c] = a;
+  sums2[C + c] = b;
+}
+
+static int head_loss_impl(const float* feat, const float* feat_stats, const float* w, const float* bias, const float* image,
                   int image_channels,
                   const int* res_idx, const float* target, float* pred, float* dfeat, float* dw, float* db,
                   double* loss, float* gout_scratch, int B, int d0, int d1, int d2, int C, int L, int metric,
-                  const int* crop_size, const int* crop_begin, int train, void* stream) {
+                  const int* crop_size, const int* crop_begin, int train, void* stream, float* xdot) {
   SSR_CHECK_ARG(feat && w && bias && target && loss && pred, "pointers");
   SSR_CHECK_ARG(L >= 1 && L <= 4 && C * L <= 2048 && (metric == 1 || metric == 2), "head shape/metric");
   SSR_CHECK_ARG(!train || (dfeat && dw && db && gout_scratch), "train buffers");
@@ -1684,8 +1731,8 @@ int ssr_head_loss(const float* feat, const float* feat_stats, const float* w, co
     if (nb > 148 * 8) nb = 148 * 8;
 #define SSR_HEAD_LAUNCH(GS_)                                                                                              \
   do {                                                                                                                  \
-    if (L == 1) head_loss_vec_kernel<GS_, 1><<<(unsigned)nb, 256, 0, st>>>(feat, feat_stats, w, bias, image, target, pred, dfeat, dw, db, loss, P); \
-    else head_loss_vec_kernel<GS_, 4><<<(unsigned)nb, 256, 0, st>>>(feat, feat_stats, w, bias, image, target, pred, dfeat, dw, db, loss, P);        \
+    if (L == 1) head_loss_vec_kernel<GS_, 1><<<(unsigned)nb, 256, 0, st>>>(feat, feat_stats, w, bias, image, target, pred, dfeat, dw, db, loss, xdot, P); \
+    else head_loss_vec_kernel<GS_, 4><<<(unsigned)nb, 256, 0, st>>>(feat, feat_stats, w, bias, image, target, pred, dfeat, dw, db, loss, xdot, P);        \
   } while (0)
     switch (gs) {
       case 1: SSR_HEAD_LAUNCH(1); break;
@@ -1700,6 +1747,7 @@ int ssr_head_loss(const float* feat, const float* feat_stats, const float* w, co
     SSR_CHECK_LAUNCH();
     return SSR_OK;
   }
+  SSR_CHECK_ARG(!xdot, "the BatchNorm-sums output needs the vectorised head path");
   head_loss_kernel<<<grid_for(nvox), 256, 0, st>>>(feat, w, bias, image, target, pred, dfeat, dw, db, loss, P);
   SSR_COUNT_LAUNCH();
   if (train) {
@@ -1710,6 +1758,34 @@ int ssr_head_loss(const float* feat, const float* feat_stats, const float* w, co
     head_wgrad_kernel<<<g, blk, 32 * 8 * sizeof(double), st>>>(feat, gout_scratch, nvox, C, L, dw);
     SSR_COUNT_LAUNCH();
   }
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
+int ssr_head_loss(const float* feat, const float* feat_stats, const float* w, const float* bias, const float* image,
+                  int image_channels,
+                  const int* res_idx, const float* target, float* pred, float* dfeat, float* dw, float* db,
+                  double* loss, float* gout_scratch, int B, int d0, int d1, int d2, int C, int L, int metric,
+                  const int* crop_size, const int* crop_begin, int train, void* stream) {
+  return head_loss_impl(feat, feat_stats, w, bias, image, image_channels, res_idx, target, pred, dfeat, dw, db, loss,
+                        gout_scratch, B, d0, d1, d2, C, L, metric, crop_size, crop_begin, train, stream, nullptr);
+}
+// same with feat_stats given (BatchNorm folded into the head) and train = 1; additionally writes the two reductions of
+// that BatchNorm's backward, sums2 = [sum_v dy | sum_v dy * xhat] (2*C doubles) for dy = dfeat, so that ssr_bn_bwd_sums
+// needs no reduction pass.  db_head must be ZERO on entry (it is read back as sum_v g); xdot_scratch: C*L floats.
+int ssr_head_loss_bnsums(const float* feat, const float* feat_stats, const float* w, const float* bias, const float* image,
+                         int image_channels, const int* res_idx, const float* target, float* pred, float* dfeat,
+                         float* dw, float* db, double* loss, float* gout_scratch, int B, int d0, int d1, int d2, int C,
+                         int L, int metric, const int* crop_size, const int* crop_begin, float* xdot_scratch,
+                         double* sums2, void* stream) {
+  SSR_CHECK_ARG(feat_stats && xdot_scratch && sums2 && db, "bn sums buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  SSR_CHECK_CUDA(cudaMemsetAsync(xdot_scratch, 0, (size_t)C * L * sizeof(float), st));
+  int rc = head_loss_impl(feat, feat_stats, w, bias, image, image_channels, res_idx, target, pred, dfeat, dw, db, loss,
+                          gout_scratch, B, d0, d1, d2, C, L, metric, crop_size, crop_begin, 1, stream, xdot_scratch);
+  if (rc) return rc;
+  head_bn_sums_kernel<<<(C + 127) / 128, 128, 0, st>>>(w, db, xdot_scratch, C, L, sums2);
+  SSR_COUNT_LAUNCH();
   SSR_CHECK_LAUNCH();
   return SSR_OK;
 }

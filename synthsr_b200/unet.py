@@ -79,6 +79,7 @@ class UNet3D:
         self.materialise_feat = os.environ.get('SSR_MATERIALISE_FEAT') is not None
         # BN statistics / ELU backward of the full-resolution 24-channel layers inside the k2n convolution epilogues
         self.pool_bn_fusion = os.environ.get('SSR_NO_POOL_BN_FUSION') is None    # MaxPool + BN backward in two passes
+        self.head_bn_sums = os.environ.get('SSR_NO_HEAD_BN_SUMS') is None        # BN-backward reductions from the head
         # decoder convolutions over the upsampled tensor as 8 parity classes of effective 2x2x2 kernels on the
         # low-resolution tensor (conv3d_tc_up_kernel): levels whose low-resolution grid is at least up_min_dim wide
         self.up_parity = conv_impl == 'tc' and os.environ.get('SSR_NO_UP_PARITY') is None
@@ -569,6 +570,20 @@ class UNet3D:
             crop_size = ctypes.cast(self._crop_keep[0], ctypes.c_void_p)
             crop_begin = ctypes.cast(self._crop_keep[1], ctypes.c_void_p)
         name = 'unet_likelihood'
+        self._head_sums_valid = False
+        if train and self.head_bn_sums and self._feat_stats is not None:
+            # folded BatchNorm: the head also delivers the two reductions of that BatchNorm's backward
+            C = self.feats[0]
+            if getattr(self, '_xdot', None) is None:
+                self._xdot = torch.empty(C * self.nb_labels, dtype=torch.float32, device=self.device)
+                self._sums_head = torch.empty(2 * C, dtype=torch.float64, device=self.device)
+            lib.ssr_head_loss_bnsums(self._feat_src, self._feat_stats, self.p[name + '/kernel'], self.p[name + '/bias'],
+                                     self._image if residual is not None else None, self.cin, res_idx, target, self.pred,
+                                     self.dbn_dec[0], self.g[name + '/kernel'], self.g[name + '/bias'], self.loss_buf,
+                                     self.gout, self.B, *self.dims, C, self.nb_labels, 1 if metric == 'l1' else 2,
+                                     crop_size, crop_begin, self._xdot, self._sums_head, st)
+            self._head_sums_valid = True
+            return
         lib.ssr_head_loss(self._feat_src, self._feat_stats, self.p[name + '/kernel'], self.p[name + '/bias'],
                           self._image if residual is not None else None, self.cin, res_idx, target, self.pred,
                           self.dbn_dec[0] if train else None, self.g[name + '/kernel'] if train else None,
@@ -604,8 +619,13 @@ class UNet3D:
                 d = L - 2 - l
                 c0, c1n = 'unet_conv_uparm_%d_0' % (L + d), 'unet_conv_uparm_%d_1' % (L + d)
                 bn = 'unet_bn_up_%d' % d
-                lib.ssr_bn_bwd(self.dbn_dec[l], self.g1[l], self.stats_dec[l], self.nvox[l], F[l], None, 0, 0, 1, self.ga[l],
-                               self.g[bn + '/gamma'], self.g[bn + '/beta'], self.g[c1n + '/bias'], self.sums, st)
+                if l == 0 and getattr(self, '_head_sums_valid', False):
+                    lib.ssr_bn_bwd_sums(self.dbn_dec[l], self.g1[l], self.stats_dec[l], self.nvox[l], F[l], None, 0, 0, 1,
+                                        self.ga[l], self.g[bn + '/gamma'], self.g[bn + '/beta'], self.g[c1n + '/bias'],
+                                        self._sums_head, st)
+                else:
+                    lib.ssr_bn_bwd(self.dbn_dec[l], self.g1[l], self.stats_dec[l], self.nvox[l], F[l], None, 0, 0, 1,
+                                   self.ga[l], self.g[bn + '/gamma'], self.g[bn + '/beta'], self.g[c1n + '/bias'], self.sums, st)
                 self._wgrad_async(c1n, self.g0[l], F[l], None, 0, self.ga[l], l, F[l])
                 if self._k2n_epi_ok(F[l], F[l]):
                     self._conv_dgrad(c1n, self.ga[l], self.gb[l], l, F[l], F[l], elu_h=self.g0[l], dbias=self.g[c0 + '/bias'])

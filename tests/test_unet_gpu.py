@@ -697,3 +697,50 @@ def test_tc_generic_fused_epilogues_match_float64():
         dxd = dx.double().cpu()
         err = ((db.double().cpu() - db0.double().cpu() - dxd.sum(0)).abs() / dxd.abs().sum(0)).max().item()
         assert err < 3e-6, ('dbias', d, cin, co, err)
+
+
+def test_head_bn_sums_match_direct_reductions():
+    """ssr_head_loss_bnsums: the reductions of the folded BatchNorm's backward (sum dy, sum dy * xhat with dy = dfeat)
+    obtained algebraically from the head gradients, against float64 sums over the dfeat the kernel wrote; every other
+    output identical to ssr_head_loss."""
+    import ctypes
+    from synthsr_b200._lib import lib, stream_ptr
+    rng = np.random.default_rng(31)
+    for (d, C, L, metric) in [([16, 20, 24], 24, 1, 1), ([9, 11, 13], 24, 2, 2), ([32, 32, 32], 8, 1, 1)]:
+        nv = int(np.prod(d))
+        st = stream_ptr()
+        feat = torch.from_numpy(rng.normal(size=(nv, C)).astype(np.float32) * 2 + 1).cuda()
+        gamma = torch.from_numpy(rng.uniform(.5, 1.5, size=C).astype(np.float32)).cuda()
+        beta = torch.from_numpy(rng.normal(size=C).astype(np.float32)).cuda()
+        stats = torch.empty(4 * C, device='cuda')
+        scratch = torch.zeros(2 * C, dtype=torch.float64, device='cuda')
+        lib.ssr_bn_stats(feat, nv, C, gamma, beta, None, None, 1e-3, .99, scratch, stats, st)
+        w = torch.from_numpy(rng.normal(size=(C, L)).astype(np.float32)).cuda()
+        b = torch.from_numpy(rng.normal(size=L).astype(np.float32)).cuda()
+        target = torch.from_numpy(rng.normal(size=(nv, L)).astype(np.float32)).cuda()
+        outs = []
+        for mode in (0, 1):
+            pred = torch.empty((nv, L), device='cuda')
+            dfeat = torch.full((nv, C), float('nan'), device='cuda')
+            dw, db = torch.zeros((C, L), device='cuda'), torch.zeros(L, device='cuda')
+            loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+            gout = torch.empty((nv, L), device='cuda')
+            if mode == 0:
+                lib.ssr_head_loss(feat, stats, w, b, None, 1, None, target, pred, dfeat, dw, db, loss, gout, 1, *d, C, L,
+                                  metric, None, None, 1, st)
+                sums2 = None
+            else:
+                xdot = torch.full((C * L,), 7., device='cuda')
+                sums2 = torch.full((2 * C,), 5., dtype=torch.float64, device='cuda')
+                lib.ssr_head_loss_bnsums(feat, stats, w, b, None, 1, None, target, pred, dfeat, dw, db, loss, gout, 1, *d, C,
+                                         L, metric, None, None, xdot, sums2, st)
+            torch.cuda.synchronize()
+            outs.append((pred, dfeat, dw, db, loss, sums2))
+        for a, b_ in zip(outs[0][:5], outs[1][:5]):
+            assert torch.allclose(a, b_, rtol=1e-5, atol=1e-8)
+        dfd = outs[1][1].double()
+        xhat = (feat.double() - stats[:C].double()) * stats[C:2 * C].double()
+        ref = torch.cat([dfd.sum(0), (dfd * xhat).sum(0)])
+        mag = torch.cat([dfd.abs().sum(0), (dfd * xhat).abs().sum(0)])
+        err = ((outs[1][5] - ref).abs() / mag).max().item()
+        assert err < 2e-5, (d, C, L, err)
