@@ -744,3 +744,45 @@ def test_head_bn_sums_match_direct_reductions():
         mag = torch.cat([dfd.abs().sum(0), (dfd * xhat).abs().sum(0)])
         err = ((outs[1][5] - ref).abs() / mag).max().item()
         assert err < 2e-5, (d, C, L, err)
+
+
+def test_tc_up_parity_kernels_batched():
+    """batch > 1 through the parity kernels (the strided dy views carry the batch stride): forward / gradient of a batch of
+    two equal the two samples run one by one; the weight gradient is their sum."""
+    from synthsr_b200._lib import lib, stream_ptr
+    rng = np.random.default_rng(23)
+    dl, cs, cu, co = [6, 9, 8], 24, 48, 24
+    df = [2 * v for v in dl]
+    nl, nf = int(np.prod(dl)), int(np.prod(df))
+    st = stream_ptr()
+    w = torch.from_numpy((rng.normal(size=(3, 3, 3, cs + cu, co)) / np.sqrt(27 * (cs + cu))).astype(np.float32)).cuda()
+    low = torch.from_numpy(rng.normal(size=(2, nl, cu)).astype(np.float32)).cuda()
+    dy = torch.from_numpy(rng.normal(size=(2, nf, co)).astype(np.float32)).cuda()
+    wskip = torch.empty(27 * cs * co, device='cuda')
+    weff = torch.empty(8 * 27 * cu * co, device='cuda')
+    lib.ssr_conv3d_up_weights(w, cs, cu, co, wskip, weff, st)
+    nfw, ndg = lib.ssr_conv3d_packed_size(cu, 0, co, 0), lib.ssr_conv3d_packed_size(cu, 0, co, 1)
+    fwd8, dgr8 = torch.empty(8 * nfw, device='cuda'), torch.empty(8 * ndg, device='cuda')
+    for par in range(8):
+        src = weff[par * 27 * cu * co:(par + 1) * 27 * cu * co]
+        lib.ssr_conv3d_pack_weights(src, fwd8[par * nfw:(par + 1) * nfw], cu, 0, co, 0, st)
+        lib.ssr_conv3d_pack_weights(src, dgr8[par * ndg:(par + 1) * ndg], cu, 0, co, 1, st)
+
+    def run(B, lo, d):
+        y = torch.full((B, nf, co), float('nan'), device='cuda')
+        dlow = torch.full((B, nl, cu), float('nan'), device='cuda')
+        dw = torch.zeros((27, cs + cu, co), device='cuda')
+        scratch = torch.empty(8 * 27 * cu * co, device='cuda')
+        lib.ssr_conv3d_fwd_tc_up(lo, cu, fwd8, y, B, *dl, co, st)
+        lib.ssr_conv3d_dgrad_tc_up(d, co, dgr8, dlow, B, *dl, cu, st)
+        lib.ssr_conv3d_wgrad_tc_up(lo, cu, d, dw, cs + cu, cs, scratch, B, *dl, co, st)
+        torch.cuda.synchronize()
+        return y, dlow, dw
+
+    y2, dl2, dw2 = run(2, low, dy)
+    singles = [run(1, low[b:b + 1].contiguous(), dy[b:b + 1].contiguous()) for b in range(2)]
+    assert not torch.isnan(y2).any() and not torch.isnan(dl2).any()
+    for b in range(2):
+        assert torch.equal(y2[b], singles[b][0][0]) and torch.equal(dl2[b], singles[b][1][0])
+    ref = singles[0][2] + singles[1][2]
+    assert (dw2 - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
