@@ -103,24 +103,32 @@ def _maxpool_same(x):
     return F.max_pool3d(x, 2)
 
 
-def forward(params, image, training=True, nb_levels=5, nb_conv_per_level=2, new_stats=None, activations=None):
-    """image [B,X,Y,Z,Cin] -> prediction [B,X,Y,Z,nb_labels].  (ext/neuron/models.py:301-360, 420-498)"""
+def forward(params, image, training=True, nb_levels=5, nb_conv_per_level=2, new_stats=None, activations=None,
+            _wrong=()):
+    """image [B,X,Y,Z,Cin] -> prediction [B,X,Y,Z,nb_labels].  (ext/neuron/models.py:301-360, 420-498)
+    _wrong: deliberately wrong readings of the graph ('concat_swapped', 'skip_after_bn', 'relu'), only for the test that
+    shows the reference's trained weights reject them (tests/test_oracle_unet.py)."""
+    act = F.relu if 'relu' in _wrong else F.elu
     x = image.permute(0, 4, 1, 2, 3)
     skips = []
     for level in range(nb_levels):
         for j in range(nb_conv_per_level):
-            x = F.elu(_conv(x, params, 'unet_conv_downarm_%d_%d' % (level, j)))
+            x = act(_conv(x, params, 'unet_conv_downarm_%d_%d' % (level, j)))
             if activations is not None:
                 activations['unet_conv_downarm_%d_%d' % (level, j)] = x
-        skips.append(x)                                            # conv output, pre-BN (models.py:431-432)
+        if 'skip_after_bn' not in _wrong:
+            skips.append(x)                                        # conv output, pre-BN (models.py:431-432)
         x = _bn(x, params, 'unet_bn_down_%d' % level, training, new_stats)
+        if 'skip_after_bn' in _wrong:
+            skips.append(x)
         if level < nb_levels - 1:
             x = _maxpool_same(x)
     for level in range(nb_levels - 1):
         x = F.interpolate(x, scale_factor=2, mode='nearest')       # UpSampling3D (models.py:425-427)
-        x = torch.cat([skips[nb_levels - 2 - level], x], dim=1)    # models.py:434
+        pair = [skips[nb_levels - 2 - level], x]
+        x = torch.cat(pair[::-1] if 'concat_swapped' in _wrong else pair, dim=1)    # models.py:434
         for j in range(nb_conv_per_level):
-            x = F.elu(_conv(x, params, 'unet_conv_uparm_%d_%d' % (nb_levels + level, j)))
+            x = act(_conv(x, params, 'unet_conv_uparm_%d_%d' % (nb_levels + level, j)))
             if activations is not None:
                 activations['unet_conv_uparm_%d_%d' % (nb_levels + level, j)] = x
         x = _bn(x, params, 'unet_bn_up_%d' % level, training, new_stats)

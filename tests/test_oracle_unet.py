@@ -1,8 +1,10 @@
 """CPU tests pinning the torch U-Net oracle: topology / parameter count of the reference model, Keras layer names,
 analytic known-answer cases, and the Keras Adam / BN-moving-average formulas."""
 import math
+import os
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import unet as OU
@@ -93,3 +95,47 @@ def test_train_step_reduces_loss():
     for _ in range(3):
         l1, _, _ = OU.train_step(p, opt, x, t, lr=1e-3)
     assert l1 < l0 and opt['iterations'] == 4
+
+
+@pytest.mark.skipif(not os.path.isfile('/root/reference/models/SynthSR_v10_210712.h5'),
+                    reason='reference weights / scan are only mounted in the build container')
+def test_trained_reference_weights_pin_the_layer_semantics():
+    """TensorFlow / Keras cannot run here, so the oracle's reading of the Keras graph (U3: cross-correlation kernels in
+    (kd,kh,kw,Cin,Cout) layout, ELU, skip taken before BatchNorm, concat order [skip, upsampled], inference BatchNorm on
+    the moving statistics) has no TF output to be compared with.  The reference ships something almost as good: a model
+    TRAINED under those semantics (models/SynthSR_v10_210712.h5) and a 1 mm scan it was meant for
+    (data/images/brain1.nii.gz).  Under the oracle's reading the network reproduces the anatomy of its input (correlation
+    > 0.85 on a 96^3 crop); under every plausible misreading it falls apart."""
+    import torch
+    from oracle import unet as OU
+    from SynthSR import predict as P
+    from ext.lab2im import utils
+    from synthsr_b200 import h5lite
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    sd, _ = h5lite.load_keras_weights('/root/reference/models/SynthSR_v10_210712.h5')
+    params = {k: torch.tensor(v) for k, v in sd.items()}
+    im, aff, _ = utils.load_volume('/root/reference/data/images/brain1.nii.gz', im_only=False, dtype='float')
+    S, idx, shape, _ = P.preprocess(im, aff)
+    c = [s // 2 - 48 for s in S.shape[1:4]]
+    crop = np.ascontiguousarray(S[:, c[0]:c[0] + 96, c[1]:c[1] + 96, c[2]:c[2] + 96, :], dtype=np.float32)
+    x = torch.from_numpy(crop)
+
+    def corr(p, **kw):
+        with torch.no_grad():
+            pred = OU.forward(p, x, training=kw.pop('training', False), **kw).numpy()
+        a, b = pred[0, 16:-16, 16:-16, 16:-16, 0].ravel(), crop[0, 16:-16, 16:-16, 16:-16, 0].ravel()
+        return float(np.corrcoef(a, b)[0, 1])
+
+    right = corr(params)
+    flipped = {k: (v.flip(0, 1, 2) if k.endswith('kernel') and v.shape[0] == 3 else v) for k, v in params.items()}
+    transposed = {k: (v.permute(2, 1, 0, 3, 4).contiguous() if k.endswith('kernel') and v.shape[0] == 3 else v)
+                  for k, v in params.items()}
+    wrong = {'true convolution (flipped kernels)': corr(flipped),
+             'kernel axes in (kw,kh,kd) order': corr(transposed),
+             'concat order [upsampled, skip]': corr(params, _wrong=('concat_swapped',)),
+             'skip taken after BatchNorm': corr(params, _wrong=('skip_after_bn',)),
+             'ReLU instead of ELU': corr(params, _wrong=('relu',)),
+             'batch statistics at inference': corr(params, training=True)}
+    assert right > 0.85, right
+    for name, r in wrong.items():
+        assert r < right - 0.15, (name, r, right)
