@@ -230,6 +230,9 @@ struct TcGeom {
   int n1tiles, n2tiles, n0tiles, nNtiles;
   int act;
   int accumulate;    // epilogue adds the partial result already in y (before bias / activation)
+  int pl_pitch;      // PL mode: d2 pitch of the zero-padded plane (D2 + 2); M windows = n2tiles (n1tiles = 1)
+  int pl_slab;       // PL mode: bytes of a slab stage (padded plane + over-read slack, multiple of 1024)
+  int pl_tx;         // PL mode: bytes one TMA load of a padded plane writes
   int tmem_cols;
   unsigned char chunk_src[MAX_CHUNKS];    // 0: x1, 1: x2
   unsigned char chunk_ks[MAX_CHUNKS];     // K-steps of 8 channels actually present in the chunk (1..4)
@@ -292,7 +295,12 @@ __device__ __forceinline__ float colsum16_transpose(const float (&v)[16], int la
 //   1 (data gradient): out *= elu'(elu_h) and dbias[c] += sum_v out[v][c]      -- replaces elu_bwd_kernel
 //   2 (forward):       sums[c] += sum_v out, sums[Cout + c] += sum_v out^2    -- replaces colsum2_vec_kernel<0>
 // Column sums: transposed warp butterfly per 16-channel block -> shared-memory floats per CTA -> one atomic per channel.
-template <int EPI>
+// PL ("plane-linearised", the small deep levels): a tile is a window of 128 consecutive rows of the whole zero-padded
+// (D1 + 2) x (D2 + 2) plane, loaded as ONE slab; output voxel (i1, i2) <-> row r = i1 * pitch + i2 and every (k1, k2) tap is
+// the row shift k1 * pitch + k2 of the same slab (row-shifted K-major views read consistently with the TMA swizzle,
+// profiles/r01_desc_probe_unaligned_views.txt).  With 16 x 8 tiles a 10^3 / 20^3 plane fills 39 % / 52 % of the GEMM rows
+// it pays for, a linearised plane 78 %; rows that fall into the halo columns are computed and dropped.
+template <int EPI, bool PL = false>
 __global__ void __launch_bounds__(288, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_x2,
                  const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias, float* __restrict__ y,
@@ -302,7 +310,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   const int bgroup_bytes = G.KG * 3 * G.NT * 128;
-  uint8_t* sB = sA + (size_t)G.SA * SLAB_BYTES;
+  const int slab_bytes = PL ? G.pl_slab : SLAB_BYTES;
+  uint8_t* sB = sA + (size_t)G.SA * slab_bytes;
   uint64_t* bars = (uint64_t*)(sB + (size_t)SB * bgroup_bytes);
   uint64_t* fullA = bars;
   uint64_t* emptyA = bars + G.SA;
@@ -383,8 +392,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
               if (++sb == SB) { sb = 0; pb ^= 1; }
               for (int zin = zin_lo; zin < zin_hi; ++zin) {
                 { const long long w0 = dbg ? clock64() : 0; mbar_wait(emptyA + sa, pa ^ 1); if (dbg) wait_empty += clock64() - w0; }
-                mbar_expect_tx(fullA + sa, SLAB_BYTES);
-                tma_load_5d(mx, fullA + sa, sA + (size_t)sa * SLAB_BYTES, c0, x0 + k2 - 1, y0 - 1, z0 + k0g + zin - 1, b);
+                if (PL) {      // the whole zero-padded plane (the d2 tap is a row shift of the operand view, not of the box)
+                  mbar_expect_tx(fullA + sa, (uint32_t)G.pl_tx);
+                  tma_load_5d(mx, fullA + sa, sA + (size_t)sa * slab_bytes, c0, -1, -1, z0 + k0g + zin - 1, b);
+                } else {
+                  mbar_expect_tx(fullA + sa, SLAB_BYTES);
+                  tma_load_5d(mx, fullA + sa, sA + (size_t)sa * SLAB_BYTES, c0, x0 + k2 - 1, y0 - 1, z0 + k0g + zin - 1, b);
+                }
                 if (++sa == G.SA) { sa = 0; pa ^= 1; }
               }
             }
@@ -433,7 +447,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                 const int kk = zin - zo;
                 if (active && kk >= 0 && kk < KG) {            // warp-uniform
                   if (elect_one()) {
-                    uint32_t alo = a_base + (uint32_t)sa * (SLAB_BYTES >> 4);
+                    uint32_t alo = a_base + (uint32_t)sa * ((uint32_t)slab_bytes >> 4);
+                    if (PL) alo += (uint32_t)(t2 * 128 + k2) * 8u;      // window start + d2 tap, in 128-byte rows
+                    const uint32_t k1_step = PL ? (uint32_t)G.pl_pitch * 8u : (uint32_t)(TM2 * 128 >> 4);
                     uint32_t blo = blo0 + (uint32_t)(kk * 3) * btile16;
 #pragma unroll
                     for (int k1 = 0; k1 < 3; ++k1) {
@@ -442,7 +458,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                       else if (nks == 2) umma_chain_k<2>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
                       else umma_chain_k<1>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
                       acc = 1u;
-                      alo += (uint32_t)(TM2 * 128 >> 4);
+                      alo += k1_step;
                       blo += btile16;
                     }
                     umma_commit(emptyA + sa);        // this warp's reads of the slab are done once these MMAs complete
@@ -476,7 +492,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
       DECODE_TILE(tile)
       const int set = it & 1;
       const uint32_t acc_base = tmem_base + (uint32_t)set * set_cols;
-      const int i1 = y0 + (r >> 3), i2 = x0 + (r & 7);
+      int i1 = y0 + (r >> 3), i2 = x0 + (r & 7);
+      if (PL) { const int rr = t2 * 128 + r; i1 = rr / G.pl_pitch; i2 = rr - i1 * G.pl_pitch; }   // halo columns: i2 >= D2
       mbar_wait(accFull + set, (it >> 1) & 1);
       tc_fence_after();
       if (warp == G.TZ + 1 && lane == 0 && it == 0) DBG_STAMP(5);
@@ -2170,11 +2187,26 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
     int ks_total = 0;
     for (int c = 0; c < C1; c += 32) ks_total += ((C1 - c < 32 ? C1 - c : 32) + 7) / 8;
     for (int c = 0; c < C2; c += 32) ks_total += ((C2 - c < 32 ? C2 - c : 32) + 7) / 8;
-    const int n1t = (D1 + TM1 - 1) / TM1, n2t = (D2 + TM2 - 1) / TM2;
+    int n1t = (D1 + TM1 - 1) / TM1, n2t = (D2 + TM2 - 1) / TM2;
+    // plane-linearised tiling for the small deep levels: windows of 128 rows of the padded plane instead of 16 x 8 tiles
+    const int pitch = D2 + 2;
+    const int nwin = ((D1 - 1) * pitch + D2 + 127) / 128;
+    const int pl_slab = round_up((nwin * 128 + 2 * pitch + 2) * 128, 1024);
+    // measured (160^3 net): 10^3 layers 74 vs 80 us with plane tiles; at 20^3 the 71 KB slabs leave only two pipeline
+    // stages and the layers get slower (82 vs 75 us), so plane tiles are used while a slab stays at the 18 x 8 slab's size
+    const int pl_max = getenv("SSR_PLANE_TILES_MAX_KB") ? atoi(getenv("SSR_PLANE_TILES_MAX_KB")) * 1024 : 24 * 1024;
+    if (nwin < n1t * n2t && pl_slab <= pl_max && D1 + 2 <= 256 && pitch <= 256 && !getenv("SSR_NO_PLANE_TILES")) {
+      G.pl_pitch = pitch; G.pl_slab = pl_slab; G.pl_tx = (D1 + 2) * pitch * 128;
+      n1t = 1; n2t = nwin;
+    }
+    // shared-memory fit of an N tile: two B groups (all 9 (k0,k1) taps of a d2 tap when they fit, else 3) + >= 2 slabs
+    const int slab_b = G.pl_pitch > 0 ? G.pl_slab : SLAB_BYTES;
+    const int avail = 227 * 1024 - 1024 - 2816 - (epi ? 2 * 4 * 576 : 0);
+    auto fits = [&](int nt) { return SB * 3 * nt * 128 + 2 * slab_b <= avail; };
     double best = 1e300;
     int best_nt = 0, best_tz = 0;
     for (int nt = 16; nt <= 192 && nt <= G.Npad; nt += 16) {
-      if (G.Npad % nt) continue;
+      if (G.Npad % nt || !fits(nt)) continue;
       for (int tz = 1; tz <= 4 && tz <= D0 && tz * nt <= 256; ++tz) {   // two accumulator sets in 512 TMEM columns
         const long long tiles = (long long)B * ((D0 + tz - 1) / tz) * n1t * n2t * (G.Npad / nt);
         const long long rounds = (tiles + 147) / 148;
@@ -2192,6 +2224,7 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
   }
   G.nNtiles = G.Npad / G.NT;
   G.KG = (3 * 3 * G.NT * 128 <= 74 * 1024) ? 3 : 1;
+  if (G.pl_pitch > 0 && SB * 9 * G.NT * 128 + 2 * G.pl_slab > 227 * 1024 - 1024 - 2816 - (epi ? 2 * 4 * 576 : 0)) G.KG = 1;
   int cols = 2 * G.TZ * G.NT, pc = 32;
   while (pc < cols) pc <<= 1;
   G.tmem_cols = pc;
@@ -2205,29 +2238,36 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
     G.chunk_src[nch] = 1; G.chunk_c0[nch] = (short)c; G.chunk_ks[nch] = (unsigned char)(((C2 - c < 32 ? C2 - c : 32) + 7) / 8); ++nch;
   }
   G.nchunks = nch;
+  const bool pl = G.pl_pitch > 0;
   G.n2tiles = (D2 + TM2 - 1) / TM2; G.n1tiles = (D1 + TM1 - 1) / TM1; G.n0tiles = (D0 + G.TZ - 1) / G.TZ;
+  if (pl) { G.n1tiles = 1; G.n2tiles = ((D1 - 1) * G.pl_pitch + D2 + 127) / 128; }
+  const int slab_bytes = pl ? G.pl_slab : SLAB_BYTES;
   const int bgroup = G.KG * 3 * G.NT * 128;
   const int tail = 2816 /*barriers + bias*/ + (epi ? 2 * 4 * 576 : 0) /*per-CTA channel sums of the fused epilogues*/;
   const int budget = 227 * 1024 - 1024 /*align slack*/ - tail - SB * bgroup;
-  int sa = budget / SLAB_BYTES; if (sa > 8) sa = 8;
+  int sa = budget / slab_bytes; if (sa > 8) sa = 8;
   SSR_CHECK_ARG(sa >= 2, "shared memory budget");
   G.SA = sa;
-  const size_t smem = 1024 + (size_t)G.SA * SLAB_BYTES + (size_t)SB * bgroup + tail;
+  const size_t smem = 1024 + (size_t)G.SA * slab_bytes + (size_t)SB * bgroup + tail;
   SSR_CHECK_ARG(epi == 0 || (epi == 1 ? (elu_h && dbias) : (epi == 2 && sums)), "fused epilogue buffers");
   SSR_CHECK_ARG(epi == 0 || !accumulate, "fused epilogues do not combine with accumulate");
 
   CUtensorMap m1, m2, mw;
-  int rc = make_map_act(&m1, x1, C1, B, D0, D1, D2);
+  const int bx1 = pl ? D1 + 2 : TM1 + 2, bx2 = pl ? G.pl_pitch : TM2;        // TMA box: whole padded plane / 18 x 8 slab
+  int rc = make_map_act(&m1, x1, C1, B, D0, D1, D2, bx1, CU_TENSOR_MAP_SWIZZLE_128B, bx2);
   if (rc) return rc;
-  if (C2 > 0) { rc = make_map_act(&m2, x2, C2, B, D0, D1, D2); if (rc) return rc; } else m2 = m1;
+  if (C2 > 0) { rc = make_map_act(&m2, x2, C2, B, D0, D1, D2, bx1, CU_TENSOR_MAP_SWIZZLE_128B, bx2); if (rc) return rc; } else m2 = m1;
   rc = make_map_w(&mw, wp, (long long)nch * 27 * G.Npad, G.NT);
   if (rc) return rc;
 
   static bool attr_set = false;
   if (!attr_set) {
-    SSR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SSR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SSR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SSR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SSR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SSR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SSR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SSR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SSR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const long long ntiles = (long long)B * G.n0tiles * G.n1tiles * G.n2tiles * G.nNtiles;
@@ -2240,9 +2280,17 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
   }
   const unsigned grid = (unsigned)(ntiles < num_sms ? ntiles : num_sms);       // persistent: one CTA per SM
   // TMA + TZ MMA + 4 epilogue warps
-  if (epi == 1) conv3d_tc_kernel<1><<<grid, 32 * (5 + G.TZ), smem, (cudaStream_t)stream>>>(m1, m2, mw, bias, y, G, elu_h, dbias, sums);
-  else if (epi == 2) conv3d_tc_kernel<2><<<grid, 32 * (5 + G.TZ), smem, (cudaStream_t)stream>>>(m1, m2, mw, bias, y, G, elu_h, dbias, sums);
-  else conv3d_tc_kernel<0><<<grid, 32 * (5 + G.TZ), smem, (cudaStream_t)stream>>>(m1, m2, mw, bias, y, G, nullptr, nullptr, nullptr);
+  const unsigned nthr = 32 * (5 + G.TZ);
+  cudaStream_t cst = (cudaStream_t)stream;
+  if (pl) {
+    if (epi == 1) conv3d_tc_kernel<1, true><<<grid, nthr, smem, cst>>>(m1, m2, mw, bias, y, G, elu_h, dbias, sums);
+    else if (epi == 2) conv3d_tc_kernel<2, true><<<grid, nthr, smem, cst>>>(m1, m2, mw, bias, y, G, elu_h, dbias, sums);
+    else conv3d_tc_kernel<0, true><<<grid, nthr, smem, cst>>>(m1, m2, mw, bias, y, G, nullptr, nullptr, nullptr);
+  } else {
+    if (epi == 1) conv3d_tc_kernel<1, false><<<grid, nthr, smem, cst>>>(m1, m2, mw, bias, y, G, elu_h, dbias, sums);
+    else if (epi == 2) conv3d_tc_kernel<2, false><<<grid, nthr, smem, cst>>>(m1, m2, mw, bias, y, G, elu_h, dbias, sums);
+    else conv3d_tc_kernel<0, false><<<grid, nthr, smem, cst>>>(m1, m2, mw, bias, y, G, nullptr, nullptr, nullptr);
+  }
   SSR_COUNT_LAUNCH();
   SSR_CHECK_LAUNCH();
   return SSR_OK;
