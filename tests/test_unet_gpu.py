@@ -786,3 +786,15 @@ def test_tc_up_parity_kernels_batched():
         assert torch.equal(y2[b], singles[b][0][0]) and torch.equal(dl2[b], singles[b][1][0])
     ref = singles[0][2] + singles[1][2]
     assert (dw2 - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+
+
+def test_tc_plane_linearised_tiles_all_shapes():
+    """plane-linearised tiles are enabled by default only while a padded plane fits a 24 KB slab; with the limit lifted the
+    multi-window shapes of the generic-kernel tests (3 - 6 windows, two tensor maps, fused epilogues) go through them."""
+    import os
+    os.environ['SSR_PLANE_TILES_MAX_KB'] = '72'
+    try:
+        test_tc_generic_fused_epilogues_match_float64()
+        test_tc_matches_ref_kernels()
+    finally:
+        os.environ.pop('SSR_PLANE_TILES_MAX_KB', None)
