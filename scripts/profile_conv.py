@@ -57,8 +57,62 @@ def run(name, reps):
     print('%-8s %s c=%d+%d->%d  %.3f ms  %.1f TFLOP/s' % (name, d, c1, c2, co, ms, flops / ms / 1e9))
 
 
+def run_special(name, reps):
+    """'up72': parity forward / gradient / weight gradient of the level-0 decoder convolution (48 upsampled channels of
+    80^3 -> 24 channels at 160^3); 'first': the exact-fp32 first layer (1 -> 24 at 160^3) forward + weight gradient."""
+    st = stream_ptr()
+    g = torch.Generator(device='cuda').manual_seed(0)
+    fns = {}
+    if name == 'up72':
+        dl, cs, cu, co = [80, 80, 80], 24, 48, 24
+        nl, nf = 80 ** 3, 160 ** 3
+        w = torch.randn((3, 3, 3, cs + cu, co), device='cuda', generator=g) / np.sqrt(27 * (cs + cu))
+        low = torch.randn((nl, cu), device='cuda', generator=g)
+        dy = torch.randn((nf, co), device='cuda', generator=g)
+        wskip, weff = torch.empty(27 * cs * co, device='cuda'), torch.empty(8 * 27 * cu * co, device='cuda')
+        lib.ssr_conv3d_up_weights(w, cs, cu, co, wskip, weff, st)
+        nfw, ndg = lib.ssr_conv3d_packed_size(cu, 0, co, 0), lib.ssr_conv3d_packed_size(cu, 0, co, 1)
+        fwd8, dgr8 = torch.empty(8 * nfw, device='cuda'), torch.empty(8 * ndg, device='cuda')
+        for par in range(8):
+            src = weff[par * 27 * cu * co:(par + 1) * 27 * cu * co]
+            lib.ssr_conv3d_pack_weights(src, fwd8[par * nfw:(par + 1) * nfw], cu, 0, co, 0, st)
+            lib.ssr_conv3d_pack_weights(src, dgr8[par * ndg:(par + 1) * ndg], cu, 0, co, 1, st)
+        y, dlow = torch.empty((nf, co), device='cuda'), torch.empty((nl, cu), device='cuda')
+        dw, scratch = torch.zeros((27, cs + cu, co), device='cuda'), torch.empty(8 * 27 * cu * co, device='cuda')
+        fl = 2. * 27 * cu * co * nf
+        fns = {'fwd_up': (lambda: lib.ssr_conv3d_fwd_tc_up(low, cu, fwd8, y, 1, *dl, co, st), fl),
+               'dgrad_up': (lambda: lib.ssr_conv3d_dgrad_tc_up(dy, co, dgr8, dlow, 1, *dl, cu, st), fl),
+               'wgrad_up': (lambda: lib.ssr_conv3d_wgrad_tc_up(low, cu, dy, dw, cs + cu, cs, scratch, 1, *dl, co, st), fl)}
+    elif name == 'first':
+        d, co = [160, 160, 160], 24
+        nv = 160 ** 3
+        x = torch.rand((nv, 1), device='cuda', generator=g)
+        w = torch.randn((3, 3, 3, 1, co), device='cuda', generator=g) / np.sqrt(27)
+        b = torch.zeros(co, device='cuda')
+        y = torch.empty((nv, co), device='cuda')
+        dy = torch.randn((nv, co), device='cuda', generator=g)
+        dw = torch.zeros(27 * co, device='cuda')
+        fl = 2. * 27 * co * nv
+        fns = {'first_fwd': (lambda: lib.ssr_conv3d_fwd_ref(x, 1, None, 0, w, b, y, 1, *d, co, 3, 1, st), fl),
+               'first_wgrad': (lambda: lib.ssr_conv3d_wgrad_ref(x, 1, None, 0, dy, dw, None, 1, *d, co, 3, st), fl)}
+    for k, (fn, fl) in fns.items():
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        print('%-12s %.3f ms  %.1f TFLOP/s (algorithmic)' % (k, ms, fl / ms / 1e9))
+
+
 if __name__ == '__main__':
     which = sys.argv[1] if len(sys.argv) > 1 else 'all'
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
     for n in (CASES if which == 'all' else which.split(',')):
-        run(n, reps)
+        if n in ('up72', 'first'):
+            run_special(n, reps)
+        else:
+            run(n, reps)
