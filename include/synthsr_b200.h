@@ -131,6 +131,12 @@ int ssr_conv3d_fwd_tc_up(const float* low, int Cup, const float* wp8, float* y, 
                          void* stream);
 int ssr_conv3d_dgrad_tc_up(const float* dy, int Cout_layer, const float* wp8, float* dlow, int B, int d0, int d1, int d2,
                            int Cup, void* stream);
+/* ssr_conv3d_fwd_tc_up in the k2n layout for the last decoder level (Cout == 24, Cup <= 64): d2 parity and its two taps in
+ * the MMA N dimension, the kernels of one (p0, p1) class resident per CTA; wpk: 4*8*96*32 floats from
+ * ssr_conv3d_pack_up_k2n(weff of ssr_conv3d_up_weights) */
+int ssr_conv3d_pack_up_k2n(const float* weff, float* wpk, int Cup, void* stream);
+int ssr_conv3d_fwd_tc_up_k2n(const float* low, int Cup, const float* wpk, float* y, int B, int d0, int d1, int d2, int Cout,
+                             void* stream);
 /* Cin <= 32, Cout <= 32 (the full-resolution layers): the three d2 taps ride in the MMA N dimension; weights packed
  * with mode 2 (forward) / 3 (data gradient: x = dy, Cout = the layer's Cin).  Same result contract as ssr_conv3d_fwd_tc. */
 int ssr_conv3d_fwd_tc_k2n(const float* x, int C, const float* wp, const float* bias, float* y, int B, int d0, int d1,

@@ -1231,6 +1231,235 @@ conv3d_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Forward of the upsampled part of the LAST decoder convolution (Cup <= 64 -> 24 channels at full resolution) in the
+// k2n layout: conv3d_tc_up_kernel<1> with N = 24 is bound by L2 -> shared-memory slab traffic (844 B per output,
+// profiles/r01_fwd_up72_ncu_full.txt), so the d2 parity p2 and its two taps ride in N instead:
+//     Q_g[v'] = sum_{k0, k1, ci} low[v' + (k0 - 1, k1 - 1, 0)][ci] * Weff_(p0,p1,p2)[k0][k1][k2][ci][:]   g = (p2, k2) in
+//               {(0,0), (0,1), (1,1), (1,2)}  ->  one MMA with N = 4 x 24 = 96
+//     y[2 i0 + p0, 2 i1 + p1, 2 i2]     = Q_(0,0)[i2 - 1] + Q_(0,1)[i2]          (epilogue: lane shuffles, two adjacent
+//     y[2 i0 + p0, 2 i1 + p1, 2 i2 + 1] = Q_(1,1)[i2]     + Q_(1,2)[i2 + 1]       full-resolution voxels = 192 B per thread)
+//   class     a CTA serves ONE (p0, p1) class (blockIdx.x & 3): its 2 (d0 tap) x 2 (d1 tap) x 2 (chunk) kernel tiles of
+//             96 rows (96 KB) stay resident in shared memory
+//   A         slab = TMA box 32 ch x 16 x 10 of low-resolution plane q and chunk ch (as conv3d_tc_k2n_kernel); output plane
+//             z takes planes z + p0 - 1 and z + p0, so a slab is read by two output planes (ring of 6 = 3 planes x 2 chunks)
+//   D         ring of four accumulators (96 TMEM columns), MMA warp w owns slot w, eight epilogue warps in two sets
+// ---------------------------------------------------------------------------------------------------------
+constexpr int KU_SA = 6;
+
+struct KuGeom {
+  int B, D0, D1, D2;       // LOW-resolution grid
+  int Cout;                // 24
+  int nch;                 // channel chunks of the low-resolution tensor (1 or 2)
+  int nks[2];              // K-steps of 8 channels per chunk
+  int n1tiles, n2tiles, nzr, zlen;
+};
+
+__global__ void __launch_bounds__(416, 1)
+conv3d_tc_up_k2n_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                        float* __restrict__ y, const KuGeom G) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = smem;                                            // [t][k1i][ch] x 96 rows x 128 B
+  uint8_t* sA = sB + 8 * KF_BTILE_BYTES;
+  uint64_t* bars = (uint64_t*)(sA + (size_t)KU_SA * KF_SLAB_BYTES);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = bars + KU_SA;
+  uint64_t* accFull = bars + 2 * KU_SA;
+  uint64_t* accEmpty = accFull + KF_NACC;
+  uint64_t* fullB = accEmpty + KF_NACC;
+  uint32_t* tmem_slot = (uint32_t*)(fullB + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cls = blockIdx.x & 3, p0 = cls >> 1, p1 = cls & 1;   // parity class of this CTA
+  const int cta = blockIdx.x >> 2, ncta = gridDim.x >> 2;        // index / count of the CTAs serving this class
+  const int nch = G.nch;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < KU_SA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, 2); }   // output planes q - p0 + 1, q - p0
+    for (int i = 0; i < KF_NACC; ++i) { mbar_init(accFull + i, 1); mbar_init(accEmpty + i, 4); }
+    mbar_init(fullB, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_w); }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nitems = G.B * G.n1tiles * G.n2tiles * G.nzr;
+
+  // input planes of output plane z: z + da and z + da + 1 with da = p0 - 1 (d0 taps k0 = p0 and p0 + 1)
+  const int da = p0 - 1;
+#define KU_DECODE(item)                                                          \
+  int t_ = (item);                                                                \
+  const int zr = t_ % G.nzr; t_ /= G.nzr;                                         \
+  const int t2 = t_ % G.n2tiles; t_ /= G.n2tiles;                                 \
+  const int t1 = t_ % G.n1tiles;                                                  \
+  const int b = t_ / G.n1tiles;                                                   \
+  const int x0 = t2 * KF_OUT2, y0 = t1 * KF_TM1;                                  \
+  const int zs = zr * G.zlen, ze = min(G.D0, zs + G.zlen);                        \
+  const int pmin = max(zs + da, 0), pmax = min(ze + da, G.D0 - 1);                \
+  (void)x0; (void)y0; (void)b; (void)pmax;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      mbar_expect_tx(fullB, (uint32_t)(4 * nch * KF_BTILE_BYTES));
+      for (int t = 0; t < 4; ++t)
+        for (int ch = 0; ch < nch; ++ch)
+          tma_load_2d(&map_w, fullB, sB + (size_t)(t * 2 + ch) * KF_BTILE_BYTES, 0, ((cls * 4 + t) * 2 + ch) * KF_N);
+      int seq = 0;
+      for (int item = cta; item < nitems; item += ncta) {
+        KU_DECODE(item)
+        for (int q = pmin; q <= pmax; ++q)
+          for (int ch = 0; ch < nch; ++ch, ++seq) {
+            const int slot = seq % KU_SA;
+            mbar_wait(emptyA + slot, ((seq / KU_SA) & 1) ^ 1);
+            mbar_expect_tx(fullA + slot, KF_SLAB_BYTES);
+            tma_load_5d(&map_x, fullA + slot, sA + (size_t)slot * KF_SLAB_BYTES, ch * 32, x0 - 1, y0 - 1, q, b);
+          }
+      }
+    }
+  } else if (warp <= KF_NACC) {
+    // ================================ MMA issuers: warp w owns accumulator ring slot w - 1 ================================
+    const int w = warp - 1;
+    const uint32_t idesc = make_idesc_tf32(KF_N);
+    const uint32_t a_base = desc_lo(smem_u32(sA), 16), b_base = desc_lo(smem_u32(sB), 16);
+    const uint32_t dcol = tmem_base + (uint32_t)(w * KF_N);
+    mbar_wait(fullB, 0);
+    int seq_base = 0;
+    uint32_t uses = 0;
+    for (int item = cta; item < nitems; item += ncta) {
+      KU_DECODE(item)
+      for (int z = zs + w; z < ze; z += KF_NACC) {
+        mbar_wait(accEmpty + w, (uses & 1u) ^ 1u);            // epilogue has drained this ring slot
+        tc_fence_after();
+        uint32_t acc = 0u;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {                           // d0 tap k0 = p0 + t reads plane z + da + t
+          const int q = z + da + t;
+          if (q < 0 || q >= G.D0) continue;                     // zero padding along d0
+          // slab (q, ch) is released by two arrivals (output planes q - da and q - da - 1); the one that falls outside
+          // this item's plane range is accounted for by the in-range reader
+          const int extra = t == 0 ? (z == zs ? 1 : 0) : (z == ze - 1 ? 1 : 0);
+          for (int ch = 0; ch < nch; ++ch) {
+            const int seq = seq_base + (q - pmin) * nch + ch, slot = seq % KU_SA;
+            mbar_wait(fullA + slot, (seq / KU_SA) & 1);
+            const int nks = G.nks[ch];
+            if (elect_one()) {
+              // d1 taps k1 = p1 + k1i: operand view starts k1 rows of 16 voxels into the slab
+              uint32_t alo = a_base + (uint32_t)slot * (KF_SLAB_BYTES >> 4) + (uint32_t)p1 * (uint32_t)(KF_TM2 * 128 >> 4);
+              uint32_t blo = b_base + (uint32_t)((t * 2) * 2 + ch) * (KF_BTILE_BYTES >> 4);
+#pragma unroll
+              for (int k1i = 0; k1i < 2; ++k1i) {
+                if (nks == 4) umma_chain_k<4>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+                else if (nks == 3) umma_chain_k<3>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+                else if (nks == 2) umma_chain_k<2>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+                else umma_chain_k<1>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+                acc = 1u;
+                alo += (uint32_t)(KF_TM2 * 128 >> 4);
+                blo += (uint32_t)(2 * KF_BTILE_BYTES >> 4);       // tile index (t * 2 + k1i) * 2 + ch
+              }
+              umma_commit(emptyA + slot);
+            }
+            acc = 1u;
+            if (lane == 0 && extra) mbar_arrive(emptyA + slot);
+            __syncwarp();
+          }
+        }
+        if (elect_one()) umma_commit(accFull + w);
+        __syncwarp();
+        ++uses;
+      }
+      seq_base += (pmax - pmin + 1) * nch;
+    }
+  } else {
+    // ================================ epilogue (last eight warps: two sets of four) ================================
+    const int q4 = warp & 3;                        // TMEM lane quarter of this warp
+    const int h = (warp - (KF_NACC + 1)) >> 2;      // epilogue set 0 / 1
+    const int r = q4 * 32 + lane;                   // GEMM row = (d1 row r / 16, input column r % 16)
+    const int xin = r & 15, yl = r >> 4;
+    const long long F1 = 2LL * G.D1, F2 = 2LL * G.D2;
+    uint32_t par = 0;                               // phase bit per ring slot
+    for (int item = cta; item < nitems; item += ncta) {
+      KU_DECODE(item)
+      const int i1 = y0 + yl, i2 = x0 - 1 + xin;
+      const bool store_ok = xin >= 1 && xin <= KF_OUT2 && i1 < G.D1 && i2 < G.D2;
+      for (int z = zs + h; z < ze; z += 2) {
+        const int slot = (z - zs) & (KF_NACC - 1);
+        mbar_wait(accFull + slot, (par >> slot) & 1u);
+        par ^= 1u << slot;
+        tc_fence_after();
+        // two adjacent full-resolution voxels (2 i2, 2 i2 + 1) of row (2 z + p0, 2 i1 + p1): 48 contiguous floats
+        float* orow = y + ((((long long)b * (2 * G.D0) + 2 * z + p0) * F1 + 2 * i1 + p1) * F2 + 2 * i2) * 24;
+        const uint32_t tbase = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(slot * KF_N);
+#pragma unroll
+        for (int cb = 0; cb < 24; cb += 8) {
+          uint32_t v0[8], v1[8], v2[8], v3[8];
+          tmem_ld8(tbase + (uint32_t)cb, v0);              // (p2, k2) = (0, 0)
+          tmem_ld8(tbase + (uint32_t)(24 + cb), v1);       // (0, 1)
+          tmem_ld8(tbase + (uint32_t)(48 + cb), v2);       // (1, 1)
+          tmem_ld8(tbase + (uint32_t)(72 + cb), v3);       // (1, 2)
+          tmem_ld_wait();
+          float o0[8], o1[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[e]), 1);      // Q_(0,0) at input column x - 1
+            const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(v3[e]), 1);   // Q_(1,2) at input column x + 1
+            o0[e] = left + __uint_as_float(v1[e]);
+            o1[e] = __uint_as_float(v2[e]) + right;
+          }
+          if (store_ok) {
+            *reinterpret_cast<float4*>(orow + cb) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+            *reinterpret_cast<float4*>(orow + cb + 4) = make_float4(o0[4], o0[5], o0[6], o0[7]);
+            *reinterpret_cast<float4*>(orow + 24 + cb) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+            *reinterpret_cast<float4*>(orow + 24 + cb + 4) = make_float4(o1[4], o1[5], o1[6], o1[7]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(accEmpty + slot);
+      }
+    }
+  }
+#undef KU_DECODE
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// packed kernels of conv3d_tc_up_k2n_kernel from the effective kernels weff (8, 27, Cup, 24) of up_weights_kernel:
+//   wp[cls = p0 * 2 + p1][t][k1i][ch][row = g * 24 + co][s]  =  weff[p0 * 4 + p1 * 2 + p2(g)][k0 = p0 + t][k1 = p1 + k1i][k2(g)]
+//   [ch * 32 + s][co],  g = 0..3 <-> (p2, k2) = (0,0), (0,1), (1,1), (1,2);  zero for channels >= Cup; TF32-rounded
+__global__ void pack_up_k2n_kernel(const float* __restrict__ weff, float* __restrict__ wp, int Cup, int round_rn) {
+  const long long total = 4LL * 8 * 96 * 32;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(i & 31);
+    long long r = i >> 5;
+    const int row = (int)(r % 96); r /= 96;
+    const int ch = (int)(r % 2); r /= 2;
+    const int k1i = (int)(r % 2); r /= 2;
+    const int t = (int)(r % 2);
+    const int cls = (int)(r / 2);
+    const int p0 = cls >> 1, p1 = cls & 1;
+    const int g = row / 24, co = row % 24;
+    const int p2 = g >> 1, k2 = g == 0 ? 0 : (g == 3 ? 2 : 1);
+    const int ci = ch * 32 + s;
+    float val = 0.f;
+    if (ci < Cup) {
+      const int par = p0 * 4 + p1 * 2 + p2, tap = ((p0 + t) * 3 + (p1 + k1i)) * 3 + k2;
+      val = weff[(((long long)par * 27 + tap) * Cup + ci) * 24 + co];
+    }
+    if (round_rn) {
+      uint32_t u;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(val));
+      val = __uint_as_float(u);
+    }
+    wp[i] = val;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // weight gradient on tcgen05:  dW[k0][k1][k2][ci][co] += sum_v X[v + (k0,k1,k2) - 1][ci] * dY[v][co]
 //
 //   GEMM   D[M x N] += A[M x K] * B[N x K]^T   with K = 8 voxels per instruction, both operands MN-major:
@@ -2437,6 +2666,64 @@ int ssr_conv3d_fwd_tc_up(const float* low, int Cup, const float* wp8, float* y, 
 int ssr_conv3d_dgrad_tc_up(const float* dy, int Cout_layer, const float* wp8, float* dlow, int B, int d0, int d1, int d2,
                            int Cup, void* stream) {
   return conv3d_tc_up_impl(2, dy, Cout_layer, wp8, dlow, B, d0, d1, d2, Cup, stream);
+}
+
+// k2n layout of ssr_conv3d_fwd_tc_up for Cout == 24, Cup <= 64 (the last decoder level): wpk from
+// ssr_conv3d_pack_up_k2n (4 * 8 * 96 * 32 floats).  Same result contract as ssr_conv3d_fwd_tc_up.
+int ssr_conv3d_pack_up_k2n(const float* weff, float* wpk, int Cup, void* stream) {
+  SSR_CHECK_ARG(weff && wpk && Cup > 0 && Cup <= 64 && Cup % 8 == 0, "pack_up_k2n args");
+  pack_up_k2n_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(weff, wpk, Cup, getenv("SSR_PACK_TRUNC") ? 0 : 1);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+int ssr_conv3d_fwd_tc_up_k2n(const float* low, int Cup, const float* wpk, float* y, int B, int D0, int D1, int D2, int Cout,
+                             void* stream) {
+  SSR_CHECK_ARG(low && wpk && y && B > 0 && D0 > 0 && D1 > 0 && D2 > 0, "pointers/shape");
+  SSR_CHECK_ARG(Cout == 24 && Cup > 0 && Cup <= 64 && Cup % 8 == 0, "the k2n parity forward needs Cout == 24 and Cup <= 64");
+  SSR_CHECK_ARG(((uintptr_t)low & 15) == 0 && ((uintptr_t)wpk & 127) == 0 && ((uintptr_t)y & 15) == 0, "alignment");
+  KuGeom G;
+  memset(&G, 0, sizeof(G));
+  G.B = B; G.D0 = D0; G.D1 = D1; G.D2 = D2; G.Cout = Cout;
+  G.nch = (Cup + 31) / 32;
+  for (int ch = 0; ch < G.nch; ++ch) G.nks[ch] = ((Cup - ch * 32 < 32 ? Cup - ch * 32 : 32) + 7) / 8;
+  G.n1tiles = (D1 + KF_TM1 - 1) / KF_TM1; G.n2tiles = (D2 + KF_OUT2 - 1) / KF_OUT2;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    SSR_CHECK_CUDA(cudaGetDevice(&dev));
+    SSR_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int per_class = num_sms / 4;               // CTAs per parity class
+  SSR_CHECK_ARG(per_class >= 1, "device too small");
+  const long long cols = (long long)B * G.n1tiles * G.n2tiles;
+  long long best = -1; int best_nzr = 1;
+  for (int nzr = 1; nzr <= D0; ++nzr) {
+    const int zlen = (D0 + nzr - 1) / nzr;
+    if (zlen < 8 && nzr > 1) break;
+    const long long items = cols * ((D0 + zlen - 1) / zlen);
+    const long long cost = ((items + per_class - 1) / per_class) * (zlen + 1);
+    if (best < 0 || cost < best) { best = cost; best_nzr = (D0 + zlen - 1) / zlen; G.zlen = zlen; }
+  }
+  G.nzr = best_nzr;
+  CUtensorMap mx, mw;
+  int rc = make_map_act(&mx, low, Cup, B, D0, D1, D2, KF_TM1 + 2, CU_TENSOR_MAP_SWIZZLE_128B, KF_TM2);
+  if (rc) return rc;
+  rc = make_map_w(&mw, wpk, 4LL * 8 * KF_N, KF_N);
+  if (rc) return rc;
+  const size_t smem = 1024 + 8 * (size_t)KF_BTILE_BYTES + (size_t)KU_SA * KF_SLAB_BYTES + 32 * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_up_k2n_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const long long nitems = cols * G.nzr;
+  SSR_CHECK_ARG(nitems < (1LL << 31), "grid too large");
+  long long ncta = nitems < per_class ? nitems : per_class;
+  conv3d_tc_up_k2n_kernel<<<(unsigned)(4 * ncta), 416, smem, (cudaStream_t)stream>>>(mx, mw, y, G);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
 }
 
 // wskip (27, Cskip, Cout) = skip part of w (27, Cskip + Cup, Cout); weff (8, 27, Cup, Cout) = effective kernels of the

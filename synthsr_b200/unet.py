@@ -84,6 +84,10 @@ class UNet3D:
         # low-resolution tensor (conv3d_tc_up_kernel): levels whose low-resolution grid is at least up_min_dim wide
         self.up_parity = conv_impl == 'tc' and os.environ.get('SSR_NO_UP_PARITY') is None
         self.up_min_dim = int(os.environ.get('SSR_UP_MIN_DIM', '16'))
+        # last decoder level: forward of the upsampled part in the k2n layout (conv3d_tc_up_k2n_kernel).  WORK IN PROGRESS:
+        # the kernel does not reproduce the parity forward yet, so it is opt-in and nothing
+        # depends on it
+        self.up_k2n = os.environ.get('SSR_UP_K2N') is not None
         # weight gradient of those layers from the low-resolution tensor too (the upsampled tensor is never materialised)
         self.up_wgrad = self.up_parity and os.environ.get('SSR_NO_UP_WGRAD') is None
         self.epi_fusion = self.fwd_k2n and os.environ.get('SSR_NO_EPI_FUSION') is None
@@ -288,7 +292,13 @@ class UNet3D:
     def _conv_fwd_up_impl(self, name, l, act):
         st, F, B = stream_ptr(), self.feats, self.B
         u = self._up_state(l)
-        lib.ssr_conv3d_fwd_tc_up(self.vlow[l], F[l + 1], self._up_packs(l, 'fwd8'), self.g0[l], B, *self.ldims[l + 1], F[l], st)
+        if self._up_k2n_ok(l):
+            if not self._up_valid:
+                self._up_weights_all(st)
+            lib.ssr_conv3d_fwd_tc_up_k2n(self.vlow[l], F[l + 1], u['wpk'], self.g0[l], B, *self.ldims[l + 1], F[l], st)
+        else:
+            lib.ssr_conv3d_fwd_tc_up(self.vlow[l], F[l + 1], self._up_packs(l, 'fwd8'), self.g0[l], B, *self.ldims[l + 1],
+                                     F[l], st)
         if self.fwd_k2n and F[l] <= 32:
             wp = self._packed_w(name, 2, F[l], 0, F[l], tag='skip', src=u['wskip'])
             lib.ssr_conv3d_fwd_tc_k2n_part(self.h1[l], F[l], 0, F[l], wp, self.p[name + '/bias'], self.g0[l], B,
@@ -450,7 +460,14 @@ class UNet3D:
             u = self._up_state(l)
             lib.ssr_conv3d_up_weights(self.p['unet_conv_uparm_%d_0/kernel' % (L + (L - 2 - l))], F[l], F[l + 1], F[l], u['wskip'],
                                       u['weff'], st)
+            if self._up_k2n_ok(l):
+                if 'wpk' not in u:
+                    u['wpk'] = torch.empty(4 * 8 * 96 * 32, dtype=torch.float32, device=self.device)
+                lib.ssr_conv3d_pack_up_k2n(u['weff'], u['wpk'], F[l + 1], st)
         self._up_valid = True
+
+    def _up_k2n_ok(self, l):
+        return self.up_k2n and self.fwd_k2n and self.feats[l] == 24 and self.feats[l + 1] <= 64
 
     def _up_packs(self, l, which):
         """packed weights of the parity kernels of level l: 'fwd8' (mode 0 per class) or 'dgr8' (mode 1 per class)."""
