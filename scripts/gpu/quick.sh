@@ -1,4 +1,3 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 200 python scripts/ku_diag.py > gpurun_out/ku_diag.txt 2>&1
-head -60 gpurun_out/ku_diag.txt
+# scratch: the test subset / A-B of the change being worked on
+timeout 70 python -m pytest tests -m gpu -q -x 2>&1 | tail -4

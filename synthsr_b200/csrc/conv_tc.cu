@@ -1274,7 +1274,7 @@ conv3d_tc_up_k2n_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   const int nch = G.nch;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < KU_SA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, 2); }   // output planes q - p0 + 1, q - p0
+    for (int i = 0; i < KU_SA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, KF_NACC); }   // every issuing warp releases every slab
     for (int i = 0; i < KF_NACC; ++i) { mbar_init(accFull + i, 1); mbar_init(accEmpty + i, 4); }
     mbar_init(fullB, 1);
     fence_barrier_init();
@@ -1322,29 +1322,34 @@ conv3d_tc_up_k2n_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     }
   } else if (warp <= KF_NACC) {
     // ================================ MMA issuers: warp w owns accumulator ring slot w - 1 ================================
+    // Every issuing warp walks EVERY slab in producer order (and releases the ones it does not read): a slab is read by
+    // only two of the four warps here, and a warp that skipped a slot's earlier phases could not tell them apart from the
+    // one it needs (mbarrier parity waits alias every other phase).
     const int w = warp - 1;
     const uint32_t idesc = make_idesc_tf32(KF_N);
     const uint32_t a_base = desc_lo(smem_u32(sA), 16), b_base = desc_lo(smem_u32(sB), 16);
     const uint32_t dcol = tmem_base + (uint32_t)(w * KF_N);
     mbar_wait(fullB, 0);
-    int seq_base = 0;
-    uint32_t uses = 0;
+    int seq = 0;
+    uint32_t uses = 0, acc = 0u;
     for (int item = cta; item < nitems; item += ncta) {
       KU_DECODE(item)
-      for (int z = zs + w; z < ze; z += KF_NACC) {
-        mbar_wait(accEmpty + w, (uses & 1u) ^ 1u);            // epilogue has drained this ring slot
-        tc_fence_after();
-        uint32_t acc = 0u;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {                           // d0 tap k0 = p0 + t reads plane z + da + t
-          const int q = z + da + t;
-          if (q < 0 || q >= G.D0) continue;                     // zero padding along d0
-          // slab (q, ch) is released by two arrivals (output planes q - da and q - da - 1); the one that falls outside
-          // this item's plane range is accounted for by the in-range reader
-          const int extra = t == 0 ? (z == zs ? 1 : 0) : (z == ze - 1 ? 1 : 0);
-          for (int ch = 0; ch < nch; ++ch) {
-            const int seq = seq_base + (q - pmin) * nch + ch, slot = seq % KU_SA;
-            mbar_wait(fullA + slot, (seq / KU_SA) & 1);
+      for (int q = pmin; q <= pmax; ++q) {
+        // readers of plane q: output plane q - da through its first d0 tap (t = 0), q - da - 1 through its second (t = 1)
+        int z = -1, t = 0;
+        const int z1 = q - da, z2 = q - da - 1;
+        if (z1 >= zs && z1 < ze && ((z1 - zs) & (KF_NACC - 1)) == w) { z = z1; t = 0; }
+        if (z2 >= zs && z2 < ze && ((z2 - zs) & (KF_NACC - 1)) == w) { z = z2; t = 1; }
+        for (int ch = 0; ch < nch; ++ch, ++seq) {
+          const int slot = seq % KU_SA;
+          mbar_wait(fullA + slot, (seq / KU_SA) & 1);
+          if (z >= 0) {                                           // warp-uniform
+            // first chain of output plane z: its t = 0 slab, or the t = 1 slab when plane z + da lies outside the volume
+            if (ch == 0 && (t == 0 || z + da < 0)) {
+              mbar_wait(accEmpty + w, (uses & 1u) ^ 1u);          // epilogue has drained this ring slot
+              tc_fence_after();
+              acc = 0u;
+            }
             const int nks = G.nks[ch];
             if (elect_one()) {
               // d1 taps k1 = p1 + k1i: operand view starts k1 rows of 16 voxels into the slab
@@ -1363,15 +1368,17 @@ conv3d_tc_up_k2n_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
               umma_commit(emptyA + slot);
             }
             acc = 1u;
-            if (lane == 0 && extra) mbar_arrive(emptyA + slot);
-            __syncwarp();
+            // last chain of output plane z: its t = 1 slab, or the t = 0 slab when plane z + da + 1 lies outside the volume
+            if (ch == nch - 1 && (t == 1 || z + da + 1 > G.D0 - 1)) {
+              if (elect_one()) umma_commit(accFull + w);
+              ++uses;
+            }
+          } else if (lane == 0) {
+            mbar_arrive(emptyA + slot);                           // not read by this warp: release immediately
           }
+          __syncwarp();
         }
-        if (elect_one()) umma_commit(accFull + w);
-        __syncwarp();
-        ++uses;
       }
-      seq_base += (pmax - pmin + 1) * nch;
     }
   } else {
     // ================================ epilogue (last eight warps: two sets of four) ================================

@@ -84,10 +84,8 @@ class UNet3D:
         # low-resolution tensor (conv3d_tc_up_kernel): levels whose low-resolution grid is at least up_min_dim wide
         self.up_parity = conv_impl == 'tc' and os.environ.get('SSR_NO_UP_PARITY') is None
         self.up_min_dim = int(os.environ.get('SSR_UP_MIN_DIM', '16'))
-        # last decoder level: forward of the upsampled part in the k2n layout (conv3d_tc_up_k2n_kernel).  WORK IN PROGRESS:
-        # the kernel does not reproduce the parity forward yet, so it is opt-in and nothing
-        # depends on it
-        self.up_k2n = os.environ.get('SSR_UP_K2N') is not None
+        # last decoder level: forward of the upsampled part in the k2n layout (conv3d_tc_up_k2n_kernel)
+        self.up_k2n = os.environ.get('SSR_NO_UP_K2N') is None
         # weight gradient of those layers from the low-resolution tensor too (the upsampled tensor is never materialised)
         self.up_wgrad = self.up_parity and os.environ.get('SSR_NO_UP_WGRAD') is None
         self.epi_fusion = self.fwd_k2n and os.environ.get('SSR_NO_EPI_FUSION') is None

@@ -544,7 +544,7 @@ def test_tc_up_parity_kernels_match_float64():
         ya = ya.permute(0, 2, 3, 4, 1).reshape(nf, co)
         err = (y.double().cpu() - ya).abs().max().item() / ya.abs().max().item()
         assert err < 2e-5, ('fwd-up rounded', dl, cu, co, err)
-        if co == 24 and cu <= 64 and os.environ.get('SSR_UP_K2N'):   # work in progress (opt-in): the k2n layout of the same forward
+        if co == 24 and cu <= 64:       # the k2n layout of the same forward (d2 parity and its taps in N, resident kernels)
             wpk = torch.empty(4 * 8 * 96 * 32, device='cuda')
             lib.ssr_conv3d_pack_up_k2n(weff, wpk, cu, st)
             yk = torch.full((nf, co), float('nan'), device='cuda')
