@@ -475,7 +475,8 @@ def test_pool_bn_bwd_equals_maxpool_bwd_then_bn_bwd():
             res.append((dx, dg, db, dbias))
         for a, b_, name in zip(res[0], res[1], ('dx', 'dgamma', 'dbeta', 'dbias')):
             err = (a - b_).abs().max().item() / (a.abs().max().item() + 1e-30)
-            assert err < 2e-6, (name, B, d, C, err)
+            # dbias: float atomics of block partials in launch-dependent order (round-off of the sum of magnitudes)
+            assert err < (2e-5 if name == 'dbias' else 2e-6), (name, B, d, C, err)
 
 
 def _parity_taps(p, k):
@@ -748,8 +749,14 @@ def test_head_bn_sums_match_direct_reductions():
                                          L, metric, None, None, xdot, sums2, st)
             torch.cuda.synchronize()
             outs.append((pred, dfeat, dw, db, loss, sums2))
-        for a, b_ in zip(outs[0][:5], outs[1][:5]):
-            assert torch.allclose(a, b_, rtol=1e-5, atol=1e-8)
+        # pred / dfeat: same arithmetic per voxel.  dw / db are sums of +-|g| terms accumulated with float atomics in a
+        # launch-dependent order: they agree to float round-off of the SUM OF MAGNITUDES (sum |g| <= ~3 here), not of the
+        # possibly cancelling totals -- an rtol-only comparison of those is flaky
+        assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-6, atol=1e-7), 'pred'
+        assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-6, atol=1e-12), 'dfeat'
+        assert torch.allclose(outs[0][2], outs[1][2], rtol=1e-4, atol=5e-6), 'dw'
+        assert torch.allclose(outs[0][3], outs[1][3], rtol=1e-4, atol=5e-6), 'db'
+        assert torch.allclose(outs[0][4], outs[1][4], rtol=1e-9, atol=1e-12), 'loss'
         dfd = outs[1][1].double()
         xhat = (feat.double() - stats[:C].double()) * stats[C:2 * C].double()
         ref = torch.cat([dfd.sum(0), (dfd * xhat).sum(0)])
