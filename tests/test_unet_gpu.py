@@ -616,7 +616,7 @@ def test_tc_step_parity_path_equals_materialised_upsampling():
         finally:
             os.environ.pop('SSR_NO_UP_PARITY', None)
         assert bool(net.up_levels) == parity
-        loss = net.loss_and_grad(image, target, metric='l2')       # continuous gradient (the L1 sign is not)
+        loss = net.loss_and_grad(image, target)
         torch.cuda.synchronize()
         out.append((loss.item(), net.grads.clone(), net.pred.clone()))
     (l1, g1, p1), (l2, g2, p2) = out
