@@ -567,36 +567,22 @@ def labels_to_image(cfg, inputs, draws, return_intermediates=False):
         # --- RandomCrop (layers.py:252-270) ---
         cs = r['crop_shape']
         if cs != shape:
-            ci = [int(v) for v in draws['crop_idx'][b]]
-            lab = lab[ci[0]:ci[0] + cs[0], ci[1]:ci[1] + cs[1], ci[2]:ci[2] + cs[2]]
+            lab = random_crop(lab, draws['crop_idx'][b], cs)
             if real is not None:
-                real = real[ci[0]:ci[0] + cs[0], ci[1]:ci[1] + cs[1], ci[2]:ci[2] + cs[2]]
+                real = random_crop(real, draws['crop_idx'][b], cs)
         # --- RandomFlip axis 0, swap labels (layers.py:362-427) ---
         if cfg.get('flipping', True):
             flip = bool(draws['flip'][b])
-            if flip and n_neutral != len(gen_labels):
-                n_lab = len(gen_labels)
-                split = np.split(gen_labels, [n_neutral, n_neutral + int((n_lab - n_neutral) / 2)])   # :382
-                lut = get_mapping_lut(gen_labels, np.concatenate((split[0], split[2], split[1])))
-                lab = lut[lab]
-            if flip:
-                lab = lab[::-1]
-                if real is not None:
-                    real = real[::-1]
+            lab = random_flip(lab, flip, gen_labels, n_neutral, swap=True)
+            if real is not None:
+                real = random_flip(real, flip, gen_labels, n_neutral, swap=False)
         lab = np.ascontiguousarray(lab)
         if b == 0:
             inter['labels'] = lab.copy()
         # --- SampleConditionalGMM (layers.py:472-498) ---
         C = r['n_channels']
-        max_label = int(np.max(gen_labels)) + 1
-        chans = []
-        for i in range(C):
-            mlut = np.zeros(max_label, dtype=f32)
-            slut = np.zeros(max_label, dtype=f32)
-            mlut[gen_labels] = means_in[b, :, i]
-            slut[gen_labels] = stds_in[b, :, i]
-            noise = np.asarray(draws['gmm_normal'][b, ..., i], dtype=f32)
-            chans.append(((slut[lab] * noise).astype(f32) + mlut[lab]).astype(f32))             # :498
+        chans = [sample_conditional_gmm(lab, means_in[:, :, i], stds_in[:, :, i],
+                                        np.asarray(draws['gmm_normal'][b, ..., i], dtype=f32), gen_labels) for i in range(C)]
         if b == 0:
             inter['gmm'] = np.stack(chans, -1)
         # --- per-channel processing (labels_to_image_model.py:175-242) ---
@@ -679,6 +665,40 @@ def labels_to_image(cfg, inputs, draws, return_intermediates=False):
     if return_intermediates:
         return image, target, inter
     return image, target
+
+
+def sample_conditional_gmm(lab, means, stds, noise, gen_labels):
+    """ext/lab2im/layers.py:480-498 for one channel of one example: lab [X,Y,Z] int, means / stds [B, L] (the WHOLE batch:
+    tf.scatter_nd adds the tables of all batch elements into one, which is then tiled over the batch -- with batchsize 1
+    that is the per-example table), noise [X,Y,Z] standard normals.  Unlisted label values get mean = std = 0."""
+    means, stds = np.asarray(means, dtype=f32), np.asarray(stds, dtype=f32)
+    max_label = int(np.max(gen_labels)) + 1
+    msum, ssum = means[0].copy(), stds[0].copy()
+    for bb in range(1, means.shape[0]):
+        msum = (msum + means[bb]).astype(f32)
+        ssum = (ssum + stds[bb]).astype(f32)
+    mlut = np.zeros(max_label, dtype=f32)
+    slut = np.zeros(max_label, dtype=f32)
+    mlut[gen_labels] = msum
+    slut[gen_labels] = ssum
+    return ((slut[lab] * noise).astype(f32) + mlut[lab]).astype(f32)                            # :498
+
+
+def random_crop(vol, crop_idx, crop_shape):
+    """ext/lab2im/layers.py:266-270: tf.slice at the (truncated) per-example offsets, same for every input."""
+    ci = [int(v) for v in crop_idx]
+    return vol[ci[0]:ci[0] + crop_shape[0], ci[1]:ci[1] + crop_shape[1], ci[2]:ci[2] + crop_shape[2]]
+
+
+def random_flip(vol, flip, label_list, n_neutral, swap):
+    """ext/lab2im/layers.py:362-427 for flip_axis 0: swap the right / left label values (inputs with swap_labels) when the
+    example is flipped an odd number of times, then reverse axis 0."""
+    if flip and swap and n_neutral != len(label_list):
+        n_lab = len(label_list)
+        split = np.split(np.asarray(label_list), [n_neutral, n_neutral + int((n_lab - n_neutral) / 2)])   # :382
+        lut = get_mapping_lut(np.asarray(label_list), np.concatenate((split[0], split[2], split[1])))
+        vol = lut[vol]
+    return vol[::-1] if flip else vol
 
 
 def _mm4(a, b):

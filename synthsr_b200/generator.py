@@ -287,6 +287,26 @@ class GeneratorPlan:
         return list(self.output_shape) + [self.n_target_channels]
 
 
+def gmm_luts(means, stds, generation_labels, lut_len):
+    """label -> (mean, std) look-up tables [B, lut_len] of one channel, as SampleConditionalGMM builds them
+    (ext/lab2im/layers.py:480-497): unlisted label values get 0.  Reference behaviour kept on purpose: the layer scatters
+    the means of ALL batch elements into ONE table with tf.scatter_nd, which ADDS duplicate indices, and tiles that table
+    over the batch -- for batchsize > 1 every example is sampled from the SUM over the batch of the drawn parameters
+    (reproduced by executing the reference layer, tests/golden/make_reference_layer_goldens.py).  With batchsize 1, the
+    reference's default and what every data-parallel rank runs, this is the plain per-example table."""
+    means, stds = np.asarray(means, dtype=f32), np.asarray(stds, dtype=f32)
+    B = means.shape[0]
+    msum, ssum = means[0].copy(), stds[0].copy()
+    for b in range(1, B):                                  # float32 accumulation in scatter order
+        msum = (msum + means[b]).astype(f32)
+        ssum = (ssum + stds[b]).astype(f32)
+    ml = np.zeros((B, lut_len), dtype=f32)
+    sl = np.zeros((B, lut_len), dtype=f32)
+    ml[:, generation_labels] = msum[None]
+    sl[:, generation_labels] = ssum[None]
+    return ml, sl
+
+
 class _Staging:
     """Pinned host buffers + one device buffer: all small per-step inputs go to the GPU in a single async copy.
     The host side is a ring of NBUF pinned buffers, each guarded by the event of its last copy: the host may enqueue
@@ -398,10 +418,7 @@ class SynthGenerator:
         chan = []
         for i in range(p.n_channels):
             c = {}
-            ml = np.zeros((B, p.lut_len), dtype=f32)
-            sl = np.zeros((B, p.lut_len), dtype=f32)
-            ml[:, p.generation_labels] = means[:, :, i]
-            sl[:, p.generation_labels] = stds[:, :, i]
+            ml, sl = gmm_luts(means[:, :, i], stds[:, :, i], p.generation_labels, p.lut_len)
             c['mean'], c['std'] = sg.put(ml), sg.put(sl)
             c['bias'] = None
             c['apply'] = 0
