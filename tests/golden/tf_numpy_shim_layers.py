@@ -84,6 +84,23 @@ def install(random_queue):
         return self.call(inputs, **kwargs)
 
     Layer.__call__ = layer_call
+    def matmul(a, b):
+        """2-D as in the base shim; batched [B,n,k] @ [B,k,m] with the same pinned left-to-right float32 accumulation."""
+        a, b = _np(a), _np(b)
+        if a.ndim == 2:
+            return base._matmul(a, b)
+        return _t(np.stack([_np(base._matmul(a[i], b[i])) for i in range(a.shape[0])]))
+
+    def diag(x):
+        x = _np(x)
+        out = np.zeros(x.shape + (x.shape[-1],), x.dtype)
+        for i in range(x.shape[-1]):
+            out[..., i, i] = x[..., i]
+        return _t(out)
+
+    tf.matmul = matmul
+    tf.linalg = types.SimpleNamespace(diag=diag)
+    tf.eye = lambda n, dtype='float32': _t(np.eye(int(n), dtype=np.float32))
     tf.split = split
     tf.scatter_nd = scatter_nd
     tf.slice = slice_

@@ -84,3 +84,41 @@ def test_gaussian_blur_matches_reference_layer():
     np.testing.assert_allclose(OG.gaussian_blur(x, .5), G['blur_out_05'][0, ..., 0], rtol=0, atol=5e-7)
     got = OG.gaussian_blur(x, list(G['blur_sigma']), G['blur_mult'])
     np.testing.assert_allclose(got, G['blur_out_acq'][0, ..., 0], rtol=0, atol=5e-7)
+
+
+S = np.load(os.path.join(HERE, 'golden', 'reference_spatial.npz'))
+
+
+def test_sample_affine_transform_bit_exact():
+    """ext/lab2im/utils.py sample_affine_transform / create_rotation_transform / create_shearing_transform executed on the
+    shim with the training() bounds (rotation, shearing, scaling, translation draws injected): the oracle's and the
+    product's affine builders give the same 4x4 matrices bit for bit."""
+    from synthsr_b200 import draws as D
+    for b in range(3):
+        args = (S['aff_rotation'][b], S['aff_shearing'][b], S['aff_scaling'][b], S['aff_translation'][b])
+        np.testing.assert_array_equal(OG.build_affine(*args), S['aff_out'][b])
+        np.testing.assert_array_equal(D.build_affine(*args), S['aff_out'][b])
+
+
+def test_random_spatial_deformation_layer_bit_exact():
+    """the complete RandomSpatialDeformation layer of the reference (layers.py:161-211: affine sampling, SVF draw -> Resize ->
+    VecInt -> Resize, SpatialTransformer with the non-linear field first) on labels ('nearest') and an image ('linear'),
+    plus its elastic-only and affine-only configurations."""
+    shape = list(S['rsd_labels'].shape[1:4])
+    lab_in = S['rsd_labels'][0].astype(f32)
+    assert OG.get_resample_shape(shape, .0625) == [int(v) for v in S['rsd_small_shape'][:3]]
+    draws = {'svf_std': S['rsd_svf_std'].reshape(-1)[0], 'svf_normal': S['rsd_svf_normal']}
+    field, _ = OG.random_spatial_deformation_field(draws, 0, shape, .0625)
+    aff = OG.build_affine(S['rsd_rotation'][0], S['rsd_shearing'][0], S['rsd_scaling'][0], S['rsd_translation'][0])
+    lab = OG.spatial_transformer(lab_in, aff, field, 'nearest')[..., 0].astype(np.int32)
+    img = OG.spatial_transformer(S['rsd_image'][0], aff, field, 'linear')[..., 0]
+    np.testing.assert_array_equal(lab, S['rsd_out_labels'][0, ..., 0])
+    np.testing.assert_array_equal(img, S['rsd_out_image'][0, ..., 0])
+    assert (lab != S['rsd_labels'][0, ..., 0]).mean() > .5                      # the deformation really moved the labels
+    draws = {'svf_std': S['el_svf_std'].reshape(-1)[0], 'svf_normal': S['el_svf_normal']}
+    field, _ = OG.random_spatial_deformation_field(draws, 0, shape, .0625)
+    lab = OG.transform(lab_in, field, 'nearest')[..., 0].astype(np.int32)
+    np.testing.assert_array_equal(lab, S['el_out_labels'][0, ..., 0])
+    aff = OG.build_affine(S['af_rotation'][0], S['af_shearing'][0], S['af_scaling'][0], None)
+    lab = OG.spatial_transformer(lab_in, aff, None, 'nearest')[..., 0].astype(np.int32)
+    np.testing.assert_array_equal(lab, S['af_out_labels'][0, ..., 0])
