@@ -606,6 +606,10 @@ def labels_to_image(cfg, inputs, draws, return_intermediates=False):
                     sigma = blurring_sigma_for_downsampling(r['atlas_res'], r['target_res'])     # :192
                     tgt = gaussian_blur(tgt, list(sigma))
                     tgt = resample_tensor(tgt[..., None], r['output_shape'])[..., 0]             # :195
+                    # the reference REBINDS `channel` at :194-195: when this channel is also an input, its acquisition
+                    # chain (:199-238) starts from the blurred, resampled target on the output grid, not from the
+                    # full-resolution channel (pinned by executing the graph: tests/golden/make_reference_model_goldens.py)
+                    ch = tgt
                 out_targets.append(tgt)
             if r['input_channels'][i]:
                 do_reg = r['sim_reg'][i] and (i != r['idx_first_input_channel'])

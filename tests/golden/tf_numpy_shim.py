@@ -22,6 +22,9 @@ class TensorShape(tuple):
         return TensorShape(r) if isinstance(item, slice) else r
 
 
+GRAPH_BATCH = [None]      # set by make_reference_model_goldens.py while the reference builds its graph
+
+
 class T(np.ndarray):
     """ndarray that answers the TF tensor API used by the reference."""
 
@@ -33,6 +36,8 @@ class T(np.ndarray):
         shp = np.ndarray.shape.__get__(self)
         if getattr(self, 'static_batch_unknown', False):
             return TensorShape((None,) + tuple(shp[1:]))
+        if GRAPH_BATCH[0] is not None and len(shp) >= 2 and shp[0] == GRAPH_BATCH[0]:
+            return TensorShape((None,) + tuple(shp[1:]))       # whole-graph runs: every batched tensor has batch dim None
         return TensorShape(shp)
 
     @property
@@ -149,7 +154,18 @@ def install(random_queue=None):
     tf.equal = lambda a, b: _t(_np(a) == _np(b))
     tf.where = lambda c, a=None, b=None: _t(np.where(_np(c), _np(a), _np(b)))
     tf.reduce_sum = lambda x, axis=None, keepdims=False: _t(np.sum(_np(x), axis=axis, keepdims=keepdims, dtype=_np(x).dtype))
-    tf.map_fn = lambda fn, elems, dtype=None: _t(np.stack([_np(fn(e)) for e in (zip(*elems) if isinstance(elems, (list, tuple)) else elems)]))
+    def map_fn(fn, elems, dtype=None):
+        saved, GRAPH_BATCH[0] = GRAPH_BATCH[0], None           # inside the mapped function the tensors have no batch dimension
+        try:
+            it = zip(*elems) if isinstance(elems, (list, tuple)) else elems
+            res = [fn(list(e)) if isinstance(e, tuple) else fn(e) for e in it]
+        finally:
+            GRAPH_BATCH[0] = saved
+        if isinstance(res[0], (list, tuple)):
+            return [_t(np.stack([_np(r[j]) for r in res])) for j in range(len(res[0]))]
+        return _t(np.stack([_np(r) for r in res]))
+
+    tf.map_fn = map_fn
     tf.math = types.SimpleNamespace(log=lambda x: _t(np.log(_np(x))), exp=tf.exp, minimum=lambda a, b: _t(np.minimum(_np(a), _np(b))),
                                     equal=tf.equal, pow=lambda a, b: _t(np.power(_np(a), _np(b))),
                                     floor=lambda x: _t(np.floor(_np(x))), ceil=lambda x: _t(np.ceil(_np(x))),

@@ -79,7 +79,9 @@ def install(random_queue):
 
     def layer_call(self, inputs, **kwargs):            # Keras Layer.__call__: build on first use from the input shapes
         if not getattr(self, 'built', False):
-            shp = [tuple(_np(v).shape) for v in inputs] if isinstance(inputs, (list, tuple)) else tuple(_np(inputs).shape)
+            def shape_of(v):                             # Keras hands build() the STATIC shape (batch None in a graph)
+                return tuple(v.get_shape()) if isinstance(v, T) else tuple(_np(v).shape)
+            shp = [shape_of(v) for v in inputs] if isinstance(inputs, (list, tuple)) else shape_of(inputs)
             self.build(shp)
         return self.call(inputs, **kwargs)
 
