@@ -271,11 +271,18 @@ class GeneratorPlan:
         # max_res = 9 mm -> separable 1-D kernels of a fixed window (ext/lab2im/layers.py:808, edit_tensors.py:124)
         self.dyn_max_sigma = 0.75 * 9. / np.asarray(self.atlas_res, dtype=np.float64)
         self.dyn_window = [int(w) for w in (np.int32(np.ceil(2.5 * self.dyn_max_sigma) / 2) * 2 + 1)]
+        # grid each input channel's acquisition chain (:199-238) runs on.  The reference REBINDS `channel` to the blurred,
+        # resampled regression target at :193-195, so a channel that is both a target and an input continues on the OUTPUT
+        # grid when target_res != atlas_res (pinned by executing the reference graph: tests/golden/reference_model.npz, B/E)
+        self.chan_grid = []
+        for i in range(self.n_channels):
+            rebound = (not self.use_real_image) and i in self.output_channel and self.crop_shape != self.output_shape
+            self.chan_grid.append(list(self.output_shape) if rebound else list(self.crop_shape))
         self.down_shape = []
         for i in range(self.n_channels):
-            ds = list(self.crop_shape)
+            ds = list(self.chan_grid[i])                                       # edit_tensors.py:292-299 (tensor shape)
             if self.downsample[i] and list(self.data_res[i]) != list(self.atlas_res):
-                ds = [int(self.crop_shape[k] * float(self.atlas_res[k]) / float(self.data_res[i][k])) for k in range(3)]
+                ds = [int(self.chan_grid[i][k] * float(self.atlas_res[k]) / float(self.data_res[i][k])) for k in range(3)]
             self.down_shape.append(ds)
 
     @property
@@ -356,6 +363,9 @@ class SynthGenerator:
         self.plan = plan
         self.B = int(batchsize)
         self.device = torch.device(device)
+        if self.device.type != 'cuda' and not getattr(lib, 'host_emulation', False):
+            raise RuntimeError('SynthGenerator needs a CUDA device: there is no CPU path (the CPU suite swaps `lib` for '
+                               'tests/host_emulator.py to exercise the orchestration only)')
         p = plan
         B = self.B
         dev = self.device
@@ -392,7 +402,7 @@ class SynthGenerator:
         st = stream_ptr()
         sg = self.stage
         sg.reset()
-        assert labels.dtype == torch.int32 and labels.is_cuda and labels.is_contiguous()
+        assert labels.dtype == torch.int32 and labels.device.type == self.device.type and labels.is_contiguous()
         assert list(labels.shape) == [B] + p.labels_shape, (labels.shape, p.labels_shape)
         means = np.asarray(means, dtype=f32).reshape(B, len(p.generation_labels), p.n_channels)
         stds = np.asarray(stds, dtype=f32).reshape(B, len(p.generation_labels), p.n_channels)
@@ -436,7 +446,7 @@ class SynthGenerator:
                 sig = dynamic_sigma(p.atlas_res, draws['res_%d' % i], draws['thick_%d' % i], .42)
                 ks = dynamic_kernels(sig, p.dyn_window, draws['blur_mult_dyn_%d' % i] if jit else None)
                 c['kdyn'] = [None if k is None else sg.put(k) for k in ks]   # [B, window] per axis
-                c['mimic'] = sg.put(np.stack([mimic_zooms(p.crop_shape, p.atlas_res, draws['res_%d' % i][b],
+                c['mimic'] = sg.put(np.stack([mimic_zooms(p.chan_grid[i], p.atlas_res, draws['res_%d' % i][b],
                                                           p.output_shape) for b in range(B)]))
                 c['kacq'] = []
             elif p.input_channels[i]:
@@ -454,7 +464,7 @@ class SynthGenerator:
                                            translation=draws['reg_err_trans_%d' % i][b]) for b in range(B)]
                     c['T'] = sg.put(np.stack(T))
                     c['Tie'] = sg.put(np.stack([D.matmul4(Terr[b], Tinv[b]) for b in range(B)]))
-                if p.build_reliability_maps and p.down_shape[i] != p.crop_shape and not p.randomise_res[i]:
+                if p.build_reliability_maps and p.down_shape[i] != p.chan_grid[i] and not p.randomise_res[i]:
                     c['rel'] = [sg.put(f) for f in reliability_factors(p.output_shape, p.down_shape[i])]
             if (not p.use_real_image) and i in p.output_channel and p.target_sigma is not None:
                 c['ktgt'] = [(sg.put(k), k.shape) for k in gaussian_kernel(list(p.target_sigma))]
@@ -480,7 +490,7 @@ class SynthGenerator:
         if keep is not None:
             keep['labels'] = self.labels.clone()
         if p.use_real_image:
-            assert real_image is not None and real_image.dtype == torch.float32 and real_image.is_cuda
+            assert real_image is not None and real_image.dtype == torch.float32 and real_image.device.type == self.device.type
             lib.ssr_warp_linear(real_image.contiguous(), self.real, aff_ptr, field_ptr, B, *g, *pad, *h, crop_ptr, *cs,
                                 flip_ptr, st)
         # ---- per-channel chain --------------------------------------------------------------------------------
@@ -494,6 +504,7 @@ class SynthGenerator:
         tgt_c = 0
         os_ = p.output_shape
         for i, c in enumerate(chan):
+            cs = p.crop_shape                                                  # GMM / bias / intensity / blur(.5): crop grid
             nptr = noise_t[i].data_ptr() if noise_t is not None else None
             bsh = p.bias_small_shape if c['bias'] else [0, 0, 0]
             lib.ssr_gmm_bias_minmax(self.labels, c['mean'], c['std'], p.lut_len, nptr, int(seed),
@@ -505,10 +516,14 @@ class SynthGenerator:
             lib.ssr_blur3d(self.raw, self.tmp_a, c['k05'], 3, 3, 3, self.minmax, c['gamma'], B, *cs, 1, 0, 1, 0, st)
             if keep is not None:
                 keep['blur_%d' % i] = self.tmp_a.clone()
+            cur = self.tmp_a
             if (not p.use_real_image) and i in p.output_channel:
+                rebound = p.input_channels[i] and p.chan_grid[i] != cs         # :193-195 `channel` now IS the target
                 for _ in range(p.output_channel.count(i)):
-                    self._emit_target(self.tmp_a, c.get('ktgt'), tgt_c, st)
+                    res = self._emit_target(self.tmp_a, c.get('ktgt'), tgt_c, st, rebound)
                     tgt_c += 1
+                if rebound:
+                    cur = res
             if not p.input_channels[i]:
                 continue
             bufs = [self.tmp_a, self.tmp_b, self.tmp_c]
@@ -516,7 +531,7 @@ class SynthGenerator:
             def free(*used):
                 return next(t for t in bufs if all(t is not u for u in used))
 
-            cur = self.tmp_a
+            cs = p.chan_grid[i]                                                # grid of this channel's acquisition chain
             if c['reg']:                                                       # :202-208
                 dst = free(cur)
                 lib.ssr_warp_linear(cur, dst, c['T'], None, B, *cs, 0, 0, 0, 0, 0, 0, None, *cs, None, st)
@@ -591,6 +606,7 @@ class SynthGenerator:
                 else:
                     lib.ssr_fill_outer3(self.image, *(rel or [None, None, None]), B, *os_, p.n_image_channels, out_c, st)
                 out_c += 1
+        cs = p.crop_shape
         if p.use_real_image:                                                   # :248-255
             lib.ssr_minmax(self.real, self.minmax, B, int(np.prod(cs)), st)
             unit = torch.ones(1, dtype=torch.float32, device=self.device)   # normalise through a 1x1x1 "stencil"
@@ -598,18 +614,26 @@ class SynthGenerator:
             self._emit_target(self.tmp_a, ktgt_real if p.target_sigma is not None else None, 0, st)
         return self.image, self.target
 
-    def _emit_target(self, src, ktgt, tgt_c, st):
+    def _emit_target(self, src, ktgt, tgt_c, st, rebound=False):
         """regression target: optional blur + linear resample to output_shape (labels_to_image_model.py:189-196)."""
         p, B = self.plan, self.B
         cs, os_ = p.crop_shape, p.output_shape
         nt = p.n_target_channels
         if os_ == cs:
             lib.ssr_copy_strided(src, self.target, B * int(np.prod(cs)), 1, 0, nt, tgt_c, st)
-            return
+            return src
         cur = src
         bufs = [self.tmp_b, self.tmp_c]
         for n, (kp, ksh) in enumerate(ktgt or []):
             dst = bufs[n % 2]
             lib.ssr_blur3d(cur, dst, kp, *ksh, None, None, B, *cs, 1, 0, 1, 0, st)
             cur = dst
-        lib.ssr_resize(cur, self.target, B, *cs, *os_, 1, 0, nt, tgt_c, st)
+        if not rebound:
+            lib.ssr_resize(cur, self.target, B, *cs, *os_, 1, 0, nt, tgt_c, st)
+            return None
+        # the input chain of this channel continues from the resampled target (GeneratorPlan.chan_grid): resample into a
+        # contiguous [B, *output_shape] buffer first, then interleave it into the target tensor
+        res = next(t for t in (self.tmp_b, self.tmp_c, self.tmp_a) if t is not cur and t is not src)
+        lib.ssr_resize(cur, res, B, *cs, *os_, 1, 0, 0, 0, st)
+        lib.ssr_copy_strided(res, self.target, B * int(np.prod(os_)), 1, 0, nt, tgt_c, st)
+        return res
