@@ -139,3 +139,19 @@ def test_trained_reference_weights_pin_the_layer_semantics():
     assert right > 0.85, right
     for name, r in wrong.items():
         assert r < right - 0.15, (name, r, right)
+
+
+def test_loss_matches_reference_metrics_model():
+    """oracle loss_fn vs the reference's own metrics_model() executed on the tf shim (tests/golden/make_reference_loss_goldens.py):
+    residual addition from 'image_out' channels, centre cropping (including odd margins), L1 / L2.  Tolerance 2e-6 relative:
+    only the order of the mean's summation differs."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_loss.npz'))
+    cases = {'l1_plain': dict(metric='l1'),
+             'l2_crop_res': dict(metric='l2', loss_cropping=8, work_with_residual_channel=[0]),
+             'l1_crop3_res2': dict(metric='l1', loss_cropping=[8, 10, 6], work_with_residual_channel=[0, 2]),
+             'l1_crop_odd': dict(metric='l1', loss_cropping=6)}
+    for name, kw in cases.items():
+        loss = OU.loss_fn(torch.from_numpy(G[name + '_pred']), torch.from_numpy(G[name + '_image']),
+                          torch.from_numpy(G[name + '_target']), **kw)
+        np.testing.assert_allclose(float(loss), float(G[name + '_loss']), rtol=2e-6)
