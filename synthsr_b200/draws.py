@@ -66,7 +66,7 @@ def sample_draws(rng, plan, batch, gmm_noise=False):
         d['gamma_normal_%d' % i] = rng.standard_normal(batch, dtype=f32)
         if plan.input_channels[i]:
             r = plan.blur_range
-            if r is not None and r != 1:
+            if r is not None and r != 1 and not plan.randomise_res[i]:    # GaussianBlur(sigma, blur_range) of the fixed-res branch
                 d['blur_mult_%d' % i] = rng.uniform(1. / r, r, size=3).astype(f32)
             if plan.randomise_res[i]:
                 # SampleResolution(atlas_res, max_res_iso=[9,9,9]) (ext/lab2im/layers.py:619-625, 646-647): resolution

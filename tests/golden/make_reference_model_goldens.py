@@ -33,6 +33,7 @@ _np = np.asarray
 
 # ---- the few extra pieces the graph-building function needs on top of the layer shim ----------------------------------
 FEED, LOG, FORCED = [], [], []
+BOUNDS = {}
 RNG = [None]
 
 
@@ -44,7 +45,7 @@ def uniform(shape, minval=0, maxval=1, dtype='float32'):
     shp = _shape(shape)
     if 'int' in str(dtype):
         v = RNG[0].integers(int(minval), int(maxval), size=shp).astype(np.int32)
-        LOG.append(('uniform_int', v))
+        LOG.append(('uniform_int', v, minval, maxval))
         return T(v)
     lo, hi = _np(_np(minval), dtype=f32), _np(_np(maxval), dtype=f32)
     if shp == (1,) and float(lo) == 0. and float(hi) == 1. and FORCED:
@@ -53,13 +54,13 @@ def uniform(shape, minval=0, maxval=1, dtype='float32'):
         u = RNG[0].uniform(size=shp).astype(f32)
     v = (u * (hi - lo).astype(f32) + lo).astype(f32)                  # the TF kernel: rand * (maxval - minval) + minval
     v = np.minimum(v, np.nextafter(np.broadcast_to(hi, v.shape), -np.inf, dtype=f32)) if np.any(v >= hi) and np.all(hi > lo) else v
-    LOG.append(('uniform', v))
+    LOG.append(('uniform', v, lo.tolist(), hi.tolist()))
     return T(v)
 
 
 def normal(shape, mean=0., stddev=1., dtype='float32'):
     z = RNG[0].standard_normal(_shape(shape)).astype(f32)
-    LOG.append(('normal', z))                                          # the STANDARD normal is what the oracle is handed
+    LOG.append(('normal', z, _np(_np(mean), dtype=f32).tolist(), _np(_np(stddev), dtype=f32).tolist()))   # the STANDARD normal is what the oracle gets
     return T((z * _np(_np(stddev), dtype=f32) + _np(_np(mean), dtype=f32)).astype(f32))
 
 
@@ -118,18 +119,29 @@ def run(seed, labels_shape, batch, forced, real=False, **kw):
     shim.base.GRAPH_BATCH[0] = None
     assert not FEED and not FORCED
     image, target = (np.asarray(o) for o in model.outputs)
-    return inputs, image, target, [(k, np.asarray(v)) for k, v in LOG]
+    return inputs, image, target, [(k, np.asarray(v), a, b) for k, v, a, b in LOG]
 
 
 def to_draws(cfg, log, batch, crop_differs):
     """call-order log -> the `draws` dict of synthsr_b200/draws.py (same order as the graph: labels_to_image_model.py:128-238)."""
     it = iter(log)
     d = {}
+    last = [None]
 
     def nxt(kind):
-        k, v = next(it)
+        k, v, a, b = next(it)
         assert k == kind, (k, kind)
+        last[0] = [k, a, b]                  # (minval, maxval) of a uniform, (mean, stddev) of a normal, as the graph passed them
         return v
+
+    class Recorder(dict):                    # remembers the distribution parameters of the call that produced each entry
+        def __setitem__(self, key, value):
+            if value is not None and key not in BOUNDS:
+                BOUNDS[key] = last[0]
+            dict.__setitem__(self, key, value)
+
+    BOUNDS.clear()
+    d = Recorder()
 
     for key, name in [('rotation_bounds', 'aff_rotation'), ('shearing_bounds', 'aff_shearing'),
                       ('scaling_bounds', 'aff_scaling'), ('translation_bounds', 'aff_translation')]:
@@ -141,7 +153,12 @@ def to_draws(cfg, log, batch, crop_differs):
         d['crop_idx'] = np.stack([nxt('uniform').astype(np.int32) for _ in range(batch)])       # tf.cast -> int32 truncates
     else:
         d['crop_idx'] = np.zeros((batch, 3), np.int32)
-    d['flip'] = (nxt('uniform')[:, 0] < f32(.5)) if cfg.get('flipping', True) else np.zeros(batch, bool)
+        BOUNDS.pop('crop_idx', None)                                    # nothing was drawn
+    if cfg.get('flipping', True):
+        d['flip'] = nxt('uniform')[:, 0] < f32(.5)
+    else:
+        d['flip'] = np.zeros(batch, bool)
+        BOUNDS.pop('flip', None)
     d['gmm_normal'] = nxt('normal')
     C = len(cfg['input_channels'])
     first = int(np.argmax(cfg['input_channels']))
@@ -159,10 +176,12 @@ def to_draws(cfg, log, batch, crop_differs):
         if inp:
             reg = sim[i] and i != first
             if reg:
-                d['reg_rot_%d' % i], d['reg_trans_%d' % i] = nxt('uniform'), nxt('uniform')
+                d['reg_rot_%d' % i] = nxt('uniform')
+                d['reg_trans_%d' % i] = nxt('uniform')
             if rr[i]:
                 nxt('uniform_int')                                     # anisotropy axis: drawn, unused when max_res_aniso is None
                 res = nxt('uniform')
+                BOUNDS['res_%d' % i] = last[0]
                 at_min = bool(nxt('uniform')[0] < f32(.05))
                 lo = np.tile(np.asarray(cfg['atlas_res'], dtype=f32).reshape(-1)[:3][None] if np.ndim(cfg['atlas_res']) else
                              np.full((1, 3), cfg['atlas_res'], f32), (batch, 1))
@@ -172,10 +191,11 @@ def to_draws(cfg, log, batch, crop_differs):
             else:
                 d['blur_mult_%d' % i] = nxt('uniform')
             if reg:
-                d['reg_err_rot_%d' % i], d['reg_err_trans_%d' % i] = nxt('uniform'), nxt('uniform')
+                d['reg_err_rot_%d' % i] = nxt('uniform')
+                d['reg_err_trans_%d' % i] = nxt('uniform')
     rest = list(it)
-    assert not rest, 'unconsumed draws: %s' % [(k, v.shape) for k, v in rest]
-    return d
+    assert not rest, 'unconsumed draws: %s' % [(k, v.shape) for k, v, _, _ in rest]
+    return dict(d)
 
 
 CASES = {
@@ -219,9 +239,7 @@ if __name__ == '__main__':
         pm = c['cfg'].get('padding_margin') or 0
         grid = [s + 2 * pm for s in c['labels_shape']]
         # the crop shape the reference derived = shape of the GMM noise it asked for
-        gmm_shape = [v.shape for k, v in log if k == 'normal' and v.ndim == 5 and v.shape[-1] == len(c['cfg']['input_channels'])
-                     and list(v.shape[1:4]) != grid or False]
-        crop = [v for k, v in log if k == 'normal' and v.ndim == 5][1 if c['cfg'].get('nonlin_std', 3.) > 0 else 0].shape[1:4]
+        crop = [v for k, v, _, _ in log if k == 'normal' and v.ndim == 5][1 if c['cfg'].get('nonlin_std', 3.) > 0 else 0].shape[1:4]
         d = to_draws(c['cfg'], log, c['batch'], list(crop) != grid)
         for i, a in enumerate(inputs):
             out['%s_in%d' % (tag, i)] = a
@@ -232,7 +250,8 @@ if __name__ == '__main__':
         meta[tag] = dict(labels_shape=list(c['labels_shape']), batch=c['batch'],
                          cfg={k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in c['cfg'].items()},
                          image_shape=list(image.shape), target_shape=list(target.shape),
-                         n_draw_calls=len(log), draw_calls=[[k, list(v.shape)] for k, v in log])
+                         n_draw_calls=len(log), draw_calls=[[k, list(v.shape)] for k, v, _, _ in log],
+                         bounds={k: v for k, v in BOUNDS.items() if v is not None})
         print(tag, 'image', image.shape, 'target', target.shape, '%d random ops' % len(log))
     out['generation_labels'] = GEN
     out['n_neutral_labels'] = np.array(N_NEUTRAL)

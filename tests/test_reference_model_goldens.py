@@ -18,6 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 M = np.load(os.path.join(HERE, 'golden', 'reference_model.npz'))
 META = json.loads(bytes(M['meta_json']).decode())
 ATOL = 2e-6
+f32 = np.float32
 
 
 def _case(tag):
@@ -90,3 +91,64 @@ def test_target_rebinding_quirk_is_what_the_reference_does():
     alt = OG.gaussian_blur(full, [.42, .42, .42], draws['blur_mult_0'])
     alt = OG.resample_tensor(alt[..., None], list(ref_image.shape[1:4]))[..., 0]
     assert np.abs(alt - ref_image[0, ..., 0]).max() > .1
+
+
+class _EdgeRng:
+    """stands in for numpy's Generator inside synthsr_b200.draws.sample_draws: every uniform returns its lower (or upper)
+    bound, so the bounds the product samples from can be read off the draws dict."""
+
+    def __init__(self, edge):
+        self.edge = edge
+
+    def uniform(self, low=0., high=1., size=None):
+        v = np.asarray(low if self.edge == 'lo' else high, dtype=np.float64)
+        if size is None:
+            size = np.broadcast(np.asarray(low), np.asarray(high)).shape
+            if size == ():
+                return float(v)
+        return np.broadcast_to(v, size).copy()
+
+    def standard_normal(self, size=None, dtype=np.float64):
+        return np.ones(size, dtype=dtype)
+
+
+@pytest.mark.parametrize('tag', sorted(META))
+def test_product_samples_from_the_distributions_the_graph_uses(tag):
+    """the (minval, maxval) of every tf.random.uniform the reference graph executed (logged by the golden script) against
+    the bounds synthsr_b200.draws.sample_draws hands to its generator, entry by entry; normals are standard normals on
+    both sides (their scale is applied downstream and is covered by the value comparison above)."""
+    from synthsr_b200.draws import sample_draws
+    from synthsr_b200.generator import GeneratorPlan
+    cfg, inputs, _, _, _ = _case(tag)
+    m = META[tag]
+    skip = ('input_channels', 'output_channel', 'n_neutral_labels', 'atlas_res', 'target_res', 'generation_labels')
+    plan = GeneratorPlan(m['labels_shape'], cfg['input_channels'], cfg['output_channel'], cfg['generation_labels'],
+                         cfg['n_neutral_labels'], cfg['atlas_res'], cfg['target_res'],
+                         **{k: v for k, v in cfg.items() if k not in skip})
+    B = m['batch']
+    lo = sample_draws(_EdgeRng('lo'), plan, B, gmm_noise=True)
+    hi = sample_draws(_EdgeRng('hi'), plan, B, gmm_noise=True)
+    checked = 0
+    for key, (kind, a, b) in m['bounds'].items():
+        assert key in lo and lo[key] is not None, key
+        if kind == 'normal':
+            assert np.all(np.asarray(lo[key]) == 1)                                # raw standard normals
+            continue
+        if key in ('flip',) or key.startswith('bias_apply'):                      # Bernoulli through a U(0,1) threshold
+            assert (a, b) == (0., 1.)
+            assert np.all(np.asarray(lo[key])) and not np.any(np.asarray(hi[key]))
+        elif key == 'crop_idx':
+            assert np.all(np.asarray(lo[key]) == 0)
+            np.testing.assert_array_equal(np.asarray(hi[key])[0], np.asarray(b).astype(np.int32))
+        elif key.startswith('thick_'):                                             # U(atlas_res, resolution drawn just before)
+            np.testing.assert_allclose(np.asarray(lo[key]), np.broadcast_to(np.asarray(a, f32), np.shape(lo[key])))
+            np.testing.assert_array_equal(np.asarray(hi[key]), np.asarray(hi['res_' + key[6:]]))
+        else:
+            np.testing.assert_allclose(np.asarray(lo[key], f32), np.broadcast_to(np.asarray(a, f32), np.shape(lo[key])), rtol=1e-6)
+            np.testing.assert_allclose(np.asarray(hi[key], f32), np.broadcast_to(np.asarray(b, f32), np.shape(hi[key])), rtol=1e-6)
+        checked += 1
+    assert checked >= 5
+    # and nothing is sampled that the graph does not draw
+    drawn = {k for k, v in lo.items() if v is not None and not (k == 'crop_idx' and 'crop_idx' not in m['bounds'])
+             and not (k == 'flip' and 'flip' not in m['bounds'])}
+    assert drawn == set(m['bounds']), drawn ^ set(m['bounds'])
