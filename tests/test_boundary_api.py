@@ -98,3 +98,39 @@ def test_build_model_inputs_protocol(tmp_path):
     gen2 = build_model_inputs(paths, len(GEN_LABELS), pm, ps, 'normal', batchsize=3, n_channels=2, generation_classes=GEN_CLASSES)
     lab, means, stds = next(gen2)
     assert lab.shape == (3, 16, 18, 14, 1) and means.shape == (3, 19, 2)
+
+
+def test_build_model_inputs_matches_reference_draw_for_draw(tmp_path):
+    """the reference's own build_model_inputs (NumPy only) run on .npz label maps with np.random seeded
+    (tests/golden/make_reference_model_inputs_goldens.py); the product's sampler, reseeded, must return the same label maps and
+    exactly the same GMM means / stds -- same draws from the same distributions in the same order (uniform / normal priors,
+    class regrouping, per-channel prior blocks, batch 2 with real images)."""
+    import os
+    from SynthSR.model_inputs import build_model_inputs
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_model_inputs.npz'))
+    lp, ip = [], []
+    for i in range(3):
+        lp.append(str(tmp_path / ('lab%d.npz' % i)))
+        ip.append(str(tmp_path / ('img%d.npz' % i)))
+        np.savez(lp[-1], vol_data=G['map_%d' % i])
+        np.savez(ip[-1], vol_data=G['img_%d' % i])
+    K = 7
+    cases = {
+        'default': dict(n_labels=K, prior_means=None, prior_stds=None, prior_distributions='uniform'),
+        'normal_classes': dict(n_labels=K, prior_means=G['pm2'], prior_stds=G['ps2'], prior_distributions='normal',
+                               generation_classes=G['classes']),
+        'two_channels_images': dict(n_labels=K, prior_means=G['pm4'], prior_stds=G['ps4'], prior_distributions='uniform',
+                                    n_channels=2, batchsize=2, path_images=ip),
+        'range_pair': dict(n_labels=K, prior_means=[40, 180], prior_stds=[3, 12], prior_distributions='uniform'),
+    }
+    for name, kw in cases.items():
+        np.random.seed(1234)
+        g = build_model_inputs(lp, **kw)
+        for it in range(3):
+            res = next(g)
+            n = 4 if 'path_images' in kw else 3
+            assert len(res) == n
+            for j, a in enumerate(res):
+                ref = G['%s_it%d_%d' % (name, it, j)]
+                assert np.asarray(a).shape == ref.shape, (name, it, j)
+                np.testing.assert_array_equal(np.asarray(a), ref, err_msg='%s it%d input %d' % (name, it, j))
