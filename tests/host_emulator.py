@@ -25,8 +25,22 @@ def view(p, shape, dtype=np.float32):
         return None
     addr = p.data_ptr() if hasattr(p, 'data_ptr') else int(p)
     n = int(np.prod(shape))
+    if hasattr(p, 'numel'):                                # a whole tensor was passed: the launch must fit inside it
+        assert p.numel() * p.element_size() >= n * np.dtype(dtype).itemsize, \
+            'launch touches %d bytes of a %d-byte buffer' % (n * np.dtype(dtype).itemsize, p.numel() * p.element_size())
     buf = (ctypes.c_char * (n * np.dtype(dtype).itemsize)).from_address(addr)
     return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+def _addr(p):
+    return p.data_ptr() if hasattr(p, 'data_ptr') else int(p)
+
+
+def disjoint(src, n_src, dst, n_dst, what):
+    """gather / stencil kernels read neighbours of what other threads write: source and destination must not overlap
+    (the emulator works on copies, which would hide such a hazard -- so it is asserted instead).  Sizes in float32."""
+    a0, b0 = _addr(src), _addr(dst)
+    assert a0 + 4 * n_src <= b0 or b0 + 4 * n_dst <= a0, '%s: source and destination buffers overlap' % what
 
 
 def _pad3(vol, pads):
@@ -52,6 +66,7 @@ class HostEmulator:
             dst_stride, dst_off = C, 0
         x = view(src, (B, s0, s1, s2, C)).copy()
         nv = d0 * d1 * d2
+        disjoint(src, B * s0 * s1 * s2 * C, dst, B * nv * dst_stride, 'ssr_resize')
         out = view(dst, (B * nv, dst_stride))
         for b in range(B):
             r = OG.resize(x[b], [d0, d1, d2], 'nearest' if nearest else 'linear')
@@ -110,6 +125,7 @@ class HostEmulator:
                         flip, stream):
         self._log('ssr_warp_linear', (n0, n1, n2), (p0, p1, p2), (h0, h1, h2), (c0, c1, c2))
         img = view(image, (B, n0 - 2 * p0, n1 - 2 * p1, n2 - 2 * p2)).copy()
+        disjoint(image, img.size, out, B * c0 * c1 * c2, 'ssr_warp_linear')
         A = view(aff, (B, 4, 4))
         fh = view(field_half, (B, h0, h1, h2, 3)) if field_half is not None else None
         ci = view(crop_idx, (B, 3), np.int32)
@@ -159,6 +175,7 @@ class HostEmulator:
                   dst_off)
         nv = n0 * n1 * n2
         x = view(src, (B * nv, src_stride))[:, src_off].reshape(B, n0, n1, n2).copy()
+        disjoint(src, B * nv * src_stride, dst, B * nv * dst_stride, 'ssr_blur3d')
         k = view(kern, (k0, k1, k2)).copy()
         mm = view(minmax, (B, 2))
         ge = view(gamma_exp, (B,))
@@ -182,6 +199,9 @@ class HostEmulator:
         x = view(src, (B, n0, n1, n2, 1)).copy()
         P = view(params, (B, 9))
         nv = o0 * o1 * o2
+        disjoint(src, x.size, dst, B * nv * dst_stride, 'ssr_mimic_acquisition')
+        if dist is not None and _addr(dist) != _addr(dst):
+            disjoint(src, x.size, dist, B * nv * dist_stride, 'ssr_mimic_acquisition (dist)')
         o = view(dst, (B * nv, dst_stride))
         dd = view(dist, (B * nv, dist_stride)) if dist is not None else None
         inshape = [n0, n1, n2]

@@ -88,6 +88,8 @@ CONFIGS = [   # the configurations of tests/test_generator_gpu.py, at sizes the 
     ('randomise_res', dict(input_channels=[True, True], output_channel=0, randomise_res=True, build_reliability_maps=True,
                            simulate_registration_error=True, output_shape=16), [20, 20, 20], 1, False),
     ('target_res', dict(target_res=2., padding_margin=4, nonlin_std=2.), [16, 24, 16], 1, False),
+    ('target_res_finer', dict(target_res=.5, build_reliability_maps=True, data_res=np.array([[1., 2., 1.]]),
+                              thickness=np.array([[1., 2., 1.]]), downsample=True), [12, 10, 12], 1, False),
     ('identity', dict(scaling_bounds=False, rotation_bounds=False, shearing_bounds=False, translation_bounds=False,
                       nonlin_std=0., flipping=False), [16, 16, 16], 1, False),
     ('real_image', dict(output_channel=None, output_shape=16), [20, 20, 18], 1, True),
