@@ -155,3 +155,38 @@ def test_loss_matches_reference_metrics_model():
         loss = OU.loss_fn(torch.from_numpy(G[name + '_pred']), torch.from_numpy(G[name + '_image']),
                           torch.from_numpy(G[name + '_target']), **kw)
         np.testing.assert_allclose(float(loss), float(G[name + '_loss']), rtol=2e-6)
+
+
+def test_graph_built_by_the_reference_unet_function():
+    """ext/neuron/models.unet() (-> conv_enc, conv_dec) executed unmodified on a functional-API stand-in for Keras
+    (tests/golden/make_reference_unet_goldens.py): the layers it creates -- names, order, kernel shapes -- are exactly the
+    product's layer_specs / keras_layer_order, and the oracle's forward on the same weights reproduces the prediction and the
+    intermediate activations of THAT graph (skip taken from conv_downarm_l_1's output, concat [skip, up], BN after the second
+    activation, linear 1x1x1 head)."""
+    import os
+    from synthsr_b200.unet import keras_layer_order, layer_specs
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_unet.npz'))
+    assert [str(n) for n in G['layer_order']] == keras_layer_order(nb_levels=3)
+    weights = {k[2:]: G[k] for k in G.files if k.startswith('w/')}
+    specs = layer_specs(2, nb_features=4, nb_levels=3, feat_mult=2, nb_conv_per_level=2, nb_labels=1)
+    want = {}
+    for name, kind, ci, co in specs:
+        if kind == 'bn':
+            want[name + '/gamma'], want[name + '/beta'] = (co,), (co,)
+        else:
+            ks = 3 if kind == 'conv' else 1
+            want[name + '/kernel'], want[name + '/bias'] = (ks, ks, ks, ci, co), (co,)
+    assert {k: tuple(v.shape) for k, v in weights.items()} == want
+    params = OU.init_params(0, 2, dtype=torch.float64, nb_features=4, nb_levels=3, feat_mult=2, nb_conv_per_level=2, nb_labels=1)
+    for k, v in weights.items():
+        assert tuple(params[k].shape) == tuple(v.shape), k
+        params[k] = torch.from_numpy(v.astype(np.float64))
+    acts = {}
+    pred = OU.forward(params, torch.from_numpy(G['image'].astype(np.float64)), training=True, nb_levels=3, activations=acts)
+    np.testing.assert_allclose(pred.numpy(), G['prediction'], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(acts['unet_conv_downarm_0_1'].permute(0, 2, 3, 4, 1).numpy(), G['act/unet_conv_downarm_0_1'],
+                               rtol=0, atol=1e-12)
+    # the wrong readings really are different graphs
+    for wrong in ('concat_swapped', 'skip_after_bn', 'relu'):
+        p2 = OU.forward(params, torch.from_numpy(G['image'].astype(np.float64)), training=True, nb_levels=3, _wrong=(wrong,))
+        assert np.abs(p2.numpy() - G['prediction']).max() > 1e-2, wrong
