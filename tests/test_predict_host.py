@@ -74,3 +74,52 @@ def test_dynamic_unet_model_checks_shapes_and_keeps_weights_by_name(tmp_path):
     h5lite.save_keras_weights(p, w)
     with pytest.raises(ValueError, match='not compatible'):
         m.load_weights(p, by_name=True)
+
+
+class _StandInUnet:
+    """the deterministic stand-in network of tests/golden/make_reference_predict_script_goldens.py (same arithmetic)."""
+
+    def load_weights(self, path, by_name=True):
+        self.loaded = path
+
+    def predict(self, S):
+        S = np.asarray(S, dtype=np.float64)
+        g = [np.arange(n, dtype=np.float64) for n in S.shape[1:4]]
+        ramp = (np.sin(.37 * g[0])[:, None, None] + .5 * np.cos(.21 * g[1])[None, :, None] + .002 * g[2][None, None, :] ** 1.5)
+        out = .55 * S[..., 0] + .25 * np.roll(S[..., 0], 2, axis=1) * (1 + .1 * ramp) - .03 + .02 * ramp
+        if S.shape[-1] > 1:
+            out = out * .3 - .2 * S[..., 1] + .1 * np.roll(S[..., 1], 1, axis=2)
+        return out[..., None]
+
+
+def test_predict_glue_matches_the_reference_scripts_run_end_to_end(monkeypatch):
+    """the reference's own scripts/predict_command_line.py (default + --ct --disable_flipping) and
+    scripts/predict_command_line_hyperfine.py executed with runpy around a stand-in network and in-memory volume I/O
+    (tests/golden/make_reference_predict_script_goldens.py) vs SynthSR.predict with the same stand-in: saved volume and saved
+    affine.  Pure float64 NumPy on both sides -> 1e-9."""
+    import SynthSR.predict as P
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_predict_scripts.npz'))
+    net = _StandInUnet()
+    pred, aff = P.predict_volume(net, G['a_im'], G['a_aff'])
+    assert pred.shape == G['a_pred'].shape
+    np.testing.assert_allclose(pred, G['a_pred'], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(aff, G['a_pred_aff'], rtol=0, atol=1e-9)
+    pred, aff = P.predict_volume(net, G['b_im'], G['b_aff'], ct=True, disable_flipping=True)
+    np.testing.assert_allclose(pred, G['b_pred'], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(aff, G['b_pred_aff'], rtol=0, atol=1e-9)
+    # flip test-time augmentation really matters for this stand-in (else the comparison above would not see it)
+    p2, _ = P.predict_volume(net, G['a_im'], G['a_aff'], disable_flipping=True)
+    assert np.abs(p2 - G['a_pred']).max() > 1.
+
+    vols = {'/t1.nii.gz': (G['h_t1'], G['h_t1_aff']), '/t2.nii.gz': (G['h_t2'], G['h_t2_aff'])}
+    saved = {}
+    monkeypatch.setattr(P, 'build_unet', lambda *a, **k: net)
+    monkeypatch.setattr(P.utils, 'load_volume', lambda path, im_only=True, dtype=None, **kw: (
+        vols[path][0].astype(np.float64).copy(), vols[path][1].copy(), None))
+    monkeypatch.setattr(P.utils, 'save_volume', lambda vol, aff, hdr, path, **kw: saved.__setitem__(path, (np.array(vol), np.array(aff))))
+    real_isfile = os.path.isfile
+    monkeypatch.setattr(os.path, 'isfile', lambda p: p in vols or real_isfile(p))
+    P.predict_hyperfine('/t1.nii.gz', '/t2.nii.gz', '/pred_h.nii.gz')
+    pred, aff = saved['/pred_h.nii.gz']
+    np.testing.assert_allclose(pred, G['h_pred'], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(aff, G['h_pred_aff'], rtol=0, atol=1e-9)
