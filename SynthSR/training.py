@@ -89,9 +89,19 @@ def training(labels_dir,
         if any(x >= n_channels for x in work_with_residual_channel):
             raise Exception('indices in work_with_residual_channel cannot be greater than the total number of channels')
         if build_reliability_maps:
-            # reference :270-271 does `2 * list` (repeats the list instead of doubling the indices); the indices
-            # address image_out channels [ch0, rel0, ch1, rel1, ...] (metrics_model.py:58-59), so double them here.
-            work_with_residual_channel = [2 * int(c) for c in work_with_residual_channel]
+            # Reference behaviour kept on purpose (training.py:270-271, pinned by executing training() itself:
+            # tests/golden/make_reference_training_goldens.py): `2 * work_with_residual_channel` REPEATS the list instead
+            # of doubling the indices, so metrics_model adds image_out channel c -- of [ch0, rel0, ch1, rel1, ...] -- twice
+            # and Keras' Add broadcasts the single predicted channel over the two copies.  Mean and gradient of the L1 / L2
+            # loss over two identical copies equal those over one, i.e. the step is that of residual channel c, UN-doubled
+            # (for c >= 1 that is a reliability map: the reference's quirk, reproduced).  With several output channels the
+            # repeated list no longer broadcasts against the prediction and Keras refuses to build the Add layer.
+            if len(work_with_residual_channel) > 1:
+                raise ValueError('Operands could not be broadcast together with shapes (..., %d) (..., %d): the reference '
+                                 'repeats work_with_residual_channel when build_reliability_maps is set, which only works '
+                                 'for a single output channel' % (2 * len(work_with_residual_channel),
+                                                                  len(work_with_residual_channel)))
+            work_with_residual_channel = [int(c) for c in work_with_residual_channel]
     if segmentation_model_file is not None:
         add_seg_loss_to_model()
 

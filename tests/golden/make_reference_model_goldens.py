@@ -82,8 +82,13 @@ KLm.Input = lambda shape=None, name=None, dtype=None: FEED.pop(0)
 
 
 class Model:
-    def __init__(self, inputs=None, outputs=None):
+    def __init__(self, inputs=None, outputs=None, name=None):
         self.inputs, self.outputs = inputs, outputs
+        self.input = inputs[0] if isinstance(inputs, list) and len(inputs) == 1 else inputs
+        self.output = outputs[0] if isinstance(outputs, list) and len(outputs) == 1 else outputs
+
+    def get_layer(self, name):                               # (whole-training harness: layers are registered by name there)
+        return sys.modules['make_reference_unet_goldens'].LAYERS[name]
 
 
 sys.modules['keras.models'].Model = Model

@@ -21,7 +21,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import tf_numpy_shim  # noqa: E402
 
-tf, K, T = tf_numpy_shim.install([])
+if 'tensorflow' not in sys.modules:                   # (imported by make_reference_training_goldens.py after the tf shim is up)
+    tf_numpy_shim.install([])
 KL = sys.modules['keras.layers']
 
 WEIGHTS = {}          # '<layer>/<weight>' -> array, created on first use with the shapes the reference's layers ask for
@@ -156,35 +157,45 @@ class Model:
     def __init__(self, inputs=None, outputs=None, name=None):
         self.inputs = inputs if isinstance(inputs, list) else [inputs]
         self.outputs = outputs if isinstance(outputs, list) else [outputs]
-        self.input, self.output, self.name = self.inputs[0], self.outputs[0], name
+        self.input = self.inputs[0] if len(self.inputs) == 1 else self.inputs          # Keras: a list when there are several
+        self.output = self.outputs[0] if len(self.outputs) == 1 else self.outputs
+        self.name = name
 
     def get_layer(self, name):
         return LAYERS[name]
 
 
-KL.Conv3D, KL.BatchNormalization, KL.MaxPooling3D, KL.UpSampling3D = Conv3D, BatchNormalization, MaxPooling3D, UpSampling3D
-KL.Activation, KL.Input, KL.concatenate = Activation, Input, concatenate
-sys.modules['keras.models'].Model = Model
-sys.path.insert(0, '/root/reference')
-from ext.neuron import models as nrn_models  # noqa: E402
+def install():
+    KL.Conv3D, KL.BatchNormalization, KL.MaxPooling3D, KL.UpSampling3D = Conv3D, BatchNormalization, MaxPooling3D, UpSampling3D
+    KL.Activation, KL.Input, KL.concatenate = Activation, Input, concatenate
+    sys.modules['keras.models'].Model = Model
 
-out = {}
-# the configuration SynthSR.training() builds (training.py:330-341) at toy size: 3 levels, 4 features (spatial dims
-# divisible by 4, as the reference requires through output_div_by_n)
-shape = [12, 8, 16]
-image = RNG.normal(size=(2, *shape, 2)).astype(np.float32)
-FEED.append(KTensor(image))
-model = nrn_models.unet(nb_features=4, input_shape=[*shape, 2], nb_levels=3, conv_size=3, nb_labels=1, feat_mult=2,
-                        nb_conv_per_level=2, conv_dropout=0, final_pred_activation='linear', batch_norm=-1,
-                        activation='elu', input_model=None)
-out['image'] = image
-out['prediction'] = np.asarray(model.output, dtype=np.float64)
-out['layer_order'] = np.array(list(LAYERS))
-for n in ('unet_conv_downarm_0_1', 'unet_bn_down_0', 'unet_maxpool_0', 'unet_up_3', 'unet_merge_3', 'unet_bn_up_1',
-          'unet_likelihood'):
-    out['act/' + n] = np.asarray(LAYERS[n].output, dtype=np.float64)
-for k, v in WEIGHTS.items():
-    out['w/' + k] = v
-print(len(LAYERS), 'layers;', len(WEIGHTS), 'weights; prediction', out['prediction'].shape)
-print(list(LAYERS))
-np.savez_compressed(os.path.join(HERE, 'reference_unet.npz'), **out)
+
+def main():
+    install()
+    sys.path.insert(0, '/root/reference')
+    from ext.neuron import models as nrn_models
+    out = {}
+    # the configuration SynthSR.training() builds (training.py:330-341) at toy size: 3 levels, 4 features (spatial dims
+    # divisible by 4, as the reference requires through output_div_by_n)
+    shape = [12, 8, 16]
+    image = RNG.normal(size=(2, *shape, 2)).astype(np.float32)
+    FEED.append(KTensor(image))
+    model = nrn_models.unet(nb_features=4, input_shape=[*shape, 2], nb_levels=3, conv_size=3, nb_labels=1, feat_mult=2,
+                            nb_conv_per_level=2, conv_dropout=0, final_pred_activation='linear', batch_norm=-1,
+                            activation='elu', input_model=None)
+    out['image'] = image
+    out['prediction'] = np.asarray(model.output, dtype=np.float64)
+    out['layer_order'] = np.array(list(LAYERS))
+    for n in ('unet_conv_downarm_0_1', 'unet_bn_down_0', 'unet_maxpool_0', 'unet_up_3', 'unet_merge_3', 'unet_bn_up_1',
+              'unet_likelihood'):
+        out['act/' + n] = np.asarray(LAYERS[n].output, dtype=np.float64)
+    for k, v in WEIGHTS.items():
+        out['w/' + k] = v
+    print(len(LAYERS), 'layers;', len(WEIGHTS), 'weights; prediction', out['prediction'].shape)
+    print(list(LAYERS))
+    np.savez_compressed(os.path.join(HERE, 'reference_unet.npz'), **out)
+
+
+if __name__ == '__main__':
+    main()
