@@ -48,10 +48,11 @@ class LabelsToImageModel:
         B = labels.shape[0]
         if B != self.batchsize:
             self.batchsize, self._gen = B, None
-        lab_t = torch.as_tensor(np.ascontiguousarray(labels[..., 0], dtype=np.int32)).cuda()
+        dev = self.engine.device                            # 'cuda': SynthGenerator refuses anything else
+        lab_t = torch.as_tensor(np.ascontiguousarray(labels[..., 0], dtype=np.int32)).to(dev)
         real_t = None
         if self.plan.use_real_image:
-            real_t = torch.as_tensor(np.ascontiguousarray(np.asarray(inputs[3])[..., 0], dtype=np.float32)).cuda()
+            real_t = torch.as_tensor(np.ascontiguousarray(np.asarray(inputs[3])[..., 0], dtype=np.float32)).to(dev)
         draws = sample_draws(self._rng, self.plan, B)
         image, target = self.engine.run(lab_t, inputs[1], inputs[2], draws, real_image=real_t, seed=self._seed)
         return [image.cpu().numpy(), target.cpu().numpy()]
