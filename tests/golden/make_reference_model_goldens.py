@@ -4,7 +4,7 @@ order the graph is built (which is the order TF evaluates the random ops' depend
 Every tf.random draw is generated here from a seeded NumPy generator, logged in call order, and stored next to the
 outputs, so the test can hand the SAME numbers to oracle.generator.labels_to_image through its `draws` interface.
 
-Five configurations (all tiny, the shim is pure NumPy):
+Eight configurations (all tiny, the shim is pure NumPy):
   A  training() defaults shape-for-shape: 1 channel, crop, flip, elastic + affine, bias, gamma, blur jitter,
      anisotropic acquisition (data_res [1,1,3], thickness [1,1,2] -> downsample), reliability map;
   B  batch 2, 2 channels: second channel with simulated registration error and randomise_res (SampleResolution,
@@ -13,7 +13,13 @@ Five configurations (all tiny, the shim is pure NumPy):
   D  target-only second channel at target_res 2 (blur + resample), anisotropic input channel resampled to the output grid;
   E  second channel both input and target at target_res 1.5: the reference rebinds `channel` to the resampled target
      (:194-195), so that channel's registration error, acquisition blur, down/up-sampling and reliability map all run
-     on the OUTPUT grid.
+     on the OUTPUT grid;
+  F  batch 2 with per-example crops, rotation + translation only, no flipping, bias field drawn but skipped (the 5 %
+     branch), no blur jitter,
+     blur-only acquisition (data_res [2,1,1], no down-sampling -> all-ones reliability map);
+  G  no spatial deformation at all, asymmetric padding margin + output_div_by_n, three channels (target-only + two inputs,
+     the second with registration error), thickness above / below the slice spacing, blur_range 1, no reliability maps;
+  H  randomise_res with the 5 % branch taken (acquisition at the atlas resolution).
 
 Writes tests/golden/reference_model.npz.   (build container only: needs /root/reference)"""
 import json
@@ -171,9 +177,10 @@ def to_draws(cfg, log, batch, crop_differs):
     rr = [rr] * C if isinstance(rr, bool) else rr
     sim = cfg.get('simulate_registration_error', True)
     sim = [sim] * C if isinstance(sim, bool) else sim
+    jitter = cfg.get('blur_range', 1.15) is not None and cfg.get('blur_range', 1.15) != 1
     for i in range(C):
         inp = bool(cfg['input_channels'][i])
-        if inp:
+        if inp and cfg.get('bias_field_std', .3) > 0:
             d['bias_std_%d' % i] = nxt('uniform').reshape(batch)
             d['bias_normal_%d' % i] = nxt('normal')[..., 0]
             d['bias_apply_%d' % i] = bool(nxt('uniform')[0] < f32(.95))
@@ -192,8 +199,9 @@ def to_draws(cfg, log, batch, crop_differs):
                              np.full((1, 3), cfg['atlas_res'], f32), (batch, 1))
                 d['res_%d' % i] = lo.astype(f32) if at_min else res
                 d['thick_%d' % i] = nxt('uniform')
-                d['blur_mult_dyn_%d' % i] = nxt('uniform')
-            else:
+                if jitter:
+                    d['blur_mult_dyn_%d' % i] = nxt('uniform')
+            elif jitter:
                 d['blur_mult_%d' % i] = nxt('uniform')
             if reg:
                 d['reg_err_rot_%d' % i] = nxt('uniform')
@@ -234,6 +242,23 @@ CASES = {
         nonlin_shape_factor=.0625, simulate_registration_error=True, randomise_res=False,
         data_res=np.array([[1., 1., 3.], [1., 2.5, 1.]]), thickness=np.array([[1., 1., 2.], [1., 2.5, 1.]]), downsample=True,
         build_reliability_maps=True, blur_range=1.15, bias_field_std=.3, bias_shape_factor=.025)),
+    'F': dict(seed=606, labels_shape=(20, 22, 18), batch=2, forced=[.96], cfg=dict(
+        input_channels=[True], output_channel=[0], atlas_res=1., target_res=None, output_shape=[16, 16, 16], flipping=False,
+        aff=None, scaling_bounds=False, rotation_bounds=20, shearing_bounds=False, translation_bounds=4, nonlin_std=3.,
+        nonlin_shape_factor=.125, simulate_registration_error=True, randomise_res=False, data_res=np.array([[2., 1., 1.]]),
+        thickness=None, downsample=False, build_reliability_maps=True, blur_range=None, bias_field_std=.2,
+        bias_shape_factor=.025)),
+    'G': dict(seed=707, labels_shape=(17, 21, 19), batch=1, forced=[.5, .5], cfg=dict(
+        input_channels=[False, True, True], output_channel=[0], atlas_res=1., target_res=None, output_shape=None,
+        output_div_by_n=8, padding_margin=[2, 0, 3], flipping=True, aff=np.eye(4), scaling_bounds=False, rotation_bounds=False,
+        shearing_bounds=False, translation_bounds=False, nonlin_std=0., simulate_registration_error=[True, True, True],
+        randomise_res=False, data_res=np.array([[1., 1., 2.], [1., 3., 1.]]), thickness=np.array([[1., 1., 4.], [1., 2., 1.]]),
+        downsample=False, build_reliability_maps=False, blur_range=1., bias_field_std=.5, bias_shape_factor=.1)),
+    'H': dict(seed=808, labels_shape=(16, 16, 20), batch=1, forced=[.3, .01], cfg=dict(
+        input_channels=[True], output_channel=[0], atlas_res=1., target_res=None, output_shape=None, flipping=True,
+        aff=np.eye(4), scaling_bounds=.15, rotation_bounds=15, shearing_bounds=.012, translation_bounds=False, nonlin_std=3.,
+        nonlin_shape_factor=.0625, simulate_registration_error=True, randomise_res=True, data_res=None, thickness=None,
+        downsample=False, build_reliability_maps=True, blur_range=1.15, bias_field_std=.3, bias_shape_factor=.025)),
 }
 
 if __name__ == '__main__':
@@ -242,7 +267,8 @@ if __name__ == '__main__':
         inputs, image, target, log = run(c['seed'], c['labels_shape'], c['batch'], c['forced'], real=c.get('real', False),
                                          **c['cfg'])
         pm = c['cfg'].get('padding_margin') or 0
-        grid = [s + 2 * pm for s in c['labels_shape']]
+        pm = (list(np.ravel(pm)) * 3)[:3]
+        grid = [s + 2 * int(m) for s, m in zip(c['labels_shape'], pm)]
         # the crop shape the reference derived = shape of the GMM noise it asked for
         crop = [v for k, v, _, _ in log if k == 'normal' and v.ndim == 5][1 if c['cfg'].get('nonlin_std', 3.) > 0 else 0].shape[1:4]
         d = to_draws(c['cfg'], log, c['batch'], list(crop) != grid)
