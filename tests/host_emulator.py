@@ -143,10 +143,13 @@ class HostEmulator:
     def ssr_gmm_bias_minmax(self, labels, lut_mean, lut_std, lut_len, noise, seed, stream_id, bias_small, b0, b1, b2,
                             apply_bias, clip_max, out, minmax, B, n0, n1, n2, stream):
         self._log('ssr_gmm_bias_minmax', (n0, n1, n2), (b0, b1, b2), apply_bias)
-        assert noise is not None, 'the emulator needs injected GMM noise (draws from sample_draws(..., gmm_noise=True))'
         lab = view(labels, (B, n0, n1, n2), np.int32)
         lm, ls = view(lut_mean, (B, lut_len)), view(lut_std, (B, lut_len))
-        nz = view(noise, (B, n0, n1, n2))
+        if noise is not None:
+            nz = view(noise, (B, n0, n1, n2))
+        else:   # throughput mode: the kernel draws Philox normals from (seed, stream_id); any standard normals keyed the same way
+            nz = np.random.default_rng([int(seed) & 0xffffffff, int(stream_id) & 0xffffffff]).standard_normal(
+                (B, n0, n1, n2)).astype(f32)
         o = view(out, (B, n0, n1, n2))
         mm = view(minmax, (B, 2))                          # the emulator keeps min/max as plain floats in the int32 slots
         small = view(bias_small, (B, b0, b1, b2)) if bias_small is not None else None

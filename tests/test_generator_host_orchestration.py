@@ -113,3 +113,42 @@ def test_orchestration_matches_oracle(emu, name, cfg, shape, batch, real):
     np.testing.assert_array_equal(keep['labels'][0].numpy(), inter['labels'])
     np.testing.assert_allclose(image, o_image, rtol=0, atol=ATOL)
     np.testing.assert_allclose(target, o_target, rtol=0, atol=ATOL)
+
+
+@pytest.fixture
+def small_dataset(tmp_path):
+    from ext.lab2im import utils
+    from synthsr_b200.synthetic import GEN_CLASSES, GEN_LABELS as GL, phantom_labels as pl, synthetic_priors
+    labels_dir = tmp_path / 'labels'
+    labels_dir.mkdir()
+    aff = np.array([[1., 0, 0, 40], [0, 1., 0, 16], [0, 0, 1., 63], [0, 0, 0, 1]])
+    for i in range(2):
+        utils.save_volume(pl([24, 28, 20], seed=i).astype(np.float32), aff, None, str(labels_dir / ('brain%d_labels.nii.gz' % i)))
+    pm, ps = synthetic_priors(14, 1, seed=0)
+    paths = {k: str(tmp_path / (k + '.npy')) for k in ('labels', 'classes', 'means', 'stds')}
+    np.save(paths['labels'], GL); np.save(paths['classes'], GEN_CLASSES); np.save(paths['means'], pm); np.save(paths['stds'], ps)
+    return str(labels_dir), paths
+
+
+def test_brain_generator_generate_brain_on_the_emulated_entry_points(emu, small_dataset, monkeypatch):
+    """the user-facing path of tutorials 1-6 -- BrainGenerator -> build_model_inputs -> labels_to_image_model.predict ->
+    generate_brain (back to native space) -- end to end in the CPU suite (the GPU twin is tests/test_training_api_gpu.py)."""
+    import functools
+    import synthsr_b200.generator as G
+    from SynthSR.brain_generator import BrainGenerator
+    monkeypatch.setattr(G, 'SynthGenerator', functools.partial(G.SynthGenerator, device='cpu'))
+    labels_dir, p = small_dataset
+    gen = BrainGenerator(labels_dir, p['means'], p['stds'], 'normal', p['labels'], generation_classes=p['classes'],
+                         output_shape=16, data_res=np.array([1., 1., 3.]), thickness=np.array([1., 1., 3.]),
+                         downsample=True, build_reliability_maps=True)
+    assert gen.labels_shape == [24, 28, 20] and gen.n_dims == 3 and gen.model_output_shape == [16, 16, 16, 2]
+    image, target = gen.generate_brain()
+    assert image.shape == (16, 16, 16, 2) and target.shape == (16, 16, 16)
+    assert image.dtype == np.float32 and np.isfinite(image).all() and np.isfinite(target).all()
+    assert 0. <= target.min() and target.max() <= 1. + 1e-6 and target.std() > 0.01
+    rel = image[..., 1]
+    assert rel.min() >= 0 and rel.max() <= 1 + 1e-6 and (rel < 0.99).any()      # interpolated slices are marked
+    image2, _ = gen.generate_brain()
+    assert not np.array_equal(image, image2)                                    # fresh augmentation every call
+    names = [n for n, _ in emu.calls]
+    assert names.count('ssr_deform_labels_nearest') == 2 and names.count('ssr_gmm_bias_minmax') == 2
