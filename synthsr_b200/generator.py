@@ -4,7 +4,6 @@
 time; `SynthGenerator.run` executes one step (labels, GMM parameters, draws) -> (image, target) on the current CUDA
 stream through the C ABI in include/synthsr_b200.h.  No TensorFlow, no CPU fallback.
 """
-import math
 
 import numpy as np
 import torch

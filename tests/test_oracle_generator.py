@@ -2,9 +2,8 @@
 cases (the reference ships no tests or golden vectors -- SURVEY.md 4 / 8c), and the product's host-side plan / draws
 logic against the oracle's independent restatement."""
 import numpy as np
-import pytest
 
-from helpers import GEN_LABELS, SIDED_LABELS, gmm_params, phantom_labels
+from helpers import GEN_LABELS, phantom_labels
 from oracle import generator as OG
 
 f32 = np.float32

@@ -102,7 +102,6 @@ def test_product_training_derives_what_the_reference_training_derives(name, tmp_
     against what the reference's training() handed to labels_to_image_model / unet / metrics_model / train_model."""
     import SynthSR.training as PT
     import synthsr_b200.trainer as TR
-    from ext.lab2im import utils
     m = META[name]
     labels_dir = tmp_path / 'labels'
     labels_dir.mkdir()

@@ -716,7 +716,6 @@ def test_head_bn_sums_match_direct_reductions():
     """ssr_head_loss_bnsums: the reductions of the folded BatchNorm's backward (sum dy, sum dy * xhat with dy = dfeat)
     obtained algebraically from the head gradients, against float64 sums over the dfeat the kernel wrote; every other
     output identical to ssr_head_loss."""
-    import ctypes
     from synthsr_b200._lib import lib, stream_ptr
     rng = np.random.default_rng(31)
     for (d, C, L, metric) in [([16, 20, 24], 24, 1, 1), ([9, 11, 13], 24, 2, 2), ([32, 32, 32], 8, 1, 1)]:
