@@ -6,6 +6,8 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm --format=csv,noheader
 echo "== gpu tests"
 timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -8
+echo "== generator entry points vs the host emulator (opt-in cross-check)"
+SSR_KERNEL_CROSSCHECK=1 timeout 600 python -m pytest tests/test_generator_entry_points_gpu.py -m gpu -q 2>&1 | tail -8
 echo "== smoke"
 timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2
 echo "== bench"
