@@ -71,6 +71,23 @@ def main():
         crop, outs, pad = l2i.get_shapes(*args)
         out['get_shapes'].append({'args': args, 'crop': [int(v) for v in crop], 'out': [int(v) for v in outs],
                                   'pad': None if pad is None else [int(v) for v in pad]})
+    # randomised sweep of the same function (seeded): odd shapes, anisotropic atlas / target resolutions, scalar and list crops
+    rng = np.random.default_rng(2024)
+    res_choices = [.5, .7, 1., 1.2, 1.5, 2., 3.]
+    for _ in range(200):
+        shape = [int(v) for v in rng.integers(17, 200, size=3)]
+        atlas = [float(rng.choice(res_choices))] * 3 if rng.uniform() < .6 else [float(v) for v in rng.choice(res_choices, 3)]
+        target = list(atlas) if rng.uniform() < .4 else ([float(rng.choice(res_choices))] * 3 if rng.uniform() < .6 else
+                                                         [float(v) for v in rng.choice(res_choices, 3)])
+        u = rng.uniform()
+        oshape = None if u < .3 else (int(rng.integers(16, 160)) if u < .65 else [int(v) for v in rng.integers(16, 160, size=3)])
+        pad = None if rng.uniform() < .6 else (int(rng.integers(1, 9)) if rng.uniform() < .5 else
+                                               [int(v) for v in rng.integers(0, 9, size=3)])
+        div = None if rng.uniform() < .3 else int(rng.choice([2, 4, 8, 16, 32]))
+        args = (shape, oshape, atlas, target, pad, div)
+        crop, outs, pd = l2i.get_shapes(*args)
+        out['get_shapes'].append({'args': list(args), 'crop': [int(v) for v in crop], 'out': [int(v) for v in outs],
+                                  'pad': None if pd is None else [int(v) for v in pd]})
     for shape, f in [([148, 187, 155], .03125), ([148, 187, 155], .0625), ([160] * 3, .03125), ([160] * 3, .025),
                      ([256] * 3, .025), ([192, 192, 64], .025), ([64] * 3, .0625), ([128] * 3, [.03125, .0625, .025])]:
         out['resample_shape'].append({'shape': shape, 'factor': f, 'res': utils.get_resample_shape(shape, f)})
