@@ -231,6 +231,14 @@ class GeneratorPlan:
         self.generation_labels = np.asarray(generation_labels).astype(np.int64)
         self.n_neutral_labels = len(self.generation_labels) if n_neutral_labels is None else int(n_neutral_labels)
         self.flipping = bool(flipping)
+        if self.flipping and aff is not None:
+            # the reference flips along get_ras_axes(aff)[0] (labels_to_image_model.py:159-162); BrainGenerator always hands
+            # np.eye(4) because label maps are re-oriented at load time.  The fused deformation kernel flips axis 0 only.
+            from ext.lab2im.edit_volumes import get_ras_axes
+            if int(get_ras_axes(np.asarray(aff, dtype=np.float64), 3)[0]) != 0:
+                raise NotImplementedError('right/left flipping along axis %d: only volumes whose first axis is the R/L axis '
+                                          '(aff aligned like np.eye(4), what BrainGenerator passes) are supported'
+                                          % int(get_ras_axes(np.asarray(aff, dtype=np.float64), 3)[0]))
         self.scaling_bounds, self.rotation_bounds = scaling_bounds, rotation_bounds
         self.shearing_bounds, self.translation_bounds = shearing_bounds, translation_bounds
         self.apply_affine = any(b is not False for b in (scaling_bounds, rotation_bounds, shearing_bounds,

@@ -237,3 +237,15 @@ def test_dynamic_kernels_host_logic_matches_oracle():
     z = mimic_zooms([40, 44, 36], [1., 1., 1.], res[0], [32, 32, 32])
     ds, dz, uz = OG.mimic_acquisition_zooms([40, 44, 36], [1., 1., 1.], res[0], [32, 32, 32])
     np.testing.assert_array_equal(z, np.concatenate([dz, uz, res[0]]).astype(np.float32))
+
+
+def test_flip_axis_other_than_zero_is_refused():
+    """the reference flips along get_ras_axes(aff)[0] (labels_to_image_model.py:159-162); the fused kernel flips axis 0 (what
+    BrainGenerator's np.eye(4) selects) -- any other orientation must raise instead of silently flipping the wrong axis."""
+    import pytest
+    from synthsr_b200.generator import GeneratorPlan
+    swapped = np.array([[0, 1., 0, 0], [1., 0, 0, 0], [0, 0, 1., 0], [0, 0, 0, 1.]])
+    GeneratorPlan([16, 16, 16], True, 0, GEN_LABELS, None, 1., None, aff=np.eye(4))
+    GeneratorPlan([16, 16, 16], True, 0, GEN_LABELS, None, 1., None, aff=swapped, flipping=False)
+    with pytest.raises(NotImplementedError, match='flipping along axis 1'):
+        GeneratorPlan([16, 16, 16], True, 0, GEN_LABELS, None, 1., None, aff=swapped)
