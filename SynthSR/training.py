@@ -104,6 +104,12 @@ def training(labels_dir,
             work_with_residual_channel = [int(c) for c in work_with_residual_channel]
     if segmentation_model_file is not None:
         add_seg_loss_to_model()
+    # options the engine does not implement fail here, before any GPU work, instead of silently training something else
+    if activation != 'elu':
+        raise NotImplementedError("activation %r: the engine implements the reference's default 'elu' only "
+                                  "(ELU and its derivative are fused into the convolution epilogues)" % (activation,))
+    if regression_metric not in ('l1', 'l2'):
+        metrics_model(None, metrics=regression_metric)      # raises like the reference / NotImplementedError for ssim, laplace
 
     generation_labels, n_neutral_labels = utils.get_list_labels(label_list=path_generation_labels,
                                                                 labels_dir=labels_dir, FS_sort=FS_sort)

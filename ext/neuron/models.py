@@ -148,6 +148,7 @@ def unet(nb_features, input_shape, nb_levels, conv_size, nb_labels, name='unet',
     if layer_nb_feats is not None: unsupported.append('layer_nb_feats')
     if conv_dropout: unsupported.append('conv_dropout')
     if batch_norm != -1: unsupported.append('batch_norm')
+    if (prefix if prefix is not None else name) != 'unet': unsupported.append('name/prefix (layer names are unet_*)')
     if unsupported:
         raise NotImplementedError('unet(): options outside the SynthSR training configuration: %s' % ', '.join(unsupported))
     if input_model is not None:

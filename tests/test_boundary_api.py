@@ -58,6 +58,9 @@ def test_unet_rejects_unsupported_options():
         unet(24, [32, 32, 32, 1], 5, 3, 1, feat_mult=2, nb_conv_per_level=2, batch_norm=-1)
     with pytest.raises(NotImplementedError, match='batch_norm'):
         unet(24, [32, 32, 32, 1], 5, 3, 1, feat_mult=2, nb_conv_per_level=2, final_pred_activation='linear')
+    with pytest.raises(NotImplementedError, match='name/prefix'):
+        unet(24, [32, 32, 32, 1], 5, 3, 1, feat_mult=2, nb_conv_per_level=2, final_pred_activation='linear', batch_norm=-1,
+             prefix='seg')
 
 
 def test_nifti_roundtrip_and_volume_info(tmp_path):
@@ -134,3 +137,18 @@ def test_build_model_inputs_matches_reference_draw_for_draw(tmp_path):
                 ref = G['%s_it%d_%d' % (name, it, j)]
                 assert np.asarray(a).shape == ref.shape, (name, it, j)
                 np.testing.assert_array_equal(np.asarray(a), ref, err_msg='%s it%d input %d' % (name, it, j))
+
+
+def test_training_refuses_options_the_engine_does_not_implement(tmp_path):
+    """accepted by the reference, not by this engine: must raise before any work instead of silently training something else."""
+    from SynthSR.training import training
+    with pytest.raises(NotImplementedError, match="activation 'relu'"):
+        training('x', str(tmp_path), None, None, None, activation='relu')
+    with pytest.raises(NotImplementedError, match='ssim'):
+        training('x', str(tmp_path), None, None, None, regression_metric='ssim')
+    with pytest.raises(NotImplementedError, match='laplace'):
+        training('x', str(tmp_path), None, None, None, regression_metric='laplace')
+    with pytest.raises(Exception, match='metrics should either be'):
+        training('x', str(tmp_path), None, None, None, regression_metric='huber')
+    with pytest.raises(NotImplementedError, match='segmentation'):
+        training('x', str(tmp_path), None, None, None, segmentation_model_file='seg.h5')
