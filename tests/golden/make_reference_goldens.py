@@ -119,6 +119,25 @@ def main():
                    [0, 24, 4, 43, 17, 53, 2, 41]]:
         ll, nn = utils.get_list_labels(label_list=labels, FS_sort=True)
         out['fs_sort'].append({'labels': labels, 'sorted': [int(v) for v in ll], 'n_neutral': int(nn)})
+    # get_list_labels scanning a folder of label maps (training() without path_generation_labels) and get_volume_info on .npz
+    import tempfile
+    out['labels_dir'] = []
+    rng = np.random.default_rng(5)
+    for pools, fs in [([[0, 2, 3, 41, 42], [0, 3, 4, 14, 43], [0, 16, 24, 2, 41]], True),
+                      ([[0, 5, 9, 1], [7, 3, 0]], False)]:
+        d = tempfile.mkdtemp()
+        maps = []
+        for i, pool in enumerate(pools):
+            m = np.array(pool)[rng.integers(0, len(pool), size=(4, 5, 3))].astype(np.int32)
+            m.reshape(-1)[:len(pool)] = pool
+            np.savez(os.path.join(d, 'lab%d.npz' % i), vol_data=m)
+            maps.append(m.tolist())
+        ll, nn = utils.get_list_labels(labels_dir=d, FS_sort=fs)
+        info = utils.get_volume_info(os.path.join(d, 'lab0.npz'), aff_ref=np.eye(4))
+        out['labels_dir'].append({'maps': maps, 'FS_sort': fs, 'labels': [int(v) for v in ll], 'n_neutral': None if nn is None else int(nn),
+                                  'info_shape': [int(v) for v in info[0]], 'info_aff': np.asarray(info[1]).tolist(),
+                                  'info_n_dims': int(info[2]), 'info_n_channels': int(info[3]),
+                                  'info_res': [float(v) for v in info[5]]})
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'reference_host_logic.json')
     json.dump(out, open(path, 'w'), indent=1)
     print('wrote', path, {k: len(v) for k, v in out.items()})

@@ -84,6 +84,17 @@ def test_host_logic_matches_reference():
     for c in H['fs_sort']:
         ll, nn = U.get_list_labels(label_list=c['labels'], FS_sort=True)
         assert [int(v) for v in ll] == c['sorted'] and nn == c['n_neutral']
+    import tempfile
+    for c in H['labels_dir']:                              # folder scan (training() without a label list) + .npz volume info
+        d = tempfile.mkdtemp()
+        for i, m in enumerate(c['maps']):
+            np.savez(os.path.join(d, 'lab%d.npz' % i), vol_data=np.array(m, dtype=np.int32))
+        ll, nn = U.get_list_labels(labels_dir=d, FS_sort=c['FS_sort'])
+        assert [int(v) for v in ll] == c['labels'] and (None if nn is None else int(nn)) == c['n_neutral']
+        info = U.get_volume_info(os.path.join(d, 'lab0.npz'), aff_ref=np.eye(4))
+        assert [int(v) for v in info[0]] == c['info_shape'] and int(info[2]) == c['info_n_dims'] and int(info[3]) == c['info_n_channels']
+        np.testing.assert_allclose(np.asarray(info[1]), np.array(c['info_aff']))
+        np.testing.assert_allclose([float(v) for v in info[5]], c['info_res'])
 
 
 def test_randomise_res_branch_bit_exact():
