@@ -2,11 +2,35 @@
 random label map(s), draws per-class GMM means/stds from the priors, yields [labels, means, stds(, image)].
 
 Difference from the reference: decoded label maps are cached (the reference re-decodes a gzip NIfTI every step,
-:91, which alone would cap throughput below 20 volumes/s)."""
+:91, which alone would cap throughput below 20 volumes/s).  The cache is least-recently-used with a byte budget
+(SSR_LABEL_CACHE_GB, default 8), so a dataset of thousands of label maps degrades to re-decoding instead of exhausting
+host memory."""
+import os
+from collections import OrderedDict
+
 import numpy as np
 import numpy.random as npr
 
 from ext.lab2im import utils
+
+
+class _VolumeCache(OrderedDict):
+    def __init__(self, budget_bytes):
+        super().__init__()
+        self.budget, self.used = int(budget_bytes), 0
+
+    def get_or_load(self, key, loader):
+        if key in self:
+            self.move_to_end(key)
+            return self[key]
+        vol = loader()
+        if vol.nbytes <= self.budget:
+            self[key] = vol
+            self.used += vol.nbytes
+            while self.used > self.budget:
+                _, old = self.popitem(last=False)
+                self.used -= old.nbytes
+        return vol
 
 
 def build_model_inputs(path_label_maps, n_labels, prior_means, prior_stds, prior_distributions, path_images=None,
@@ -15,12 +39,11 @@ def build_model_inputs(path_label_maps, n_labels, prior_means, prior_stds, prior
     if generation_classes is None:
         generation_classes = np.arange(n_labels)
     n_classes = len(np.unique(generation_classes))
-    cache = {} if cache is None else cache
+    if cache is None:
+        cache = _VolumeCache(float(os.environ.get('SSR_LABEL_CACHE_GB', '8')) * (1 << 30))
 
     def load(path, dtype):
-        if (path, dtype) not in cache:
-            cache[(path, dtype)] = utils.load_volume(path, dtype=dtype, aff_ref=np.eye(4))
-        return cache[(path, dtype)]
+        return cache.get_or_load((path, dtype), lambda: utils.load_volume(path, dtype=dtype, aff_ref=np.eye(4)))
 
     while True:
         indices = npr.randint(len(path_label_maps), size=batchsize)

@@ -152,3 +152,24 @@ def test_training_refuses_options_the_engine_does_not_implement(tmp_path):
         training('x', str(tmp_path), None, None, None, regression_metric='huber')
     with pytest.raises(NotImplementedError, match='segmentation'):
         training('x', str(tmp_path), None, None, None, segmentation_model_file='seg.h5')
+
+
+def test_label_map_cache_is_bounded(tmp_path, monkeypatch):
+    """decoded label maps are cached least-recently-used within a byte budget (the reference re-decodes every step)."""
+    from SynthSR.model_inputs import _VolumeCache, build_model_inputs
+    c = _VolumeCache(3 * 800)
+    loads = []
+    for k in [0, 1, 2, 0, 3, 1]:
+        c.get_or_load(k, lambda k=k: loads.append(k) or np.zeros(100, np.float64))      # 800 bytes each
+    assert loads == [0, 1, 2, 3, 1] and list(c) == [0, 3, 1] and c.used == 2400         # 1 was evicted by 3, reloaded
+    big = _VolumeCache(100)
+    assert big.get_or_load('x', lambda: np.zeros(100)).shape == (100,) and len(big) == 0  # larger than the budget: not kept
+    paths = []
+    for i in range(3):
+        paths.append(str(tmp_path / ('m%d.npz' % i)))
+        np.savez(paths[-1], vol_data=np.full((4, 4, 4), i, np.int32))
+    monkeypatch.setenv('SSR_LABEL_CACHE_GB', '1e-9')                                    # ~1 byte: nothing is cached
+    g = build_model_inputs(paths, 3, None, None, 'uniform')
+    for _ in range(4):
+        lab, means, stds = next(g)
+        assert lab.shape == (1, 4, 4, 4, 1) and means.shape == (1, 3, 1)
