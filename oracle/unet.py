@@ -155,6 +155,47 @@ def loss_fn(pred, image, target, metric='l1', work_with_residual_channel=None, l
     raise NotImplementedError(metric)
 
 
+def seg_regularised_loss(image_loss, predicted_image, seg_target, seg_params, generation_labels, equivalency, rel_weight,
+                         loss_cropping=None, m=None, M=None, fs_header=False, nb_levels=5):
+    """SynthSR/metrics_model.py:136-215 (`add_seg_loss_to_model`) + ext/lab2im/layers.py:1334-1376 (`DiceLoss`,
+    enable_checks=False, no class / boundary weights): image loss + rel_weight * soft Dice between the one-hot segmentation
+    target and the prediction of a frozen segmentation U-Net (softmax head) applied to the predicted image.
+    SURVEY.md 8f rank 4 -- oracle only, the GPU side is not built yet.  predicted_image [B,X,Y,Z,1], seg_target [B,X,Y,Z,1] int.
+
+    Kept as the reference has them: the ground-truth map of generation label i is `seg_target == i` -- the loop INDEX, not the
+    label value generation_labels[i] (:188); the frozen network's BatchNorm normalises with batch statistics while fitting
+    (Keras 2.3.1 BatchNormalization.call ignores `trainable`; restated, unpinned)."""
+    x = predicted_image
+    if m is not None:
+        x = (torch.clamp(x, m, M) - m) / (M - m)                                       # :154
+    if fs_header:
+        x = x.permute(0, 1, 3, 2, 4).flip(2)                                           # :158
+    seg = torch.softmax(forward(seg_params, x, training=True, nb_levels=nb_levels), dim=-1)
+    if fs_header:
+        seg = seg.flip(2).permute(0, 1, 3, 2, 4)                                       # :161-162
+    tgt = seg_target
+    if loss_cropping is not None:                                                      # :167-183
+        shp = predicted_image.shape[1:4]
+        lc = [loss_cropping] * 3 if isinstance(loss_cropping, int) else list(loss_cropping)
+        b = [int((shp[i] - lc[i]) / 2) for i in range(3)]
+        sl = (slice(None),) + tuple(slice(b[i], b[i] + lc[i]) for i in range(3))
+        tgt, seg = tgt[sl], seg[sl]
+    equivalency = np.asarray(equivalency)
+    gts, preds = [], []
+    for i in range(len(generation_labels)):                                            # :189-204
+        idx = np.where(equivalency == generation_labels[i])[0]
+        if len(idx) > 0:
+            if len(idx) > 3:
+                raise Exception("uuummm weird that you're merging so many labels...")
+            gts.append((tgt[..., -1] == i).to(seg.dtype))
+            preds.append(sum(seg[..., int(j)] for j in idx))
+    gt, pred = torch.stack(gts, -1), torch.stack(preds, -1)
+    top = (2 * gt * pred).sum(dim=(1, 2, 3))                                           # layers.py:1344, 1361
+    bottom = (gt ** 2 + pred ** 2).sum(dim=(1, 2, 3))
+    dice = (top + 1e-7) / (bottom + 1e-7)
+    return image_loss + rel_weight * (1 - dice).mean()                                 # layers.py:1364, 1376; :209
+
+
 def adam_init(params):
     return {'iterations': 0, 'm': {k: torch.zeros_like(params[k]) for k in trainable_names(params)},
             'v': {k: torch.zeros_like(params[k]) for k in trainable_names(params)}}

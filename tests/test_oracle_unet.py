@@ -190,3 +190,26 @@ def test_graph_built_by_the_reference_unet_function():
     for wrong in ('concat_swapped', 'skip_after_bn', 'relu'):
         p2 = OU.forward(params, torch.from_numpy(G['image'].astype(np.float64)), training=True, nb_levels=3, _wrong=(wrong,))
         assert np.abs(p2.numpy() - G['prediction']).max() > 1e-2, wrong
+
+
+def test_segmentation_regularised_loss_matches_reference():
+    """SURVEY.md 8f rank 4, oracle only (no GPU side yet): the reference's own add_seg_loss_to_model() + DiceLoss executed on
+    the stand-ins, its frozen segmentation network built by the reference's unet(final_pred_activation='softmax')
+    (tests/golden/make_reference_segloss_goldens.py), against oracle seg_regularised_loss -- label merging through the
+    equivalency table, ignored labels, centre cropping, intensity clipping, the FreeSurfer-header axis swap."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_segloss.npz'))
+    cases = {'plain': dict(rel_weight=.25), 'crop_clip_fs': dict(rel_weight=.5, loss_cropping=8, m=.1, M=.8, fs_header=True)}
+    for name, kw in cases.items():
+        pre = name + '_w/'
+        weights = {k[len(pre):]: G[k] for k in G.files if k.startswith(pre)}
+        n_seg = len(G[name + '_equiv'])
+        params = OU.init_params(0, 1, dtype=torch.float64, nb_features=4, nb_levels=3, feat_mult=2, nb_conv_per_level=2,
+                                nb_labels=n_seg)
+        assert {k for k in params if not k.endswith(('moving_mean', 'moving_variance'))} == set(weights)
+        for k, v in weights.items():
+            params[k] = torch.from_numpy(v.astype(np.float64))
+        total = OU.seg_regularised_loss(float(G[name + '_image_loss']), torch.from_numpy(G[name + '_pred_image'].astype(np.float64)),
+                                        torch.from_numpy(G[name + '_seg_target']), params, G['generation_labels'],
+                                        G[name + '_equiv'], nb_levels=3, **kw)
+        np.testing.assert_allclose(float(total), float(G[name + '_total']), rtol=1e-9)
