@@ -32,5 +32,6 @@ def metrics_model(input_model, loss_cropping=16, metrics='l1', work_with_residua
 
 
 def add_seg_loss_to_model(*args, **kwargs):
-    raise NotImplementedError('segmentation-regularised loss (frozen second U-Net + Dice, metrics_model.py:136-215) '
-                              'is listed as a next-tier component (SURVEY.md 8f #4)')
+    raise NotImplementedError('segmentation-regularised loss (frozen second U-Net + Dice, metrics_model.py:136-215; SURVEY.md '
+                              '8f #4): the GPU implementation (synthsr_b200/seg_loss.py) has not been validated on a B200 '
+                              'yet and is off by default -- set SSR_ENABLE_SEG_LOSS=1 to use it')

@@ -102,8 +102,8 @@ def training(labels_dir,
                                  'for a single output channel' % (2 * len(work_with_residual_channel),
                                                                   len(work_with_residual_channel)))
             work_with_residual_channel = [int(c) for c in work_with_residual_channel]
-    if segmentation_model_file is not None:
-        add_seg_loss_to_model()
+    if segmentation_model_file is not None and os.environ.get('SSR_ENABLE_SEG_LOSS') != '1':
+        add_seg_loss_to_model()      # raises: the GPU side exists (synthsr_b200/seg_loss.py) but has not been validated yet
     # options the engine does not implement fail here, before any GPU work, instead of silently training something else
     if activation != 'elu':
         raise NotImplementedError("activation %r: the engine implements the reference's default 'elu' only "
@@ -146,11 +146,27 @@ def training(labels_dir,
         torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', 0)))
         if not dist.is_initialized():
             dist.init_process_group('nccl')
+    seg = None
+    if segmentation_model_file is not None:          # training.py:371-411: frozen segmentation U-Net + Dice regulariser
+        from synthsr_b200 import h5lite
+        from synthsr_b200.seg_loss import SegRegulariser
+        segmentation_labels = np.load(segmentation_label_list)
+        seg_sd, _ = h5lite.load_keras_weights(segmentation_model_file)
+        if images_dir is None:
+            m = M = None
+        else:                                        # clip the synthesised image at the 2nd / 98th percentile of the first scan
+            im = utils.load_volume(utils.list_images_in_folder(images_dir)[0], im_only=True).flatten()
+            m, M = np.percentile(im, 2), np.percentile(im, 98)
+        seg = SegRegulariser(plan.output_shape, batchsize, seg_sd, len(segmentation_labels), generation_labels,
+                             utils.load_array_if_path(segmentation_label_equivalency), relative_weight_segmentation,
+                             loss_cropping=loss_cropping, m=m, M=M, fs_header=fs_header_segnet, nb_features=unet_feat_count,
+                             nb_levels=n_levels, conv_size=conv_size, feat_mult=feat_multiplier,
+                             nb_conv_per_level=nb_conv_per_level)
     engine = TrainingEngine(plan, batchsize=batchsize, nb_features=unet_feat_count, nb_levels=n_levels,
                             conv_size=conv_size, feat_mult=feat_multiplier, nb_conv_per_level=nb_conv_per_level,
                             nb_labels=nb_labels_unet, lr=lr, lr_decay=lr_decay, metric=regression_metric,
                             work_with_residual_channel=work_with_residual_channel, loss_cropping=loss_cropping,
-                            rank=rank, world_size=world)
+                            rank=rank, world_size=world, seg=seg)
     # the Keras-style handles the reference builds (kept so client code can introspect the same objects)
     model = metrics_model(nrn_models.UnetModel(engine.net, brain_generator.labels_to_image_model),
                           loss_cropping=loss_cropping, metrics=regression_metric,

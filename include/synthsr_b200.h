@@ -232,6 +232,31 @@ int ssr_head_loss_bnsums(const float* feat, const float* feat_stats, const float
 int ssr_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
                   float eps, float grad_scale, void* stream);
 
+/* ---------------------------------------------------------------- segmentation-regularised loss (8f rank 4) -- */
+/* SynthSR/metrics_model.py:136-215 (add_seg_loss_to_model) + ext/lab2im/layers.py:1334-1376 (DiceLoss, enable_checks=False).
+ * NOT YET VALIDATED ON A B200; oracle: oracle/unet.py:seg_regularised_loss.
+ * input of the frozen segmentation network: y = pred (+ image[..., res_channel]) [-> (clip(y, m, M) - m) / (M - m)]  (:151-154) */
+int ssr_seg_input(const float* pred, const float* image, int image_channels, int res_channel, int use_clip, float m, float M,
+                  float* y, long long nvox, void* stream);
+int ssr_seg_input_bwd(const float* pred, const float* image, int image_channels, int res_channel, int use_clip, float m,
+                      float M, const float* dy, float* dpred, long long nvox, void* stream);
+/* softmax over S segmentation logits per voxel, channels merged into K generation classes (cls_of_seg[j] = class or -1,
+ * device int[S]); gt of class k = [label == gt_value[k]] (device int[K]; the reference compares with the loop index, :188);
+ * sums [B][K][2] doubles = sum 2 gt p | sum gt^2 + p^2 over the (optionally cropped, HOST int[3] size / begin) volume. */
+int ssr_softmax_dice_sums(const float* logits, int S, const int* labels, const int* cls_of_seg, const int* gt_value, int K,
+                          int B, int d0, int d1, int d2, const int* crop_size, const int* crop_begin, double* sums,
+                          void* stream);
+/* loss[0] += rel_weight * mean_{b,k} (1 - (top + 1e-7) / (bottom + 1e-7))   (layers.py:1363-1376, metrics_model.py:209) */
+int ssr_dice_finalize(const double* sums, int B, int K, double rel_weight, double* loss, void* stream);
+/* gradient of rel_weight * dice loss w.r.t. the logits (zero outside the crop) */
+int ssr_softmax_dice_grad(const float* logits, int S, const int* labels, const int* cls_of_seg, const int* gt_value, int K,
+                          int B, int d0, int d1, int d2, const int* crop_size, const int* crop_begin, const double* sums,
+                          float rel_weight, float* dlogits, void* stream);
+/* extra gradient e = dL_dice/d(prediction) [nvox] through the main network's single-output 1x1x1 head: dfeat += e w^T,
+ * dw += feat^T e, db += sum e; feat_stats (optional): the folded BatchNorm of ssr_head_loss (x * s[2C+c] + s[3C+c]). */
+int ssr_head_extra_grad(const float* feat, const float* feat_stats, const float* w, const float* e, long long nvox, int C,
+                        float* dfeat, float* dw, float* db, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

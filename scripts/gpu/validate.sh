@@ -8,6 +8,8 @@ echo "== gpu tests"
 timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -8
 echo "== generator entry points vs the host emulator (opt-in cross-check)"
 SSR_KERNEL_CROSSCHECK=1 timeout 600 python -m pytest tests/test_generator_entry_points_gpu.py -m gpu -q 2>&1 | tail -8
+echo "== segmentation-regularised loss (opt-in, first GPU contact)"
+SSR_ENABLE_SEG_LOSS=1 timeout 900 python -m pytest tests/test_seg_loss_gpu.py -m gpu -q 2>&1 | tail -12
 echo "== smoke"
 timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2
 echo "== bench"

@@ -20,6 +20,7 @@ SOURCES = [
     ('generator.cu', ['-fmad=false']),
     ('unet_kernels.cu', []),
     ('conv_tc.cu', []),
+    ('seg_loss.cu', []),
 ]
 
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')

@@ -17,14 +17,22 @@ from .unet import UNet3D
 class TrainingEngine:
     def __init__(self, plan, batchsize=1, nb_features=24, nb_levels=5, conv_size=3, feat_mult=2, nb_conv_per_level=2,
                  nb_labels=None, lr=1e-4, lr_decay=0., metric='l1', work_with_residual_channel=None,
-                 loss_cropping=None, conv_impl='tc', seed=0, device='cuda', rank=0, world_size=1):
+                 loss_cropping=None, conv_impl='tc', seed=0, device='cuda', rank=0, world_size=1, seg=None):
+        """seg: optional synthsr_b200.seg_loss.SegRegulariser (segmentation-regularised loss, metrics_model.py:136-215)."""
         self.plan, self.B = plan, int(batchsize)
         self.device = torch.device(device)
         self.rank, self.world = int(rank), int(world_size)
         self.gen = SynthGenerator(plan, batchsize, device)
         nb_labels = plan.n_target_channels if nb_labels is None else nb_labels
-        self.net = UNet3D(plan.image_shape, nb_features, nb_levels, conv_size, nb_labels, feat_mult, nb_conv_per_level,
-                          batchsize, device, conv_impl, seed=seed)        # same seed on every rank: identical replicas
+        self.seg = seg
+        if seg is None:
+            self.net = UNet3D(plan.image_shape, nb_features, nb_levels, conv_size, nb_labels, feat_mult, nb_conv_per_level,
+                              batchsize, device, conv_impl, seed=seed)    # same seed on every rank: identical replicas
+        else:
+            from .seg_loss import SegRegularisedUNet3D
+            assert plan.crop_shape == plan.output_shape, 'the segmentation target lives on the crop grid (target_res = atlas_res)'
+            self.net = SegRegularisedUNet3D(plan.image_shape, nb_features, nb_levels, conv_size, nb_labels, feat_mult,
+                                            nb_conv_per_level, batchsize, device, conv_impl, seed=seed, seg=seg)
         self.lr, self.lr_decay, self.metric = lr, lr_decay, metric
         self.residual, self.loss_cropping = work_with_residual_channel, loss_cropping
         self.rng = np.random.default_rng(seed * 1000003 + 7919 * self.rank)   # per-rank augmentation stream
@@ -42,6 +50,8 @@ class TrainingEngine:
         if draws is None:
             draws = sample_draws(self.rng, self.plan, self.B)
         image, target = self.gen.run(labels, means, stds, draws, real_image=real_image, seed=self.seed)
+        if self.seg is not None:
+            self.net.seg_labels = self.gen.labels                         # `segmentation_target` of this batch
         loss = self.net.loss_and_grad(image, target, self.metric, self.residual, self.loss_cropping)
         scale = 1.
         if self.world > 1:
@@ -92,6 +102,8 @@ class TrainingEngine:
         image, target, k = self._pending
         self._pending = None
         torch.cuda.current_stream().wait_event(self._gen_done[k])
+        if self.seg is not None:
+            self.net.seg_labels = self._gens[k].labels
         loss = self.net.loss_and_grad(image, target, self.metric, self.residual, self.loss_cropping)
         scale = 1.
         if self.world > 1:

@@ -213,3 +213,29 @@ def test_segmentation_regularised_loss_matches_reference():
                                         torch.from_numpy(G[name + '_seg_target']), params, G['generation_labels'],
                                         G[name + '_equiv'], nb_levels=3, **kw)
         np.testing.assert_allclose(float(total), float(G[name + '_total']), rtol=1e-9)
+
+
+def test_class_tables_formulation_of_the_dice_matches_reference():
+    """the (cls_of_seg, gt_value) tables the CUDA Dice kernels take (synthsr_b200.seg_loss.class_tables) express the reference's
+    label-merging loop: softmax -> merge by table -> soft Dice on the reference-executed golden gives the reference's total."""
+    import os
+    from synthsr_b200.seg_loss import class_tables
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_segloss.npz'))
+    name = 'plain'
+    pre = name + '_w/'
+    weights = {k[len(pre):]: G[k] for k in G.files if k.startswith(pre)}
+    equiv = G[name + '_equiv']
+    params = OU.init_params(0, 1, dtype=torch.float64, nb_features=4, nb_levels=3, feat_mult=2, nb_conv_per_level=2,
+                            nb_labels=len(equiv))
+    for k, v in weights.items():
+        params[k] = torch.from_numpy(v.astype(np.float64))
+    logits = OU.forward(params, torch.from_numpy(G[name + '_pred_image'].astype(np.float64)), training=True, nb_levels=3)
+    cls, gtv = class_tables(G['generation_labels'], equiv)
+    s = torch.softmax(logits, -1)
+    K = len(gtv)
+    p = torch.stack([sum(s[..., j] for j in range(len(cls)) if cls[j] == k) for k in range(K)], -1)
+    lab = torch.from_numpy(G[name + '_seg_target'])[..., 0]
+    gt = torch.stack([(lab == int(gtv[k])).double() for k in range(K)], -1)
+    top, bot = (2 * gt * p).sum((1, 2, 3)), (gt ** 2 + p ** 2).sum((1, 2, 3))
+    total = float(G[name + '_image_loss']) + .25 * float((1 - (top + 1e-7) / (bot + 1e-7)).mean())
+    np.testing.assert_allclose(total, float(G[name + '_total']), rtol=1e-9)
