@@ -18,7 +18,7 @@ from ext.neuron import models as nrn_models
 _HOME = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def build_unet(n_channels=1, model_file=None, conv_impl='tc'):
+def build_unet(n_channels=1, model_file=None, conv_impl='tc3'):
     """the U-Net of the shipped models (predict_command_line.py:66-77) with weights from a Keras .h5 file."""
     unet_model = nrn_models.unet(nb_features=24, input_shape=[None, None, None, n_channels], nb_levels=5, conv_size=3,
                                  nb_labels=1, feat_mult=2, nb_conv_per_level=2, conv_dropout=0,
@@ -91,7 +91,7 @@ def predict_volume(unet_model, im, aff, ct=False, disable_flipping=False):
     return postprocess(output, idx, shape), aff2
 
 
-def predict(path_images, path_predictions, model=None, ct=False, disable_flipping=False, conv_impl='tc'):
+def predict(path_images, path_predictions, model=None, ct=False, disable_flipping=False, conv_impl='tc3'):
     """super-resolve / synthesise 1 mm MP-RAGEs from the scans in `path_images` (file or folder)."""
     unet_model = build_unet(1, model if model is not None else os.path.join(_HOME, 'models/SynthSR_v10_210712.h5'), conv_impl)
     images, preds = _io_lists(path_images, path_predictions)
@@ -105,7 +105,7 @@ def predict(path_images, path_predictions, model=None, ct=False, disable_flippin
     return preds
 
 
-def predict_hyperfine(path_t1_images, path_t2_images, path_predictions, model=None, conv_impl='tc'):
+def predict_hyperfine(path_t1_images, path_t2_images, path_predictions, model=None, conv_impl='tc3'):
     """T1 + T2 Hyperfine pairs (1.5 x 1.5 x 5 mm) -> 1 mm MP-RAGE; the network predicts a residual on the T1 channel
     (predict_command_line_hyperfine.py:108-133, including its intensity scalings)."""
     unet_model = build_unet(2, model if model is not None else os.path.join(_HOME, 'models/SynthSR_v10_210712_hyperfine.h5'),

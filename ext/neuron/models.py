@@ -130,7 +130,7 @@ class UnetModel:
 def unet(nb_features, input_shape, nb_levels, conv_size, nb_labels, name='unet', prefix=None, feat_mult=1, pool_size=2,
          use_logp=True, padding='same', dilation_rate_mult=1, activation='elu', skip_n_concatenations=0,
          use_residuals=False, final_pred_activation='softmax', nb_conv_per_level=1, add_prior_layer=False,
-         layer_nb_feats=None, conv_dropout=0, batch_norm=None, input_model=None, batchsize=1, conv_impl='tc', seed=None):
+         layer_nb_feats=None, conv_dropout=0, batch_norm=None, input_model=None, batchsize=1, conv_impl='tc3', seed=None):
     """Same keyword names as the reference.  The engine implements the configuration SynthSR.training() uses
     (training.py:330-341): 'same' padding, ELU, batch_norm=-1, 2 convs per level, no residuals/dropout/dilation,
     linear final activation; anything else raises NotImplementedError instead of silently differing."""

@@ -155,6 +155,22 @@ int ssr_conv3d_fwd_tc_k2n_stats(const float* x, int C, const float* wp, const fl
  * dx = conv(dy, wp) * elu'(h), dbias[c] += sum_v dx[v][c]; h = that convolution's forward output.  Cout = 24 or 32. */
 int ssr_conv3d_dgrad_tc_k2n_elu(const float* dy, int C, const float* wp, const float* h, float* dx, float* dbias, int B,
                                 int d0, int d1, int d2, int Cout, void* stream);
+/* Compensated forward ("3xTF32"): fp32-class accuracy of KL.Conv3D (fp32 in the reference, ext/neuron/models.py:316,444,
+ * 481) on the TF32 tensor cores.  With x = x_hi + x_lo (x_hi = what the TMA's TFLOAT32 load makes of x, x_lo =
+ * ssr_tf32_residual(x)) and w = w_hi + w_lo (pack mode 5: Cin1 = total input channels of the kernel, Cin2 = (first channel
+ * << 12) | channels; pack mode 6: the lo part in the k2n layout of mode 2) the convolution is evaluated as ONE implicit
+ * GEMM over K = [x | x_lo | x] against [w_hi | w_hi | w_lo] (level 3), or [x | x_lo] against [w_hi | w_hi] (level 2).
+ * sums (or NULL): BatchNorm sums of the output, as ssr_conv3d_fwd_tc_stats; accumulate: add to the partial result in y. */
+int ssr_tf32_residual(const float* x, float* lo, long long n, void* stream);
+int ssr_conv3d_fwd_tc_comp(const float* x, const float* xlo, int C, const float* wp, const float* bias, float* y,
+                           double* sums, int B, int d0, int d1, int d2, int Cout, int act, int accumulate, int level,
+                           void* stream);
+int ssr_conv3d_fwd_tc_up_comp(const float* low, const float* lowlo, int Cup, const float* wp8c, float* y, int B, int d0,
+                              int d1, int d2, int Cout, int level, void* stream);
+/* last channel part of a k2n convolution + the BatchNorm sums of the finished output (sums zeroed here) */
+int ssr_conv3d_fwd_tc_k2n_part_stats(const float* x, int Ctot, int c0, int C, const float* wp, const float* bias, float* y,
+                                     double* sums, int B, int d0, int d1, int d2, int Cout, int act, int accumulate,
+                                     void* stream);
 int ssr_conv3d_wgrad_tc(const float* x1, int C1, const float* x2, int C2, const float* dy, float* dw, float* db,
                         float* scratch, long long scratch_bytes, int B, int d0, int d1, int d2, int Cout,
                         void* stream);

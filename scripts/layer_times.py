@@ -10,7 +10,7 @@ from synthsr_b200.trainer import TrainingEngine
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 160
 maps, pm, ps, gl, gc = bench.make_inputs(size, 2, seed=0)
 plan = GeneratorPlan([size] * 3, True, 0, gl, None, 1., None, **bench.TRAINING_DEFAULTS)
-eng = TrainingEngine(plan, batchsize=1, conv_impl='tc', seed=0)
+eng = TrainingEngine(plan, batchsize=1, conv_impl=os.environ.get('SSR_CONV_IMPL', 'tc3'), seed=0)
 dev = [torch.from_numpy(m[None]).cuda() for m in maps]
 rng = np.random.default_rng(0)
 for i in range(3):

@@ -216,7 +216,7 @@ constexpr int TM1 = 16, TM2 = 8;                  // output tile: 16 (d1) x 8 (d
 constexpr int SLAB_ROWS = (TM1 + 2) * TM2;         // 144 rows x 128 B
 constexpr int SLAB_BYTES = SLAB_ROWS * 128;        // 18432 (multiple of 1024)
 constexpr int SB = 2;                              // B-group stages
-constexpr int MAX_CHUNKS = 24;
+constexpr int MAX_CHUNKS = 40;                   // 12 chunks (384 channels) x 3 terms of a compensated convolution
 
 struct TcGeom {
   int B, D0, D1, D2;
@@ -237,6 +237,8 @@ struct TcGeom {
   unsigned char chunk_src[MAX_CHUNKS];    // 0: x1, 1: x2
   unsigned char chunk_ks[MAX_CHUNKS];     // K-steps of 8 channels actually present in the chunk (1..4)
   short chunk_c0[MAX_CHUNKS];             // first channel of the chunk inside its source
+  unsigned char chunk_w[MAX_CHUNKS];      // chunk of the PACKED WEIGHTS this chunk multiplies (== index, except in the
+                                          // compensated forward, where [x | x_lo | x] meet [w_hi | w_hi | w_lo])
 };
 
 __device__ __forceinline__ bool slab_needed(const TcGeom& G, int z0, int k0g, int zin) {
@@ -386,7 +388,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
               mbar_expect_tx(fullB + sb, (uint32_t)bgroup_bytes);
               for (int kk = 0; kk < G.KG; ++kk)
                 for (int k1 = 0; k1 < 3; ++k1) {
-                  const int row = (((ch * 3 + k2) * 3 + (k0g + kk)) * 3 + k1) * G.Npad + n0;
+                  const int row = (((G.chunk_w[ch] * 3 + k2) * 3 + (k0g + kk)) * 3 + k1) * G.Npad + n0;
                   tma_load_2d(&map_w, fullB + sb, sB + (size_t)sb * bgroup_bytes + (size_t)(kk * 3 + k1) * G.NT * 128, 0, row);
                 }
               if (++sb == SB) { sb = 0; pb ^= 1; }
@@ -628,7 +630,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
 //                       part of the GEMM.
 // Same tiling / pipeline / warp roles as conv3d_tc_kernel (its protocol is kept line by line).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int UP_MAX_CHUNKS = 8;
+constexpr int UP_MAX_CHUNKS = 24;                 // 8 chunks (256 channels) x 3 terms of a compensated convolution
 
 struct UpGeom {
   int B, D0, D1, D2;     // LOW-resolution grid = GEMM rows
@@ -639,6 +641,8 @@ struct UpGeom {
   int par_rows;          // rows of the packed weights per parity class (= nchunks * 27 * Npad)
   unsigned char chunk_ks[UP_MAX_CHUNKS];
   short chunk_c0[UP_MAX_CHUNKS];
+  unsigned char chunk_src[UP_MAX_CHUNKS];   // MODE 1: tensor map of the chunk (0: x, 1: its TF32 residual x_lo)
+  unsigned char chunk_w[UP_MAX_CHUNKS];     // chunk of the packed weights (see TcGeom::chunk_w)
 };
 struct UpMaps { CUtensorMap x[8]; };
 
@@ -669,7 +673,7 @@ conv3d_tc_up_kernel(const __grid_constant__ UpMaps maps, const __grid_constant__
     fence_proxy_async();
   }
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < (MODE == 2 ? 8 : 1); ++i) tma_prefetch_desc(&maps.x[i]);
+    for (int i = 0; i < (MODE == 2 ? 8 : 2); ++i) tma_prefetch_desc(&maps.x[i]);
     tma_prefetch_desc(&map_w);
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)G.tmem_cols);
@@ -707,10 +711,10 @@ conv3d_tc_up_kernel(const __grid_constant__ UpMaps maps, const __grid_constant__
         for (int pk = 0; pk < NPK; ++pk) {
           const int par = MODE == 1 ? tpar : pk;
           UP_TAPS(par)
-          const CUtensorMap* mx = &maps.x[MODE == 2 ? pk : 0];
           for (int ch = 0; ch < G.nchunks; ++ch) {
+            const CUtensorMap* mx = &maps.x[MODE == 2 ? pk : G.chunk_src[ch]];
             const int c0 = G.chunk_c0[ch];
-            const int brow = par * G.par_rows + ch * 27 * G.Npad + n0;
+            const int brow = par * G.par_rows + G.chunk_w[ch] * 27 * G.Npad + n0;
             for (int k2 = k2lo; k2 <= k2lo + 1; ++k2) {
               for (int k0g = 0; k0g < 3; k0g += G.KG) {
                 const int kk_lo = max(k0lo - k0g, 0), kk_hi = min(k0lo + 1 - k0g, G.KG - 1);
@@ -2216,6 +2220,22 @@ mma_microbench_kernel(float* __restrict__ out, int N, int nacc, int chain, int i
   if (warp == 1) tmem_dealloc(tb, 512);
 }
 
+__device__ __forceinline__ float tf32_lo(float v) {
+  uint32_t u = __float_as_uint(v);
+  u = (u + 0xFFFu + ((u >> 13) & 1u)) & ~0x1FFFu;      // round to nearest even on the 13 dropped bits (what the TMA does)
+  return v - __uint_as_float(u);
+}
+__global__ void tf32_residual_kernel(const float* __restrict__ x, float* __restrict__ lo, long long n) {
+  const long long n4 = n >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  float4* l4 = reinterpret_cast<float4*>(lo);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x4 + i);
+    l4[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) lo[(n4 << 2) + threadIdx.x] = tf32_lo(x[(n4 << 2) + threadIdx.x]);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // weight packing:  wp[chunk][k2][k0][k1][n][32]   (K-major rows of 32 input channels, zero padded)
 //   mode 0 (forward):       value = w[k0][k1][k2][cin(chunk, s)][n]
@@ -2223,8 +2243,9 @@ mma_microbench_kernel(float* __restrict__ out, int N, int nacc, int chain, int i
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pack_weights_body(const float* __restrict__ w, float* __restrict__ wp, int C1, int C2,
                                                   int Cout, int mode, int Npad, int nchunks, int nch1, int round_rn) {
-  const long long total = mode >= 2 ? 9LL * 96 * 32 : (long long)nchunks * 27 * Npad * 32;
-  const int Cin = C1 + C2;
+  const bool k2n_layout = mode >= 2 && mode != 5;
+  const long long total = k2n_layout ? 9LL * 96 * 32 : (long long)nchunks * 27 * Npad * 32;
+  const int Cin = mode == 5 ? C1 : C1 + C2;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int s = (int)(t & 31);
     long long r = t >> 5;
@@ -2234,7 +2255,8 @@ __device__ __forceinline__ void pack_weights_body(const float* __restrict__ w, f
     const int k2 = (int)(r % 3);
     const int ch = (int)(r / 3);
     float val = 0.f;
-    if (mode >= 2) {
+    bool lo_part = mode == 6;      // compensated forward: this entry holds w - rna_tf32(w) (then rounded itself)
+    if (k2n_layout) {
       // d2-taps-in-N layout of conv3d_tc_k2n_kernel: t = ((k0 * 3 + k1) * 96 + (k2 * 32 + n)) * 32 + s, one 32-channel chunk
       long long r2 = t >> 5;
       const int nn = (int)(r2 % 96); r2 /= 96;
@@ -2245,8 +2267,16 @@ __device__ __forceinline__ void pack_weights_body(const float* __restrict__ w, f
         const int coff = C2 >> 8, cn = C2 & 255;
         if (s < cn && no < Cout) val = w[((long long)((q0 * 3 + q1) * 3 + q2) * C1 + coff + s) * Cout + no];
       } else
-      if (mode == 2) { if (s < C1 && no < Cout) val = w[((long long)((q0 * 3 + q1) * 3 + q2) * Cin + s) * Cout + no]; }
+      if (mode == 2 || mode == 6) { if (s < C1 && no < Cout) val = w[((long long)((q0 * 3 + q1) * 3 + q2) * Cin + s) * Cout + no]; }
       else { if (s < Cout && no < Cin) val = w[((long long)(((2 - q0) * 3 + (2 - q1)) * 3 + (2 - q2)) * Cin + no) * Cout + s]; }
+    } else
+    if (mode == 5) {
+      // hi / lo split of the input channels [coff, coff + cn) of a (27, C1, Cout) kernel: chunks [0, nch1) hold rna(w),
+      // chunks [nch1, 2 nch1) hold rna(w - rna(w)); C2 = (coff << 12) | cn
+      const int coff = C2 >> 12, cn = C2 & 4095;
+      lo_part = ch >= nch1;
+      const int cl = (lo_part ? ch - nch1 : ch) * 32 + s;
+      if (cl < cn && n < Cout) val = w[((long long)((k0 * 3 + k1) * 3 + k2) * Cin + coff + cl) * Cout + n];
     } else
     if (mode == 0) {
       int c;   // concat channel index
@@ -2257,7 +2287,12 @@ __device__ __forceinline__ void pack_weights_body(const float* __restrict__ w, f
       const int co = ch * 32 + s;      // K runs over the layer's output channels
       if (co < Cout && n < Cin) val = w[((long long)(((2 - k0) * 3 + (2 - k1)) * 3 + (2 - k2)) * Cin + n) * Cout + co];
     }
-    if (round_rn) {   // round-to-nearest TF32 (the tensor core would otherwise truncate the low 13 mantissa bits)
+    if (lo_part) {
+      uint32_t u;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(val));
+      val -= __uint_as_float(u);                   // exact in fp32
+    }
+    if (round_rn || mode >= 5) {   // round-to-nearest TF32 (the tensor core would otherwise truncate the low 13 mantissa bits)
       uint32_t u;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(val));
       val = __uint_as_float(u);
@@ -2274,7 +2309,8 @@ __global__ void pack_weights_batch_kernel(const long long* __restrict__ jobs, in
   const long long* j = jobs + (long long)blockIdx.y * 6;
   const int C1 = (int)j[2], C2 = (int)j[3], Cout = (int)j[4], mode = (int)j[5];
   int Npad, nch, nch1;
-  if (mode >= 2) { Npad = 96; nch = 1; nch1 = 1; }
+  if (mode == 5) { Npad = (Cout + 15) / 16 * 16; nch1 = ((C2 & 4095) + 31) / 32; nch = 2 * nch1; }
+  else if (mode >= 2) { Npad = 96; nch = 1; nch1 = 1; }
   else if (mode == 0) { Npad = (Cout + 15) / 16 * 16; nch1 = (C1 + 31) / 32; nch = nch1 + (C2 + 31) / 32; }
   else { Npad = (C1 + C2 + 15) / 16 * 16; nch = (Cout + 31) / 32; nch1 = nch; }
   pack_weights_body(reinterpret_cast<const float*>(j[0]), reinterpret_cast<float*>(j[1]), C1, C2, Cout, mode, Npad, nch,
@@ -2374,6 +2410,7 @@ int ssr_conv3d_pack_weights_batch(const long long* jobs, int njobs, void* stream
   return SSR_OK;
 }
 long long ssr_conv3d_packed_size(int Cin1, int Cin2, int Cout, int mode) {
+  if (mode == 5) return 2LL * (((Cin2 & 4095) + 31) / 32) * 27 * round_up(Cout, 16) * 32;
   if (mode >= 2) return 9LL * 96 * 32;
   if (mode == 0) {
     const int nch = (Cin1 + 31) / 32 + (Cin2 + 31) / 32;
@@ -2384,15 +2421,18 @@ long long ssr_conv3d_packed_size(int Cin1, int Cin2, int Cout, int mode) {
 }
 
 int ssr_conv3d_pack_weights(const float* w, float* wp, int Cin1, int Cin2, int Cout, int mode, void* stream) {
-  SSR_CHECK_ARG(w && wp && Cin1 > 0 && Cin2 >= 0 && Cout > 0 && mode >= 0 && mode <= 4, "pack args");
-  SSR_CHECK_ARG(mode < 2 || mode == 4 || (Cin2 == 0 && Cin1 <= 32 && Cout <= 32), "k2n packing needs Cin <= 32, Cout <= 32");
+  SSR_CHECK_ARG(w && wp && Cin1 > 0 && Cin2 >= 0 && Cout > 0 && mode >= 0 && mode <= 6, "pack args");
+  SSR_CHECK_ARG(mode < 2 || mode == 4 || mode == 5 || (Cin2 == 0 && Cin1 <= 32 && Cout <= 32), "k2n packing needs Cin <= 32, Cout <= 32");
+  SSR_CHECK_ARG(mode != 5 || ((Cin2 & 4095) > 0 && (Cin2 >> 12) + (Cin2 & 4095) <= Cin1),
+                "hi/lo packing: Cin1 = total input channels, Cin2 = (first channel << 12) | channels");
   SSR_CHECK_ARG(mode != 4 || ((Cin2 & 255) <= 32 && (Cin2 >> 8) + (Cin2 & 255) <= Cin1 && Cout <= 32),
                 "part packing: Cin1 = total input channels, Cin2 = (first channel << 8) | channels (<= 32)");
   int Npad, nch, nch1;
-  if (mode >= 2) { Npad = 96; nch = 1; nch1 = 1; }
+  if (mode == 5) { Npad = round_up(Cout, 16); nch1 = ((Cin2 & 4095) + 31) / 32; nch = 2 * nch1; }
+  else if (mode >= 2) { Npad = 96; nch = 1; nch1 = 1; }
   else if (mode == 0) { Npad = round_up(Cout, 16); nch1 = (Cin1 + 31) / 32; nch = nch1 + (Cin2 + 31) / 32; }
   else { Npad = round_up(Cin1 + Cin2, 16); nch = (Cout + 31) / 32; nch1 = nch; }
-  const long long total = mode >= 2 ? 9LL * 96 * 32 : (long long)nch * 27 * Npad * 32;
+  const long long total = (mode >= 2 && mode != 5) ? 9LL * 96 * 32 : (long long)nch * 27 * Npad * 32;
   long long g = (total + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
   pack_weights_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(w, wp, Cin1, Cin2, Cout, mode, Npad, nch, nch1,
@@ -2406,7 +2446,10 @@ int ssr_conv3d_pack_weights(const float* w, float* wp, int Cin1, int Cin2, int C
 // Used for the data gradient too (x1 = dy, wp packed with mode 1, Cout = layer's Cin, bias NULL, act 0).
 static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, const float* wp, const float* bias, float* y,
                               int B, int D0, int D1, int D2, int Cout, int act, int accumulate, void* stream, int epi = 0,
-                              const float* elu_h = nullptr, float* dbias = nullptr, double* sums = nullptr) {
+                              const float* elu_h = nullptr, float* dbias = nullptr, double* sums = nullptr, int comp = 0) {
+  // comp (compensated forward, "3xTF32"): x2 = x1 - rne_tf32(x1) (ssr_tf32_residual), wp = hi/lo packing (mode 5);
+  // K = [x1 | x2 | x1] against [w_hi | w_hi | w_lo] (comp == 3), or [x1 | x2] against [w_hi | w_hi] (comp == 2)
+  SSR_CHECK_ARG(comp == 0 || ((comp == 2 || comp == 3) && x2 && C2 == C1), "compensated forward: x2 = residual of x1");
   SSR_CHECK_ARG(x1 && wp && y && B > 0 && D0 > 0 && D1 > 0 && D2 > 0 && Cout > 0, "pointers/shape");
   SSR_CHECK_ARG(C1 > 0 && C1 % 4 == 0 && C2 >= 0 && C2 % 4 == 0 && (C2 == 0 || x2), "channel counts must be multiples of 4");
   SSR_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0, "channel counts must be multiples of 8 (TF32 K-step)");
@@ -2423,6 +2466,7 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
     int ks_total = 0;
     for (int c = 0; c < C1; c += 32) ks_total += ((C1 - c < 32 ? C1 - c : 32) + 7) / 8;
     for (int c = 0; c < C2; c += 32) ks_total += ((C2 - c < 32 ? C2 - c : 32) + 7) / 8;
+    if (comp == 3) ks_total = ks_total / 2 * 3;
     int n1t = (D1 + TM1 - 1) / TM1, n2t = (D2 + TM2 - 1) / TM2;
     // plane-linearised tiling for the small deep levels: windows of 128 rows of the padded plane instead of 16 x 8 tiles
     const int pitch = D2 + 2;
@@ -2464,14 +2508,29 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
   int cols = 2 * G.TZ * G.NT, pc = 32;
   while (pc < cols) pc <<= 1;
   G.tmem_cols = pc;
-  int nch = 0;
-  for (int c = 0; c < C1; c += 32) {
-    SSR_CHECK_ARG(nch < MAX_CHUNKS, "too many input channels");
-    G.chunk_src[nch] = 0; G.chunk_c0[nch] = (short)c; G.chunk_ks[nch] = (unsigned char)(((C1 - c < 32 ? C1 - c : 32) + 7) / 8); ++nch;
-  }
-  for (int c = 0; c < C2; c += 32) {
-    SSR_CHECK_ARG(nch < MAX_CHUNKS, "too many input channels");
-    G.chunk_src[nch] = 1; G.chunk_c0[nch] = (short)c; G.chunk_ks[nch] = (unsigned char)(((C2 - c < 32 ? C2 - c : 32) + 7) / 8); ++nch;
+  int nch = 0, nwch = 0;                       // chunks of K, chunks of the packed weights
+  if (comp) {
+    const int nchc = (C1 + 31) / 32;
+    for (int term = 0; term < comp; ++term)
+      for (int c = 0; c < C1; c += 32) {
+        SSR_CHECK_ARG(nch < MAX_CHUNKS, "too many input channels");
+        G.chunk_src[nch] = (unsigned char)(term == 1); G.chunk_c0[nch] = (short)c;
+        G.chunk_ks[nch] = (unsigned char)(((C1 - c < 32 ? C1 - c : 32) + 7) / 8);
+        G.chunk_w[nch] = (unsigned char)((term == 2 ? nchc : 0) + c / 32); ++nch;
+      }
+    nwch = 2 * nchc;
+  } else {
+    for (int c = 0; c < C1; c += 32) {
+      SSR_CHECK_ARG(nch < MAX_CHUNKS, "too many input channels");
+      G.chunk_src[nch] = 0; G.chunk_c0[nch] = (short)c; G.chunk_ks[nch] = (unsigned char)(((C1 - c < 32 ? C1 - c : 32) + 7) / 8);
+      G.chunk_w[nch] = (unsigned char)nch; ++nch;
+    }
+    for (int c = 0; c < C2; c += 32) {
+      SSR_CHECK_ARG(nch < MAX_CHUNKS, "too many input channels");
+      G.chunk_src[nch] = 1; G.chunk_c0[nch] = (short)c; G.chunk_ks[nch] = (unsigned char)(((C2 - c < 32 ? C2 - c : 32) + 7) / 8);
+      G.chunk_w[nch] = (unsigned char)nch; ++nch;
+    }
+    nwch = nch;
   }
   G.nchunks = nch;
   const bool pl = G.pl_pitch > 0;
@@ -2493,7 +2552,7 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
   int rc = make_map_act(&m1, x1, C1, B, D0, D1, D2, bx1, CU_TENSOR_MAP_SWIZZLE_128B, bx2);
   if (rc) return rc;
   if (C2 > 0) { rc = make_map_act(&m2, x2, C2, B, D0, D1, D2, bx1, CU_TENSOR_MAP_SWIZZLE_128B, bx2); if (rc) return rc; } else m2 = m1;
-  rc = make_map_w(&mw, wp, (long long)nch * 27 * G.Npad, G.NT);
+  rc = make_map_w(&mw, wp, (long long)nwch * 27 * G.Npad, G.NT);
   if (rc) return rc;
 
   static bool attr_set = false;
@@ -2557,6 +2616,22 @@ int ssr_conv3d_dgrad_tc_elu(const float* dy, int C, const float* wp, const float
   return conv3d_fwd_tc_impl(dy, C, nullptr, 0, wp, nullptr, dx, B, D0, D1, D2, Cout, 0, 0, stream, 1, h, dbias, nullptr);
 }
 
+// Compensated forward ("3xTF32", fp32-class accuracy on the TF32 tensor cores): with x = x_hi + x_lo, w = w_hi + w_lo
+// (x_hi = the TF32 value the TMA load produces, x_lo from ssr_tf32_residual; weights from pack mode 5) the convolution is
+//   x * w ~= x_hi * w_hi + x_lo * w_hi + x_hi * w_lo          (level 3; the dropped x_lo * w_lo term is ~2^-22 relative)
+// evaluated as ONE implicit GEMM whose K dimension is the concatenation [x | x_lo | x] against [w_hi | w_hi | w_lo].
+// level 2 keeps only the activation correction ([x | x_lo] against [w_hi | w_hi]).  sums != NULL: BatchNorm sums in the
+// epilogue (as ssr_conv3d_fwd_tc_stats); accumulate: add to the partial result already in y before bias / activation.
+int ssr_conv3d_fwd_tc_comp(const float* x, const float* xlo, int C, const float* wp, const float* bias, float* y,
+                           double* sums, int B, int D0, int D1, int D2, int Cout, int act, int accumulate, int level,
+                           void* stream) {
+  SSR_CHECK_ARG(level == 2 || level == 3, "compensation level must be 2 or 3");
+  SSR_CHECK_ARG(!(sums && accumulate), "BatchNorm sums do not combine with accumulate");
+  if (sums) SSR_CHECK_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)Cout * sizeof(double), (cudaStream_t)stream));
+  return conv3d_fwd_tc_impl(x, C, xlo, C, wp, bias, y, B, D0, D1, D2, Cout, act, accumulate, stream, sums ? 2 : 0, nullptr,
+                            nullptr, sums, level);
+}
+
 // ---- convolution over a 2x nearest-upsampled tensor from its LOW-resolution source (conv3d_tc_up_kernel) ------------
 static int up_tile_shape(int Npad, int B, int D0, int D1, int D2, int ks_total, int kparts, int tile_mult, int* NT, int* TZ) {
   const int n1t = (D1 + TM1 - 1) / TM1, n2t = (D2 + TM2 - 1) / TM2;
@@ -2597,19 +2672,26 @@ static int make_map_view(CUtensorMap* m, const float* ptr, int C, int B, int D0,
 // mode 2: x = full-resolution dy [B,2d0,2d1,2d2,C], y = gradient w.r.t. the low-resolution tensor [B,d0,d1,d2,Cout].
 // wp8: 8 parity classes x standard packed weights (mode 0 / mode 1 packing of the effective kernels).
 static int conv3d_tc_up_impl(int mode, const float* x, int C, const float* wp8, float* y, int B, int D0, int D1, int D2,
-                             int Cout, void* stream) {
+                             int Cout, void* stream, const float* xlo = nullptr, int comp = 0) {
+  // comp (mode 1 only): compensated forward, see ssr_conv3d_fwd_tc_comp; wp8 = 8 parity classes x hi/lo packing (mode 5)
   SSR_CHECK_ARG(x && wp8 && y && B > 0 && D0 > 0 && D1 > 0 && D2 > 0 && Cout > 0, "pointers/shape");
-  SSR_CHECK_ARG(C > 0 && C % 8 == 0 && C <= 32 * UP_MAX_CHUNKS, "channel count must be a multiple of 8 (<= 256)");
-  SSR_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp8 & 127) == 0, "alignment");
+  SSR_CHECK_ARG(comp == 0 || (mode == 1 && xlo && (comp == 2 || comp == 3)), "compensated parity forward args");
+  SSR_CHECK_ARG(C > 0 && C % 8 == 0 && (C + 31) / 32 * (comp ? comp : 1) <= UP_MAX_CHUNKS,
+                "channel count must be a multiple of 8 (<= 768; <= 256 compensated)");
+  SSR_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp8 & 127) == 0 && ((uintptr_t)xlo & 15) == 0, "alignment");
   UpGeom G;
   memset(&G, 0, sizeof(G));
   G.B = B; G.D0 = D0; G.D1 = D1; G.D2 = D2; G.Cout = Cout;
   G.Npad = round_up(Cout, 16);
   int ks_total = 0, nch = 0;
-  for (int c = 0; c < C; c += 32) {
-    G.chunk_c0[nch] = (short)c; G.chunk_ks[nch] = (unsigned char)(((C - c < 32 ? C - c : 32) + 7) / 8);
-    ks_total += G.chunk_ks[nch]; ++nch;
-  }
+  const int nchc = (C + 31) / 32;
+  for (int term = 0; term < (comp ? comp : 1); ++term)
+    for (int c = 0; c < C; c += 32) {
+      G.chunk_c0[nch] = (short)c; G.chunk_ks[nch] = (unsigned char)(((C - c < 32 ? C - c : 32) + 7) / 8);
+      G.chunk_src[nch] = (unsigned char)(term == 1); G.chunk_w[nch] = (unsigned char)((term == 2 ? nchc : 0) + c / 32);
+      ks_total += G.chunk_ks[nch]; ++nch;
+    }
+  const int nwch = comp ? 2 * nchc : nchc;          // chunks of the packed weights per parity class
   G.nchunks = nch;
   int rc = up_tile_shape(G.Npad, B, D0, D1, D2, ks_total, mode == 2 ? 8 : 1, mode == 1 ? 8 : 1, &G.NT, &G.TZ);
   if (rc) { ssr_set_error("no tile shape"); return rc; }
@@ -2618,7 +2700,7 @@ static int conv3d_tc_up_impl(int mode, const float* x, int C, const float* wp8, 
   int cols = 2 * G.TZ * G.NT, pc = 32;
   while (pc < cols) pc <<= 1;
   G.tmem_cols = pc;
-  G.par_rows = nch * 27 * G.Npad;
+  G.par_rows = nwch * 27 * G.Npad;
   G.n2tiles = (D2 + TM2 - 1) / TM2; G.n1tiles = (D1 + TM1 - 1) / TM1; G.n0tiles = (D0 + G.TZ - 1) / G.TZ;
   const int bgroup = G.KG * 3 * G.NT * 128;
   const int budget = 227 * 1024 - 1024 - 2816 - SB * bgroup;
@@ -2632,6 +2714,7 @@ static int conv3d_tc_up_impl(int mode, const float* x, int C, const float* wp8, 
     rc = make_map_act(&maps.x[0], x, C, B, D0, D1, D2);
     if (rc) return rc;
     for (int i = 1; i < 8; ++i) maps.x[i] = maps.x[0];
+    if (comp) { rc = make_map_act(&maps.x[1], xlo, C, B, D0, D1, D2); if (rc) return rc; }
   } else {
     const long long F0 = 2LL * D0, F1 = 2LL * D1, F2 = 2LL * D2;
     for (int par = 0; par < 8; ++par) {
@@ -2669,6 +2752,11 @@ static int conv3d_tc_up_impl(int mode, const float* x, int C, const float* wp8, 
 int ssr_conv3d_fwd_tc_up(const float* low, int Cup, const float* wp8, float* y, int B, int d0, int d1, int d2, int Cout,
                          void* stream) {
   return conv3d_tc_up_impl(1, low, Cup, wp8, y, B, d0, d1, d2, Cout, stream);
+}
+// compensated parity forward (see ssr_conv3d_fwd_tc_comp): lowlo = ssr_tf32_residual(low), wp8c = 8 x pack mode 5
+int ssr_conv3d_fwd_tc_up_comp(const float* low, const float* lowlo, int Cup, const float* wp8c, float* y, int B, int d0,
+                              int d1, int d2, int Cout, int level, void* stream) {
+  return conv3d_tc_up_impl(1, low, Cup, wp8c, y, B, d0, d1, d2, Cout, stream, lowlo, level);
 }
 int ssr_conv3d_dgrad_tc_up(const float* dy, int Cout_layer, const float* wp8, float* dlow, int B, int d0, int d1, int d2,
                            int Cup, void* stream) {
@@ -2832,6 +2920,30 @@ int ssr_conv3d_fwd_tc_k2n_stats(const float* x, int C, const float* wp, const fl
   SSR_CHECK_ARG(sums, "sums");
   SSR_CHECK_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)Cout * sizeof(double), (cudaStream_t)stream));
   return conv3d_fwd_tc_k2n_impl(x, C, 0, C, wp, bias, y, B, D0, D1, D2, Cout, act, 0, 1, stream, 2, nullptr, nullptr, sums);
+}
+
+// final channel part of a k2n convolution that also accumulates the BatchNorm sums of the finished output (the last
+// term of a compensated convolution: x * w_hi and x_lo * w_hi are already in y)
+int ssr_conv3d_fwd_tc_k2n_part_stats(const float* x, int Ctot, int c0, int C, const float* wp, const float* bias, float* y,
+                                     double* sums, int B, int D0, int D1, int D2, int Cout, int act, int accumulate,
+                                     void* stream) {
+  SSR_CHECK_ARG(sums, "sums");
+  SSR_CHECK_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)Cout * sizeof(double), (cudaStream_t)stream));
+  return conv3d_fwd_tc_k2n_impl(x, Ctot, c0, C, wp, bias, y, B, D0, D1, D2, Cout, act, accumulate, 1, stream, 2, nullptr,
+                                nullptr, sums);
+}
+
+// lo[i] = x[i] - rne_tf32(x[i]): the part of an fp32 activation the TMA's TFLOAT32 load rounds away (round to nearest
+// even on the 13 dropped mantissa bits, profiles/r01_tma_tfloat32_rounding.txt); exact in fp32
+int ssr_tf32_residual(const float* x, float* lo, long long n, void* stream) {
+  SSR_CHECK_ARG(x && lo && n > 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)lo & 15) == 0, "tf32_residual args");
+  long long g = (n / 4 + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  tf32_residual_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(x, lo, n);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
 }
 
 long long ssr_conv3d_wgrad_scratch_bytes(int, int, int, int, int, int, int) { return 0; }

@@ -132,7 +132,7 @@ def class_tables(generation_labels, segmentation_label_equivalency):
 class SegRegulariser:
     def __init__(self, dims, batchsize, seg_state_dict, n_seg_labels, generation_labels, segmentation_label_equivalency,
                  rel_weight, loss_cropping=None, m=None, M=None, fs_header=False, nb_features=24, nb_levels=5, conv_size=3,
-                 feat_mult=2, nb_conv_per_level=2, conv_impl='tc', device='cuda'):
+                 feat_mult=2, nb_conv_per_level=2, conv_impl='tc3', device='cuda'):
         if fs_header:
             raise NotImplementedError('fs_header_segnet=True (axis swap + flip around the segmentation network, '
                                       'metrics_model.py:157-162) is not implemented')

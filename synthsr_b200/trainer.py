@@ -17,7 +17,7 @@ from .unet import UNet3D
 class TrainingEngine:
     def __init__(self, plan, batchsize=1, nb_features=24, nb_levels=5, conv_size=3, feat_mult=2, nb_conv_per_level=2,
                  nb_labels=None, lr=1e-4, lr_decay=0., metric='l1', work_with_residual_channel=None,
-                 loss_cropping=None, conv_impl='tc', seed=0, device='cuda', rank=0, world_size=1, seg=None):
+                 loss_cropping=None, conv_impl='tc3', seed=0, device='cuda', rank=0, world_size=1, seg=None):
         """seg: optional synthsr_b200.seg_loss.SegRegulariser (segmentation-regularised loss, metrics_model.py:136-215)."""
         self.plan, self.B = plan, int(batchsize)
         self.device = torch.device(device)

@@ -5,12 +5,18 @@ Parameters live in ONE flat float32 buffer (so the data-parallel step is a singl
 buffer and a single fused Adam launch); views into it carry the Keras layer names and Keras layouts
 (kernels (k,k,k,Cin,Cout)), which is what checkpoints store.
 
-conv_impl = 'tc'  : tcgen05 TF32 implicit-GEMM convolutions (conv_tc.cu)            -- throughput mode
-conv_impl = 'ref' : exact fp32 CUDA-core convolutions (unet_kernels.cu)             -- parity mode / cross-check
+conv_impl = 'tc3' : tcgen05 convolutions, forward COMPENSATED to fp32-class accuracy ("3xTF32": x = x_hi + x_lo,
+                    w = w_hi + w_lo, K = [x | x_lo | x] against [w_hi | w_hi | w_lo] in one implicit GEMM) on every layer
+                    but the last decoder level; backward in plain TF32.  The mode that meets the 1e-3 parity bar on the
+                    prediction / loss and 1e-2 on the gradients (tests/test_unet_parity_gpu.py) -- the default.
+conv_impl = 'tc'  : plain TF32 everywhere (conv_tc.cu): ~2.9e-4 per convolution, 2-3e-3 on the prediction of a randomly
+                    initialised net (scripts/tf32_error_emulation.py) -- throughput mode, outside the parity bar
+conv_impl = 'ref' : exact fp32 CUDA-core convolutions (unet_kernels.cu)             -- cross-check
 """
 import contextlib
 import math
 import os
+import re
 from collections import OrderedDict
 
 import numpy as np
@@ -61,7 +67,7 @@ def keras_layer_order(nb_levels=5, nb_conv_per_level=2, prefix='unet'):
 
 class UNet3D:
     def __init__(self, input_shape, nb_features=24, nb_levels=5, conv_size=3, nb_labels=1, feat_mult=2,
-                 nb_conv_per_level=2, batchsize=1, device='cuda', conv_impl='tc', seed=None):
+                 nb_conv_per_level=2, batchsize=1, device='cuda', conv_impl='tc3', seed=None):
         assert nb_conv_per_level == 2, 'the reference training path uses nb_conv_per_level=2 (SynthSR/training.py:75)'
         assert conv_size == 3 or conv_impl == 'ref'
         self.B = int(batchsize)
@@ -70,6 +76,17 @@ class UNet3D:
         self.L = int(nb_levels)
         self.k = int(conv_size)
         self.nb_labels = int(nb_labels)
+        assert conv_impl in ('tc', 'tc3', 'ref'), conv_impl
+        # compensated forward: {regex over layer names: level}; level 3 = full hi/lo split of activations and weights,
+        # level 2 = activations only.  SSR_COMP='regex:level[,regex:level...]' overrides (experiments).
+        self.comp = []
+        if conv_impl == 'tc3':
+            last = 'uparm_%d_' % (2 * int(nb_levels) - 2)
+            self.comp = [(re.compile(r'^(?!.*%s).*_conv_' % last), 3)]
+            conv_impl = 'tc'
+        if os.environ.get('SSR_COMP') and conv_impl == 'tc':
+            self.comp = [(re.compile(r.rsplit(':', 1)[0]), int(r.rsplit(':', 1)[1])) for r in os.environ['SSR_COMP'].split(',')]
+        self._lo = None                 # scratch for the TF32 residual x_lo of the convolution being run (stream ordered)
         self.conv_impl = conv_impl
         self.wgrad_tc = conv_impl == 'tc'
         self.prof = None          # list of (kind, flops, start_event, end_event) when profiling is enabled
@@ -252,9 +269,60 @@ class UNet3D:
         self._timed('fwd_tc' if tc else 'fwd_ref', l, c1 + c2, cout,
                     lambda: self._conv_fwd_impl(tc, name, x1, c1, x2, c2, y, l, cout, act, stats_sums))
 
+    def _comp_level(self, name):
+        for rx, level in self.comp:
+            if rx.search(name):
+                return level
+        return 0
+
+    def _residual(self, x, n):
+        """x_lo = x - rne_tf32(x) of the first n floats of x, in the shared scratch (consumed by the next launch on this
+        stream, so one buffer serves every layer)."""
+        if self._lo is None or self._lo.numel() < n:
+            self._lo = torch.empty(max(n, self.nvox[0] * self.feats[0]), dtype=torch.float32, device=self.device)
+        lib.ssr_tf32_residual(x, self._lo, n, stream_ptr())
+        return self._lo
+
+    def _conv_fwd_comp(self, level, name, x1, c1, x2, c2, y, l, cout, act, stats_sums):
+        """compensated forward of one layer (see the module docstring); the concatenated input of a decoder level that
+        does not take the parity path is the sum of its two parts."""
+        st, B, d = stream_ptr(), self.B, self.ldims[l]
+        nv = self.nvox[l]
+        bias = self.p[name + '/bias']
+        if c2 == 0 and self._k2n_ok(c1, cout):
+            # full-resolution 24-channel layers: three passes of the k2n kernel (its 27 taps stay resident per pass)
+            whi = self._packed_w(name, 2, c1, 0, cout)
+            lo = self._residual(x1, nv * c1)
+            lib.ssr_conv3d_fwd_tc_k2n_part(x1, c1, 0, c1, whi, bias, y, B, *d, cout, act, 0, 0, st)
+            last_hi = level == 2
+            if last_hi and stats_sums is not None:
+                lib.ssr_conv3d_fwd_tc_k2n_part_stats(lo, c1, 0, c1, whi, bias, y, stats_sums, B, *d, cout, act, 1, st)
+            else:
+                lib.ssr_conv3d_fwd_tc_k2n_part(lo, c1, 0, c1, whi, bias, y, B, *d, cout, act, 1, 1 if last_hi else 0, st)
+            if level == 3:
+                wlo = self._packed_w(name, 6, c1, 0, cout)
+                if stats_sums is not None:
+                    lib.ssr_conv3d_fwd_tc_k2n_part_stats(x1, c1, 0, c1, wlo, bias, y, stats_sums, B, *d, cout, act, 1, st)
+                else:
+                    lib.ssr_conv3d_fwd_tc_k2n_part(x1, c1, 0, c1, wlo, bias, y, B, *d, cout, act, 1, 1, st)
+            return
+        if c2 == 0:
+            wp = self._packed_w(name, 5, c1, c1, cout)
+            lib.ssr_conv3d_fwd_tc_comp(x1, self._residual(x1, nv * c1), c1, wp, bias, y, stats_sums, B, *d, cout, act, 0,
+                                       level, st)
+            return
+        assert stats_sums is None
+        wp1 = self._packed_w(name, 5, c1 + c2, c1, cout, tag='c0')
+        lib.ssr_conv3d_fwd_tc_comp(x1, self._residual(x1, nv * c1), c1, wp1, None, y, None, B, *d, cout, 0, 0, level, st)
+        wp2 = self._packed_w(name, 5, c1 + c2, (c1 << 12) | c2, cout, tag='c1')
+        lib.ssr_conv3d_fwd_tc_comp(x2, self._residual(x2, nv * c2), c2, wp2, bias, y, None, B, *d, cout, act, 1, level, st)
+
     def _conv_fwd_impl(self, tc, name, x1, c1, x2, c2, y, l, cout, act, stats_sums=None):
         st = stream_ptr()
         d = self.ldims[l]
+        level = self._comp_level(name) if tc else 0
+        if level:
+            return self._conv_fwd_comp(level, name, x1, c1, x2, c2, y, l, cout, act, stats_sums)
         if stats_sums is not None and self._k2n_ok(c1, cout):
             assert tc and c2 == 0
             lib.ssr_conv3d_fwd_tc_k2n_stats(x1, c1, self._packed_w(name, 2, c1, 0, cout), self.p[name + '/bias'], y,
@@ -290,6 +358,16 @@ class UNet3D:
     def _conv_fwd_up_impl(self, name, l, act):
         st, F, B = stream_ptr(), self.feats, self.B
         u = self._up_state(l)
+        level = self._comp_level(name)
+        if level:
+            # compensated: parity kernel on [vlow | vlow_lo | vlow], then the skip part accumulates (+ bias + ELU)
+            nlow, nsk = self.nvox[l + 1] * F[l + 1], self.nvox[l] * F[l]
+            lib.ssr_conv3d_fwd_tc_up_comp(self.vlow[l], self._residual(self.vlow[l], nlow), F[l + 1],
+                                          self._up_packs(l, 'fwd8c'), self.g0[l], B, *self.ldims[l + 1], F[l], level, st)
+            wp = self._packed_w(name, 5, F[l], F[l], F[l], tag='skipc', src=u['wskip'])
+            lib.ssr_conv3d_fwd_tc_comp(self.h1[l], self._residual(self.h1[l], nsk), F[l], wp, self.p[name + '/bias'],
+                                       self.g0[l], None, B, *self.ldims[l], F[l], act, 1, level, st)
+            return
         if self._up_k2n_ok(l):
             if not self._up_valid:
                 self._up_weights_all(st)
@@ -473,9 +551,12 @@ class UNet3D:
         u = self._up_state(l)
         name = 'unet_conv_uparm_%d_0' % (L + (L - 2 - l))
         cu, co = F[l + 1], F[l]
-        n, mode = (u['nf'], 0) if which == 'fwd8' else (u['nd'], 1)
+        if which == 'fwd8c' and which not in u:      # hi / lo packing of the 8 effective kernels (compensated forward)
+            u['nfc'] = lib.ssr_conv3d_packed_size(cu, cu, co, 5)
+            u[which] = torch.empty(8 * u['nfc'], dtype=torch.float32, device=self.device)
+        n, mode, c2 = {'fwd8': (u['nf'], 0, 0), 'dgr8': (u['nd'], 1, 0), 'fwd8c': (u.get('nfc'), 5, cu)}[which]
         for par in range(8):
-            self._packed_w(name, mode, cu, 0, co, tag=('up', par), src=u['weff'][par * 27 * cu * co:(par + 1) * 27 * cu * co],
+            self._packed_w(name, mode, cu, c2, co, tag=('up', par), src=u['weff'][par * 27 * cu * co:(par + 1) * 27 * cu * co],
                            buf=u[which][par * n:(par + 1) * n])
         return u[which]
 

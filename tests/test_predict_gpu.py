@@ -32,7 +32,7 @@ def test_dynamic_model_predict_matches_oracle_random_weights():
     from ext.neuron import models as nrn_models
     from synthsr_b200.unet import UNet3D
     rng = np.random.default_rng(5)
-    for impl, tol in (('ref', 2e-5), ('tc', 4e-3)):
+    for impl, tol in (('ref', 2e-5), ('tc3', 1e-3), ('tc', 4e-3)):     # 'tc' = plain-TF32 fast mode (not the default)
         m = nrn_models.unet(nb_features=8, input_shape=[None, None, None, 2], nb_levels=3, conv_size=3, nb_labels=1, feat_mult=2,
                             nb_conv_per_level=2, final_pred_activation='linear', batch_norm=-1, activation='elu',
                             conv_impl=impl)
@@ -73,9 +73,9 @@ def test_real_weights_inference_on_a_real_scan_matches_oracle():
     emax = np.abs(pred - ref).max() / np.abs(ref).max()
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     with open(os.path.join(ROOT, 'gpurun_out', 'real_weights_inference.txt'), 'a') as f:
-        f.write('real weights, 64^3 crop of brain1: tc vs float64 oracle rel L2 %.3e, max/max %.3e; pred range [%.3f, %.3f]\n'
+        f.write('real weights, 64^3 crop of brain1: tc3 (default mode) vs float64 oracle rel L2 %.3e, max/max %.3e; pred range [%.3f, %.3f]\n'
                 % (err, emax, pred.min(), pred.max()))
-    assert err < 5e-3, err
+    assert err < 1e-3 and emax < 1e-3, (err, emax)      # default mode ('tc3'), north_star bar
     out, aff_out = P.predict_volume(model, im, aff)
     assert out.shape == im.shape and np.isfinite(out).all() and out.min() >= 0 and out.max() <= 128
     assert np.allclose(aff_out, aff)

@@ -217,16 +217,21 @@ def test_tc_matches_ref_kernels():
         assert err < 2e-3, ('dgrad', d, c1, c2, co, err)
 
 
-def test_tc_training_step_32cube():
-    """full step with tcgen05 TF32 convolutions at the reference topology, against the exact float64 oracle.
+def test_tc3_training_step_32cube():
+    """full step in the BENCHMARKED mode (conv_impl='tc3': compensated forward, TF32 backward) at the reference topology
+    against the exact float64 oracle, north_star bars: prediction / loss 1e-3, gradients 1e-2 of max(|tensor|, 1e-2 |full
+    gradient|).  (tests/test_unet_parity_gpu.py repeats this at 64^3, 96^3, 160^3 and with the trained weights.)"""
+    _one_step([32, 32, 32], 1, 24, 5, 1, 'tc3', 1e-3, 1e-2, metric='l2')
+    _one_step([32, 32, 32], 1, 24, 5, 1, 'tc3', 1e-3, 1e-2)
 
-    Kernel correctness is established per layer (test_tc_matches_ref: 2e-5 against a float64 convolution of the
-    identically rounded operands).  End to end the TF32 operand rounding (2.9e-4 rel. L2 per convolution) accumulates to
-    ~2e-3 on the prediction and ~1e-4 on the loss at random init; a CPU emulation of the rounding gives the same
-    numbers.  A TF32-rounded network is discontinuous in its inputs (merely switching ties-to-even -> ties-away, or
-    fp32 -> fp64 accumulation of identical operands, moves the prediction by 1.4e-3 on the CPU), so no two non-bit-
-    identical TF32 implementations agree more tightly than this noise level.  Bars: prediction 5e-3, loss 1e-3;
-    gradients (smooth l2 loss) 0.25 of max(|tensor|, 1e-2 |full gradient|); with l1 the sign() flips add to that."""
+
+def test_tc_fast_mode_error_class_32cube():
+    """the plain-TF32 FAST mode (conv_impl='tc'), which is NOT the benchmarked / parity-gated mode: kernel correctness is
+    established per layer (test_tc_matches_ref_kernels: 2e-5 against a float64 convolution of the identically rounded
+    operands); end to end the TF32 operand rounding (2.9e-4 rel. L2 per convolution) is amplified to 2-3e-3 on the
+    prediction of a randomly initialised net and ~1e-1 on its gradients at any size (scripts/tf32_error_emulation.py
+    reproduces these numbers on the CPU; almost all of it is the FORWARD rounding, which is why 'tc3' compensates the
+    forward only).  This test only pins that error class so a kernel regression in the fast path is caught."""
     _one_step([32, 32, 32], 1, 24, 5, 1, 'tc', 5e-3, 0.25, metric='l2')
     _one_step([32, 32, 32], 1, 24, 5, 1, 'tc', 5e-3, 0.5)
 

@@ -1,0 +1,291 @@
+"""Parity of the BENCHMARKED convolution mode (conv_impl='tc3': tcgen05, forward compensated to fp32-class accuracy,
+backward plain TF32) against the float64 oracle at north_star's bars, un-widened:
+
+    prediction: relative L2 <= 1e-3 AND max|err| / max|pred| <= 1e-3;  loss <= 1e-3;  every gradient tensor <= 1e-2
+
+* kernel level: every compensated entry point against a float64 convolution of the UNROUNDED operands (what KL.Conv3D
+  computes in fp32, ext/neuron/models.py:316,444,481);
+* full training step, reference topology (24 features, 5 levels), random init: 32^3, 64^3, 96^3 against oracle/unet.py in
+  float64 on the CPU; with the reference's trained weights on a crop of the reference's scan (when the files travel);
+* 160^3 (BASELINE configs[1], the benchmark size): against the exact-fp32 CUDA-core mode (conv_impl='ref', itself within
+  2e-5 of the float64 oracle, tests/test_unet_gpu.py::test_ref_*), because a float64 CPU step at 160^3 needs ~30 GB.
+
+Every measured number is appended to gpurun_out/unet_parity.txt.  scripts/tf32_error_emulation.py reproduces the error
+levels on the CPU and is how the set of compensated layers was chosen."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PRED_TOL, LOSS_TOL, GRAD_TOL = 1e-3, 1e-3, 1e-2          # north_star
+
+
+def _log(line):
+    try:
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        with open(os.path.join(ROOT, 'gpurun_out', 'unet_parity.txt'), 'a') as f:
+            f.write(line + '\n')
+    except OSError:
+        pass
+
+
+def _find(rel):
+    for base in (os.path.join(ROOT, 'baseline', '_ref'), '/root/reference', '/root/reference/data'):
+        p = os.path.join(base, rel)
+        if os.path.isfile(p):
+            return p
+    return None
+
+
+def _conv64(x, w, b, d, elu=True):
+    """float64 3x3x3 'same' convolution of [nv, C] activations on grid d with a (3,3,3,Cin,Cout) kernel."""
+    xr = x.double().cpu().view(1, *d, -1).permute(0, 4, 1, 2, 3)
+    wr = w.double().cpu().permute(4, 3, 0, 1, 2)
+    y = torch.nn.functional.conv3d(xr, wr, None if b is None else b.double().cpu(), padding=1)
+    if elu:
+        y = torch.nn.functional.elu(y)
+    return y.permute(0, 2, 3, 4, 1).reshape(-1, w.shape[-1])
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def test_tf32_residual_is_the_part_the_tma_rounds_away():
+    from synthsr_b200._lib import lib, stream_ptr
+    rng = np.random.default_rng(0)
+    x = _t(rng.normal(size=100003) * np.exp(rng.normal(size=100003) * 3))
+    lo = torch.full_like(x, float('nan'))
+    lib.ssr_tf32_residual(x, lo, x.numel(), stream_ptr())
+    torch.cuda.synchronize()
+    u = x.view(torch.int32)
+    hi = ((u + 0xFFF + ((u >> 13) & 1)) & ~0x1FFF).view(torch.float32)      # round to nearest even TF32
+    assert torch.equal(lo, x - hi)
+    assert torch.equal(hi + lo, x)                                            # the split is exact
+    assert (lo.abs() <= x.abs() * 2.0 ** -11).all()
+
+
+@pytest.mark.parametrize('d,c,co,level', [([8, 16, 24], 48, 96, 3), ([10, 10, 10], 192, 384, 3), ([16, 16, 16], 24, 48, 3),
+                                          ([20, 20, 20], 96, 192, 3), ([8, 16, 24], 48, 96, 2), ([12, 20, 8], 384, 384, 3)])
+def test_compensated_generic_forward_matches_float64(d, c, co, level):
+    """ssr_conv3d_fwd_tc_comp (with and without the BatchNorm sums): level 3 reaches fp32 accuracy; level 2 leaves the
+    weight rounding (compared with a float64 convolution of the rna-rounded weights)."""
+    from synthsr_b200._lib import lib, stream_ptr
+    rng = np.random.default_rng(1)
+    nv = int(np.prod(d))
+    x = _t(rng.normal(size=(nv, c)))
+    w = _t(rng.normal(size=(3, 3, 3, c, co)) / np.sqrt(27 * c))
+    b = _t(rng.normal(size=co))
+    st = stream_ptr()
+    lo = torch.empty_like(x)
+    lib.ssr_tf32_residual(x, lo, x.numel(), st)
+    wp = torch.empty(lib.ssr_conv3d_packed_size(c, c, co, 5), dtype=torch.float32, device='cuda')
+    lib.ssr_conv3d_pack_weights(w, wp, c, c, co, 5, st)
+    wref = w
+    if level == 2:
+        uw = w.view(torch.int32)
+        wref = ((uw + 0x1000) & ~0x1FFF).view(torch.float32)
+    y64 = _conv64(x, wref, b, d)
+    for with_sums in (False, True):
+        y = torch.full((nv, co), float('nan'), dtype=torch.float32, device='cuda')
+        sums = torch.full((2 * co,), float('nan'), dtype=torch.float64, device='cuda') if with_sums else None
+        lib.ssr_conv3d_fwd_tc_comp(x, lo, c, wp, b, y, sums, 1, *d, co, 1, 0, level, st)
+        torch.cuda.synchronize()
+        err = (y.double().cpu() - y64).abs().max().item() / y64.abs().max().item()
+        _log('comp generic level %d %s %d->%d sums=%d: max/max %.2e' % (level, d, c, co, with_sums, err))
+        assert err < 2e-5, (d, c, co, level, err)
+        if with_sums:
+            s = sums.cpu().numpy()
+            assert np.allclose(s[:co], y.double().sum(0).cpu().numpy(), rtol=1e-6, atol=1e-6 * nv)
+            assert np.allclose(s[co:], (y.double() ** 2).sum(0).cpu().numpy(), rtol=1e-6, atol=1e-6 * nv)
+
+
+def test_compensated_generic_forward_accumulates_channel_parts():
+    """a concatenated input [x1, x2] as two compensated launches (second one accumulates, + bias + ELU)."""
+    from synthsr_b200._lib import lib, stream_ptr
+    rng = np.random.default_rng(2)
+    d, c1, c2, co = [8, 16, 16], 48, 96, 48
+    nv = int(np.prod(d))
+    x1, x2 = _t(rng.normal(size=(nv, c1))), _t(rng.normal(size=(nv, c2)))
+    w = _t(rng.normal(size=(3, 3, 3, c1 + c2, co)) / np.sqrt(27 * (c1 + c2)))
+    b = _t(rng.normal(size=co))
+    st = stream_ptr()
+    y = torch.full((nv, co), float('nan'), dtype=torch.float32, device='cuda')
+    lo = torch.empty(nv * max(c1, c2), dtype=torch.float32, device='cuda')
+    for i, (x, c, enc) in enumerate(((x1, c1, c1), (x2, c2, (c1 << 12) | c2))):
+        wp = torch.empty(lib.ssr_conv3d_packed_size(c1 + c2, enc, co, 5), dtype=torch.float32, device='cuda')
+        lib.ssr_conv3d_pack_weights(w, wp, c1 + c2, enc, co, 5, st)
+        lib.ssr_tf32_residual(x, lo, x.numel(), st)
+        lib.ssr_conv3d_fwd_tc_comp(x, lo, c, wp, b if i else None, y, None, 1, *d, co, i, i, 3, st)
+    torch.cuda.synchronize()
+    y64 = _conv64(torch.cat([x1, x2], 1), w, b, d)
+    err = (y.double().cpu() - y64).abs().max().item() / y64.abs().max().item()
+    assert err < 2e-5, err
+
+
+@pytest.mark.parametrize('d', [[16, 16, 32], [12, 20, 18]])
+def test_compensated_k2n_forward_matches_float64(d):
+    """the three k2n passes of a 24 -> 24 full-resolution layer (hi.hi, lo.hi, hi.lo; the last one with the BatchNorm sums)."""
+    from synthsr_b200._lib import lib, stream_ptr
+    rng = np.random.default_rng(3)
+    c = co = 24
+    nv = int(np.prod(d))
+    x = _t(rng.normal(size=(nv, c)))
+    w = _t(rng.normal(size=(3, 3, 3, c, co)) / np.sqrt(27 * c))
+    b = _t(rng.normal(size=co))
+    st = stream_ptr()
+    lo = torch.empty_like(x)
+    lib.ssr_tf32_residual(x, lo, x.numel(), st)
+    whi = torch.empty(lib.ssr_conv3d_packed_size(c, 0, co, 2), dtype=torch.float32, device='cuda')
+    wlo = torch.empty(lib.ssr_conv3d_packed_size(c, 0, co, 6), dtype=torch.float32, device='cuda')
+    lib.ssr_conv3d_pack_weights(w, whi, c, 0, co, 2, st)
+    lib.ssr_conv3d_pack_weights(w, wlo, c, 0, co, 6, st)
+    y = torch.full((nv, co), float('nan'), dtype=torch.float32, device='cuda')
+    sums = torch.full((2 * co,), float('nan'), dtype=torch.float64, device='cuda')
+    lib.ssr_conv3d_fwd_tc_k2n_part(x, c, 0, c, whi, b, y, 1, *d, co, 1, 0, 0, st)
+    lib.ssr_conv3d_fwd_tc_k2n_part(lo, c, 0, c, whi, b, y, 1, *d, co, 1, 1, 0, st)
+    lib.ssr_conv3d_fwd_tc_k2n_part_stats(x, c, 0, c, wlo, b, y, sums, 1, *d, co, 1, 1, st)
+    torch.cuda.synchronize()
+    y64 = _conv64(x, w, b, d)
+    err = (y.double().cpu() - y64).abs().max().item() / y64.abs().max().item()
+    _log('comp k2n %s: max/max %.2e' % (d, err))
+    assert err < 2e-5, err
+    s = sums.cpu().numpy()
+    assert np.allclose(s[:co], y.double().sum(0).cpu().numpy(), rtol=1e-6, atol=1e-6 * nv)
+    assert np.allclose(s[co:], (y.double() ** 2).sum(0).cpu().numpy(), rtol=1e-6, atol=1e-6 * nv)
+
+
+@pytest.mark.parametrize('dl,cu,co', [([8, 8, 16], 96, 48), ([10, 12, 8], 192, 96)])
+def test_compensated_parity_forward_matches_float64(dl, cu, co):
+    """ssr_conv3d_fwd_tc_up_comp: convolution over the 2x nearest-upsampled tensor from the low-resolution tensor."""
+    from synthsr_b200._lib import lib, stream_ptr
+    rng = np.random.default_rng(4)
+    cs = co
+    nl = int(np.prod(dl))
+    df = [2 * v for v in dl]
+    low = _t(rng.normal(size=(nl, cu)))
+    w = _t(rng.normal(size=(3, 3, 3, cs + cu, co)) / np.sqrt(27 * (cs + cu)))
+    st = stream_ptr()
+    wskip = torch.empty(27 * cs * co, dtype=torch.float32, device='cuda')
+    weff = torch.empty(8 * 27 * cu * co, dtype=torch.float32, device='cuda')
+    lib.ssr_conv3d_up_weights(w, cs, cu, co, wskip, weff, st)
+    n5 = lib.ssr_conv3d_packed_size(cu, cu, co, 5)
+    wp8 = torch.empty(8 * n5, dtype=torch.float32, device='cuda')
+    for par in range(8):
+        lib.ssr_conv3d_pack_weights(weff[par * 27 * cu * co:], wp8[par * n5:], cu, cu, co, 5, st)
+    lo = torch.empty_like(low)
+    lib.ssr_tf32_residual(low, lo, low.numel(), st)
+    y = torch.full((8 * nl, co), float('nan'), dtype=torch.float32, device='cuda')
+    lib.ssr_conv3d_fwd_tc_up_comp(low, lo, cu, wp8, y, 1, *dl, co, 3, st)
+    torch.cuda.synchronize()
+    up = low.view(*dl, cu).repeat_interleave(2, 0).repeat_interleave(2, 1).repeat_interleave(2, 2).reshape(-1, cu)
+    y64 = _conv64(up, w[:, :, :, cs:, :], None, df, elu=False)
+    err = (y.double().cpu() - y64).abs().max().item() / y64.abs().max().item()
+    _log('comp parity %s %d->%d: max/max %.2e' % (dl, cu, co, err))
+    assert err < 2e-5, err
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def _step_errors(net, image, target, pred_ref, loss_ref, grads_ref, tag, **loss_kw):
+    loss = net.loss_and_grad(torch.from_numpy(image).cuda(), torch.from_numpy(target).cuda(), **loss_kw)
+    torch.cuda.synchronize()
+    pred = net.pred.view(pred_ref.shape).cpu().numpy().astype(np.float64)
+    e_l2 = np.linalg.norm(pred - pred_ref) / np.linalg.norm(pred_ref)
+    e_max = np.abs(pred - pred_ref).max() / np.abs(pred_ref).max()
+    e_loss = abs(loss.item() - loss_ref) / abs(loss_ref)
+    # per tensor, relative to max(|tensor|, 1e-2 |whole gradient|) (tensors that are analytically ~0 are rounding noise)
+    gtot = np.sqrt(sum(float((np.asarray(g, np.float64) ** 2).sum()) for g in grads_ref.values()))
+    gerr = {k: np.linalg.norm(net.g[k].cpu().numpy().astype(np.float64) - np.asarray(g, np.float64)) /
+            max(np.linalg.norm(np.asarray(g, np.float64)), 1e-2 * gtot) for k, g in grads_ref.items()}
+    worst = max(gerr, key=gerr.get)
+    _log('%s: pred relL2 %.3e max/max %.3e loss rel %.3e worst grad relL2 %.3e (%s)' % (tag, e_l2, e_max, e_loss,
+                                                                                       gerr[worst], worst))
+    return e_l2, e_max, e_loss, gerr
+
+
+def _assert_north_star(e_l2, e_max, e_loss, gerr):
+    assert e_l2 <= PRED_TOL, ('prediction relative L2', e_l2)
+    assert e_max <= PRED_TOL, ('prediction max/max', e_max)
+    assert e_loss <= LOSS_TOL, ('loss', e_loss)
+    for k, e in gerr.items():
+        assert e <= GRAD_TOL, ('gradient', k, e)
+
+
+def _oracle64(sd, image, target, nb_levels, **loss_kw):
+    from oracle import unet as OU
+    params = {k: torch.tensor(np.asarray(v), dtype=torch.float64) for k, v in sd.items()}
+    names = OU.trainable_names(params)
+    leaves = {k: params[k].clone().requires_grad_(True) for k in names}
+    p = {k: leaves.get(k, params[k]) for k in params}
+    img, tgt = torch.tensor(image, dtype=torch.float64), torch.tensor(target, dtype=torch.float64)
+    pred = OU.forward(p, img, training=True, nb_levels=nb_levels)
+    loss = OU.loss_fn(pred, img, tgt, **loss_kw)
+    grads = dict(zip(names, torch.autograd.grad(loss, [leaves[k] for k in names])))
+    return pred.detach().numpy(), float(loss.detach()), {k: v.numpy() for k, v in grads.items()}
+
+
+@pytest.mark.parametrize('size,metric', [(32, 'l1'), (32, 'l2'), (64, 'l1'), (96, 'l1')])
+def test_tc3_training_step_meets_north_star_vs_float64_oracle(size, metric):
+    """random init (glorot, seed 0), uniform-noise image and target -- the hardest input for error amplification."""
+    from synthsr_b200.unet import UNet3D
+    dims = [size] * 3
+    net = UNet3D(dims + [1], batchsize=1, conv_impl='tc3', seed=0)
+    rng = np.random.default_rng(1)
+    image = rng.uniform(0, 1, size=(1, *dims, 1)).astype(np.float32)
+    target = rng.uniform(0, 1, size=(1, *dims, 1)).astype(np.float32)
+    pred_o, loss_o, grads_o = _oracle64(net.state_dict(), image, target, 5, metric=metric)
+    errs = _step_errors(net, image, target, pred_o, loss_o, grads_o, 'tc3 %d^3 %s random init vs float64 oracle' % (size, metric),
+                        metric=metric)
+    _assert_north_star(*errs)
+
+
+def test_tc3_training_step_trained_reference_weights_real_scan():
+    """the reference's trained weights (models/SynthSR_v10_210712.h5) on a 96^3 crop of data/images/brain1.nii.gz."""
+    wfile, image = _find('models/SynthSR_v10_210712.h5'), _find('images/brain1.nii.gz')
+    if wfile is None or image is None:
+        pytest.skip('reference weights / scan not available on this machine')
+    from SynthSR import predict as P
+    from ext.lab2im import utils
+    from synthsr_b200 import h5lite
+    from synthsr_b200.unet import UNet3D
+    im, aff, _ = utils.load_volume(image, im_only=False, dtype='float')
+    S = P.preprocess(im, aff)[0]
+    c = [s // 2 - 48 for s in S.shape[1:4]]
+    crop = np.ascontiguousarray(S[:, c[0]:c[0] + 96, c[1]:c[1] + 96, c[2]:c[2] + 96, :], dtype=np.float32)
+    target = np.ascontiguousarray(np.roll(crop, 1, axis=1) * .5 + crop * .5)       # a smooth, image-like target
+    sd, _ = h5lite.load_keras_weights(wfile)
+    net = UNet3D([96, 96, 96, 1], batchsize=1, conv_impl='tc3', seed=0)
+    net.load_state_dict(sd)
+    pred_o, loss_o, grads_o = _oracle64(net.state_dict(), crop, target, 5)
+    errs = _step_errors(net, crop, target, pred_o, loss_o, grads_o, 'tc3 96^3 trained reference weights, brain1 crop')
+    _assert_north_star(*errs)
+
+
+def test_tc3_training_step_at_benchmark_size_160():
+    """BASELINE configs[1]: 160^3, batch 1, reference topology.  Reference = the exact-fp32 CUDA-core mode on the same
+    device (validated against the float64 oracle to 2e-5 / 5e-4 at the sizes the CPU oracle reaches)."""
+    from synthsr_b200.unet import UNet3D
+    dims = [160] * 3
+    rng = np.random.default_rng(1)
+    image = rng.uniform(0, 1, size=(1, *dims, 1)).astype(np.float32)
+    target = rng.uniform(0, 1, size=(1, *dims, 1)).astype(np.float32)
+    ref = UNet3D(dims + [1], batchsize=1, conv_impl='ref', seed=0)
+    loss_r = ref.loss_and_grad(torch.from_numpy(image).cuda(), torch.from_numpy(target).cuda())
+    torch.cuda.synchronize()
+    pred_r = ref.pred.view(1, *dims, 1).cpu().numpy().astype(np.float64)
+    grads_r = {k: ref.g[k].cpu().numpy().astype(np.float64) for k in ref.layout}
+    loss_r = loss_r.item()
+    del ref
+    torch.cuda.empty_cache()
+    net = UNet3D(dims + [1], batchsize=1, conv_impl='tc3', seed=0)
+    errs = _step_errors(net, image, target, pred_r, loss_r, grads_r, 'tc3 160^3 random init vs exact-fp32 mode')
+    _assert_north_star(*errs)
+    del net
+    torch.cuda.empty_cache()
+    # the plain-TF32 fast mode on the same input, for the record (NOT parity gated: outside the bar by design)
+    fast = UNet3D(dims + [1], batchsize=1, conv_impl='tc', seed=0)
+    _step_errors(fast, image, target, pred_r, loss_r, grads_r, 'tc (plain TF32, fast mode, not gated) 160^3 vs exact-fp32 mode')
