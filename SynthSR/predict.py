@@ -25,6 +25,9 @@ def build_unet(n_channels=1, model_file=None, conv_impl='tc3'):
                                  final_pred_activation='linear', batch_norm=-1, activation='elu', input_model=None,
                                  conv_impl=conv_impl)
     if model_file is not None:
+        if not os.path.isfile(model_file):
+            raise FileNotFoundError('model weights not found: %s -- pass --model / model=<path to a Keras .h5 file> (the '
+                                    "reference ships models/SynthSR_v10_210712*.h5; this repository does not)" % model_file)
         unet_model.load_weights(model_file, by_name=True)
     return unet_model
 

@@ -162,7 +162,14 @@ def training(labels_dir,
                              loss_cropping=loss_cropping, m=m, M=M, fs_header=fs_header_segnet, nb_features=unet_feat_count,
                              nb_levels=n_levels, conv_size=conv_size, feat_mult=feat_multiplier,
                              nb_conv_per_level=nb_conv_per_level)
-    engine = TrainingEngine(plan, batchsize=batchsize, nb_features=unet_feat_count, nb_levels=n_levels,
+    # augmentation / initialisation seed: fresh OS entropy per run like the reference's unseeded tf.random / glorot draws
+    # (SSR_SEED pins it); rank 0's value is shared so that every replica initialises the same weights
+    seed = int(os.environ['SSR_SEED']) if os.environ.get('SSR_SEED') else int.from_bytes(os.urandom(4), 'little') >> 2
+    if world > 1:
+        box = [seed]
+        dist.broadcast_object_list(box, src=0)
+        seed = int(box[0])
+    engine = TrainingEngine(plan, batchsize=batchsize, nb_features=unet_feat_count, nb_levels=n_levels, seed=seed,
                             conv_size=conv_size, feat_mult=feat_multiplier, nb_conv_per_level=nb_conv_per_level,
                             nb_labels=nb_labels_unet, lr=lr, lr_decay=lr_decay, metric=regression_metric,
                             work_with_residual_channel=work_with_residual_channel, loss_cropping=loss_cropping,
@@ -181,6 +188,9 @@ def training(labels_dir,
     return model
 
 
+FLAT_LAYOUT_VERSION = 2      # 2: flat parameter buffer in backward-completion order (synthsr_b200/unet.py)
+
+
 def load_checkpoint(engine, path, different_lhood_layer=False):
     """weights by Keras layer name (+ this engine's Adam state when the file holds it).  Accepts the reference's own
     checkpoints (Keras .h5: ModelCheckpoint full-model files or `save_weights` files, training.py:353-369, 429) and the
@@ -197,11 +207,17 @@ def load_checkpoint(engine, path, different_lhood_layer=False):
     if different_lhood_layer:
         sd = {k: v for k, v in sd.items() if not k.startswith('unet_likelihood')}
     engine.net.load_state_dict(sd, strict=False)
-    if 'm' in opt and not different_lhood_layer and np.size(opt['m']) == engine.net.n_params:
+    # the flat Adam moments are positional: only a file written with the same buffer layout may restore them
+    same_layout = 'layout' in opt and int(np.asarray(opt['layout']).reshape(-1)[0]) == FLAT_LAYOUT_VERSION
+    if 'm' in opt and same_layout and not different_lhood_layer and np.size(opt['m']) == engine.net.n_params:
         import torch
         engine.net.adam_m.copy_(torch.as_tensor(np.asarray(opt['m'], dtype=np.float32)))
         engine.net.adam_v.copy_(torch.as_tensor(np.asarray(opt['v'], dtype=np.float32)))
         engine.net.iterations = int(np.asarray(opt['iterations']).reshape(-1)[0])
+        if 'aug_state' in opt:       # continue the augmentation counters instead of replaying the first steps' noise
+            steps, philox = [int(v) for v in np.asarray(opt['aug_state']).reshape(-1)[:2]]
+            engine.steps = steps
+            engine.gen.philox_step = philox
     stem = os.path.splitext(os.path.basename(path))[0]
     return int(stem[-3:]) if stem[-3:].isdigit() else 0
 
@@ -212,8 +228,11 @@ def save_checkpoint(engine, path):
     /optimizer_weights for an exact resume on this engine."""
     from synthsr_b200 import h5lite
     from synthsr_b200.unet import keras_layer_order
+    philox = max(g.philox_step for g in (engine._gens or [engine.gen]))
     extra = {'m': engine.net.adam_m.cpu().numpy(), 'v': engine.net.adam_v.cpu().numpy(),
-             'iterations': np.array([engine.net.iterations], dtype=np.int64)}
+             'iterations': np.array([engine.net.iterations], dtype=np.int64),
+             'layout': np.array([FLAT_LAYOUT_VERSION], dtype=np.int64),
+             'aug_state': np.array([engine.steps, philox], dtype=np.int64)}
     if str(path).endswith('.h5'):
         h5lite.save_keras_weights(path, engine.net.state_dict(), keras_layer_order(engine.net.L), extra=extra,
                                   full_model=True)
@@ -223,31 +242,97 @@ def save_checkpoint(engine, path):
         np.savez(path, **sd)
 
 
+class _PinnedInputs:
+    """Host side of the per-step input feed: label maps (and real images) as PINNED int32 / float32 tensors the engine copies
+    to the device asynchronously on its generator stream.  With batchsize 1 the sampler hands out views of its cached
+    volumes, so each distinct volume is converted (int64 -> int32) and pinned ONCE and then re-used every time it is drawn;
+    anything else (batchsize > 1, evicted volumes) goes through a small ring of pinned buffers guarded by copy events.
+    (The reference re-decodes and feeds an int64 array through feed_dict every step, model_inputs.py:91, training.py:449.)"""
+
+    def __init__(self, cuda, budget_bytes=None, ring=4):
+        import torch
+        self.torch, self.cuda = torch, cuda
+        self.budget = int(float(os.environ.get('SSR_PINNED_INPUTS_GB', '4')) * (1 << 30)) if budget_bytes is None else budget_bytes
+        self.used, self.cache = 0, {}
+        self.ring, self.ring_i, self.nring = {}, 0, ring
+
+    def _new(self, shape, dtype):
+        return self.torch.empty(tuple(shape), dtype=dtype, pin_memory=self.cuda)
+
+    def get(self, arr, dtype, gen_stream=None):
+        """arr: numpy array [B, X, Y, Z] (any integer / float dtype) -> (pinned tensor, release) ; call release(stream)
+        after the engine has enqueued its copy."""
+        torch = self.torch
+        root = arr
+        while isinstance(root.base, np.ndarray):
+            root = root.base
+        nbytes = arr.size * 4
+        if root.size == arr.size and self.used + nbytes <= self.budget or (id(root), dtype) in self.cache:
+            hit = self.cache.get((id(root), dtype))
+            if hit is not None and hit[0] is root:
+                return hit[1], None
+            t = self._new(arr.shape, dtype)
+            np.copyto(t.numpy(), arr, casting='unsafe')
+            if root.size == arr.size:
+                self.cache[(id(root), dtype)] = (root, t)         # holding `root` keeps id() unique
+                self.used += nbytes
+            return t, None
+        key = (tuple(arr.shape), dtype)
+        slots = self.ring.setdefault(key, [[self._new(arr.shape, dtype), None] for _ in range(self.nring)])
+        slot = slots[self.ring_i % self.nring]
+        self.ring_i += 1
+        if slot[1] is not None:
+            slot[1].synchronize()                                 # the copy that last read this buffer has executed
+        np.copyto(slot[0].numpy(), arr, casting='unsafe')
+
+        def release(stream):
+            if self.cuda:
+                slot[1] = slot[1] or torch.cuda.Event()
+                slot[1].record(stream)
+        return slot[0], release
+
+
 def train_model(engine, generator, learning_rate, lr_decay, n_epochs, n_steps, model_dir, init_epoch=0):
     """epochs x steps loop of the reference's fit_generator call (training.py:449-453) with one checkpoint per epoch
-    ('%03d', :429) and a plain-text loss log under model_dir/logs (:425-431 uses TensorBoard)."""
+    ('%03d', :429), TensorBoard scalars (epoch_loss, :425-431) and a plain-text loss log under model_dir/logs.
+    Per step: pinned host label map -> async H2D on the generator stream -> generator -> U-Net step; the loss of every
+    step is read back to a pinned host buffer asynchronously (Keras reads it for its progress bar) and consumed at the end
+    of the epoch, so the host never waits for the GPU inside an epoch."""
     import torch
     log_dir = os.path.join(model_dir, 'logs')
     utils.mkdir(log_dir)
     engine.lr, engine.lr_decay = learning_rate, lr_decay
     is_main = engine.rank == 0
     log = open(os.path.join(log_dir, 'loss.csv'), 'a') if is_main else None
+    tb = None
+    if is_main:
+        from synthsr_b200.tbevents import EventWriter
+        tb = EventWriter(log_dir)
+    cuda = engine.device.type == 'cuda'
+    feed = _PinnedInputs(cuda)
+    host_losses = torch.zeros(n_steps, dtype=torch.float64, pin_memory=cuda)
     for epoch in range(init_epoch, n_epochs):
-        t0, losses = time.time(), []
+        t0, n_loss = time.time(), 0
         for step in range(n_steps):
             inputs, _ = next(generator)
-            labels = torch.as_tensor(np.ascontiguousarray(np.asarray(inputs[0])[..., 0], dtype=np.int32))
-            labels = labels.pin_memory().cuda(non_blocking=True)
-            real = None
+            lab, rel_lab = feed.get(np.asarray(inputs[0])[..., 0], torch.int32)
+            real, rel_real = (None, None)
             if len(inputs) > 3:
-                real = torch.as_tensor(np.ascontiguousarray(np.asarray(inputs[3])[..., 0], dtype=np.float32)).cuda()
+                real, rel_real = feed.get(np.asarray(inputs[3])[..., 0], torch.float32)
             # pipelined like fit_generator's queue: this batch is generated while the previous one is trained on; the
             # last batch of the epoch is flushed before the loss is reported and the checkpoint written
-            l = engine.train_step_pipelined(labels, inputs[1], inputs[2], real_image=real)
+            l = engine.train_step_pipelined(lab, inputs[1], inputs[2], real_image=real)
+            for rel in (rel_lab, rel_real):
+                if rel is not None:
+                    rel(engine._gen_stream)
             if l is not None:
-                losses.append(l.clone())
-        losses.append(engine.flush().clone())
-        loss = float(torch.stack([l.reshape(()) for l in losses]).mean().item())
+                host_losses[n_loss:n_loss + 1].copy_(l, non_blocking=True)
+                n_loss += 1
+        host_losses[n_loss:n_loss + 1].copy_(engine.flush(), non_blocking=True)
+        n_loss += 1
+        if cuda:
+            torch.cuda.current_stream().synchronize()
+        loss = float(host_losses[:n_loss].mean().item())
         if not np.isfinite(loss):
             raise FloatingPointError('Loss not finite')              # tf.debugging.check_numerics (metrics_model.py:228)
         if is_main:
@@ -256,6 +341,10 @@ def train_model(engine, generator, learning_rate, lr_decay, n_epochs, n_steps, m
                                                                        n_steps * engine.B * engine.world / dt))
             log.write('%d,%.6f,%.3f\n' % (epoch + 1, loss, dt))
             log.flush()
+            tb.scalar('epoch_loss', loss, epoch)                     # what Keras' TensorBoard callback logs per epoch
+            tb.scalar('volumes_per_second', n_steps * engine.B * engine.world / dt, epoch)
             save_checkpoint(engine, os.path.join(model_dir, '%03d.h5' % (epoch + 1)))
     if log:
         log.close()
+    if tb:
+        tb.close()

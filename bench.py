@@ -2,17 +2,27 @@
 """Headline benchmark (BASELINE.json): training volumes/sec on 160^3 single-channel volumes, 5-level 24-feature U-Net,
 generator + U-Net + Adam every step, at N GPUs of one node (data parallel, one process per GPU).
 
-    python bench.py --gpus 1 --steps 20 --warmup 5
+    python bench.py --gpus 1 --steps 50 --warmup 10
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...        # CPU arm: the oracle restatement of the reference on the host cores
+    python bench.py --config c1|c4|c5           # the other BASELINE.json configs (c2 = the headline, default)
 
 Prints ONE JSON line (rank 0).  A "step" is one pass of the hot path (generate a synthetic scan pair from a label map,
 U-Net forward/backward, L1 loss, Adam) over one mini-batch of 1 volume per GPU.
+
+  value   K steps timed on the device (CUDA events, barrier + synchronize on both sides, max over ranks), label maps
+          already resident in HBM; per-step percentiles from one event per step
+  e2e     the same metric through the drop-in call a user makes -- SynthSR.training.training() on a directory of .npz
+          label maps (epochs=2, steps_per_epoch=K; epoch 1 warms up) -- timed from the CUDA events the engine records after
+          every step of epoch 2: host sampler, pinned label map -> H2D, generator, U-Net step, loss read-back, every step
+  parity  measured live on one batch: prediction / loss of the benchmarked mode against the exact-fp32 mode
 """
 import argparse
 import json
 import os
+import shutil
 import sys
+import tempfile
 import threading
 import time
 
@@ -32,14 +42,15 @@ SIZE = 160
 TRAINING_DEFAULTS = dict(scaling_bounds=0.15, rotation_bounds=15, shearing_bounds=0.02, translation_bounds=5,
                          nonlin_std=4., nonlin_shape_factor=0.03125, bias_field_std=.3, bias_shape_factor=0.03125,
                          blur_range=1.15, build_reliability_maps=False, output_div_by_n=32)   # SynthSR/training.py:57-73
+HYPERFINE_RES = [[1.5, 1.5, 5.], [1.5, 1.5, 5.]]
 
 
-def conv_flops_per_step(size, cin=1):
+def conv_flops_per_step(shape, cin=1):
     """algorithmic conv FLOPs of one training step: fwd + dgrad + wgrad."""
     from synthsr_b200.unet import layer_specs
-    v = float(size) ** 3
+    shape = [shape] * 3 if isinstance(shape, (int, np.integer)) else shape
+    v = float(np.prod(shape))
     fwd, first = 0., None
-    lvl = {}
     for name, kind, ci, co in layer_specs(cin):
         if kind == 'bn':
             continue
@@ -57,21 +68,36 @@ def conv_flops_per_step(size, cin=1):
     return fwd, 3 * fwd - first
 
 
-def make_inputs(size, n_maps=2, seed=0):
+def make_inputs(shape, n_maps=2, seed=0, n_channels=1):
     from synthsr_b200.synthetic import GEN_CLASSES, GEN_LABELS, phantom_labels, synthetic_priors
+    shape = [int(s) for s in (shape if isinstance(shape, (list, tuple)) else [shape] * 3)]
     maps = []
     for i in range(n_maps):
-        lo = phantom_labels([size // 2] * 3, GEN_LABELS, seed=seed + i)
-        maps.append(np.ascontiguousarray(np.repeat(np.repeat(np.repeat(lo, 2, 0), 2, 1), 2, 2)[:size, :size, :size]))
-    pm, ps = synthetic_priors(int(GEN_CLASSES.max()) + 1, 1, seed)
+        lo = phantom_labels([(s + 1) // 2 for s in shape], GEN_LABELS, seed=seed + i)
+        maps.append(np.ascontiguousarray(np.repeat(np.repeat(np.repeat(lo, 2, 0), 2, 1), 2, 2)[:shape[0], :shape[1], :shape[2]]))
+    pm, ps = synthetic_priors(int(GEN_CLASSES.max()) + 1, n_channels, seed)
     return maps, pm, ps, GEN_LABELS, GEN_CLASSES
 
 
-def draw_gmm(rng, pm, ps, classes):
+def draw_gmm(rng, pm, ps, classes, n_channels=1):
     """SynthSR/model_inputs.py:118-123 ('normal' priors, negatives clipped)."""
-    m = np.clip(rng.normal(pm[0], pm[1]), 0, None)[classes]
-    s = np.clip(rng.normal(ps[0], ps[1]), 0, None)[classes]
-    return m[None, :, None].astype(np.float32), s[None, :, None].astype(np.float32)
+    m = np.stack([np.clip(rng.normal(pm[2 * c], pm[2 * c + 1]), 0, None)[classes] for c in range(n_channels)], -1)[None]
+    s = np.stack([np.clip(rng.normal(ps[2 * c], ps[2 * c + 1]), 0, None)[classes] for c in range(n_channels)], -1)[None]
+    return m.astype(np.float32), s.astype(np.float32)
+
+
+def workload(config, size):
+    """-> (label shape, (input_channels, output_channel), GeneratorPlan kwargs, engine kwargs, description)"""
+    if config == 'c4':       # BASELINE configs[3]: Hyperfine T1+T2 (scripts/predict_command_line_hyperfine.py:60-73; SURVEY 8d c4)
+        gen = dict(TRAINING_DEFAULTS, data_res=np.array(HYPERFINE_RES), thickness=np.array(HYPERFINE_RES), downsample=True,
+                   simulate_registration_error=True)
+        return [192, 192, 64], ([False, True, True], 0), gen, dict(work_with_residual_channel=[0]), \
+            'Hyperfine 192x192x64: synthetic 1 mm target + T1/T2 inputs at 1.5x1.5x5 mm with registration error -> 2-channel ' \
+            '5-level 24-feature U-Net (residual on channel 0) fwd/bwd, L1, Adam; batch 1 per GPU (BASELINE configs[3])'
+    n = 256 if config == 'c5' else size
+    return [n] * 3, (True, 0), dict(TRAINING_DEFAULTS), {}, \
+        '%d^3 single-channel label map -> generator (training() defaults) -> 5-level 24-feature U-Net fwd/bwd, L1, Adam; ' \
+        'batch 1 per GPU (BASELINE configs[%s])' % (n, '4' if config == 'c5' else '1]/[2')
 
 
 class ClockSampler(threading.Thread):
@@ -105,7 +131,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
         if not self.samples:
@@ -113,81 +139,144 @@ class ClockSampler(threading.Thread):
         return {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
 
 
-def cpu_reference_steps(size, steps, warmup, threads):
-    """the reference's algorithm on the host cores (oracle restatement; TensorFlow itself is not installable here):
-    generator (NumPy) + U-Net fwd/bwd + Adam (torch CPU fp32).  Returns seconds per step for a size^3 volume."""
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm on the host cores (oracle restatement; TensorFlow is not installable here)
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference_steps(shape, steps, warmup, threads, budget_s=None, gen_kw=None, channels=(True, 0), cin=1, loss_kw=None):
+    """generator (NumPy) + U-Net fwd/bwd + Adam (torch CPU fp32) on volumes of `shape`: REAL steps at the real size.
+    Stops early once `budget_s` seconds of timed steps are spent (at least one).  -> (seconds per step, steps timed)."""
     import torch
     from oracle import generator as OG
     from oracle import unet as OU
     from synthsr_b200.draws import sample_draws
     from synthsr_b200.generator import GeneratorPlan
     torch.set_num_threads(threads)
-    maps, pm, ps, gl, gc = make_inputs(size, 1)
-    cfg = dict(TRAINING_DEFAULTS)
-    plan = GeneratorPlan([size] * 3, True, 0, gl, None, 1., None, **cfg)
+    shape = [shape] * 3 if isinstance(shape, (int, np.integer)) else list(shape)
+    n_ch = len(channels[0]) if isinstance(channels[0], (list, tuple)) else 1
+    maps, pm, ps, gl, gc = make_inputs(shape, 1, n_channels=n_ch)
+    cfg = dict(gen_kw or TRAINING_DEFAULTS)
+    plan = GeneratorPlan(shape, channels[0], channels[1], gl, None, 1., None, **cfg)
     rng = np.random.default_rng(0)
-    params = OU.init_params(0, 1)
+    params = OU.init_params(0, cin)
     opt = OU.adam_init(params)
+    ocfg = dict(cfg, generation_labels=gl)
+    if n_ch > 1:
+        ocfg.update(input_channels=channels[0], output_channel=channels[1])
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         draws = sample_draws(rng, plan, 1, gmm_noise=True)
-        m, s = draw_gmm(rng, pm, ps, gc)
-        image, target = OG.labels_to_image(dict(cfg, generation_labels=gl), [maps[0][None, ..., None], m, s], draws)
-        OU.train_step(params, opt, torch.from_numpy(image), torch.from_numpy(target), lr=1e-4)
+        m, s = draw_gmm(rng, pm, ps, gc, n_ch)
+        image, target = OG.labels_to_image(ocfg, [maps[0][None, ..., None], m, s], draws)
+        OU.train_step(params, opt, torch.from_numpy(image), torch.from_numpy(target), lr=1e-4, **(loss_kw or {}))
         if it >= warmup:
             times.append(time.perf_counter() - t0)
+            if budget_s is not None and sum(times) > budget_s:
+                break
+    return float(np.mean(times)), len(times)
+
+
+def cpu_generator_calls(shape, calls):
+    """c1 on the host: oracle generator (NumPy float32) with BrainGenerator's defaults -> seconds per volume"""
+    from oracle import generator as OG
+    from synthsr_b200.draws import sample_draws
+    from synthsr_b200.generator import GeneratorPlan
+    maps, pm, ps, gl, gc = make_inputs(shape, 1)
+    plan = GeneratorPlan(list(shape), True, 0, gl, None, 1., None)
+    rng = np.random.default_rng(0)
+    times = []
+    for it in range(calls + 1):
+        t0 = time.perf_counter()
+        draws = sample_draws(rng, plan, 1, gmm_noise=True)
+        m, s = draw_gmm(rng, pm, ps, gc)
+        OG.labels_to_image(dict(generation_labels=gl), [maps[0][None, ..., None], m, s], draws)
+        if it:
+            times.append(time.perf_counter() - t0)
     return float(np.mean(times))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def write_dataset(root, maps, pm, ps, gl, gc):
+    """the on-disk inputs SynthSR.training.training() / BrainGenerator take: a folder of label maps + .npy hyper-parameters"""
+    lab_dir = os.path.join(root, 'labels')
+    os.makedirs(lab_dir, exist_ok=True)
+    for i, m in enumerate(maps):
+        np.savez(os.path.join(lab_dir, 'map_%02d.npz' % i), vol_data=m.astype(np.int32))
+    paths = {}
+    for name, arr in (('prior_means', pm), ('prior_stds', ps), ('generation_labels', gl), ('generation_classes', gc)):
+        paths[name] = os.path.join(root, name + '.npy')
+        np.save(paths[name], arr)
+    return lab_dir, paths
+
+
+def percentiles(ms):
+    ms = np.asarray(ms, dtype=np.float64)
+    return {'median': float(np.median(ms)), 'p10': float(np.percentile(ms, 10)), 'p90': float(np.percentile(ms, 90)),
+            'n': int(ms.size)}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='c2', choices=['c1', 'c2', 'c4', 'c5'],
+                    help='BASELINE.json configs: c1 generator only 64^3 via BrainGenerator.generate_brain(); c2 160^3 training '
+                         'step (headline, also configs[2] at N GPUs); c4 Hyperfine 192x192x64 two input channels; c5 256^3')
     ap.add_argument('--size', type=int, default=SIZE)
     ap.add_argument('--conv-impl', default='tc3', choices=['tc3', 'tc', 'ref'],
                     help="tc3 (default): forward compensated to fp32-class accuracy (the parity-gated mode); tc: plain TF32 "
                          "(fast, outside the 1e-3 bar); ref: exact fp32 CUDA-core convolutions")
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true', help='skip the SynthSR.training.training() leg')
+    ap.add_argument('--no-extras', action='store_true', help='skip the live parity check and the fast-mode secondary number')
     ap.add_argument('--no-pipeline', action='store_true',
                     help='generate and train on the same batch inside one call (no generator / training overlap)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
-    fwd_f, step_f = conv_flops_per_step(args.size)
+    if args.config == 'c1':
+        return bench_generator(args, rank, local_rank, world)
+    shape, channels, gen_kw, eng_kw, desc = workload(args.config, args.size)
+    cin = sum(bool(c) for c in channels[0]) if isinstance(channels[0], (list, tuple)) else 1
+    n_ch = len(channels[0]) if isinstance(channels[0], (list, tuple)) else 1
+    fwd_f, step_f = conv_flops_per_step(shape, cin)
     metric = 'training volumes/sec (160^3, 24-ch 5-level U-Net, generator+U-Net+Adam step)'
-    config = {'workload': '%d^3 single-channel label map -> generator (training() defaults) -> 5-level 24-feature '
-                          'U-Net fwd/bwd, L1, Adam; batch 1 per GPU (BASELINE configs[1]/[2])' % args.size,
-              'global_batch': args.gpus, 'volume': [args.size] * 3, 'parallelism': 'dp%d' % args.gpus,
+    if args.config != 'c2' or args.size != SIZE:
+        metric = 'training volumes/sec (%s, 24-ch 5-level U-Net, generator+U-Net+Adam step)' % 'x'.join(str(s) for s in shape)
+    config = {'workload': desc, 'global_batch': args.gpus, 'volume': shape, 'parallelism': 'dp%d' % args.gpus,
               'l2_policy': 'per-step working set (>4 GB of activations) exceeds the 126 MB L2; no explicit flush',
+              'conv_impl': args.conv_impl,
               'pipeline': 'generator of batch i+1 overlaps the U-Net step of batch i (one generator pass + one training '
-                          'pass per step, as the reference\'s fit_generator queue)' if '--no-pipeline' not in sys.argv
+                          'pass per step, as the reference\'s fit_generator queue)' if not args.no_pipeline
                           else 'none (generate, then train, inside each step)'}
+    loss_kw = dict(work_with_residual_channel=eng_kw['work_with_residual_channel']) if eng_kw else {}
 
     if args.impl == 'reference':
         if rank != 0:
             return
         threads = min(len(os.sched_getaffinity(0)), 32)     # torch-CPU convs stop scaling (and oversubscribe) beyond ~32
-        sample = 64                      # bounded sample: a 64^3 step is 1/15.6 of the 160^3 workload (linear in voxels)
         warm = min(args.warmup, 1)
-        sec = cpu_reference_steps(sample, args.steps, warm, threads)
-        vps = 1.0 / (sec * (args.size / sample) ** 3)
-        out = {'metric': metric, 'value': vps, 'unit': 'volumes/s', 'n_gpus': args.gpus, 'steps': args.steps,
-               'warmup': warm, 'ms_per_step': 1e3 / vps, 'higher_is_better': True, 'scaling': 'weak',
+        sec, done = cpu_reference_steps(shape, args.steps, warm, threads, budget_s=150., gen_kw=gen_kw, channels=channels,
+                                        cin=cin, loss_kw=loss_kw)
+        vps = 1.0 / sec
+        out = {'metric': metric, 'value': vps, 'unit': 'volumes/s', 'n_gpus': args.gpus, 'steps': done,
+               'warmup': warm, 'ms_per_step': 1e3 * sec, 'higher_is_better': True, 'scaling': 'weak',
                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config, 'impl': 'reference',
                'cpu_baseline': {'value': vps, 'unit': 'volumes/s', 'cores': threads, 'kind': 'port',
-                                'sample': 'oracle restatement (NumPy generator + torch-CPU fp32 U-Net step) on %d^3 '
-                                          'sub-volumes, scaled by voxel count to %d^3; reference TF-CPU: not run '
-                                          '(TensorFlow 2.0 not installable)' % (sample, args.size)},
+                                'sample': '%d real steps at the full %s size (requested %d; the loop stops once 150 s of timed '
+                                          'steps are spent): oracle restatement of the reference graph -- NumPy generator + '
+                                          'torch-CPU fp32 U-Net fwd/bwd/Adam; reference TF-CPU itself: not run (TensorFlow '
+                                          '2.0 not installable here)' % (done, 'x'.join(str(s) for s in shape), args.steps)},
                'e2e': {'value': vps, 'unit': 'volumes/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
         print(json.dumps(out))
         return
 
     import torch
     import torch.distributed as dist
+    from synthsr_b200 import trainer as T
     from synthsr_b200._lib import lib
     from synthsr_b200.generator import GeneratorPlan
     from synthsr_b200.trainer import TrainingEngine
@@ -196,11 +285,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    maps, pm, ps, gl, gc = make_inputs(args.size, 2, seed=rank)
-    plan = GeneratorPlan([args.size] * 3, True, 0, gl, None, 1., None, **TRAINING_DEFAULTS)
-    eng = TrainingEngine(plan, batchsize=1, conv_impl=args.conv_impl, seed=0, rank=rank, world_size=world)
-    dev_maps = [torch.from_numpy(m[None]).cuda() for m in maps]
-    pinned = [torch.from_numpy(m[None]).pin_memory() for m in maps]
+    maps, pm, ps, gl, gc = make_inputs(shape, 2, seed=rank, n_channels=n_ch)
+    plan = GeneratorPlan(shape, channels[0], channels[1], gl, None, 1., None, **gen_kw)
     rng = np.random.default_rng(1234 + rank)
 
     def barrier():
@@ -208,79 +294,61 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    host_loss = [torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(2)]
-    lab_dev = [torch.empty_like(dev_maps[0]) for _ in range(2)]
-    loss_ev = [torch.cuda.Event() for _ in range(2)]
+    def build(conv_impl):
+        return TrainingEngine(plan, batchsize=1, conv_impl=conv_impl, seed=0, rank=rank, world_size=world, **eng_kw)
 
-    pipelined = not args.no_pipeline
-
-    def step(lab, m, s):
-        """one step = one generator pass + one U-Net training pass.  Pipelined (default): the batch of this call is
-        generated on the generator stream while the network trains on the batch of the previous call, like the
-        reference's fit_generator queue; the returned loss is the previous batch's (None on the very first call)."""
-        return eng.train_step_pipelined(lab, m, s) if pipelined else eng.train_step(lab, m, s)
-
-    def run_steps(n, host_inputs):
-        """host_inputs (e2e): every step copies its label map from pinned host memory and reads a loss back to the host;
-        the read-back of step i is consumed while step i+1 is being enqueued (one step of lag, like a logging callback)."""
+    def run_device_steps(eng, n, dev_maps):
         loss = None
         for i in range(n):
-            m, s = draw_gmm(rng, pm, ps, gc)
-            if host_inputs:
-                if pipelined:
-                    l = step(pinned[i % len(pinned)], m, s)                        # H2D of this step's input on the generator stream
-                else:
-                    lab = lab_dev[i % 2]
-                    lab.copy_(pinned[i % len(pinned)], non_blocking=True)          # H2D of this step's input, in-stream
-                    l = step(lab, m, s)
-                if l is not None:
-                    host_loss[i % 2].copy_(l, non_blocking=True)
-                loss_ev[i % 2].record()
-                if i > 0:
-                    loss_ev[(i - 1) % 2].synchronize()
-                    loss = float(host_loss[(i - 1) % 2][0])
+            m, s = draw_gmm(rng, pm, ps, gc, n_ch)
+            if args.no_pipeline:
+                loss = eng.train_step(dev_maps[i % len(dev_maps)], m, s)
             else:
-                loss = step(dev_maps[i % len(dev_maps)], m, s)
-        if host_inputs and n > 0:
-            loss_ev[(n - 1) % 2].synchronize()
-            loss = float(host_loss[(n - 1) % 2][0])
-            assert np.isfinite(loss), 'loss is not finite'
+                loss = eng.train_step_pipelined(dev_maps[i % len(dev_maps)], m, s)
         return loss
 
-    def timed(n, host_inputs):
+    def timed_device(eng, n, dev_maps):
+        """EXACTLY n steps between two events, barrier + synchronize on both sides, max over ranks; one event per step"""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        T.STEP_EVENTS = []
         barrier()
         l0 = lib.ssr_launch_count()
         e0.record()
-        run_steps(n, host_inputs)
+        run_device_steps(eng, n, dev_maps)
         e1.record()
         barrier()
+        evs, T.STEP_EVENTS = T.STEP_EVENTS, None
         ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item(), lib.ssr_launch_count() - l0
+        per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(len(evs) - 1)]
+        return ms.item(), lib.ssr_launch_count() - l0, per_step
 
-    run_steps(max(args.warmup, 3), False)
+    eng = build(args.conv_impl)
+    dev_maps = [torch.from_numpy(m[None]).cuda() for m in maps]
+    run_device_steps(eng, max(args.warmup, 3), dev_maps)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms, launches = timed(args.steps, False)
+    ms, launches, per_step = timed_device(eng, args.steps, dev_maps)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     value = world * args.steps / (ms / 1e3)
-    run_steps(max(args.warmup, 3), True)              # the host-buffer path gets the same warm-up as the device path
-    def staged():
-        return sum(g.stage.bytes_moved for g in (eng._gens or [eng.gen]))
-    sg_before = staged()
-    ms_e2e, _ = timed(args.steps, True)
-    e2e = world * args.steps / (ms_e2e / 1e3)
-    h2d = maps[0].nbytes + (staged() - sg_before) // max(args.steps, 1)
+    eng.flush()
+    torch.cuda.synchronize()
+
+    replicas = None
+    if world > 1:      # NCCL path correctness: every replica must hold bit-identical parameters after the timed steps
+        chk = torch.stack([eng.net.params.double().sum(), eng.net.params.double().abs().sum(),
+                           eng.net.comm[eng.net.n_params:].double().sum()])
+        allc = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        replicas = bool(all(torch.equal(allc[0], c) for c in allc))
+        assert replicas, 'replicas diverged: parameter checksums differ across ranks'
 
     # ---- roofline of the dominant kernel class: live CUDA-event timing of every convolution launch ------------
-    eng.flush()                                  # train the pending batch of the pipelined loop, then profile unpipelined
-    torch.cuda.synchronize()
     eng.net.prof = []
     for i in range(2):
-        eng.train_step(dev_maps[i % len(dev_maps)], *draw_gmm(rng, pm, ps, gc))
+        eng.train_step(dev_maps[i % len(dev_maps)], *draw_gmm(rng, pm, ps, gc, n_ch))
     torch.cuda.synchronize()
     agg = {}
     for kind, fl, a, b in eng.net.prof:
@@ -298,11 +366,13 @@ def main():
     # dominant kernel = the tensor-core convolution kind with the largest share of the step (each kind is one kernel
     # family: wgrad_tc -> wgrad_tc_persistent_kernel, fwd_tc / dgrad_tc -> conv3d_tc_kernel + conv3d_tc_k2n_kernel +
     # conv3d_tc_up_kernel).  FLOPs are ALGORITHMIC (2*27*Cin*Cout*voxels of the reference's layer): the
-    # parity path of the decoder convolutions executes 8 instead of 27 taps on the upsampled channels.
+    # parity path of the decoder convolutions executes 8 instead of 27 taps on the upsampled channels, the compensated
+    # forward executes 3 MMAs per algorithmic one.
     tc = {k: v for k, v in agg.items() if k.endswith('_tc')}
     dom = max(tc, key=lambda k: tc[k][0]) if tc else None
     names = {'wgrad_tc': 'wgrad_tc_persistent_kernel (<0> plain, <1> parity classes of the decoder convolutions)',
-             'fwd_tc': 'conv3d_tc_kernel / conv3d_tc_k2n_kernel / conv3d_tc_up_kernel<1> (forward)',
+             'fwd_tc': 'conv3d_tc_kernel / conv3d_tc_k2n_kernel / conv3d_tc_up_kernel<1> (forward%s)' % (
+                 '; compensated: K = [x | x_lo | x] x [w_hi | w_hi | w_lo], + tf32_residual_kernel' if args.conv_impl == 'tc3' else ''),
              'dgrad_tc': 'conv3d_tc_kernel / conv3d_tc_k2n_kernel / conv3d_tc_up_kernel<2> (data gradient)'}
     achieved = tc[dom][1] / (tc[dom][0] * 1e-3) / 1e12 if dom else 0.       # algorithmic 2*27*Cin*Cout*voxels per launch
     tc_ms = sum(v[0] for v in tc.values())
@@ -315,30 +385,206 @@ def main():
             traffic, traffic_note = tj[dom]['dram_bytes_per_launch'], tj[dom]['launch']
     except Exception:
         pass
+    step_tf = step_f / (ms / args.steps * 1e-3) / 1e12
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
                 'traffic': traffic, 'traffic_launch': traffic_note, 'peak_source': peak_src,
                 'kernel': '%s (tcgen05 kind::tf32), %.2f ms of the step in %d launches' % (
                     names.get(dom, dom), tc[dom][0] / 2, tc[dom][2] // 2) if dom else None,
                 'frac_of_tf32_peak': achieved / (peak / 2),
                 'all_tc_convolutions': {'tflops': all_tc, 'frac_of_tf32_peak': all_tc / (peak / 2), 'ms_per_step': tc_ms / 2},
+                'whole_step': {'tflops': step_tf, 'frac_of_tf32_peak': step_tf / (peak / 2)},
                 'per_kind': {k: {'ms_per_step': agg[k][0] / 2, 'tflops': agg[k][1] / (agg[k][0] * 1e-3) / 1e12 if agg[k][0] else 0.,
                                  'launches_per_step': agg[k][2] // 2} for k in sorted(agg)},
                 'conv_share_of_step': (sum(v[0] for v in agg.values()) / 2) / (ms / args.steps),
-                'note': 'per-kind times are measured with the weight-gradient overlap disabled (serialised launches)'}
+                'note': 'FLOPs are algorithmic (one per reference multiply-add x 2); per-kind times are measured with the '
+                        'weight-gradient overlap disabled (serialised launches)'}
     out = {'metric': metric, 'value': value, 'unit': 'volumes/s', 'n_gpus': args.gpus, 'steps': args.steps,
            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
            'vs_baseline': None, 'dtype': 'tf32' if args.conv_impl in ('tc', 'tc3') else 'f32', 'data': 'synthetic',
            'config': config, 'clocks': sampler.summary(), 'gpu_launches': int(launches),
-           'e2e': {'value': e2e, 'unit': 'volumes/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 8},
+           'step_ms': percentiles(per_step) if per_step else None,
            'roofline': roofline, 'conv_gflop_per_step': step_f / 1e9}
+    if replicas is not None:
+        out['replicas_identical'] = replicas
+
+    # ---- live parity of the benchmarked mode on one generated batch, against the exact-fp32 mode -----------------------
+    image = eng.gen.image.clone()
+    target = eng.gen.target.clone()
+    del eng
+    torch.cuda.empty_cache()
+    if not args.no_extras and args.conv_impl != 'ref' and rank == 0:
+        from synthsr_b200.unet import UNet3D
+        res = {}
+        for impl in ('ref', args.conv_impl):
+            net = UNet3D(plan.image_shape, batchsize=1, conv_impl=impl, seed=0, nb_labels=plan.n_target_channels)
+            loss = net.loss_and_grad(image, target, 'l1', eng_kw.get('work_with_residual_channel'), None)
+            torch.cuda.synchronize()
+            res[impl] = (net.pred.double().clone(), loss.item(), net.grads.double().clone())
+            del net
+            torch.cuda.empty_cache()
+        (p0, l0_, g0), (p1, l1_, g1) = res['ref'], res[args.conv_impl]
+        out['parity'] = {'mode': args.conv_impl, 'against': "exact-fp32 CUDA-core mode (conv_impl='ref') on the same device, "
+                         'same generated batch, random-init weights (seed 0); the float64 oracle comparisons are in '
+                         'tests/test_unet_parity_gpu.py',
+                         'pred_rel_l2': float((p1 - p0).norm() / p0.norm()),
+                         'pred_max_over_max': float((p1 - p0).abs().max() / p0.abs().max()),
+                         'loss_rel': abs(l1_ - l0_) / abs(l0_),
+                         'grad_rel_l2': float((g1 - g0).norm() / g0.norm()), 'bar': '1e-3 prediction / loss, 1e-2 gradients'}
+        del res, p0, p1, g0, g1
+    if world > 1:
+        dist.barrier()
+
+    # ---- secondary number: the plain-TF32 fast mode (outside the parity bar), same protocol ---------------------------
+    if not args.no_extras and args.conv_impl == 'tc3':
+        eng2 = build('tc')
+        run_device_steps(eng2, max(args.warmup, 3), dev_maps)
+        ms2, _, _ = timed_device(eng2, args.steps, dev_maps)
+        eng2.flush()
+        out['fast_mode'] = {'conv_impl': 'tc', 'value': world * args.steps / (ms2 / 1e3), 'ms_per_step': ms2 / args.steps,
+                            'note': 'plain TF32 forward: 2-3e-3 on the prediction of a randomly initialised net, i.e. OUTSIDE '
+                                    'the 1e-3 parity bar; not the headline'}
+        del eng2
+        torch.cuda.empty_cache()
+    del dev_maps
+
+    # ---- e2e: the drop-in call, SynthSR.training.training(), on a directory of label maps --------------------------------
+    if not args.no_e2e:
+        from SynthSR.training import training
+        tmp = tempfile.mkdtemp(prefix='ssr_bench_%d_' % rank)
+        try:
+            lab_dir, paths = write_dataset(tmp, maps, pm, ps, gl, gc)
+            kw = dict(gen_kw)
+            kw.pop('output_div_by_n')
+            if args.config == 'c4':
+                kw.update(input_channels=channels[0], output_channel=channels[1], **eng_kw)
+            os.environ['SSR_CONV_IMPL'] = args.conv_impl
+            os.environ.setdefault('SSR_SEED', '0')
+            T.STEP_EVENTS = []
+            barrier()
+            training(lab_dir, os.path.join(tmp, 'models'), paths['prior_means'], paths['prior_stds'],
+                     paths['generation_labels'], path_generation_classes=paths['generation_classes'], batchsize=1,
+                     epochs=2, steps_per_epoch=args.steps, **kw)
+            barrier()
+            evs, T.STEP_EVENTS = T.STEP_EVENTS, None
+            assert len(evs) == 2 * args.steps, len(evs)
+            # steady-state steps of epoch 2, measured from its FIRST step's event: K - 1 step intervals (the checkpoint of
+            # epoch 1 is written between the last event of epoch 1 and the first of epoch 2, outside the interval)
+            ms_e = torch.tensor([evs[args.steps].elapsed_time(evs[-1])], device='cuda')
+            if world > 1:
+                dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
+            e2e = world * (args.steps - 1) / (ms_e.item() / 1e3)
+            small = int(4 * (16 + 3 * int(np.prod(plan.svf_small_shape or [1])) + 64 * n_ch + 2 * plan.lut_len * n_ch))
+            out['e2e'] = {'value': e2e, 'unit': 'volumes/s', 'h2d_bytes_per_step': int(maps[0].nbytes + small),
+                          'd2h_bytes_per_step': 8,
+                          'how': 'SynthSR.training.training(labels_dir of .npz maps, epochs=2, steps_per_epoch=%d): CUDA events '
+                                 'after every step; %d steady-state step intervals of epoch 2 (epoch 1 = warm-up; the '
+                                 'per-epoch checkpoint write lies between the epochs, outside the interval)' % (
+                                     args.steps, args.steps - 1)}
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    else:
+        out['e2e'] = None
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = min(len(os.sched_getaffinity(0)), 32)
-        sample = 64
-        sec = cpu_reference_steps(sample, 2, 1, threads)
-        vps = 1.0 / (sec * (args.size / sample) ** 3)
-        out['cpu_baseline'] = {'value': vps, 'unit': 'volumes/s', 'cores': threads, 'kind': 'port',
-                               'sample': '2 oracle steps (NumPy generator + torch-CPU fp32 U-Net fwd/bwd/Adam) on a 64^3 '
-                                         'volume, scaled by voxel count to %d^3' % args.size}
+        sec, done = cpu_reference_steps(shape, 2, 0, threads, budget_s=20., gen_kw=gen_kw, channels=channels, cin=cin,
+                                        loss_kw=loss_kw)
+        out['cpu_baseline'] = {'value': 1.0 / sec, 'unit': 'volumes/s', 'cores': threads, 'kind': 'port',
+                               'sample': '%d real oracle step(s) at the full %s size (NumPy generator + torch-CPU fp32 U-Net '
+                                         'fwd/bwd/Adam); not TensorFlow' % (done, 'x'.join(str(s) for s in shape))}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def bench_generator(args, rank, local_rank, world):
+    """BASELINE configs[0]: single 64^3 label map -> BrainGenerator.generate_brain() (SynthSR/brain_generator.py:317-330,
+    the class' own defaults), 1 volume per call.  HBM-bound kernels: roofline on 20 algorithmic bytes per voxel."""
+    shape = [64, 64, 64] if args.size == SIZE else [args.size] * 3
+    vox = float(np.prod(shape))
+    metric = 'generated volumes/sec (%d^3 label map -> BrainGenerator.generate_brain())' % shape[0]
+    config = {'workload': 'single %d^3 label map -> BrainGenerator defaults (brain_generator.py:30-61) -> generate_brain(): '
+                          '1 synthetic image + target per call, returned as NumPy arrays (BASELINE configs[0])' % shape[0],
+              'global_batch': args.gpus, 'volume': shape, 'parallelism': 'replicas%d' % args.gpus,
+              'l2_policy': 'inputs fit the L2 at this size (5.2 MB compulsory traffic per volume): launch- and host-bound'}
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        n = min(args.steps, 10)
+        sec = cpu_generator_calls(shape, n)
+        out = {'metric': metric, 'value': 1. / sec, 'unit': 'volumes/s', 'n_gpus': args.gpus, 'steps': n,
+               'warmup': 1, 'ms_per_step': 1e3 * sec, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+               'dtype': 'f32', 'data': 'synthetic', 'config': config, 'impl': 'reference',
+               'cpu_baseline': {'value': 1. / sec, 'unit': 'volumes/s', 'cores': 1, 'kind': 'port',
+                                'sample': 'oracle generator (NumPy float32, single thread) on the same 64^3 label map; not TF'},
+               'e2e': {'value': 1. / sec, 'unit': 'volumes/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(out))
+        return
+    import torch
+    import torch.distributed as dist
+    from SynthSR.brain_generator import BrainGenerator
+    from synthsr_b200._lib import lib
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    maps, pm, ps, gl, gc = make_inputs(shape, 1, seed=rank)
+    tmp = tempfile.mkdtemp(prefix='ssr_bench_c1_%d_' % rank)
+    try:
+        lab_dir, paths = write_dataset(tmp, maps, pm, ps, gl, gc)
+        bg = BrainGenerator(lab_dir, paths['prior_means'], paths['prior_stds'], 'normal', paths['generation_labels'],
+                            generation_classes=paths['generation_classes'])
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        for _ in range(max(args.warmup, 3)):
+            bg.generate_brain()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        barrier()
+        l0 = lib.ssr_launch_count()
+        e0.record()
+        for _ in range(args.steps):
+            im, tgt = bg.generate_brain()
+        e1.record()
+        barrier()
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+        launches = lib.ssr_launch_count() - l0
+        ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = ms.item()
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = peaks.get('hbm_gbs', 6650.)
+    achieved = 20. * vox * args.steps / (ms * 1e-3) / 1e9
+    value = world * args.steps / (ms / 1e3)
+    out = {'metric': metric, 'value': value, 'unit': 'volumes/s', 'n_gpus': args.gpus, 'steps': args.steps,
+           'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config, 'clocks': sampler.summary(),
+           'gpu_launches': int(launches),
+           'e2e': {'value': value, 'unit': 'volumes/s', 'h2d_bytes_per_step': int(maps[0].nbytes),
+                   'd2h_bytes_per_step': int(im.nbytes + tgt.nbytes),
+                   'how': 'generate_brain() IS the end-to-end call: host label map in, NumPy image + target out, every call'},
+           'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                        'traffic': None, 'kernel': 'whole generator call (deform / gmm_bias / blur3d kernels; at 64^3 the call '
+                                                   'is bound by its launches + the blocking NumPy round trip, not by HBM)',
+                        'peak_source': 'measured (MEASURED_PEAKS.json hbm_gbs)' if peaks else 'fallback 6650 GB/s'}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sec = cpu_generator_calls(shape, 5)
+        out['cpu_baseline'] = {'value': 1. / sec, 'unit': 'volumes/s', 'cores': 1, 'kind': 'port',
+                               'sample': '5 oracle generator calls (NumPy float32, single thread) on the same 64^3 label map'}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

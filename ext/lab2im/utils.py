@@ -54,6 +54,9 @@ def save_volume(volume, aff, header, path, res=None, dtype=None, n_dims=3):
             n_dims, _ = get_dims(volume.shape)
         header = header or nifti.blank_header()
         header.set_zooms(reformat_to_list(res, length=n_dims))
+    if path.endswith(('.mgz', '.mgh')):                  # nib.save picks the image class from the extension (utils.py:158-160)
+        nifti.save_mgz(path, volume, aff, header, dtype=dtype)
+        return
     nifti.save_nifti(path, volume, aff, header, dtype=dtype)
 
 

@@ -34,18 +34,21 @@ def rna_tf32(t):
     return u.view(torch.float32).to(t.dtype)
 
 
+LEVEL2 = None     # regex of layers compensated at level 2
 ROUND = 'xw'      # which forward operands are rounded: 'x' (activations), 'w' (weights) or both
 
 
 class ConvTF32(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, pad, fwd_exact, bwd_exact):
+        """fwd_exact: True (level 3: nothing rounded), 'w' (level 2: the weights stay rounded), False (plain TF32)"""
         ctx.save_for_backward(x, w)
         ctx.pad, ctx.bwd_exact = pad, bwd_exact
-        if fwd_exact:
+        if fwd_exact is True:
             return torch.nn.functional.conv3d(x, w, b, padding=pad)
-        xr = rne_tf32(x) if 'x' in ROUND else x
-        wr = rna_tf32(w) if 'w' in ROUND else w
+        rnd = fwd_exact if isinstance(fwd_exact, str) else ROUND
+        xr = rne_tf32(x) if 'x' in rnd else x
+        wr = rna_tf32(w) if 'w' in rnd else w
         return torch.nn.functional.conv3d(xr, wr, b, padding=pad)
 
     @staticmethod
@@ -67,6 +70,8 @@ def make_conv(exact_fwd, exact_bwd):
         if w.shape[1] % 8 != 0 or k == 1:       # first layer / head are exact fp32 on the GPU too
             return torch.nn.functional.conv3d(x, w, params[name + '/bias'], padding=k // 2)
         fe = exact_fwd is not None and re.search(exact_fwd, name) is not None
+        if LEVEL2 is not None and re.search(LEVEL2, name) is not None:
+            fe = 'w'                               # activation residual only (2 MMAs): the weight rounding remains
         be = exact_bwd is not None and re.search(exact_bwd, name) is not None
         return ConvTF32.apply(x, w, params[name + '/bias'], k // 2, fe, be)
     return conv
@@ -97,10 +102,11 @@ def main():
     ap.add_argument('--weights', default=None, help='.h5 file (trained Keras weights) instead of glorot init')
     ap.add_argument('--image', default='uniform', choices=['uniform', 'smooth'])
     ap.add_argument('--seed', type=int, default=0)
+    ap.add_argument('--level2', default=None, help='regex of layers whose forward keeps only the weight rounding')
     ap.add_argument('--round', default='xw', help="forward operands rounded to TF32: x, w or xw")
     args = ap.parse_args()
-    global ROUND
-    ROUND = args.round
+    global ROUND, LEVEL2
+    ROUND, LEVEL2 = args.round, args.level2
     n = args.size
     params = OU.init_params(args.seed, 1, dtype=torch.float64)
     if args.weights:

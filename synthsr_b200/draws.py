@@ -14,7 +14,7 @@ import numpy as np
 f32 = np.float32
 
 
-def _bounds(hyper, size, centre, default_range):
+def _bounds(hyper, size, centre, default_range, rng=None):
     """-> (lo, hi) arrays of length `size` following draw_value_from_distribution (ext/lab2im/utils.py:1001-1016)."""
     if isinstance(hyper, str):
         hyper = np.load(hyper)
@@ -23,7 +23,7 @@ def _bounds(hyper, size, centre, default_range):
     if isinstance(hyper, np.ndarray):
         assert hyper.shape[0] % 2 == 0
         n_mod = hyper.shape[0] // 2
-        idx = 2 * np.random.randint(n_mod) if n_mod > 1 else 0
+        idx = 2 * int((rng or np.random.default_rng()).integers(n_mod)) if n_mod > 1 else 0
         return hyper[idx], hyper[idx + 1]
     if isinstance(hyper, (int, float, np.integer, np.floating)):
         return np.full(size, centre - hyper), np.full(size, centre + hyper)
@@ -36,7 +36,7 @@ def _bounds(hyper, size, centre, default_range):
 def _uniform(rng, hyper, batch, size, centre=0., default_range=10.):
     if hyper is False:
         return None
-    lo, hi = _bounds(hyper, size, centre, default_range)
+    lo, hi = _bounds(hyper, size, centre, default_range, rng)
     return rng.uniform(np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64), size=(batch, size)).astype(f32)
 
 

@@ -504,9 +504,15 @@ class _Writer:
 
 
 def write_h5(path, root):
+    """atomic: a crash mid-write must not leave a truncated checkpoint under the final name"""
+    import os
     data = _Writer().finish(root)
-    with open(path, 'wb') as fh:
+    tmp = '%s.tmp%d' % (path, os.getpid())
+    with open(tmp, 'wb') as fh:
         fh.write(data)
+        fh.flush()
+        os.fsync(fh.fileno())
+    os.replace(tmp, path)
 
 
 # =====================================================================================================================

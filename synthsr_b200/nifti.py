@@ -148,3 +148,39 @@ def load_mgz(path):
     h = Header(dim=np.array([len(shape)] + shape + [1] * (7 - len(shape)), np.int16), delta=delta,
                pixdim=np.array([1, *delta, 1, 1, 1, 1], np.float32))
     return data, aff, h
+
+
+def save_mgz(path, volume, aff, header=None, dtype=None):
+    """FreeSurfer .mgh / .mgz writer (what nib.save does for those extensions, ext/lab2im/utils.py:158-160): 284-byte
+    big-endian header (version 1, dims, type, goodRASFlag, voxel sizes, direction cosines, centre RAS), voxels in Fortran
+    order, gzip for .mgz.  MGH stores uint8 / int16 / int32 / float32 only; other dtypes are converted to float32."""
+    volume = np.asarray(volume)
+    if dtype is not None:
+        volume = volume.astype(dtype)
+    if volume.ndim > 4:
+        raise ValueError('MGH files hold at most 4 dimensions')
+    codes = {'u1': 0, 'i2': 4, 'i4': 1, 'f4': 3}
+    if volume.dtype.str[1:] not in codes:
+        volume = volume.astype(np.int32 if (volume.dtype.kind in 'iub' and volume.dtype.itemsize <= 4) else np.float32)
+    typ = codes[volume.dtype.str[1:]]
+    aff = np.eye(4) if aff is None else np.asarray(aff, dtype=np.float64)
+    shape3 = list(volume.shape[:3]) + [1] * (3 - min(volume.ndim, 3))
+    nf = volume.shape[3] if volume.ndim == 4 else 1
+    delta = np.sqrt((aff[:3, :3] ** 2).sum(0))
+    delta[delta == 0] = 1.
+    mdc = aff[:3, :3] / delta
+    c = aff[:3, :3] @ (np.array(shape3, dtype=np.float64) / 2.) + aff[:3, 3]
+    buf = bytearray(284)
+    struct.pack_into('>7i', buf, 0, 1, shape3[0], shape3[1], shape3[2], nf, typ, 0)
+    struct.pack_into('>h', buf, 28, 1)
+    struct.pack_into('>3f', buf, 30, *[float(v) for v in delta])
+    struct.pack_into('>9f', buf, 42, *[float(v) for v in mdc.T.reshape(-1)])
+    struct.pack_into('>3f', buf, 78, *[float(v) for v in c])
+    payload = bytes(buf) + np.asfortranarray(volume).astype(volume.dtype.newbyteorder('>')).tobytes(order='F')
+    payload += struct.pack('>4f', 0., 0., 0., 0.)            # footer: TR, flip angle, TE, TI
+    if path.endswith('.mgz') or path.endswith('.gz'):
+        with gzip.open(path, 'wb') as f:
+            f.write(payload)
+    else:
+        with open(path, 'wb') as f:
+            f.write(payload)

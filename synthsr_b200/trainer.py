@@ -6,6 +6,9 @@ mini-batch shard; the ONLY exchange per step is one all-reduce of the flat gradi
 ride at its tail so all replicas keep identical state).  BN batch statistics stay rank-local (equals the reference's
 batchsize-per-GPU semantics per shard; documented deviation from a single big batch).
 """
+import contextlib
+import os
+
 import numpy as np
 import torch
 
@@ -14,11 +17,31 @@ from .generator import SynthGenerator
 from .unet import UNet3D
 
 
+# when a list, every engine appends a timing CUDA event after each trained step (bench.py measures the throughput of the
+# drop-in SynthSR.training.training() call from them, without touching its code path)
+STEP_EVENTS = None
+_NVTX = os.environ.get('SSR_NVTX') == '1'
+
+
+@contextlib.contextmanager
+def _range(name):
+    """NVTX range (SSR_NVTX=1): generator / forward+backward / exchange / optimiser show up as named spans in nsys."""
+    if _NVTX:
+        torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+
+
 class TrainingEngine:
     def __init__(self, plan, batchsize=1, nb_features=24, nb_levels=5, conv_size=3, feat_mult=2, nb_conv_per_level=2,
                  nb_labels=None, lr=1e-4, lr_decay=0., metric='l1', work_with_residual_channel=None,
-                 loss_cropping=None, conv_impl='tc3', seed=0, device='cuda', rank=0, world_size=1, seg=None):
+                 loss_cropping=None, conv_impl=None, seed=0, device='cuda', rank=0, world_size=1, seg=None):
         """seg: optional synthsr_b200.seg_loss.SegRegulariser (segmentation-regularised loss, metrics_model.py:136-215)."""
+        # conv_impl None: SSR_CONV_IMPL or 'tc3' (compensated forward, the parity-gated mode); see synthsr_b200/unet.py
+        conv_impl = conv_impl or os.environ.get('SSR_CONV_IMPL', 'tc3')
         self.plan, self.B = plan, int(batchsize)
         self.device = torch.device(device)
         self.rank, self.world = int(rank), int(world_size)
@@ -38,9 +61,9 @@ class TrainingEngine:
         self.rng = np.random.default_rng(seed * 1000003 + 7919 * self.rank)   # per-rank augmentation stream
         self.seed = seed * 65537 + self.rank
         self.steps = 0
+        self.exchange = None
         if self.world > 1:
-            n_mv = sum(t.numel() for t in self.net.moving.values())
-            self.flat = torch.zeros(self.net.n_params + n_mv + 1, dtype=torch.float32, device=self.device)
+            self.exchange = GradientExchange(self.net, self.world)
         # pipelined mode (train_step_pipelined): a second generator instance and a generator stream
         self._gens, self._gen_stream, self._pending, self._pipe_i = None, None, None, 0
 
@@ -49,16 +72,27 @@ class TrainingEngine:
         tensor, float64; averaged over ranks when world_size > 1)."""
         if draws is None:
             draws = sample_draws(self.rng, self.plan, self.B)
-        image, target = self.gen.run(labels, means, stds, draws, real_image=real_image, seed=self.seed)
+        with _range('generator'):
+            image, target = self.gen.run(labels, means, stds, draws, real_image=real_image, seed=self.seed)
         if self.seg is not None:
             self.net.seg_labels = self.gen.labels                         # `segmentation_target` of this batch
-        loss = self.net.loss_and_grad(image, target, self.metric, self.residual, self.loss_cropping)
+        return self._train_on(image, target)
+
+    def _train_on(self, image, target):
+        with _range('unet fwd+bwd'):
+            loss = self.net.loss_and_grad(image, target, self.metric, self.residual, self.loss_cropping)
         scale = 1.
         if self.world > 1:
-            loss = self._allreduce(loss)
+            with _range('gradient exchange'):
+                loss = self._allreduce(loss)
             scale = 1. / self.world
-        self.net.adam_step(self.lr, self.lr_decay, grad_scale=scale)
+        with _range('adam'):
+            self.net.adam_step(self.lr, self.lr_decay, grad_scale=scale)
         self.steps += 1
+        if STEP_EVENTS is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            STEP_EVENTS.append(ev)
         return loss
 
     # -----------------------------------------------------------------------------------------------------------------
@@ -68,12 +102,13 @@ class TrainingEngine:
         optimiser): the batch passed in is generated on a second stream while the network trains on the batch of the
         PREVIOUS call, so the latency-bound generator kernels fill the SMs the backward chain leaves idle.  Batches are
         trained exactly once, in order.  Returns the loss of the previous call's batch (None on the first call);
-        `flush()` trains the last pending batch.  labels may be a pinned host tensor (copied on the generator stream)."""
+        `flush()` trains the last pending batch.  labels / real_image may be pinned host tensors (copied on the generator
+        stream into per-slot device buffers, so nothing the caller allocated is read across streams)."""
         if self._gens is None:
             self._gens = [self.gen, SynthGenerator(self.plan, self.B, self.device)]
             self._gen_stream = torch.cuda.Stream(device=self.device)
             self._gen_done = [torch.cuda.Event(), torch.cuda.Event()]
-            self._lab_dev = [None, None]
+            self._lab_dev, self._real_dev = [None, None], [None, None]
         i = self._pipe_i
         k = i % 2
         cur = torch.cuda.current_stream()
@@ -88,8 +123,14 @@ class TrainingEngine:
                     self._lab_dev[k] = torch.empty(labels.shape, dtype=torch.int32, device=self.device)
                 self._lab_dev[k].copy_(labels, non_blocking=True)
                 labels = self._lab_dev[k]
+            if real_image is not None and not real_image.is_cuda:
+                if self._real_dev[k] is None:
+                    self._real_dev[k] = torch.empty(real_image.shape, dtype=torch.float32, device=self.device)
+                self._real_dev[k].copy_(real_image, non_blocking=True)
+                real_image = self._real_dev[k]
             self._gens[k].philox_step = max(g.philox_step for g in self._gens)    # one noise-counter sequence for both
-            image, target = self._gens[k].run(labels, means, stds, draws, real_image=real_image, seed=self.seed)
+            with _range('generator'):
+                image, target = self._gens[k].run(labels, means, stds, draws, real_image=real_image, seed=self.seed)
             self._gen_done[k].record()
         loss = self._train_pending()
         self._pending = (image, target, k)
@@ -104,39 +145,79 @@ class TrainingEngine:
         torch.cuda.current_stream().wait_event(self._gen_done[k])
         if self.seg is not None:
             self.net.seg_labels = self._gens[k].labels
-        loss = self.net.loss_and_grad(image, target, self.metric, self.residual, self.loss_cropping)
-        scale = 1.
-        if self.world > 1:
-            loss = self._allreduce(loss)
-            scale = 1. / self.world
-        self.net.adam_step(self.lr, self.lr_decay, grad_scale=scale)
-        self.steps += 1
-        return loss
+        return self._train_on(image, target)
 
     def flush(self):
         """train on the batch generated by the last train_step_pipelined call (end of an epoch / of training)."""
         return self._train_pending()
 
     def _allreduce(self, loss):
-        return allreduce_step(self.net.grads, list(self.net.moving.values()), loss, self.flat, self.world)
+        return self.exchange.finish(loss)
 
 
-def allreduce_step(grads, moving, loss, flat, world):
-    """THE one collective of the data-parallel step: a single SUM all-reduce of [gradients | BN moving stats | loss].
-    Gradients are left SUMMED in `grads` (Adam applies the 1/world scale), moving statistics and the loss are
-    averaged in place.  Device agnostic (NCCL on GPUs, gloo in the CPU tests).  Returns the mean loss (float64)."""
+def exchange_inplace(comm, n_grads, split, world, stage):
+    """The data-parallel exchange of one step on the buffer comm = [gradients (n_grads) | BN moving stats | loss], IN PLACE
+    (no staging copy), as one logical SUM all-reduce issued in two pieces so that the first overlaps the backward pass:
+      stage 0: comm[:split]  -- the gradient prefix that is complete once the deep levels are differentiated (the buffer
+               is laid out in backward-completion order, UNet3D.__init__; the deep layers hold > 90 % of the bytes);
+      stage 1: comm[split:]  -- the shallow levels' gradients, the moving statistics and the loss; the tail
+               [n_grads:] is then averaged (gradients stay SUMMED: Adam applies the 1/world scale).
+    Device agnostic (NCCL on the GPUs, gloo in the CPU tests); stream placement is the caller's business."""
     import torch.distributed as dist
-    n = grads.numel()
-    flat[:n].copy_(grads)
-    o = n
-    for t in moving:
-        flat[o:o + t.numel()].copy_(t.reshape(-1))
-        o += t.numel()
-    flat[o] = loss.reshape(-1)[0].to(flat.dtype)
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    grads.copy_(flat[:n])
-    o = n
-    for t in moving:
-        t.copy_((flat[o:o + t.numel()] / world).reshape(t.shape))
-        o += t.numel()
-    return (flat[o:o + 1] / world).double()
+    if stage == 0:
+        if split > 0:
+            dist.all_reduce(comm[:split], op=dist.ReduceOp.SUM)
+        return
+    dist.all_reduce(comm[split:], op=dist.ReduceOp.SUM)
+    comm[n_grads:].mul_(1. / world)
+
+
+class GradientExchange:
+    """Issues exchange_inplace for a UNet3D: stage 0 from the network's grads_ready_hook (on a communication stream, behind
+    events of the backward-chain stream and the weight-gradient side stream), stage 1 after the backward pass."""
+
+    def __init__(self, net, world, split_level=None):
+        self.net, self.world = net, int(world)
+        L = net.L
+        # the prefix is sent once encoder level `split_level` is done: levels below it (>= 85 % of the backward time of
+        # the 160^3 net is still to come at level 2) hide the transfer of the deep layers' gradients
+        if split_level is None and os.environ.get('SSR_EXCHANGE_SPLIT_LEVEL'):      # 0: one all-reduce after the backward pass
+            split_level = int(os.environ['SSR_EXCHANGE_SPLIT_LEVEL'])
+        self.split_level = min(2, L - 1) if split_level is None else int(split_level)
+        self.split = net.level_end.get(self.split_level, 0) if self.split_level > 0 else 0
+        self.cuda = net.comm.is_cuda
+        self.stream = torch.cuda.Stream(device=net.device) if self.cuda else None
+        self._sent = False
+        if self.split > 0:
+            net.grads_ready_hook = self._on_level
+
+    def _on_level(self, level):
+        if level != self.split_level:
+            return
+        net = self.net
+        if self.cuda:
+            cur = torch.cuda.current_stream()
+            self.stream.wait_stream(cur)                       # bias / BatchNorm gradients + data-gradient chain
+            if net._side is not None:
+                self.stream.wait_stream(net._side)             # weight gradients enqueued so far
+            with torch.cuda.stream(self.stream):
+                exchange_inplace(net.comm, net.n_params, self.split, self.world, 0)
+        else:
+            exchange_inplace(net.comm, net.n_params, self.split, self.world, 0)
+        self._sent = True
+
+    def finish(self, loss):
+        """after loss_and_grad: exchanges the rest and returns the mean loss (1-element float64 tensor)."""
+        net = self.net
+        split = self.split if self._sent else 0
+        self._sent = False
+        net.comm[-1:].copy_(loss.reshape(-1)[:1])
+        if self.cuda:
+            cur = torch.cuda.current_stream()
+            self.stream.wait_stream(cur)
+            with torch.cuda.stream(self.stream):
+                exchange_inplace(net.comm, net.n_params, split, self.world, 1)
+            cur.wait_stream(self.stream)
+        else:
+            exchange_inplace(net.comm, net.n_params, split, self.world, 1)
+        return net.comm[-1:].double()

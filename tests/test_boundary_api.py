@@ -173,3 +173,25 @@ def test_label_map_cache_is_bounded(tmp_path, monkeypatch):
     for _ in range(4):
         lab, means, stds = next(g)
         assert lab.shape == (1, 4, 4, 4, 1) and means.shape == (1, 3, 1)
+
+
+def test_save_volume_round_trips_per_extension(tmp_path):
+    """utils.save_volume picks the file format from the extension like nib.save does (ext/lab2im/utils.py:122-160): a
+    '.mgz' destination (what predict() writes for .mgz inputs) must be a real MGH file that load_volume reads back."""
+    import gzip
+    import struct
+    from ext.lab2im import utils
+    rng = np.random.default_rng(0)
+    aff = np.array([[-1.2, 0, 0, 10], [0, 0, 1.5, -3], [0, -0.9, 0, 7], [0, 0, 0, 1.]])
+    for ext in ('.mgz', '.nii.gz', '.nii', '.npz'):
+        for dt in (None, 'int32', 'uint8'):
+            v = rng.uniform(0, 100, size=(5, 6, 7)).astype(np.float32)
+            p = str(tmp_path / ('a_SynthSR' + ext))
+            utils.save_volume(v, aff, None, p, dtype=dt)
+            w, a2, _ = utils.load_volume(p, im_only=False)
+            exp = np.round(v) if (dt and ext != '.npz') else v       # .npz is written as handed over (utils.py:131-133)
+            assert w.shape == (5, 6, 7) and np.allclose(w, exp, atol=1e-4), (ext, dt)
+            if ext != '.npz':
+                assert np.allclose(a2, aff, atol=1e-5), (ext, a2)
+    raw = gzip.open(str(tmp_path / 'a_SynthSR.mgz')).read()
+    assert struct.unpack('>4i', raw[:16]) == (1, 5, 6, 7)          # MGH magic (version 1) + dims, not the NIfTI 348

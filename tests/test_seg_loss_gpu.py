@@ -97,7 +97,7 @@ def test_seg_input_and_head_extra_grad():
         np.testing.assert_allclose(db.item() + 1., e.double().sum().item(), rtol=1e-4, atol=1e-3)
 
 
-@pytest.mark.parametrize('impl,tol', [('ref', 2e-4), ('tc', 5e-3)])
+@pytest.mark.parametrize('impl,tol', [('ref', 2e-4), ('tc3', 1e-3)])
 def test_step_with_segmentation_regulariser_matches_oracle(impl, tol):
     """one training step of a small network (3 levels, 8 features) with a small frozen segmentation network attached: loss
     and every gradient of the trained network against float64 autograd through the oracle's seg_regularised_loss."""
@@ -144,5 +144,5 @@ def test_step_with_segmentation_regulariser_matches_oracle(impl, tol):
     gtot = np.sqrt(sum(float((g ** 2).sum()) for g in grads))
     for k, g in zip(names, grads):
         err = np.linalg.norm(net.g[k].cpu().numpy().astype(np.float64) - g.numpy()) / max(np.linalg.norm(g.numpy()), 1e-2 * gtot)
-        assert err < (5e-4 if impl == 'ref' else 3e-2), (k, err)
+        assert err < (5e-4 if impl == 'ref' else 1e-2), (k, err)          # north_star bars in the default mode
     assert class_tables(gen_labels, equiv)[1].tolist() == [0, 2, 3]
