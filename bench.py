@@ -461,9 +461,11 @@ def main():
             os.environ.setdefault('SSR_SEED', '0')
             T.STEP_EVENTS = []
             barrier()
-            training(lab_dir, os.path.join(tmp, 'models'), paths['prior_means'], paths['prior_stds'],
-                     paths['generation_labels'], path_generation_classes=paths['generation_classes'], batchsize=1,
-                     epochs=2, steps_per_epoch=args.steps, **kw)
+            import contextlib
+            with contextlib.redirect_stdout(sys.stderr):         # training() prints its per-epoch line; stdout is ONE JSON line
+                training(lab_dir, os.path.join(tmp, 'models'), paths['prior_means'], paths['prior_stds'],
+                         paths['generation_labels'], path_generation_classes=paths['generation_classes'], batchsize=1,
+                         epochs=2, steps_per_epoch=args.steps, **kw)
             barrier()
             evs, T.STEP_EVENTS = T.STEP_EVENTS, None
             assert len(evs) == 2 * args.steps, len(evs)

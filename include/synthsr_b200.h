@@ -167,6 +167,14 @@ int ssr_conv3d_fwd_tc_comp(const float* x, const float* xlo, int C, const float*
                            void* stream);
 int ssr_conv3d_fwd_tc_up_comp(const float* low, const float* lowlo, int Cup, const float* wp8c, float* y, int B, int d0,
                               int d1, int d2, int Cout, int level, void* stream);
+/* Hybrid scheme (level 4, the default of conv_impl='tc3'): the two correction terms run as ONE bf16 MMA chain -- x2 =
+ * [bf16(x_lo) | bf16(x_hi)] (ssr_tf32_split_bf16: a 2C-channel bf16 tensor, same bytes as x) against [w_hi ; w_lo] in bf16
+ * (pack mode 7 = TF32 hi chunks followed by the bf16 chunks; pack mode 8 = the bf16 chunk in the k2n layout).  The
+ * corrections are ~2^-11 of the result, so bf16's 8-bit operands leave ~2^-20 relative -- and a bf16 MMA covers twice the
+ * K of a TF32 one: 2 chains per convolution instead of 3.  x2 / lowlo of the *_comp entry points is then that bf16 tensor. */
+int ssr_tf32_split_bf16(const float* x, void* x2, long long nvox, int C, void* stream);
+int ssr_conv3d_fwd_tc_k2n_bf16(const void* x2, int C2, const float* wp, const float* bias, float* y, double* sums, int B,
+                               int d0, int d1, int d2, int Cout, int act, void* stream);
 /* last channel part of a k2n convolution + the BatchNorm sums of the finished output (sums zeroed here) */
 int ssr_conv3d_fwd_tc_k2n_part_stats(const float* x, int Ctot, int c0, int C, const float* wp, const float* bias, float* y,
                                      double* sums, int B, int d0, int d1, int d2, int Cout, int act, int accumulate,

@@ -177,6 +177,33 @@ __device__ __forceinline__ void umma_chain_k(uint32_t d_tmem, uint32_t alo, uint
   if (NK == 3) asm volatile(SSR_MMA_HEAD SSR_MMA1 SSR_MMAN(2) SSR_MMAN(2) "}" SSR_MMA_ARGS);
   if (NK == 4) asm volatile(SSR_MMA_HEAD SSR_MMA1 SSR_MMAN(2) SSR_MMAN(2) SSR_MMAN(2) "}" SSR_MMA_ARGS);
 }
+// same chains with kind::f16 (bf16 operands, 16 elements = 32 B per K-step): the correction term of the compensated forward
+#define SSR_MMA1_H "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+#define SSR_MMAN_H(STEP) "add.s64 da, da, " #STEP ";\n\tadd.s64 db, db, " #STEP ";\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, q;\n\t"
+template <int NK>
+__device__ __forceinline__ void umma_chain_k16(uint32_t d_tmem, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+  if (NK == 1) asm volatile(SSR_MMA_HEAD SSR_MMA1_H "}" SSR_MMA_ARGS);
+  if (NK == 2) asm volatile(SSR_MMA_HEAD SSR_MMA1_H SSR_MMAN_H(2) "}" SSR_MMA_ARGS);
+  if (NK == 3) asm volatile(SSR_MMA_HEAD SSR_MMA1_H SSR_MMAN_H(2) SSR_MMAN_H(2) "}" SSR_MMA_ARGS);
+  if (NK == 4) asm volatile(SSR_MMA_HEAD SSR_MMA1_H SSR_MMAN_H(2) SSR_MMAN_H(2) SSR_MMAN_H(2) "}" SSR_MMA_ARGS);
+}
+// nks K-steps of a K-major chunk, TF32 (f16 == false) or bf16 operands
+__device__ __forceinline__ void umma_chain_any(bool f16, int nks, uint32_t d_tmem, uint32_t alo, uint32_t blo, uint32_t idesc,
+                                               uint32_t accumulate) {
+  if (!f16) {
+    if (nks == 4) umma_chain_k<4>(d_tmem, alo, blo, DESC_HI_K_SW128, idesc, accumulate);
+    else if (nks == 3) umma_chain_k<3>(d_tmem, alo, blo, DESC_HI_K_SW128, idesc, accumulate);
+    else if (nks == 2) umma_chain_k<2>(d_tmem, alo, blo, DESC_HI_K_SW128, idesc, accumulate);
+    else umma_chain_k<1>(d_tmem, alo, blo, DESC_HI_K_SW128, idesc, accumulate);
+  } else {
+    if (nks == 4) umma_chain_k16<4>(d_tmem, alo, blo, DESC_HI_K_SW128, idesc, accumulate);
+    else if (nks == 3) umma_chain_k16<3>(d_tmem, alo, blo, DESC_HI_K_SW128, idesc, accumulate);
+    else if (nks == 2) umma_chain_k16<2>(d_tmem, alo, blo, DESC_HI_K_SW128, idesc, accumulate);
+    else umma_chain_k16<1>(d_tmem, alo, blo, DESC_HI_K_SW128, idesc, accumulate);
+  }
+}
+
 // 16 K-steps of the weight-gradient tile (MN-major operands: +1024 B per K-step)
 __device__ __forceinline__ void umma_chain_mn16(uint32_t d_tmem, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc,
                                                 uint32_t accumulate) {
@@ -206,6 +233,11 @@ __device__ __forceinline__ void umma_chain_mn_ab(int n, uint32_t d_tmem, uint32_
 // instruction descriptor: D=F32, A=B=TF32, both K-major, M=128, N
 __device__ __forceinline__ uint32_t make_idesc_tf32(int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// same with A = B = BF16 (kind::f16; cute::UMMA::InstrDescriptor: a_format / b_format 1 = BF16)
+__device__ __forceinline__ uint32_t make_idesc_bf16(int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -239,6 +271,7 @@ struct TcGeom {
   short chunk_c0[MAX_CHUNKS];             // first channel of the chunk inside its source
   unsigned char chunk_w[MAX_CHUNKS];      // chunk of the PACKED WEIGHTS this chunk multiplies (== index, except in the
                                           // compensated forward, where [x | x_lo | x] meet [w_hi | w_hi | w_lo])
+  unsigned char chunk_f16[MAX_CHUNKS];    // 1: the chunk holds 64 bf16 channels (kind::f16 MMAs) instead of 32 fp32 / TF32
 };
 
 __device__ __forceinline__ bool slab_needed(const TcGeom& G, int z0, int k0g, int zin) {
@@ -419,7 +452,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
     // arrivals per stage) and issues only the d0 tap kk = zin - zo that lands in its own accumulator.
     {
       const int zo = warp - 1;
-      const uint32_t idesc = make_idesc_tf32(G.NT);
+      const uint32_t idesc32 = make_idesc_tf32(G.NT), idesc16 = make_idesc_bf16(G.NT);
       const int KG = G.KG, SA = G.SA, nchunks = G.nchunks, D0 = G.D0;
       const uint32_t NT = (uint32_t)G.NT;
       const uint32_t btile16 = (NT * 128u) >> 4;
@@ -437,6 +470,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
         uint32_t acc = 0u;                         // first MMA of the tile into this accumulator overwrites
         for (int ch = 0; ch < nchunks; ++ch) {
           const int nks = G.chunk_ks[ch];
+          const bool f16 = G.chunk_f16[ch] != 0;
+          const uint32_t idesc = f16 ? idesc16 : idesc32;
           for (int k2 = 0; k2 < 3; ++k2) {
             for (int k0g = 0; k0g < 3; k0g += KG) {
               const int zin_lo = (z0 + k0g == 0) ? 1 : 0;
@@ -455,10 +490,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                     uint32_t blo = blo0 + (uint32_t)(kk * 3) * btile16;
 #pragma unroll
                     for (int k1 = 0; k1 < 3; ++k1) {
-                      if (nks == 4) umma_chain_k<4>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
-                      else if (nks == 3) umma_chain_k<3>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
-                      else if (nks == 2) umma_chain_k<2>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
-                      else umma_chain_k<1>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+                      umma_chain_any(f16, nks, dcol, alo, blo, idesc, acc);
                       acc = 1u;
                       alo += k1_step;
                       blo += btile16;
@@ -643,6 +675,7 @@ struct UpGeom {
   short chunk_c0[UP_MAX_CHUNKS];
   unsigned char chunk_src[UP_MAX_CHUNKS];   // MODE 1: tensor map of the chunk (0: x, 1: its TF32 residual x_lo)
   unsigned char chunk_w[UP_MAX_CHUNKS];     // chunk of the packed weights (see TcGeom::chunk_w)
+  unsigned char chunk_f16[UP_MAX_CHUNKS];   // 1: 64 bf16 channels, kind::f16 MMAs (see TcGeom::chunk_f16)
 };
 struct UpMaps { CUtensorMap x[8]; };
 
@@ -744,7 +777,7 @@ conv3d_tc_up_kernel(const __grid_constant__ UpMaps maps, const __grid_constant__
   } else if (warp <= G.TZ) {
     // ================================ MMA issuers: warp w owns accumulator (output plane) zo = w - 1 ================
     const int zo = warp - 1;
-    const uint32_t idesc = make_idesc_tf32(G.NT);
+    const uint32_t idesc32 = make_idesc_tf32(G.NT), idesc16 = make_idesc_bf16(G.NT);
     const int KG = G.KG, SA = G.SA, nchunks = G.nchunks, D0 = G.D0;
     const uint32_t NT = (uint32_t)G.NT;
     const uint32_t btile16 = (NT * 128u) >> 4;
@@ -764,6 +797,8 @@ conv3d_tc_up_kernel(const __grid_constant__ UpMaps maps, const __grid_constant__
         (void)k2lo;
         for (int ch = 0; ch < nchunks; ++ch) {
           const int nks = G.chunk_ks[ch];
+          const bool f16 = G.chunk_f16[ch] != 0;
+          const uint32_t idesc = f16 ? idesc16 : idesc32;
           for (int k2i = 0; k2i < 2; ++k2i) {
             for (int k0g = 0; k0g < 3; k0g += KG) {
               const int kk_lo = max(k0lo - k0g, 0), kk_hi = min(k0lo + 1 - k0g, KG - 1);
@@ -782,10 +817,7 @@ conv3d_tc_up_kernel(const __grid_constant__ UpMaps maps, const __grid_constant__
                     uint32_t blo = blo0 + (uint32_t)(kk * 3 + k1lo) * btile16;
 #pragma unroll
                     for (int k1i = 0; k1i < 2; ++k1i) {
-                      if (nks == 4) umma_chain_k<4>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
-                      else if (nks == 3) umma_chain_k<3>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
-                      else if (nks == 2) umma_chain_k<2>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
-                      else umma_chain_k<1>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+                      umma_chain_any(f16, nks, dcol, alo, blo, idesc, acc);
                       acc = 1u;
                       alo += (uint32_t)(TM2 * 128 >> 4);
                       blo += btile16;
@@ -959,6 +991,7 @@ constexpr int KF_SA = 5, KF_NACC = 4, KF_N = 96;
 
 struct KfGeom {
   int B, D0, D1, D2, Cout, act, nks;
+  int f16;         // the source holds bf16 channels (64 per chunk) and the weights bf16 pairs: kind::f16 MMAs
   int c0;          // first channel of this part in the source tensor (TMA coordinate)
   int accumulate;  // epilogue adds the partial result already in y (earlier channel parts of a concatenated input)
   int final;       // last part: bias + activation are applied
@@ -1041,7 +1074,8 @@ conv3d_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   } else if (warp <= KF_NACC) {
     // ================================ MMA issuers: warp w owns accumulator ring slot w - 1 ================================
     const int w = warp - 1;
-    const uint32_t idesc = make_idesc_tf32(KF_N);
+    const bool f16 = G.f16 != 0;
+    const uint32_t idesc = f16 ? make_idesc_bf16(KF_N) : make_idesc_tf32(KF_N);
     const uint32_t a_base = desc_lo(smem_u32(sA), 16), b_base = desc_lo(smem_u32(sB), 16);
     const uint32_t dcol = tmem_base + (uint32_t)(w * KF_N);
     const int nks = G.nks;
@@ -1067,10 +1101,7 @@ conv3d_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             uint32_t blo = b_base + (uint32_t)(k0 * 3) * (KF_BTILE_BYTES >> 4);
 #pragma unroll
             for (int k1 = 0; k1 < 3; ++k1) {
-              if (nks == 4) umma_chain_k<4>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
-              else if (nks == 3) umma_chain_k<3>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
-              else if (nks == 2) umma_chain_k<2>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
-              else umma_chain_k<1>(dcol, alo, blo, DESC_HI_K_SW128, idesc, acc);
+              umma_chain_any(f16, nks, dcol, alo, blo, idesc, acc);
               acc = 1u;
               alo += (uint32_t)(KF_TM2 * 128 >> 4);
               blo += (uint32_t)(KF_BTILE_BYTES >> 4);
@@ -2236,6 +2267,35 @@ __global__ void tf32_residual_kernel(const float* __restrict__ x, float* __restr
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) lo[(n4 << 2) + threadIdx.x] = tf32_lo(x[(n4 << 2) + threadIdx.x]);
 }
 
+__device__ __forceinline__ uint32_t bf16_bits(float v) {       // round to nearest even bf16 (operands are finite)
+  const uint32_t u = __float_as_uint(v);
+  return (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;
+}
+// x2[v][0:C] = bf16(x - rne_tf32(x)),  x2[v][C:2C] = bf16(rne_tf32(x)): the two operands of the bf16 correction term of
+// the compensated forward, written as ONE 2C-channel bf16 tensor (same bytes per voxel as C fp32 channels)
+__global__ void tf32_split_bf16_kernel(const float* __restrict__ x, uint16_t* __restrict__ x2, long long nvox, int C) {
+  const int c4 = C >> 2;                                      // C % 4 == 0 (host-checked)
+  const long long total = nvox * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i / c4;
+    const int c = (int)(i - v * c4) << 2;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x + v * C + c));
+    const float in[4] = {a.x, a.y, a.z, a.w};
+    uint32_t lo[4], hi[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      uint32_t u = __float_as_uint(in[e]);
+      u = (u + 0xFFFu + ((u >> 13) & 1u)) & ~0x1FFFu;
+      const float h = __uint_as_float(u);
+      hi[e] = bf16_bits(h);
+      lo[e] = bf16_bits(in[e] - h);
+    }
+    uint16_t* row = x2 + v * 2 * C;
+    *reinterpret_cast<uint2*>(row + c) = make_uint2(lo[0] | (lo[1] << 16), lo[2] | (lo[3] << 16));
+    *reinterpret_cast<uint2*>(row + C + c) = make_uint2(hi[0] | (hi[1] << 16), hi[2] | (hi[3] << 16));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // weight packing:  wp[chunk][k2][k0][k1][n][32]   (K-major rows of 32 input channels, zero padded)
 //   mode 0 (forward):       value = w[k0][k1][k2][cin(chunk, s)][n]
@@ -2243,7 +2303,7 @@ __global__ void tf32_residual_kernel(const float* __restrict__ x, float* __restr
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pack_weights_body(const float* __restrict__ w, float* __restrict__ wp, int C1, int C2,
                                                   int Cout, int mode, int Npad, int nchunks, int nch1, int round_rn) {
-  const bool k2n_layout = mode >= 2 && mode != 5;
+  const bool k2n_layout = mode >= 2 && mode != 5 && mode != 7;
   const long long total = k2n_layout ? 9LL * 96 * 32 : (long long)nchunks * 27 * Npad * 32;
   const int Cin = mode == 5 ? C1 : C1 + C2;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -2256,6 +2316,47 @@ __device__ __forceinline__ void pack_weights_body(const float* __restrict__ w, f
     const int ch = (int)(r / 3);
     float val = 0.f;
     bool lo_part = mode == 6;      // compensated forward: this entry holds w - rna_tf32(w) (then rounded itself)
+    if (mode == 7 && ch >= nch1) {
+      // bf16 chunks of the hybrid compensated forward: K' = [w_hi (cn) ; w_lo (cn)] in 64-channel bf16 chunks, two bf16 per
+      // float slot; they meet x2 = [x_lo | x_hi] (tf32_split_bf16_kernel).  C2 = (coff << 12) | cn, C1 = total Cin
+      const int coff = C2 >> 12, cn = C2 & 4095;
+      uint32_t pair = 0;
+      for (int e = 0; e < 2; ++e) {
+        const int kk = (ch - nch1) * 64 + 2 * s + e;
+        float v = 0.f;
+        if (kk < 2 * cn && n < Cout) {
+          const float wv = w[((long long)((k0 * 3 + k1) * 3 + k2) * C1 + coff + (kk < cn ? kk : kk - cn)) * Cout + n];
+          uint32_t u;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(wv));
+          v = kk < cn ? __uint_as_float(u) : wv - __uint_as_float(u);
+        }
+        pair |= bf16_bits(v) << (16 * e);
+      }
+      wp[t] = __uint_as_float(pair);
+      continue;
+    }
+    if (mode == 8) {
+      // k2n layout (one 64-channel bf16 chunk, 2 C1 <= 64): row ((k0, k1), k2 * 32 + n), K' = [w_hi (C1) ; w_lo (C1)]
+      long long r2 = t >> 5;
+      const int nn = (int)(r2 % 96); r2 /= 96;
+      const int q1 = (int)(r2 % 3);
+      const int q0 = (int)(r2 / 3);
+      const int q2 = nn >> 5, no = nn & 31;
+      uint32_t pair = 0;
+      for (int e = 0; e < 2; ++e) {
+        const int kk = 2 * s + e;
+        float v = 0.f;
+        if (kk < 2 * C1 && no < Cout) {
+          const float wv = w[((long long)((q0 * 3 + q1) * 3 + q2) * C1 + (kk < C1 ? kk : kk - C1)) * Cout + no];
+          uint32_t u;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(wv));
+          v = kk < C1 ? __uint_as_float(u) : wv - __uint_as_float(u);
+        }
+        pair |= bf16_bits(v) << (16 * e);
+      }
+      wp[t] = __uint_as_float(pair);
+      continue;
+    }
     if (k2n_layout) {
       // d2-taps-in-N layout of conv3d_tc_k2n_kernel: t = ((k0 * 3 + k1) * 96 + (k2 * 32 + n)) * 32 + s, one 32-channel chunk
       long long r2 = t >> 5;
@@ -2270,9 +2371,9 @@ __device__ __forceinline__ void pack_weights_body(const float* __restrict__ w, f
       if (mode == 2 || mode == 6) { if (s < C1 && no < Cout) val = w[((long long)((q0 * 3 + q1) * 3 + q2) * Cin + s) * Cout + no]; }
       else { if (s < Cout && no < Cin) val = w[((long long)(((2 - q0) * 3 + (2 - q1)) * 3 + (2 - q2)) * Cin + no) * Cout + s]; }
     } else
-    if (mode == 5) {
+    if (mode == 5 || mode == 7) {
       // hi / lo split of the input channels [coff, coff + cn) of a (27, C1, Cout) kernel: chunks [0, nch1) hold rna(w),
-      // chunks [nch1, 2 nch1) hold rna(w - rna(w)); C2 = (coff << 12) | cn
+      // chunks [nch1, 2 nch1) hold rna(w - rna(w)); C2 = (coff << 12) | cn   (mode 7: only the hi chunks get here)
       const int coff = C2 >> 12, cn = C2 & 4095;
       lo_part = ch >= nch1;
       const int cl = (lo_part ? ch - nch1 : ch) * 32 + s;
@@ -2310,6 +2411,7 @@ __global__ void pack_weights_batch_kernel(const long long* __restrict__ jobs, in
   const int C1 = (int)j[2], C2 = (int)j[3], Cout = (int)j[4], mode = (int)j[5];
   int Npad, nch, nch1;
   if (mode == 5) { Npad = (Cout + 15) / 16 * 16; nch1 = ((C2 & 4095) + 31) / 32; nch = 2 * nch1; }
+  else if (mode == 7) { Npad = (Cout + 15) / 16 * 16; nch1 = ((C2 & 4095) + 31) / 32; nch = nch1 + (2 * (C2 & 4095) + 63) / 64; }
   else if (mode >= 2) { Npad = 96; nch = 1; nch1 = 1; }
   else if (mode == 0) { Npad = (Cout + 15) / 16 * 16; nch1 = (C1 + 31) / 32; nch = nch1 + (C2 + 31) / 32; }
   else { Npad = (C1 + C2 + 15) / 16 * 16; nch = (Cout + 31) / 32; nch1 = nch; }
@@ -2362,6 +2464,23 @@ int make_map_act(CUtensorMap* m, const float* ptr, int C, int B, int D0, int D1,
   return SSR_OK;
 }
 
+// bf16 activation tensor [B, D0, D1, D2, C2] (C2 = 2 C: [x_lo | x_hi], tf32_split_bf16_kernel): boxes of 64 channels = 128 B
+int make_map_act16(CUtensorMap* m, const void* ptr, int C2, int B, int D0, int D1, int D2, int box_d1 = TM1 + 2,
+                   int box_d2 = TM2) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { ssr_set_error("cuTensorMapEncodeTiled not available"); return SSR_ERR_CUDA; }
+  cuuint64_t dims[5] = {(cuuint64_t)C2, (cuuint64_t)D2, (cuuint64_t)D1, (cuuint64_t)D0, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)C2 * 2, (cuuint64_t)D2 * C2 * 2, (cuuint64_t)D1 * D2 * C2 * 2,
+                           (cuuint64_t)D0 * D1 * D2 * C2 * 2};
+  cuuint32_t box[5] = {64, (cuuint32_t)box_d2, (cuuint32_t)box_d1, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { ssr_set_error("cuTensorMapEncodeTiled(bf16 activation C=%d %dx%dx%d) failed: %d", C2, D0, D1, D2, (int)r); return SSR_ERR_CUDA; }
+  return SSR_OK;
+}
+
 int make_map_w(CUtensorMap* m, const float* ptr, long long rows, int NT) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { ssr_set_error("cuTensorMapEncodeTiled not available"); return SSR_ERR_CUDA; }
@@ -2411,6 +2530,7 @@ int ssr_conv3d_pack_weights_batch(const long long* jobs, int njobs, void* stream
 }
 long long ssr_conv3d_packed_size(int Cin1, int Cin2, int Cout, int mode) {
   if (mode == 5) return 2LL * (((Cin2 & 4095) + 31) / 32) * 27 * round_up(Cout, 16) * 32;
+  if (mode == 7) return (long long)(((Cin2 & 4095) + 31) / 32 + (2 * (Cin2 & 4095) + 63) / 64) * 27 * round_up(Cout, 16) * 32;
   if (mode >= 2) return 9LL * 96 * 32;
   if (mode == 0) {
     const int nch = (Cin1 + 31) / 32 + (Cin2 + 31) / 32;
@@ -2421,18 +2541,19 @@ long long ssr_conv3d_packed_size(int Cin1, int Cin2, int Cout, int mode) {
 }
 
 int ssr_conv3d_pack_weights(const float* w, float* wp, int Cin1, int Cin2, int Cout, int mode, void* stream) {
-  SSR_CHECK_ARG(w && wp && Cin1 > 0 && Cin2 >= 0 && Cout > 0 && mode >= 0 && mode <= 6, "pack args");
-  SSR_CHECK_ARG(mode < 2 || mode == 4 || mode == 5 || (Cin2 == 0 && Cin1 <= 32 && Cout <= 32), "k2n packing needs Cin <= 32, Cout <= 32");
-  SSR_CHECK_ARG(mode != 5 || ((Cin2 & 4095) > 0 && (Cin2 >> 12) + (Cin2 & 4095) <= Cin1),
+  SSR_CHECK_ARG(w && wp && Cin1 > 0 && Cin2 >= 0 && Cout > 0 && mode >= 0 && mode <= 8, "pack args");
+  SSR_CHECK_ARG(mode < 2 || mode == 4 || mode == 5 || mode == 7 || (Cin2 == 0 && Cin1 <= 32 && Cout <= 32), "k2n packing needs Cin <= 32, Cout <= 32");
+  SSR_CHECK_ARG((mode != 5 && mode != 7) || ((Cin2 & 4095) > 0 && (Cin2 >> 12) + (Cin2 & 4095) <= Cin1),
                 "hi/lo packing: Cin1 = total input channels, Cin2 = (first channel << 12) | channels");
   SSR_CHECK_ARG(mode != 4 || ((Cin2 & 255) <= 32 && (Cin2 >> 8) + (Cin2 & 255) <= Cin1 && Cout <= 32),
                 "part packing: Cin1 = total input channels, Cin2 = (first channel << 8) | channels (<= 32)");
   int Npad, nch, nch1;
   if (mode == 5) { Npad = round_up(Cout, 16); nch1 = ((Cin2 & 4095) + 31) / 32; nch = 2 * nch1; }
+  else if (mode == 7) { Npad = round_up(Cout, 16); nch1 = ((Cin2 & 4095) + 31) / 32; nch = nch1 + (2 * (Cin2 & 4095) + 63) / 64; }
   else if (mode >= 2) { Npad = 96; nch = 1; nch1 = 1; }
   else if (mode == 0) { Npad = round_up(Cout, 16); nch1 = (Cin1 + 31) / 32; nch = nch1 + (Cin2 + 31) / 32; }
   else { Npad = round_up(Cin1 + Cin2, 16); nch = (Cout + 31) / 32; nch1 = nch; }
-  const long long total = (mode >= 2 && mode != 5) ? 9LL * 96 * 32 : (long long)nch * 27 * Npad * 32;
+  const long long total = (mode >= 2 && mode != 5 && mode != 7) ? 9LL * 96 * 32 : (long long)nch * 27 * Npad * 32;
   long long g = (total + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
   pack_weights_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(w, wp, Cin1, Cin2, Cout, mode, Npad, nch, nch1,
@@ -2449,7 +2570,10 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
                               const float* elu_h = nullptr, float* dbias = nullptr, double* sums = nullptr, int comp = 0) {
   // comp (compensated forward, "3xTF32"): x2 = x1 - rne_tf32(x1) (ssr_tf32_residual), wp = hi/lo packing (mode 5);
   // K = [x1 | x2 | x1] against [w_hi | w_hi | w_lo] (comp == 3), or [x1 | x2] against [w_hi | w_hi] (comp == 2)
-  SSR_CHECK_ARG(comp == 0 || ((comp == 2 || comp == 3) && x2 && C2 == C1), "compensated forward: x2 = residual of x1");
+  // comp == 4 (hybrid, 2 MMA chains instead of 3): x2 = [x_lo | x_hi] as 2 C1 bf16 channels (ssr_tf32_split_bf16), wp = pack mode
+  // 7; K = [x (TF32) | x2 (bf16)] against [w_hi (TF32) | w_hi ; w_lo (bf16)]: the corrections x_lo w_hi + x_hi w_lo are
+  // ~2^-11 of the result, so bf16's 8 bits on their operands leave ~2^-20 -- at twice the K per MMA of TF32
+  SSR_CHECK_ARG(comp == 0 || ((comp == 2 || comp == 3 || comp == 4) && x2 && C2 == C1), "compensated forward: x2 = residual of x1");
   SSR_CHECK_ARG(x1 && wp && y && B > 0 && D0 > 0 && D1 > 0 && D2 > 0 && Cout > 0, "pointers/shape");
   SSR_CHECK_ARG(C1 > 0 && C1 % 4 == 0 && C2 >= 0 && C2 % 4 == 0 && (C2 == 0 || x2), "channel counts must be multiples of 4");
   SSR_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0, "channel counts must be multiples of 8 (TF32 K-step)");
@@ -2467,6 +2591,7 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
     for (int c = 0; c < C1; c += 32) ks_total += ((C1 - c < 32 ? C1 - c : 32) + 7) / 8;
     for (int c = 0; c < C2; c += 32) ks_total += ((C2 - c < 32 ? C2 - c : 32) + 7) / 8;
     if (comp == 3) ks_total = ks_total / 2 * 3;
+    if (comp == 4) ks_total = ks_total / 2 + (2 * C1 + 15) / 16;
     int n1t = (D1 + TM1 - 1) / TM1, n2t = (D2 + TM2 - 1) / TM2;
     // plane-linearised tiling for the small deep levels: windows of 128 rows of the padded plane instead of 16 x 8 tiles
     const int pitch = D2 + 2;
@@ -2509,7 +2634,20 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
   while (pc < cols) pc <<= 1;
   G.tmem_cols = pc;
   int nch = 0, nwch = 0;                       // chunks of K, chunks of the packed weights
-  if (comp) {
+  if (comp == 4) {
+    const int nchc = (C1 + 31) / 32, nch2 = (2 * C1 + 63) / 64;
+    for (int c = 0; c < C1; c += 32) {
+      G.chunk_src[nch] = 0; G.chunk_c0[nch] = (short)c; G.chunk_ks[nch] = (unsigned char)(((C1 - c < 32 ? C1 - c : 32) + 7) / 8);
+      G.chunk_w[nch] = (unsigned char)nch; ++nch;
+    }
+    for (int j = 0; j < nch2; ++j) {
+      SSR_CHECK_ARG(nch < MAX_CHUNKS, "too many input channels");
+      const int left = 2 * C1 - 64 * j;
+      G.chunk_src[nch] = 1; G.chunk_c0[nch] = (short)(64 * j); G.chunk_ks[nch] = (unsigned char)(((left < 64 ? left : 64) + 15) / 16);
+      G.chunk_w[nch] = (unsigned char)(nchc + j); G.chunk_f16[nch] = 1; ++nch;
+    }
+    nwch = nchc + nch2;
+  } else if (comp) {
     const int nchc = (C1 + 31) / 32;
     for (int term = 0; term < comp; ++term)
       for (int c = 0; c < C1; c += 32) {
@@ -2551,7 +2689,8 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
   const int bx1 = pl ? D1 + 2 : TM1 + 2, bx2 = pl ? G.pl_pitch : TM2;        // TMA box: whole padded plane / 18 x 8 slab
   int rc = make_map_act(&m1, x1, C1, B, D0, D1, D2, bx1, CU_TENSOR_MAP_SWIZZLE_128B, bx2);
   if (rc) return rc;
-  if (C2 > 0) { rc = make_map_act(&m2, x2, C2, B, D0, D1, D2, bx1, CU_TENSOR_MAP_SWIZZLE_128B, bx2); if (rc) return rc; } else m2 = m1;
+  if (comp == 4) { rc = make_map_act16(&m2, x2, 2 * C1, B, D0, D1, D2, bx1, bx2); if (rc) return rc; }
+  else if (C2 > 0) { rc = make_map_act(&m2, x2, C2, B, D0, D1, D2, bx1, CU_TENSOR_MAP_SWIZZLE_128B, bx2); if (rc) return rc; } else m2 = m1;
   rc = make_map_w(&mw, wp, (long long)nwch * 27 * G.Npad, G.NT);
   if (rc) return rc;
 
@@ -2625,7 +2764,7 @@ int ssr_conv3d_dgrad_tc_elu(const float* dy, int C, const float* wp, const float
 int ssr_conv3d_fwd_tc_comp(const float* x, const float* xlo, int C, const float* wp, const float* bias, float* y,
                            double* sums, int B, int D0, int D1, int D2, int Cout, int act, int accumulate, int level,
                            void* stream) {
-  SSR_CHECK_ARG(level == 2 || level == 3, "compensation level must be 2 or 3");
+  SSR_CHECK_ARG(level == 2 || level == 3 || level == 4, "compensation level must be 2, 3 or 4 (hybrid TF32 + bf16)");
   SSR_CHECK_ARG(!(sums && accumulate), "BatchNorm sums do not combine with accumulate");
   if (sums) SSR_CHECK_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)Cout * sizeof(double), (cudaStream_t)stream));
   return conv3d_fwd_tc_impl(x, C, xlo, C, wp, bias, y, B, D0, D1, D2, Cout, act, accumulate, stream, sums ? 2 : 0, nullptr,
@@ -2675,8 +2814,8 @@ static int conv3d_tc_up_impl(int mode, const float* x, int C, const float* wp8, 
                              int Cout, void* stream, const float* xlo = nullptr, int comp = 0) {
   // comp (mode 1 only): compensated forward, see ssr_conv3d_fwd_tc_comp; wp8 = 8 parity classes x hi/lo packing (mode 5)
   SSR_CHECK_ARG(x && wp8 && y && B > 0 && D0 > 0 && D1 > 0 && D2 > 0 && Cout > 0, "pointers/shape");
-  SSR_CHECK_ARG(comp == 0 || (mode == 1 && xlo && (comp == 2 || comp == 3)), "compensated parity forward args");
-  SSR_CHECK_ARG(C > 0 && C % 8 == 0 && (C + 31) / 32 * (comp ? comp : 1) <= UP_MAX_CHUNKS,
+  SSR_CHECK_ARG(comp == 0 || (mode == 1 && xlo && (comp == 2 || comp == 3 || comp == 4)), "compensated parity forward args");
+  SSR_CHECK_ARG(C > 0 && C % 8 == 0 && (C + 31) / 32 * (comp == 4 ? 2 : comp ? comp : 1) <= UP_MAX_CHUNKS,
                 "channel count must be a multiple of 8 (<= 768; <= 256 compensated)");
   SSR_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp8 & 127) == 0 && ((uintptr_t)xlo & 15) == 0, "alignment");
   UpGeom G;
@@ -2685,13 +2824,23 @@ static int conv3d_tc_up_impl(int mode, const float* x, int C, const float* wp8, 
   G.Npad = round_up(Cout, 16);
   int ks_total = 0, nch = 0;
   const int nchc = (C + 31) / 32;
-  for (int term = 0; term < (comp ? comp : 1); ++term)
+  for (int term = 0; term < (comp == 4 ? 1 : comp ? comp : 1); ++term)
     for (int c = 0; c < C; c += 32) {
       G.chunk_c0[nch] = (short)c; G.chunk_ks[nch] = (unsigned char)(((C - c < 32 ? C - c : 32) + 7) / 8);
       G.chunk_src[nch] = (unsigned char)(term == 1); G.chunk_w[nch] = (unsigned char)((term == 2 ? nchc : 0) + c / 32);
       ks_total += G.chunk_ks[nch]; ++nch;
     }
-  const int nwch = comp ? 2 * nchc : nchc;          // chunks of the packed weights per parity class
+  int nwch = comp ? 2 * nchc : nchc;                // chunks of the packed weights per parity class
+  if (comp == 4) {                                  // hybrid: bf16 chunks of x2 = [x_lo | x_hi] against [w_hi ; w_lo]
+    const int nch2 = (2 * C + 63) / 64;
+    for (int j = 0; j < nch2; ++j) {
+      const int left = 2 * C - 64 * j;
+      G.chunk_c0[nch] = (short)(64 * j); G.chunk_ks[nch] = (unsigned char)(((left < 64 ? left : 64) + 15) / 16);
+      G.chunk_src[nch] = 1; G.chunk_w[nch] = (unsigned char)(nchc + j); G.chunk_f16[nch] = 1;
+      ks_total += G.chunk_ks[nch]; ++nch;
+    }
+    nwch = nchc + nch2;
+  }
   G.nchunks = nch;
   int rc = up_tile_shape(G.Npad, B, D0, D1, D2, ks_total, mode == 2 ? 8 : 1, mode == 1 ? 8 : 1, &G.NT, &G.TZ);
   if (rc) { ssr_set_error("no tile shape"); return rc; }
@@ -2714,7 +2863,8 @@ static int conv3d_tc_up_impl(int mode, const float* x, int C, const float* wp8, 
     rc = make_map_act(&maps.x[0], x, C, B, D0, D1, D2);
     if (rc) return rc;
     for (int i = 1; i < 8; ++i) maps.x[i] = maps.x[0];
-    if (comp) { rc = make_map_act(&maps.x[1], xlo, C, B, D0, D1, D2); if (rc) return rc; }
+    if (comp == 4) { rc = make_map_act16(&maps.x[1], xlo, 2 * C, B, D0, D1, D2); if (rc) return rc; }
+    else if (comp) { rc = make_map_act(&maps.x[1], xlo, C, B, D0, D1, D2); if (rc) return rc; }
   } else {
     const long long F0 = 2LL * D0, F1 = 2LL * D1, F2 = 2LL * D2;
     for (int par = 0; par < 8; ++par) {
@@ -2841,15 +2991,18 @@ int ssr_conv3d_up_weights(const float* w, int Cskip, int Cup, int Cout, float* w
 // epi: 0 plain, 1 multiply by elu'(elu_h) and accumulate dbias, 2 accumulate BatchNorm sums (sum | sum of squares)
 static int conv3d_fwd_tc_k2n_impl(const float* x, int Ctot, int c0, int C, const float* wp, const float* bias, float* y,
                                   int B, int D0, int D1, int D2, int Cout, int act, int accumulate, int final, void* stream,
-                                  int epi = 0, const float* elu_h = nullptr, float* dbias = nullptr, double* sums = nullptr) {
+                                  int epi = 0, const float* elu_h = nullptr, float* dbias = nullptr, double* sums = nullptr,
+                                  int f16 = 0) {
+  // f16: x is the bf16 tensor [x_lo | x_hi] of Ctot = C = 2 * (layer channels) <= 64 channels, wp from pack mode 8
   SSR_CHECK_ARG(x && wp && y && B > 0 && D0 > 0 && D1 > 0 && D2 > 0, "pointers/shape");
-  SSR_CHECK_ARG(C > 0 && C <= 32 && C % 8 == 0 && Cout > 0 && Cout <= 32 && c0 >= 0 && c0 + C <= Ctot && Ctot % 4 == 0,
+  SSR_CHECK_ARG(C > 0 && C <= (f16 ? 64 : 32) && C % (f16 ? 16 : 8) == 0 && Cout > 0 && Cout <= 32 && c0 >= 0 && c0 + C <= Ctot &&
+                Ctot % 4 == 0 && (!f16 || (c0 == 0 && C == Ctot)),
                 "k2n forward needs <= 32 input channels per part (multiple of 8), Cout <= 32");
   SSR_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 127) == 0, "alignment");
   KfGeom G;
   memset(&G, 0, sizeof(G));
-  G.B = B; G.D0 = D0; G.D1 = D1; G.D2 = D2; G.Cout = Cout; G.act = act; G.nks = C / 8;
-  G.c0 = c0; G.accumulate = accumulate; G.final = final;
+  G.B = B; G.D0 = D0; G.D1 = D1; G.D2 = D2; G.Cout = Cout; G.act = act; G.nks = f16 ? C / 16 : C / 8;
+  G.c0 = c0; G.accumulate = accumulate; G.final = final; G.f16 = f16;
   G.n1tiles = (D1 + KF_TM1 - 1) / KF_TM1; G.n2tiles = (D2 + KF_OUT2 - 1) / KF_OUT2;
   static int num_sms = 0;
   if (!num_sms) {
@@ -2870,7 +3023,8 @@ static int conv3d_fwd_tc_k2n_impl(const float* x, int Ctot, int c0, int C, const
   }
   G.nzr = best_nzr;
   CUtensorMap mx, mw;
-  int rc = make_map_act(&mx, x, Ctot, B, D0, D1, D2, KF_TM1 + 2, CU_TENSOR_MAP_SWIZZLE_128B, KF_TM2);
+  int rc = f16 ? make_map_act16(&mx, x, Ctot, B, D0, D1, D2, KF_TM1 + 2, KF_TM2)
+               : make_map_act(&mx, x, Ctot, B, D0, D1, D2, KF_TM1 + 2, CU_TENSOR_MAP_SWIZZLE_128B, KF_TM2);
   if (rc) return rc;
   rc = make_map_w(&mw, wp, 9 * KF_N, KF_N);
   if (rc) return rc;
@@ -2931,6 +3085,28 @@ int ssr_conv3d_fwd_tc_k2n_part_stats(const float* x, int Ctot, int c0, int C, co
   SSR_CHECK_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)Cout * sizeof(double), (cudaStream_t)stream));
   return conv3d_fwd_tc_k2n_impl(x, Ctot, c0, C, wp, bias, y, B, D0, D1, D2, Cout, act, accumulate, 1, stream, 2, nullptr,
                                 nullptr, sums);
+}
+
+// second (and last) pass of a compensated k2n convolution in the hybrid scheme: x2 = [x_lo | x_hi] (2 C bf16 channels,
+// ssr_tf32_split_bf16), wp = pack mode 8; adds x_lo w_hi + x_hi w_lo to the partial result x_hi w_hi already in y, then
+// bias + activation (+ the BatchNorm sums of the finished output when sums != NULL)
+int ssr_conv3d_fwd_tc_k2n_bf16(const void* x2, int C2, const float* wp, const float* bias, float* y, double* sums, int B,
+                               int D0, int D1, int D2, int Cout, int act, void* stream) {
+  if (sums) SSR_CHECK_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)Cout * sizeof(double), (cudaStream_t)stream));
+  return conv3d_fwd_tc_k2n_impl(reinterpret_cast<const float*>(x2), C2, 0, C2, wp, bias, y, B, D0, D1, D2, Cout, act, 1, 1,
+                                stream, sums ? 2 : 0, nullptr, nullptr, sums, 1);
+}
+
+// x2[v][0:C] = bf16(x - rne_tf32(x)), x2[v][C:2C] = bf16(rne_tf32(x))  (x: [nvox, C] fp32; x2: [nvox, 2C] bf16)
+int ssr_tf32_split_bf16(const float* x, void* x2, long long nvox, int C, void* stream) {
+  SSR_CHECK_ARG(x && x2 && nvox > 0 && C > 0 && C % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)x2 & 15) == 0,
+                "tf32_split_bf16 args (C must be a multiple of 4)");
+  long long g = (nvox * (C / 4) + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  tf32_split_bf16_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<uint16_t*>(x2), nvox, C);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
 }
 
 // lo[i] = x[i] - rne_tf32(x[i]): the part of an fp32 activation the TMA's TFLOAT32 load rounds away (round to nearest

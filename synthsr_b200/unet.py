@@ -89,6 +89,9 @@ class UNet3D:
         if os.environ.get('SSR_COMP') and conv_impl == 'tc':
             self.comp = [(re.compile(r.rsplit(':', 1)[0]), int(r.rsplit(':', 1)[1])) for r in os.environ['SSR_COMP'].split(',')]
         self._lo = None                 # scratch for the TF32 residual x_lo of the convolution being run (stream ordered)
+        # 'hybrid' (default): x_hi w_hi in TF32 + the two correction terms as one bf16 MMA chain (2 chains per convolution);
+        # 'tf32x3': all three terms in TF32 (3 chains) -- the first implementation, kept as a cross-check
+        self.comp_scheme = os.environ.get('SSR_COMP_SCHEME', 'hybrid')
         self.conv_impl = conv_impl
         self.wgrad_tc = conv_impl == 'tc'
         self.prof = None          # list of (kind, flops, start_event, end_event) when profiling is enabled
@@ -309,9 +312,41 @@ class UNet3D:
         lib.ssr_tf32_residual(x, self._lo, n, stream_ptr())
         return self._lo
 
+    def _split16(self, x, nvox, c):
+        """x2 = [bf16(x_lo) | bf16(x_hi)] (2c bf16 channels per voxel = the bytes of c floats) in the shared scratch"""
+        n = nvox * c
+        if self._lo is None or self._lo.numel() < n:
+            self._lo = torch.empty(max(n, self.nvox[0] * self.feats[0]), dtype=torch.float32, device=self.device)
+        lib.ssr_tf32_split_bf16(x, self._lo, nvox, c, stream_ptr())
+        return self._lo
+
+    def _conv_fwd_hybrid(self, name, x1, c1, x2, c2, y, l, cout, act, stats_sums):
+        """compensated forward, hybrid scheme: TF32 main term + one bf16 chain for x_lo w_hi + x_hi w_lo"""
+        st, B, d = stream_ptr(), self.B, self.ldims[l]
+        nv = self.nvox[l]
+        bias = self.p[name + '/bias']
+        if c2 == 0 and self._k2n_ok(c1, cout):
+            whi = self._packed_w(name, 2, c1, 0, cout)
+            w16 = self._packed_w(name, 8, c1, 0, cout)
+            x16 = self._split16(x1, nv, c1)
+            lib.ssr_conv3d_fwd_tc_k2n_part(x1, c1, 0, c1, whi, bias, y, B, *d, cout, act, 0, 0, st)
+            lib.ssr_conv3d_fwd_tc_k2n_bf16(x16, 2 * c1, w16, bias, y, stats_sums, B, *d, cout, act, st)
+            return
+        if c2 == 0:
+            wp = self._packed_w(name, 7, c1, c1, cout)
+            lib.ssr_conv3d_fwd_tc_comp(x1, self._split16(x1, nv, c1), c1, wp, bias, y, stats_sums, B, *d, cout, act, 0, 4, st)
+            return
+        assert stats_sums is None
+        wp1 = self._packed_w(name, 7, c1 + c2, c1, cout, tag='c0')
+        lib.ssr_conv3d_fwd_tc_comp(x1, self._split16(x1, nv, c1), c1, wp1, None, y, None, B, *d, cout, 0, 0, 4, st)
+        wp2 = self._packed_w(name, 7, c1 + c2, (c1 << 12) | c2, cout, tag='c1')
+        lib.ssr_conv3d_fwd_tc_comp(x2, self._split16(x2, nv, c2), c2, wp2, bias, y, None, B, *d, cout, act, 1, 4, st)
+
     def _conv_fwd_comp(self, level, name, x1, c1, x2, c2, y, l, cout, act, stats_sums):
         """compensated forward of one layer (see the module docstring); the concatenated input of a decoder level that
         does not take the parity path is the sum of its two parts."""
+        if level == 3 and self.comp_scheme == 'hybrid':
+            return self._conv_fwd_hybrid(name, x1, c1, x2, c2, y, l, cout, act, stats_sums)
         st, B, d = stream_ptr(), self.B, self.ldims[l]
         nv = self.nvox[l]
         bias = self.p[name + '/bias']
@@ -385,6 +420,13 @@ class UNet3D:
         st, F, B = stream_ptr(), self.feats, self.B
         u = self._up_state(l)
         level = self._comp_level(name)
+        if level == 3 and self.comp_scheme == 'hybrid':
+            lib.ssr_conv3d_fwd_tc_up_comp(self.vlow[l], self._split16(self.vlow[l], self.nvox[l + 1], F[l + 1]), F[l + 1],
+                                          self._up_packs(l, 'fwd8h'), self.g0[l], B, *self.ldims[l + 1], F[l], 4, st)
+            wp = self._packed_w(name, 7, F[l], F[l], F[l], tag='skiph', src=u['wskip'])
+            lib.ssr_conv3d_fwd_tc_comp(self.h1[l], self._split16(self.h1[l], self.nvox[l], F[l]), F[l], wp,
+                                       self.p[name + '/bias'], self.g0[l], None, B, *self.ldims[l], F[l], act, 1, 4, st)
+            return
         if level:
             # compensated: parity kernel on [vlow | vlow_lo | vlow], then the skip part accumulates (+ bias + ELU)
             nlow, nsk = self.nvox[l + 1] * F[l + 1], self.nvox[l] * F[l]
@@ -580,7 +622,11 @@ class UNet3D:
         if which == 'fwd8c' and which not in u:      # hi / lo packing of the 8 effective kernels (compensated forward)
             u['nfc'] = lib.ssr_conv3d_packed_size(cu, cu, co, 5)
             u[which] = torch.empty(8 * u['nfc'], dtype=torch.float32, device=self.device)
-        n, mode, c2 = {'fwd8': (u['nf'], 0, 0), 'dgr8': (u['nd'], 1, 0), 'fwd8c': (u.get('nfc'), 5, cu)}[which]
+        if which == 'fwd8h' and which not in u:      # same for the hybrid scheme (TF32 hi chunks + bf16 chunks)
+            u['nfh'] = lib.ssr_conv3d_packed_size(cu, cu, co, 7)
+            u[which] = torch.empty(8 * u['nfh'], dtype=torch.float32, device=self.device)
+        n, mode, c2 = {'fwd8': (u['nf'], 0, 0), 'dgr8': (u['nd'], 1, 0), 'fwd8c': (u.get('nfc'), 5, cu),
+                       'fwd8h': (u.get('nfh'), 7, cu)}[which]
         for par in range(8):
             self._packed_w(name, mode, cu, c2, co, tag=('up', par), src=u['weff'][par * 27 * cu * co:(par + 1) * 27 * cu * co],
                            buf=u[which][par * n:(par + 1) * n])

@@ -14,13 +14,13 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3
 
 
-def _run_case(cfg, labels_shape, label_list, seed=0, batch=1, real=False):
+def _run_case(cfg, labels_shape, label_list, seed=0, batch=1, real=False, phantom=phantom_labels):
     from oracle import generator as OG
     from synthsr_b200.draws import sample_draws
     from synthsr_b200.generator import GeneratorPlan, SynthGenerator
 
     rng = np.random.default_rng(seed)
-    labs = np.stack([phantom_labels(labels_shape, label_list, seed=seed + b) for b in range(batch)])
+    labs = np.stack([phantom(labels_shape, label_list, seed=seed + b) for b in range(batch)])
     plan = GeneratorPlan(labels_shape, cfg.get('input_channels', True), cfg.get('output_channel', 0), label_list,
                          cfg.get('n_neutral_labels'), cfg.get('atlas_res', 1.), cfg.get('target_res'),
                          **{k: v for k, v in cfg.items() if k not in ('input_channels', 'output_channel',
@@ -63,6 +63,29 @@ def test_training_defaults_no_crop_batch2():
     cfg = dict(scaling_bounds=.15, rotation_bounds=15, shearing_bounds=.02, translation_bounds=5, nonlin_std=4.,
                nonlin_shape_factor=.03125, bias_field_std=.3, bias_shape_factor=.03125, output_div_by_n=32)
     _check(*_run_case(cfg, [64, 64, 32], GEN_LABELS, seed=2, batch=2))
+
+
+def test_benchmark_shape_160_training_defaults():
+    """BASELINE configs[1]/[2]: the 160^3 label map of bench.py through the generator with training()'s defaults
+    (SynthSR/training.py:57-73), against the oracle at full size: integrated SVF and labels bit exact, images <= 1e-3."""
+    import bench
+    cfg = {k: v for k, v in bench.TRAINING_DEFAULTS.items()}
+    for seed in (0, 1):
+        _check(*_run_case(cfg, [160, 160, 160], GEN_LABELS, seed=seed, phantom=lambda shape, labels, seed: bench.make_inputs(
+            shape, 1, seed=seed)[0][0]))
+
+
+def test_benchmark_shape_64_brain_generator_defaults():
+    """BASELINE configs[0]: single 64^3 label map with BrainGenerator's own defaults (SynthSR/brain_generator.py:30-61:
+    nonlin_std 3, factor .0625, shearing .012, bias factor .025, no reliability maps), every intermediate the oracle keeps."""
+    for seed in (0, 1, 2):
+        plan, image, target, keep, o_image, o_target, inter = _run_case(dict(aff=np.eye(4)), [64, 64, 64], GEN_LABELS, seed=seed)
+        _check(plan, image, target, keep, o_image, o_target, inter)
+        assert image.shape == (1, 64, 64, 64, 1) and plan.svf_small_shape == [4, 4, 4] and plan.svf_half_shape == [32, 32, 32]
+        for name in ('raw_0', 'blur_0'):
+            if name in inter:
+                scale = max(1., float(np.abs(inter[name]).max()))
+                assert np.abs(keep[name].cpu().numpy().reshape(inter[name].shape) - inter[name]).max() <= TOL * scale, name
 
 
 def test_flip_swaps_sided_labels():

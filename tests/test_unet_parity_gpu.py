@@ -192,6 +192,111 @@ def test_compensated_parity_forward_matches_float64(dl, cu, co):
     assert err < KERNEL_TOL, err
 
 
+def test_tf32_split_bf16_layout():
+    """x2 = [bf16(x - rne_tf32(x)) | bf16(rne_tf32(x))], 2C bf16 channels per voxel"""
+    from synthsr_b200._lib import lib, stream_ptr
+    rng = np.random.default_rng(0)
+    nv, c = 1000, 24
+    x = _t(rng.normal(size=(nv, c)) * np.exp(rng.normal(size=(nv, c)) * 2))
+    x2 = torch.zeros((nv, 2 * c), dtype=torch.bfloat16, device='cuda')
+    lib.ssr_tf32_split_bf16(x, x2, nv, c, stream_ptr())
+    torch.cuda.synchronize()
+    u = x.view(torch.int32)
+    hi = ((u + 0xFFF + ((u >> 13) & 1)) & ~0x1FFF).view(torch.float32)
+    assert torch.equal(x2[:, c:], hi.to(torch.bfloat16)) and torch.equal(x2[:, :c], (x - hi).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize('d,c,co', [([8, 16, 24], 48, 96), ([10, 10, 10], 192, 384), ([16, 16, 16], 24, 48),
+                                    ([20, 20, 20], 96, 192), ([12, 20, 8], 384, 384), ([16, 16, 16], 40, 24)])
+def test_hybrid_generic_forward_matches_float64(d, c, co):
+    """level 4 of ssr_conv3d_fwd_tc_comp: TF32 main term + ONE bf16 chain for both correction terms"""
+    from synthsr_b200._lib import lib, stream_ptr
+    rng = np.random.default_rng(1)
+    nv = int(np.prod(d))
+    x = _t(rng.normal(size=(nv, c)))
+    w = _t(rng.normal(size=(3, 3, 3, c, co)) / np.sqrt(27 * c))
+    b = _t(rng.normal(size=co))
+    st = stream_ptr()
+    x2 = torch.empty((nv, 2 * c), dtype=torch.bfloat16, device='cuda')
+    lib.ssr_tf32_split_bf16(x, x2, nv, c, st)
+    wp = torch.empty(lib.ssr_conv3d_packed_size(c, c, co, 7), dtype=torch.float32, device='cuda')
+    lib.ssr_conv3d_pack_weights(w, wp, c, c, co, 7, st)
+    y64 = _conv64(x, w, b, d)
+    for with_sums in (False, True):
+        y = torch.full((nv, co), float('nan'), dtype=torch.float32, device='cuda')
+        sums = torch.full((2 * co,), float('nan'), dtype=torch.float64, device='cuda') if with_sums else None
+        lib.ssr_conv3d_fwd_tc_comp(x, x2, c, wp, b, y, sums, 1, *d, co, 1, 0, 4, st)
+        torch.cuda.synchronize()
+        err = (y.double().cpu() - y64).abs().max().item() / y64.abs().max().item()
+        _log('hybrid generic %s %d->%d sums=%d: max/max %.2e' % (d, c, co, with_sums, err))
+        assert err < KERNEL_TOL, (d, c, co, err)
+        if with_sums:
+            s = sums.cpu().numpy()
+            assert np.allclose(s[:co], y.double().sum(0).cpu().numpy(), rtol=1e-6, atol=1e-6 * nv)
+
+
+@pytest.mark.parametrize('d', [[16, 16, 32], [12, 20, 18]])
+def test_hybrid_k2n_forward_matches_float64(d):
+    """24 -> 24 full-resolution layer: TF32 pass (x, w_hi) + bf16 pass ([x_lo | x_hi], [w_hi ; w_lo]) with the BatchNorm sums"""
+    from synthsr_b200._lib import lib, stream_ptr
+    rng = np.random.default_rng(3)
+    c = co = 24
+    nv = int(np.prod(d))
+    x = _t(rng.normal(size=(nv, c)))
+    w = _t(rng.normal(size=(3, 3, 3, c, co)) / np.sqrt(27 * c))
+    b = _t(rng.normal(size=co))
+    st = stream_ptr()
+    x2 = torch.empty((nv, 2 * c), dtype=torch.bfloat16, device='cuda')
+    lib.ssr_tf32_split_bf16(x, x2, nv, c, st)
+    whi = torch.empty(lib.ssr_conv3d_packed_size(c, 0, co, 2), dtype=torch.float32, device='cuda')
+    w16 = torch.empty(lib.ssr_conv3d_packed_size(c, 0, co, 8), dtype=torch.float32, device='cuda')
+    lib.ssr_conv3d_pack_weights(w, whi, c, 0, co, 2, st)
+    lib.ssr_conv3d_pack_weights(w, w16, c, 0, co, 8, st)
+    for with_sums in (False, True):
+        y = torch.full((nv, co), float('nan'), dtype=torch.float32, device='cuda')
+        sums = torch.full((2 * co,), float('nan'), dtype=torch.float64, device='cuda') if with_sums else None
+        lib.ssr_conv3d_fwd_tc_k2n_part(x, c, 0, c, whi, b, y, 1, *d, co, 1, 0, 0, st)
+        lib.ssr_conv3d_fwd_tc_k2n_bf16(x2, 2 * c, w16, b, y, sums, 1, *d, co, 1, st)
+        torch.cuda.synchronize()
+        y64 = _conv64(x, w, b, d)
+        err = (y.double().cpu() - y64).abs().max().item() / y64.abs().max().item()
+        _log('hybrid k2n %s sums=%d: max/max %.2e' % (d, with_sums, err))
+        assert err < KERNEL_TOL, err
+        if with_sums:
+            s = sums.cpu().numpy()
+            assert np.allclose(s[:co], y.double().sum(0).cpu().numpy(), rtol=1e-6, atol=1e-6 * nv)
+            assert np.allclose(s[co:], (y.double() ** 2).sum(0).cpu().numpy(), rtol=1e-6, atol=1e-6 * nv)
+
+
+@pytest.mark.parametrize('dl,cu,co', [([8, 8, 16], 96, 48), ([10, 12, 8], 192, 96), ([8, 8, 8], 48, 24)])
+def test_hybrid_parity_forward_matches_float64(dl, cu, co):
+    from synthsr_b200._lib import lib, stream_ptr
+    rng = np.random.default_rng(4)
+    cs = co
+    nl = int(np.prod(dl))
+    df = [2 * v for v in dl]
+    low = _t(rng.normal(size=(nl, cu)))
+    w = _t(rng.normal(size=(3, 3, 3, cs + cu, co)) / np.sqrt(27 * (cs + cu)))
+    st = stream_ptr()
+    wskip = torch.empty(27 * cs * co, dtype=torch.float32, device='cuda')
+    weff = torch.empty(8 * 27 * cu * co, dtype=torch.float32, device='cuda')
+    lib.ssr_conv3d_up_weights(w, cs, cu, co, wskip, weff, st)
+    n7 = lib.ssr_conv3d_packed_size(cu, cu, co, 7)
+    wp8 = torch.empty(8 * n7, dtype=torch.float32, device='cuda')
+    for par in range(8):
+        lib.ssr_conv3d_pack_weights(weff[par * 27 * cu * co:], wp8[par * n7:], cu, cu, co, 7, st)
+    low2 = torch.empty((nl, 2 * cu), dtype=torch.bfloat16, device='cuda')
+    lib.ssr_tf32_split_bf16(low, low2, nl, cu, st)
+    y = torch.full((8 * nl, co), float('nan'), dtype=torch.float32, device='cuda')
+    lib.ssr_conv3d_fwd_tc_up_comp(low, low2, cu, wp8, y, 1, *dl, co, 4, st)
+    torch.cuda.synchronize()
+    up = low.view(*dl, cu).repeat_interleave(2, 0).repeat_interleave(2, 1).repeat_interleave(2, 2).reshape(-1, cu)
+    y64 = _conv64(up, w[:, :, :, cs:, :], None, df, elu=False)
+    err = (y.double().cpu() - y64).abs().max().item() / y64.abs().max().item()
+    _log('hybrid parity %s %d->%d: max/max %.2e' % (dl, cu, co, err))
+    assert err < KERNEL_TOL, err
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def _step_errors(net, image, target, pred_ref, loss_ref, grads_ref, tag, **loss_kw):
     loss = net.loss_and_grad(torch.from_numpy(image).cuda(), torch.from_numpy(target).cuda(), **loss_kw)
