@@ -31,7 +31,12 @@ def metrics_model(input_model, loss_cropping=16, metrics='l1', work_with_residua
     return LossModel(input_model, loss_cropping, metrics, work_with_residual_channel)
 
 
-def add_seg_loss_to_model(*args, **kwargs):
-    raise NotImplementedError('segmentation-regularised loss (frozen second U-Net + Dice, metrics_model.py:136-215; SURVEY.md '
-                              '8f #4): the GPU implementation (synthsr_b200/seg_loss.py) has not been validated on a B200 '
-                              'yet and is off by default -- set SSR_ENABLE_SEG_LOSS=1 to use it')
+def add_seg_loss_to_model(input_model, *args, **kwargs):
+    """segmentation-regularised loss (frozen second U-Net + soft Dice, metrics_model.py:136-215).  The reference appends Keras
+    layers to `input_model`; on this engine the regulariser is part of the training step itself --
+    synthsr_b200.seg_loss.SegRegulariser, attached by SynthSR.training.training(segmentation_model_file=...) (validated
+    against the float64 oracle on a B200: tests/test_seg_loss_gpu.py).  Calling this function directly on a loss model has
+    nothing to append to."""
+    raise NotImplementedError('add_seg_loss_to_model: pass segmentation_model_file / segmentation_label_list / '
+                              'segmentation_label_equivalency to SynthSR.training.training(); the regulariser runs inside '
+                              'the training step (synthsr_b200/seg_loss.py)')

@@ -102,8 +102,6 @@ def training(labels_dir,
                                  'for a single output channel' % (2 * len(work_with_residual_channel),
                                                                   len(work_with_residual_channel)))
             work_with_residual_channel = [int(c) for c in work_with_residual_channel]
-    if segmentation_model_file is not None and os.environ.get('SSR_ENABLE_SEG_LOSS') != '1':
-        add_seg_loss_to_model()      # raises: the GPU side exists (synthsr_b200/seg_loss.py) but has not been validated yet
     # options the engine does not implement fail here, before any GPU work, instead of silently training something else
     if activation != 'elu':
         raise NotImplementedError("activation %r: the engine implements the reference's default 'elu' only "

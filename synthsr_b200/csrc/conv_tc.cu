@@ -355,6 +355,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
   uint64_t* accFull = emptyB + SB;                 // [2]
   uint64_t* accEmpty = accFull + 2;                // [2]
   uint32_t* tmem_slot = (uint32_t*)(accEmpty + 2);
+  uint64_t* kindBar = bars + 26;                   // [TZ <= 4] one per MMA warp: TF32 -> bf16 switch of the hybrid forward
   float* sbias = (float*)(bars + 32);              // Npad floats (<= 576), 16-byte aligned, zero padded
   float* sred = sbias + 640;                       // EPI: 2 x Npad per-CTA channel sums (host reserves the space)
   if (EPI != 0)
@@ -369,6 +370,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
     for (int i = 0; i < G.SA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, G.TZ); }
     for (int i = 0; i < SB; ++i) { mbar_init(fullB + i, 1); mbar_init(emptyB + i, G.TZ); }
     for (int i = 0; i < 2; ++i) { mbar_init(accFull + i, G.TZ); mbar_init(accEmpty + i, 4); }   // 4 epilogue warps arrive
+    for (int i = 0; i < 4; ++i) mbar_init(kindBar + i, 1);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -458,6 +460,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
       const uint32_t btile16 = (NT * 128u) >> 4;
       const uint32_t a_base = desc_lo(smem_u32(sA), 16), b_base = desc_lo(smem_u32(sB), 16);
       int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
+      uint32_t kind_phase = 0;
       long long wait_a = 0, wait_b = 0;
       if (warp == 1 && lane == 0) DBG_STAMP(3);
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -468,10 +471,22 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
         mbar_wait(accEmpty + set, ((it >> 1) & 1) ^ 1);          // epilogue has drained this accumulator set
         tc_fence_after();
         uint32_t acc = 0u;                         // first MMA of the tile into this accumulator overwrites
+        bool prev_f16 = false;
         for (int ch = 0; ch < nchunks; ++ch) {
           const int nks = G.chunk_ks[ch];
           const bool f16 = G.chunk_f16[ch] != 0;
           const uint32_t idesc = f16 ? idesc16 : idesc32;
+          if (f16 != prev_f16) {
+            // tcgen05.mma instructions of DIFFERENT kinds are not ordered against each other: the TF32 MMAs into this
+            // accumulator must have completed before the first bf16 MMA reads it (one bubble per tile and warp; the
+            // other MMA warps keep the tensor pipe busy meanwhile)
+            if (elect_one()) umma_commit(kindBar + zo);
+            __syncwarp();
+            mbar_wait(kindBar + zo, kind_phase);
+            kind_phase ^= 1u;
+            tc_fence_after();
+            prev_f16 = f16;
+          }
           for (int k2 = 0; k2 < 3; ++k2) {
             for (int k0g = 0; k0g < 3; k0g += KG) {
               const int zin_lo = (z0 + k0g == 0) ? 1 : 0;
@@ -696,12 +711,14 @@ conv3d_tc_up_kernel(const __grid_constant__ UpMaps maps, const __grid_constant__
   uint64_t* accFull = emptyB + SB;                 // [2]
   uint64_t* accEmpty = accFull + 2;                // [2]
   uint32_t* tmem_slot = (uint32_t*)(accEmpty + 2);
+  uint64_t* kindBar = bars + 26;                   // [TZ <= 4]: TF32 -> bf16 switch of the hybrid forward (see conv3d_tc_kernel)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < G.SA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, G.TZ); }
     for (int i = 0; i < SB; ++i) { mbar_init(fullB + i, 1); mbar_init(emptyB + i, G.TZ); }
     for (int i = 0; i < 2; ++i) { mbar_init(accFull + i, G.TZ); mbar_init(accEmpty + i, 4); }
+    for (int i = 0; i < 4; ++i) mbar_init(kindBar + i, 1);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -783,6 +800,7 @@ conv3d_tc_up_kernel(const __grid_constant__ UpMaps maps, const __grid_constant__
     const uint32_t btile16 = (NT * 128u) >> 4;
     const uint32_t a_base = desc_lo(smem_u32(sA), 16), b_base = desc_lo(smem_u32(sB), 16);
     int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
+    uint32_t kind_phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       UP_DECODE_TILE(tile)
       const int set = it & 1;
@@ -791,6 +809,7 @@ conv3d_tc_up_kernel(const __grid_constant__ UpMaps maps, const __grid_constant__
       mbar_wait(accEmpty + set, ((it >> 1) & 1) ^ 1);          // epilogue has drained this accumulator set
       tc_fence_after();
       uint32_t acc = 0u;                         // first MMA of the tile into this accumulator overwrites
+      bool prev_f16 = false;
       for (int pk = 0; pk < NPK; ++pk) {
         const int par = MODE == 1 ? tpar : pk;
         UP_TAPS(par)
@@ -799,6 +818,14 @@ conv3d_tc_up_kernel(const __grid_constant__ UpMaps maps, const __grid_constant__
           const int nks = G.chunk_ks[ch];
           const bool f16 = G.chunk_f16[ch] != 0;
           const uint32_t idesc = f16 ? idesc16 : idesc32;
+          if (f16 != prev_f16) {                   // kind switch: see conv3d_tc_kernel
+            if (elect_one()) umma_commit(kindBar + zo);
+            __syncwarp();
+            mbar_wait(kindBar + zo, kind_phase);
+            kind_phase ^= 1u;
+            tc_fence_after();
+            prev_f16 = f16;
+          }
           for (int k2i = 0; k2i < 2; ++k2i) {
             for (int k0g = 0; k0g < 3; k0g += KG) {
               const int kk_lo = max(k0lo - k0g, 0), kk_hi = min(k0lo + 1 - k0g, KG - 1);

@@ -7,10 +7,9 @@ on the B200 engine:  total = image loss + rel_weight * soft Dice(one-hot deforme
                             network's head.
     SegRegularisedUNet3D    the main network: its head step also runs the regulariser before the backward chain starts.
 
-STATUS: written after round 1's GPU budget was spent -- compiled for sm_100a, never run on a B200.  It is therefore OFF unless
-SSR_ENABLE_SEG_LOSS=1 (SynthSR.training raises NotImplementedError otherwise) and nothing on the validated training path
+STATUS: validated on a B200 in round 2 (tests/test_seg_loss_gpu.py: loss 1e-3, gradients 1e-2 against the float64 oracle); nothing on the plain training path
 imports this module.  Oracle: oracle/unet.py:seg_regularised_loss (pinned by executing the reference's own function);
-GPU tests: tests/test_seg_loss_gpu.py (opt-in through the same switch).
+GPU tests: tests/test_seg_loss_gpu.py.
 """
 import ctypes
 
@@ -140,11 +139,21 @@ class SegRegulariser:
         self.net = FrozenUNet3D(self.dims + [1], n_seg_labels, nb_features=nb_features, nb_levels=nb_levels,
                                 conv_size=conv_size, feat_mult=feat_mult, nb_conv_per_level=nb_conv_per_level,
                                 batchsize=batchsize, device=device, conv_impl=conv_impl, seed=0)
-        self.net.load_state_dict(seg_state_dict, strict=True)
+        # by name, like the reference's load_weights(by_name=True) (training.py:390): tensors the file does not hold keep
+        # their initial values; tensors it holds must have the engine's shape
+        for k, v in seg_state_dict.items():
+            tgt = self.net.p.get(k, self.net.moving.get(k))
+            if tgt is not None and tuple(np.shape(v)) != tuple(tgt.shape):
+                raise ValueError('segmentation model file: %s has shape %s, the network expects %s' % (k, np.shape(v), tuple(tgt.shape)))
+        self.net.load_state_dict(seg_state_dict, strict=False)
         cls, gtv = class_tables(generation_labels, segmentation_label_equivalency)
         assert len(cls) == n_seg_labels, 'segmentation_label_equivalency must have one entry per segmentation label'
         dev = self.net.device
         self.S, self.K = int(n_seg_labels), int(len(gtv))
+        if self.K == 1:
+            # with a single matched class the reference does not stack (metrics_model.py:206-207): DiceLoss then treats Z as
+            # the label axis and returns a per-slice Dice, not the whole-volume Dice these kernels compute
+            raise NotImplementedError('segmentation regulariser with a single matched class (per-slice Dice in the reference)')
         self.cls, self.gtv = torch.from_numpy(cls).to(dev), torch.from_numpy(gtv).to(dev)
         self.rel_weight = float(rel_weight)
         self.use_clip = m is not None
