@@ -2332,7 +2332,7 @@ __device__ __forceinline__ void pack_weights_body(const float* __restrict__ w, f
                                                   int Cout, int mode, int Npad, int nchunks, int nch1, int round_rn) {
   const bool k2n_layout = mode >= 2 && mode != 5 && mode != 7;
   const long long total = k2n_layout ? 9LL * 96 * 32 : (long long)nchunks * 27 * Npad * 32;
-  const int Cin = mode == 5 ? C1 : C1 + C2;
+  const int Cin = (mode == 5 || mode == 7) ? C1 : C1 + C2;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int s = (int)(t & 31);
     long long r = t >> 5;

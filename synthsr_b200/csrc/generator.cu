@@ -9,7 +9,9 @@
 // (ext/neuron/utils.py:67-122, 147-154, 267-286, 316-317), so no multiply-add contraction is allowed.
 // Volumes are [B][d0][d1][d2](,C) with d2 (the reference's last spatial axis) contiguous.
 #include "common.cuh"
+#include <cuda.h>
 #include <math_constants.h>
+#include <mutex>
 
 namespace {
 
@@ -607,6 +609,135 @@ blur3d_333_kernel(const float* __restrict__ src, float* __restrict__ dst, const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// TMA-staged, persistent version of blur3d_333_kernel (the two 3x3x3 blurs of the default training configuration).
+// The halo tile of a block of 8 x 8 x 32 outputs is ONE 4-D TMA box {36, 10, 10, 1} of the dense source volume
+// (cp.async.bulk.tensor, completion on an mbarrier): out-of-volume elements arrive as zeros = the 'SAME' zero padding of
+// tf.nn.conv3d (ext/lab2im/layers.py:748,758), no per-element bounds logic or index arithmetic on the load path.  CTAs are
+// persistent (grid = a multiple of the SM count) and double-buffered: thread 0 issues the box of tile t + 1 before the CTA
+// works on tile t, so the global -> shared latency that bounded the one-tile-per-CTA kernel (2 CTAs / SM, load -> sync ->
+// compute -> exit; profiles/r02_generator_ncu_baseline.txt: 305 - 523 GB/s) overlaps the normalise / gamma / stencil work.
+// Same arithmetic and accumulation order as blur3d_333_kernel (bit-identical results).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TB2 = 36;                                       // box width: BT2 + 2 rounded up to a multiple of 4 floats
+constexpr int TMA_TILE_FLOATS = (BT0 + 2) * (BT1 + 2) * TB2;  // 3600 floats = 14400 B per stage
+
+__device__ __forceinline__ uint32_t gen_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gen_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gen_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void gen_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gen_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gen_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = gen_smem_u32(bar);
+  uint32_t done = 0;
+  for (int spin = 0;; ++spin) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity), "r"(0x989680u) : "memory");
+    if (done) break;
+    if (spin > 2000) { printf("generator: mbarrier timeout (block %d)\n", blockIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void gen_tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                                int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(gen_smem_u32(dst)), "l"((uint64_t)map), "r"(gen_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(256, 3)
+blur3d_333_tma_kernel(const __grid_constant__ CUtensorMap map_src, float* __restrict__ dst, const float* __restrict__ kern,
+                      const uint32_t* __restrict__ minmax, const float* __restrict__ gamma_exp, BlurParams P) {
+  constexpr int T1 = BT1 + 2, T2 = TB2;
+  __shared__ __align__(128) float tiles[2][TMA_TILE_FLOATS];
+  __shared__ __align__(8) uint64_t full[2];
+  const int nb2 = (P.n2 + BT2 - 1) / BT2, nb1 = (P.n1 + BT1 - 1) / BT1, nb0 = (P.n0 + BT0 - 1) / BT0;
+  const long long ntiles = (long long)P.B * nb0 * nb1 * nb2;
+  const long long nvox = (long long)P.n0 * P.n1 * P.n2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    gen_mbar_init(full + 0, 1);
+    gen_mbar_init(full + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](long long tile, int stage) {              // thread 0 only
+    long long blk = tile;
+    const int bz = (int)(blk % nb2); blk /= nb2;
+    const int by = (int)(blk % nb1); blk /= nb1;
+    const int bx = (int)(blk % nb0);
+    const int b = (int)(blk / nb0);
+    gen_mbar_expect_tx(full + stage, TMA_TILE_FLOATS * 4);
+    gen_tma_load_4d(&map_src, full + stage, tiles[stage], bz * BT2 - 1, by * BT1 - 1, bx * BT0 - 1, b);
+  };
+  float kr[27];
+#pragma unroll
+  for (int t = 0; t < 27; ++t) kr[t] = kern[t];
+  if (threadIdx.x == 0 && (long long)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+  int it = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int stage = it & 1;
+    long long blk = tile;
+    const int bz = (int)(blk % nb2); blk /= nb2;
+    const int by = (int)(blk % nb1); blk /= nb1;
+    const int bx = (int)(blk % nb0);
+    const int b = (int)(blk / nb0);
+    // the other stage was last read in iteration it - 1, which ended with __syncthreads: safe to refill it now
+    if (threadIdx.x == 0 && tile + gridDim.x < ntiles) issue(tile + gridDim.x, stage ^ 1);
+    gen_mbar_wait(full + stage, (uint32_t)((it >> 1) & 1));
+    float* tile_s = tiles[stage];
+    if (P.normalise) {                                       // IntensityAugmentation on the staged tile (layers.py:1235-1242)
+      const float m = ord2f(minmax[2 * b]);
+      const float inv_den = (ord2f(minmax[2 * b + 1]) - m) + 1e-7f;
+      const float ge = P.use_gamma ? gamma_exp[b] : 1.f;
+      const int o0 = bx * BT0 - 1, o1 = by * BT1 - 1, o2 = bz * BT2 - 1;
+      for (int row = warp; row < (BT0 + 2) * T1; row += 8) {
+        const int a = row / T1, bb = row - a * T1;
+        const int i = o0 + a, j = o1 + bb;
+        const bool row_ok = i >= 0 && i < P.n0 && j >= 0 && j < P.n1;
+        for (int c = lane; c < BT2 + 2; c += 32) {
+          const int k = o2 + c;
+          float val = 0.f;                                   // padding stays exactly zero (it is not normalised)
+          if (row_ok && k >= 0 && k < P.n2) {
+            val = (tile_s[row * T2 + c] - m) / inv_den;
+            if (P.use_gamma) val = powf(val, ge);
+          }
+          tile_s[row * T2 + c] = val;
+        }
+      }
+      __syncthreads();
+    }
+    const int c = lane, a = warp;
+    const int i = bx * BT0 + a, k = bz * BT2 + c;
+    if (i < P.n0 && k < P.n2) {
+      float v[3][T1][3];
+#pragma unroll
+      for (int x = 0; x < 3; ++x)
+#pragma unroll
+        for (int r = 0; r < T1; ++r)
+#pragma unroll
+          for (int z = 0; z < 3; ++z) v[x][r][z] = tile_s[((a + x) * T1 + r) * T2 + c + z];
+#pragma unroll
+      for (int bb = 0; bb < BT1; ++bb) {
+        const int j = by * BT1 + bb;
+        if (j < P.n1) {
+          float acc = 0.f;
+#pragma unroll
+          for (int x = 0; x < 3; ++x)
+#pragma unroll
+            for (int y = 0; y < 3; ++y)
+#pragma unroll
+              for (int z = 0; z < 3; ++z) acc += kr[(x * 3 + y) * 3 + z] * v[x][bb + y][z];
+          dst[((long long)b * nvox + ((long long)i * P.n1 + j) * P.n2 + k) * P.dst_stride + P.dst_off] = acc;
+        }
+      }
+    }
+    __syncthreads();                                         // every reader is done with tiles[stage]
+  }
+}
+
 // elementwise normalise(+gamma) without blur (window 1x1x1 special case is handled by blur3d too; this is for
 // the real-image target where no blur follows)
 __global__ void copy_strided_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n, int ss, int so,
@@ -771,6 +902,35 @@ int ssr_minmax(const float* x, unsigned int* minmax, int B, long long nvox, void
   return SSR_OK;
 }
 
+typedef CUresult (*GenEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static GenEncodeTiledFn gen_get_encode() {
+  static GenEncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (GenEncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// dense single-channel volume [B][n0][n1][n2] as a 4-D tensor map with the blur's halo box; false when TMA's alignment
+// rules (16-byte base and strides) do not hold for this volume -- the caller then uses the plain shared-memory kernel
+static bool gen_blur_map(CUtensorMap* m, const float* src, int B, int n0, int n1, int n2) {
+  GenEncodeTiledFn enc = gen_get_encode();
+  if (!enc || ((uintptr_t)src & 15) != 0 || (n2 & 3) != 0) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)n2, (cuuint64_t)n1, (cuuint64_t)n0, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)n2 * 4, (cuuint64_t)n1 * n2 * 4, (cuuint64_t)n0 * n1 * n2 * 4};
+  cuuint32_t box[4] = {TB2, BT1 + 2, BT0 + 2, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)src, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int ssr_blur3d(const float* src, float* dst, const float* kern, int k0, int k1, int k2, const unsigned int* minmax,
                const float* gamma_exp, int B, int n0, int n1, int n2, int src_stride, int src_off, int dst_stride,
                int dst_off, void* stream) {
@@ -786,7 +946,18 @@ int ssr_blur3d(const float* src, float* dst, const float* kern, int k0, int k1, 
   if (smem > 48 * 1024)
     SSR_CHECK_CUDA(cudaFuncSetAttribute(blur3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long nblk = (long long)B * ssr_div_up(n0, BT0) * ssr_div_up(n1, BT1) * ssr_div_up(n2, BT2);
-  if (k0 == 3 && k1 == 3 && k2 == 3)
+  CUtensorMap map;
+  if (k0 == 3 && k1 == 3 && k2 == 3 && P.src_stride == 1 && P.src_off == 0 && !getenv("SSR_NO_TMA_BLUR") &&
+      gen_blur_map(&map, src, B, n0, n1, n2)) {
+    static int num_sms = 0;
+    if (!num_sms) {
+      int dev = 0;
+      SSR_CHECK_CUDA(cudaGetDevice(&dev));
+      SSR_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const long long grid = nblk < 3LL * num_sms ? nblk : 3LL * num_sms;        // persistent: 3 CTAs per SM
+    blur3d_333_tma_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(map, dst, kern, minmax, gamma_exp, P);
+  } else if (k0 == 3 && k1 == 3 && k2 == 3)
     blur3d_333_kernel<<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(src, dst, kern, minmax, gamma_exp, P);
   else
     blur3d_kernel<<<(unsigned)nblk, 256, smem, (cudaStream_t)stream>>>(src, dst, kern, minmax, gamma_exp, P);
