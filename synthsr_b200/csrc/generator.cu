@@ -620,7 +620,8 @@ blur3d_333_kernel(const float* __restrict__ src, float* __restrict__ dst, const 
 // Same arithmetic and accumulation order as blur3d_333_kernel (bit-identical results).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int TB2 = 36;                                       // box width: BT2 + 2 rounded up to a multiple of 4 floats
-constexpr int TMA_TILE_FLOATS = (BT0 + 2) * (BT1 + 2) * TB2;  // 3600 floats = 14400 B per stage
+constexpr int TMA_TILE_FLOATS = (BT0 + 2) * (BT1 + 2) * TB2;  // 3600 floats = 14400 B per box
+constexpr int TMA_STAGE_FLOATS = (TMA_TILE_FLOATS + 31) / 32 * 32;   // stage stride: TMA destinations are 128-byte aligned
 
 __device__ __forceinline__ uint32_t gen_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void gen_mbar_init(uint64_t* bar, uint32_t count) {
@@ -650,7 +651,7 @@ __global__ void __launch_bounds__(256, 3)
 blur3d_333_tma_kernel(const __grid_constant__ CUtensorMap map_src, float* __restrict__ dst, const float* __restrict__ kern,
                       const uint32_t* __restrict__ minmax, const float* __restrict__ gamma_exp, BlurParams P) {
   constexpr int T1 = BT1 + 2, T2 = TB2;
-  __shared__ __align__(128) float tiles[2][TMA_TILE_FLOATS];
+  __shared__ __align__(128) float tiles[2][TMA_STAGE_FLOATS];
   __shared__ __align__(8) uint64_t full[2];
   const int nb2 = (P.n2 + BT2 - 1) / BT2, nb1 = (P.n1 + BT1 - 1) / BT1, nb0 = (P.n0 + BT0 - 1) / BT0;
   const long long ntiles = (long long)P.B * nb0 * nb1 * nb2;
