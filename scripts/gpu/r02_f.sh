@@ -3,6 +3,12 @@
 # generator ncu capture with the TMA-staged blur
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm --format=csv,noheader
+echo "== TMA-staged blur on its own first (a fault would poison the rest of the process)"
+if timeout 600 python -m pytest tests/test_generator_gpu.py tests/test_generator_entry_points_gpu.py -m gpu -q -k "not benchmark_shape" 2>&1 | tail -4 | tee /dev/stderr | grep -q " passed" && ! timeout 600 python -m pytest tests/test_generator_gpu.py -m gpu -q -k "training_defaults" 2>&1 | grep -q "failed\|error"; then
+  echo "TMA blur OK"
+else
+  echo "TMA blur FAILED -> SSR_NO_TMA_BLUR=1 for the rest of this call"; export SSR_NO_TMA_BLUR=1
+fi
 echo "== gpu tests (all)"
 timeout 2400 python -m pytest tests -m gpu -q 2>&1 | tail -25
 grep -v "comp \|hybrid " gpurun_out/unet_parity.txt

@@ -647,12 +647,18 @@ __device__ __forceinline__ void gen_tma_load_4d(const CUtensorMap* map, uint64_t
                : "memory");
 }
 
-__global__ void __launch_bounds__(256, 3)
+__device__ __forceinline__ void gen_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gen_smem_u32(bar)) : "memory");
+}
+
+// 288 threads: warps 0-7 compute (one d0 plane of the tile each), warp 8 is the TMA producer (same warp-specialised
+// full / empty mbarrier ring as the convolution kernels)
+__global__ void __launch_bounds__(288, 2)
 blur3d_333_tma_kernel(const __grid_constant__ CUtensorMap map_src, float* __restrict__ dst, const float* __restrict__ kern,
                       const uint32_t* __restrict__ minmax, const float* __restrict__ gamma_exp, BlurParams P) {
   constexpr int T1 = BT1 + 2, T2 = TB2;
   __shared__ __align__(128) float tiles[2][TMA_STAGE_FLOATS];
-  __shared__ __align__(8) uint64_t full[2];
+  __shared__ __align__(8) uint64_t full[2], empty[2];
   const int nb2 = (P.n2 + BT2 - 1) / BT2, nb1 = (P.n1 + BT1 - 1) / BT1, nb0 = (P.n0 + BT0 - 1) / BT0;
   const long long ntiles = (long long)P.B * nb0 * nb1 * nb2;
   const long long nvox = (long long)P.n0 * P.n1 * P.n2;
@@ -660,23 +666,35 @@ blur3d_333_tma_kernel(const __grid_constant__ CUtensorMap map_src, float* __rest
   if (threadIdx.x == 0) {
     gen_mbar_init(full + 0, 1);
     gen_mbar_init(full + 1, 1);
+    gen_mbar_init(empty + 0, 8);
+    gen_mbar_init(empty + 1, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  auto issue = [&](long long tile, int stage) {              // thread 0 only
-    long long blk = tile;
-    const int bz = (int)(blk % nb2); blk /= nb2;
-    const int by = (int)(blk % nb1); blk /= nb1;
-    const int bx = (int)(blk % nb0);
-    const int b = (int)(blk / nb0);
-    gen_mbar_expect_tx(full + stage, TMA_TILE_FLOATS * 4);
-    gen_tma_load_4d(&map_src, full + stage, tiles[stage], bz * BT2 - 1, by * BT1 - 1, bx * BT0 - 1, b);
-  };
+  if (warp == 8) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_src) : "memory");
+      int it = 0;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int stage = it & 1;
+        long long blk = tile;
+        const int bz = (int)(blk % nb2); blk /= nb2;
+        const int by = (int)(blk % nb1); blk /= nb1;
+        const int bx = (int)(blk % nb0);
+        const int b = (int)(blk / nb0);
+        gen_mbar_wait(empty + stage, (uint32_t)(((it >> 1) & 1) ^ 1));      // the consumers are done with this stage
+        gen_mbar_expect_tx(full + stage, TMA_TILE_FLOATS * 4);
+        gen_tma_load_4d(&map_src, full + stage, tiles[stage], bz * BT2 - 1, by * BT1 - 1, bx * BT0 - 1, b);
+      }
+    }
+    return;
+  }
+  // ================================ consumers (256 threads) ================================
   float kr[27];
 #pragma unroll
   for (int t = 0; t < 27; ++t) kr[t] = kern[t];
-  if (threadIdx.x == 0 && (long long)blockIdx.x < ntiles) issue(blockIdx.x, 0);
   int it = 0;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const int stage = it & 1;
@@ -685,8 +703,6 @@ blur3d_333_tma_kernel(const __grid_constant__ CUtensorMap map_src, float* __rest
     const int by = (int)(blk % nb1); blk /= nb1;
     const int bx = (int)(blk % nb0);
     const int b = (int)(blk / nb0);
-    // the other stage was last read in iteration it - 1, which ended with __syncthreads: safe to refill it now
-    if (threadIdx.x == 0 && tile + gridDim.x < ntiles) issue(tile + gridDim.x, stage ^ 1);
     gen_mbar_wait(full + stage, (uint32_t)((it >> 1) & 1));
     float* tile_s = tiles[stage];
     if (P.normalise) {                                       // IntensityAugmentation on the staged tile (layers.py:1235-1242)
@@ -708,7 +724,7 @@ blur3d_333_tma_kernel(const __grid_constant__ CUtensorMap map_src, float* __rest
           tile_s[row * T2 + c] = val;
         }
       }
-      __syncthreads();
+      asm volatile("bar.sync 1, 256;" ::: "memory");         // consumers only: the producer warp is not part of it
     }
     const int c = lane, a = warp;
     const int i = bx * BT0 + a, k = bz * BT2 + c;
@@ -735,7 +751,8 @@ blur3d_333_tma_kernel(const __grid_constant__ CUtensorMap map_src, float* __rest
         }
       }
     }
-    __syncthreads();                                         // every reader is done with tiles[stage]
+    __syncwarp();
+    if (lane == 0) gen_mbar_arrive(empty + stage);           // this warp's reads of tiles[stage] are complete
   }
 }
 
@@ -956,8 +973,8 @@ int ssr_blur3d(const float* src, float* dst, const float* kern, int k0, int k1, 
       SSR_CHECK_CUDA(cudaGetDevice(&dev));
       SSR_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    const long long grid = nblk < 3LL * num_sms ? nblk : 3LL * num_sms;        // persistent: 3 CTAs per SM
-    blur3d_333_tma_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(map, dst, kern, minmax, gamma_exp, P);
+    const long long grid = nblk < 2LL * num_sms ? nblk : 2LL * num_sms;        // persistent: 2 CTAs per SM
+    blur3d_333_tma_kernel<<<(unsigned)grid, 288, 0, (cudaStream_t)stream>>>(map, dst, kern, minmax, gamma_exp, P);
   } else if (k0 == 3 && k1 == 3 && k2 == 3)
     blur3d_333_kernel<<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(src, dst, kern, minmax, gamma_exp, P);
   else
