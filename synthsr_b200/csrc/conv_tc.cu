@@ -3066,6 +3066,8 @@ static int conv3d_fwd_tc_k2n_impl(const float* x, int Ctot, int c0, int C, const
   }
   if (epi == 1 && Cout == 24) rc = launch_k2n<1, 3>(grid, smem, st, mx, mw, bias, y, G, elu_h, dbias, sums);
   else if (epi == 1) rc = launch_k2n<1, 4>(grid, smem, st, mx, mw, bias, y, G, elu_h, dbias, sums);
+  else if (epi == 2 && accumulate && Cout == 24) rc = launch_k2n<2, 3, true>(grid, smem, st, mx, mw, bias, y, G, elu_h, dbias, sums);
+  else if (epi == 2 && accumulate) rc = launch_k2n<2, 4, true>(grid, smem, st, mx, mw, bias, y, G, elu_h, dbias, sums);
   else if (epi == 2 && Cout == 24) rc = launch_k2n<2, 3>(grid, smem, st, mx, mw, bias, y, G, elu_h, dbias, sums);
   else if (epi == 2) rc = launch_k2n<2, 4>(grid, smem, st, mx, mw, bias, y, G, elu_h, dbias, sums);
   else if (accumulate && Cout == 24 && !getenv("SSR_K2N_NO_ACC_PREFETCH")) rc = launch_k2n<0, 3, true>(grid, smem, st, mx, mw, bias, y, G, nullptr, nullptr, nullptr);

@@ -611,7 +611,7 @@ blur3d_333_kernel(const float* __restrict__ src, float* __restrict__ dst, const 
 
 // ---------------------------------------------------------------------------------------------------------
 // TMA-staged, persistent version of blur3d_333_kernel (the two 3x3x3 blurs of the default training configuration).
-// The halo tile of a block of 8 x 8 x 32 outputs is ONE 4-D TMA box {36, 10, 10, 1} of the dense source volume
+// The halo tile of a block of 8 x 8 x 32 outputs is ONE 4-D TMA box {40, 10, 10, 1} of the dense source volume
 // (cp.async.bulk.tensor, completion on an mbarrier): out-of-volume elements arrive as zeros = the 'SAME' zero padding of
 // tf.nn.conv3d (ext/lab2im/layers.py:748,758), no per-element bounds logic or index arithmetic on the load path.  CTAs are
 // persistent (grid = a multiple of the SM count) and double-buffered: thread 0 issues the box of tile t + 1 before the CTA
@@ -619,8 +619,11 @@ blur3d_333_kernel(const float* __restrict__ src, float* __restrict__ dst, const 
 // compute -> exit; profiles/r02_generator_ncu_baseline.txt: 305 - 523 GB/s) overlaps the normalise / gamma / stencil work.
 // Same arithmetic and accumulation order as blur3d_333_kernel (bit-identical results).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int TB2 = 36;                                       // box width: BT2 + 2 rounded up to a multiple of 4 floats
-constexpr int TMA_TILE_FLOATS = (BT0 + 2) * (BT1 + 2) * TB2;  // 3600 floats = 14400 B per box
+constexpr int TBX = 4;                                        // the box starts TBX floats left of the tile: the innermost start of a
+                                                              // TMA box must be 16-byte aligned (a start at x0 - 1 is an illegal
+                                                              // instruction at run time: profiles/r02_tma_blur_sanitizer.txt)
+constexpr int TB2 = 40;                                       // box width: TBX + BT2 + 1, rounded up to a multiple of 4 floats
+constexpr int TMA_TILE_FLOATS = (BT0 + 2) * (BT1 + 2) * TB2;  // 4000 floats = 16000 B per box
 constexpr int TMA_STAGE_FLOATS = (TMA_TILE_FLOATS + 31) / 32 * 32;   // stage stride: TMA destinations are 128-byte aligned
 
 __device__ __forceinline__ uint32_t gen_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -686,7 +689,7 @@ blur3d_333_tma_kernel(const __grid_constant__ CUtensorMap map_src, float* __rest
         const int b = (int)(blk / nb0);
         gen_mbar_wait(empty + stage, (uint32_t)(((it >> 1) & 1) ^ 1));      // the consumers are done with this stage
         gen_mbar_expect_tx(full + stage, TMA_TILE_FLOATS * 4);
-        gen_tma_load_4d(&map_src, full + stage, tiles[stage], bz * BT2 - 1, by * BT1 - 1, bx * BT0 - 1, b);
+        gen_tma_load_4d(&map_src, full + stage, tiles[stage], bz * BT2 - TBX, by * BT1 - 1, bx * BT0 - 1, b);
       }
     }
     return;
@@ -718,10 +721,10 @@ blur3d_333_tma_kernel(const __grid_constant__ CUtensorMap map_src, float* __rest
           const int k = o2 + c;
           float val = 0.f;                                   // padding stays exactly zero (it is not normalised)
           if (row_ok && k >= 0 && k < P.n2) {
-            val = (tile_s[row * T2 + c] - m) / inv_den;
+            val = (tile_s[row * T2 + (TBX - 1) + c] - m) / inv_den;
             if (P.use_gamma) val = powf(val, ge);
           }
-          tile_s[row * T2 + c] = val;
+          tile_s[row * T2 + (TBX - 1) + c] = val;
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");         // consumers only: the producer warp is not part of it
@@ -735,7 +738,7 @@ blur3d_333_tma_kernel(const __grid_constant__ CUtensorMap map_src, float* __rest
 #pragma unroll
         for (int r = 0; r < T1; ++r)
 #pragma unroll
-          for (int z = 0; z < 3; ++z) v[x][r][z] = tile_s[((a + x) * T1 + r) * T2 + c + z];
+          for (int z = 0; z < 3; ++z) v[x][r][z] = tile_s[((a + x) * T1 + r) * T2 + (TBX - 1) + c + z];
 #pragma unroll
       for (int bb = 0; bb < BT1; ++bb) {
         const int j = by * BT1 + bb;
