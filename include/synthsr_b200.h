@@ -175,6 +175,13 @@ int ssr_conv3d_fwd_tc_up_comp(const float* low, const float* lowlo, int Cup, con
 int ssr_tf32_split_bf16(const float* x, void* x2, long long nvox, int C, void* stream);
 int ssr_conv3d_fwd_tc_k2n_bf16(const void* x2, int C2, const float* wp, const float* bias, float* y, double* sums, int B,
                                int d0, int d1, int d2, int Cout, int act, void* stream);
+/* producers that emit the next layer's x2 from their own epilogue (bit-identical to ssr_tf32_split_bf16 of their output,
+ * without the extra pass): the first layer (KL.Conv3D with Cin <= 2) and the final k2n channel part */
+int ssr_conv3d_first_fwd_split(const float* x, int C1, const float* w, const float* bias, float* y, void* y2, int B, int d0,
+                               int d1, int d2, int Cout, int act, void* stream);
+int ssr_conv3d_fwd_tc_k2n_part_split(const float* x, int Ctot, int c0, int C, const float* wp, const float* bias, float* y,
+                                     void* y2, int B, int d0, int d1, int d2, int Cout, int act, int accumulate,
+                                     void* stream);
 /* last channel part of a k2n convolution + the BatchNorm sums of the finished output (sums zeroed here) */
 int ssr_conv3d_fwd_tc_k2n_part_stats(const float* x, int Ctot, int c0, int C, const float* wp, const float* bias, float* y,
                                      double* sums, int B, int d0, int d1, int d2, int Cout, int act, int accumulate,

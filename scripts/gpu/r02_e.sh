@@ -16,6 +16,8 @@ except Exception as e:
     print('$tag failed', e)
 PY
 }
+echo "== new fused-split producers + generator tests (1 GPU)"
+timeout 900 python -m pytest tests/test_unet_parity_gpu.py tests/test_generator_gpu.py tests/test_generator_entry_points_gpu.py -m gpu -q -k "producers or 32 or generator or blur or default or training" 2>&1 | tail -6
 echo "== 1 GPU reference point (same flags)"
 timeout 600 python bench.py --gpus 1 --steps 40 --warmup 8 --no-e2e --no-extras --no-cpu-baseline > gpurun_out/r02e_n1.json 2> gpurun_out/r02e_n1.err
 python -c "

@@ -230,6 +230,20 @@ __device__ __forceinline__ void umma_chain_mn_ab(int n, uint32_t d_tmem, uint32_
   }
 }
 
+__device__ __forceinline__ uint32_t bf16_bits(float v) {       // round to nearest even bf16 (operands are finite)
+  const uint32_t u = __float_as_uint(v);
+  return (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;
+}
+// the two bf16 operands of the hybrid forward's correction term for one fp32 activation: hi = bf16(rne_tf32(v)),
+// lo = bf16(v - rne_tf32(v))  (identical to tf32_split_bf16_kernel, so producers may emit them in their epilogue)
+__device__ __forceinline__ void split_bf16(float v, uint32_t& lo, uint32_t& hi) {
+  uint32_t u = __float_as_uint(v);
+  u = (u + 0xFFFu + ((u >> 13) & 1u)) & ~0x1FFFu;
+  const float h = __uint_as_float(u);
+  hi = bf16_bits(h);
+  lo = bf16_bits(v - h);
+}
+
 // instruction descriptor: D=F32, A=B=TF32, both K-major, M=128, N
 __device__ __forceinline__ uint32_t make_idesc_tf32(int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
@@ -1018,6 +1032,8 @@ constexpr int KF_SA = 5, KF_NACC = 4, KF_N = 96;
 
 struct KfGeom {
   int B, D0, D1, D2, Cout, act, nks;
+  uint16_t* y2;    // optional (final part): also write [bf16(y_lo) | bf16(y_hi)] (2 Cout bf16 per voxel), the input of the
+                   // NEXT layer's hybrid forward -- saves that layer's ssr_tf32_split_bf16 pass over y
   int f16;         // the source holds bf16 channels (64 per chunk) and the weights bf16 pairs: kind::f16 MMAs
   int c0;          // first channel of this part in the source tensor (TMA coordinate)
   int accumulate;  // epilogue adds the partial result already in y (earlier channel parts of a concatenated input)
@@ -1241,6 +1257,16 @@ conv3d_tc_k2n_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             for (int e = 0; e < 8; ++e) s2[blk * 8 + e] += o[e] * o[e];
           }
           const int nvalid = G.Cout - cb;
+          if (G.y2 != nullptr && G.final && nvalid >= 8) {          // Cout % 8 == 0 (host-checked)
+            uint32_t lo[8], hi[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split_bf16(o[e], lo[e], hi[e]);
+            uint16_t* r2 = G.y2 + 2 * voff + cb;
+            *reinterpret_cast<uint4*>(r2) = make_uint4(lo[0] | (lo[1] << 16), lo[2] | (lo[3] << 16), lo[4] | (lo[5] << 16),
+                                                       lo[6] | (lo[7] << 16));
+            *reinterpret_cast<uint4*>(r2 + G.Cout) = make_uint4(hi[0] | (hi[1] << 16), hi[2] | (hi[3] << 16),
+                                                                hi[4] | (hi[5] << 16), hi[6] | (hi[7] << 16));
+          }
           if (nvalid >= 8 && vec_ok) {
             *reinterpret_cast<float4*>(orow + cb) = make_float4(o[0], o[1], o[2], o[3]);
             *reinterpret_cast<float4*>(orow + cb + 4) = make_float4(o[4], o[5], o[6], o[7]);
@@ -2294,10 +2320,6 @@ __global__ void tf32_residual_kernel(const float* __restrict__ x, float* __restr
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) lo[(n4 << 2) + threadIdx.x] = tf32_lo(x[(n4 << 2) + threadIdx.x]);
 }
 
-__device__ __forceinline__ uint32_t bf16_bits(float v) {       // round to nearest even bf16 (operands are finite)
-  const uint32_t u = __float_as_uint(v);
-  return (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;
-}
 // x2[v][0:C] = bf16(x - rne_tf32(x)),  x2[v][C:2C] = bf16(rne_tf32(x)): the two operands of the bf16 correction term of
 // the compensated forward, written as ONE 2C-channel bf16 tensor (same bytes per voxel as C fp32 channels)
 __global__ void tf32_split_bf16_kernel(const float* __restrict__ x, uint16_t* __restrict__ x2, long long nvox, int C) {
@@ -3019,7 +3041,7 @@ int ssr_conv3d_up_weights(const float* w, int Cskip, int Cup, int Cout, float* w
 static int conv3d_fwd_tc_k2n_impl(const float* x, int Ctot, int c0, int C, const float* wp, const float* bias, float* y,
                                   int B, int D0, int D1, int D2, int Cout, int act, int accumulate, int final, void* stream,
                                   int epi = 0, const float* elu_h = nullptr, float* dbias = nullptr, double* sums = nullptr,
-                                  int f16 = 0) {
+                                  int f16 = 0, void* y2 = nullptr) {
   // f16: x is the bf16 tensor [x_lo | x_hi] of Ctot = C = 2 * (layer channels) <= 64 channels, wp from pack mode 8
   SSR_CHECK_ARG(x && wp && y && B > 0 && D0 > 0 && D1 > 0 && D2 > 0, "pointers/shape");
   SSR_CHECK_ARG(C > 0 && C <= (f16 ? 64 : 32) && C % (f16 ? 16 : 8) == 0 && Cout > 0 && Cout <= 32 && c0 >= 0 && c0 + C <= Ctot &&
@@ -3030,6 +3052,8 @@ static int conv3d_fwd_tc_k2n_impl(const float* x, int Ctot, int c0, int C, const
   memset(&G, 0, sizeof(G));
   G.B = B; G.D0 = D0; G.D1 = D1; G.D2 = D2; G.Cout = Cout; G.act = act; G.nks = f16 ? C / 16 : C / 8;
   G.c0 = c0; G.accumulate = accumulate; G.final = final; G.f16 = f16;
+  SSR_CHECK_ARG(!y2 || (final && Cout % 8 == 0 && ((uintptr_t)y2 & 15) == 0), "split output needs the final part, Cout % 8 == 0");
+  G.y2 = reinterpret_cast<uint16_t*>(y2);
   G.n1tiles = (D1 + KF_TM1 - 1) / KF_TM1; G.n2tiles = (D2 + KF_OUT2 - 1) / KF_OUT2;
   static int num_sms = 0;
   if (!num_sms) {
@@ -3086,6 +3110,13 @@ int ssr_conv3d_fwd_tc_k2n(const float* x, int C, const float* wp, const float* b
 int ssr_conv3d_fwd_tc_k2n_part(const float* x, int Ctot, int c0, int C, const float* wp, const float* bias, float* y, int B,
                                int D0, int D1, int D2, int Cout, int act, int accumulate, int final, void* stream) {
   return conv3d_fwd_tc_k2n_impl(x, Ctot, c0, C, wp, bias, y, B, D0, D1, D2, Cout, act, accumulate, final, stream);
+}
+// final part that ALSO writes y2 = [bf16(y_lo) | bf16(y_hi)] (what ssr_tf32_split_bf16(y) would produce) from its epilogue
+int ssr_conv3d_fwd_tc_k2n_part_split(const float* x, int Ctot, int c0, int C, const float* wp, const float* bias, float* y,
+                                     void* y2, int B, int D0, int D1, int D2, int Cout, int act, int accumulate,
+                                     void* stream) {
+  return conv3d_fwd_tc_k2n_impl(x, Ctot, c0, C, wp, bias, y, B, D0, D1, D2, Cout, act, accumulate, 1, stream, 0, nullptr,
+                                nullptr, nullptr, 0, y2);
 }
 
 // Data gradient of a Cin, Cout <= 32 layer fused with the ELU backward of the convolution below it (replaces

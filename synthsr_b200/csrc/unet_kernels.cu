@@ -118,7 +118,9 @@ constexpr int FT0 = 4, FT1 = 8, FT2 = 32;
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(256)
 conv3d_first_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                    float* __restrict__ y, int B, int d0, int d1, int d2, int act) {
+                    float* __restrict__ y, int B, int d0, int d1, int d2, int act, uint16_t* __restrict__ y2) {
+  // y2 (optional): [bf16(y_lo) | bf16(y_hi)], 2 COUT bf16 per voxel = the operand of the next layer's hybrid compensated
+  // forward (conv_tc.cu: tf32_split_bf16_kernel), written from the same staged rows instead of a separate pass over y
   __shared__ float sx[(FT0 + 2) * (FT1 + 2) * (FT2 + 2) * CIN];
   __shared__ __align__(16) float sw[27 * CIN * COUT];
   __shared__ float sb[COUT];
@@ -189,9 +191,27 @@ conv3d_first_kernel(const float* __restrict__ x, const float* __restrict__ w, co
       for (int e = threadIdx.x; e < FT1 * FT2 * (COUT / 4); e += 256) {
         const int vox = e / (COUT / 4), part = e % (COUT / 4);
         const int j1 = b1 * FT1 + (vox >> 5), j2 = b2 * FT2 + (vox & 31);
-        if (j1 < d1 && j2 < d2)
-          reinterpret_cast<float4*>(y + ((((long long)b * d0 + i0 + pl) * d1 + j1) * d2 + j2) * COUT)[part] =
-              reinterpret_cast<const float4*>(sst)[e];
+        if (j1 < d1 && j2 < d2) {
+          const long long vidx = (((long long)b * d0 + i0 + pl) * d1 + j1) * d2 + j2;
+          const float4 v = reinterpret_cast<const float4*>(sst)[e];
+          reinterpret_cast<float4*>(y + vidx * COUT)[part] = v;
+          if (y2 != nullptr) {
+            const float in[4] = {v.x, v.y, v.z, v.w};
+            uint32_t lo[4], hi[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t u = __float_as_uint(in[q]);
+              u = (u + 0xFFFu + ((u >> 13) & 1u)) & ~0x1FFFu;          // rne_tf32, as the TMA load rounds
+              const float h = __uint_as_float(u);
+              const uint32_t uh = __float_as_uint(h), ul = __float_as_uint(in[q] - h);
+              hi[q] = (uh + 0x7FFFu + ((uh >> 16) & 1u)) >> 16;        // rne bf16
+              lo[q] = (ul + 0x7FFFu + ((ul >> 16) & 1u)) >> 16;
+            }
+            uint16_t* r2 = y2 + vidx * (2 * COUT) + part * 4;
+            *reinterpret_cast<uint2*>(r2) = make_uint2(lo[0] | (lo[1] << 16), lo[2] | (lo[3] << 16));
+            *reinterpret_cast<uint2*>(r2 + COUT) = make_uint2(hi[0] | (hi[1] << 16), hi[2] | (hi[3] << 16));
+          }
+        }
       }
     }
   }
@@ -1398,22 +1418,35 @@ int grid_for(long long n, int block = 256) {
 
 extern "C" {
 
+static int conv3d_first_launch(const float* x1, int C1, const float* w, const float* bias, float* y, uint16_t* y2, int B,
+                               int d0, int d1, int d2, int Cout, int act, void* stream) {
+  const long long nblk = (long long)B * ((d0 + FT0 - 1) / FT0) * ((d1 + FT1 - 1) / FT1) * ((d2 + FT2 - 1) / FT2);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C1 == 1 && Cout == 24) conv3d_first_kernel<1, 24><<<(unsigned)nblk, 256, 0, st>>>(x1, w, bias, y, B, d0, d1, d2, act, y2);
+  else if (C1 == 2 && Cout == 24) conv3d_first_kernel<2, 24><<<(unsigned)nblk, 256, 0, st>>>(x1, w, bias, y, B, d0, d1, d2, act, y2);
+  else if (C1 == 1 && Cout == 8) conv3d_first_kernel<1, 8><<<(unsigned)nblk, 256, 0, st>>>(x1, w, bias, y, B, d0, d1, d2, act, y2);
+  else conv3d_first_kernel<2, 8><<<(unsigned)nblk, 256, 0, st>>>(x1, w, bias, y, B, d0, d1, d2, act, y2);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+
+// first layer (Cin <= 2, Cout 8 / 24, k = 3) that also writes y2 = [bf16(y_lo) | bf16(y_hi)] -- what
+// ssr_tf32_split_bf16(y) would produce -- for the hybrid compensated forward of the next layer
+int ssr_conv3d_first_fwd_split(const float* x, int C1, const float* w, const float* bias, float* y, void* y2, int B, int d0,
+                               int d1, int d2, int Cout, int act, void* stream) {
+  SSR_CHECK_ARG(x && w && y && y2 && (C1 == 1 || C1 == 2) && (Cout == 24 || Cout == 8) && (((uintptr_t)y | (uintptr_t)y2) & 15) == 0,
+                "first-layer split forward: Cin 1 / 2, Cout 8 / 24, 16-byte aligned outputs");
+  return conv3d_first_launch(x, C1, w, bias, y, reinterpret_cast<uint16_t*>(y2), B, d0, d1, d2, Cout, act, stream);
+}
+
 int ssr_conv3d_fwd_ref(const float* x1, int C1, const float* x2, int C2, const float* w, const float* bias, float* y,
                        int B, int d0, int d1, int d2, int Cout, int k, int act, void* stream) {
   SSR_CHECK_ARG(x1 && w && y && C1 > 0 && C2 >= 0 && (C2 == 0 || x2) && Cout > 0 && (k & 1), "conv args");
   ConvGeom G{B, d0, d1, d2, C1, C2, Cout, k, act};
   const long long nvox = (long long)B * d0 * d1 * d2;
-  if (k == 3 && C2 == 0 && C1 <= 2 && (Cout == 24 || Cout == 8) && (((uintptr_t)y) & 15) == 0) {   // first-layer kernel
-    const long long nblk = (long long)B * ((d0 + FT0 - 1) / FT0) * ((d1 + FT1 - 1) / FT1) * ((d2 + FT2 - 1) / FT2);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (C1 == 1 && Cout == 24) conv3d_first_kernel<1, 24><<<(unsigned)nblk, 256, 0, st>>>(x1, w, bias, y, B, d0, d1, d2, act);
-    else if (C1 == 2 && Cout == 24) conv3d_first_kernel<2, 24><<<(unsigned)nblk, 256, 0, st>>>(x1, w, bias, y, B, d0, d1, d2, act);
-    else if (C1 == 1 && Cout == 8) conv3d_first_kernel<1, 8><<<(unsigned)nblk, 256, 0, st>>>(x1, w, bias, y, B, d0, d1, d2, act);
-    else conv3d_first_kernel<2, 8><<<(unsigned)nblk, 256, 0, st>>>(x1, w, bias, y, B, d0, d1, d2, act);
-    SSR_COUNT_LAUNCH();
-    SSR_CHECK_LAUNCH();
-    return SSR_OK;
-  }
+  if (k == 3 && C2 == 0 && C1 <= 2 && (Cout == 24 || Cout == 8) && (((uintptr_t)y) & 15) == 0)     // first-layer kernel
+    return conv3d_first_launch(x1, C1, w, bias, y, nullptr, B, d0, d1, d2, Cout, act, stream);
   dim3 grid((unsigned)((nvox + 255) / 256), (unsigned)((Cout + CO_T - 1) / CO_T));
   conv3d_direct_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x1, x2, w, bias, y, G);
   SSR_COUNT_LAUNCH();

@@ -89,6 +89,7 @@ class UNet3D:
         if os.environ.get('SSR_COMP') and conv_impl == 'tc':
             self.comp = [(re.compile(r.rsplit(':', 1)[0]), int(r.rsplit(':', 1)[1])) for r in os.environ['SSR_COMP'].split(',')]
         self._lo = None                 # scratch for the TF32 residual x_lo of the convolution being run (stream ordered)
+        self._lo_src = None             # (data_ptr, nvox, channels) of the tensor whose bf16 split _lo currently holds
         # 'hybrid' (default): x_hi w_hi in TF32 + the two correction terms as one bf16 MMA chain (2 chains per convolution);
         # 'tf32x3': all three terms in TF32 (3 chains) -- the first implementation, kept as a cross-check
         self.comp_scheme = os.environ.get('SSR_COMP_SCHEME', 'hybrid')
@@ -307,18 +308,31 @@ class UNet3D:
     def _residual(self, x, n):
         """x_lo = x - rne_tf32(x) of the first n floats of x, in the shared scratch (consumed by the next launch on this
         stream, so one buffer serves every layer)."""
+        self._lo_src = None
+        lib.ssr_tf32_residual(x, self._lo_buf(n), n, stream_ptr())
+        return self._lo
+
+    def _lo_buf(self, n):
         if self._lo is None or self._lo.numel() < n:
             self._lo = torch.empty(max(n, self.nvox[0] * self.feats[0]), dtype=torch.float32, device=self.device)
-        lib.ssr_tf32_residual(x, self._lo, n, stream_ptr())
         return self._lo
 
     def _split16(self, x, nvox, c):
-        """x2 = [bf16(x_lo) | bf16(x_hi)] (2c bf16 channels per voxel = the bytes of c floats) in the shared scratch"""
-        n = nvox * c
-        if self._lo is None or self._lo.numel() < n:
-            self._lo = torch.empty(max(n, self.nvox[0] * self.feats[0]), dtype=torch.float32, device=self.device)
-        lib.ssr_tf32_split_bf16(x, self._lo, nvox, c, stream_ptr())
+        """x2 = [bf16(x_lo) | bf16(x_hi)] (2c bf16 channels per voxel = the bytes of c floats) in the shared scratch;
+        skipped when the kernel that produced x has just written it from its own epilogue (_lo_src)."""
+        key = (x.data_ptr(), nvox, c)
+        if self._lo_src == key:
+            self._lo_src = None
+            return self._lo
+        self._lo_src = None
+        lib.ssr_tf32_split_bf16(x, self._lo_buf(nvox * c), nvox, c, stream_ptr())
         return self._lo
+
+    def _fuse_split_ok(self, next_name, c1, cout):
+        """the layer `next_name` (c1 -> cout) will run the hybrid compensated forward through the k2n kernel on the tensor
+        being produced now: the producer may emit its bf16 split directly (the two full-resolution 24-channel tensors)"""
+        return (self.conv_impl == 'tc' and self.comp_scheme == 'hybrid' and self._comp_level(next_name) == 3 and
+                self._k2n_ok(c1, cout) and os.environ.get('SSR_NO_SPLIT_FUSION') is None)
 
     def _conv_fwd_hybrid(self, name, x1, c1, x2, c2, y, l, cout, act, stats_sums):
         """compensated forward, hybrid scheme: TF32 main term + one bf16 chain for x_lo w_hi + x_hi w_lo"""
@@ -445,6 +459,11 @@ class UNet3D:
                                      F[l], st)
         if self.fwd_k2n and F[l] <= 32:
             wp = self._packed_w(name, 2, F[l], 0, F[l], tag='skip', src=u['wskip'])
+            if self._fuse_split_ok(name[:-1] + '1', F[l], F[l]):      # the next convolution's bf16 operand from this epilogue
+                lib.ssr_conv3d_fwd_tc_k2n_part_split(self.h1[l], F[l], 0, F[l], wp, self.p[name + '/bias'], self.g0[l],
+                                                     self._lo_buf(self.nvox[l] * F[l]), B, *self.ldims[l], F[l], act, 1, st)
+                self._lo_src = (self.g0[l].data_ptr(), self.nvox[l], F[l])
+                return
             lib.ssr_conv3d_fwd_tc_k2n_part(self.h1[l], F[l], 0, F[l], wp, self.p[name + '/bias'], self.g0[l], B,
                                            *self.ldims[l], F[l], act, 1, 1, st)
         else:
@@ -663,7 +682,11 @@ class UNet3D:
             self._pack_event = None
         x, cx = image, self.cin
         for l in range(L):
-            self._conv_fwd('unet_conv_downarm_%d_0' % l, x, cx, None, 0, self.h0[l], l, F[l])
+            if (l == 0 and cx <= 2 and self.k == 3 and F[0] in (8, 24) and
+                    self._fuse_split_ok('unet_conv_downarm_0_1', F[0], F[0])):
+                self._timed('fwd_ref', 0, cx, F[0], lambda: self._first_fwd_split(x, cx))
+            else:
+                self._conv_fwd('unet_conv_downarm_%d_0' % l, x, cx, None, 0, self.h0[l], l, F[l])
             bn = 'unet_bn_down_%d' % l
             fused = training and self._k2n_epi_ok(F[l], F[l])
             self._conv_fwd('unet_conv_downarm_%d_1' % l, self.h0[l], F[l], None, 0, self.h1[l], l, F[l],
@@ -696,6 +719,13 @@ class UNet3D:
         lib.ssr_bn_apply(self.g1[0], self.feat, self.stats_dec[0], B, *self.ldims[0], F[0], 0, 0, 0, st)
         self._feat_src, self._feat_stats = self.feat, None
         return self.feat
+
+    def _first_fwd_split(self, x, cx):
+        """first convolution (exact fp32 on the CUDA cores) + the bf16 split of its output for downarm_0_1's hybrid forward"""
+        F0, name = self.feats[0], 'unet_conv_downarm_0_0'
+        lib.ssr_conv3d_first_fwd_split(x, cx, self.p[name + '/kernel'], self.p[name + '/bias'], self.h0[0],
+                                       self._lo_buf(self.nvox[0] * F0), self.B, *self.ldims[0], F0, 1, stream_ptr())
+        self._lo_src = (self.h0[0].data_ptr(), self.nvox[0], F0)
 
     def _u(self, l):
         if self.u[l] is None:

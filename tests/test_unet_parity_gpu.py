@@ -305,6 +305,58 @@ def test_hybrid_parity_forward_matches_float64(dl, cu, co):
     assert err < KERNEL_TOL, err
 
 
+def test_producers_emit_the_same_bf16_split_as_the_standalone_pass():
+    """ssr_conv3d_first_fwd_split and ssr_conv3d_fwd_tc_k2n_part_split write [bf16(y_lo) | bf16(y_hi)] from their epilogues:
+    bit-identical to ssr_tf32_split_bf16 of their output, and the whole step is bit-identical with the fusion switched off."""
+    from synthsr_b200._lib import lib, stream_ptr
+    from synthsr_b200.unet import UNet3D
+    rng = np.random.default_rng(5)
+    d, co = [12, 20, 36], 24
+    nv = int(np.prod(d))
+    st = stream_ptr()
+    for cin in (1, 2):
+        x = _t(rng.normal(size=(nv, cin)))
+        w = _t(rng.normal(size=(3, 3, 3, cin, co)) / np.sqrt(27 * cin))
+        b = _t(rng.normal(size=co))
+        y, y_ref = torch.empty((nv, co), device='cuda'), torch.empty((nv, co), device='cuda')
+        y2 = torch.zeros((nv, 2 * co), dtype=torch.bfloat16, device='cuda')
+        y2_ref = torch.zeros_like(y2)
+        lib.ssr_conv3d_first_fwd_split(x, cin, w, b, y, y2, 1, *d, co, 1, st)
+        lib.ssr_conv3d_fwd_ref(x, cin, None, 0, w, b, y_ref, 1, *d, co, 3, 1, st)
+        lib.ssr_tf32_split_bf16(y_ref, y2_ref, nv, co, st)
+        torch.cuda.synchronize()
+        assert torch.equal(y, y_ref) and torch.equal(y2.view(torch.int16), y2_ref.view(torch.int16)), cin
+    x = _t(rng.normal(size=(nv, co)))
+    w = _t(rng.normal(size=(3, 3, 3, co, co)) / np.sqrt(27 * co))
+    b = _t(rng.normal(size=co))
+    wp = torch.empty(lib.ssr_conv3d_packed_size(co, 0, co, 2), dtype=torch.float32, device='cuda')
+    lib.ssr_conv3d_pack_weights(w, wp, co, 0, co, 2, st)
+    part = _t(rng.normal(size=(nv, co)))
+    for acc in (0, 1):
+        y, y_ref = part.clone(), part.clone()
+        y2 = torch.zeros((nv, 2 * co), dtype=torch.bfloat16, device='cuda')
+        y2_ref = torch.zeros_like(y2)
+        lib.ssr_conv3d_fwd_tc_k2n_part_split(x, co, 0, co, wp, b, y, y2, 1, *d, co, 1, acc, st)
+        lib.ssr_conv3d_fwd_tc_k2n_part(x, co, 0, co, wp, b, y_ref, 1, *d, co, 1, acc, 1, st)
+        lib.ssr_tf32_split_bf16(y_ref, y2_ref, nv, co, st)
+        torch.cuda.synchronize()
+        assert torch.equal(y, y_ref) and torch.equal(y2.view(torch.int16), y2_ref.view(torch.int16)), acc
+    # whole step: fused vs separate split passes
+    image, target = _t(rng.uniform(0, 1, size=(1, 32, 32, 32, 1))), _t(rng.uniform(0, 1, size=(1, 32, 32, 32, 1)))
+    out = []
+    for fused in (True, False):
+        if not fused:
+            os.environ['SSR_NO_SPLIT_FUSION'] = '1'
+        try:
+            net = UNet3D([32, 32, 32, 1], batchsize=1, conv_impl='tc3', seed=0)
+            loss = net.loss_and_grad(image, target)
+            torch.cuda.synchronize()
+            out.append((loss.item(), net.pred.clone()))
+        finally:
+            os.environ.pop('SSR_NO_SPLIT_FUSION', None)
+    assert out[0][0] == out[1][0] and torch.equal(out[0][1], out[1][1])
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def _step_errors(net, image, target, pred_ref, loss_ref, grads_ref, tag, **loss_kw):
     loss = net.loss_and_grad(torch.from_numpy(image).cuda(), torch.from_numpy(target).cuda(), **loss_kw)
