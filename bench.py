@@ -350,10 +350,11 @@ def main():
     for i in range(2):
         eng.train_step(dev_maps[i % len(dev_maps)], *draw_gmm(rng, pm, ps, gc, n_ch))
     torch.cuda.synchronize()
-    agg = {}
-    for kind, fl, a, b in eng.net.prof:
+    agg, executed = {}, {}
+    for kind, fl, a, b, mult in eng.net.prof:
         t, f, n = agg.get(kind, (0., 0., 0))
         agg[kind] = (t + a.elapsed_time(b), f + fl, n + 1)
+        executed[kind] = executed.get(kind, 0.) + fl * mult
     eng.net.prof = None
     peaks = {}
     try:
@@ -372,7 +373,8 @@ def main():
     dom = max(tc, key=lambda k: tc[k][0]) if tc else None
     names = {'wgrad_tc': 'wgrad_tc_persistent_kernel (<0> plain, <1> parity classes of the decoder convolutions)',
              'fwd_tc': 'conv3d_tc_kernel / conv3d_tc_k2n_kernel / conv3d_tc_up_kernel<1> (forward%s)' % (
-                 '; compensated: K = [x | x_lo | x] x [w_hi | w_hi | w_lo], + tf32_residual_kernel' if args.conv_impl == 'tc3' else ''),
+                 '; compensated on every layer but uparm_8_0: TF32 chain x_hi w_hi + ONE bf16 chain for x_lo w_hi + x_hi w_lo, '
+                 '+ tf32_split_bf16_kernel' if args.conv_impl == 'tc3' else ''),
              'dgrad_tc': 'conv3d_tc_kernel / conv3d_tc_k2n_kernel / conv3d_tc_up_kernel<2> (data gradient)'}
     achieved = tc[dom][1] / (tc[dom][0] * 1e-3) / 1e12 if dom else 0.       # algorithmic 2*27*Cin*Cout*voxels per launch
     tc_ms = sum(v[0] for v in tc.values())
@@ -393,6 +395,12 @@ def main():
                 'frac_of_tf32_peak': achieved / (peak / 2),
                 'all_tc_convolutions': {'tflops': all_tc, 'frac_of_tf32_peak': all_tc / (peak / 2), 'ms_per_step': tc_ms / 2},
                 'whole_step': {'tflops': step_tf, 'frac_of_tf32_peak': step_tf / (peak / 2)},
+                'executed': {'note': 'tensor-core work actually issued, in TF32-equivalent FLOPs: a compensated forward '
+                                     'convolution runs 2 MMA chains per algorithmic one (the bf16 chain covers twice the K per '
+                                     'instruction), so the hardware utilisation of the forward is this figure, not `achieved`',
+                             'dominant_kind_tflops': executed.get(dom, 0.) / (tc[dom][0] * 1e-3) / 1e12 if dom else 0.,
+                             'dominant_kind_frac_of_tf32_peak': (executed.get(dom, 0.) / (tc[dom][0] * 1e-3) / 1e12) / (peak / 2) if dom else 0.,
+                             'all_tc_tflops': sum(executed.get(k, 0.) for k in tc) / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.},
                 'per_kind': {k: {'ms_per_step': agg[k][0] / 2, 'tflops': agg[k][1] / (agg[k][0] * 1e-3) / 1e12 if agg[k][0] else 0.,
                                  'launches_per_step': agg[k][2] // 2} for k in sorted(agg)},
                 'conv_share_of_step': (sum(v[0] for v in agg.values()) / 2) / (ms / args.steps),

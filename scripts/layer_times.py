@@ -23,7 +23,7 @@ n = len(eng.net.prof) // 3
 rows = {}
 for rep in range(3):
     for j in range(n):
-        kind, fl, a, b = eng.net.prof[rep * n + j]
+        kind, fl, a, b = eng.net.prof[rep * n + j][:4]
         rows.setdefault(j, [kind, fl, 0.])[2] += a.elapsed_time(b) / 3
 tot = {}
 for j in range(n):

@@ -273,14 +273,18 @@ class UNet3D:
     # -------------------------------------------------------------------------------------------------------------
     # convolution dispatch
     # -------------------------------------------------------------------------------------------------------------
-    def _timed(self, kind, l, cin, cout, fn):
+    def _timed(self, kind, l, cin, cout, fn, name=None):
         if self.prof is None:
             return fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
         e1.record()
-        self.prof.append((kind, 2. * self.k ** 3 * cin * cout * self.nvox[l], e0, e1))
+        # 5th entry: MMA chains executed per algorithmic one (compensated forward: 2 in the hybrid scheme, 3 in 3xTF32)
+        mult = 1
+        if name is not None and kind == 'fwd_tc' and self._comp_level(name) == 3:
+            mult = 2 if self.comp_scheme == 'hybrid' else 3
+        self.prof.append((kind, 2. * self.k ** 3 * cin * cout * self.nvox[l], e0, e1, mult))
 
     def _k2n_ok(self, cin, cout):
         return self.fwd_k2n and cin % 8 == 0 and cin <= 32 and cout in (24, 32)
@@ -297,7 +301,7 @@ class UNet3D:
         (only offered by the caller when _k2n_epi_ok)."""
         tc = self.conv_impl == 'tc' and c1 % 8 == 0 and c2 % 8 == 0
         self._timed('fwd_tc' if tc else 'fwd_ref', l, c1 + c2, cout,
-                    lambda: self._conv_fwd_impl(tc, name, x1, c1, x2, c2, y, l, cout, act, stats_sums))
+                    lambda: self._conv_fwd_impl(tc, name, x1, c1, x2, c2, y, l, cout, act, stats_sums), name=name)
 
     def _comp_level(self, name):
         for rx, level in self.comp:
@@ -428,7 +432,7 @@ class UNet3D:
         """decoder convolution 0 of level l on [skip h1[l], upsample(vlow[l])] without the upsampled tensor: the parity
         kernel writes the partial sums of the upsampled part, the skip convolution accumulates + bias + ELU."""
         F = self.feats
-        self._timed('fwd_tc', l, F[l] + F[l + 1], F[l], lambda: self._conv_fwd_up_impl(name, l, act))
+        self._timed('fwd_tc', l, F[l] + F[l + 1], F[l], lambda: self._conv_fwd_up_impl(name, l, act), name=name)
 
     def _conv_fwd_up_impl(self, name, l, act):
         st, F, B = stream_ptr(), self.feats, self.B
