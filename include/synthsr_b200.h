@@ -115,6 +115,11 @@ int ssr_conv3d_fwd_tc_stats(const float* x1, int C1, const float* x2, int C2, co
  * dbias[c] += sum_v dx[v][c]; h = that layer's forward output, Cout = channels of dx */
 int ssr_conv3d_dgrad_tc_elu(const float* dy, int C, const float* wp, const float* h, float* dx, float* dbias, int B, int d0,
                             int d1, int d2, int Cout, void* stream);
+/* Small deep layers run split-K (the chunk list of K cut into parts that add their partial sums into y with red.global.add,
+ * bias + activation in a follow-up pass): ssr_conv3d_fwd_tc / _acc / _comp do this on their own.  The fused-epilogue entry
+ * points (*_stats, *_elu) never split; this query tells a caller which factor the plain entry point would use (1 = none) so
+ * that it can prefer the plain call + separate BatchNorm / ELU' passes there.  comp: 0, or the compensation level. */
+int ssr_conv3d_fwd_tc_ksplit(int C1, int C2, int Cout, int B, int d0, int d1, int d2, int comp);
 /* same, added to the partial result already in y before bias + activation */
 int ssr_conv3d_fwd_tc_acc(const float* x1, int C1, const float* x2, int C2, const float* wp, const float* bias, float* y,
                           int B, int d0, int d1, int d2, int Cout, int act, void* stream);

@@ -276,6 +276,10 @@ struct TcGeom {
   int n1tiles, n2tiles, n0tiles, nNtiles;
   int act;
   int accumulate;    // epilogue adds the partial result already in y (before bias / activation)
+  int ksplit;        // split-K: the chunk list is cut into ksplit contiguous parts, one CTA tile each; the parts add their raw
+                     // partial sums into y with red.global.add (y zeroed or holding earlier partial sums; bias / activation
+                     // in a follow-up pass).  For the deep levels: few voxels, long K -- without it <= 120 CTAs walk serial
+                     // MMA chains of 1300 - 5000 instructions at N = 32
   int pl_pitch;      // PL mode: d2 pitch of the zero-padded plane (D2 + 2); M windows = n2tiles (n1tiles = 1)
   int pl_slab;       // PL mode: bytes of a slab stage (padded plane + over-read slack, multiple of 1024)
   int pl_tx;         // PL mode: bytes one TMA load of a padded plane writes
@@ -305,6 +309,10 @@ __device__ __forceinline__ bool group_needed(const TcGeom& G, int z0, int k0g) {
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 // Column sums over the 32 lanes of a warp of 16 values per lane in 16 shuffles ("transposed" butterfly: every exchange
@@ -400,11 +408,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) DBG_STAMP(1);
-  const int ntiles = G.B * G.n0tiles * G.n1tiles * G.n2tiles * G.nNtiles;
+  const int ntiles = G.B * G.n0tiles * G.n1tiles * G.n2tiles * G.nNtiles * G.ksplit;
   const uint32_t set_cols = (uint32_t)(G.TZ * G.NT);
 
 #define DECODE_TILE(tile)                                                       \
   int t_ = (tile);                                                               \
+  const int kpart = t_ % G.ksplit; t_ /= G.ksplit;                               \
+  const int ch_lo = kpart * G.nchunks / G.ksplit, ch_hi = (kpart + 1) * G.nchunks / G.ksplit; \
   const int nt = t_ % G.nNtiles; t_ /= G.nNtiles;                                \
   const int t2 = t_ % G.n2tiles; t_ /= G.n2tiles;                                \
   const int t1 = t_ % G.n1tiles; t_ /= G.n1tiles;                                \
@@ -412,7 +422,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
   const int b = t_ / G.n0tiles;                                                  \
   const int x0 = t2 * TM2, y0 = t1 * TM1, z0 = t0 * G.TZ, n0 = nt * G.NT;        \
   const int nz = min(G.TZ, G.D0 - z0);                                           \
-  (void)x0; (void)y0; (void)n0; (void)b; (void)nz;
+  (void)x0; (void)y0; (void)n0; (void)b; (void)nz; (void)ch_lo; (void)ch_hi;
 
   // Closed-form slab ranges (identical in the producer and the MMA warp; no per-slab predicate evaluation in the issue
   // loop).  nz = valid output planes of the tile.  For the d0-tap group starting at k0g, slab index zin (input plane
@@ -425,7 +435,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
       long long wait_empty = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         DECODE_TILE(tile)
-        for (int ch = 0; ch < G.nchunks; ++ch) {
+        for (int ch = ch_lo; ch < ch_hi; ++ch) {
           const CUtensorMap* mx = G.chunk_src[ch] ? &map_x2 : &map_x1;
           const int c0 = G.chunk_c0[ch];
           for (int k2 = 0; k2 < 3; ++k2) {
@@ -486,19 +496,22 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
         tc_fence_after();
         uint32_t acc = 0u;                         // first MMA of the tile into this accumulator overwrites
         bool prev_f16 = false;
-        for (int ch = 0; ch < nchunks; ++ch) {
+        for (int ch = ch_lo; ch < ch_hi; ++ch) {
           const int nks = G.chunk_ks[ch];
           const bool f16 = G.chunk_f16[ch] != 0;
           const uint32_t idesc = f16 ? idesc16 : idesc32;
           if (f16 != prev_f16) {
             // tcgen05.mma instructions of DIFFERENT kinds are not ordered against each other: the TF32 MMAs into this
             // accumulator must have completed before the first bf16 MMA reads it (one bubble per tile and warp; the
-            // other MMA warps keep the tensor pipe busy meanwhile)
-            if (elect_one()) umma_commit(kindBar + zo);
-            __syncwarp();
-            mbar_wait(kindBar + zo, kind_phase);
-            kind_phase ^= 1u;
-            tc_fence_after();
+            // other MMA warps keep the tensor pipe busy meanwhile).  Nothing to wait for when this warp has not issued
+            // into the accumulator yet (a split-K part that starts with the bf16 chunks).
+            if (acc != 0u) {
+              if (elect_one()) umma_commit(kindBar + zo);
+              __syncwarp();
+              mbar_wait(kindBar + zo, kind_phase);
+              kind_phase ^= 1u;
+              tc_fence_after();
+            }
             prev_f16 = f16;
           }
           for (int k2 = 0; k2 < 3; ++k2) {
@@ -633,6 +646,17 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
           }
           if (!vox_ok) continue;
           const int nvalid = G.Cout - (n0 + cb);       // channels of this 16-block that exist
+          if (G.ksplit > 1) {                          // split-K part: add the raw partial sums (host: no bias / act / EPI)
+            if (nvalid >= 16 && vec_ok) {
+#pragma unroll
+              for (int e = 0; e < 16; e += 4) red_add_v4(orow + cb + e, o[e], o[e + 1], o[e + 2], o[e + 3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if (e < nvalid) atomicAdd(orow + cb + e, o[e]);
+            }
+            continue;
+          }
           if (nvalid >= 16 && vec_ok) {
 #pragma unroll
             for (int e = 0; e < 16; e += 4)
@@ -1938,10 +1962,6 @@ __device__ __forceinline__ WpSeg wp_segment(long long g, long long g1, long long
   return s;
 }
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 // PAR: weight gradient of the upsampled part of a decoder convolution from the LOW-resolution tensor (see
 // conv3d_tc_up_kernel): the 8 output parity classes are 8x more units; class p reads its own strided view of dy
 // (maps_dy.x[p]), accumulates the gradient of its effective kernel into dw + p * 27 * Cin * Cout (combined into the
@@ -2304,6 +2324,22 @@ mma_microbench_kernel(float* __restrict__ out, int N, int nacc, int chain, int i
   if (warp == 1) tmem_dealloc(tb, 512);
 }
 
+// y[v][c] = act(y[v][c] + bias[c]) in place: the follow-up pass of a split-K convolution (C % 4 == 0)
+__global__ void bias_act_kernel(float* __restrict__ y, const float* __restrict__ bias, long long nvox, int C, int act) {
+  const int c4 = C >> 2;
+  const long long total = nvox * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4) << 2;
+    float4 v = reinterpret_cast<float4*>(y)[i];
+    if (bias) { v.x += bias[c]; v.y += bias[c + 1]; v.z += bias[c + 2]; v.w += bias[c + 3]; }
+    if (act) {
+      v.x = v.x > 0.f ? v.x : __expf(v.x) - 1.f; v.y = v.y > 0.f ? v.y : __expf(v.y) - 1.f;
+      v.z = v.z > 0.f ? v.z : __expf(v.z) - 1.f; v.w = v.w > 0.f ? v.w : __expf(v.w) - 1.f;
+    }
+    reinterpret_cast<float4*>(y)[i] = v;
+  }
+}
+
 __device__ __forceinline__ float tf32_lo(float v) {
   uint32_t u = __float_as_uint(v);
   u = (u + 0xFFFu + ((u >> 13) & 1u)) & ~0x1FFFu;      // round to nearest even on the 13 dropped bits (what the TMA does)
@@ -2612,6 +2648,63 @@ int ssr_conv3d_pack_weights(const float* w, float* wp, int Cin1, int Cin2, int C
   return SSR_OK;
 }
 
+// Tile shape of conv3d_tc_kernel for one layer: G.NT / G.TZ / G.ksplit and the plane-linearised geometry (G.pl_*).
+// Needs G.Npad set.  epi != 0 (fused epilogue requested) excludes split-K.
+static int tc_tile_shape(TcGeom& G, int C1, int C2, int Cout, int B, int D0, int D1, int D2, int epi, int comp) {
+  int ks_total = 0;
+  for (int c = 0; c < C1; c += 32) ks_total += ((C1 - c < 32 ? C1 - c : 32) + 7) / 8;
+  for (int c = 0; c < C2; c += 32) ks_total += ((C2 - c < 32 ? C2 - c : 32) + 7) / 8;
+  if (comp == 3) ks_total = ks_total / 2 * 3;
+  if (comp == 4) ks_total = ks_total / 2 + (2 * C1 + 15) / 16;
+  int n1t = (D1 + TM1 - 1) / TM1, n2t = (D2 + TM2 - 1) / TM2;
+  // plane-linearised tiling for the small deep levels: windows of 128 rows of the padded plane instead of 16 x 8 tiles
+  const int pitch = D2 + 2;
+  const int nwin = ((D1 - 1) * pitch + D2 + 127) / 128;
+  const int pl_slab = round_up((nwin * 128 + 2 * pitch + 2) * 128, 1024);
+  // measured (160^3 net): 10^3 layers 74 vs 80 us with plane tiles; at 20^3 the 71 KB slabs leave only two pipeline
+  // stages and the layers get slower (82 vs 75 us), so plane tiles are used while a slab stays at the 18 x 8 slab's size
+  const int pl_max = getenv("SSR_PLANE_TILES_MAX_KB") ? atoi(getenv("SSR_PLANE_TILES_MAX_KB")) * 1024 : 24 * 1024;
+  if (nwin < n1t * n2t && pl_slab <= pl_max && D1 + 2 <= 256 && pitch <= 256 && !getenv("SSR_NO_PLANE_TILES")) {
+    G.pl_pitch = pitch; G.pl_slab = pl_slab; G.pl_tx = (D1 + 2) * pitch * 128;
+    n1t = 1; n2t = nwin;
+  }
+  // shared-memory fit of an N tile: two B groups (all 9 (k0,k1) taps of a d2 tap when they fit, else 3) + >= 2 slabs
+  const int slab_b = G.pl_pitch > 0 ? G.pl_slab : SLAB_BYTES;
+  const int avail = 227 * 1024 - 1024 - 2816 - (epi ? 2 * 4 * 576 : 0);
+  auto fits = [&](int nt) { return SB * 3 * nt * 128 + 2 * slab_b <= avail; };
+  double best = 1e300;
+  int best_nt = 0, best_tz = 0, best_ks = 1;
+  // split-K candidates: only where the fused epilogues are not requested, the output rows are float4-addressable and
+  // the layer is small (the parts meet in y through atomics: 2 x ksplit passes over y instead of 1)
+  const int nchunks_all = comp == 4 ? (C1 + 31) / 32 + (2 * C1 + 63) / 64 : comp ? comp * ((C1 + 31) / 32)
+                                                                                : (C1 + 31) / 32 + (C2 + 31) / 32;
+  const bool may_split = epi == 0 && Cout % 4 == 0 && !getenv("SSR_NO_SPLIT_K") &&
+                         (long long)B * D0 * D1 * D2 <= 27000;
+  for (int ksp = 1; ksp <= (may_split ? 8 : 1) && ksp <= nchunks_all; ++ksp) {
+    for (int nt = 16; nt <= 192 && nt <= G.Npad; nt += 16) {
+      if (G.Npad % nt || !fits(nt)) continue;
+      for (int tz = 1; tz <= 4 && tz <= D0 && tz * nt <= 256; ++tz) {   // two accumulator sets in 512 TMEM columns
+        const long long tiles = (long long)B * ((D0 + tz - 1) / tz) * n1t * n2t * (G.Npad / nt) * ksp;
+        const long long rounds = (tiles + 147) / 148;
+        // + issue overhead: exposed with a single issuing warp (tz == 1), mostly hidden with one warp per accumulator
+        const double mma = (nt / 2 > 32 + nt / 4 ? nt / 2 : 32 + nt / 4) + (tz == 1 ? 20.0 : 8.0);
+        // slabs are shared by up to 3 output planes: fewer planes per tile = more TMA traffic per MMA (mild penalty)
+        const double ks_part = (double)((ks_total + ksp - 1) / ksp);
+        double cost = rounds * (tz * 27.0 * ks_part * mma * (1.0 + 0.04 * (4 - tz)) + 2500.0);
+        // memset + ksp red.add passes (read-modify-write in L2) + the bias / activation pass over y, at ~3 TB/s of L2
+        // traffic shared by all CTAs (1.9 GHz: 6.5e-4 cycles per byte)
+        if (ksp > 1) cost += 6000.0 + (2.0 * ksp + 3.0) * (double)B * D0 * D1 * D2 * Cout * 4.0 * 6.5e-4;
+        if (cost < best * 0.999 || (cost < best * 1.001 && ksp == best_ks && (tz > best_tz || (tz == best_tz && nt > best_nt)))) {
+          best = cost; best_nt = nt; best_tz = tz; best_ks = ksp;
+        }
+      }
+    }
+  }
+  SSR_CHECK_ARG(best_nt > 0, "no tile shape");
+  G.NT = best_nt; G.TZ = best_tz; G.ksplit = best_ks;
+  return SSR_OK;
+}
+
 // y[B,D0,D1,D2,Cout] = act(conv3x3x3([x1,x2], wp) + bias) ; wp from ssr_conv3d_pack_weights.
 // Used for the data gradient too (x1 = dy, wp packed with mode 1, Cout = layer's Cin, bias NULL, act 0).
 static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, const float* wp, const float* bias, float* y,
@@ -2623,6 +2716,7 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
   // 7; K = [x (TF32) | x2 (bf16)] against [w_hi (TF32) | w_hi ; w_lo (bf16)]: the corrections x_lo w_hi + x_hi w_lo are
   // ~2^-11 of the result, so bf16's 8 bits on their operands leave ~2^-20 -- at twice the K per MMA of TF32
   SSR_CHECK_ARG(comp == 0 || ((comp == 2 || comp == 3 || comp == 4) && x2 && C2 == C1), "compensated forward: x2 = residual of x1");
+  const float* const bias_in = bias;
   SSR_CHECK_ARG(x1 && wp && y && B > 0 && D0 > 0 && D1 > 0 && D2 > 0 && Cout > 0, "pointers/shape");
   SSR_CHECK_ARG(C1 > 0 && C1 % 4 == 0 && C2 >= 0 && C2 % 4 == 0 && (C2 == 0 || x2), "channel counts must be multiples of 4");
   SSR_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0, "channel counts must be multiples of 8 (TF32 K-step)");
@@ -2635,47 +2729,7 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
   // over tiles, so the cost is rounds x per-tile time.  Small layers (40^3 and below) have few tiles: a narrower N tile or
   // fewer planes per tile trades MMA efficiency for SM utilisation.  MMA cost per instruction from the measured
   // max(N/2, 32 + N/4) (+ issue overhead), profiles/r01_mma_issue_microbench.txt.
-  {
-    int ks_total = 0;
-    for (int c = 0; c < C1; c += 32) ks_total += ((C1 - c < 32 ? C1 - c : 32) + 7) / 8;
-    for (int c = 0; c < C2; c += 32) ks_total += ((C2 - c < 32 ? C2 - c : 32) + 7) / 8;
-    if (comp == 3) ks_total = ks_total / 2 * 3;
-    if (comp == 4) ks_total = ks_total / 2 + (2 * C1 + 15) / 16;
-    int n1t = (D1 + TM1 - 1) / TM1, n2t = (D2 + TM2 - 1) / TM2;
-    // plane-linearised tiling for the small deep levels: windows of 128 rows of the padded plane instead of 16 x 8 tiles
-    const int pitch = D2 + 2;
-    const int nwin = ((D1 - 1) * pitch + D2 + 127) / 128;
-    const int pl_slab = round_up((nwin * 128 + 2 * pitch + 2) * 128, 1024);
-    // measured (160^3 net): 10^3 layers 74 vs 80 us with plane tiles; at 20^3 the 71 KB slabs leave only two pipeline
-    // stages and the layers get slower (82 vs 75 us), so plane tiles are used while a slab stays at the 18 x 8 slab's size
-    const int pl_max = getenv("SSR_PLANE_TILES_MAX_KB") ? atoi(getenv("SSR_PLANE_TILES_MAX_KB")) * 1024 : 24 * 1024;
-    if (nwin < n1t * n2t && pl_slab <= pl_max && D1 + 2 <= 256 && pitch <= 256 && !getenv("SSR_NO_PLANE_TILES")) {
-      G.pl_pitch = pitch; G.pl_slab = pl_slab; G.pl_tx = (D1 + 2) * pitch * 128;
-      n1t = 1; n2t = nwin;
-    }
-    // shared-memory fit of an N tile: two B groups (all 9 (k0,k1) taps of a d2 tap when they fit, else 3) + >= 2 slabs
-    const int slab_b = G.pl_pitch > 0 ? G.pl_slab : SLAB_BYTES;
-    const int avail = 227 * 1024 - 1024 - 2816 - (epi ? 2 * 4 * 576 : 0);
-    auto fits = [&](int nt) { return SB * 3 * nt * 128 + 2 * slab_b <= avail; };
-    double best = 1e300;
-    int best_nt = 0, best_tz = 0;
-    for (int nt = 16; nt <= 192 && nt <= G.Npad; nt += 16) {
-      if (G.Npad % nt || !fits(nt)) continue;
-      for (int tz = 1; tz <= 4 && tz <= D0 && tz * nt <= 256; ++tz) {   // two accumulator sets in 512 TMEM columns
-        const long long tiles = (long long)B * ((D0 + tz - 1) / tz) * n1t * n2t * (G.Npad / nt);
-        const long long rounds = (tiles + 147) / 148;
-        // + issue overhead: exposed with a single issuing warp (tz == 1), mostly hidden with one warp per accumulator
-        const double mma = (nt / 2 > 32 + nt / 4 ? nt / 2 : 32 + nt / 4) + (tz == 1 ? 20.0 : 8.0);
-        // slabs are shared by up to 3 output planes: fewer planes per tile = more TMA traffic per MMA (mild penalty)
-        const double cost = rounds * (tz * 27.0 * ks_total * mma * (1.0 + 0.04 * (4 - tz)) + 2500.0);
-        if (cost < best * 0.999 || (cost < best * 1.001 && (tz > best_tz || (tz == best_tz && nt > best_nt)))) {
-          best = cost; best_nt = nt; best_tz = tz;
-        }
-      }
-    }
-    SSR_CHECK_ARG(best_nt > 0, "no tile shape");
-    G.NT = best_nt; G.TZ = best_tz;
-  }
+  { const int rc_shape = tc_tile_shape(G, C1, C2, Cout, B, D0, D1, D2, epi, comp); if (rc_shape) return rc_shape; }
   G.nNtiles = G.Npad / G.NT;
   G.KG = (3 * 3 * G.NT * 128 <= 74 * 1024) ? 3 : 1;
   if (G.pl_pitch > 0 && SB * 9 * G.NT * 128 + 2 * G.pl_slab > 227 * 1024 - 1024 - 2816 - (epi ? 2 * 4 * 576 : 0)) G.KG = 1;
@@ -2753,7 +2807,7 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
     SSR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const long long ntiles = (long long)B * G.n0tiles * G.n1tiles * G.n2tiles * G.nNtiles;
+  const long long ntiles = (long long)B * G.n0tiles * G.n1tiles * G.n2tiles * G.nNtiles * G.ksplit;
   SSR_CHECK_ARG(ntiles < (1LL << 31) && G.Npad <= 576, "grid / channel count too large");
   static int num_sms = 0;
   if (!num_sms) {
@@ -2765,6 +2819,15 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
   // TMA + TZ MMA + 4 epilogue warps
   const unsigned nthr = 32 * (5 + G.TZ);
   cudaStream_t cst = (cudaStream_t)stream;
+  const float* kbias = bias;
+  if (G.ksplit > 1) {
+    // split-K: the parts add raw partial sums into y (zeroed here unless it already holds the earlier channel parts);
+    // bias + activation follow in bias_act_kernel
+    const long long nvox = (long long)B * D0 * D1 * D2;
+    if (!accumulate) SSR_CHECK_CUDA(cudaMemsetAsync(y, 0, (size_t)nvox * Cout * sizeof(float), cst));
+    G.act = 0; G.accumulate = 0; kbias = nullptr;
+  }
+  bias = kbias;
   if (pl) {
     if (epi == 1) conv3d_tc_kernel<1, true><<<grid, nthr, smem, cst>>>(m1, m2, mw, bias, y, G, elu_h, dbias, sums);
     else if (epi == 2) conv3d_tc_kernel<2, true><<<grid, nthr, smem, cst>>>(m1, m2, mw, bias, y, G, elu_h, dbias, sums);
@@ -2775,8 +2838,26 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
     else conv3d_tc_kernel<0, false><<<grid, nthr, smem, cst>>>(m1, m2, mw, bias, y, G, nullptr, nullptr, nullptr);
   }
   SSR_COUNT_LAUNCH();
+  if (G.ksplit > 1 && (bias_in || act)) {
+    const long long n4 = (long long)B * D0 * D1 * D2 * (Cout / 4);
+    long long g = (n4 + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    bias_act_kernel<<<(unsigned)g, 256, 0, cst>>>(y, bias_in, (long long)B * D0 * D1 * D2, Cout, act);
+    SSR_COUNT_LAUNCH();
+  }
   SSR_CHECK_LAUNCH();
   return SSR_OK;
+}
+
+// split-K factor conv3d_fwd_tc_impl would pick for this shape without fused epilogues (1 = none): callers that would ask
+// for a fused epilogue (BatchNorm sums, ELU') use the separate passes instead where this is > 1
+int ssr_conv3d_fwd_tc_ksplit(int C1, int C2, int Cout, int B, int D0, int D1, int D2, int comp) {
+  SSR_CHECK_ARG(C1 > 0 && C2 >= 0 && Cout > 0 && B > 0 && D0 > 0 && D1 > 0 && D2 > 0, "shape");
+  TcGeom G;
+  memset(&G, 0, sizeof(G));
+  G.Npad = round_up(Cout, 16);
+  const int rc = tc_tile_shape(G, C1, comp ? C1 : C2, Cout, B, D0, D1, D2, 0, comp);
+  return rc ? rc : G.ksplit;
 }
 
 int ssr_conv3d_fwd_tc(const float* x1, int C1, const float* x2, int C2, const float* wp, const float* bias, float* y,

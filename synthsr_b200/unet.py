@@ -90,6 +90,7 @@ class UNet3D:
             self.comp = [(re.compile(r.rsplit(':', 1)[0]), int(r.rsplit(':', 1)[1])) for r in os.environ['SSR_COMP'].split(',')]
         self._lo = None                 # scratch for the TF32 residual x_lo of the convolution being run (stream ordered)
         self._lo_src = None             # (data_ptr, nvox, channels) of the tensor whose bf16 split _lo currently holds
+        self._ksplit_cache = {}
         # 'hybrid' (default): x_hi w_hi in TF32 + the two correction terms as one bf16 MMA chain (2 chains per convolution);
         # 'tf32x3': all three terms in TF32 (3 chains) -- the first implementation, kept as a cross-check
         self.comp_scheme = os.environ.get('SSR_COMP_SCHEME', 'hybrid')
@@ -289,12 +290,30 @@ class UNet3D:
     def _k2n_ok(self, cin, cout):
         return self.fwd_k2n and cin % 8 == 0 and cin <= 32 and cout in (24, 32)
 
-    def _k2n_epi_ok(self, cin, cout):
+    def _ksplit(self, l, cin, cout, comp):
+        """split-K factor the generic kernel picks for a cin -> cout convolution at level l without fused epilogues"""
+        key = (l, cin, cout, comp)
+        if key not in self._ksplit_cache:
+            self._ksplit_cache[key] = lib.ssr_conv3d_fwd_tc_ksplit(cin, 0, cout, self.B, *self.ldims[l], comp)
+        return self._ksplit_cache[key]
+
+    def _k2n_epi_ok(self, cin, cout, l=None, name=None):
         """BN sums / ELU backward + bias gradient inside the convolution epilogue: k2n kernel for the 24 / 32-channel
-        layers, generic kernel (conv3d_tc_kernel<EPI>) for the others."""
+        layers, generic kernel (conv3d_tc_kernel<EPI>) for the others -- except on the small deep levels, where the plain
+        entry point runs split-K (much faster there) and the BatchNorm sums / ELU' run as their own small passes.
+        l: level of the layer; name: the forward layer (its compensation decides the K length), None for a data gradient."""
         if not (self.conv_impl == 'tc' and self.epi_fusion and cin % 8 == 0 and cout % 8 == 0):
             return False
-        return self._k2n_ok(cin, cout) or (self.epi_fusion_generic and not (cin <= 32 and cout <= 32))
+        if self._k2n_ok(cin, cout):
+            return True
+        if not (self.epi_fusion_generic and not (cin <= 32 and cout <= 32)):
+            return False
+        if l is not None:
+            comp = 4 if (name is not None and self._comp_level(name) == 3 and self.comp_scheme == 'hybrid') else \
+                (3 if name is not None and self._comp_level(name) else 0)
+            if self._ksplit(l, cin, cout, comp) > 1:
+                return False
+        return True
 
     def _conv_fwd(self, name, x1, c1, x2, c2, y, l, cout, act=1, stats_sums=None):
         """stats_sums (2*cout doubles): the convolution also accumulates the BatchNorm sums of its output in its epilogue
@@ -692,7 +711,7 @@ class UNet3D:
             else:
                 self._conv_fwd('unet_conv_downarm_%d_0' % l, x, cx, None, 0, self.h0[l], l, F[l])
             bn = 'unet_bn_down_%d' % l
-            fused = training and self._k2n_epi_ok(F[l], F[l])
+            fused = training and self._k2n_epi_ok(F[l], F[l], l, 'unet_conv_downarm_%d_1' % l)
             self._conv_fwd('unet_conv_downarm_%d_1' % l, self.h0[l], F[l], None, 0, self.h1[l], l, F[l],
                            stats_sums=self.sums if fused else None)
             self._bn_stats(bn, self.h1[l], self.nvox[l], F[l], self.stats_enc[l], training, have_sums=fused)
@@ -710,7 +729,7 @@ class UNet3D:
             else:
                 lib.ssr_bn_apply(prev, self._u(l), prev_stats, B, *self.ldims[prev_l], F[prev_l], 2, 0, 0, st)
                 self._conv_fwd('unet_conv_uparm_%d_0' % (L + d), self.h1[l], F[l], self.u[l], F[l + 1], self.g0[l], l, F[l])
-            fused = training and self._k2n_epi_ok(F[l], F[l])
+            fused = training and self._k2n_epi_ok(F[l], F[l], l, 'unet_conv_uparm_%d_1' % (L + d))
             self._conv_fwd('unet_conv_uparm_%d_1' % (L + d), self.g0[l], F[l], None, 0, self.g1[l], l, F[l],
                            stats_sums=self.sums if fused else None)
             self._bn_stats('unet_bn_up_%d' % d, self.g1[l], self.nvox[l], F[l], self.stats_dec[l], training,
@@ -829,7 +848,7 @@ class UNet3D:
                     lib.ssr_bn_bwd(self.dbn_dec[l], self.g1[l], self.stats_dec[l], self.nvox[l], F[l], None, 0, 0, 1,
                                    self.ga[l], self.g[bn + '/gamma'], self.g[bn + '/beta'], self.g[c1n + '/bias'], self.sums, st)
                 self._wgrad_async(c1n, self.g0[l], F[l], None, 0, self.ga[l], l, F[l])
-                if self._k2n_epi_ok(F[l], F[l]):
+                if self._k2n_epi_ok(F[l], F[l], l):
                     self._conv_dgrad(c1n, self.ga[l], self.gb[l], l, F[l], F[l], elu_h=self.g0[l], dbias=self.g[c0 + '/bias'])
                 else:
                     self._conv_dgrad(c1n, self.ga[l], self.gb[l], l, F[l], F[l])
@@ -863,7 +882,7 @@ class UNet3D:
                                    add_stride, 0, 1, self.ga_e[l], self.g[bn + '/gamma'], self.g[bn + '/beta'],
                                    self.g[c1n + '/bias'], self.sums, st)
                 self._wgrad_async(c1n, self.h0[l], F[l], None, 0, self.ga_e[l], l, F[l])
-                if self._k2n_epi_ok(F[l], F[l]):
+                if self._k2n_epi_ok(F[l], F[l], l):
                     self._conv_dgrad(c1n, self.ga_e[l], self.gb_e[l], l, F[l], F[l], elu_h=self.h0[l],
                                      dbias=self.g[c0 + '/bias'])
                 else:
