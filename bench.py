@@ -351,6 +351,9 @@ def main():
         eng.train_step(dev_maps[i % len(dev_maps)], *draw_gmm(rng, pm, ps, gc, n_ch))
     torch.cuda.synchronize()
     agg, executed = {}, {}
+    if os.environ.get('SSR_BENCH_DUMP_PROF'):
+        for j, (kind, fl, a, b, mult) in enumerate(eng.net.prof):
+            print('prof %3d %-9s %8.3f ms  x%d' % (j, kind, a.elapsed_time(b), mult), file=sys.stderr)
     for kind, fl, a, b, mult in eng.net.prof:
         t, f, n = agg.get(kind, (0., 0., 0))
         agg[kind] = (t + a.elapsed_time(b), f + fl, n + 1)

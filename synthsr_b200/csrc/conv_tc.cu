@@ -2691,6 +2691,15 @@ static int tc_tile_shape(TcGeom& G, int C1, int C2, int Cout, int B, int D0, int
         // slabs are shared by up to 3 output planes: fewer planes per tile = more TMA traffic per MMA (mild penalty)
         const double ks_part = (double)((ks_total + ksp - 1) / ksp);
         double cost = rounds * (tz * 27.0 * ks_part * mma * (1.0 + 0.04 * (4 - tz)) + 2500.0);
+        if (may_split) {
+          // L2 -> shared-memory traffic of the whole launch: every tile streams its weight slice (27 taps x K x nt x 4 B)
+          // and its activation slabs.  With <= 148 single-plane tiles THIS bounds the 20^3 / 10^3 levels, not the MMA
+          // chain: 192 -> 192 at 20^3 moved 480 MB in 82 us (5.9 TB/s of L2 bandwidth) for 39 us of MMAs.  More planes
+          // per tile (tz) share the weights; split-K restores the CTA count.
+          const double l2_bytes = (double)tiles * (27.0 * ks_part * 8.0 * nt * 4.0 + (ks_part / 4.0) * 3.0 * (tz + 2) * slab_b);
+          const double l2_cycles = l2_bytes / 3000.0 + 2500.0;          // ~5.7 TB/s at 1.9 GHz
+          if (l2_cycles > cost) cost = l2_cycles;
+        }
         // memset + ksp red.add passes (read-modify-write in L2) + the bias / activation pass over y, at ~3 TB/s of L2
         // traffic shared by all CTAs (1.9 GHz: 6.5e-4 cycles per byte)
         if (ksp > 1) cost += 6000.0 + (2.0 * ksp + 3.0) * (double)B * D0 * D1 * D2 * Cout * 4.0 * 6.5e-4;
