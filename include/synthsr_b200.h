@@ -180,6 +180,12 @@ int ssr_conv3d_fwd_tc_up_comp(const float* low, const float* lowlo, int Cup, con
 int ssr_tf32_split_bf16(const float* x, void* x2, long long nvox, int C, void* stream);
 int ssr_conv3d_fwd_tc_k2n_bf16(const void* x2, int C2, const float* wp, const float* bias, float* y, double* sums, int B,
                                int d0, int d1, int d2, int Cout, int act, void* stream);
+/* bf16x3 scheme (level 5; generic and parity kernels): every term in bf16.  x = x1 + x2 (+ 2^-18), w = w1 + w2 (+ 2^-18)
+ * with 8-bit pieces; the convolution is x1 w1 + x2 w1 + x1 w2 -- three bf16 K-chunks per 64 input channels = 1.5 TF32
+ * chains (the hybrid scheme runs 2), the dropped terms are ~2^-17 of a product.  x2 / lowlo of the *_comp entry points is
+ * ssr_bf16x3_split's [x1 | x2] (2C bf16 channels per voxel); the weights are pack mode 9 (w1 chunks, then w2 chunks; Cin1 /
+ * Cin2 as in mode 5). */
+int ssr_bf16x3_split(const float* x, void* x2, long long nvox, int C, void* stream);
 /* producers that emit the next layer's x2 from their own epilogue (bit-identical to ssr_tf32_split_bf16 of their output,
  * without the extra pass): the first layer (KL.Conv3D with Cin <= 2) and the final k2n channel part */
 int ssr_conv3d_first_fwd_split(const float* x, int C1, const float* w, const float* bias, float* y, void* y2, int B, int d0,

@@ -2358,7 +2358,9 @@ __global__ void tf32_residual_kernel(const float* __restrict__ x, float* __restr
 
 // x2[v][0:C] = bf16(x - rne_tf32(x)),  x2[v][C:2C] = bf16(rne_tf32(x)): the two operands of the bf16 correction term of
 // the compensated forward, written as ONE 2C-channel bf16 tensor (same bytes per voxel as C fp32 channels)
-__global__ void tf32_split_bf16_kernel(const float* __restrict__ x, uint16_t* __restrict__ x2, long long nvox, int C) {
+// bf16x3 (mode 1): x2[v][0:C] = x1 = bf16(x),  x2[v][C:2C] = bf16(x - x1): the operands of x1 w1 + x2 w1 + x1 w2
+__global__ void tf32_split_bf16_kernel(const float* __restrict__ x, uint16_t* __restrict__ x2, long long nvox, int C,
+                                       int mode) {
   const int c4 = C >> 2;                                      // C % 4 == 0 (host-checked)
   const long long total = nvox * c4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -2369,6 +2371,12 @@ __global__ void tf32_split_bf16_kernel(const float* __restrict__ x, uint16_t* __
     uint32_t lo[4], hi[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
+      if (mode == 1) {
+        const uint32_t b1 = bf16_bits(in[e]);
+        lo[e] = b1;                                              // first half of the row: x1
+        hi[e] = bf16_bits(in[e] - __uint_as_float(b1 << 16));    // second half: x2 (the subtraction is exact)
+        continue;
+      }
       uint32_t u = __float_as_uint(in[e]);
       u = (u + 0xFFFu + ((u >> 13) & 1u)) & ~0x1FFFu;
       const float h = __uint_as_float(u);
@@ -2388,9 +2396,9 @@ __global__ void tf32_split_bf16_kernel(const float* __restrict__ x, uint16_t* __
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pack_weights_body(const float* __restrict__ w, float* __restrict__ wp, int C1, int C2,
                                                   int Cout, int mode, int Npad, int nchunks, int nch1, int round_rn) {
-  const bool k2n_layout = mode >= 2 && mode != 5 && mode != 7;
+  const bool k2n_layout = mode >= 2 && mode != 5 && mode != 7 && mode != 9;
   const long long total = k2n_layout ? 9LL * 96 * 32 : (long long)nchunks * 27 * Npad * 32;
-  const int Cin = (mode == 5 || mode == 7) ? C1 : C1 + C2;
+  const int Cin = (mode == 5 || mode == 7 || mode == 9) ? C1 : C1 + C2;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int s = (int)(t & 31);
     long long r = t >> 5;
@@ -2416,6 +2424,26 @@ __device__ __forceinline__ void pack_weights_body(const float* __restrict__ w, f
           v = kk < cn ? __uint_as_float(u) : wv - __uint_as_float(u);
         }
         pair |= bf16_bits(v) << (16 * e);
+      }
+      wp[t] = __uint_as_float(pair);
+      continue;
+    }
+    if (mode == 9) {
+      // bf16x3 compensated forward: 64-channel bf16 chunks (two bf16 per float slot) of the input channels [coff, coff + cn)
+      // of a (27, C1, Cout) kernel; chunks [0, nch1) hold w1 = bf16(w), chunks [nch1, 2 nch1) hold w2 = bf16(w - w1).
+      // Rows past cn are zero (a partial chunk of x1 reads on into the x2 half of the activation row).
+      const int coff = C2 >> 12, cn = C2 & 4095;
+      const bool second = ch >= nch1;
+      uint32_t pair = 0;
+      for (int e = 0; e < 2; ++e) {
+        const int cl = (second ? ch - nch1 : ch) * 64 + 2 * s + e;
+        uint32_t bits = 0;
+        if (cl < cn && n < Cout) {
+          const float wv = w[((long long)((k0 * 3 + k1) * 3 + k2) * C1 + coff + cl) * Cout + n];
+          const uint32_t b1 = bf16_bits(wv);
+          bits = second ? bf16_bits(wv - __uint_as_float(b1 << 16)) : b1;
+        }
+        pair |= bits << (16 * e);
       }
       wp[t] = __uint_as_float(pair);
       continue;
@@ -2497,6 +2525,7 @@ __global__ void pack_weights_batch_kernel(const long long* __restrict__ jobs, in
   int Npad, nch, nch1;
   if (mode == 5) { Npad = (Cout + 15) / 16 * 16; nch1 = ((C2 & 4095) + 31) / 32; nch = 2 * nch1; }
   else if (mode == 7) { Npad = (Cout + 15) / 16 * 16; nch1 = ((C2 & 4095) + 31) / 32; nch = nch1 + (2 * (C2 & 4095) + 63) / 64; }
+  else if (mode == 9) { Npad = (Cout + 15) / 16 * 16; nch1 = ((C2 & 4095) + 63) / 64; nch = 2 * nch1; }
   else if (mode >= 2) { Npad = 96; nch = 1; nch1 = 1; }
   else if (mode == 0) { Npad = (Cout + 15) / 16 * 16; nch1 = (C1 + 31) / 32; nch = nch1 + (C2 + 31) / 32; }
   else { Npad = (C1 + C2 + 15) / 16 * 16; nch = (Cout + 31) / 32; nch1 = nch; }
@@ -2616,6 +2645,7 @@ int ssr_conv3d_pack_weights_batch(const long long* jobs, int njobs, void* stream
 long long ssr_conv3d_packed_size(int Cin1, int Cin2, int Cout, int mode) {
   if (mode == 5) return 2LL * (((Cin2 & 4095) + 31) / 32) * 27 * round_up(Cout, 16) * 32;
   if (mode == 7) return (long long)(((Cin2 & 4095) + 31) / 32 + (2 * (Cin2 & 4095) + 63) / 64) * 27 * round_up(Cout, 16) * 32;
+  if (mode == 9) return 2LL * (((Cin2 & 4095) + 63) / 64) * 27 * round_up(Cout, 16) * 32;
   if (mode >= 2) return 9LL * 96 * 32;
   if (mode == 0) {
     const int nch = (Cin1 + 31) / 32 + (Cin2 + 31) / 32;
@@ -2626,19 +2656,20 @@ long long ssr_conv3d_packed_size(int Cin1, int Cin2, int Cout, int mode) {
 }
 
 int ssr_conv3d_pack_weights(const float* w, float* wp, int Cin1, int Cin2, int Cout, int mode, void* stream) {
-  SSR_CHECK_ARG(w && wp && Cin1 > 0 && Cin2 >= 0 && Cout > 0 && mode >= 0 && mode <= 8, "pack args");
-  SSR_CHECK_ARG(mode < 2 || mode == 4 || mode == 5 || mode == 7 || (Cin2 == 0 && Cin1 <= 32 && Cout <= 32), "k2n packing needs Cin <= 32, Cout <= 32");
-  SSR_CHECK_ARG((mode != 5 && mode != 7) || ((Cin2 & 4095) > 0 && (Cin2 >> 12) + (Cin2 & 4095) <= Cin1),
+  SSR_CHECK_ARG(w && wp && Cin1 > 0 && Cin2 >= 0 && Cout > 0 && mode >= 0 && mode <= 9, "pack args");
+  SSR_CHECK_ARG(mode < 2 || mode == 4 || mode == 5 || mode == 7 || mode == 9 || (Cin2 == 0 && Cin1 <= 32 && Cout <= 32), "k2n packing needs Cin <= 32, Cout <= 32");
+  SSR_CHECK_ARG((mode != 5 && mode != 7 && mode != 9) || ((Cin2 & 4095) > 0 && (Cin2 >> 12) + (Cin2 & 4095) <= Cin1),
                 "hi/lo packing: Cin1 = total input channels, Cin2 = (first channel << 12) | channels");
   SSR_CHECK_ARG(mode != 4 || ((Cin2 & 255) <= 32 && (Cin2 >> 8) + (Cin2 & 255) <= Cin1 && Cout <= 32),
                 "part packing: Cin1 = total input channels, Cin2 = (first channel << 8) | channels (<= 32)");
   int Npad, nch, nch1;
   if (mode == 5) { Npad = round_up(Cout, 16); nch1 = ((Cin2 & 4095) + 31) / 32; nch = 2 * nch1; }
   else if (mode == 7) { Npad = round_up(Cout, 16); nch1 = ((Cin2 & 4095) + 31) / 32; nch = nch1 + (2 * (Cin2 & 4095) + 63) / 64; }
+  else if (mode == 9) { Npad = round_up(Cout, 16); nch1 = ((Cin2 & 4095) + 63) / 64; nch = 2 * nch1; }
   else if (mode >= 2) { Npad = 96; nch = 1; nch1 = 1; }
   else if (mode == 0) { Npad = round_up(Cout, 16); nch1 = (Cin1 + 31) / 32; nch = nch1 + (Cin2 + 31) / 32; }
   else { Npad = round_up(Cin1 + Cin2, 16); nch = (Cout + 31) / 32; nch1 = nch; }
-  const long long total = (mode >= 2 && mode != 5 && mode != 7) ? 9LL * 96 * 32 : (long long)nch * 27 * Npad * 32;
+  const long long total = (mode >= 2 && mode != 5 && mode != 7 && mode != 9) ? 9LL * 96 * 32 : (long long)nch * 27 * Npad * 32;
   long long g = (total + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
   pack_weights_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(w, wp, Cin1, Cin2, Cout, mode, Npad, nch, nch1,
@@ -2656,6 +2687,7 @@ static int tc_tile_shape(TcGeom& G, int C1, int C2, int Cout, int B, int D0, int
   for (int c = 0; c < C2; c += 32) ks_total += ((C2 - c < 32 ? C2 - c : 32) + 7) / 8;
   if (comp == 3) ks_total = ks_total / 2 * 3;
   if (comp == 4) ks_total = ks_total / 2 + (2 * C1 + 15) / 16;
+  if (comp == 5) { ks_total = 0; for (int c = 0; c < C1; c += 64) ks_total += 3 * (((C1 - c < 64 ? C1 - c : 64) + 15) / 16); }
   int n1t = (D1 + TM1 - 1) / TM1, n2t = (D2 + TM2 - 1) / TM2;
   // plane-linearised tiling for the small deep levels: windows of 128 rows of the padded plane instead of 16 x 8 tiles
   const int pitch = D2 + 2;
@@ -2676,7 +2708,7 @@ static int tc_tile_shape(TcGeom& G, int C1, int C2, int Cout, int B, int D0, int
   int best_nt = 0, best_tz = 0, best_ks = 1;
   // split-K candidates: only where the fused epilogues are not requested, the output rows are float4-addressable and
   // the layer is small (the parts meet in y through atomics: 2 x ksplit passes over y instead of 1)
-  const int nchunks_all = comp == 4 ? (C1 + 31) / 32 + (2 * C1 + 63) / 64 : comp ? comp * ((C1 + 31) / 32)
+  const int nchunks_all = comp == 5 ? 3 * ((C1 + 63) / 64) : comp == 4 ? (C1 + 31) / 32 + (2 * C1 + 63) / 64 : comp ? comp * ((C1 + 31) / 32)
                                                                                 : (C1 + 31) / 32 + (C2 + 31) / 32;
   const bool may_split = epi == 0 && Cout % 4 == 0 && !getenv("SSR_NO_SPLIT_K") &&
                          (long long)B * D0 * D1 * D2 <= 27000;
@@ -2724,7 +2756,9 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
   // comp == 4 (hybrid, 2 MMA chains instead of 3): x2 = [x_lo | x_hi] as 2 C1 bf16 channels (ssr_tf32_split_bf16), wp = pack mode
   // 7; K = [x (TF32) | x2 (bf16)] against [w_hi (TF32) | w_hi ; w_lo (bf16)]: the corrections x_lo w_hi + x_hi w_lo are
   // ~2^-11 of the result, so bf16's 8 bits on their operands leave ~2^-20 -- at twice the K per MMA of TF32
-  SSR_CHECK_ARG(comp == 0 || ((comp == 2 || comp == 3 || comp == 4) && x2 && C2 == C1), "compensated forward: x2 = residual of x1");
+  // comp == 5 (bf16x3, 1.5 chains): x2 = [x1 | x2] as 2 C1 bf16 channels (ssr_bf16x3_split), wp = pack mode 9; three bf16 terms
+  // x1 w1 + x2 w1 + x1 w2 per 64-channel chunk -- what is dropped (x2 w2 and the third bf16 pieces) is ~2^-17 of a product
+  SSR_CHECK_ARG(comp == 0 || ((comp >= 2 && comp <= 5) && x2 && C2 == C1), "compensated forward: x2 = residual of x1");
   const float* const bias_in = bias;
   SSR_CHECK_ARG(x1 && wp && y && B > 0 && D0 > 0 && D1 > 0 && D2 > 0 && Cout > 0, "pointers/shape");
   SSR_CHECK_ARG(C1 > 0 && C1 % 4 == 0 && C2 >= 0 && C2 % 4 == 0 && (C2 == 0 || x2), "channel counts must be multiples of 4");
@@ -2746,7 +2780,18 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
   while (pc < cols) pc <<= 1;
   G.tmem_cols = pc;
   int nch = 0, nwch = 0;                       // chunks of K, chunks of the packed weights
-  if (comp == 4) {
+  if (comp == 5) {
+    const int nchb = (C1 + 63) / 64;
+    for (int term = 0; term < 3; ++term)
+      for (int j = 0; j < nchb; ++j) {
+        SSR_CHECK_ARG(nch < MAX_CHUNKS, "too many input channels");
+        const int left = C1 - 64 * j;
+        G.chunk_src[nch] = 1; G.chunk_c0[nch] = (short)((term == 1 ? C1 : 0) + 64 * j);
+        G.chunk_ks[nch] = (unsigned char)(((left < 64 ? left : 64) + 15) / 16);
+        G.chunk_w[nch] = (unsigned char)((term == 2 ? nchb : 0) + j); G.chunk_f16[nch] = 1; ++nch;
+      }
+    nwch = 2 * nchb;
+  } else if (comp == 4) {
     const int nchc = (C1 + 31) / 32, nch2 = (2 * C1 + 63) / 64;
     for (int c = 0; c < C1; c += 32) {
       G.chunk_src[nch] = 0; G.chunk_c0[nch] = (short)c; G.chunk_ks[nch] = (unsigned char)(((C1 - c < 32 ? C1 - c : 32) + 7) / 8);
@@ -2801,7 +2846,7 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
   const int bx1 = pl ? D1 + 2 : TM1 + 2, bx2 = pl ? G.pl_pitch : TM2;        // TMA box: whole padded plane / 18 x 8 slab
   int rc = make_map_act(&m1, x1, C1, B, D0, D1, D2, bx1, CU_TENSOR_MAP_SWIZZLE_128B, bx2);
   if (rc) return rc;
-  if (comp == 4) { rc = make_map_act16(&m2, x2, 2 * C1, B, D0, D1, D2, bx1, bx2); if (rc) return rc; }
+  if (comp == 4 || comp == 5) { rc = make_map_act16(&m2, x2, 2 * C1, B, D0, D1, D2, bx1, bx2); if (rc) return rc; }
   else if (C2 > 0) { rc = make_map_act(&m2, x2, C2, B, D0, D1, D2, bx1, CU_TENSOR_MAP_SWIZZLE_128B, bx2); if (rc) return rc; } else m2 = m1;
   rc = make_map_w(&mw, wp, (long long)nwch * 27 * G.Npad, G.NT);
   if (rc) return rc;
@@ -2903,7 +2948,7 @@ int ssr_conv3d_dgrad_tc_elu(const float* dy, int C, const float* wp, const float
 int ssr_conv3d_fwd_tc_comp(const float* x, const float* xlo, int C, const float* wp, const float* bias, float* y,
                            double* sums, int B, int D0, int D1, int D2, int Cout, int act, int accumulate, int level,
                            void* stream) {
-  SSR_CHECK_ARG(level == 2 || level == 3 || level == 4, "compensation level must be 2, 3 or 4 (hybrid TF32 + bf16)");
+  SSR_CHECK_ARG(level >= 2 && level <= 5, "compensation level must be 2, 3, 4 (hybrid TF32 + bf16) or 5 (bf16x3)");
   SSR_CHECK_ARG(!(sums && accumulate), "BatchNorm sums do not combine with accumulate");
   if (sums) SSR_CHECK_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)Cout * sizeof(double), (cudaStream_t)stream));
   return conv3d_fwd_tc_impl(x, C, xlo, C, wp, bias, y, B, D0, D1, D2, Cout, act, accumulate, stream, sums ? 2 : 0, nullptr,
@@ -2953,8 +2998,9 @@ static int conv3d_tc_up_impl(int mode, const float* x, int C, const float* wp8, 
                              int Cout, void* stream, const float* xlo = nullptr, int comp = 0) {
   // comp (mode 1 only): compensated forward, see ssr_conv3d_fwd_tc_comp; wp8 = 8 parity classes x hi/lo packing (mode 5)
   SSR_CHECK_ARG(x && wp8 && y && B > 0 && D0 > 0 && D1 > 0 && D2 > 0 && Cout > 0, "pointers/shape");
-  SSR_CHECK_ARG(comp == 0 || (mode == 1 && xlo && (comp == 2 || comp == 3 || comp == 4)), "compensated parity forward args");
-  SSR_CHECK_ARG(C > 0 && C % 8 == 0 && (C + 31) / 32 * (comp == 4 ? 2 : comp ? comp : 1) <= UP_MAX_CHUNKS,
+  SSR_CHECK_ARG(comp == 0 || (mode == 1 && xlo && comp >= 2 && comp <= 5), "compensated parity forward args");
+  SSR_CHECK_ARG(C > 0 && C % 8 == 0 &&
+                    (comp == 5 ? 3 * ((C + 63) / 64) : (C + 31) / 32 * (comp == 4 ? 2 : comp ? comp : 1)) <= UP_MAX_CHUNKS,
                 "channel count must be a multiple of 8 (<= 768; <= 256 compensated)");
   SSR_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp8 & 127) == 0 && ((uintptr_t)xlo & 15) == 0, "alignment");
   UpGeom G;
@@ -2963,7 +3009,7 @@ static int conv3d_tc_up_impl(int mode, const float* x, int C, const float* wp8, 
   G.Npad = round_up(Cout, 16);
   int ks_total = 0, nch = 0;
   const int nchc = (C + 31) / 32;
-  for (int term = 0; term < (comp == 4 ? 1 : comp ? comp : 1); ++term)
+  for (int term = 0; term < (comp == 5 ? 0 : comp == 4 ? 1 : comp ? comp : 1); ++term)
     for (int c = 0; c < C; c += 32) {
       G.chunk_c0[nch] = (short)c; G.chunk_ks[nch] = (unsigned char)(((C - c < 32 ? C - c : 32) + 7) / 8);
       G.chunk_src[nch] = (unsigned char)(term == 1); G.chunk_w[nch] = (unsigned char)((term == 2 ? nchc : 0) + c / 32);
@@ -2979,6 +3025,17 @@ static int conv3d_tc_up_impl(int mode, const float* x, int C, const float* wp8, 
       ks_total += G.chunk_ks[nch]; ++nch;
     }
     nwch = nchc + nch2;
+  }
+  if (comp == 5) {                                  // bf16x3: [x1 | x2 | x1] against [w1 ; w1 ; w2], all bf16
+    const int nchb = (C + 63) / 64;
+    for (int term = 0; term < 3; ++term)
+      for (int j = 0; j < nchb; ++j) {
+        const int left = C - 64 * j;
+        G.chunk_c0[nch] = (short)((term == 1 ? C : 0) + 64 * j); G.chunk_ks[nch] = (unsigned char)(((left < 64 ? left : 64) + 15) / 16);
+        G.chunk_src[nch] = 1; G.chunk_w[nch] = (unsigned char)((term == 2 ? nchb : 0) + j); G.chunk_f16[nch] = 1;
+        ks_total += G.chunk_ks[nch]; ++nch;
+      }
+    nwch = 2 * nchb;
   }
   G.nchunks = nch;
   int rc = up_tile_shape(G.Npad, B, D0, D1, D2, ks_total, mode == 2 ? 8 : 1, mode == 1 ? 8 : 1, &G.NT, &G.TZ);
@@ -3002,7 +3059,7 @@ static int conv3d_tc_up_impl(int mode, const float* x, int C, const float* wp8, 
     rc = make_map_act(&maps.x[0], x, C, B, D0, D1, D2);
     if (rc) return rc;
     for (int i = 1; i < 8; ++i) maps.x[i] = maps.x[0];
-    if (comp == 4) { rc = make_map_act16(&maps.x[1], xlo, 2 * C, B, D0, D1, D2); if (rc) return rc; }
+    if (comp == 4 || comp == 5) { rc = make_map_act16(&maps.x[1], xlo, 2 * C, B, D0, D1, D2); if (rc) return rc; }
     else if (comp) { rc = make_map_act(&maps.x[1], xlo, C, B, D0, D1, D2); if (rc) return rc; }
   } else {
     const long long F0 = 2LL * D0, F1 = 2LL * D1, F2 = 2LL * D2;
@@ -3253,7 +3310,18 @@ int ssr_tf32_split_bf16(const float* x, void* x2, long long nvox, int C, void* s
                 "tf32_split_bf16 args (C must be a multiple of 4)");
   long long g = (nvox * (C / 4) + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
-  tf32_split_bf16_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<uint16_t*>(x2), nvox, C);
+  tf32_split_bf16_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<uint16_t*>(x2), nvox, C, 0);
+  SSR_COUNT_LAUNCH();
+  SSR_CHECK_LAUNCH();
+  return SSR_OK;
+}
+// x2[v][0:C] = x1 = bf16(x), x2[v][C:2C] = bf16(x - x1): the activation operand of the bf16x3 compensated forward (level 5)
+int ssr_bf16x3_split(const float* x, void* x2, long long nvox, int C, void* stream) {
+  SSR_CHECK_ARG(x && x2 && nvox > 0 && C > 0 && C % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)x2 & 15) == 0,
+                "bf16x3_split args (C must be a multiple of 4)");
+  long long g = (nvox * (C / 4) + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  tf32_split_bf16_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<uint16_t*>(x2), nvox, C, 1);
   SSR_COUNT_LAUNCH();
   SSR_CHECK_LAUNCH();
   return SSR_OK;

@@ -284,7 +284,7 @@ class UNet3D:
         # 5th entry: MMA chains executed per algorithmic one (compensated forward: 2 in the hybrid scheme, 3 in 3xTF32)
         mult = 1
         if name is not None and kind == 'fwd_tc' and self._comp_level(name) == 3:
-            mult = 2 if self.comp_scheme == 'hybrid' else 3
+            mult = {'hybrid': 2, 'bf16x3': 2 if self._k2n_ok(cin, cout) else 1.5}.get(self.comp_scheme, 3)
         self.prof.append((kind, 2. * self.k ** 3 * cin * cout * self.nvox[l], e0, e1, mult))
 
     def _k2n_ok(self, cin, cout):
@@ -309,8 +309,9 @@ class UNet3D:
         if not (self.epi_fusion_generic and not (cin <= 32 and cout <= 32)):
             return False
         if l is not None:
-            comp = 4 if (name is not None and self._comp_level(name) == 3 and self.comp_scheme == 'hybrid') else \
-                (3 if name is not None and self._comp_level(name) else 0)
+            comp = 0
+            if name is not None and self._comp_level(name):
+                comp = {'hybrid': 4, 'bf16x3': 5}.get(self.comp_scheme, 3) if self._comp_level(name) == 3 else 3
             if self._ksplit(l, cin, cout, comp) > 1:
                 return False
         return True
@@ -340,21 +341,22 @@ class UNet3D:
             self._lo = torch.empty(max(n, self.nvox[0] * self.feats[0]), dtype=torch.float32, device=self.device)
         return self._lo
 
-    def _split16(self, x, nvox, c):
+    def _split16(self, x, nvox, c, x3=False):
         """x2 = [bf16(x_lo) | bf16(x_hi)] (2c bf16 channels per voxel = the bytes of c floats) in the shared scratch;
-        skipped when the kernel that produced x has just written it from its own epilogue (_lo_src)."""
+        skipped when the kernel that produced x has just written it from its own epilogue (_lo_src).
+        x3: the bf16x3 scheme's operand [bf16(x) | bf16(x - bf16(x))] instead."""
         key = (x.data_ptr(), nvox, c)
-        if self._lo_src == key:
+        if self._lo_src == key and not x3:
             self._lo_src = None
             return self._lo
         self._lo_src = None
-        lib.ssr_tf32_split_bf16(x, self._lo_buf(nvox * c), nvox, c, stream_ptr())
+        (lib.ssr_bf16x3_split if x3 else lib.ssr_tf32_split_bf16)(x, self._lo_buf(nvox * c), nvox, c, stream_ptr())
         return self._lo
 
     def _fuse_split_ok(self, next_name, c1, cout):
         """the layer `next_name` (c1 -> cout) will run the hybrid compensated forward through the k2n kernel on the tensor
         being produced now: the producer may emit its bf16 split directly (the two full-resolution 24-channel tensors)"""
-        return (self.conv_impl == 'tc' and self.comp_scheme == 'hybrid' and self._comp_level(next_name) == 3 and
+        return (self.conv_impl == 'tc' and self.comp_scheme in ('hybrid', 'bf16x3') and self._comp_level(next_name) == 3 and
                 self._k2n_ok(c1, cout) and os.environ.get('SSR_NO_SPLIT_FUSION') is None)
 
     def _conv_fwd_hybrid(self, name, x1, c1, x2, c2, y, l, cout, act, stats_sums):
@@ -369,20 +371,23 @@ class UNet3D:
             lib.ssr_conv3d_fwd_tc_k2n_part(x1, c1, 0, c1, whi, bias, y, B, *d, cout, act, 0, 0, st)
             lib.ssr_conv3d_fwd_tc_k2n_bf16(x16, 2 * c1, w16, bias, y, stats_sums, B, *d, cout, act, st)
             return
+        # generic kernel: TF32 main term + bf16 correction chain (hybrid, level 4), or three bf16 terms (bf16x3, level 5)
+        x3 = self.comp_scheme == 'bf16x3'
+        pm, lv = (9, 5) if x3 else (7, 4)
         if c2 == 0:
-            wp = self._packed_w(name, 7, c1, c1, cout)
-            lib.ssr_conv3d_fwd_tc_comp(x1, self._split16(x1, nv, c1), c1, wp, bias, y, stats_sums, B, *d, cout, act, 0, 4, st)
+            wp = self._packed_w(name, pm, c1, c1, cout)
+            lib.ssr_conv3d_fwd_tc_comp(x1, self._split16(x1, nv, c1, x3), c1, wp, bias, y, stats_sums, B, *d, cout, act, 0, lv, st)
             return
         assert stats_sums is None
-        wp1 = self._packed_w(name, 7, c1 + c2, c1, cout, tag='c0')
-        lib.ssr_conv3d_fwd_tc_comp(x1, self._split16(x1, nv, c1), c1, wp1, None, y, None, B, *d, cout, 0, 0, 4, st)
-        wp2 = self._packed_w(name, 7, c1 + c2, (c1 << 12) | c2, cout, tag='c1')
-        lib.ssr_conv3d_fwd_tc_comp(x2, self._split16(x2, nv, c2), c2, wp2, bias, y, None, B, *d, cout, act, 1, 4, st)
+        wp1 = self._packed_w(name, pm, c1 + c2, c1, cout, tag='c0')
+        lib.ssr_conv3d_fwd_tc_comp(x1, self._split16(x1, nv, c1, x3), c1, wp1, None, y, None, B, *d, cout, 0, 0, lv, st)
+        wp2 = self._packed_w(name, pm, c1 + c2, (c1 << 12) | c2, cout, tag='c1')
+        lib.ssr_conv3d_fwd_tc_comp(x2, self._split16(x2, nv, c2, x3), c2, wp2, bias, y, None, B, *d, cout, act, 1, lv, st)
 
     def _conv_fwd_comp(self, level, name, x1, c1, x2, c2, y, l, cout, act, stats_sums):
         """compensated forward of one layer (see the module docstring); the concatenated input of a decoder level that
         does not take the parity path is the sum of its two parts."""
-        if level == 3 and self.comp_scheme == 'hybrid':
+        if level == 3 and self.comp_scheme in ('hybrid', 'bf16x3'):
             return self._conv_fwd_hybrid(name, x1, c1, x2, c2, y, l, cout, act, stats_sums)
         st, B, d = stream_ptr(), self.B, self.ldims[l]
         nv = self.nvox[l]
@@ -457,12 +462,14 @@ class UNet3D:
         st, F, B = stream_ptr(), self.feats, self.B
         u = self._up_state(l)
         level = self._comp_level(name)
-        if level == 3 and self.comp_scheme == 'hybrid':
-            lib.ssr_conv3d_fwd_tc_up_comp(self.vlow[l], self._split16(self.vlow[l], self.nvox[l + 1], F[l + 1]), F[l + 1],
-                                          self._up_packs(l, 'fwd8h'), self.g0[l], B, *self.ldims[l + 1], F[l], 4, st)
-            wp = self._packed_w(name, 7, F[l], F[l], F[l], tag='skiph', src=u['wskip'])
-            lib.ssr_conv3d_fwd_tc_comp(self.h1[l], self._split16(self.h1[l], self.nvox[l], F[l]), F[l], wp,
-                                       self.p[name + '/bias'], self.g0[l], None, B, *self.ldims[l], F[l], act, 1, 4, st)
+        if level == 3 and self.comp_scheme in ('hybrid', 'bf16x3'):
+            x3 = self.comp_scheme == 'bf16x3'
+            pm, lv, pk = (9, 5, 'fwd8b') if x3 else (7, 4, 'fwd8h')
+            lib.ssr_conv3d_fwd_tc_up_comp(self.vlow[l], self._split16(self.vlow[l], self.nvox[l + 1], F[l + 1], x3), F[l + 1],
+                                          self._up_packs(l, pk), self.g0[l], B, *self.ldims[l + 1], F[l], lv, st)
+            wp = self._packed_w(name, pm, F[l], F[l], F[l], tag='skip' + pk[-1], src=u['wskip'])
+            lib.ssr_conv3d_fwd_tc_comp(self.h1[l], self._split16(self.h1[l], self.nvox[l], F[l], x3), F[l], wp,
+                                       self.p[name + '/bias'], self.g0[l], None, B, *self.ldims[l], F[l], act, 1, lv, st)
             return
         if level:
             # compensated: parity kernel on [vlow | vlow_lo | vlow], then the skip part accumulates (+ bias + ELU)
@@ -667,8 +674,11 @@ class UNet3D:
         if which == 'fwd8h' and which not in u:      # same for the hybrid scheme (TF32 hi chunks + bf16 chunks)
             u['nfh'] = lib.ssr_conv3d_packed_size(cu, cu, co, 7)
             u[which] = torch.empty(8 * u['nfh'], dtype=torch.float32, device=self.device)
+        if which == 'fwd8b' and which not in u:      # bf16x3 scheme (w1 chunks + w2 chunks, all bf16)
+            u['nfb'] = lib.ssr_conv3d_packed_size(cu, cu, co, 9)
+            u[which] = torch.empty(8 * u['nfb'], dtype=torch.float32, device=self.device)
         n, mode, c2 = {'fwd8': (u['nf'], 0, 0), 'dgr8': (u['nd'], 1, 0), 'fwd8c': (u.get('nfc'), 5, cu),
-                       'fwd8h': (u.get('nfh'), 7, cu)}[which]
+                       'fwd8h': (u.get('nfh'), 7, cu), 'fwd8b': (u.get('nfb'), 9, cu)}[which]
         for par in range(8):
             self._packed_w(name, mode, cu, c2, co, tag=('up', par), src=u['weff'][par * 27 * cu * co:(par + 1) * 27 * cu * co],
                            buf=u[which][par * n:(par + 1) * n])

@@ -214,11 +214,17 @@ def test_tf32_split_bf16_layout():
     assert torch.equal(x2[:, c:], hi.to(torch.bfloat16)) and torch.equal(x2[:, :c], (x - hi).to(torch.bfloat16))
 
 
+_SCHEME = {4: ('ssr_tf32_split_bf16', 7), 5: ('ssr_bf16x3_split', 9)}      # level -> (activation split, weight pack mode)
+
+
 @pytest.mark.parametrize('d,c,co', [([8, 16, 24], 48, 96), ([10, 10, 10], 192, 384), ([16, 16, 16], 24, 48),
                                     ([20, 20, 20], 96, 192), ([12, 20, 8], 384, 384), ([16, 16, 16], 40, 24)])
-def test_hybrid_generic_forward_matches_float64(d, c, co):
-    """level 4 of ssr_conv3d_fwd_tc_comp: TF32 main term + ONE bf16 chain for both correction terms"""
+@pytest.mark.parametrize('level', [4, 5])
+def test_hybrid_generic_forward_matches_float64(d, c, co, level):
+    """level 4 of ssr_conv3d_fwd_tc_comp: TF32 main term + ONE bf16 chain for both correction terms;
+    level 5 (bf16x3): x1 w1 + x2 w1 + x1 w2 with 8-bit pieces, every term a bf16 MMA"""
     from synthsr_b200._lib import lib, stream_ptr
+    split, pm = _SCHEME[level]
     rng = np.random.default_rng(1)
     nv = int(np.prod(d))
     x = _t(rng.normal(size=(nv, c)))
@@ -226,17 +232,17 @@ def test_hybrid_generic_forward_matches_float64(d, c, co):
     b = _t(rng.normal(size=co))
     st = stream_ptr()
     x2 = torch.empty((nv, 2 * c), dtype=torch.bfloat16, device='cuda')
-    lib.ssr_tf32_split_bf16(x, x2, nv, c, st)
-    wp = torch.empty(lib.ssr_conv3d_packed_size(c, c, co, 7), dtype=torch.float32, device='cuda')
-    lib.ssr_conv3d_pack_weights(w, wp, c, c, co, 7, st)
+    getattr(lib, split)(x, x2, nv, c, st)
+    wp = torch.empty(lib.ssr_conv3d_packed_size(c, c, co, pm), dtype=torch.float32, device='cuda')
+    lib.ssr_conv3d_pack_weights(w, wp, c, c, co, pm, st)
     y64 = _conv64(x, w, b, d)
     for with_sums in (False, True):
         y = torch.full((nv, co), float('nan'), dtype=torch.float32, device='cuda')
         sums = torch.full((2 * co,), float('nan'), dtype=torch.float64, device='cuda') if with_sums else None
-        lib.ssr_conv3d_fwd_tc_comp(x, x2, c, wp, b, y, sums, 1, *d, co, 1, 0, 4, st)
+        lib.ssr_conv3d_fwd_tc_comp(x, x2, c, wp, b, y, sums, 1, *d, co, 1, 0, level, st)
         torch.cuda.synchronize()
         err = (y.double().cpu() - y64).abs().max().item() / y64.abs().max().item()
-        _log('hybrid generic %s %d->%d sums=%d: max/max %.2e' % (d, c, co, with_sums, err))
+        _log('%s generic %s %d->%d sums=%d: max/max %.2e' % (split, d, c, co, with_sums, err))
         assert err < KERNEL_TOL, (d, c, co, err)
         if with_sums:
             s = sums.cpu().numpy()
@@ -277,8 +283,10 @@ def test_hybrid_k2n_forward_matches_float64(d):
 
 
 @pytest.mark.parametrize('dl,cu,co', [([8, 8, 16], 96, 48), ([10, 12, 8], 192, 96), ([8, 8, 8], 48, 24)])
-def test_hybrid_parity_forward_matches_float64(dl, cu, co):
+@pytest.mark.parametrize('level', [4, 5])
+def test_hybrid_parity_forward_matches_float64(dl, cu, co, level):
     from synthsr_b200._lib import lib, stream_ptr
+    split, pm = _SCHEME[level]
     rng = np.random.default_rng(4)
     cs = co
     nl = int(np.prod(dl))
@@ -289,19 +297,19 @@ def test_hybrid_parity_forward_matches_float64(dl, cu, co):
     wskip = torch.empty(27 * cs * co, dtype=torch.float32, device='cuda')
     weff = torch.empty(8 * 27 * cu * co, dtype=torch.float32, device='cuda')
     lib.ssr_conv3d_up_weights(w, cs, cu, co, wskip, weff, st)
-    n7 = lib.ssr_conv3d_packed_size(cu, cu, co, 7)
+    n7 = lib.ssr_conv3d_packed_size(cu, cu, co, pm)
     wp8 = torch.empty(8 * n7, dtype=torch.float32, device='cuda')
     for par in range(8):
-        lib.ssr_conv3d_pack_weights(weff[par * 27 * cu * co:], wp8[par * n7:], cu, cu, co, 7, st)
+        lib.ssr_conv3d_pack_weights(weff[par * 27 * cu * co:], wp8[par * n7:], cu, cu, co, pm, st)
     low2 = torch.empty((nl, 2 * cu), dtype=torch.bfloat16, device='cuda')
-    lib.ssr_tf32_split_bf16(low, low2, nl, cu, st)
+    getattr(lib, split)(low, low2, nl, cu, st)
     y = torch.full((8 * nl, co), float('nan'), dtype=torch.float32, device='cuda')
-    lib.ssr_conv3d_fwd_tc_up_comp(low, low2, cu, wp8, y, 1, *dl, co, 4, st)
+    lib.ssr_conv3d_fwd_tc_up_comp(low, low2, cu, wp8, y, 1, *dl, co, level, st)
     torch.cuda.synchronize()
     up = low.view(*dl, cu).repeat_interleave(2, 0).repeat_interleave(2, 1).repeat_interleave(2, 2).reshape(-1, cu)
     y64 = _conv64(up, w[:, :, :, cs:, :], None, df, elu=False)
     err = (y.double().cpu() - y64).abs().max().item() / y64.abs().max().item()
-    _log('hybrid parity %s %d->%d: max/max %.2e' % (dl, cu, co, err))
+    _log('%s parity %s %d->%d: max/max %.2e' % (split, dl, cu, co, err))
     assert err < KERNEL_TOL, err
 
 
