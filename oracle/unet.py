@@ -103,9 +103,27 @@ def _maxpool_same(x):
     return F.max_pool3d(x, 2)
 
 
+def _maxpool_routed(x, idx, report, level):
+    """MaxPooling3D with the window winners GIVEN (idx: what F.max_pool3d(..., return_indices=True) returned for another
+    implementation's forward of the same tensor).  Comparing two implementations' GRADIENTS tensor by tensor is only
+    well-posed under the same routing: a window whose two largest entries agree to the last bits is won by a different
+    entry in two forwards that differ by rounding, and one such window changes the whole level's gradient (see
+    tests/test_unet_parity_gpu.py).  report[level] = (windows routed differently from this forward's own argmax,
+    windows, largest (own max - routed entry) / max|x|): how far the given routing is from this forward's max-pool."""
+    assert all(x.shape[d] % 2 == 0 for d in (2, 3, 4)), 'routed pooling: even sizes only'
+    flat = x.flatten(2)
+    out = flat.gather(2, idx.flatten(2)).view(idx.shape)
+    if report is not None:
+        own, own_idx = F.max_pool3d(x.detach(), 2, return_indices=True)
+        report[level] = (int((own_idx != idx).sum()), idx.numel(),
+                         float((own - out.detach()).max() / x.detach().abs().max()))
+    return out
+
+
 def forward(params, image, training=True, nb_levels=5, nb_conv_per_level=2, new_stats=None, activations=None,
-            _wrong=()):
+            _wrong=(), pool_routing=None, routing_report=None):
     """image [B,X,Y,Z,Cin] -> prediction [B,X,Y,Z,nb_labels].  (ext/neuron/models.py:301-360, 420-498)
+    pool_routing (test aid, see _maxpool_routed): per encoder level, the max-pool winners to use instead of this forward's own.
     _wrong: deliberately wrong readings of the graph ('concat_swapped', 'skip_after_bn', 'relu'), only for the test that
     shows the reference's trained weights reject them (tests/test_oracle_unet.py)."""
     act = F.relu if 'relu' in _wrong else F.elu
@@ -122,7 +140,7 @@ def forward(params, image, training=True, nb_levels=5, nb_conv_per_level=2, new_
         if 'skip_after_bn' in _wrong:
             skips.append(x)
         if level < nb_levels - 1:
-            x = _maxpool_same(x)
+            x = _maxpool_same(x) if pool_routing is None else _maxpool_routed(x, pool_routing[level], routing_report, level)
     for level in range(nb_levels - 1):
         x = F.interpolate(x, scale_factor=2, mode='nearest')       # UpSampling3D (models.py:425-427)
         pair = [skips[nb_levels - 2 - level], x]

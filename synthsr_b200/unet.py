@@ -91,9 +91,13 @@ class UNet3D:
         self._lo = None                 # scratch for the TF32 residual x_lo of the convolution being run (stream ordered)
         self._lo_src = None             # (data_ptr, nvox, channels) of the tensor whose bf16 split _lo currently holds
         self._ksplit_cache = {}
-        # 'hybrid' (default): x_hi w_hi in TF32 + the two correction terms as one bf16 MMA chain (2 chains per convolution);
+        # 'bf16x3' (default): x = x1 + x2, w = w1 + w2 in 8-bit pieces, x1 w1 + x2 w1 + x1 w2 as three bf16 K-chunks per 64
+        #     input channels = 1.5 TF32 chains (generic / parity kernels from 48 channels on; the k2n layers and 24-channel
+        #     operands run 'hybrid');
+        # 'hybrid': x_hi w_hi in TF32 + the two correction terms as one bf16 MMA chain (2 chains per convolution);
         # 'tf32x3': all three terms in TF32 (3 chains) -- the first implementation, kept as a cross-check
-        self.comp_scheme = os.environ.get('SSR_COMP_SCHEME', 'hybrid')
+        self.comp_scheme = os.environ.get('SSR_COMP_SCHEME', 'bf16x3')
+        assert self.comp_scheme in ('bf16x3', 'hybrid', 'tf32x3'), self.comp_scheme
         self.conv_impl = conv_impl
         self.wgrad_tc = conv_impl == 'tc'
         self.prof = None          # list of (kind, flops, start_event, end_event) when profiling is enabled
@@ -284,7 +288,7 @@ class UNet3D:
         # 5th entry: MMA chains executed per algorithmic one (compensated forward: 2 in the hybrid scheme, 3 in 3xTF32)
         mult = 1
         if name is not None and kind == 'fwd_tc' and self._comp_level(name) == 3:
-            mult = {'hybrid': 2, 'bf16x3': 2 if self._k2n_ok(cin, cout) else 1.5}.get(self.comp_scheme, 3)
+            mult = {'hybrid': 2, 'bf16x3': 2 if (self._k2n_ok(cin, cout) or cin < 48) else 1.5}.get(self.comp_scheme, 3)
         self.prof.append((kind, 2. * self.k ** 3 * cin * cout * self.nvox[l], e0, e1, mult))
 
     def _k2n_ok(self, cin, cout):
@@ -311,7 +315,7 @@ class UNet3D:
         if l is not None:
             comp = 0
             if name is not None and self._comp_level(name):
-                comp = {'hybrid': 4, 'bf16x3': 5}.get(self.comp_scheme, 3) if self._comp_level(name) == 3 else 3
+                comp = {'hybrid': 4, 'bf16x3': self._x3(cin)[2]}.get(self.comp_scheme, 3) if self._comp_level(name) == 3 else 3
             if self._ksplit(l, cin, cout, comp) > 1:
                 return False
         return True
@@ -359,6 +363,13 @@ class UNet3D:
         return (self.conv_impl == 'tc' and self.comp_scheme in ('hybrid', 'bf16x3') and self._comp_level(next_name) == 3 and
                 self._k2n_ok(c1, cout) and os.environ.get('SSR_NO_SPLIT_FUSION') is None)
 
+    def _x3(self, c):
+        """(bf16x3?, weight pack mode, compensation level) of a c-channel operand in the generic / parity kernels.  bf16x3
+        wins from 48 channels on (3 bf16 chunks against 2 TF32 + 2 bf16); a 24-channel operand fills a 64-channel bf16 chunk
+        to 3/8 and is cheaper in the hybrid scheme (24 -> 48 @ 80^3: 0.170 ms hybrid, 0.205 ms bf16x3)."""
+        x3 = self.comp_scheme == 'bf16x3' and c >= 48
+        return (True, 9, 5) if x3 else (False, 7, 4)
+
     def _conv_fwd_hybrid(self, name, x1, c1, x2, c2, y, l, cout, act, stats_sums):
         """compensated forward, hybrid scheme: TF32 main term + one bf16 chain for x_lo w_hi + x_hi w_lo"""
         st, B, d = stream_ptr(), self.B, self.ldims[l]
@@ -372,15 +383,16 @@ class UNet3D:
             lib.ssr_conv3d_fwd_tc_k2n_bf16(x16, 2 * c1, w16, bias, y, stats_sums, B, *d, cout, act, st)
             return
         # generic kernel: TF32 main term + bf16 correction chain (hybrid, level 4), or three bf16 terms (bf16x3, level 5)
-        x3 = self.comp_scheme == 'bf16x3'
-        pm, lv = (9, 5) if x3 else (7, 4)
         if c2 == 0:
+            x3, pm, lv = self._x3(c1)
             wp = self._packed_w(name, pm, c1, c1, cout)
             lib.ssr_conv3d_fwd_tc_comp(x1, self._split16(x1, nv, c1, x3), c1, wp, bias, y, stats_sums, B, *d, cout, act, 0, lv, st)
             return
         assert stats_sums is None
+        x3, pm, lv = self._x3(c1)
         wp1 = self._packed_w(name, pm, c1 + c2, c1, cout, tag='c0')
         lib.ssr_conv3d_fwd_tc_comp(x1, self._split16(x1, nv, c1, x3), c1, wp1, None, y, None, B, *d, cout, 0, 0, lv, st)
+        x3, pm, lv = self._x3(c2)
         wp2 = self._packed_w(name, pm, c1 + c2, (c1 << 12) | c2, cout, tag='c1')
         lib.ssr_conv3d_fwd_tc_comp(x2, self._split16(x2, nv, c2, x3), c2, wp2, bias, y, None, B, *d, cout, act, 1, lv, st)
 
@@ -463,11 +475,12 @@ class UNet3D:
         u = self._up_state(l)
         level = self._comp_level(name)
         if level == 3 and self.comp_scheme in ('hybrid', 'bf16x3'):
-            x3 = self.comp_scheme == 'bf16x3'
-            pm, lv, pk = (9, 5, 'fwd8b') if x3 else (7, 4, 'fwd8h')
+            x3, pm, lv = self._x3(F[l + 1])
             lib.ssr_conv3d_fwd_tc_up_comp(self.vlow[l], self._split16(self.vlow[l], self.nvox[l + 1], F[l + 1], x3), F[l + 1],
-                                          self._up_packs(l, pk), self.g0[l], B, *self.ldims[l + 1], F[l], lv, st)
-            wp = self._packed_w(name, pm, F[l], F[l], F[l], tag='skip' + pk[-1], src=u['wskip'])
+                                          self._up_packs(l, 'fwd8b' if x3 else 'fwd8h'), self.g0[l], B, *self.ldims[l + 1],
+                                          F[l], lv, st)
+            x3, pm, lv = self._x3(F[l])
+            wp = self._packed_w(name, pm, F[l], F[l], F[l], tag='skipb' if x3 else 'skiph', src=u['wskip'])
             lib.ssr_conv3d_fwd_tc_comp(self.h1[l], self._split16(self.h1[l], self.nvox[l], F[l], x3), F[l], wp,
                                        self.p[name + '/bias'], self.g0[l], None, B, *self.ldims[l], F[l], act, 1, lv, st)
             return

@@ -57,6 +57,36 @@ def test_maxpool_same_odd():
     assert y.shape == (1, 1, 2, 2, 2) and y[0, 0, 1, 1, 1] == 26 and y[0, 0, 0, 0, 0] == 13
 
 
+def test_routed_maxpool_is_the_free_one_under_its_own_winners():
+    """pool_routing (test aid of the GPU gradient-parity tests): with the forward's own window winners the routed pooling is
+    MaxPooling3D -- same prediction, same gradients; with one near-tied window resolved the other way the prediction
+    barely moves and the report says so"""
+    import torch.nn.functional as F
+    params = OU.init_params(0, 1, dtype=torch.float64, nb_features=4, nb_levels=3)
+    leaves = {k: params[k].clone().requires_grad_(True) for k in OU.trainable_names(params)}
+    p = {k: leaves.get(k, params[k]) for k in params}
+    img = torch.rand(1, 8, 8, 8, 1, dtype=torch.float64, generator=torch.Generator().manual_seed(0))
+    x, routing = img.permute(0, 4, 1, 2, 3), []
+    for level in range(2):
+        for j in range(2):
+            x = F.elu(OU._conv(x, params, 'unet_conv_downarm_%d_%d' % (level, j)))
+        x = OU._bn(x, params, 'unet_bn_down_%d' % level, True, None)
+        x, idx = F.max_pool3d(x, 2, return_indices=True)
+        routing.append(idx)
+    free = OU.forward(p, img, nb_levels=3)
+    g_free = torch.autograd.grad(free.square().sum(), list(leaves.values()))
+    report = {}
+    routed = OU.forward(p, img, nb_levels=3, pool_routing=routing, routing_report=report)
+    g_routed = torch.autograd.grad(routed.square().sum(), list(leaves.values()))
+    assert torch.equal(free, routed) and all(torch.equal(a, b) for a, b in zip(g_free, g_routed))
+    assert report == {0: (0, routing[0].numel(), 0.), 1: (0, routing[1].numel(), 0.)}
+    other = [routing[0].clone(), routing[1]]
+    other[0][0, 0, 0, 0, 0] = 0 if routing[0][0, 0, 0, 0, 0] != 0 else 1       # another entry of the first window
+    report = {}
+    OU.forward(p, img, nb_levels=3, pool_routing=other, routing_report=report)
+    assert report[0][0] == 1 and report[0][2] > 0 and report[1][0] == 0
+
+
 def test_adam_and_bn_moving_formulas():
     p = OU.init_params(2, 1, nb_features=4, nb_levels=2)
     p = {k: v.double() for k, v in p.items()}
