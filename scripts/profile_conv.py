@@ -13,7 +13,11 @@ CASES = {'fwd24': ('fwd', [160, 160, 160], 24, 0, 24), 'fwd72': ('fwd', [160, 16
          'fwd48': ('fwd', [80, 80, 80], 48, 0, 48), 'fwd96': ('fwd', [40, 40, 40], 96, 0, 96),
          'fwd384': ('fwd', [10, 10, 10], 384, 0, 384), 'dgrad72': ('fwd', [160, 160, 160], 24, 0, 72),
          'wgrad24': ('wgrad', [160, 160, 160], 24, 0, 24), 'wgrad72': ('wgrad', [160, 160, 160], 24, 48, 24),
-         'wgrad96': ('wgrad', [40, 40, 40], 96, 0, 96)}
+         'wgrad96': ('wgrad', [40, 40, 40], 96, 0, 96),
+         # compensated forward of the same layers: 'x3' = bf16x3 (level 5), 'hy' = hybrid TF32 + bf16 (level 4)
+         'fwd48x3': ('comp5', [80, 80, 80], 48, 0, 48), 'fwd48hy': ('comp4', [80, 80, 80], 48, 0, 48),
+         'fwd96x3': ('comp5', [40, 40, 40], 96, 0, 96), 'fwd96hy': ('comp4', [40, 40, 40], 96, 0, 96),
+         'fwd192x3': ('comp5', [20, 20, 20], 192, 0, 192), 'fwd192hy': ('comp4', [20, 20, 20], 192, 0, 192)}
 
 
 def run(name, reps):
@@ -27,7 +31,18 @@ def run(name, reps):
         x2 = torch.full_like(x2, float(os.environ['SSR_CONST_DATA'])) if c2 else None
     st = stream_ptr()
     flops = 2. * 27 * (c1 + c2) * co * nv
-    if kind == 'fwd':
+    if kind.startswith('comp'):
+        level = int(kind[-1])
+        w = torch.randn((3, 3, 3, c1, co), device='cuda', generator=g) / np.sqrt(27 * c1)
+        b = torch.zeros(co, device='cuda')
+        y = torch.empty((nv, co), device='cuda')
+        xs = torch.empty((nv, 2 * c1), dtype=torch.bfloat16, device='cuda')
+        pm = 9 if level == 5 else 7
+        (lib.ssr_bf16x3_split if level == 5 else lib.ssr_tf32_split_bf16)(x1, xs, nv, c1, st)
+        wp = torch.empty(lib.ssr_conv3d_packed_size(c1, c1, co, pm), device='cuda')
+        lib.ssr_conv3d_pack_weights(w, wp, c1, c1, co, pm, st)
+        fn = lambda: lib.ssr_conv3d_fwd_tc_comp(x1, xs, c1, wp, b, y, None, 1, *d, co, 1, 0, level, st)
+    elif kind == 'fwd':
         w = torch.randn((3, 3, 3, c1 + c2, co), device='cuda', generator=g) / np.sqrt(27 * (c1 + c2))
         b = torch.zeros(co, device='cuda')
         y = torch.empty((nv, co), device='cuda')
