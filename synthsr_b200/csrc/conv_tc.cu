@@ -262,6 +262,7 @@ constexpr int TM1 = 16, TM2 = 8;                  // output tile: 16 (d1) x 8 (d
 constexpr int SLAB_ROWS = (TM1 + 2) * TM2;         // 144 rows x 128 B
 constexpr int SLAB_BYTES = SLAB_ROWS * 128;        // 18432 (multiple of 1024)
 constexpr int SB = 2;                              // B-group stages
+constexpr int TC_TAIL_BYTES = 3072;              // conv3d_tc_kernel: 52 barrier words + 640 floats of bias behind the stages
 constexpr int MAX_CHUNKS = 40;                   // 12 chunks (384 channels) x 3 terms of a compensated convolution
 
 struct TcGeom {
@@ -269,7 +270,10 @@ struct TcGeom {
   int Cout;          // real output channels
   int Npad;          // Cout rounded up to 16 (rows per tap in the packed weights)
   int NT;            // output channels per CTA (multiple of 16, <= 192)
-  int TZ;            // accumulators (d0 planes) per CTA
+  int TZ;            // d0 planes per CTA tile (one MMA-issuing warp each, <= 8)
+  int nslot;         // ring of plane accumulators in TMEM (NT columns each): plane zo of the CTA's it-th tile lives in slot
+                     // (it * TZ + zo) % nslot, so the epilogue drains plane by plane while the next tile's planes start in
+                     // the slots already freed (nslot = 2 TZ is the old "two accumulator sets")
   int KG;            // d0 taps per B group: 3 (all 9 taps resident) or 1
   int SA;            // A stages
   int nchunks;
@@ -345,9 +349,12 @@ __device__ __forceinline__ float colsum16_transpose(const float (&v)[16], int la
   return d;
 }
 
-// Persistent: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The TMEM holds TWO accumulator sets,
-// so the epilogue of tile i (TMEM -> registers -> bias/ELU -> global) overlaps the MMAs of tile i+1, and the TMA
-// producer runs ahead across tile boundaries (no pipeline refill, no per-tile setup).
+// Persistent: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The TMEM holds a RING of plane
+// accumulators (G.nslot slots of NT columns, each with its own full / empty barrier), so the epilogue of a plane (TMEM ->
+// registers -> bias/ELU -> global) overlaps the MMAs of the following planes and of the next tile, and the TMA producer
+// runs ahead across tile boundaries (no pipeline refill, no per-tile setup).  Deep tiles (TZ up to 8 planes) are what cuts
+// the L2 -> shared-memory traffic these kernels are bound by (profiles/r02_conv_schemes_ncu.txt: 6.3 TB/s on every
+// variant): the weights of a chunk are streamed once per tile and the d0 halo is 2 planes per TZ.
 // EPI (epilogue fusions for the levels below full resolution, the counterpart of the k2n kernel's):
 //   1 (data gradient): out *= elu'(elu_h) and dbias[c] += sum_v out[v][c]      -- replaces elu_bwd_kernel
 //   2 (forward):       sums[c] += sum_v out, sums[Cout + c] += sum_v out^2    -- replaces colsum2_vec_kernel<0>
@@ -358,7 +365,7 @@ __device__ __forceinline__ float colsum16_transpose(const float (&v)[16], int la
 // profiles/r01_desc_probe_unaligned_views.txt).  With 16 x 8 tiles a 10^3 / 20^3 plane fills 39 % / 52 % of the GEMM rows
 // it pays for, a linearised plane 78 %; rows that fall into the halo columns are computed and dropped.
 template <int EPI, bool PL = false>
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(416, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_x2,
                  const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias, float* __restrict__ y,
                  const TcGeom G, const float* __restrict__ elu_h, float* __restrict__ dbias, double* __restrict__ sums) {
@@ -370,15 +377,15 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
   const int slab_bytes = PL ? G.pl_slab : SLAB_BYTES;
   uint8_t* sB = sA + (size_t)G.SA * slab_bytes;
   uint64_t* bars = (uint64_t*)(sB + (size_t)SB * bgroup_bytes);
-  uint64_t* fullA = bars;
-  uint64_t* emptyA = bars + G.SA;
-  uint64_t* fullB = bars + 2 * G.SA;
-  uint64_t* emptyB = fullB + SB;
-  uint64_t* accFull = emptyB + SB;                 // [2]
-  uint64_t* accEmpty = accFull + 2;                // [2]
-  uint32_t* tmem_slot = (uint32_t*)(accEmpty + 2);
-  uint64_t* kindBar = bars + 26;                   // [TZ <= 4] one per MMA warp: TF32 -> bf16 switch of the hybrid forward
-  float* sbias = (float*)(bars + 32);              // Npad floats (<= 576), 16-byte aligned, zero padded
+  uint64_t* fullA = bars;                          // [SA <= 8]
+  uint64_t* emptyA = bars + 8;                     // [8]
+  uint64_t* fullB = bars + 16;                     // [SB]
+  uint64_t* emptyB = bars + 18;                    // [SB]
+  uint64_t* accFull = bars + 20;                   // [nslot <= 10]
+  uint64_t* accEmpty = bars + 30;                  // [10]
+  uint64_t* kindBar = bars + 40;                   // [TZ <= 8] one per MMA warp: TF32 -> bf16 switch of the hybrid forward
+  uint32_t* tmem_slot = (uint32_t*)(bars + 48);
+  float* sbias = (float*)(bars + 52);              // Npad floats (<= 576), 16-byte aligned, zero padded
   float* sred = sbias + 640;                       // EPI: 2 x Npad per-CTA channel sums (host reserves the space)
   if (EPI != 0)
     for (int i = threadIdx.x; i < 2 * G.Npad; i += blockDim.x) sred[i] = 0.f;
@@ -391,8 +398,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
     // NW = G.TZ MMA warps: each of them releases every ring stage and signals every accumulator set
     for (int i = 0; i < G.SA; ++i) { mbar_init(fullA + i, 1); mbar_init(emptyA + i, G.TZ); }
     for (int i = 0; i < SB; ++i) { mbar_init(fullB + i, 1); mbar_init(emptyB + i, G.TZ); }
-    for (int i = 0; i < 2; ++i) { mbar_init(accFull + i, G.TZ); mbar_init(accEmpty + i, 4); }   // 4 epilogue warps arrive
-    for (int i = 0; i < 4; ++i) mbar_init(kindBar + i, 1);
+    for (int i = 0; i < G.nslot; ++i) { mbar_init(accFull + i, 1); mbar_init(accEmpty + i, 4); }   // owner warp / 4 epilogue warps
+    for (int i = 0; i < 8; ++i) mbar_init(kindBar + i, 1);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -409,7 +416,6 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) DBG_STAMP(1);
   const int ntiles = G.B * G.n0tiles * G.n1tiles * G.n2tiles * G.nNtiles * G.ksplit;
-  const uint32_t set_cols = (uint32_t)(G.TZ * G.NT);
 
 #define DECODE_TILE(tile)                                                       \
   int t_ = (tile);                                                               \
@@ -489,11 +495,14 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
       if (warp == 1 && lane == 0) DBG_STAMP(3);
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         DECODE_TILE(tile)
-        const int set = it & 1;
-        const uint32_t dcol = tmem_base + (uint32_t)set * set_cols + (uint32_t)zo * NT;
+        const int gpl = it * G.TZ + zo, slot = gpl % G.nslot;     // this plane's accumulator slot and how often it was used
+        const uint32_t use = (uint32_t)(gpl / G.nslot);
+        const uint32_t dcol = tmem_base + (uint32_t)slot * NT;
         const bool active = zo < nz;
-        mbar_wait(accEmpty + set, ((it >> 1) & 1) ^ 1);          // epilogue has drained this accumulator set
-        tc_fence_after();
+        // The slot must have been drained by the epilogue -- checked right before this warp's FIRST MMA of the tile, not
+        // here: until then the warp only walks the ring (waits / releases slabs it has no tap in), and the epilogue of the
+        // previous tile's planes gets zo slab times of head start instead of stalling the whole ring.
+        bool slot_ready = false;
         uint32_t acc = 0u;                         // first MMA of the tile into this accumulator overwrites
         bool prev_f16 = false;
         for (int ch = ch_lo; ch < ch_hi; ++ch) {
@@ -525,6 +534,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                 { const long long w0 = dbg ? clock64() : 0; mbar_wait(fullA + sa, pa); if (dbg) wait_a += clock64() - w0; }
                 const int kk = zin - zo;
                 if (active && kk >= 0 && kk < KG) {            // warp-uniform
+                  if (!slot_ready) {
+                    mbar_wait(accEmpty + slot, (use & 1u) ^ 1u);
+                    tc_fence_after();
+                    slot_ready = true;
+                  }
                   if (elect_one()) {
                     uint32_t alo = a_base + (uint32_t)sa * ((uint32_t)slab_bytes >> 4);
                     if (PL) alo += (uint32_t)(t2 * 128 + k2) * 8u;      // window start + d2 tap, in 128-byte rows
@@ -552,7 +566,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             }
           }
         }
-        if (elect_one()) umma_commit(accFull + set);
+        if (!slot_ready) mbar_wait(accEmpty + slot, (use & 1u) ^ 1u);   // plane without MMAs (clipped tile): keep the phases in step
+        if (elect_one()) umma_commit(accFull + slot);
         __syncwarp();
         if (warp == 1 && lane == 0 && it == 0) { DBG_STAMP(4); if (dbg) { dbg[9] = wait_a; dbg[10] = wait_b; } }
       }
@@ -566,20 +581,20 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       DECODE_TILE(tile)
-      const int set = it & 1;
-      const uint32_t acc_base = tmem_base + (uint32_t)set * set_cols;
       int i1 = y0 + (r >> 3), i2 = x0 + (r & 7);
       if (PL) { const int rr = t2 * 128 + r; i1 = rr / G.pl_pitch; i2 = rr - i1 * G.pl_pitch; }   // halo columns: i2 >= D2
-      mbar_wait(accFull + set, (it >> 1) & 1);
-      tc_fence_after();
-      if (warp == G.TZ + 1 && lane == 0 && it == 0) DBG_STAMP(5);
       const bool vox_ok = i1 < G.D1 && i2 < G.D2;
-      for (int zo = 0; zo < nz; ++zo) {
+      for (int zo = 0; zo < G.TZ; ++zo) {
+        const int gpl = it * G.TZ + zo, slot = gpl % G.nslot;
+        mbar_wait(accFull + slot, (uint32_t)(gpl / G.nslot) & 1u);
+        tc_fence_after();
+        if (warp == G.TZ + 1 && lane == 0 && it == 0 && zo == 0) DBG_STAMP(5);
+        const uint32_t acc_base = tmem_base + (uint32_t)(slot * G.NT);
         const int i0 = z0 + zo;
         float* orow = y + ((((long long)b * G.D0 + i0) * G.D1 + i1) * G.D2 + i2) * G.Cout + n0;
-        for (int cb = 0; cb < G.NT; cb += 16) {
+        for (int cb = 0; cb < (zo < nz ? G.NT : 0); cb += 16) {       // planes past the volume end: nothing to drain
           uint32_t v[16];
-          tmem_ld16(acc_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(zo * G.NT + cb), v);
+          tmem_ld16(acc_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
           tmem_ld_wait();
           float o[16];
           const float4* bs = reinterpret_cast<const float4*>(sbias + n0 + cb);      // zero padded, 16-byte aligned
@@ -673,11 +688,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
               if (e < nvalid) orow[cb + e] = o[e];
           }
         }
+        // slot drained: hand it back to the MMA warp that uses it next
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(accEmpty + slot);
       }
-      // accumulator set drained: hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(accEmpty + set);
       if (warp == G.TZ + 1 && lane == 0 && it == 0) DBG_STAMP(6);
     }
   }
@@ -2702,7 +2717,7 @@ static int tc_tile_shape(TcGeom& G, int C1, int C2, int Cout, int B, int D0, int
   }
   // shared-memory fit of an N tile: two B groups (all 9 (k0,k1) taps of a d2 tap when they fit, else 3) + >= 2 slabs
   const int slab_b = G.pl_pitch > 0 ? G.pl_slab : SLAB_BYTES;
-  const int avail = 227 * 1024 - 1024 - 2816 - (epi ? 2 * 4 * 576 : 0);
+  const int avail = 227 * 1024 - 1024 - TC_TAIL_BYTES - (epi ? 2 * 4 * 576 : 0);
   auto fits = [&](int nt) { return SB * 3 * nt * 128 + 2 * slab_b <= avail; };
   double best = 1e300;
   int best_nt = 0, best_tz = 0, best_ks = 1;
@@ -2712,23 +2727,38 @@ static int tc_tile_shape(TcGeom& G, int C1, int C2, int Cout, int B, int D0, int
                                                                                 : (C1 + 31) / 32 + (C2 + 31) / 32;
   const bool may_split = epi == 0 && Cout % 4 == 0 && !getenv("SSR_NO_SPLIT_K") &&
                          (long long)B * D0 * D1 * D2 <= 27000;
+  // Default: <= 4 planes per tile, ring = two tiles' planes, L2 term only on the small (split-K) levels.  SSR_TC_DEEP_TILES=1
+  // lets the L2-traffic term choose on every level (up to 5 planes of 48 channels): fewer operand bytes per output, but
+  // measured slower at 80^3 (48 -> 48: 0.318 ms against 0.301; data gradient 0.193 against 0.172) and only marginally faster
+  // at 40^3 -- 14.00 against 13.92 ms per step (scripts/gpu/r02_s.sh), so it stays an experiment.
+  const bool old_tiles = getenv("SSR_TC_DEEP_TILES") == nullptr;
   for (int ksp = 1; ksp <= (may_split ? 8 : 1) && ksp <= nchunks_all; ++ksp) {
     for (int nt = 16; nt <= 192 && nt <= G.Npad; nt += 16) {
       if (G.Npad % nt || !fits(nt)) continue;
-      for (int tz = 1; tz <= 4 && tz <= D0 && tz * nt <= 256; ++tz) {   // two accumulator sets in 512 TMEM columns
+      // plane accumulators that fit the TMEM (and the barrier arrays).  A tile's planes all complete within its last few
+      // slabs, so the ring must hold TWO tiles' planes for the epilogue burst to hide behind the next tile: with 8 planes in
+      // 10 slots the MMA warps of the next tile caught up with the four epilogue warps (48 -> 48 at 80^3: 0.23 ms against
+      // 0.16 ms, gpurun_out/r02q_layer_times.txt)
+      const int slots_max = 512 / nt < 10 ? 512 / nt : 10;
+      for (int tz = 1; tz <= (old_tiles ? 4 : 8) && tz <= D0 && (old_tiles ? tz * nt <= 256 : 2 * tz <= slots_max); ++tz) {
         const long long tiles = (long long)B * ((D0 + tz - 1) / tz) * n1t * n2t * (G.Npad / nt) * ksp;
         const long long rounds = (tiles + 147) / 148;
         // + issue overhead: exposed with a single issuing warp (tz == 1), mostly hidden with one warp per accumulator
         const double mma = (nt / 2 > 32 + nt / 4 ? nt / 2 : 32 + nt / 4) + (tz == 1 ? 20.0 : 8.0);
-        // slabs are shared by up to 3 output planes: fewer planes per tile = more TMA traffic per MMA (mild penalty)
         const double ks_part = (double)((ks_total + ksp - 1) / ksp);
-        double cost = rounds * (tz * 27.0 * ks_part * mma * (1.0 + 0.04 * (4 - tz)) + 2500.0);
-        if (may_split) {
-          // L2 -> shared-memory traffic of the whole launch: every tile streams its weight slice (27 taps x K x nt x 4 B)
-          // and its activation slabs.  With <= 148 single-plane tiles THIS bounds the 20^3 / 10^3 levels, not the MMA
-          // chain: 192 -> 192 at 20^3 moved 480 MB in 82 us (5.9 TB/s of L2 bandwidth) for 39 us of MMAs.  More planes
-          // per tile (tz) share the weights; split-K restores the CTA count.
-          const double l2_bytes = (double)tiles * (27.0 * ks_part * 8.0 * nt * 4.0 + (ks_part / 4.0) * 3.0 * (tz + 2) * slab_b);
+        double cost = rounds * (tz * 27.0 * ks_part * mma * (old_tiles ? 1.0 + 0.04 * (4 - tz) : 1.0) + 2500.0);
+        if (may_split || !old_tiles) {
+          // L2 -> shared-memory traffic of the whole launch: every tile streams its weight slice (27 taps x 128-byte rows x
+          // nt per chunk) and its activation slabs: with all 9 (k0, k1) taps of a d2 tap resident (KG = 3, nt <= 64) a slab
+          // serves up to 3 output planes, tz + 2 slabs per (chunk, d2 tap); otherwise every plane is loaded once per d0 tap.
+          // THIS bounds the kernel on every level, not the MMA chain: 48 -> 48 at 80^3 moves 984 MB in 158 us, 6.2 TB/s, with
+          // the tensor pipe 42 % busy (profiles/r02_conv_schemes_ncu.txt); 192 -> 192 at 20^3 480 MB in 82 us.  More planes
+          // per tile share the weights and shrink the d0 halo; split-K restores the CTA count on the small levels.
+          const double nch_part = (double)((nchunks_all + ksp - 1) / ksp);
+          const bool kg3 = 9 * nt * 128 <= 74 * 1024 && !(G.pl_pitch > 0 && SB * 9 * nt * 128 + 2 * slab_b > avail);
+          const double slabs = 3.0 * (kg3 ? tz + 2 : 3 * tz);
+          const double l2_bytes = old_tiles ? (double)tiles * (27.0 * ks_part * 8.0 * nt * 4.0 + (ks_part / 4.0) * 3.0 * (tz + 2) * slab_b)
+                                            : (double)tiles * nch_part * (27.0 * nt * 128.0 + slabs * slab_b);
           const double l2_cycles = l2_bytes / 3000.0 + 2500.0;          // ~5.7 TB/s at 1.9 GHz
           if (l2_cycles > cost) cost = l2_cycles;
         }
@@ -2775,10 +2805,17 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
   { const int rc_shape = tc_tile_shape(G, C1, C2, Cout, B, D0, D1, D2, epi, comp); if (rc_shape) return rc_shape; }
   G.nNtiles = G.Npad / G.NT;
   G.KG = (3 * 3 * G.NT * 128 <= 74 * 1024) ? 3 : 1;
-  if (G.pl_pitch > 0 && SB * 9 * G.NT * 128 + 2 * G.pl_slab > 227 * 1024 - 1024 - 2816 - (epi ? 2 * 4 * 576 : 0)) G.KG = 1;
-  int cols = 2 * G.TZ * G.NT, pc = 32;
+  if (G.pl_pitch > 0 && SB * 9 * G.NT * 128 + 2 * G.pl_slab > 227 * 1024 - 1024 - TC_TAIL_BYTES - (epi ? 2 * 4 * 576 : 0)) G.KG = 1;
+  // ring of plane accumulators: as many slots as fit the TMEM, at most two tiles' worth (and the barrier arrays' 10)
+  G.nslot = 512 / G.NT < 2 * G.TZ ? 512 / G.NT : 2 * G.TZ;
+  if (G.nslot > 10) G.nslot = 10;
+  SSR_CHECK_ARG(G.nslot >= G.TZ && G.TZ <= 8, "accumulator ring");
+  int cols = G.nslot * G.NT, pc = 32;
   while (pc < cols) pc <<= 1;
   G.tmem_cols = pc;
+  if (getenv("SSR_TC_PRINT_TILES"))
+    fprintf(stderr, "conv3d_tc %dx%dx%d C=%d+%d->%d comp=%d epi=%d: NT=%d TZ=%d KG=%d nslot=%d ksplit=%d pl=%d\n", D0, D1, D2, C1,
+            comp ? 0 : C2, Cout, comp, epi, G.NT, G.TZ, G.KG, G.nslot, G.ksplit, G.pl_pitch);
   int nch = 0, nwch = 0;                       // chunks of K, chunks of the packed weights
   if (comp == 5) {
     const int nchb = (C1 + 63) / 64;
@@ -2833,7 +2870,7 @@ static int conv3d_fwd_tc_impl(const float* x1, int C1, const float* x2, int C2, 
   if (pl) { G.n1tiles = 1; G.n2tiles = ((D1 - 1) * G.pl_pitch + D2 + 127) / 128; }
   const int slab_bytes = pl ? G.pl_slab : SLAB_BYTES;
   const int bgroup = G.KG * 3 * G.NT * 128;
-  const int tail = 2816 /*barriers + bias*/ + (epi ? 2 * 4 * 576 : 0) /*per-CTA channel sums of the fused epilogues*/;
+  const int tail = TC_TAIL_BYTES /*barriers + bias*/ + (epi ? 2 * 4 * 576 : 0) /*per-CTA channel sums of the fused epilogues*/;
   const int budget = 227 * 1024 - 1024 /*align slack*/ - tail - SB * bgroup;
   int sa = budget / slab_bytes; if (sa > 8) sa = 8;
   SSR_CHECK_ARG(sa >= 2, "shared memory budget");
