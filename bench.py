@@ -371,12 +371,13 @@ def main():
     # family: wgrad_tc -> wgrad_tc_persistent_kernel, fwd_tc / dgrad_tc -> conv3d_tc_kernel + conv3d_tc_k2n_kernel +
     # conv3d_tc_up_kernel).  FLOPs are ALGORITHMIC (2*27*Cin*Cout*voxels of the reference's layer): the
     # parity path of the decoder convolutions executes 8 instead of 27 taps on the upsampled channels, the compensated
-    # forward executes 3 MMAs per algorithmic one.
+    # forward executes 1.5 (bf16x3) or 2 (hybrid, the 24-channel layers) MMA chains per algorithmic one.
     tc = {k: v for k, v in agg.items() if k.endswith('_tc')}
     dom = max(tc, key=lambda k: tc[k][0]) if tc else None
     names = {'wgrad_tc': 'wgrad_tc_persistent_kernel (<0> plain, <1> parity classes of the decoder convolutions)',
              'fwd_tc': 'conv3d_tc_kernel / conv3d_tc_k2n_kernel / conv3d_tc_up_kernel<1> (forward%s)' % (
-                 '; compensated on every layer but uparm_8_0: TF32 chain x_hi w_hi + ONE bf16 chain for x_lo w_hi + x_hi w_lo, '
+                 '; compensated on every layer but uparm_8_0: bf16x3 = three bf16 K-chunks x1 w1 + x2 w1 + x1 w2 per 64 input '
+                 'channels (kind::f16), the 24-channel layers TF32 chain + one bf16 correction chain, '
                  '+ tf32_split_bf16_kernel' if args.conv_impl == 'tc3' else ''),
              'dgrad_tc': 'conv3d_tc_kernel / conv3d_tc_k2n_kernel / conv3d_tc_up_kernel<2> (data gradient)'}
     achieved = tc[dom][1] / (tc[dom][0] * 1e-3) / 1e12 if dom else 0.       # algorithmic 2*27*Cin*Cout*voxels per launch
@@ -393,7 +394,7 @@ def main():
     step_tf = step_f / (ms / args.steps * 1e-3) / 1e12
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
                 'traffic': traffic, 'traffic_launch': traffic_note, 'peak_source': peak_src,
-                'kernel': '%s (tcgen05 kind::tf32), %.2f ms of the step in %d launches' % (
+                'kernel': '%s (tcgen05 kind::tf32 / kind::f16), %.2f ms of the step in %d launches' % (
                     names.get(dom, dom), tc[dom][0] / 2, tc[dom][2] // 2) if dom else None,
                 'frac_of_tf32_peak': achieved / (peak / 2),
                 'all_tc_convolutions': {'tflops': all_tc, 'frac_of_tf32_peak': all_tc / (peak / 2), 'ms_per_step': tc_ms / 2},

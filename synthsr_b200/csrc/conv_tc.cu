@@ -499,10 +499,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
         const uint32_t use = (uint32_t)(gpl / G.nslot);
         const uint32_t dcol = tmem_base + (uint32_t)slot * NT;
         const bool active = zo < nz;
-        // The slot must have been drained by the epilogue -- checked right before this warp's FIRST MMA of the tile, not
-        // here: until then the warp only walks the ring (waits / releases slabs it has no tap in), and the epilogue of the
-        // previous tile's planes gets zo slab times of head start instead of stalling the whole ring.
-        bool slot_ready = false;
+        // epilogue has drained this slot.  (Deferring this wait to the warp's first MMA of the tile -- so that warps without
+        // a tap in the first slabs keep walking the ring -- measured 5 % SLOWER on every generic layer: forward 5.04 -> 5.28
+        // ms, data gradient 3.00 -> 3.16 ms per step, scripts/gpu/r02_q.sh against r02_s.sh.)
+        mbar_wait(accEmpty + slot, (use & 1u) ^ 1u);
+        tc_fence_after();
         uint32_t acc = 0u;                         // first MMA of the tile into this accumulator overwrites
         bool prev_f16 = false;
         for (int ch = ch_lo; ch < ch_hi; ++ch) {
@@ -534,11 +535,6 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                 { const long long w0 = dbg ? clock64() : 0; mbar_wait(fullA + sa, pa); if (dbg) wait_a += clock64() - w0; }
                 const int kk = zin - zo;
                 if (active && kk >= 0 && kk < KG) {            // warp-uniform
-                  if (!slot_ready) {
-                    mbar_wait(accEmpty + slot, (use & 1u) ^ 1u);
-                    tc_fence_after();
-                    slot_ready = true;
-                  }
                   if (elect_one()) {
                     uint32_t alo = a_base + (uint32_t)sa * ((uint32_t)slab_bytes >> 4);
                     if (PL) alo += (uint32_t)(t2 * 128 + k2) * 8u;      // window start + d2 tap, in 128-byte rows
@@ -566,8 +562,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             }
           }
         }
-        if (!slot_ready) mbar_wait(accEmpty + slot, (use & 1u) ^ 1u);   // plane without MMAs (clipped tile): keep the phases in step
-        if (elect_one()) umma_commit(accFull + slot);
+        if (elect_one()) umma_commit(accFull + slot);            // (an inactive plane of a clipped tile arrives at once)
         __syncwarp();
         if (warp == 1 && lane == 0 && it == 0) { DBG_STAMP(4); if (dbg) { dbg[9] = wait_a; dbg[10] = wait_b; } }
       }
