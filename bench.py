@@ -400,8 +400,9 @@ def main():
                 'all_tc_convolutions': {'tflops': all_tc, 'frac_of_tf32_peak': all_tc / (peak / 2), 'ms_per_step': tc_ms / 2},
                 'whole_step': {'tflops': step_tf, 'frac_of_tf32_peak': step_tf / (peak / 2)},
                 'executed': {'note': 'tensor-core work actually issued, in TF32-equivalent FLOPs: a compensated forward '
-                                     'convolution runs 2 MMA chains per algorithmic one (the bf16 chain covers twice the K per '
-                                     'instruction), so the hardware utilisation of the forward is this figure, not `achieved`',
+                                     'convolution runs 1.5 MMA chains per algorithmic one in the bf16x3 scheme (three bf16 '
+                                     'K-chunks, each covering twice the K of a TF32 instruction) and 2 on the 24-channel layers '
+                                     '(hybrid), so the hardware utilisation of the forward is this figure, not `achieved`',
                              'dominant_kind_tflops': executed.get(dom, 0.) / (tc[dom][0] * 1e-3) / 1e12 if dom else 0.,
                              'dominant_kind_frac_of_tf32_peak': (executed.get(dom, 0.) / (tc[dom][0] * 1e-3) / 1e12) / (peak / 2) if dom else 0.,
                              'all_tc_tflops': sum(executed.get(k, 0.) for k in tc) / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.},
