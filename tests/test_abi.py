@@ -31,3 +31,32 @@ def test_argument_errors_are_reported_not_swallowed():
     dll.ssr_resize.restype = ctypes.c_int
     r = dll.ssr_resize(None, None, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, None)
     assert r == -1 and b'invalid argument' in dll.ssr_last_error()
+
+
+def test_packed_weight_sizes_of_every_pack_mode():
+    """ssr_conv3d_packed_size is host arithmetic (no CUDA): floats of the K-major packed copy per pack mode.
+    0 / 1: 32-channel TF32 chunks of the forward / data-gradient kernel; 2, 3, 4, 6, 8: the k2n layout (9 tiles of 96 rows);
+    5: hi / lo TF32 chunks; 7: TF32 hi chunks + bf16 [w_hi ; w_lo] chunks; 9: bf16 w1 chunks + bf16 w2 chunks (64 channels each)."""
+    dll = ctypes.CDLL(_lib.LIB_PATH)
+    f = dll.ssr_conv3d_packed_size
+    f.restype = ctypes.c_longlong
+    row = 27 * 32          # floats per output row of one chunk: 27 taps x 128 bytes
+
+    def up16(n):
+        return (n + 15) // 16 * 16
+    for cin, cout in ((24, 24), (48, 96), (96, 48), (192, 192), (384, 384), (40, 24)):
+        n32, n64 = (cin + 31) // 32, (cin + 63) // 64
+        assert f(cin, 0, cout, 0) == n32 * row * up16(cout)
+        assert f(cin, 0, cout, 1) == ((cout + 31) // 32) * row * up16(cin)
+        assert f(cin, cin, cout, 5) == 2 * n32 * row * up16(cout)
+        assert f(cin, cin, cout, 7) == (n32 + (2 * cin + 63) // 64) * row * up16(cout)
+        assert f(cin, cin, cout, 9) == 2 * n64 * row * up16(cout)
+        assert f(cin, cin, cout, 9) <= f(cin, cin, cout, 7)          # bf16x3 never streams more weight bytes than hybrid
+    for mode in (2, 3, 4, 6, 8):
+        assert f(24, 0, 24, mode) == 9 * 96 * 32
+    # a channel part of a concatenated kernel: Cin2 = (first channel << 12) | channels
+    assert f(144, (48 << 12) | 96, 48, 9) == 2 * 2 * row * 48
+    # bad pack arguments are reported before any CUDA call
+    dll.ssr_last_error.restype = ctypes.c_char_p
+    dll.ssr_conv3d_pack_weights.restype = ctypes.c_int
+    assert dll.ssr_conv3d_pack_weights(None, None, 24, 0, 24, 10, None) == -1 and b'pack args' in dll.ssr_last_error()
