@@ -249,6 +249,12 @@ def main():
     config = {'workload': desc, 'global_batch': args.gpus, 'volume': shape, 'parallelism': 'dp%d' % args.gpus,
               'l2_policy': 'per-step working set (>4 GB of activations) exceeds the 126 MB L2; no explicit flush',
               'conv_impl': args.conv_impl,
+              'precision': {'tc3': 'forward: fp32 operands split into 8-bit pieces, three bf16 MMA terms per convolution (bf16x3; '
+                                   'TF32 + one bf16 correction chain on the 24-channel layers), fp32 accumulation in TMEM -- '
+                                   'fp32-class results (1e-5 per convolution); backward: TF32 operands, fp32 accumulation; first '
+                                   'layer, BatchNorm, loss, Adam: fp32',
+                            'tc': 'forward and backward: TF32 operands, fp32 accumulation (outside the 1e-3 parity bar)',
+                            'ref': 'fp32 on the CUDA cores'}.get(args.conv_impl),
               'pipeline': 'generator of batch i+1 overlaps the U-Net step of batch i (one generator pass + one training '
                           'pass per step, as the reference\'s fit_generator queue)' if not args.no_pipeline
                           else 'none (generate, then train, inside each step)'}
