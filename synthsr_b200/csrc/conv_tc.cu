@@ -2722,11 +2722,15 @@ static int tc_tile_shape(TcGeom& G, int C1, int C2, int Cout, int B, int D0, int
                                                                                 : (C1 + 31) / 32 + (C2 + 31) / 32;
   const bool may_split = epi == 0 && Cout % 4 == 0 && !getenv("SSR_NO_SPLIT_K") &&
                          (long long)B * D0 * D1 * D2 <= 27000;
-  // Default: <= 4 planes per tile, ring = two tiles' planes, L2 term only on the small (split-K) levels.  SSR_TC_DEEP_TILES=1
-  // lets the L2-traffic term choose on every level (up to 5 planes of 48 channels): fewer operand bytes per output, but
-  // measured slower at 80^3 (48 -> 48: 0.318 ms against 0.301; data gradient 0.193 against 0.172) and only marginally faster
-  // at 40^3 -- 14.00 against 13.92 ms per step (scripts/gpu/r02_s.sh), so it stays an experiment.
-  const bool old_tiles = getenv("SSR_TC_DEEP_TILES") == nullptr;
+  // Default: <= 4 planes per tile in a ring of two tiles' planes, L2 term on the small (split-K) levels only.
+  // SSR_TC_DEEP_TILES=1 lets the L2-traffic term choose on EVERY level (up to 5 planes of 48 channels): fewer operand bytes
+  // per output, but measured slower at 80^3 (48 -> 48: 0.318 ms against 0.301; data gradient 0.193 against 0.172) -- 14.00
+  // against 13.92 ms per step (scripts/gpu/r02_s.sh).  SSR_TC_MID_TILES=1 does so on the 40^3-class levels only (27k .. 100k
+  // voxels), where single layers measured 5 - 8 % faster -- and the whole step 0.1 ms SLOWER (13.43 / 13.45 against 13.29 /
+  // 13.37 ms, scripts/gpu/r02_w.sh).  Both stay experiments.
+  const long long nvox_all = (long long)B * D0 * D1 * D2;
+  const bool old_tiles = getenv("SSR_TC_DEEP_TILES") == nullptr &&
+                         !(nvox_all > 27000 && nvox_all <= 100000 && getenv("SSR_TC_MID_TILES"));
   for (int ksp = 1; ksp <= (may_split ? 8 : 1) && ksp <= nchunks_all; ++ksp) {
     for (int nt = 16; nt <= 192 && nt <= G.Npad; nt += 16) {
       if (G.Npad % nt || !fits(nt)) continue;
