@@ -109,10 +109,11 @@ class FrozenUNet3D(UNet3D):
         return self.dx
 
 
-def class_tables(generation_labels, segmentation_label_equivalency):
+def class_tables(generation_labels, segmentation_label_equivalency, gt_by_value=False):
     """metrics_model.py:185-204 -> (cls_of_seg int32[S], gt_value int32[K]): segmentation channel j belongs to class k when
     equivalency[j] == generation_labels[i] for the k-th such i; the ground truth of that class is `labels == i` -- the loop
-    INDEX, as the reference writes it (:188), not the label value."""
+    INDEX, as the reference writes it (:188), not the label value.  gt_by_value: `labels == generation_labels[i]`, the way
+    fine_tuning_with_adversary.py:551 writes the same loop."""
     eq = np.asarray(segmentation_label_equivalency)
     cls = np.full(len(eq), -1, dtype=np.int32)
     gtv = []
@@ -122,7 +123,7 @@ def class_tables(generation_labels, segmentation_label_equivalency):
             if len(idx) > 3:
                 raise Exception("uuummm weird that you're merging so many labels...")
             cls[idx] = len(gtv)
-            gtv.append(i)
+            gtv.append(int(gl) if gt_by_value else i)
     if not gtv:
         raise ValueError('segmentation_label_equivalency matches none of the generation labels')
     return cls, np.asarray(gtv, dtype=np.int32)
@@ -131,7 +132,7 @@ def class_tables(generation_labels, segmentation_label_equivalency):
 class SegRegulariser:
     def __init__(self, dims, batchsize, seg_state_dict, n_seg_labels, generation_labels, segmentation_label_equivalency,
                  rel_weight, loss_cropping=None, m=None, M=None, fs_header=False, nb_features=24, nb_levels=5, conv_size=3,
-                 feat_mult=2, nb_conv_per_level=2, conv_impl='tc3', device='cuda'):
+                 feat_mult=2, nb_conv_per_level=2, conv_impl='tc3', device='cuda', gt_by_value=False):
         if fs_header:
             raise NotImplementedError('fs_header_segnet=True (axis swap + flip around the segmentation network, '
                                       'metrics_model.py:157-162) is not implemented')
@@ -146,7 +147,7 @@ class SegRegulariser:
             if tgt is not None and tuple(np.shape(v)) != tuple(tgt.shape):
                 raise ValueError('segmentation model file: %s has shape %s, the network expects %s' % (k, np.shape(v), tuple(tgt.shape)))
         self.net.load_state_dict(seg_state_dict, strict=False)
-        cls, gtv = class_tables(generation_labels, segmentation_label_equivalency)
+        cls, gtv = class_tables(generation_labels, segmentation_label_equivalency, gt_by_value)
         assert len(cls) == n_seg_labels, 'segmentation_label_equivalency must have one entry per segmentation label'
         dev = self.net.device
         self.S, self.K = int(n_seg_labels), int(len(gtv))

@@ -38,8 +38,11 @@ def _range(name):
 class TrainingEngine:
     def __init__(self, plan, batchsize=1, nb_features=24, nb_levels=5, conv_size=3, feat_mult=2, nb_conv_per_level=2,
                  nb_labels=None, lr=1e-4, lr_decay=0., metric='l1', work_with_residual_channel=None,
-                 loss_cropping=None, conv_impl=None, seed=0, device='cuda', rank=0, world_size=1, seg=None):
-        """seg: optional synthsr_b200.seg_loss.SegRegulariser (segmentation-regularised loss, metrics_model.py:136-215)."""
+                 loss_cropping=None, conv_impl=None, seed=0, device='cuda', rank=0, world_size=1, seg=None, net_cls=None,
+                 net_kwargs=None):
+        """seg: optional synthsr_b200.seg_loss.SegRegulariser (segmentation-regularised loss, metrics_model.py:136-215).
+        net_cls / net_kwargs: a UNet3D subclass (and extra keyword arguments) to train instead, e.g. the adversarial
+        fine-tuner's network (synthsr_b200/adversary.py)."""
         # conv_impl None: SSR_CONV_IMPL or 'tc3' (compensated forward, the parity-gated mode); see synthsr_b200/unet.py
         conv_impl = conv_impl or os.environ.get('SSR_CONV_IMPL', 'tc3')
         self.plan, self.B = plan, int(batchsize)
@@ -48,7 +51,10 @@ class TrainingEngine:
         self.gen = SynthGenerator(plan, batchsize, device)
         nb_labels = plan.n_target_channels if nb_labels is None else nb_labels
         self.seg = seg
-        if seg is None:
+        if net_cls is not None:
+            self.net = net_cls(plan.image_shape, nb_features, nb_levels, conv_size, nb_labels, feat_mult, nb_conv_per_level,
+                               batchsize, device, conv_impl, seed=seed, seg=seg, **(net_kwargs or {}))
+        elif seg is None:
             self.net = UNet3D(plan.image_shape, nb_features, nb_levels, conv_size, nb_labels, feat_mult, nb_conv_per_level,
                               batchsize, device, conv_impl, seed=seed)    # same seed on every rank: identical replicas
         else:
@@ -74,7 +80,7 @@ class TrainingEngine:
             draws = sample_draws(self.rng, self.plan, self.B)
         with _range('generator'):
             image, target = self.gen.run(labels, means, stds, draws, real_image=real_image, seed=self.seed)
-        if self.seg is not None:
+        if hasattr(self.net, 'seg_labels'):
             self.net.seg_labels = self.gen.labels                         # `segmentation_target` of this batch
         return self._train_on(image, target)
 
@@ -143,7 +149,7 @@ class TrainingEngine:
         image, target, k = self._pending
         self._pending = None
         torch.cuda.current_stream().wait_event(self._gen_done[k])
-        if self.seg is not None:
+        if hasattr(self.net, 'seg_labels'):
             self.net.seg_labels = self._gens[k].labels
         return self._train_on(image, target)
 

@@ -88,6 +88,10 @@ class UNet3D:
             conv_impl = 'tc'
         if os.environ.get('SSR_COMP') and conv_impl == 'tc':
             self.comp = [(re.compile(r.rsplit(':', 1)[0]), int(r.rsplit(':', 1)[1])) for r in os.environ['SSR_COMP'].split(',')]
+        # momentum of the moving-statistics update of a training-mode forward; 1.0 = leave them alone (a forward of the network
+        # while it is frozen, e.g. under the discriminator steps of the adversarial fine-tuner: Keras drops the updates of a
+        # non-trainable layer but still normalises with the batch statistics)
+        self.bn_momentum = BN_MOMENTUM
         self._lo = None                 # scratch for the TF32 residual x_lo of the convolution being run (stream ordered)
         self._lo_src = None             # (data_ptr, nvox, channels) of the tensor whose bf16 split _lo currently holds
         self._ksplit_cache = {}
@@ -783,13 +787,25 @@ class UNet3D:
         if training and have_sums:       # self.sums was filled by the epilogue of the convolution that wrote x
             lib.ssr_bn_finalize(self.sums, nvox, C, self.p[bn + '/gamma'], self.p[bn + '/beta'],
                                 self.moving[bn + '/moving_mean'], self.moving[bn + '/moving_variance'], BN_EPS,
-                                BN_MOMENTUM, stats, st)
+                                self.bn_momentum, stats, st)
         elif training:
             lib.ssr_bn_stats(x, nvox, C, self.p[bn + '/gamma'], self.p[bn + '/beta'], self.moving[bn + '/moving_mean'],
-                             self.moving[bn + '/moving_variance'], BN_EPS, BN_MOMENTUM, self.sums, stats, st)
+                             self.moving[bn + '/moving_variance'], BN_EPS, self.bn_momentum, self.sums, stats, st)
         else:
             lib.ssr_bn_stats_inference(C, self.p[bn + '/gamma'], self.p[bn + '/beta'], self.moving[bn + '/moving_mean'],
                                        self.moving[bn + '/moving_variance'], BN_EPS, stats, st)
+
+    def forward_frozen(self, image):
+        """training-mode forward (batch statistics) that leaves the moving statistics untouched -> [B,X,Y,Z,nb_labels]:
+        what Keras computes for this network inside a model that is being fitted while the network is `trainable = False`."""
+        keep, self.bn_momentum = self.bn_momentum, 1.
+        try:
+            self.forward(image, training=True)
+        finally:
+            self.bn_momentum = keep
+        zeros = torch.zeros((self.nvox[0], self.nb_labels), dtype=torch.float32, device=self.device)
+        UNet3D._head(self, zeros, 'l1', None, None, train=False)
+        return self.pred.view(self.B, *self.dims, self.nb_labels)
 
     def predict(self, image):
         """inference-mode forward (moving BN statistics) -> [B,X,Y,Z,nb_labels] tensor."""

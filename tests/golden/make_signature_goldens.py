@@ -9,6 +9,7 @@ TARGETS = {'SynthSR/training.py': ['training'], 'SynthSR/brain_generator.py': ['
            'SynthSR/labels_to_image_model.py': ['labels_to_image_model', 'get_shapes'],
            'SynthSR/model_inputs.py': ['build_model_inputs'], 'SynthSR/metrics_model.py': ['metrics_model'],
            'ext/neuron/models.py': ['unet'],
+           'SynthSR/fine_tuning_with_adversary.py': ['training', 'make_discriminator'],
            'ext/lab2im/utils.py': ['load_volume', 'save_volume', 'get_volume_info', 'get_list_labels', 'reformat_to_list',
                                    'get_padding_margin', 'build_training_generator', 'draw_value_from_distribution']}
 
