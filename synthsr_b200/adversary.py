@@ -42,6 +42,12 @@ def same_padding(n, k, s):
     return total // 2, total - total // 2
 
 
+def fp32_convs():
+    """context for everything that evaluates or differentiates the discriminator on the GPU: the reference convolves in fp32,
+    cuDNN's TF32 default costs 4e-4 on the discriminator loss (the flag is read when a kernel runs, backward passes included)"""
+    return torch.backends.cudnn.flags(enabled=True, allow_tf32=False)
+
+
 class Discriminator:
     """fine_tuning_with_adversary.py:482-508.  Tensors are channels-last [B, X, Y, Z, C] at the interface (the layout of
     the engine and of Keras); kernels are kept in the Keras layout (3, 3, 3, Cin, Cout) / (in, out) as views of one flat
@@ -157,7 +163,7 @@ def discriminator_loss(disc, real, fake, weights, gradient_penalty_weight=10., m
 def wasserstein_generator_term(disc, pred, mask=None):
     """w_loss of build_generator_loss (:541): mean(-D(prediction)) and its gradient w.r.t. the prediction."""
     x = pred.detach().clone().requires_grad_(True)
-    with torch.enable_grad():
+    with torch.enable_grad(), fp32_convs():
         w = (-disc(x, mask)).mean()
         (dx,) = torch.autograd.grad(w, x)
     return w.detach(), dx
@@ -230,9 +236,10 @@ class AdversarialEngine:
         mask = e.net.mask_of(e.gen.labels) if getattr(e.net, 'mask_lut', None) is not None else None
         weights = torch.rand((e.B, 1, 1, 1, 1), generator=self.gen_w).to(fake.device)
         leaves = d.leaves()
-        loss, _ = discriminator_loss(d, real, fake, weights, self.gp_weight, mask, leaves)
         names = list(leaves)
-        grads = torch.autograd.grad(loss, [leaves[k] for k in names])
+        with fp32_convs():
+            loss, _ = discriminator_loss(d, real, fake, weights, self.gp_weight, mask, leaves)
+            grads = torch.autograd.grad(loss, [leaves[k] for k in names])
         d.grads.zero_()
         for k, g in zip(names, grads):
             d.g[k].copy_(g)

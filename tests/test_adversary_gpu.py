@@ -8,6 +8,8 @@ import numpy as np
 import pytest
 import torch
 
+from helpers import gpu_pool_routing
+
 pytestmark = pytest.mark.gpu
 
 PRED_TOL, LOSS_TOL, GRAD_TOL = 1e-3, 1e-3, 1e-2
@@ -17,18 +19,19 @@ def _t(a):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
 
 
-def _make(disc_kw=None, net_kw=None, dims=(32, 32, 32), seed=0):
+def _make(disc_kw=None, net_kw=None, dims=(32, 32, 32), seed=0, conv_impl='tc3', feats=8, levels=3):
     from synthsr_b200.adversary import AdversarialUNet3D, Discriminator
     disc = Discriminator([*dims, 1], n_filters=4, n_levels=2, seed=seed + 1, **(disc_kw or {}))
     rng = np.random.default_rng(seed)
     for k in disc.p:                                      # non-trivial biases
         if k.endswith('bias'):
             disc.p[k].copy_(_t(rng.normal(size=tuple(disc.p[k].shape)) * .1))
-    net = AdversarialUNet3D([*dims, 1], 8, 3, 3, 1, 2, 2, 1, 'cuda', 'tc3', seed=seed, seg=None, disc=disc, **(net_kw or {}))
+    net = AdversarialUNet3D([*dims, 1], feats, levels, 3, 1, 2, 2, 1, 'cuda', conv_impl, seed=seed, seg=None, disc=disc,
+                            **(net_kw or {}))
     return net, disc
 
 
-def _oracle_generator_step(net, disc, image, target, discr_weight, loss_cropping=None, mask=None):
+def _oracle_generator_step(net, disc, image, target, discr_weight, loss_cropping=None, mask=None, routing=None):
     from oracle import adversary as OA
     from oracle import unet as OU
     sd = net.state_dict()
@@ -37,7 +40,7 @@ def _oracle_generator_step(net, disc, image, target, discr_weight, loss_cropping
     leaves = {k: params[k].clone().requires_grad_(True) for k in names}
     p = {k: leaves.get(k, params[k]) for k in params}
     img, tgt = torch.tensor(image, dtype=torch.float64), torch.tensor(target, dtype=torch.float64)
-    pred = OU.forward(p, img, training=True, nb_levels=3)
+    pred = OU.forward(p, img, training=True, nb_levels=net.L, pool_routing=routing)
     dparams = {k: torch.tensor(v, dtype=torch.float64) for k, v in disc.state_dict().items()}
     d_out = OA.discriminator_forward(dparams, pred, None if mask is None else torch.tensor(mask, dtype=torch.float64),
                                      n_levels=2)
@@ -46,11 +49,19 @@ def _oracle_generator_step(net, disc, image, target, discr_weight, loss_cropping
     return pred.detach().numpy(), float(loss), {k: v.numpy() for k, v in grads.items()}
 
 
-@pytest.mark.parametrize('discr_weight,loss_cropping,use_mask', [(.05, None, False), (.3, 16, True)])
-def test_generator_step_matches_float64_oracle(discr_weight, loss_cropping, use_mask):
+@pytest.mark.parametrize('conv_impl,discr_weight,loss_cropping,use_mask',
+                         [('ref', .05, None, False), ('ref', .3, 16, True), ('tc3', .01, None, False), ('tc3', .05, 16, True)])
+def test_generator_step_matches_float64_oracle(conv_impl, discr_weight, loss_cropping, use_mask):
     """loss_and_grad of the fine-tuned U-Net = l1_weight * L1 + discr_weight * mean(-D(pred)): loss and every gradient tensor
-    against the oracle (autograd through the oracle U-Net AND the oracle discriminator).  The large discr_weight makes the
-    adversarial term dominate the gradient, so a wrong extra-gradient path cannot hide behind the L1 term."""
+    against the oracle (autograd through the oracle U-Net AND the oracle discriminator).
+    'ref' (exact-fp32 convolutions, a small 3-level net): every tensor to 1e-4 -- the algebra of the step (loss weights, the
+    discriminator's input gradient, the extra-gradient path through the head) with nothing to hide behind; the large
+    discr_weight makes the adversarial term dominate.  'tc3' (the default mode, reference topology of 24 features / 5
+    levels): north_star's bars -- 1e-3 on the prediction and the loss, 1e-2 on every gradient tensor (measured 1.8e-3 ..
+    2.7e-3; on the small 3-level net the plain-TF32 backward passes the noise-like discriminator gradient on with 1.7e-2,
+    which is why the strict case runs in 'ref' mode: scripts/adv_grad_diag.py)."""
+    strict = conv_impl == 'ref'
+    topo = dict(feats=8, levels=3) if strict else dict(feats=24, levels=5)
     rng = np.random.default_rng(3)
     lut = None
     labels = mask = None
@@ -59,28 +70,42 @@ def test_generator_step_matches_float64_oracle(discr_weight, loss_cropping, use_
         lab_np = rng.integers(0, 5, size=(1, 32, 32, 32)).astype(np.int32)
         labels = torch.from_numpy(lab_np).cuda()
         mask = lut.cpu().numpy()[lab_np][..., None]
-    net, disc = _make(disc_kw=dict(mask_input=use_mask), net_kw=dict(discr_weight=discr_weight, mask_lut=lut))
+    net, disc = _make(disc_kw=dict(mask_input=use_mask), net_kw=dict(discr_weight=discr_weight, mask_lut=lut),
+                      conv_impl=conv_impl, **topo)
     image = rng.uniform(0, 1, size=(1, 32, 32, 32, 1)).astype(np.float32)
     target = rng.uniform(0, 1, size=(1, 32, 32, 32, 1)).astype(np.float32)
     net.seg_labels = labels
     loss = net.loss_and_grad(_t(image), _t(target), 'l1', None, loss_cropping)
     torch.cuda.synchronize()
-    pred_o, loss_o, grads_o = _oracle_generator_step(net, disc, image, target, discr_weight, loss_cropping, mask)
+    # the oracle's MaxPooling3D takes the GPU forward's window winners (tests/test_unet_parity_gpu.py explains why: with 8 / 16
+    # channels a level has 32k / 8k windows, and ONE near-tied window resolved differently moves a gradient tensor by 1e-2)
+    pred_o, loss_o, grads_o = _oracle_generator_step(net, disc, image, target, discr_weight, loss_cropping, mask,
+                                                     gpu_pool_routing(net))
     pred = net.pred.view(1, 32, 32, 32, 1).cpu().numpy().astype(np.float64)
     assert np.linalg.norm(pred - pred_o) <= PRED_TOL * np.linalg.norm(pred_o)
     assert abs(loss.item() - loss_o) <= LOSS_TOL * abs(loss_o), (loss.item(), loss_o)
     gtot = np.sqrt(sum(float((g ** 2).sum()) for g in grads_o.values()))
-    worst = 0.
+    worst, whole = 0., 0.
     for k, g in grads_o.items():
-        e = np.linalg.norm(net.g[k].cpu().numpy().astype(np.float64) - g) / max(np.linalg.norm(g), 1e-2 * gtot)
-        worst = max(worst, e)
-        assert e <= GRAD_TOL, (k, e)
+        diff = net.g[k].cpu().numpy().astype(np.float64) - g
+        e = np.linalg.norm(diff) / max(np.linalg.norm(g), 1e-2 * gtot)
+        worst, whole = max(worst, e), whole + float((diff ** 2).sum())
+        assert e <= (1e-4 if strict else GRAD_TOL), (k, e)
+    whole = np.sqrt(whole) / gtot
+    assert whole <= (1e-4 if strict else GRAD_TOL), whole
     # the image term and the adversarial term the head reported
     image_term, w = net.last_terms
     l1 = np.abs(pred_o - target).mean() if loss_cropping is None else \
         np.abs(pred_o - target)[:, 8:24, 8:24, 8:24].mean()
     assert abs(image_term.item() - (1 - discr_weight) * l1) <= 1e-3 * l1
-    print('generator step: loss %.6f (oracle %.6f), worst gradient tensor %.2e' % (loss.item(), loss_o, worst))
+    line = 'adversarial generator step %s w_d=%g crop=%s mask=%d: loss %.6f (oracle %.6f), whole gradient %.2e, worst tensor %.2e' % (
+        conv_impl, discr_weight, loss_cropping, use_mask, loss.item(), loss_o, whole, worst)
+    print(line)
+    try:
+        os.makedirs(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out'), exist_ok=True)
+        open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out', 'adversary_parity.txt'), 'a').write(line + '\n')
+    except OSError:
+        pass
 
 
 def test_frozen_forward_uses_batch_statistics_and_keeps_the_moving_ones():
@@ -115,8 +140,9 @@ def test_discriminator_step_on_the_device_matches_oracle():
     fake = rng.uniform(0, 1, size=(1, 32, 32, 32, 1)).astype(np.float32)
     w = np.array([[[[[.37]]]]], dtype=np.float32)
     leaves = disc.leaves()
-    loss, parts = PA.discriminator_loss(disc, _t(real), _t(fake), _t(w), 10., None, leaves)
-    grads = torch.autograd.grad(loss, list(leaves.values()))
+    with PA.fp32_convs():
+        loss, parts = PA.discriminator_loss(disc, _t(real), _t(fake), _t(w), 10., None, leaves)
+        grads = torch.autograd.grad(loss, list(leaves.values()))
     t64 = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64)  # noqa: E731
     oleaves = {k: t64(v).requires_grad_(True) for k, v in disc.state_dict().items()}
     loss_o = OA.discriminator_loss(oleaves, t64(real), t64(fake), t64(w), 10., None, n_levels=2)

@@ -27,6 +27,8 @@ import numpy as np
 import pytest
 import torch
 
+from helpers import gpu_pool_routing as _gpu_routing
+
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -374,22 +376,6 @@ def test_producers_emit_the_same_bf16_split_as_the_standalone_pass():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def _gpu_routing(net):
-    """max-pool winners of the GPU forward that has just run, per encoder level, in F.max_pool3d's index convention:
-    BatchNorm of the level's output through the library's own kernel (ssr_bn_apply mode 0), torch's max_pool3d for the
-    indices -- checked bit for bit against the pooled tensor the forward itself produced (BN + pool fused, mode 1)."""
-    from synthsr_b200._lib import lib, stream_ptr
-    routing = []
-    for l in range(net.L - 1):
-        d, c = net.ldims[l], net.feats[l]
-        bn = torch.empty_like(net.h1[l])
-        lib.ssr_bn_apply(net.h1[l], bn, net.stats_enc[l], net.B, *d, c, 0, 0, 0, stream_ptr())
-        pooled, idx = torch.nn.functional.max_pool3d(bn.view(net.B, *d, c).permute(0, 4, 1, 2, 3), 2, return_indices=True)
-        assert torch.equal(pooled.permute(0, 2, 3, 4, 1).reshape(net.inp[l + 1].shape), net.inp[l + 1]), l
-        routing.append(idx.cpu())
-    return routing
-
-
 def _step_vs_routed_oracle(net, image, target, tag, nb_levels=5, **loss_kw):
     """one training step of `net`, then the float64 oracle on the same inputs WITH THE GPU FORWARD'S MAX-POOL WINNERS
     (oracle.unet._maxpool_routed): the only setting in which gradients can be compared tensor by tensor at every size.
