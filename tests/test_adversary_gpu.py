@@ -108,6 +108,58 @@ def test_generator_step_matches_float64_oracle(conv_impl, discr_weight, loss_cro
         pass
 
 
+def test_generator_step_with_discriminator_and_segmentation_regulariser():
+    """all three terms of build_generator_loss (:568-573): (1 - w_d - w_s) * L1 + w_d * mean(-D) + w_s * Dice, the Dice ground
+    truth being `labels == label VALUE` (:551) -- exact-fp32 mode, every gradient tensor against float64 autograd through the
+    oracle U-Net, the oracle discriminator and the oracle segmentation network"""
+    from oracle import adversary as OA
+    from oracle import unet as OU
+    from synthsr_b200.adversary import AdversarialUNet3D, Discriminator
+    from synthsr_b200.seg_loss import SegRegulariser, class_tables
+    from synthsr_b200.unet import UNet3D
+    rng = np.random.default_rng(11)
+    dims, L, F, S, w_d, w_s, crop, m, M = [16, 16, 16], 3, 8, 5, .1, .3, 12, .05, .9
+    gen_labels = np.array([0, 1, 2, 3, 4, 14, 15])
+    equiv = np.array([0, 14, 14, 3, -1])
+    assert class_tables(gen_labels, equiv, gt_by_value=True)[1].tolist() == [0, 3, 14]      # label values, not loop indices
+    tmp = UNet3D(dims + [1], nb_features=F, nb_levels=L, nb_labels=S, batchsize=1, conv_impl='ref', seed=5)
+    seg_sd = tmp.state_dict()
+    for k in seg_sd:
+        if k.endswith('gamma'):
+            seg_sd[k] = rng.uniform(.7, 1.3, size=seg_sd[k].shape).astype(np.float32)
+        elif k.endswith(('beta', 'bias')):
+            seg_sd[k] = (rng.normal(size=seg_sd[k].shape) * .1).astype(np.float32)
+    del tmp
+    seg = SegRegulariser(dims, 1, seg_sd, S, gen_labels, equiv, rel_weight=w_s, loss_cropping=crop, m=m, M=M, nb_features=F,
+                         nb_levels=L, conv_impl='ref', gt_by_value=True)
+    disc = Discriminator([*dims, 1], n_filters=4, n_levels=2, seed=2)
+    net = AdversarialUNet3D(dims + [1], F, L, 3, 1, 2, 2, 1, 'cuda', 'ref', seed=1, seg=seg, disc=disc, discr_weight=w_d)
+    assert abs(net.l1_weight - (1 - w_d - w_s)) < 1e-12
+    image = rng.uniform(0, 1, size=(1, *dims, 1)).astype(np.float32)
+    target = rng.uniform(0, 1, size=(1, *dims, 1)).astype(np.float32)
+    labels = gen_labels[rng.integers(0, len(gen_labels), size=(1, *dims))].astype(np.int32)
+    net.seg_labels = torch.from_numpy(labels).cuda()
+    loss = net.loss_and_grad(_t(image), _t(target), 'l1', None, crop)
+    torch.cuda.synchronize()
+    t64 = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64)  # noqa: E731
+    params = {k: t64(v) for k, v in net.state_dict().items()}
+    names = OU.trainable_names(params)
+    for k in names:
+        params[k].requires_grad_(True)
+    pred = OU.forward(params, t64(image), training=True, nb_levels=L, pool_routing=gpu_pool_routing(net))
+    d_out = OA.discriminator_forward({k: t64(v) for k, v in disc.state_dict().items()}, pred, None, n_levels=2)
+    x = (torch.clamp(pred, m, M) - m) / (M - m)                                     # input_normalized, :386
+    seg_out = torch.softmax(OU.forward({k: t64(v) for k, v in seg_sd.items()}, x, training=True, nb_levels=L), -1)
+    total = OA.generator_loss(t64(target), pred, d_out, w_d, crop, target_seg=torch.from_numpy(labels)[..., None],
+                              seg_out=seg_out, generation_labels=gen_labels, segmentation_equivalency=equiv, dice_weight=w_s)
+    grads = torch.autograd.grad(total, [params[k] for k in names])
+    assert abs(loss.item() - float(total.detach())) <= 2e-4 * abs(float(total.detach())), (loss.item(), float(total.detach()))
+    gtot = np.sqrt(sum(float((g ** 2).sum()) for g in grads))
+    for k, g in zip(names, grads):
+        err = np.linalg.norm(net.g[k].cpu().numpy().astype(np.float64) - g.numpy()) / max(np.linalg.norm(g.numpy()), 1e-2 * gtot)
+        assert err < 5e-4, (k, err)
+
+
 def test_frozen_forward_uses_batch_statistics_and_keeps_the_moving_ones():
     """the U-Net under the discriminator steps (generator.trainable = False inside a fitted Keras model): batch-statistics
     BatchNorm, no moving-average update, no parameter change"""
