@@ -23,6 +23,7 @@ Flatten is channels-last; glorot-uniform kernels and zero biases; a non-trainabl
 normalises with batch statistics and only drops its moving-average updates.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -45,7 +46,11 @@ def same_padding(n, k, s):
 def fp32_convs():
     """context for everything that evaluates or differentiates the discriminator on the GPU: the reference convolves in fp32,
     cuDNN's TF32 default costs 4e-4 on the discriminator loss (the flag is read when a kernel runs, backward passes included)"""
-    return torch.backends.cudnn.flags(enabled=True, allow_tf32=False)
+    # cuDNN times its algorithms for the discriminator's few shapes (still fp32): 1616 -> 700 ms per discriminator step at
+    # 160^3 (scripts/adv_step_time.py); SSR_ADV_CUDNN_BENCHMARK=0 switches that off.  SSR_ADV_TF32=1 additionally lets
+    # cuDNN use TF32 (325 ms; outside the fp32 parity the tests check).
+    return torch.backends.cudnn.flags(enabled=True, allow_tf32=os.environ.get('SSR_ADV_TF32') == '1',
+                                      benchmark=os.environ.get('SSR_ADV_CUDNN_BENCHMARK') != '0')
 
 
 class Discriminator:
