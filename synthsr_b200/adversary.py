@@ -157,6 +157,8 @@ def discriminator_loss(disc, real, fake, weights, gradient_penalty_weight=10., m
     """build_discriminator_loss (:580-596) -> (loss, parts).  real / fake [B, X, Y, Z, C]; weights [B, 1, 1, 1, 1].
     The gradient norm is taken over the SPATIAL axes only (axis = 1 .. n_dims, :585), i.e. per batch element and channel."""
     avg = random_weighted_average(real, fake, weights).detach().requires_grad_(True)
+    # three calls like the reference (:420-426); ONE call on the stacked batch measured 2.5x slower at 160^3 (1758 against 700 ms
+    # per discriminator step: cuDNN's double backward at batch 3)
     d_real, d_fake, d_avg = disc(real, mask, params), disc(fake, mask, params), disc(avg, mask, params)
     grads = torch.autograd.grad(d_avg.sum(), avg, create_graph=True)[0]              # K.gradients(discriminator_av, samples)
     norm = torch.sqrt(torch.sum(grads * grads, dim=tuple(range(1, avg.dim() - 1))))
