@@ -5,10 +5,12 @@ Parameters live in ONE flat float32 buffer (so the data-parallel step is a singl
 buffer and a single fused Adam launch); views into it carry the Keras layer names and Keras layouts
 (kernels (k,k,k,Cin,Cout)), which is what checkpoints store.
 
-conv_impl = 'tc3' : tcgen05 convolutions, forward COMPENSATED to fp32-class accuracy ("3xTF32": x = x_hi + x_lo,
-                    w = w_hi + w_lo, K = [x | x_lo | x] against [w_hi | w_hi | w_lo] in one implicit GEMM) on every layer
-                    but the first convolution of the last decoder level; backward in plain TF32.  The mode that meets the 1e-3 parity bar on the
-                    prediction / loss and 1e-2 on the gradients (tests/test_unet_parity_gpu.py) -- the default.
+conv_impl = 'tc3' : tcgen05 convolutions, forward COMPENSATED to fp32-class accuracy on every layer but the first
+                    convolution of the last decoder level -- both operands split into two pieces, the cross terms as extra
+                    K-chunks of the same implicit GEMM: x1 w1 + x2 w1 + x1 w2 in bf16 ("bf16x3", the default scheme), a TF32
+                    main term + one bf16 correction chain on the 24-channel layers ("hybrid"), or three TF32 chains
+                    ("tf32x3", the first implementation) -- backward in plain TF32.  The mode that meets the 1e-3 parity bar
+                    on the prediction / loss and 1e-2 on the gradients (tests/test_unet_parity_gpu.py) -- the default.
 conv_impl = 'tc'  : plain TF32 everywhere (conv_tc.cu): ~2.9e-4 per convolution, 2-3e-3 on the prediction of a randomly
                     initialised net (scripts/tf32_error_emulation.py) -- throughput mode, outside the parity bar
 conv_impl = 'ref' : exact fp32 CUDA-core convolutions (unet_kernels.cu)             -- cross-check
@@ -289,7 +291,7 @@ class UNet3D:
         e0.record()
         fn()
         e1.record()
-        # 5th entry: MMA chains executed per algorithmic one (compensated forward: 2 in the hybrid scheme, 3 in 3xTF32)
+        # 5th entry: MMA chains executed per algorithmic one (compensated forward: 1.5 bf16x3, 2 hybrid, 3 in 3xTF32)
         mult = 1
         if name is not None and kind == 'fwd_tc' and self._comp_level(name) == 3:
             mult = {'hybrid': 2, 'bf16x3': 2 if (self._k2n_ok(cin, cout) or cin < 48) else 1.5}.get(self.comp_scheme, 3)
