@@ -187,6 +187,11 @@ def training(labels_dir,
     if checkpoint_generator is not None:
         print('loading', checkpoint_generator)
         load_checkpoint(engine, checkpoint_generator)                                # by name, like :327-329
+        # `load_weights` brings weights only: the fine-tuning run starts with a fresh optimizer even when the file is one of
+        # this engine's own checkpoints (which also carry the Adam moments of the run that wrote them)
+        engine.net.adam_m.zero_()
+        engine.net.adam_v.zero_()
+        engine.net.iterations = 0
     adv = AdversarialEngine(engine, discriminator, lr_discriminator=lr_discriminator, lr_decay=lr_decay,
                             gradient_penalty_weight=gradient_penalty_weight, seed=seed)
 
