@@ -268,7 +268,9 @@ def test_fine_tuning_runs_end_to_end(dataset, real_targets, monkeypatch):
                 path_generation_classes=p['classes'], output_channel=None if real_targets else 0, output_shape=32,
                 n_levels=3, unet_feat_count=8, epochs=1, steps_per_epoch=2, first_training_ratio=2, training_ratio=1,
                 loss_cropping=16, relative_weight_discriminator=.05, labels_to_mask=p['mask'] if real_targets else None,
-                randomise_res=False, data_res=np.array([1., 1., 2.]))
+                randomise_res=False, data_res=np.array([1., 1., 2.]),
+                # the second case starts from the U-Net the first one wrote (weights by name, fresh optimizer)
+                checkpoint_generator=os.path.join(str(root / 'model_syn'), 'generator_1.h5') if real_targets else None)
     assert seen['d'] == [(True, False)] * 3 and seen['g'] == [(False, True)] * 2, seen
     for name in ('generator_1.h5', 'discriminator_1.h5'):
         assert os.path.isfile(os.path.join(model_dir, name)), name
