@@ -60,3 +60,25 @@ def test_packed_weight_sizes_of_every_pack_mode():
     dll.ssr_last_error.restype = ctypes.c_char_p
     dll.ssr_conv3d_pack_weights.restype = ctypes.c_int
     assert dll.ssr_conv3d_pack_weights(None, None, 24, 0, 24, 10, None) == -1 and b'pack args' in dll.ssr_last_error()
+
+
+def test_split_k_choice_is_host_arithmetic_and_bounded():
+    """ssr_conv3d_fwd_tc_ksplit (the tile model of conv3d_tc_kernel, no CUDA): split-K only on the small deep levels of the
+    160^3 network (<= 27000 voxels), never more parts than 8 or than K chunks, and off under SSR_NO_SPLIT_K."""
+    import subprocess
+    import sys
+    dll = ctypes.CDLL(_lib.LIB_PATH)
+    f = dll.ssr_conv3d_fwd_tc_ksplit
+    f.restype = ctypes.c_int
+    small = [(192, 384, 10, 5), (384, 384, 10, 5), (384, 384, 10, 0), (384, 192, 10, 0)]
+    for c, co, d, comp in small:
+        k = f(c, 0, co, 1, d, d, d, comp)
+        assert 2 <= k <= 8, (c, co, d, comp, k)                      # 10^3: <= 64 tiles without it
+    for c, co, d, comp in [(96, 96, 40, 5), (48, 48, 80, 5), (24, 48, 80, 4), (24, 24, 160, 0)]:
+        assert f(c, 0, co, 1, d, d, d, comp) == 1, (c, co, d)        # enough tiles; y traffic would dominate
+    assert f(8, 0, 16, 1, 10, 10, 10, 0) == 1                        # one K chunk: nothing to split
+    code = ("import ctypes; from synthsr_b200 import _lib; f = ctypes.CDLL(_lib.LIB_PATH).ssr_conv3d_fwd_tc_ksplit; "
+            "f.restype = ctypes.c_int; print(f(384, 0, 384, 1, 10, 10, 10, 5))")
+    env = dict(os.environ, SSR_NO_SPLIT_K='1')
+    out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(_lib.__file__)))
+    assert out.stdout.strip() == '1', (out.stdout, out.stderr)
